@@ -1,0 +1,186 @@
+/*
+ * se_b200.h -- C ABI of libse_b200.so: the B200 (sm_100a) decode hot path
+ *              STFT -> mask/mapping network -> recombine -> overlap-add iSTFT.
+ *
+ * The reference (cszheng-ioa/Sixty-years-of-frequency-domain-monaural-speech-enhancement)
+ * is pure Python and has NO FFI of its own; the boundary its
+ * decode scripts would bind is therefore defined here, one entry point per step of
+ * the shared decode loop, each citing the reference lines it replaces.  All pointers
+ * are DEVICE pointers owned by the caller unless the name says "host"; nothing in
+ * this library allocates device memory except se_*_plan objects (none yet); every
+ * launch takes the caller's cudaStream_t (passed as void*).  No C++ types and no
+ * exceptions cross this boundary.  Every function returns 0 (SE_OK) or a negative
+ * se_status; se_last_error() gives the message for the calling thread.
+ */
+#ifndef SE_B200_H_
+#define SE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE_B200_ABI_VERSION 1
+
+typedef enum se_status {
+  SE_OK = 0,
+  SE_ERR_SHAPE = -1, /* bad argument / unsupported geometry */
+  SE_ERR_ARCH = -2,  /* current device is not sm_100 */
+  SE_ERR_CUDA = -3   /* CUDA runtime error, see se_last_error() */
+} se_status;
+
+typedef enum se_act {
+  SE_ACT_NONE = 0,
+  SE_ACT_ELU = 1,      /* nn.ELU(alpha=1)              CRN/CRN.py:43 */
+  SE_ACT_SOFTPLUS = 2, /* nn.Softplus(beta=1,thr=20)   CRN/CRN.py:102, LSTM/LSTM.py:22 */
+  SE_ACT_RELU = 3,
+  SE_ACT_SIGMOID = 4,
+  SE_ACT_TANH = 5
+} se_act;
+
+typedef void* se_stream_t; /* cudaStream_t */
+
+int se_abi_version(void);
+const char* se_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, else SE_ERR_ARCH. */
+int se_device_check(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long se_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * a1  RMS normalisation constant.  Replaces `c = np.sqrt(len(x)/np.sum(x**2)); x = x*c`
+ *     (CRN/crn_decode.py:39-40, LSTM/lstm_decode_vb.py:35-36, DCCRN/dccrn_decode.py:31-32,
+ *     FullSubNet/fullsubnet_sa_decode.py:46-47, Uformer/uformer_decode_vb.py:35-36).
+ *     wav [B, N] fp32 (row stride wav_stride floats).  Writes c[b] and inv_c[b] = 1/c[b]
+ *     (sum of squares accumulated in fp64).  The scaled waveform is never materialised:
+ *     se_stft() takes c as `scale`, se_istft() takes inv_c as `out_scale`.
+ *     reciprocal != 0 selects the G2Net convention c = sqrt(sum x^2 / N)
+ *     (G2Net_new/com_decode.py:43-44): then c[b] holds 1/that and inv_c[b] that, so the
+ *     same two downstream arguments apply.
+ * ------------------------------------------------------------------------------------- */
+int se_rms_scale(const float* wav, long long wav_stride, int B, int N, int reciprocal, float* c, float* inv_c,
+                 se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a3+a4  Fused reflect-pad + framing + periodic-Hann + one-sided FFT + feature split.
+ *     Replaces librosa.stft(x, n_fft, hop, window='hanning') / torch.stft(x, n_fft, hop, win,
+ *     hann_window(win)) with center=True (CRN/crn_decode.py:41, DCCRN/dccrn_decode.py:41,
+ *     FullSubNet/fullsubnet_sa_decode.py:53, Uformer/uformer.py:178) AND the feature split
+ *     that follows it: |X|**p (crn_decode.py:44), |X|**p * cos/sin(angle)
+ *     (gcrn_decode.py:45-49, dccrn_decode.py:44-46).
+ *     wav [B,N]; scale [B] or NULL (multiplies the waveform, i.e. the `* c` of a1).
+ *     Supported (n_fft, win, hop): n_fft in {320, 512}, win <= n_fft (window centred,
+ *     zero padded), hop even, hop <= n_fft.  T must equal 1 + N/hop.
+ *     Up to three output planes, any may be NULL, all addressed as
+ *        plane[b*sb + t*st + f*sf]   (strides in floats; F = n_fft/2+1 bins)
+ *        mag = |X|^p_mag ; re,im = X * |X|^(p_ri-1)  (p_ri = 1: the plain spectrum).
+ *     An interleaved complex64 [B,T,F] tensor is (re = base, im = base+1, sb=2TF, st=2F, sf=2).
+ * ------------------------------------------------------------------------------------- */
+int se_stft(const float* wav, long long wav_stride, int B, int N, const float* scale, int n_fft, int win, int hop,
+            int T, float* mag, float* re, float* im, long long sb, long long st, long long sf, float p_mag, float p_ri,
+            se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a7+a8+a9  Fused recombination prologue + irFFT + window + overlap-add + envelope
+ *     normalisation + trim + 1/c.  Replaces the numpy/torch glue and librosa.istft /
+ *     torch.istft of every decode script (CRN/crn_decode.py:51-57, gcrn_decode.py:52-63,
+ *     dccrn_decode.py:49-60, fullsubnet_sa_decode.py:64-78, Uformer/uformer.py:276).
+ *     mode:
+ *       SE_ISTFT_SPEC       Y = (a_re, a_im)                              (already a spectrum)
+ *       SE_ISTFT_RI_DECOMP  Y = A * |A|^(inv_p-1), A=(a_re,a_im)         (backend rule (ii))
+ *       SE_ISTFT_MAG_PHASE  Y = a_re^inv_p * X/|X|, X=(b_re,b_im)        (rule (i); a_im unused)
+ *       SE_ISTFT_CMASK      C = A * (X*|X|^(p_x-1)); Y = C*|C|^(inv_p-1) (rule (iii); A = mask)
+ *     a_* / b_* planes are addressed plane[b*sb + t*st + f*sf] with their own stride sets.
+ *     out[b*out_stride + n], n in [0, L): sample n + n_fft/2 of the overlap-add, divided by
+ *     the window-sum-square envelope where it exceeds FLT_MIN, times out_scale[b] (or 1).
+ *     Samples beyond the overlap-add extent are written as 0 (librosa fix_length).
+ * ------------------------------------------------------------------------------------- */
+typedef enum se_istft_mode {
+  SE_ISTFT_SPEC = 0,
+  SE_ISTFT_RI_DECOMP = 1,
+  SE_ISTFT_MAG_PHASE = 2,
+  SE_ISTFT_CMASK = 3
+} se_istft_mode;
+
+int se_istft(int mode, const float* a_re, const float* a_im, long long a_sb, long long a_st, long long a_sf,
+             const float* b_re, const float* b_im, long long b_sb, long long b_st, long long b_sf, float inv_p,
+             float p_x, int B, int T, int n_fft, int win, int hop, const float* out_scale, float* out,
+             long long out_stride, int L, se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a6 building block: causal Conv2d / ConvTranspose2d / Linear as one implicit GEMM.
+ *     Activations are channels-last [B, T, F, C] fp32.  For an output position (b, t, fo)
+ *     and output channel co:
+ *        out[b, t, dst_f0 + fo*dst_fstep, co] =
+ *           act( bias[co] + sum_{tap < ntaps} sum_{ci < C0+C1}
+ *                  in[b, t + dt[tap], fo*sf + df[tap], ci] * W[(tap*(C0+C1) + ci) * ldw + co] )
+ *     where `in` is the channel concatenation of src0 (C0 channels) and src1 (C1, may be
+ *     0): the decoder's torch.cat((x, skip), dim=1) (CRN/CRN.py:107) without the copy.
+ *     Out-of-range (t+dt < 0, f outside [0,Fin)) taps read zero: the causal top pad of
+ *     CRN/CRN.py:38 and the transposed-convolution borders.  BatchNorm (eval) is folded
+ *     into W / bias by the caller.  Covers nn.Conv2d k(2,3) s(1,2) (CRN.py:40), the two
+ *     output-column parities of nn.ConvTranspose2d k(2,3) s(1,2) (CRN.py:77), nn.Linear and
+ *     the hoisted LSTM input projection (ntaps=1, F=1).
+ *     fill_f >= 0 additionally writes act(fill[co]) into output column fill_f (the left F-pad
+ *     of de4, CRN.py:92-97, which passes through BN+ELU).
+ * ------------------------------------------------------------------------------------- */
+#define SE_MAX_TAPS 8
+typedef struct se_conv_desc {
+  const float* src0;
+  const float* src1;
+  int C0, C1;
+  int B, T, Fin;
+  int Fout;       /* output columns computed by this launch */
+  int ntaps;
+  int dt[SE_MAX_TAPS];
+  int df[SE_MAX_TAPS];
+  int sf;
+  const float* W; /* [ntaps*(C0+C1)][ldw] */
+  int ldw;        /* >= Cout, multiple of 4 */
+  const float* bias; /* [Cout] or NULL */
+  int Cout;
+  int act;        /* se_act */
+  float* dst;     /* [B, T, dstF, Cout] */
+  int dstF, dst_f0, dst_fstep;
+  int fill_f;     /* -1: none */
+  const float* fill; /* [Cout] */
+} se_conv_desc;
+
+int se_conv_gemm(const se_conv_desc* desc, se_stream_t stream);
+
+/* First encoder layer (C_in = 1): Conv2d(1,Cout,k(2,3),s(1,2)) + folded BN + act on a
+ * [B,T,Fin] plane -> channels-last [B,T,Fout,Cout].  CRN/CRN.py:37-43.  W [6][Cout] (tap
+ * major: kt*3+kf), Cout <= 64. */
+int se_conv_in1(const float* src, int B, int T, int Fin, const float* W, const float* bias, int Cout, int act,
+                float* dst, int Fout, se_stream_t stream);
+
+/* Last decoder layer (C_out = 1): ConvTranspose2d(C0+C1,1,k(2,3),s(1,2)) + drop last frame
+ * + folded BN + act on channels-last inputs -> [B,T,2*Fin+1] plane.  CRN/CRN.py:98-102.
+ * W [6][C0+C1] (tap major kt*3+kf). */
+int se_deconv_out1(const float* src0, const float* src1, int C0, int C1, int B, int T, int Fin, const float* W,
+                   float bias, int act, float* dst, se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a6 building block: the LSTM recurrence (nn.LSTM, batch_first, zero initial state, gate
+ *     order i,f,g,o; CRN/CRN.py:20,29; LSTM/LSTM.py:17-18).  The input projection
+ *     x W_ih^T + b_ih + b_hh for all T is computed beforehand by se_conv_gemm into
+ *     xproj [B, T, 4H] whose columns are in "slice order": column  s*4*HU + gate*HU + j
+ *     is gate `gate` of hidden unit u = s*HU + j  (HU = H / nslices).  whh is packed the
+ *     same way: whh[s][k][gate*HU + j] = W_hh[gate*H + s*HU + j][k]  (size nslices*H*4*HU).
+ *     One persistent CTA per slice keeps its W_hh slice resident in shared memory for all
+ *     T steps; steps are separated by a device-wide barrier on `sync` (>= 2 unsigned,
+ *     zeroed by the caller before each call is NOT required: the kernel is given a base
+ *     epoch).  hseq [B, T, H] receives h_t (natural unit order).  work: >= 2*H*Bpad floats,
+ *     Bpad = 8*ceil(B/8), scratch for the transposed state.
+ *     Requires H % nslices == 0, 4*HU == 32 (HU = 8), H % 128 == 0, B <= 64.
+ * ------------------------------------------------------------------------------------- */
+int se_lstm_seq(const float* xproj, const float* whh, int B, int T, int H, float* hseq, long long hseq_sb,
+                long long hseq_st, float* work, unsigned* sync, se_stream_t stream);
+/* Bytes of `work` se_lstm_seq needs. */
+long long se_lstm_seq_work_bytes(int B, int H);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE_B200_H_ */

@@ -1,0 +1,53 @@
+"""Oracle decode loops: restatements of the reference ``enhance()`` bodies, one clip at a time.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Waveform in (float64, as
+``soundfile.read`` returns it) -> enhanced waveform out (float32), no disk I/O.
+Every function returns ``(enhanced, taps)`` where ``taps`` holds the intermediate
+arrays the parity tests bisect on, all on the c-normalised scale except ``wav``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import dsp, nets
+
+
+def _mag_mapping_320(sd, forward, wav, p):
+    """Shared body of ``CRN/crn_decode.py:38-57`` and ``LSTM/lstm_decode_vb.py:35-52``
+    (librosa dialect, magnitude mapping with the noisy phase, backend rule (i))."""
+    n_fft, win, hop = dsp.GEOMETRIES["320"]
+    x, c = dsp.rms_scale(wav)                                   # crn_decode.py:39-40
+    spec = dsp.stft(x, n_fft, win, hop).T                       # :41   [T,161] complex64
+    mag = np.abs(spec) ** p                                     # :44
+    phase = np.angle(spec)
+    feat = torch.from_numpy(mag.astype(np.float32))             # :46 FloatTensor
+    with torch.no_grad():
+        est = forward(sd, feat.unsqueeze(0)).squeeze(0).numpy() # :48
+    est = est ** (1.0 / p)                                      # :51
+    de = est * np.exp(1j * phase)                               # :54
+    y = dsp.istft(de.T, n_fft, win, hop, length=len(x))         # :55-56
+    y = y / c                                                   # :57
+    taps = {"c": c, "mag": mag.astype(np.float32), "spec": spec, "est": est,
+            "y_norm": (y * c).astype(np.float32)}
+    return y.astype(np.float32), taps
+
+
+def enhance_crn(sd, wav, p=1.0):
+    """``CRN/crn_decode.py`` (p = 1.0 as shipped: ``**1.0`` at :44 and ``**1.`` at :51)."""
+    return _mag_mapping_320(sd, nets.crn_forward, wav, p)
+
+
+def enhance_lstm(sd, wav, p=1.0):
+    """``LSTM/lstm_decode_vb.py`` at 16 kHz (the 48k->16k resample at :34 sits before the path)."""
+    return _mag_mapping_320(sd, nets.lstm_net_forward, wav, p)
+
+
+def dsp_identity(wav, geometry="fullsubnet"):
+    """STFT -> identity mask -> iSTFT at a given geometry (the literal 512/256 DSP-only run of
+    SURVEY.md section 8(d)); returns the reconstructed waveform (float32)."""
+    n_fft, win, hop = dsp.GEOMETRIES[geometry]
+    x, c = dsp.rms_scale(wav)
+    spec = dsp.stft(x.astype(np.float32), n_fft, win, hop)
+    y = dsp.istft(spec, n_fft, win, hop, length=len(x))
+    return (y / c).astype(np.float32)

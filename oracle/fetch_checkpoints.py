@@ -1,0 +1,30 @@
+"""Copy the shipped checkpoints the parity tests use from /root/reference into
+checkpoints/_ref/ (git-ignored data, not source; travels to the GPU box with the snapshot).
+Build container only."""
+from __future__ import annotations
+
+import os
+import shutil
+
+from . import ref_shims
+
+WANTED = [("CRN", "wsj0_si84_300h_crn_noncprs_model.pth"), ("LSTM", "vb_lstm_noncprs_model.pth")]
+DEST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "checkpoints", "_ref")
+
+
+def main():
+    os.makedirs(DEST, exist_ok=True)
+    for mdir, name in WANTED:
+        src = ref_shims.checkpoint_path(mdir, name)
+        dst = os.path.join(DEST, f"{mdir}__{name}")
+        if not os.path.exists(dst):
+            shutil.copyfile(src, dst)
+        print(dst, os.path.getsize(dst))
+
+
+def path_for(mdir: str, name: str) -> str:
+    return os.path.join(DEST, f"{mdir}__{name}")
+
+
+if __name__ == "__main__":
+    main()

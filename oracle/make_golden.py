@@ -1,0 +1,78 @@
+"""Generate the committed fixtures under tests/golden/ by running the UNMODIFIED reference
+modules (imported from /root/reference through oracle.ref_shims) -- build container only.
+
+    python -m oracle.make_golden
+
+For every case the reference nn.Module produces the network output; the oracle restatement
+(oracle.nets / oracle.decode) is checked against it on the spot and the max-abs difference is
+stored in the fixture (``ref_vs_oracle``).  Cases:
+  *_synth : weights from oracle.synth.synthetic_state_dict (reproducible anywhere);
+  *_ckpt  : the shipped checkpoint the matching decode script loads (needs the checkpoint copy
+            under checkpoints/_ref/ at test time -- see oracle/fetch_checkpoints.py).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+
+import numpy as np
+import torch
+
+from . import decode, ref_shims, synth, templates
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = [
+    # name, model dir, module, class, checkpoint, enhance fn, template, clip samples, clip ids
+    ("crn_synth", "CRN", "CRN", "crn_net", None, decode.enhance_crn, templates.crn_template, 8000, (0, 1)),
+    ("crn_ckpt", "CRN", "CRN", "crn_net", "wsj0_si84_300h_crn_noncprs_model.pth", decode.enhance_crn,
+     templates.crn_template, 16000, (0, 1)),
+    ("lstm_synth", "LSTM", "LSTM", "lstm_net", None, decode.enhance_lstm, templates.lstm_template, 8000, (2, 3)),
+    ("lstm_ckpt", "LSTM", "LSTM", "lstm_net", "vb_lstm_noncprs_model.pth", decode.enhance_lstm,
+     templates.lstm_template, 16000, (2, 3)),
+]
+
+
+def sd_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for name, mdir, module, cls, ckpt, enh, tmpl, nsamp, clip_ids in CASES:
+        mod = ref_shims.import_reference(mdir, module)
+        net = getattr(mod, cls)().eval()
+        if ckpt is None:
+            sd = synth.synthetic_state_dict(tmpl(), seed=0)
+        else:
+            sd = torch.load(ref_shims.checkpoint_path(mdir, ckpt), map_location="cpu")
+            assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(s) for k, s in tmpl().items()}
+        net.load_state_dict(sd)
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp)}
+        worst = 0.0
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = enh(sd, wav.astype(np.float64))
+            with torch.no_grad():
+                est_ref = net(torch.from_numpy(taps["mag"])[None]).squeeze(0).numpy()
+            worst = max(worst, float(np.abs(est_ref - taps["est"]).max()))
+            rec[f"wav{j}"] = wav
+            rec[f"mag{j}"] = taps["mag"]
+            rec[f"est{j}"] = est_ref.astype(np.float32)          # the REFERENCE module's output
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        rec["ref_vs_oracle"] = np.array(worst)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: ref_vs_oracle max-abs {worst:.3e}, out rms "
+              f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

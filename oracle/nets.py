@@ -1,0 +1,120 @@
+"""Oracle networks: functional torch-CPU restatements of the reference forward() bodies.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Each function takes the
+reference's own state-dict (same keys as the shipped ``BEST_MODEL/*.pth``) and an
+input tensor, and computes what the reference ``nn.Module`` computes in
+``eval()`` mode, with the same ATen CPU operators the reference would dispatch to
+(``conv2d``, ``conv_transpose2d``, ``batch_norm``, ``lstm`` ...), so that it is
+also a fair CPU timing arm.  Pinned against the unmodified reference modules by
+``oracle/make_golden.py`` (max-abs difference recorded in the fixture).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.BatchNorm default, used by every BN in CRN.py / LSTM.py
+
+
+def _bn(x, sd, prefix):
+    """eval-mode BatchNorm{1,2}d: running statistics, affine."""
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
+                        sd[prefix + ".weight"], sd[prefix + ".bias"], False, 0.0, BN_EPS)
+
+
+def lstm(x, sd, prefix, num_layers):
+    """nn.LSTM(batch_first=True), zero initial state, eval.  x [B,T,I] -> [B,T,H]."""
+    flat = []
+    for l in range(num_layers):
+        flat += [sd[f"{prefix}.weight_ih_l{l}"], sd[f"{prefix}.weight_hh_l{l}"],
+                 sd[f"{prefix}.bias_ih_l{l}"], sd[f"{prefix}.bias_hh_l{l}"]]
+    hid = flat[1].shape[1]
+    b = x.shape[0]
+    h0 = x.new_zeros(num_layers, b, hid)
+    c0 = x.new_zeros(num_layers, b, hid)
+    out, _, _ = torch._VF.lstm(x, (h0, c0), flat, True, num_layers, 0.0, False, False, True)
+    return out
+
+
+def lstm_manual(x, sd, prefix, num_layers):
+    """Same as :func:`lstm` but spelled out step by step (gate order i,f,g,o) -- used by the
+    tests to show that the ATen fused op and the textbook recurrence agree."""
+    b, t, _ = x.shape
+    for l in range(num_layers):
+        w_ih, w_hh = sd[f"{prefix}.weight_ih_l{l}"], sd[f"{prefix}.weight_hh_l{l}"]
+        bias = sd[f"{prefix}.bias_ih_l{l}"] + sd[f"{prefix}.bias_hh_l{l}"]
+        hid = w_hh.shape[1]
+        h = x.new_zeros(b, hid)
+        c = x.new_zeros(b, hid)
+        outs = []
+        xp = x @ w_ih.t() + bias
+        for s in range(t):
+            g = xp[:, s] + h @ w_hh.t()
+            i, f, gg, o = g.chunk(4, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        x = torch.stack(outs, dim=1)
+    return x
+
+
+# ----------------------------------------------------------------------------------------
+# CRN  (CRN/CRN.py)
+# ----------------------------------------------------------------------------------------
+def crn_forward(sd, x, taps=None):
+    """crn_net.forward, CRN/CRN.py:23-33.  x [B,T,161] magnitude -> [B,T,161] estimated magnitude.
+
+    Encoder (CRN.py:35-71): 5 x [pad one frame on top, Conv2d k(2,3) s(1,2), BN, ELU].
+    LSTM (CRN.py:20,27-31): [B,T,256*4] (channel-major flatten), 2 layers of 1024.
+    Decoder (CRN.py:73-109): 5 x [cat skip, ConvTranspose2d k(2,3) s(1,2), (de4: left-pad F by 1,
+    CRN.py:92-97), drop last frame, BN, ELU]; de5 ends in BN(1)+Softplus.
+    ``taps`` (optional dict) receives per-layer activations for bisecting.
+    """
+    x = x.unsqueeze(1)
+    b, _, t, _ = x.shape
+    skips = []
+    for i in range(5):
+        x = F.pad(x, (0, 0, 1, 0))
+        x = F.conv2d(x, sd[f"en.en_module.{i}.1.weight"], sd[f"en.en_module.{i}.1.bias"], stride=(1, 2))
+        x = F.elu(_bn(x, sd, f"en.en_module.{i}.2"))
+        skips.append(x)
+        if taps is not None:
+            taps[f"en{i + 1}"] = x
+    x = x.permute(0, 2, 1, 3).contiguous().view(b, t, -1)
+    x = lstm(x, sd, "lstm", 2)
+    if taps is not None:
+        taps["lstm"] = x
+    x = x.view(b, t, 256, 4).permute(0, 2, 1, 3).contiguous()
+    for i in range(5):
+        x = torch.cat((x, skips[-(i + 1)]), dim=1)
+        x = F.conv_transpose2d(x, sd[f"de.de_module.{i}.0.weight"], sd[f"de.de_module.{i}.0.bias"],
+                               stride=(1, 2))
+        if i == 3:
+            x = F.pad(x, (1, 0, 0, 0))
+        x = x[:, :, :-1, :]
+        bn_idx = 3 if i == 3 else 2
+        x = _bn(x, sd, f"de.de_module.{i}.{bn_idx}")
+        x = F.softplus(x) if i == 4 else F.elu(x)
+        if taps is not None:
+            taps[f"de{i + 1}"] = x
+    return x.squeeze(1)
+
+
+# ----------------------------------------------------------------------------------------
+# LSTM  (LSTM/LSTM.py)
+# ----------------------------------------------------------------------------------------
+def lstm_net_forward(sd, x, taps=None):
+    """lstm_net.forward, LSTM/LSTM.py:24-29.  x [B,T,161] -> [B,T,161].
+
+    BatchNorm1d over the 161 bins (LSTM.py:16,25), LSTM 161->1024 (:17), LSTM 1024->1024 x2 (:18),
+    Linear 1024->161 + Softplus (:19-22).
+    """
+    x = _bn(x.permute(0, 2, 1).contiguous(), sd, "bn").permute(0, 2, 1).contiguous()
+    x = lstm(x, sd, "lstm1", 1)
+    if taps is not None:
+        taps["lstm1"] = x
+    x = lstm(x, sd, "lstm2", 2)
+    if taps is not None:
+        taps["lstm2"] = x
+    x = F.softplus(F.linear(x, sd["fc.0.weight"], sd["fc.0.bias"]))
+    return x

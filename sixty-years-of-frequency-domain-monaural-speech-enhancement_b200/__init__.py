@@ -1,0 +1,11 @@
+"""se_b200 -- B200 (sm_100a) decode path for frequency-domain speech enhancement.
+
+Package directory name follows the build contract
+(``sixty-years-of-frequency-domain-monaural-speech-enhancement_b200``); it is importable as
+``se_b200`` through the alias module at the repository root.
+"""
+from . import _lib, ops, packing, decode, shard   # noqa: F401
+from .crn import crn_net                   # noqa: F401
+from .lstm import lstm_net                 # noqa: F401
+
+__all__ = ["crn_net", "lstm_net", "ops", "decode", "packing", "shard"]

@@ -1,0 +1,79 @@
+"""ctypes binding of libse_b200.so (the C ABI declared in include/se_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or the device is
+not sm_100 every op raises.  Build with ``python -m build`` in this directory or
+``__graft_entry__.build()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libse_b200.so")
+SE_MAX_TAPS = 8
+
+ACT = {"none": 0, "elu": 1, "softplus": 2, "relu": 3, "sigmoid": 4, "tanh": 5}
+ISTFT_SPEC, ISTFT_RI_DECOMP, ISTFT_MAG_PHASE, ISTFT_CMASK = 0, 1, 2, 3
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("src0", C.c_void_p), ("src1", C.c_void_p), ("C0", C.c_int), ("C1", C.c_int),
+        ("B", C.c_int), ("T", C.c_int), ("Fin", C.c_int), ("Fout", C.c_int), ("ntaps", C.c_int),
+        ("dt", C.c_int * SE_MAX_TAPS), ("df", C.c_int * SE_MAX_TAPS), ("sf", C.c_int),
+        ("W", C.c_void_p), ("ldw", C.c_int), ("bias", C.c_void_p), ("Cout", C.c_int), ("act", C.c_int),
+        ("dst", C.c_void_p), ("dstF", C.c_int), ("dst_f0", C.c_int), ("dst_fstep", C.c_int),
+        ("fill_f", C.c_int), ("fill", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list EVERY symbol include/se_b200.h declares
+_LL, _I, _F, _P = C.c_longlong, C.c_int, C.c_float, C.c_void_p
+PROTOTYPES = {
+    "se_abi_version": (_I, []),
+    "se_last_error": (C.c_char_p, []),
+    "se_device_check": (_I, []),
+    "se_launch_count": (C.c_ulonglong, []),
+    "se_rms_scale": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P]),
+    "se_stft": (_I, [_P, _LL, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _LL, _LL, _LL, _F, _F, _P]),
+    "se_istft": (_I, [_I, _P, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _I, _I, _I, _I, _I, _P, _P, _LL,
+                      _I, _P]),
+    "se_conv_gemm": (_I, [C.POINTER(ConvDesc), _P]),
+    "se_conv_in1": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
+    "se_deconv_out1": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _P]),
+    "se_lstm_seq": (_I, [_P, _P, _I, _I, _I, _P, _LL, _LL, _P, _P, _P]),
+    "se_lstm_seq_work_bytes": (_LL, [_I, _I]),
+}
+
+_lib = None
+
+
+class SeB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SeB200Error(
+            f"{LIB_PATH} not found: the CUDA library has not been built (run __graft_entry__.build()). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.se_abi_version() != 1:
+        raise SeB200Error("ABI version mismatch between _lib.py and libse_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().se_last_error().decode(errors="replace")
+        raise SeB200Error(f"{what} failed with status {rc}: {msg}")

@@ -1,0 +1,151 @@
+"""Drop-in ``crn_net`` (reference: CRN/CRN.py:16-33) executing on the sm_100a kernels.
+
+Same class name, constructor, ``forward(x)`` contract ([B,T,161] magnitude -> [B,T,161]
+estimated magnitude) and state-dict keys as the reference, so
+``crn_net().load_state_dict(torch.load('BEST_MODEL/wsj0_si84_300h_crn_noncprs_model.pth'))``
+works unchanged (CRN/crn_decode.py:18-22).  Inference only.
+
+Data layout (differs from the reference's NCHW on purpose): activations are channels-last
+[B, T, F, C] so that (a) implicit-GEMM K-slices are contiguous, (b) the decoder's
+``torch.cat((x, skip), 1)`` (CRN.py:107) is two pointers instead of a copy, and (c) the
+encoder output [B,T,4,256] *is* the LSTM input [B,T,1024] -- the (c,f)->(f,c) flatten order
+difference (CRN.py:27-28,31-32) is absorbed into the LSTM weight packing.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops, packing
+from .param_tree import bn_rows, build_param_tree, lstm_rows
+
+_ENC_CH = [1, 16, 32, 64, 128, 256]          # CRN.py:40-62
+_ENC_F = [161, 80, 39, 19, 9, 4]
+_DEC_CH = [(512, 128), (256, 64), (128, 32), (64, 16), (32, 1)]   # CRN.py:77-99
+
+
+def _spec():
+    rows = []
+    for i in range(5):
+        ci, co = _ENC_CH[i], _ENC_CH[i + 1]
+        rows += [(f"en.en_module.{i}.1.weight", (co, ci, 2, 3), "param"),
+                 (f"en.en_module.{i}.1.bias", (co,), "param")]
+        rows += bn_rows(f"en.en_module.{i}.2", co)
+    rows += lstm_rows("lstm", 1024, 1024, 2)
+    for i, (ci, co) in enumerate(_DEC_CH):
+        bn = 3 if i == 3 else 2                   # de4 has the extra pad module (CRN.py:92-97)
+        rows += [(f"de.de_module.{i}.0.weight", (ci, co, 2, 3), "param"),
+                 (f"de.de_module.{i}.0.bias", (co,), "param")]
+        rows += bn_rows(f"de.de_module.{i}.{bn}", co)
+    return rows
+
+
+class crn_net(nn.Module):
+    N_BINS = 161
+
+    def __init__(self):
+        super().__init__()
+        build_param_tree(self, _spec())
+        self._packed = None
+        self._packed_key = None
+
+    # -- weight packing --------------------------------------------------------------------------
+    def _state_key(self):
+        p = next(self.parameters())
+        return (p.device, tuple(int(t._version) for t in self.state_dict().values()))
+
+    def _pack(self):
+        sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+        dev = next(self.parameters()).device
+        P = {}
+        for i in range(5):
+            bn = tuple(sd[f"en.en_module.{i}.2.{n}"] for n in ("weight", "bias", "running_mean", "running_var"))
+            P[f"en{i}"] = packing.pack_conv(sd[f"en.en_module.{i}.1.weight"], sd[f"en.en_module.{i}.1.bias"], bn)
+        # NHWC flatten index q = f*256 + c  <->  reference feature index c*4 + f
+        q = torch.arange(1024, device=dev)
+        nhwc = (q % 256) * 4 + q // 256
+        P["lstm0"] = packing.pack_lstm_layer(sd["lstm.weight_ih_l0"], sd["lstm.weight_hh_l0"], sd["lstm.bias_ih_l0"],
+                                             sd["lstm.bias_hh_l0"], in_perm=nhwc)
+        P["lstm1"] = packing.pack_lstm_layer(sd["lstm.weight_ih_l1"], sd["lstm.weight_hh_l1"], sd["lstm.bias_ih_l1"],
+                                             sd["lstm.bias_hh_l1"], unit_perm=nhwc)
+        for i in range(5):
+            bnm = 3 if i == 3 else 2
+            bn = tuple(sd[f"de.de_module.{i}.{bnm}.{n}"] for n in ("weight", "bias", "running_mean", "running_var"))
+            w, b = sd[f"de.de_module.{i}.0.weight"], sd[f"de.de_module.{i}.0.bias"]
+            if i < 4:
+                P[f"de{i}"] = packing.pack_deconv_parity(w, b, bn)
+            else:
+                s, o = packing.bn_fold(*bn)
+                wf = w * s[None, :, None, None]
+                P["de4_w"] = wf[:, 0].permute(1, 2, 0).reshape(6, w.shape[0]).contiguous()   # [kt*3+kf][ci]
+                P["de4_b"] = float((b * s + o).item())
+        self._packed = P
+
+    def _ensure_packed(self):
+        key = self._state_key()
+        if self._packed is None or key != self._packed_key:
+            self._pack()
+            self._packed_key = key
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    # -- forward ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, taps=None):
+        if not x.is_cuda:
+            raise RuntimeError("crn_net (se_b200) runs on CUDA sm_100a only; there is no CPU path")
+        return self._forward_impl(x, taps)
+
+    def _forward_impl(self, x, taps=None):
+        self._ensure_packed()
+        P = self._packed
+        x = x.contiguous().float()
+        b, t, f = x.shape
+        assert f == self.N_BINS, f"CRN checkpoints are hard-wired to 161 bins, got {f}"
+        dev = x.device
+        enc = []
+        w, bias = P["en0"]
+        h = ops.conv_in1(x, w, bias, 16, "elu", _ENC_F[1])
+        enc.append(h)
+        for i in range(1, 5):
+            w, bias = P[f"en{i}"]
+            co = _ENC_CH[i + 1]
+            out = torch.empty(b, t, _ENC_F[i + 1], co, device=dev, dtype=torch.float32)
+            ops.conv_gemm(h, None, b, t, _ENC_F[i], _ENC_F[i + 1], packing.CONV23_TAPS, 2, w, bias, co, "elu", out,
+                          _ENC_F[i + 1])
+            h = out
+            enc.append(h)
+        if taps is not None:
+            for i, e in enumerate(enc):
+                taps[f"en{i + 1}"] = e
+        # LSTM: two layers, input projection hoisted over all T
+        seq = h.view(b * t, 1024)
+        for l in range(2):
+            wih, bih, whh = P[f"lstm{l}"]
+            xp = ops.linear(seq, wih, bih, 4096)
+            hs = ops.lstm_seq(xp.view(b, t, 4096), whh, 1024)
+            seq = hs.view(b * t, 1024)
+        if taps is not None:
+            taps["lstm_nhwc"] = hs
+        h = hs.view(b, t, 4, 256)
+        # decoder
+        fin = 4
+        for i in range(4):
+            we, wo, bias, fill = P[f"de{i}"]
+            co = _DEC_CH[i][1]
+            skip = enc[4 - i]
+            shift = 1 if i == 3 else 0                      # de4: left pad on F (CRN.py:92-97)
+            fo = 2 * fin + 1 + shift
+            out = torch.empty(b, t, fo, co, device=dev, dtype=torch.float32)
+            ops.conv_gemm(h, skip, b, t, fin, fin + 1, packing.DECONV_EVEN_TAPS, 1, we, bias, co, "elu", out, fo,
+                          dst_f0=shift, dst_fstep=2)
+            ops.conv_gemm(h, skip, b, t, fin, fin, packing.DECONV_ODD_TAPS, 1, wo, bias, co, "elu", out, fo,
+                          dst_f0=shift + 1, dst_fstep=2, fill_f=(0 if shift else -1), fill=(fill if shift else None))
+            h = out
+            fin = fo
+            if taps is not None:
+                taps[f"de{i + 1}"] = h
+        y = ops.deconv_out1(h, enc[0], P["de4_w"], P["de4_b"], "softplus")
+        return y

@@ -1,0 +1,54 @@
+// C-ABI plumbing shared by every entry point: per-thread error string, launch accounting,
+// device check.  No reference counterpart (the reference has no native boundary).
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace se {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
+}  // namespace se
+
+extern "C" int se_abi_version(void) { return SE_B200_ABI_VERSION; }
+
+extern "C" const char* se_last_error(void) { return se::g_err; }
+
+extern "C" unsigned long long se_launch_count(void) { return se::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int se_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    se::set_error("se_device_check: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    se::set_error("se_device_check: device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+    return SE_ERR_ARCH;
+  }
+  return SE_OK;
+}

@@ -1,0 +1,426 @@
+// DSP front/back end of the decode loop on sm_100a:
+//   se_rms_scale  (a1)      c = sqrt(N / sum x^2)
+//   se_stft       (a3+a4)   reflect-pad + framing + Hann + rFFT + |X|^p / RI split
+//   se_istft      (a7..a9)  recombination prologue + irFFT + window + OLA + envelope + 1/c
+// Both transforms are HBM-bound: every audio sample and spectrum bin is touched once
+// (halo frames of neighbouring CTAs hit L2).  See DESIGN.md for the byte accounting.
+#include <float.h>
+
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace se {
+
+constexpr int kFramesPerCta = 32;   // STFT: frames per CTA (8 warps x 4)
+constexpr int kHopBlocksPerCta = 32;  // iSTFT: hop-sized output blocks per CTA
+constexpr int kDspThreads = 256;
+
+// -------------------------------------------------------------------------------------------
+// a1: RMS scale
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) rms_scale_kernel(const float* __restrict__ wav, long long stride, int N,
+                                                       int reciprocal, float* __restrict__ c,
+                                                       float* __restrict__ inv_c) {
+  const float* x = wav + (long long)blockIdx.x * stride;
+  double acc = 0.0;
+  const bool vec = ((((uintptr_t)x) & 15) == 0);
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int n4 = N >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 v = __ldg(x4 + i);
+      acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < N; i += blockDim.x) acc += (double)x[i] * x[i];
+  } else {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) acc += (double)x[i] * x[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double part[16];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i];
+    if (!reciprocal) {
+      const double cc = sqrt((double)N / s);  // crn_decode.py:39: x * c ... y / c
+      c[blockIdx.x] = (float)cc;
+      inv_c[blockIdx.x] = (float)(1.0 / cc);
+    } else {
+      const double cc = sqrt(s / (double)N);  // G2Net_new/com_decode.py:43-44: x / c ... y * c
+      c[blockIdx.x] = (float)(1.0 / cc);
+      inv_c[blockIdx.x] = (float)cc;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// a3+a4: STFT
+// -------------------------------------------------------------------------------------------
+struct StftParams {
+  const float* wav;
+  long long wav_stride;
+  int B, N;
+  const float* scale;
+  int win, hop, T;
+  float *mag, *re, *im;
+  long long sb, st, sf;
+  float p_mag, p_ri;
+};
+
+__device__ __forceinline__ float pow_pos(float m, float p) {
+  // m >= 0.  p = 1, 0.5, 2 are the exponents the decode scripts use.
+  if (p == 1.0f) return m;
+  if (p == 0.5f) return sqrtf(m);
+  if (p == 2.0f) return m * m;
+  return m > 0.0f ? powf(m, p) : 0.0f;
+}
+__device__ __forceinline__ float pow_scale(float m, float e) {
+  // m^e with the convention 0^e = 0 (the reference multiplies a zero magnitude by cos/sin)
+  if (e == 0.0f) return 1.0f;
+  if (m <= 0.0f) return 0.0f;
+  if (e == 1.0f) return m;
+  if (e == -0.5f) return rsqrtf(m);
+  return powf(m, e);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
+  constexpr int NFFT = 64 * R, N2 = 32 * R, F = N2 + 1;
+  constexpr int FT = kFramesPerCta;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* wtab = reinterpret_cast<float*>(smem_raw);                    // [NFFT]
+  float2* spec = reinterpret_cast<float2*>(wtab + NFFT);               // [FT][R][33]
+  float* nyq_s = reinterpret_cast<float*>(spec + FT * R * 33);         // [FT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(nyq_s + FT);             // 8-byte aligned (FT even)
+  float* tile = reinterpret_cast<float*>(bar + 2);                     // 16-byte aligned
+
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * FT;
+  const int nf = min(FT, p.T - t0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = p.wav + (long long)b * p.wav_stride;
+  const int start = t0 * p.hop - NFFT / 2;
+  const int tile_len = (nf - 1) * p.hop + NFFT;
+
+  // --- stage the audio span of this frame tile --------------------------------------------
+  const bool interior = (start >= 0) && (start + tile_len <= p.N) && ((((uintptr_t)(x + start)) & 15) == 0) &&
+                        ((tile_len & 3) == 0);
+  if (interior) {
+    // one bulk (TMA-engine) copy, completion on an mbarrier
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, (unsigned)tile_len * 4u);
+      bulk_g2s(tile, x + start, (unsigned)tile_len * 4u, bar);
+    }
+  } else {
+    // clip edges: reflect padding cannot be described to the copy engine
+    for (int i = tid; i < tile_len; i += kDspThreads) {
+      int j = start + i;
+      if (j < 0) j = -j;
+      if (j >= p.N) j = 2 * (p.N - 1) - j;
+      j = max(0, min(j, p.N - 1));
+      tile[i] = __ldg(x + j);
+    }
+  }
+  // window (periodic Hann of length win, centred in NFFT) times the clip's RMS scale
+  {
+    const float sc = p.scale ? __ldg(p.scale + b) : 1.0f;
+    const int left = (NFFT - p.win) / 2;
+    for (int i = tid; i < NFFT; i += kDspThreads) {
+      const int n = i - left;
+      float w = 0.0f;
+      if (n >= 0 && n < p.win) w = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)p.win);
+      wtab[i] = w * sc;
+    }
+  }
+  WarpFFT<R> fft;
+  fft.init(lane);
+  if (interior) mbar_wait(bar, 0);
+  __syncthreads();
+
+  // --- one warp per frame -------------------------------------------------------------------
+  for (int i = warp; i < nf; i += kDspThreads / 32) {
+    const float2* fr = reinterpret_cast<const float2*>(tile + i * p.hop);
+    const float2* w2 = reinterpret_cast<const float2*>(wtab);
+    float2 z[R];
+#pragma unroll
+    for (int m1 = 0; m1 < R; ++m1) {
+      const int m = 32 * m1 + lane;
+      const float2 v = fr[m], w = w2[m];
+      z[m1] = make_float2(v.x * w.x, v.y * w.y);
+    }
+    const float nyq = fft.forward(z);
+    const int k2 = bitrev5(lane);
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) spec[(i * R + k1) * 33 + k2] = z[k1];
+    if (lane == 0) nyq_s[i] = nyq;
+  }
+  __syncthreads();
+
+  // --- epilogue: feature split + layout-aware store ------------------------------------------
+  const bool time_major = (p.sf <= p.st);
+  const int total = nf * F;
+  for (int idx = tid; idx < total; idx += kDspThreads) {
+    int i, k;
+    if (time_major) {
+      i = idx / F;
+      k = idx - i * F;
+    } else {
+      k = idx / nf;
+      i = idx - k * nf;
+    }
+    float2 X;
+    if (k == N2) {
+      X = make_float2(nyq_s[i], 0.0f);
+    } else {
+      const int k2 = k / R, k1 = k - k2 * R;
+      X = spec[(i * R + k1) * 33 + k2];
+    }
+    const long long off = (long long)b * p.sb + (long long)(t0 + i) * p.st + (long long)k * p.sf;
+    const float m = sqrtf(X.x * X.x + X.y * X.y);
+    if (p.mag) p.mag[off] = pow_pos(m, p.p_mag);
+    if (p.re) {
+      const float s = pow_scale(m, p.p_ri - 1.0f);
+      p.re[off] = X.x * s;
+      p.im[off] = X.y * s;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// a7+a8+a9: iSTFT
+// -------------------------------------------------------------------------------------------
+struct IstftParams {
+  int mode;
+  const float *a_re, *a_im;
+  long long a_sb, a_st, a_sf;
+  const float *b_re, *b_im;
+  long long b_sb, b_st, b_sf;
+  float inv_p, p_x;
+  int B, T, win, hop;
+  const float* out_scale;
+  float* out;
+  long long out_stride;
+  int L;
+  int nf_max;
+};
+
+template <int R>
+__global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
+  constexpr int NFFT = 64 * R, N2 = 32 * R, F = N2 + 1;
+  constexpr int FRS = R * 66;  // floats per frame buffer: spectrum [R][33] float2 aliases NFFT samples
+  constexpr int OB = kHopBlocksPerCta;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* wtab = reinterpret_cast<float*>(smem_raw);  // [NFFT]
+  float* nyq_s = wtab + NFFT;                        // [nf_max]
+  float* buf = nyq_s + ((p.nf_max + 3) & ~3);        // [nf_max][FRS]
+
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * OB * p.hop;  // first output sample of this CTA
+  const int s0 = n0 + NFFT / 2;            // same, in overlap-add coordinates
+  const int s1 = s0 + OB * p.hop;
+  const int q = s0 - NFFT;
+  const int t_lo = q < 0 ? 0 : q / p.hop + 1;
+  const int t_hi = min(p.T - 1, (s1 - 1) / p.hop);
+  const int nf = t_hi - t_lo + 1;
+
+  {
+    const int left = (NFFT - p.win) / 2;
+    for (int i = tid; i < NFFT; i += kDspThreads) {
+      const int n = i - left;
+      float w = 0.0f;
+      if (n >= 0 && n < p.win) w = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)p.win);
+      wtab[i] = w;
+    }
+  }
+
+  // --- stage 1: recombination prologue, spectrum of every contributing frame -> smem --------
+  if (nf > 0) {
+    const bool time_major = (p.a_sf <= p.a_st);
+    const int total = nf * F;
+    for (int idx = tid; idx < total; idx += kDspThreads) {
+      int i, k;
+      if (time_major) {
+        i = idx / F;
+        k = idx - i * F;
+      } else {
+        k = idx / nf;
+        i = idx - k * nf;
+      }
+      const int t = t_lo + i;
+      const long long oa = (long long)b * p.a_sb + (long long)t * p.a_st + (long long)k * p.a_sf;
+      float2 Y;
+      if (p.mode == SE_ISTFT_SPEC) {
+        Y = make_float2(__ldg(p.a_re + oa), __ldg(p.a_im + oa));
+      } else if (p.mode == SE_ISTFT_RI_DECOMP) {
+        const float2 A = make_float2(__ldg(p.a_re + oa), __ldg(p.a_im + oa));
+        const float s = pow_scale(sqrtf(A.x * A.x + A.y * A.y), p.inv_p - 1.0f);
+        Y = make_float2(A.x * s, A.y * s);
+      } else {
+        const long long ob = (long long)b * p.b_sb + (long long)t * p.b_st + (long long)k * p.b_sf;
+        const float2 X = make_float2(__ldg(p.b_re + ob), __ldg(p.b_im + ob));
+        const float m = sqrtf(X.x * X.x + X.y * X.y);
+        if (p.mode == SE_ISTFT_MAG_PHASE) {
+          // est^(1/p) * exp(j angle(X));  angle(0) = 0
+          const float g = pow_pos(__ldg(p.a_re + oa), p.inv_p);
+          const float2 ph = m > 0.0f ? make_float2(X.x / m, X.y / m) : make_float2(1.0f, 0.0f);
+          Y = make_float2(g * ph.x, g * ph.y);
+        } else {  // SE_ISTFT_CMASK
+          const float sx = pow_scale(m, p.p_x - 1.0f);
+          const float2 Xc = make_float2(X.x * sx, X.y * sx);
+          const float2 A = make_float2(__ldg(p.a_re + oa), __ldg(p.a_im + oa));
+          const float2 C = make_float2(A.x * Xc.x - A.y * Xc.y, A.y * Xc.x + A.x * Xc.y);
+          const float s = pow_scale(sqrtf(C.x * C.x + C.y * C.y), p.inv_p - 1.0f);
+          Y = make_float2(C.x * s, C.y * s);
+        }
+      }
+      if (k == N2) {
+        nyq_s[i] = Y.x;
+      } else {
+        const int k2 = k / R, k1 = k - k2 * R;
+        reinterpret_cast<float2*>(buf + (size_t)i * FRS)[k1 * 33 + k2] = Y;
+      }
+    }
+  }
+  WarpFFT<R> fft;
+  fft.init(lane);
+  __syncthreads();
+
+  // --- stage 2: one warp per frame: irFFT, window, time-domain frame back into its buffer ---
+  for (int i = warp; i < nf; i += kDspThreads / 32) {
+    float* fb = buf + (size_t)i * FRS;
+    const float2* sp = reinterpret_cast<const float2*>(fb);
+    float2 x[R];
+    const int k2 = bitrev5(lane);
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) x[k1] = sp[k1 * 33 + k2];
+    const float nyq = nyq_s[i];
+    __syncwarp();
+    fft.inverse(x, nyq);
+    __syncwarp();
+    const float2* w2 = reinterpret_cast<const float2*>(wtab);
+    float2* fo = reinterpret_cast<float2*>(fb);
+#pragma unroll
+    for (int m1 = 0; m1 < R; ++m1) {
+      const int m = 32 * m1 + lane;
+      const float2 w = w2[m];
+      fo[m] = make_float2(x[m1].x * w.x, x[m1].y * w.y);
+    }
+  }
+  __syncthreads();
+
+  // --- stage 3: gather overlap-add, envelope, trim, scale ------------------------------------
+  const float osc = p.out_scale ? __ldg(p.out_scale + b) : 1.0f;
+  float* out = p.out + (long long)b * p.out_stride;
+  const int span = OB * p.hop;
+  for (int j = tid; j < span; j += kDspThreads) {
+    const int n = n0 + j;
+    if (n >= p.L) break;
+    const int s = s0 + j;
+    const int first = s - NFFT + 1;
+    int ta = first <= 0 ? 0 : (first + p.hop - 1) / p.hop;
+    ta = max(ta, t_lo);
+    const int tb = min(t_hi, s / p.hop);
+    float acc = 0.0f, env = 0.0f;
+    for (int t = ta; t <= tb; ++t) {
+      const int off = s - t * p.hop;
+      acc += buf[(size_t)(t - t_lo) * FRS + off];
+      const float w = wtab[off];
+      env += w * w;
+    }
+    if (env > FLT_MIN) acc /= env;
+    out[n] = acc * osc;
+  }
+}
+
+static int dsp_smem_stft(int R, int hop) {
+  const int nfft = 64 * R;
+  const int tile = (kFramesPerCta - 1) * hop + nfft;
+  return nfft * 4 + kFramesPerCta * R * 33 * 8 + kFramesPerCta * 4 + 16 + tile * 4 + 16;
+}
+
+}  // namespace se
+
+using namespace se;
+
+extern "C" int se_rms_scale(const float* wav, long long wav_stride, int B, int N, int reciprocal, float* c,
+                            float* inv_c, se_stream_t stream) {
+  SE_REQUIRE(wav && c && inv_c && B > 0 && N > 0, "se_rms_scale: bad arguments (B=%d N=%d)", B, N);
+  rms_scale_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wav, wav_stride, N, reciprocal, c, inv_c);
+  return check_launch("se_rms_scale");
+}
+
+static int geom_ok(const char* who, int n_fft, int win, int hop) {
+  if (!(n_fft == 320 || n_fft == 512)) {
+    set_error("%s: n_fft=%d unsupported (320 or 512)", who, n_fft);
+    return 0;
+  }
+  if (win < 2 || win > n_fft || ((n_fft - win) & 1) || hop < 2 || (hop & 1) || hop > n_fft) {
+    set_error("%s: unsupported win=%d hop=%d for n_fft=%d", who, win, hop, n_fft);
+    return 0;
+  }
+  return 1;
+}
+
+extern "C" int se_stft(const float* wav, long long wav_stride, int B, int N, const float* scale, int n_fft, int win,
+                       int hop, int T, float* mag, float* re, float* im, long long sb, long long st, long long sf,
+                       float p_mag, float p_ri, se_stream_t stream) {
+  if (!geom_ok("se_stft", n_fft, win, hop)) return SE_ERR_SHAPE;
+  SE_REQUIRE(wav && B > 0 && N >= n_fft, "se_stft: need N >= n_fft (N=%d)", N);
+  SE_REQUIRE(T == 1 + N / hop, "se_stft: T=%d but 1+N/hop=%d", T, 1 + N / hop);
+  SE_REQUIRE((re == nullptr) == (im == nullptr), "se_stft: re and im must both be given or both NULL");
+  SE_REQUIRE(mag || re, "se_stft: no output plane");
+  StftParams p{wav, wav_stride, B, N, scale, win, hop, T, mag, re, im, sb, st, sf, p_mag, p_ri};
+  dim3 grid(ceil_div(T, kFramesPerCta), B);
+  const int R = n_fft / 64;
+  const int smem = dsp_smem_stft(R, hop);
+  cudaError_t e;
+  if (R == 5) {
+    e = cudaFuncSetAttribute(stft_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) stft_kernel<5><<<grid, kDspThreads, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(stft_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) stft_kernel<8><<<grid, kDspThreads, smem, (cudaStream_t)stream>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("se_stft: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return check_launch("se_stft");
+}
+
+extern "C" int se_istft(int mode, const float* a_re, const float* a_im, long long a_sb, long long a_st,
+                        long long a_sf, const float* b_re, const float* b_im, long long b_sb, long long b_st,
+                        long long b_sf, float inv_p, float p_x, int B, int T, int n_fft, int win, int hop,
+                        const float* out_scale, float* out, long long out_stride, int L, se_stream_t stream) {
+  if (!geom_ok("se_istft", n_fft, win, hop)) return SE_ERR_SHAPE;
+  SE_REQUIRE(mode >= SE_ISTFT_SPEC && mode <= SE_ISTFT_CMASK, "se_istft: bad mode %d", mode);
+  SE_REQUIRE(a_re && out && B > 0 && T > 0 && L > 0, "se_istft: bad arguments");
+  SE_REQUIRE(mode == SE_ISTFT_MAG_PHASE || a_im, "se_istft: a_im required for mode %d", mode);
+  SE_REQUIRE(mode < SE_ISTFT_MAG_PHASE || (b_re && b_im), "se_istft: noisy spectrum (b_re,b_im) required");
+  IstftParams p{mode, a_re, a_im, a_sb, a_st, a_sf, b_re, b_im, b_sb, b_st, b_sf, inv_p, p_x, B, T, win, hop,
+                out_scale, out, out_stride, L, 0};
+  p.nf_max = kHopBlocksPerCta + ceil_div(n_fft, hop) + 1;
+  const int R = n_fft / 64;
+  const int smem = n_fft * 4 + ((p.nf_max + 3) & ~3) * 4 + p.nf_max * R * 66 * 4;
+  dim3 grid(ceil_div(L, kHopBlocksPerCta * hop), B);
+  cudaError_t e;
+  if (R == 5) {
+    e = cudaFuncSetAttribute(istft_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) istft_kernel<5><<<grid, kDspThreads, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(istft_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) istft_kernel<8><<<grid, kDspThreads, smem, (cudaStream_t)stream>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("se_istft: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return check_launch("se_istft");
+}

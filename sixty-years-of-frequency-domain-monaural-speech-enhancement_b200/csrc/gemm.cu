@@ -1,0 +1,406 @@
+// Implicit-GEMM causal Conv2d / ConvTranspose2d / Linear on channels-last fp32 activations.
+//
+// FP32 FMA (CUDA-core) path.  SURVEY.md Appendix B: rounding only the weights to TF32
+// already costs 1.1e-4 RMS on CRN -- above the 1e-4 parity gate -- so single-pass
+// tensor-core math is out; this kernel is the exact-fp32 engine (packed FFMA2 on
+// sm_100a), the 3xTF32 tcgen05 engine replaces it for the large contractions.
+//
+//   out[m, n] = act(bias[n] + sum_k A[m, k] * W[k, n]),   m = (b, t, fo),  k = (tap, ci)
+//   A[m, k]   = in[b, t + dt[tap], fo*sf + df[tap], ci]   (zero outside the tensor)
+//
+// CTA tile BM x BN, K step 16, 256 threads, register tile TM x TN, double-buffered
+// shared memory with register-staged global loads.
+#include "common.cuh"
+
+namespace se {
+
+constexpr int BK = 16;
+constexpr int kGemmThreads = 256;
+
+struct ConvParams {
+  se_conv_desc d;
+  int M, K, Ctot;
+};
+
+template <int BM, int BN, int TM, int TN, bool ALIGNED>
+__global__ void __launch_bounds__(kGemmThreads) conv_gemm_kernel(const ConvParams P) {
+  static_assert((BM / TM) * (BN / TN) == kGemmThreads, "tile/thread mismatch");
+  static_assert(TM == 4 || TM == 8, "TM");
+  static_assert(TN == 4 || TN == 8, "TN");
+  constexpr int NA = BM / 64;                    // float4 A loads per thread per K step
+  constexpr int NBQ = (BK * BN / 4);             // float4 B loads per CTA per K step
+  constexpr int NB = (NBQ + kGemmThreads - 1) / kGemmThreads;
+  constexpr int TNX = BN / TN;                   // threads along n
+
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const se_conv_desc& d = P.d;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int tn = tid % TNX, tm = tid / TNX;
+
+  // ---- per-thread A row bookkeeping (rows are fixed over the K loop) ---------------------
+  int r_t[NA], r_fo[NA];
+  long long r_bt[NA];
+  bool r_ok[NA];
+  const int kq = tid & 3;
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const int row = (tid >> 2) + i * 64;
+    const int m = m0 + row;
+    r_ok[i] = m < P.M;
+    const int mm = r_ok[i] ? m : 0;
+    const int fo = mm % d.Fout;
+    const int bt = mm / d.Fout;
+    r_fo[i] = fo;
+    r_t[i] = bt % d.T;
+    r_bt[i] = (long long)(bt - r_t[i]);  // b*T
+  }
+
+  float4 ra[NA];
+  float4 rb[NB];
+
+  auto load_tiles = [&](int k0) {
+    // ---- A ----
+    if (ALIGNED) {
+      const int tap = k0 / P.Ctot;
+      const int c = k0 - tap * P.Ctot;
+      const float* src;
+      int cs, Cs;
+      if (c < d.C0) {
+        src = d.src0; cs = c; Cs = d.C0;
+      } else {
+        src = d.src1; cs = c - d.C0; Cs = d.C1;
+      }
+      const int dt = d.dt[tap], df = d.df[tap];
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        const int ti = r_t[i] + dt;
+        const int fi = r_fo[i] * d.sf + df;
+        const bool ok = r_ok[i] && ti >= 0 && ti < d.T && fi >= 0 && fi < d.Fin;
+        if (ok) {
+          const long long pos = (r_bt[i] + ti) * d.Fin + fi;
+          ra[i] = __ldg(reinterpret_cast<const float4*>(src + pos * Cs + cs + kq * 4));
+        } else {
+          ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = k0 + kq * 4 + e;
+          float x = 0.f;
+          if (k < P.K && r_ok[i]) {
+            const int tap = k / P.Ctot;
+            const int c = k - tap * P.Ctot;
+            const int ti = r_t[i] + d.dt[tap];
+            const int fi = r_fo[i] * d.sf + d.df[tap];
+            if (ti >= 0 && ti < d.T && fi >= 0 && fi < d.Fin) {
+              const long long pos = (r_bt[i] + ti) * d.Fin + fi;
+              x = (c < d.C0) ? __ldg(d.src0 + pos * d.C0 + c) : __ldg(d.src1 + pos * d.C1 + (c - d.C0));
+            }
+          }
+          v[e] = x;
+        }
+        ra[i] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    // ---- B ----
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int f = tid + i * kGemmThreads;
+      rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < NBQ) {
+        const int kr = f / (BN / 4);
+        const int c4 = f - kr * (BN / 4);
+        const int k = k0 + kr;
+        const int n = n0 + c4 * 4;
+        if (k < P.K && n < d.ldw) rb[i] = __ldg(reinterpret_cast<const float4*>(d.W + (long long)k * d.ldw + n));
+      }
+    }
+  };
+
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int row = (tid >> 2) + i * 64;
+      const int slot = (row >> 2) ^ (2 * kq);       // float4-slot swizzle keyed by k>>2
+      const int mcol = slot * 4 + (row & 3);
+      As[buf][kq * 4 + 0][mcol] = ra[i].x;
+      As[buf][kq * 4 + 1][mcol] = ra[i].y;
+      As[buf][kq * 4 + 2][mcol] = ra[i].z;
+      As[buf][kq * 4 + 3][mcol] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int f = tid + i * kGemmThreads;
+      if (f < NBQ) {
+        const int kr = f / (BN / 4);
+        const int c4 = f - kr * (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[buf][kr][c4 * 4]) = rb[i];
+      }
+    }
+  };
+
+  float2 acc[TM][TN / 2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+  const int nk = (P.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const int q2 = 2 * ((k >> 2) & 3);
+      float a[TM];
+      float2 b[TN / 2];
+      if constexpr (TM == 8) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][((2 * tm) ^ q2) * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][((2 * tm + 1) ^ q2) * 4]);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+        a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      } else {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][(tm ^ q2) * 4]);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      }
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * 4]);
+        b[0] = make_float2(b0.x, b0.y);
+        b[1] = make_float2(b0.z, b0.w);
+        if constexpr (TN == 8) {
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][BN / 2 + tn * 4]);
+          b[2] = make_float2(b1.x, b1.y);
+          b[3] = make_float2(b1.z, b1.w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const float2 aa = make_float2(a[i], a[i]);
+#pragma unroll
+        for (int j = 0; j < TN / 2; ++j) acc[i][j] = ffma2(aa, b[j], acc[i][j]);
+      }
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias + activation + channels-last store ---------------------------------------
+  const bool vec_ok = ((d.Cout & 3) == 0) && ((((uintptr_t)d.dst) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + tm * TM + i;
+    if (m >= P.M) continue;
+    const int fo = m % d.Fout;
+    const int bt = m / d.Fout;
+    float* orow = d.dst + ((long long)bt * d.dstF + d.dst_f0 + (long long)fo * d.dst_fstep) * d.Cout;
+#pragma unroll
+    for (int h = 0; h < TN / 4; ++h) {
+      const int n = n0 + (h == 0 ? tn * 4 : BN / 2 + tn * 4);
+      float v[4] = {acc[i][2 * h].x, acc[i][2 * h].y, acc[i][2 * h + 1].x, acc[i][2 * h + 1].y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (n + e < d.Cout) {
+          const float bb = d.bias ? __ldg(d.bias + n + e) : 0.f;
+          v[e] = apply_act(v[e] + bb, d.act);
+        }
+      }
+      if (vec_ok && n + 3 < d.Cout) {
+        *reinterpret_cast<float4*>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < d.Cout) orow[n + e] = v[e];
+      }
+    }
+  }
+}
+
+// left-pad column that still goes through BN + activation (CRN de4)
+__global__ void fill_col_kernel(float* dst, long long rows, int dstF, int Cout, int fill_f, const float* fill,
+                                int act) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Cout) return;
+  const long long r = idx / Cout;
+  const int co = (int)(idx - r * Cout);
+  dst[(r * dstF + fill_f) * Cout + co] = apply_act(__ldg(fill + co), act);
+}
+
+// ---------------------------------------------------------------------------------------------
+// First encoder layer: Conv2d(1 -> Cout, k(2,3), s(1,2)), causal in T.  HBM-bound (writes
+// Fout*Cout floats per frame from Fin inputs).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_in1_kernel(const float* __restrict__ src, int B, int T, int Fin,
+                                                      const float* __restrict__ W, const float* __restrict__ bias,
+                                                      int Cout, int act, float* __restrict__ dst, int Fout) {
+  __shared__ float ws[6 * 64 + 64];
+  for (int i = threadIdx.x; i < 6 * Cout; i += blockDim.x) ws[i] = W[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[6 * 64 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int cq = Cout >> 2;
+  const long long total = (long long)B * T * Fout * cq;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % cq);
+    const long long pos = idx / cq;
+    const int fo = (int)(pos % Fout);
+    const long long bt = pos / Fout;
+    const int t = (int)(bt % T);
+    const float* r1 = src + bt * Fin + 2 * fo;  // frame t   (kt = 1)
+    const float* r0 = r1 - Fin;                  // frame t-1 (kt = 0), zero for t == 0
+    float x[6];
+#pragma unroll
+    for (int kf = 0; kf < 3; ++kf) {
+      x[kf] = t > 0 ? __ldg(r0 + kf) : 0.f;
+      x[3 + kf] = __ldg(r1 + kf);
+    }
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int co = q * 4 + e;
+      float a = ws[6 * 64 + co];
+#pragma unroll
+      for (int tp = 0; tp < 6; ++tp) a = fmaf(x[tp], ws[tp * Cout + co], a);
+      o[e] = apply_act(a, act);
+    }
+    *reinterpret_cast<float4*>(dst + pos * Cout + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Last decoder layer: ConvTranspose2d(C0+C1 -> 1, k(2,3), s(1,2)), last frame dropped.
+// out[b,t,f'] = act(bias + sum_{kt,kf: f'=2f+kf} sum_ci in[b,t-kt,f,ci] * W[kt*3+kf][ci])
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) deconv_out1_kernel(const float* __restrict__ src0,
+                                                         const float* __restrict__ src1, int C0, int C1, int B,
+                                                         int T, int Fin, const float* __restrict__ W, float bias,
+                                                         int act, float* __restrict__ dst) {
+  extern __shared__ float wsm[];  // [6][C0+C1]
+  const int Ct = C0 + C1;
+  for (int i = threadIdx.x; i < 6 * Ct; i += blockDim.x) wsm[i] = W[i];
+  __syncthreads();
+  const int Fo = 2 * Fin + 1;
+  const long long total = (long long)B * T * Fo;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int fp = (int)(idx % Fo);
+    const long long bt = idx / Fo;
+    const int t = (int)(bt % T);
+    float acc = bias;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      if (t - kt < 0) continue;
+      const long long rowpos = (bt - kt) * Fin;
+      for (int kf = (fp & 1); kf < 3; kf += 2) {
+        const int f = (fp - kf) >> 1;
+        if (f < 0 || f >= Fin) continue;
+        const float* w = wsm + (kt * 3 + kf) * Ct;
+        const float4* p0 = reinterpret_cast<const float4*>(src0 + (rowpos + f) * C0);
+        for (int c = 0; c < C0 / 4; ++c) {
+          const float4 v = __ldg(p0 + c);
+          acc = fmaf(v.x, w[4 * c], acc);
+          acc = fmaf(v.y, w[4 * c + 1], acc);
+          acc = fmaf(v.z, w[4 * c + 2], acc);
+          acc = fmaf(v.w, w[4 * c + 3], acc);
+        }
+        if (C1 > 0) {
+          const float4* p1 = reinterpret_cast<const float4*>(src1 + (rowpos + f) * C1);
+          for (int c = 0; c < C1 / 4; ++c) {
+            const float4 v = __ldg(p1 + c);
+            acc = fmaf(v.x, w[C0 + 4 * c], acc);
+            acc = fmaf(v.y, w[C0 + 4 * c + 1], acc);
+            acc = fmaf(v.z, w[C0 + 4 * c + 2], acc);
+            acc = fmaf(v.w, w[C0 + 4 * c + 3], acc);
+          }
+        }
+      }
+    }
+    dst[idx] = apply_act(acc, act);
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+static void launch_conv(const ConvParams& P, bool aligned, cudaStream_t s) {
+  dim3 grid(ceil_div(P.M, BM), ceil_div(P.d.Cout, BN));
+  if (aligned)
+    conv_gemm_kernel<BM, BN, TM, TN, true><<<grid, kGemmThreads, 0, s>>>(P);
+  else
+    conv_gemm_kernel<BM, BN, TM, TN, false><<<grid, kGemmThreads, 0, s>>>(P);
+}
+
+}  // namespace se
+
+using namespace se;
+
+extern "C" int se_conv_gemm(const se_conv_desc* desc, se_stream_t stream) {
+  SE_REQUIRE(desc != nullptr, "se_conv_gemm: null descriptor");
+  ConvParams P;
+  P.d = *desc;
+  const se_conv_desc& d = P.d;
+  SE_REQUIRE(d.src0 && d.W && d.dst, "se_conv_gemm: null pointer");
+  SE_REQUIRE(d.ntaps >= 1 && d.ntaps <= SE_MAX_TAPS, "se_conv_gemm: ntaps=%d", d.ntaps);
+  SE_REQUIRE(d.C0 > 0 && d.C1 >= 0 && (d.C1 == 0 || d.src1), "se_conv_gemm: bad channel split %d+%d", d.C0, d.C1);
+  SE_REQUIRE(d.B > 0 && d.T > 0 && d.Fin > 0 && d.Fout > 0 && d.Cout > 0, "se_conv_gemm: bad shape");
+  SE_REQUIRE(d.ldw >= d.Cout && (d.ldw & 3) == 0 && ((((uintptr_t)d.W) & 15) == 0),
+             "se_conv_gemm: W must be 16-byte aligned with ldw %% 4 == 0 (ldw=%d)", d.ldw);
+  P.Ctot = d.C0 + d.C1;
+  P.K = d.ntaps * P.Ctot;
+  const long long M = (long long)d.B * d.T * d.Fout;
+  SE_REQUIRE(M < (1ll << 31), "se_conv_gemm: M too large");
+  P.M = (int)M;
+  const bool aligned = (d.C0 % BK == 0) && (d.C1 % BK == 0) && ((((uintptr_t)d.src0) & 15) == 0) &&
+                       (d.C1 == 0 || (((uintptr_t)d.src1) & 15) == 0);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d.Cout > 64)
+    launch_conv<128, 128, 8, 8>(P, aligned, s);
+  else if (d.Cout > 32)
+    launch_conv<128, 64, 8, 4>(P, aligned, s);
+  else if (d.Cout > 16)
+    launch_conv<256, 32, 8, 4>(P, aligned, s);
+  else
+    launch_conv<256, 16, 4, 4>(P, aligned, s);
+  int rc = check_launch("se_conv_gemm");
+  if (rc) return rc;
+  if (d.fill_f >= 0) {
+    SE_REQUIRE(d.fill && d.fill_f < d.dstF, "se_conv_gemm: bad fill column");
+    const long long rows = (long long)d.B * d.T;
+    const long long n = rows * d.Cout;
+    fill_col_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, s>>>(d.dst, rows, d.dstF, d.Cout, d.fill_f, d.fill,
+                                                                  d.act);
+    rc = check_launch("se_conv_gemm(fill)");
+  }
+  return rc;
+}
+
+extern "C" int se_conv_in1(const float* src, int B, int T, int Fin, const float* W, const float* bias, int Cout,
+                           int act, float* dst, int Fout, se_stream_t stream) {
+  SE_REQUIRE(src && W && dst, "se_conv_in1: null pointer");
+  SE_REQUIRE(Cout > 0 && Cout <= 64 && (Cout & 3) == 0, "se_conv_in1: Cout=%d (<=64, %%4)", Cout);
+  SE_REQUIRE(Fout == (Fin - 3) / 2 + 1 && Fout > 0, "se_conv_in1: Fout=%d for Fin=%d", Fout, Fin);
+  const long long total = (long long)B * T * Fout * (Cout / 4);
+  const int blocks = (int)min((long long)148 * 16, ceil_div_ll(total, 256));
+  conv_in1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, B, T, Fin, W, bias, Cout, act, dst, Fout);
+  return check_launch("se_conv_in1");
+}
+
+extern "C" int se_deconv_out1(const float* src0, const float* src1, int C0, int C1, int B, int T, int Fin,
+                              const float* W, float bias, int act, float* dst, se_stream_t stream) {
+  SE_REQUIRE(src0 && W && dst, "se_deconv_out1: null pointer");
+  SE_REQUIRE(C0 > 0 && (C0 & 3) == 0 && C1 >= 0 && (C1 & 3) == 0 && (C1 == 0 || src1), "se_deconv_out1: channels");
+  const long long total = (long long)B * T * (2 * Fin + 1);
+  const int blocks = (int)min((long long)148 * 16, ceil_div_ll(total, 256));
+  const int smem = 6 * (C0 + C1) * 4;
+  deconv_out1_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(src0, src1, C0, C1, B, T, Fin, W, bias, act, dst);
+  return check_launch("se_deconv_out1");
+}

@@ -1,0 +1,234 @@
+// Persistent LSTM recurrence (nn.LSTM, gate order i,f,g,o; CRN/CRN.py:20,29, LSTM/LSTM.py:17-18).
+//
+// The input projection for all T steps is hoisted into one GEMM (se_conv_gemm); this kernel
+// runs the T dependent steps  g_t = xproj_t + h_{t-1} W_hh^T  in ONE launch:
+//   * one CTA per slice of 8 hidden units (= 32 gate columns); H = 1024 -> 128 CTAs,
+//     co-resident on the 148 SMs (cooperative launch);
+//   * the CTA's W_hh slice [H][32] fp32 (128 KB at H = 1024) stays in shared memory for
+//     the whole sequence -- HBM sees W_hh once per launch instead of once per step;
+//   * h_{t-1} is exchanged through a k-major scratch hT[2][H][64] in L2 (double buffered
+//     by step parity) and streamed into shared memory with cp.async.cg in 16-row chunks,
+//     one private double-buffered pipeline per warp (8 warps split K);
+//   * per-warp 64x32 partial tiles (8x8 per lane, packed FFMA2) are reduced through
+//     shared memory, gates/cell update fused, h_t written to hseq and hT;
+//   * steps are separated by a device-wide counter barrier (release/acquire).
+// FP32 throughout: see gemm.cu for why tensor cores are not used on this path yet.
+#include "common.cuh"
+
+namespace se {
+
+constexpr int kLstmThreads = 256;
+constexpr int kLstmWarps = 8;
+constexpr int kHU = 8;       // hidden units per CTA
+constexpr int kNC = 4 * kHU; // gate columns per CTA
+constexpr int kBT = 64;      // batch tile (rows of the per-step GEMM)
+constexpr int kKC = 16;      // k rows per pipeline stage per warp
+
+struct LstmParams {
+  const float* xproj;  // [B, T, 4H] slice-ordered columns
+  const float* whh;    // [H/8][H][32]
+  int B, T, H;
+  float* hseq;
+  long long hs_sb, hs_st;
+  float* hT;           // [2][H][64]
+  unsigned* sync;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* Ws = reinterpret_cast<float*>(smem_raw);                 // [H][32]
+  float* stage = Ws + (size_t)p.H * kNC;                           // [8 warps][2][kKC][64]  (aliased by red)
+  float* cst = stage + kLstmWarps * 2 * kKC * kBT;                 // [64][8] cell state
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x;
+  const int G = gridDim.x;
+  const int H = p.H;
+
+  // resident weights
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.whh + (size_t)slice * H * kNC);
+    float4* dst = reinterpret_cast<float4*>(Ws);
+    for (int i = tid; i < H * kNC / 4; i += kLstmThreads) dst[i] = __ldg(src + i);
+  }
+  for (int i = tid; i < kBT * kHU; i += kLstmThreads) cst[i] = 0.f;
+  __syncthreads();
+
+  const int bg = lane >> 2, cg = lane & 3;  // 8 batch groups x 4 column groups per warp
+  const int kper = H / kLstmWarps;          // k range of this warp
+  const int kbase = warp * kper;
+  const int nchunk = kper / kKC;
+  float* my_stage = stage + warp * (2 * kKC * kBT);
+
+  for (int t = 0; t < p.T; ++t) {
+    // -- prefetch this step's input projection (independent of the recurrence) -------------
+    float xg[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int idx = tid + r * kLstmThreads;
+      const int b = idx >> 3, j = idx & 7;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        xg[r][g] = 0.f;
+        if (b < p.B)
+          xg[r][g] = __ldg(p.xproj + ((size_t)b * p.T + t) * (size_t)(4 * H) + slice * kNC + g * kHU + j);
+      }
+    }
+
+    if (t > 0) {
+      // -- wait until every CTA has published h_{t-1} ------------------------------------------
+      if (tid == 0) {
+        const unsigned target = (unsigned)t * (unsigned)G;
+        while (ld_acquire_u32(p.sync) < target) {
+        }
+      }
+      __syncthreads();
+
+      const float* hprev = p.hT + (size_t)((t - 1) & 1) * H * kBT;
+      float2 acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+      auto issue = [&](int c, int buf) {
+        // 16 rows x 256 B = 256 x 16-byte pieces, 8 per lane
+        const float* g = hprev + (size_t)(kbase + c * kKC) * kBT;
+        float* s = my_stage + buf * (kKC * kBT);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int piece = lane + q * 32;
+          cp_async16(s + piece * 4, g + piece * 4);
+        }
+        cp_async_commit();
+      };
+
+      issue(0, 0);
+      for (int c = 0; c < nchunk; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunk) {
+          issue(c + 1, buf ^ 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float* hs = my_stage + buf * (kKC * kBT);
+        const float* wk = Ws + (size_t)(kbase + c * kKC) * kNC;
+#pragma unroll
+        for (int k = 0; k < kKC; ++k) {
+          const float4 h0 = *reinterpret_cast<const float4*>(hs + k * kBT + bg * 8);
+          const float4 h1 = *reinterpret_cast<const float4*>(hs + k * kBT + bg * 8 + 4);
+          const float4 w0 = *reinterpret_cast<const float4*>(wk + k * kNC + cg * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wk + k * kNC + cg * 8 + 4);
+          const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                make_float2(w1.z, w1.w)};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 hh = make_float2(hv[i], hv[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = ffma2(hh, wv[j], acc[i][j]);
+          }
+        }
+        __syncwarp();  // all lanes done with this buffer before it is refilled
+      }
+
+      // -- per-warp partial tile -> shared (aliases this warp's own stage buffers) --------------
+      // red[warp][b][col'], col' = ((col>>3) ^ (b&3))*8 + (col&7)  (bank swizzle for the gate phase)
+      float* red = my_stage;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int b = bg * 8 + i;
+        const int slot = cg ^ (b & 3);
+        float* dst = red + b * kNC + slot * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
+      }
+      __syncthreads();
+    }
+
+    // -- gates, cell and hidden update for this CTA's 8 units -------------------------------------
+    float* hcur = p.hT + (size_t)(t & 1) * H * kBT;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int idx = tid + r * kLstmThreads;
+      const int b = idx >> 3, j = idx & 7;
+      float g4[4] = {xg[r][0], xg[r][1], xg[r][2], xg[r][3]};
+      if (t > 0) {
+#pragma unroll
+        for (int w = 0; w < kLstmWarps; ++w) {
+          const float* red = stage + w * (2 * kKC * kBT) + b * kNC;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) g4[g] += red[((g ^ (b & 3)) << 3) + j];
+        }
+      }
+      const float ig = sigmoid_f(g4[0]);
+      const float fg = sigmoid_f(g4[1]);
+      const float gg = tanhf(g4[2]);
+      const float og = sigmoid_f(g4[3]);
+      const float c = fg * cst[idx] + ig * gg;
+      const float h = og * tanhf(c);
+      cst[idx] = c;
+      const int u = slice * kHU + j;
+      hcur[(size_t)u * kBT + b] = (b < p.B) ? h : 0.f;
+      if (b < p.B) p.hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
+    }
+    __syncthreads();
+    if (tid == 0 && t + 1 < p.T) {
+      __threadfence();
+      red_release_add(p.sync, 1u);
+    }
+  }
+}
+
+}  // namespace se
+
+using namespace se;
+
+extern "C" long long se_lstm_seq_work_bytes(int B, int H) {
+  (void)B;
+  return 2ll * H * kBT * (long long)sizeof(float);
+}
+
+extern "C" int se_lstm_seq(const float* xproj, const float* whh, int B, int T, int H, float* hseq,
+                           long long hseq_sb, long long hseq_st, float* work, unsigned* sync, se_stream_t stream) {
+  SE_REQUIRE(xproj && whh && hseq && work && sync, "se_lstm_seq: null pointer");
+  SE_REQUIRE(B > 0 && B <= kBT, "se_lstm_seq: B=%d (1..%d per call)", B, kBT);
+  SE_REQUIRE(T > 0 && H > 0 && H % (kLstmWarps * kKC) == 0, "se_lstm_seq: H=%d must be a multiple of %d", H,
+             kLstmWarps * kKC);
+  SE_REQUIRE((((uintptr_t)whh) & 15) == 0 && (((uintptr_t)work) & 15) == 0, "se_lstm_seq: unaligned buffers");
+  const int G = H / kHU;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  SE_REQUIRE(G <= sms, "se_lstm_seq: H=%d needs %d co-resident CTAs but the device has %d SMs", H, G, sms);
+  const size_t smem = ((size_t)H * kNC + kLstmWarps * 2 * kKC * kBT + kBT * kHU) * sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("se_lstm_seq: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  e = cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned), s);
+  if (e != cudaSuccess) {
+    set_error("se_lstm_seq: memset: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  LstmParams p{xproj, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync};
+  void* args[] = {(void*)&p};
+  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(G), dim3(kLstmThreads), args, smem, s);
+  if (e != cudaSuccess) {
+    set_error("se_lstm_seq: cooperative launch: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return check_launch("se_lstm_seq");
+}

@@ -1,0 +1,103 @@
+"""The decode loop (wav in -> enhanced wav out) batched on the GPU.
+
+Reference: the ``enhance(args)`` bodies of the ``*_decode*.py`` scripts, e.g.
+CRN/crn_decode.py:17-68, LSTM/lstm_decode_vb.py:17-60.  The reference processes one file at a
+time and does the DSP on the host; here a batch of equal-length clips stays on the device
+from the noisy waveform to the enhanced waveform:
+
+    se_rms_scale -> se_stft (|X|^p and X) -> model.forward -> se_istft (recombine + OLA + 1/c)
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import ISTFT_MAG_PHASE
+
+GEOM_320 = (320, 320, 160)   # LSTM/config.py:4-6, CRN/config.py:4-6
+
+
+@torch.no_grad()
+def enhance_mag_mapping(model, wav, p=1.0, geom=GEOM_320, taps=None):
+    """Magnitude-mapping models (LSTM, CRN): backend rule (i) of SURVEY.md section 8(a).
+    wav [B,N] float32 CUDA -> enhanced [B,N] float32 CUDA.  CRN/crn_decode.py:38-57."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    n_fft, win, hop = geom
+    wav = wav.contiguous().float()
+    b, n = wav.shape
+    t = 1 + n // hop
+    f = n_fft // 2 + 1
+    c, inv_c = ops.rms_scale(wav)
+    mag = torch.empty(b, t, f, device=wav.device, dtype=torch.float32)
+    spec = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)   # noisy spectrum (phase)
+    ops.stft(wav, c, n_fft, win, hop, mag=mag, re=None, im=None, p_mag=p)
+    ops.stft(wav, c, n_fft, win, hop, mag=None, re=spec[..., 0], im=spec[..., 1])
+    est = model(mag)
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_MAG_PHASE, est, None, spec[..., 0], spec[..., 1], n_fft, win, hop, out, n, out_scale=inv_c,
+              inv_p=1.0 / p)
+    if taps is not None:
+        taps.update(c=c, mag=mag, spec=spec, est=est)
+    return out
+
+
+def enhance_crn(model, wav, p=1.0, taps=None):
+    return enhance_mag_mapping(model, wav, p=p, taps=taps)
+
+
+def enhance_lstm(model, wav, p=1.0, taps=None):
+    return enhance_mag_mapping(model, wav, p=p, taps=taps)
+
+
+@torch.no_grad()
+def dsp_roundtrip(wav, geom):
+    """STFT -> identity -> iSTFT (the DSP-only run of SURVEY.md section 8(d))."""
+    from ._lib import ISTFT_SPEC
+    n_fft, win, hop = geom
+    b, n = wav.shape
+    t = 1 + n // hop
+    f = n_fft // 2 + 1
+    c, inv_c = ops.rms_scale(wav)
+    spec = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)
+    ops.stft(wav, c, n_fft, win, hop, mag=None, re=spec[..., 0], im=spec[..., 1])
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_SPEC, spec[..., 0], spec[..., 1], None, None, n_fft, win, hop, out, n, out_scale=inv_c)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# File-level contract of the decode scripts: every file of a directory in, same basename out.
+# soundfile is not available here; 16-bit PCM wav I/O through scipy (sf.write's default
+# subtype for .wav is PCM_16 too, CRN/crn_decode.py:67).
+# ---------------------------------------------------------------------------------------------
+def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, p=1.0, batch=64, device="cuda"):
+    from scipy.io import wavfile
+    os.makedirs(esti_file_path, exist_ok=True)
+    files = sorted(os.listdir(mix_file_path))
+    clips = []
+    for name in files:
+        sr, x = wavfile.read(os.path.join(mix_file_path, name))
+        if sr != fs:
+            raise ValueError(f"{name}: sample rate {sr} != {fs} (resampling sits before this path)")
+        if x.dtype.kind == "i":
+            x = x.astype(np.float64) / float(np.iinfo(x.dtype).max + 1)
+        clips.append((name, x.astype(np.float32)))
+    # equal-length clips batch together (no model in the reference has a padding mask)
+    by_len = {}
+    for name, x in clips:
+        by_len.setdefault(len(x), []).append((name, x))
+    count = 0
+    for n, group in by_len.items():
+        for i in range(0, len(group), batch):
+            chunk = group[i:i + batch]
+            wav = torch.from_numpy(np.stack([x for _, x in chunk])).to(device)
+            out = enhance_mag_mapping(model, wav, p=p).cpu().numpy()
+            for (name, _), y in zip(chunk, out):
+                pcm = np.clip(np.round(y * 32768.0), -32768, 32767).astype(np.int16)
+                wavfile.write(os.path.join(esti_file_path, name), fs, pcm)
+                count += 1
+    return count

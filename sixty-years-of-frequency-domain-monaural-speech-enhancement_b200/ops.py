@@ -1,0 +1,175 @@
+"""Thin torch-tensor wrappers over the C ABI (device pointers + current stream).  Plumbing only:
+no arithmetic happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, ConvDesc, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise _lib.SeB200Error("se_b200 ops need CUDA float32 tensors (no CPU fallback)")
+
+
+_checked = False
+
+
+def device_check():
+    global _checked
+    if not _checked:
+        check(_lib.load().se_device_check(), "se_device_check")
+        _checked = True
+
+
+def launch_count() -> int:
+    return int(_lib.load().se_launch_count())
+
+
+def rms_scale(wav, reciprocal=False):
+    """wav [B,N] -> (c [B], inv_c [B]).  a1."""
+    _need_cuda(wav)
+    device_check()
+    assert wav.dim() == 2 and wav.stride(1) == 1
+    b, n = wav.shape
+    c = torch.empty(b, device=wav.device, dtype=torch.float32)
+    ic = torch.empty_like(c)
+    check(_lib.load().se_rms_scale(_ptr(wav), wav.stride(0), b, n, int(reciprocal), _ptr(c), _ptr(ic), _stream()),
+          "se_rms_scale")
+    return c, ic
+
+
+def _plane_strides(t, layout):
+    """Strides (sb, st, sf) of a [B,T,F] ('btf') or [B,F,T] ('bft') plane view."""
+    if layout == "btf":
+        return t.stride(0), t.stride(1), t.stride(2)
+    return t.stride(0), t.stride(2), t.stride(1)
+
+
+def stft(wav, scale, n_fft, win, hop, mag=None, re=None, im=None, layout="btf", p_mag=1.0, p_ri=1.0):
+    """Fused STFT.  mag / re / im are pre-allocated planes ([B,T,F] for 'btf', [B,F,T] for 'bft');
+    all given planes must share strides."""
+    _need_cuda(wav, scale, mag, re, im)
+    device_check()
+    b, n = wav.shape
+    t = 1 + n // hop
+    ref = mag if mag is not None else re
+    sb, st, sf = _plane_strides(ref, layout)
+    for pl in (mag, re, im):
+        if pl is not None:
+            assert _plane_strides(pl, layout) == (sb, st, sf), "all STFT output planes must share strides"
+    check(_lib.load().se_stft(_ptr(wav), wav.stride(0), b, n, _ptr(scale), n_fft, win, hop, t, _ptr(mag), _ptr(re),
+                              _ptr(im), sb, st, sf, float(p_mag), float(p_ri), _stream()), "se_stft")
+    return t
+
+
+def istft(mode, a_re, a_im, b_re, b_im, n_fft, win, hop, out, length, out_scale=None, inv_p=1.0, p_x=1.0,
+          layout_a="btf", layout_b="btf"):
+    _need_cuda(a_re, a_im, b_re, b_im, out, out_scale)
+    device_check()
+    asb, ast, asf = _plane_strides(a_re, layout_a)
+    if a_im is not None:
+        assert _plane_strides(a_im, layout_a) == (asb, ast, asf)
+    if b_re is not None:
+        bsb, bst, bsf = _plane_strides(b_re, layout_b)
+        assert _plane_strides(b_im, layout_b) == (bsb, bst, bsf)
+    else:
+        bsb = bst = bsf = 0
+    bsz = a_re.shape[0]
+    t = a_re.shape[1] if layout_a == "btf" else a_re.shape[2]
+    check(_lib.load().se_istft(mode, _ptr(a_re), _ptr(a_im), asb, ast, asf, _ptr(b_re), _ptr(b_im), bsb, bst, bsf,
+                               float(inv_p), float(p_x), bsz, t, n_fft, win, hop, _ptr(out_scale), _ptr(out),
+                               out.stride(0), int(length), _stream()), "se_istft")
+    return out
+
+
+def conv_gemm(src0, src1, B, T, Fin, Fout, taps, sf, W, bias, Cout, act, dst, dstF, dst_f0=0, dst_fstep=1,
+              fill_f=-1, fill=None):
+    """Implicit-GEMM conv.  taps: list of (dt, df).  W [ntaps*(C0+C1), ldw] fp32 (K-major)."""
+    _need_cuda(src0, src1, W, bias, dst, fill)
+    device_check()
+    d = ConvDesc()
+    d.src0, d.src1 = src0.data_ptr(), (src1.data_ptr() if src1 is not None else 0)
+    c0 = src0.shape[-1]
+    c1 = src1.shape[-1] if src1 is not None else 0
+    d.C0, d.C1 = c0, c1
+    d.B, d.T, d.Fin, d.Fout = B, T, Fin, Fout
+    d.ntaps = len(taps)
+    for i, (dt, df) in enumerate(taps):
+        d.dt[i], d.df[i] = dt, df
+    d.sf = sf
+    assert W.is_contiguous() and W.shape[0] == len(taps) * (c0 + c1), (W.shape, len(taps), c0, c1)
+    d.W, d.ldw = W.data_ptr(), W.shape[1]
+    d.bias = bias.data_ptr() if bias is not None else 0
+    d.Cout, d.act = Cout, ACT[act]
+    d.dst, d.dstF, d.dst_f0, d.dst_fstep = dst.data_ptr(), dstF, dst_f0, dst_fstep
+    d.fill_f = fill_f
+    d.fill = fill.data_ptr() if fill is not None else 0
+    check(_lib.load().se_conv_gemm(C.byref(d), _stream()), "se_conv_gemm")
+    return dst
+
+
+def linear(x2d, W, bias, n_out, act="none", out=None):
+    """x2d [M,K] @ W [K, ldw] (+bias, act) -> [M, n_out] through the same implicit-GEMM kernel."""
+    m, k = x2d.shape
+    assert x2d.is_contiguous()
+    if out is None:
+        out = torch.empty(m, n_out, device=x2d.device, dtype=torch.float32)
+    return conv_gemm(x2d, None, m, 1, 1, 1, [(0, 0)], 1, W, bias, n_out, act, out, 1)
+
+
+def conv_in1(src, W, bias, cout, act, fout):
+    _need_cuda(src, W, bias)
+    device_check()
+    b, t, fin = src.shape
+    assert src.is_contiguous()
+    dst = torch.empty(b, t, fout, cout, device=src.device, dtype=torch.float32)
+    check(_lib.load().se_conv_in1(_ptr(src), b, t, fin, _ptr(W), _ptr(bias), cout, ACT[act], _ptr(dst), fout,
+                                  _stream()), "se_conv_in1")
+    return dst
+
+
+def deconv_out1(src0, src1, W, bias: float, act):
+    _need_cuda(src0, src1, W)
+    device_check()
+    b, t, fin, c0 = src0.shape
+    c1 = src1.shape[-1] if src1 is not None else 0
+    dst = torch.empty(b, t, 2 * fin + 1, device=src0.device, dtype=torch.float32)
+    check(_lib.load().se_deconv_out1(_ptr(src0), _ptr(src1), c0, c1, b, t, fin, _ptr(W), float(bias), ACT[act],
+                                     _ptr(dst), _stream()), "se_deconv_out1")
+    return dst
+
+
+_LSTM_MAX_B = 64
+
+
+def lstm_seq(xproj, whh, hidden, out=None):
+    """xproj [B,T,4H] (slice-ordered, bias included), whh packed [H/8, H, 32] -> hseq [B,T,H]."""
+    _need_cuda(xproj, whh)
+    device_check()
+    b, t, g4 = xproj.shape
+    assert g4 == 4 * hidden and xproj.is_contiguous()
+    if out is None:
+        out = torch.empty(b, t, hidden, device=xproj.device, dtype=torch.float32)
+    lib = _lib.load()
+    work = torch.empty(lib.se_lstm_seq_work_bytes(min(b, _LSTM_MAX_B), hidden) // 4, device=xproj.device,
+                       dtype=torch.float32)
+    sync = torch.zeros(2, device=xproj.device, dtype=torch.int32)
+    for b0 in range(0, b, _LSTM_MAX_B):
+        nb = min(_LSTM_MAX_B, b - b0)
+        xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
+        check(lib.se_lstm_seq(_ptr(xs), _ptr(whh), nb, t, hidden, _ptr(os_), os_.stride(0), os_.stride(1),
+                              _ptr(work), _ptr(sync), _stream()), "se_lstm_seq")
+    return out

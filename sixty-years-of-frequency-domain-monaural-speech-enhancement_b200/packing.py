@@ -1,0 +1,99 @@
+"""One-time weight packing: reference state-dict tensors -> the layouts the kernels read.
+
+All of this runs once per ``load_state_dict`` on the parameters' device with torch ops (layout
+plumbing; no per-inference arithmetic): eval-mode BatchNorm folded into the adjacent
+convolution, convolution weights to K-major [taps*Cin, Cout], LSTM gate rows to slice order.
+"""
+from __future__ import annotations
+
+import torch
+
+BN_EPS = 1e-5
+HU = 8  # hidden units per LSTM CTA slice (csrc/lstm.cu kHU)
+
+
+def pad_cols(w, mult=4):
+    """[K, N] -> [K, ceil(N/mult)*mult] zero padded, contiguous (16-byte aligned rows)."""
+    k, n = w.shape
+    npad = (n + mult - 1) // mult * mult
+    if npad == n:
+        return w.contiguous()
+    out = w.new_zeros(k, npad)
+    out[:, :n] = w
+    return out
+
+
+def bn_fold(gamma, beta, mean, var, eps=BN_EPS):
+    """eval BatchNorm as y = x*s + o."""
+    s = gamma / torch.sqrt(var + eps)
+    return s, beta - mean * s
+
+
+def pack_conv(w, b, bn):
+    """nn.Conv2d weight [Co,Ci,kt,kf] (+bias) followed by eval BN -> (W [kt*kf*Ci, Co], bias [Co]).
+    Tap order kt-major then kf (matches the tap tables in the model files)."""
+    s, o = bn_fold(*bn)
+    wf = w * s[:, None, None, None]
+    co, ci, kt, kf = w.shape
+    wk = wf.permute(2, 3, 1, 0).reshape(kt * kf * ci, co)
+    bias = (b if b is not None else 0.0) * s + o
+    return pad_cols(wk), bias.contiguous()
+
+
+def pack_deconv_parity(w, b, bn):
+    """nn.ConvTranspose2d weight [Ci,Co,2,3], stride (1,2), followed by eval BN.
+    Returns (W_even [4*Ci, Co], W_odd [2*Ci, Co], bias [Co], fill [Co]) where
+      even output columns f'=2m   use taps (kt,kf) in (0,0),(0,2),(1,0),(1,2)
+      odd  output columns f'=2m+1 use taps (0,1),(1,1)
+    and fill = BN(0) (a zero-padded column that still passes through BN)."""
+    if bn is not None:
+        s, o = bn_fold(*bn)
+    else:
+        s, o = torch.ones_like(b), torch.zeros_like(b)
+    wf = w * s[None, :, None, None]
+    ci, co = w.shape[0], w.shape[1]
+    even = torch.stack([wf[:, :, 0, 0], wf[:, :, 0, 2], wf[:, :, 1, 0], wf[:, :, 1, 2]], dim=0)  # [4,Ci,Co]
+    odd = torch.stack([wf[:, :, 0, 1], wf[:, :, 1, 1]], dim=0)
+    bias = b * s + o
+    return (pad_cols(even.reshape(4 * ci, co)), pad_cols(odd.reshape(2 * ci, co)), bias.contiguous(),
+            o.contiguous())
+
+
+DECONV_EVEN_TAPS = [(0, 0), (0, -1), (-1, 0), (-1, -1)]   # (dt, df) for (kt,kf) = (0,0),(0,2),(1,0),(1,2)
+DECONV_ODD_TAPS = [(0, 0), (-1, 0)]                        # (kt,kf) = (0,1),(1,1)
+CONV23_TAPS = [(kt - 1, kf) for kt in range(2) for kf in range(3)]  # causal k(2,3): in[t-1+kt, 2f+kf]
+
+
+def slice_rows(hidden, unit_perm=None):
+    """Row permutation taking torch's gate-major [i|f|g|o] x H rows to slice order:
+    row s*32 + g*8 + j  <-  g*H + unit(s*8+j)."""
+    dev = unit_perm.device if unit_perm is not None else None
+    units = torch.arange(hidden, device=dev) if unit_perm is None else unit_perm
+    s = hidden // HU
+    u = units.view(s, 1, HU)                               # [S,1,8]
+    g = torch.arange(4, device=units.device).view(1, 4, 1) * hidden
+    return (g + u).reshape(-1)                             # [S*4*8]
+
+
+def pack_lstm_layer(w_ih, w_hh, b_ih, b_hh, in_perm=None, unit_perm=None, in_scale=None, in_shift=None):
+    """Returns (Wih [I, 4H] K-major slice-ordered cols, bias [4H], Whh [H/8, H, 32]).
+
+    in_perm:  new input index -> reference input index (when the producer's layout differs)
+    unit_perm: new hidden-unit index -> reference unit index (to emit h in a consumer's layout)
+    in_scale/in_shift: an affine on the input (eval BatchNorm1d) folded into Wih / bias.
+    """
+    hidden = w_hh.shape[1]
+    rows = slice_rows(hidden, unit_perm).to(w_ih.device)
+    wi = w_ih[rows]
+    bias = (b_ih + b_hh)[rows]
+    if in_scale is not None:
+        bias = bias + wi @ in_shift
+        wi = wi * in_scale[None, :]
+    if in_perm is not None:
+        wi = wi[:, in_perm]
+    wh = w_hh[rows]
+    if unit_perm is not None:
+        wh = wh[:, unit_perm]
+    s = hidden // HU
+    whp = wh.reshape(s, 4 * HU, hidden).permute(0, 2, 1).contiguous()
+    return pad_cols(wi.t().contiguous()), bias.contiguous(), whp

@@ -1,0 +1,89 @@
+"""Pure-torch mirror of the C-ABI *semantics* (include/se_b200.h), used ONLY by the CPU tests to
+check the host-side logic (weight packing, tap tables, layouts, orchestration) without a GPU.
+It is not a fallback: product code never imports it; tests monkeypatch ``ops`` with it and call
+``model._forward_impl`` directly."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def _act(x, act):
+    return {"none": lambda v: v, "elu": F.elu, "softplus": F.softplus, "relu": F.relu,
+            "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](x)
+
+
+def conv_gemm(src0, src1, B, T, Fin, Fout, taps, sf, W, bias, Cout, act, dst, dstF, dst_f0=0, dst_fstep=1,
+              fill_f=-1, fill=None):
+    s0 = src0.reshape(B, T, Fin, -1)
+    x = s0 if src1 is None else torch.cat([s0, src1.reshape(B, T, Fin, -1)], dim=-1)
+    ct = x.shape[-1]
+    acc = torch.zeros(B, T, Fout, W.shape[1], dtype=x.dtype)
+    fo = torch.arange(Fout)
+    for i, (dt, df) in enumerate(taps):
+        fi = fo * sf + df
+        okf = (fi >= 0) & (fi < Fin)
+        g = torch.zeros(B, T, Fout, ct, dtype=x.dtype)
+        tsrc = torch.arange(T) + dt
+        okt = (tsrc >= 0) & (tsrc < T)
+        sel = x[:, tsrc.clamp(0, T - 1)][:, :, fi.clamp(0, Fin - 1)]
+        sel = sel * okt[None, :, None, None] * okf[None, None, :, None]
+        acc += sel @ W[i * ct:(i + 1) * ct]
+    out = acc[..., :Cout]
+    if bias is not None:
+        out = out + bias
+    out = _act(out, act)
+    d = dst.view(B, T, dstF, Cout)
+    d[:, :, dst_f0:dst_f0 + (Fout - 1) * dst_fstep + 1:dst_fstep] = out
+    if fill_f >= 0:
+        d[:, :, fill_f] = _act(fill, act)
+    return dst
+
+
+def linear(x2d, W, bias, n_out, act="none", out=None):
+    y = x2d @ W[:, :n_out]
+    if bias is not None:
+        y = y + bias
+    return _act(y, act)
+
+
+def conv_in1(src, W, bias, cout, act, fout):
+    b, t, fin = src.shape
+    dst = torch.empty(b, t, fout, cout)
+    taps = [(kt - 1, kf) for kt in range(2) for kf in range(3)]
+    return conv_gemm(src.unsqueeze(-1), None, b, t, fin, fout, taps, 2, W, bias, cout, act, dst, fout)
+
+
+def deconv_out1(src0, src1, W, bias, act):
+    b, t, fin, c0 = src0.shape
+    x = src0 if src1 is None else torch.cat([src0, src1], dim=-1)
+    ct = x.shape[-1]
+    out = torch.full((b, t, 2 * fin + 1), float(bias))
+    for kt in range(2):
+        xs = torch.zeros_like(x)
+        xs[:, kt:] = x[:, :t - kt] if kt else x
+        for kf in range(3):
+            contrib = xs @ W[kt * 3 + kf]            # [b,t,fin]
+            out[:, :, kf:kf + 2 * fin:2] += contrib
+    return _act(out, act)
+
+
+def lstm_seq(xproj, whh, hidden, out=None):
+    b, t, _ = xproj.shape
+    s = hidden // 8
+    h = torch.zeros(b, hidden)
+    c = torch.zeros(b, hidden)
+    outs = []
+    # whh [S, H, 32]: gates for slice s = h @ whh[s]  -> [b, 32] = (gate, j)
+    for step in range(t):
+        g = xproj[:, step].view(b, s, 4, 8) + torch.einsum("bk,skn->bsn", h, whh).view(b, s, 4, 8)
+        i, f, gg, o = g[:, :, 0], g[:, :, 1], g[:, :, 2], g[:, :, 3]
+        c = (torch.sigmoid(f) * c.view(b, s, 8) + torch.sigmoid(i) * torch.tanh(gg)).reshape(b, hidden)
+        h = (torch.sigmoid(o).reshape(b, hidden) * torch.tanh(c))
+        outs.append(h)
+    return torch.stack(outs, dim=1)
+
+
+def install(ops_module, monkeypatch):
+    for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq"):
+        monkeypatch.setattr(ops_module, name, globals()[name])

@@ -1,0 +1,118 @@
+"""GPU parity of the network building blocks (implicit-GEMM conv, LSTM recurrence) through the
+C ABI against the torch mirror of their declared semantics (tests/emu_ops.py, CPU fp32/fp64)."""
+import numpy as np
+import pytest
+import torch
+
+import emu_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+CONV_CASES = [
+    # B, T, Fin, C0, C1, Cout, kind
+    (2, 13, 80, 16, 0, 32, "conv"),
+    (2, 13, 39, 32, 0, 64, "conv"),
+    (1, 9, 19, 64, 0, 128, "conv"),
+    (3, 7, 9, 128, 0, 256, "conv"),
+    (2, 11, 4, 256, 256, 128, "deconv"),
+    (2, 11, 9, 128, 128, 64, "deconv"),
+    (1, 5, 19, 64, 64, 32, "deconv"),
+    (2, 6, 39, 32, 32, 16, "deconv_shift"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_gemm_matches_semantics(case):
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    ops = se_b200.ops
+    b, t, fin, c0, c1, co, kind = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x0 = torch.randn(b, t, fin, c0, generator=g)
+    x1 = torch.randn(b, t, fin, c1, generator=g) if c1 else None
+    ct = c0 + c1
+    bias = torch.randn(co, generator=g)
+    fill = torch.randn(co, generator=g)
+    if kind == "conv":
+        fout = (fin - 3) // 2 + 1
+        runs = [(packing.CONV23_TAPS, 2, fout, 0, 1, -1)]
+        dstF = fout
+    else:
+        shift = 1 if kind == "deconv_shift" else 0
+        dstF = 2 * fin + 1 + shift
+        runs = [(packing.DECONV_EVEN_TAPS, 1, fin + 1, shift, 2, -1),
+                (packing.DECONV_ODD_TAPS, 1, fin, shift + 1, 2, 0 if shift else -1)]
+    ref = torch.zeros(b, t, dstF, co, dtype=torch.float64)
+    got = torch.zeros(b, t, dstF, co, device=dev)
+    for taps, sf, fout, f0, fstep, fill_f in runs:
+        w = torch.randn(len(taps) * ct, co, generator=g) / np.sqrt(len(taps) * ct)
+        emu_ops.conv_gemm(x0.double(), None if x1 is None else x1.double(), b, t, fin, fout, taps, sf, w.double(),
+                          bias.double(), co, "elu", ref, dstF, f0, fstep, fill_f, fill.double())
+        ops.conv_gemm(x0.to(dev), None if x1 is None else x1.to(dev), b, t, fin, fout, taps, sf,
+                      packing.pad_cols(w).to(dev), bias.to(dev), co, "elu", got, dstF, f0, fstep, fill_f,
+                      fill.to(dev) if fill_f >= 0 else None)
+    err = (got.cpu().double() - ref).abs().max().item()
+    print(f"conv_gemm {case}: max err {err:.3e}")
+    assert err < 2e-5
+
+
+@pytest.mark.parametrize("m,k,n,act", [(37, 161, 4096, "none"), (401, 1024, 161, "softplus"), (130, 1024, 4096, "none"),
+                                       (5, 48, 20, "relu")])
+def test_linear_ragged_shapes(m, k, n, act):
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    g = torch.Generator().manual_seed(m + k + n)
+    x = torch.randn(m, k, generator=g)
+    w = torch.randn(k, n, generator=g) / np.sqrt(k)
+    bias = torch.randn(n, generator=g)
+    ref = emu_ops.linear(x.double(), w.double(), bias.double(), n, act)
+    got = se_b200.ops.linear(x.to(dev), packing.pad_cols(w).to(dev), bias.to(dev), n, act)
+    err = (got.cpu().double() - ref).abs().max().item()
+    print(f"linear {m}x{k}x{n}: max err {err:.3e}")
+    assert err < 2e-5
+
+
+def test_conv_in1_and_deconv_out1():
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(4)
+    b, t = 3, 10
+    x = torch.rand(b, t, 161, generator=g) * 3
+    w = torch.randn(6, 16, generator=g) * 0.4
+    bias = torch.randn(16, generator=g) * 0.1
+    ref = emu_ops.conv_in1(x.double(), w.double(), bias.double(), 16, "elu", 80)
+    got = ops.conv_in1(x.to(dev), w.to(dev), bias.to(dev), 16, "elu", 80)
+    e1 = (got.cpu().double() - ref).abs().max().item()
+    s0 = torch.randn(b, t, 80, 16, generator=g)
+    s1 = torch.randn(b, t, 80, 16, generator=g)
+    w2 = torch.randn(6, 32, generator=g) * 0.2
+    ref2 = emu_ops.deconv_out1(s0.double(), s1.double(), w2.double(), 0.3, "softplus")
+    got2 = ops.deconv_out1(s0.to(dev), s1.to(dev), w2.to(dev), 0.3, "softplus")
+    e2 = (got2.cpu().double() - ref2).abs().max().item()
+    print(f"conv_in1 {e1:.3e} deconv_out1 {e2:.3e}")
+    assert e1 < 1e-5 and e2 < 1e-5
+
+
+@pytest.mark.parametrize("b,t,h", [(1, 6, 1024), (5, 9, 1024), (64, 12, 1024), (70, 5, 1024), (3, 7, 256)])
+def test_lstm_seq_matches_recurrence(b, t, h):
+    dev = _dev()
+    import se_b200
+    g = torch.Generator().manual_seed(b * 100 + t)
+    xp = torch.randn(b, t, 4 * h, generator=g)
+    whh = torch.randn(h // 8, h, 32, generator=g) / np.sqrt(h)
+    ref = emu_ops.lstm_seq(xp.double(), whh.double(), h)
+    got = se_b200.ops.lstm_seq(xp.to(dev), whh.to(dev), h)
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - ref).abs().max().item()
+    print(f"lstm_seq B={b} T={t} H={h}: max err {err:.3e}")
+    assert err < 2e-5

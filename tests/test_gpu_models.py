@@ -1,0 +1,115 @@
+"""End-to-end GPU parity: drop-in models and the decode loop against the committed fixtures
+(outputs of the unmodified reference modules + decode restatement) and the oracle.
+Gate (BASELINE.json north_star): RMS error <= 1e-4 on the c-normalised waveform, fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CKPT_DIR, GOLDEN
+from oracle import decode as odecode
+from oracle import synth, templates
+
+pytestmark = pytest.mark.gpu
+RMS_GATE = 1e-4
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+CASES = {
+    "crn_synth": ("crn_net", templates.crn_template, None),
+    "crn_ckpt": ("crn_net", templates.crn_template, "CRN__wsj0_si84_300h_crn_noncprs_model.pth"),
+    "lstm_synth": ("lstm_net", templates.lstm_template, None),
+    "lstm_ckpt": ("lstm_net", templates.lstm_template, "LSTM__vb_lstm_noncprs_model.pth"),
+}
+
+
+def _load(name, dev):
+    import se_b200
+    cls, tmpl, ckpt = CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if ckpt is None:
+        sd = synth.synthetic_state_dict(tmpl(), seed=0)
+    else:
+        path = os.path.join(CKPT_DIR, ckpt)
+        if not os.path.exists(path):
+            pytest.skip("checkpoint copy not present")
+        sd = torch.load(path, map_location="cpu")
+    model = getattr(se_b200, cls)()
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    return g, sd, model
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_and_decode_match_golden(name):
+    dev = _dev()
+    import se_b200
+    g, sd, model = _load(name, dev)
+    k = len(g["clip_ids"])
+    mag = torch.from_numpy(np.stack([g[f"mag{j}"] for j in range(k)])).to(dev)
+    est = model(mag).cpu().numpy()
+    ref = np.stack([g[f"est{j}"] for j in range(k)])
+    e_net = np.abs(est - ref).max()
+    wav = torch.from_numpy(np.stack([g[f"wav{j}"] for j in range(k)])).to(dev)
+    taps = {}
+    y = se_b200.decode.enhance_mag_mapping(model, wav, taps=taps)
+    c = taps["c"].cpu().numpy()
+    yn = y.cpu().numpy() * c[:, None]
+    refn = np.stack([g[f"ynorm{j}"] for j in range(k)])
+    rms = np.sqrt(np.mean((yn - refn) ** 2, axis=1))
+    rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
+    print(f"{name}: net max-abs {e_net:.3e} (|est| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
+          f"rel {rel.max():.3e}")
+    assert rms.max() <= RMS_GATE
+    assert rel.max() <= 2e-3
+    assert np.abs(y.cpu().numpy() - np.stack([g[f"y{j}"] for j in range(k)])).max() < 1e-3
+
+
+@pytest.mark.parametrize("cls,tmpl,enh", [("crn_net", templates.crn_template, odecode.enhance_crn),
+                                          ("lstm_net", templates.lstm_template, odecode.enhance_lstm)])
+def test_batch_invariance_and_oracle_at_4s(cls, tmpl, enh):
+    """A 4 s clip inside a batch equals the same clip decoded alone (the reference is B=1) and the
+    oracle's decode of it."""
+    dev = _dev()
+    import se_b200
+    sd = synth.synthetic_state_dict(tmpl(), seed=0)
+    model = getattr(se_b200, cls)()
+    model.load_state_dict(sd)
+    model.cuda()
+    n = 64000
+    wav = synth.noisy_batch(5, n, first_index=10)
+    w = torch.from_numpy(wav).to(dev)
+    taps = {}
+    yb = se_b200.decode.enhance_mag_mapping(model, w, taps=taps)
+    y1 = se_b200.decode.enhance_mag_mapping(model, w[3:4])
+    assert (yb[3:4] - y1).abs().max().item() < 1e-6
+    yo, to = enh(sd, wav[3].astype(np.float64))
+    c = float(taps["c"][3])
+    rms = np.sqrt(np.mean((yb[3].cpu().numpy() * c - to["y_norm"]) ** 2))
+    print(f"{cls} 4 s clip vs oracle: RMS {rms:.3e}, out rms {np.sqrt(np.mean(to['y_norm'] ** 2)):.3f}")
+    assert rms <= RMS_GATE
+
+
+def test_full_config_batch64_consistency():
+    """BASELINE configs[1] size (64 x 4 s, CRN): every clip of the big batch equals the same clip
+    decoded in a small batch (no cross-utterance leakage at full size), output finite."""
+    dev = _dev()
+    import se_b200
+    sd = synth.synthetic_state_dict(templates.crn_template(), seed=0)
+    model = se_b200.crn_net()
+    model.load_state_dict(sd)
+    model.cuda()
+    n = 64000
+    base = synth.noisy_batch(4, n, first_index=20)
+    wav = torch.from_numpy(np.concatenate([base] * 16, axis=0)).to(dev)          # 64 clips
+    y = se_b200.decode.enhance_mag_mapping(model, wav)
+    assert torch.isfinite(y).all()
+    ys = se_b200.decode.enhance_mag_mapping(model, wav[:4])
+    for r in range(16):
+        assert (y[4 * r:4 * r + 4] - ys).abs().max().item() < 1e-6

@@ -1,0 +1,126 @@
+"""CPU tests of the host side: C-ABI surface, state-dict drop-in, weight packing / tap tables /
+layouts (through a torch mirror of the kernel semantics), sharding over gloo."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import emu_ops
+import se_b200
+from conftest import ROOT
+from oracle import nets, synth, templates
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "se_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(se_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert "se_stft" in syms and "se_lstm_seq" in syms
+    assert os.path.exists(se_b200._lib.LIB_PATH), "libse_b200.so not built (run __graft_entry__.build())"
+    lib = ctypes.CDLL(se_b200._lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/se_b200.h but not exported"
+    assert set(se_b200._lib.PROTOTYPES) == set(syms), "ctypes prototypes out of sync with the header"
+    assert se_b200._lib.load().se_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    m = se_b200.crn_net()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 4, 161))
+    with pytest.raises(Exception):
+        se_b200.ops.rms_scale(torch.zeros(1, 16))
+
+
+@pytest.mark.parametrize("cls,tmpl", [(se_b200.crn_net, templates.crn_template),
+                                      (se_b200.lstm_net, templates.lstm_template)])
+def test_state_dict_namespace(cls, tmpl):
+    m = cls()
+    t = tmpl()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(t.keys())
+    assert all(tuple(sd[k].shape) == tuple(t[k]) for k in t)
+    m.load_state_dict(synth.synthetic_state_dict(t, seed=1))      # strict
+    assert m.eval() is m
+
+
+@pytest.mark.parametrize("seed", [0, 7])
+def test_crn_host_logic_matches_oracle(monkeypatch, seed):
+    emu_ops.install(se_b200.ops, monkeypatch)
+    sd = synth.synthetic_state_dict(templates.crn_template(), seed=seed)
+    m = se_b200.crn_net()
+    m.load_state_dict(sd)
+    x = torch.rand(3, 17, 161, generator=torch.Generator().manual_seed(seed)) * 4
+    taps, rt = {}, {}
+    y = m._forward_impl(x, taps)
+    with torch.no_grad():
+        yr = nets.crn_forward(sd, x, rt)
+    for i in range(1, 6):
+        assert (taps[f"en{i}"].permute(0, 3, 1, 2) - rt[f"en{i}"]).abs().max() < 1e-4
+    for i in range(1, 5):
+        assert (taps[f"de{i}"].permute(0, 3, 1, 2) - rt[f"de{i}"]).abs().max() < 1e-3
+    assert (y - yr).abs().max() < 1e-3 * max(1.0, yr.abs().max().item())
+    # re-loading other weights must invalidate the packed copies
+    m.load_state_dict(synth.synthetic_state_dict(templates.crn_template(), seed=seed + 1))
+    y2 = m._forward_impl(x)
+    assert (y2 - y).abs().max() > 1e-3
+
+
+def test_lstm_net_host_logic_matches_oracle(monkeypatch):
+    emu_ops.install(se_b200.ops, monkeypatch)
+    sd = synth.synthetic_state_dict(templates.lstm_template(), seed=2)
+    m = se_b200.lstm_net()
+    m.load_state_dict(sd)
+    x = torch.rand(2, 9, 161, generator=torch.Generator().manual_seed(3)) * 4
+    y = m._forward_impl(x)
+    with torch.no_grad():
+        yr = nets.lstm_net_forward(sd, x)
+    assert (y - yr).abs().max() < 1e-4
+
+
+def test_shard_range_partitions():
+    from se_b200 import shard
+    for b in (1, 7, 64, 256, 513):
+        for w in (1, 2, 4, 8):
+            spans = [shard.shard_range(b, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == b
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, batch, q):
+    import torch.distributed as dist
+    from se_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    full = torch.arange(batch * 5, dtype=torch.float32).view(batch, 5)
+    s, e = shard.shard_range(batch, rank, world)
+    out = shard.gather_waveforms(full[s:e].clone() * 1.0, batch)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [8, 7])
+def test_gather_over_gloo_world2(batch):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
