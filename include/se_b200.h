@@ -72,14 +72,15 @@ int se_rms_scale(const float* wav, long long wav_stride, int B, int N, int recip
  *     wav [B,N]; scale [B] or NULL (multiplies the waveform, i.e. the `* c` of a1).
  *     Supported (n_fft, win, hop): n_fft in {320, 512}, win <= n_fft (window centred,
  *     zero padded), hop even, hop <= n_fft.  T must equal 1 + N/hop.
- *     Up to three output planes, any may be NULL, all addressed as
- *        plane[b*sb + t*st + f*sf]   (strides in floats; F = n_fft/2+1 bins)
+ *     Up to three output planes, any may be NULL (re/im together), addressed as
+ *        mag[b*msb + t*mst + f*msf]  and  re|im[b*sb + t*st + f*sf]
+ *     (strides in floats; F = n_fft/2+1 bins):
  *        mag = |X|^p_mag ; re,im = X * |X|^(p_ri-1)  (p_ri = 1: the plain spectrum).
  *     An interleaved complex64 [B,T,F] tensor is (re = base, im = base+1, sb=2TF, st=2F, sf=2).
  * ------------------------------------------------------------------------------------- */
 int se_stft(const float* wav, long long wav_stride, int B, int N, const float* scale, int n_fft, int win, int hop,
-            int T, float* mag, float* re, float* im, long long sb, long long st, long long sf, float p_mag, float p_ri,
-            se_stream_t stream);
+            int T, float* mag, long long msb, long long mst, long long msf, float* re, float* im, long long sb,
+            long long st, long long sf, float p_mag, float p_ri, se_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a7+a8+a9  Fused recombination prologue + irFFT + window + overlap-add + envelope
@@ -179,6 +180,20 @@ int se_lstm_seq(const float* xproj, const float* whh, int B, int T, int H, float
                 long long hseq_st, float* work, unsigned* sync, se_stream_t stream);
 /* Bytes of `work` se_lstm_seq needs. */
 long long se_lstm_seq_work_bytes(int B, int H);
+
+/* ---------------------------------------------------------------------------------------
+ * a6 building block on the tensor cores: fp32-accurate GEMM as 3xTF32 (tcgen05 + TMEM + TMA).
+ *     se_split_tf32:  x -> hi = rna_tf32(x), lo = rna_tf32(x - hi)   (n %% 4 == 0, 16-byte aligned)
+ *     se_gemm_tf32x3: C[M,N] = act(bias + (A_hi+A_lo)[M,K] * (B_hi+B_lo)[N,K]^T), dropping only
+ *                     the A_lo*B_lo term; both operands K-major (row strides lda / ldb floats),
+ *                     K %% 32 == 0.  Same contract as nn.Linear(K, N) with weight [N, K]
+ *                     (LSTM/LSTM.py:19-22) and the hoisted nn.LSTM input projection
+ *                     weight_ih_l* [4H, K] (CRN/CRN.py:20).
+ * ------------------------------------------------------------------------------------- */
+int se_split_tf32(const float* x, float* hi, float* lo, long long n, se_stream_t stream);
+int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const float* b_hi, const float* b_lo,
+                   long long ldb, int M, int N, int K, const float* bias, int act, float* C, long long ldc,
+                   se_stream_t stream);
 
 #ifdef __cplusplus
 }

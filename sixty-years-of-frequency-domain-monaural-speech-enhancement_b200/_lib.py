@@ -36,7 +36,7 @@ PROTOTYPES = {
     "se_device_check": (_I, []),
     "se_launch_count": (C.c_ulonglong, []),
     "se_rms_scale": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P]),
-    "se_stft": (_I, [_P, _LL, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _LL, _LL, _LL, _F, _F, _P]),
+    "se_stft": (_I, [_P, _LL, _I, _I, _P, _I, _I, _I, _I, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _P]),
     "se_istft": (_I, [_I, _P, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _I, _I, _I, _I, _I, _P, _P, _LL,
                       _I, _P]),
     "se_conv_gemm": (_I, [C.POINTER(ConvDesc), _P]),
@@ -44,6 +44,8 @@ PROTOTYPES = {
     "se_deconv_out1": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _P]),
     "se_lstm_seq": (_I, [_P, _P, _I, _I, _I, _P, _LL, _LL, _P, _P, _P]),
     "se_lstm_seq_work_bytes": (_LL, [_I, _I]),
+    "se_split_tf32": (_I, [_P, _P, _P, _LL, _P]),
+    "se_gemm_tf32x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _P, _LL, _P]),
 }
 
 _lib = None

@@ -64,6 +64,7 @@ struct StftParams {
   const float* scale;
   int win, hop, T;
   float *mag, *re, *im;
+  long long msb, mst, msf;
   long long sb, st, sf;
   float p_mag, p_ri;
 };
@@ -134,7 +135,10 @@ __global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
     for (int i = tid; i < NFFT; i += kDspThreads) {
       const int n = i - left;
       float w = 0.0f;
-      if (n >= 0 && n < p.win) w = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)p.win);
+      if (n >= 0 && n < p.win) {
+        const float sn = sinpif((float)n / (float)p.win);  // hann = sin^2: no cancellation near the ends
+        w = sn * sn;
+      }
       wtab[i] = w * sc;
     }
   }
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
   __syncthreads();
 
   // --- epilogue: feature split + layout-aware store ------------------------------------------
-  const bool time_major = (p.sf <= p.st);
+  const bool time_major = p.re ? (p.sf <= p.st) : (p.msf <= p.mst);
   const int total = nf * F;
   for (int idx = tid; idx < total; idx += kDspThreads) {
     int i, k;
@@ -181,10 +185,11 @@ __global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
       const int k2 = k / R, k1 = k - k2 * R;
       X = spec[(i * R + k1) * 33 + k2];
     }
-    const long long off = (long long)b * p.sb + (long long)(t0 + i) * p.st + (long long)k * p.sf;
     const float m = sqrtf(X.x * X.x + X.y * X.y);
-    if (p.mag) p.mag[off] = pow_pos(m, p.p_mag);
+    if (p.mag)
+      p.mag[(long long)b * p.msb + (long long)(t0 + i) * p.mst + (long long)k * p.msf] = pow_pos(m, p.p_mag);
     if (p.re) {
+      const long long off = (long long)b * p.sb + (long long)(t0 + i) * p.st + (long long)k * p.sf;
       const float s = pow_scale(m, p.p_ri - 1.0f);
       p.re[off] = X.x * s;
       p.im[off] = X.y * s;
@@ -235,7 +240,10 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
     for (int i = tid; i < NFFT; i += kDspThreads) {
       const int n = i - left;
       float w = 0.0f;
-      if (n >= 0 && n < p.win) w = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)p.win);
+      if (n >= 0 && n < p.win) {
+        const float sn = sinpif((float)n / (float)p.win);  // hann = sin^2: no cancellation near the ends
+        w = sn * sn;
+      }
       wtab[i] = w;
     }
   }
@@ -369,14 +377,15 @@ static int geom_ok(const char* who, int n_fft, int win, int hop) {
 }
 
 extern "C" int se_stft(const float* wav, long long wav_stride, int B, int N, const float* scale, int n_fft, int win,
-                       int hop, int T, float* mag, float* re, float* im, long long sb, long long st, long long sf,
-                       float p_mag, float p_ri, se_stream_t stream) {
+                       int hop, int T, float* mag, long long msb, long long mst, long long msf, float* re,
+                       float* im, long long sb, long long st, long long sf, float p_mag, float p_ri,
+                       se_stream_t stream) {
   if (!geom_ok("se_stft", n_fft, win, hop)) return SE_ERR_SHAPE;
   SE_REQUIRE(wav && B > 0 && N >= n_fft, "se_stft: need N >= n_fft (N=%d)", N);
   SE_REQUIRE(T == 1 + N / hop, "se_stft: T=%d but 1+N/hop=%d", T, 1 + N / hop);
   SE_REQUIRE((re == nullptr) == (im == nullptr), "se_stft: re and im must both be given or both NULL");
   SE_REQUIRE(mag || re, "se_stft: no output plane");
-  StftParams p{wav, wav_stride, B, N, scale, win, hop, T, mag, re, im, sb, st, sf, p_mag, p_ri};
+  StftParams p{wav, wav_stride, B, N, scale, win, hop, T, mag, re, im, msb, mst, msf, sb, st, sf, p_mag, p_ri};
   dim3 grid(ceil_div(T, kFramesPerCta), B);
   const int R = n_fft / 64;
   const int smem = dsp_smem_stft(R, hop);

@@ -1,0 +1,399 @@
+// 3xTF32 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   C[M,N] = act( A[M,K] * B[N,K]^T + bias ),   fp32 in, fp32 out, fp32-class accuracy.
+//
+// A single TF32 pass cannot meet the 1e-4 RMS parity gate (rounding the
+// weights alone to TF32 costs 1.1e-4 .. 5e-4), so every operand is split once into two TF32
+// numbers, x = x_hi + x_lo (x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi), 21+ mantissa bits
+// together) and the product is accumulated in fp32 in tensor memory as
+//        A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (A_lo*B_lo ~ 2^-22 is dropped)
+// i.e. three tcgen05.mma.kind::tf32 per K-slice on four TMA-staged operand tiles.
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d, SWIZZLE_128B tiles, mbarrier tx
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns), bias + activation, st.global
+//   smem ring: STAGES x {A_hi, A_lo, B_hi, B_lo} tiles of 128 rows x 32 fp32 (128-byte rows)
+//   TMEM     : 2 accumulators of 128 lanes x 128 columns (epilogue of tile i overlaps MMA of i+1)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace se {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;           // 16 KB (same for A and B tiles)
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;                          // 2 x 128-column accumulators
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_slot, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc,
+                                          unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(unsigned taddr, float (&v)[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO),
+// LBO is unused for swizzled K-major layouts (1, as CUTLASS sets it); version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
+  const uint64_t addr = (uint64_t)(smem_u32(tile) >> 4) & 0x3FFFull;
+  return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+constexpr unsigned make_idesc_tf32(int m, int n) {
+  return (1u << 4)                      // D format: F32
+         | (2u << 7) | (2u << 10)       // A, B format: TF32
+         | (0u << 15) | (0u << 16)      // A, B K-major
+         | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+
+struct TcParams {
+  int M, N, K;
+  const float* bias;
+  int act;
+  float* C;
+  long long ldc;
+  int panel_m;  // m-blocks per L2 panel
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                   const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                   const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = base;                                        // STAGES x 4 x 16 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                   // [STAGES]
+  uint64_t* empty = bars + TC_STAGES;      // [STAGES]
+  uint64_t* tfull = bars + 2 * TC_STAGES;  // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mblocks = ceil_div(p.M, TC_BM), nblocks = ceil_div(p.N, TC_BN);
+  const int ntiles = mblocks * nblocks;
+  const int kblocks = p.K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_ahi);
+    tma_prefetch_desc(&map_alo);
+    tma_prefetch_desc(&map_bhi);
+    tma_prefetch_desc(&map_blo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+
+  // tile order: panels of `panel_m` m-blocks, n fastest inside a panel (A panel + all of B stay in L2)
+  auto tile_coords = [&](int tile, int& mb, int& nb) {
+    const int per_panel = p.panel_m * nblocks;
+    const int panel = tile / per_panel;
+    const int r = tile - panel * per_panel;
+    const int pm = min(p.panel_m, mblocks - panel * p.panel_m);
+    nb = r / pm;
+    mb = panel * p.panel_m + (r - nb * pm);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int mb, nb;
+        tile_coords(tile, mb, nb);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait_parity(&empty[stage], phase ^ 1);
+          unsigned char* st = tiles + stage * TC_STAGE_BYTES;
+          mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
+          tma_load_2d(&map_ahi, &full[stage], st + 0 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
+          tma_load_2d(&map_alo, &full[stage], st + 1 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
+          tma_load_2d(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
+          tma_load_2d(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr unsigned idesc = make_idesc_tf32(TC_BM, TC_BN);
+      int stage = 0;
+      unsigned phase = 0;
+      int acc = 0;
+      unsigned acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait_parity(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const unsigned d_tmem = tmem_base + (unsigned)(acc * TC_BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait_parity(&full[stage], phase);
+          tc_fence_after();
+          unsigned char* st = tiles + stage * TC_STAGE_BYTES;
+          const uint64_t d_ahi = make_smem_desc(st + 0 * TC_TILE_BYTES);
+          const uint64_t d_alo = make_smem_desc(st + 1 * TC_TILE_BYTES);
+          const uint64_t d_bhi = make_smem_desc(st + 2 * TC_TILE_BYTES);
+          const uint64_t d_blo = make_smem_desc(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 slice, in 16-byte units
+            umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+            umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quarter = warp & 3;  // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
+    int acc = 0;
+    unsigned acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int mb, nb;
+      tile_coords(tile, mb, nb);
+      mbar_wait_parity(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = mb * TC_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* crow = p.C + (long long)row * p.ldc;
+#pragma unroll 1
+      for (int ch = 0; ch < TC_BN / 32; ++ch) {
+        float v[32];
+        const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * TC_BN + ch * 32);
+        tmem_ld_32x32(taddr, v);
+        const int n0 = nb * TC_BN + ch * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = n0 + j + e;
+              const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+              o[e] = apply_act(v[j + e] + bb, p.act);
+            }
+            if (n0 + j + 3 < p.N) {
+              *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n0 + j + e < p.N) crow[n0 + j + e] = o[e];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// x -> (hi, lo):  hi = rna_tf32(x), lo = rna_tf32(x - hi)
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
+                                                        float4* __restrict__ lo, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    float in[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      unsigned hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hb) : "f"(in[e]));
+      h[e] = __uint_as_float(hb);
+      const float r = in[e] - h[e];
+      asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lb) : "f"(r));
+      l[e] = __uint_as_float(lb);
+    }
+    hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+    lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time libcuda dependency) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SE_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d ld=%lld)", (int)r, rows, K, ld);
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
+}  // namespace se
+
+using namespace se;
+
+extern "C" int se_split_tf32(const float* x, float* hi, float* lo, long long n, se_stream_t stream) {
+  SE_REQUIRE(x && hi && lo && n > 0 && (n & 3) == 0, "se_split_tf32: n=%lld must be a positive multiple of 4", n);
+  SE_REQUIRE(((((uintptr_t)x) | ((uintptr_t)hi) | ((uintptr_t)lo)) & 15) == 0, "se_split_tf32: unaligned");
+  const long long n4 = n / 4;
+  const int blocks = (int)min((long long)148 * 8, ceil_div_ll(n4, 256));
+  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x),
+                                                              reinterpret_cast<float4*>(hi),
+                                                              reinterpret_cast<float4*>(lo), n4);
+  return check_launch("se_split_tf32");
+}
+
+extern "C" int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const float* b_hi,
+                              const float* b_lo, long long ldb, int M, int N, int K, const float* bias, int act,
+                              float* C, long long ldc, se_stream_t stream) {
+  SE_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "se_gemm_tf32x3: null pointer");
+  SE_REQUIRE(M > 0 && N > 0 && K > 0 && K % TC_BK == 0, "se_gemm_tf32x3: K=%d must be a multiple of %d", K, TC_BK);
+  SE_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (ldc & 3) == 0, "se_gemm_tf32x3: leading dims must be %% 4");
+  SE_REQUIRE(((((uintptr_t)a_hi) | ((uintptr_t)a_lo) | ((uintptr_t)b_hi) | ((uintptr_t)b_lo) | ((uintptr_t)C)) & 15) == 0,
+             "se_gemm_tf32x3: pointers must be 16-byte aligned");
+  CUtensorMap m_ahi, m_alo, m_bhi, m_blo;
+  int rc;
+  if ((rc = make_map(&m_ahi, a_hi, M, K, lda))) return rc;
+  if ((rc = make_map(&m_alo, a_lo, M, K, lda))) return rc;
+  if ((rc = make_map(&m_bhi, b_hi, N, K, ldb))) return rc;
+  if ((rc = make_map(&m_blo, b_lo, N, K, ldb))) return rc;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int mblocks = ceil_div(M, TC_BM), nblocks = ceil_div(N, TC_BN);
+  TcParams p{M, N, K, bias, act, C, ldc, 16};
+  if (p.panel_m > mblocks) p.panel_m = mblocks;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e != cudaSuccess) {
+    set_error("se_gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  const int grid = min(sms, mblocks * nblocks);
+  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(m_ahi, m_alo, m_bhi, m_blo, p);
+  return check_launch("se_gemm_tf32x3");
+}

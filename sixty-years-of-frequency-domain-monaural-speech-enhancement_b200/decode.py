@@ -34,8 +34,7 @@ def enhance_mag_mapping(model, wav, p=1.0, geom=GEOM_320, taps=None):
     c, inv_c = ops.rms_scale(wav)
     mag = torch.empty(b, t, f, device=wav.device, dtype=torch.float32)
     spec = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)   # noisy spectrum (phase)
-    ops.stft(wav, c, n_fft, win, hop, mag=mag, re=None, im=None, p_mag=p)
-    ops.stft(wav, c, n_fft, win, hop, mag=None, re=spec[..., 0], im=spec[..., 1])
+    ops.stft(wav, c, n_fft, win, hop, mag=mag, re=spec[..., 0], im=spec[..., 1], p_mag=p)
     est = model(mag)
     out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
     ops.istft(ISTFT_MAG_PHASE, est, None, spec[..., 0], spec[..., 1], n_fft, win, hop, out, n, out_scale=inv_c,

@@ -26,6 +26,40 @@ def _need_cuda(*ts):
 
 _checked = False
 
+# ---- optional per-op CUDA-event timing (bench.py's roofline leg) ---------------------------------
+_recorder = None   # dict: op name -> list of (start_event, end_event)
+
+
+class _Timed:
+    __slots__ = ("name", "s")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _recorder is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if _recorder is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            _recorder.setdefault(self.name, []).append((self.s, e))
+        return False
+
+
+def start_recording():
+    global _recorder
+    _recorder = {}
+
+
+def stop_recording():
+    """Returns {op: (launch_count, total_ms)}; call after torch.cuda.synchronize()."""
+    global _recorder
+    rec, _recorder = _recorder, None
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (rec or {}).items()}
+
 
 def device_check():
     global _checked
@@ -46,8 +80,9 @@ def rms_scale(wav, reciprocal=False):
     b, n = wav.shape
     c = torch.empty(b, device=wav.device, dtype=torch.float32)
     ic = torch.empty_like(c)
-    check(_lib.load().se_rms_scale(_ptr(wav), wav.stride(0), b, n, int(reciprocal), _ptr(c), _ptr(ic), _stream()),
-          "se_rms_scale")
+    with _Timed("rms_scale"):
+        check(_lib.load().se_rms_scale(_ptr(wav), wav.stride(0), b, n, int(reciprocal), _ptr(c), _ptr(ic),
+                                       _stream()), "se_rms_scale")
     return c, ic
 
 
@@ -60,18 +95,21 @@ def _plane_strides(t, layout):
 
 def stft(wav, scale, n_fft, win, hop, mag=None, re=None, im=None, layout="btf", p_mag=1.0, p_ri=1.0):
     """Fused STFT.  mag / re / im are pre-allocated planes ([B,T,F] for 'btf', [B,F,T] for 'bft');
-    all given planes must share strides."""
+    re and im must share strides, mag has its own."""
     _need_cuda(wav, scale, mag, re, im)
     device_check()
     b, n = wav.shape
     t = 1 + n // hop
-    ref = mag if mag is not None else re
-    sb, st, sf = _plane_strides(ref, layout)
-    for pl in (mag, re, im):
-        if pl is not None:
-            assert _plane_strides(pl, layout) == (sb, st, sf), "all STFT output planes must share strides"
-    check(_lib.load().se_stft(_ptr(wav), wav.stride(0), b, n, _ptr(scale), n_fft, win, hop, t, _ptr(mag), _ptr(re),
-                              _ptr(im), sb, st, sf, float(p_mag), float(p_ri), _stream()), "se_stft")
+    msb = mst = msf = sb = st = sf = 0
+    if mag is not None:
+        msb, mst, msf = _plane_strides(mag, layout)
+    if re is not None:
+        sb, st, sf = _plane_strides(re, layout)
+        assert _plane_strides(im, layout) == (sb, st, sf), "re and im planes must share strides"
+    with _Timed("stft"):
+        check(_lib.load().se_stft(_ptr(wav), wav.stride(0), b, n, _ptr(scale), n_fft, win, hop, t, _ptr(mag), msb,
+                                  mst, msf, _ptr(re), _ptr(im), sb, st, sf, float(p_mag), float(p_ri), _stream()),
+              "se_stft")
     return t
 
 
@@ -89,9 +127,10 @@ def istft(mode, a_re, a_im, b_re, b_im, n_fft, win, hop, out, length, out_scale=
         bsb = bst = bsf = 0
     bsz = a_re.shape[0]
     t = a_re.shape[1] if layout_a == "btf" else a_re.shape[2]
-    check(_lib.load().se_istft(mode, _ptr(a_re), _ptr(a_im), asb, ast, asf, _ptr(b_re), _ptr(b_im), bsb, bst, bsf,
-                               float(inv_p), float(p_x), bsz, t, n_fft, win, hop, _ptr(out_scale), _ptr(out),
-                               out.stride(0), int(length), _stream()), "se_istft")
+    with _Timed("istft"):
+        check(_lib.load().se_istft(mode, _ptr(a_re), _ptr(a_im), asb, ast, asf, _ptr(b_re), _ptr(b_im), bsb, bst,
+                                   bsf, float(inv_p), float(p_x), bsz, t, n_fft, win, hop, _ptr(out_scale),
+                                   _ptr(out), out.stride(0), int(length), _stream()), "se_istft")
     return out
 
 
@@ -117,7 +156,8 @@ def conv_gemm(src0, src1, B, T, Fin, Fout, taps, sf, W, bias, Cout, act, dst, ds
     d.dst, d.dstF, d.dst_f0, d.dst_fstep = dst.data_ptr(), dstF, dst_f0, dst_fstep
     d.fill_f = fill_f
     d.fill = fill.data_ptr() if fill is not None else 0
-    check(_lib.load().se_conv_gemm(C.byref(d), _stream()), "se_conv_gemm")
+    with _Timed(f"conv_gemm[K={len(taps) * (c0 + c1)},N={Cout}]"):
+        check(_lib.load().se_conv_gemm(C.byref(d), _stream()), "se_conv_gemm")
     return dst
 
 
@@ -136,8 +176,9 @@ def conv_in1(src, W, bias, cout, act, fout):
     b, t, fin = src.shape
     assert src.is_contiguous()
     dst = torch.empty(b, t, fout, cout, device=src.device, dtype=torch.float32)
-    check(_lib.load().se_conv_in1(_ptr(src), b, t, fin, _ptr(W), _ptr(bias), cout, ACT[act], _ptr(dst), fout,
-                                  _stream()), "se_conv_in1")
+    with _Timed("conv_in1"):
+        check(_lib.load().se_conv_in1(_ptr(src), b, t, fin, _ptr(W), _ptr(bias), cout, ACT[act], _ptr(dst), fout,
+                                      _stream()), "se_conv_in1")
     return dst
 
 
@@ -147,8 +188,9 @@ def deconv_out1(src0, src1, W, bias: float, act):
     b, t, fin, c0 = src0.shape
     c1 = src1.shape[-1] if src1 is not None else 0
     dst = torch.empty(b, t, 2 * fin + 1, device=src0.device, dtype=torch.float32)
-    check(_lib.load().se_deconv_out1(_ptr(src0), _ptr(src1), c0, c1, b, t, fin, _ptr(W), float(bias), ACT[act],
-                                     _ptr(dst), _stream()), "se_deconv_out1")
+    with _Timed("deconv_out1"):
+        check(_lib.load().se_deconv_out1(_ptr(src0), _ptr(src1), c0, c1, b, t, fin, _ptr(W), float(bias), ACT[act],
+                                         _ptr(dst), _stream()), "se_deconv_out1")
     return dst
 
 
@@ -170,6 +212,35 @@ def lstm_seq(xproj, whh, hidden, out=None):
     for b0 in range(0, b, _LSTM_MAX_B):
         nb = min(_LSTM_MAX_B, b - b0)
         xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
-        check(lib.se_lstm_seq(_ptr(xs), _ptr(whh), nb, t, hidden, _ptr(os_), os_.stride(0), os_.stride(1),
-                              _ptr(work), _ptr(sync), _stream()), "se_lstm_seq")
+        with _Timed("lstm_seq"):
+            check(lib.se_lstm_seq(_ptr(xs), _ptr(whh), nb, t, hidden, _ptr(os_), os_.stride(0), os_.stride(1),
+                                  _ptr(work), _ptr(sync), _stream()), "se_lstm_seq")
+    return out
+
+
+def split_tf32(x):
+    """x (contiguous fp32) -> (hi, lo) TF32 pair with x ~= hi + lo to 21+ mantissa bits."""
+    _need_cuda(x)
+    device_check()
+    assert x.is_contiguous() and x.numel() % 4 == 0
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    with _Timed("split_tf32"):
+        check(_lib.load().se_split_tf32(_ptr(x), _ptr(hi), _ptr(lo), x.numel(), _stream()), "se_split_tf32")
+    return hi, lo
+
+
+def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, n_out, act="none", out=None):
+    """(a_hi+a_lo) [M,K] @ (b_hi+b_lo) [N,K]^T (+bias, act) -> [M, n_out] on tcgen05 (3xTF32)."""
+    _need_cuda(a_hi, a_lo, b_hi, b_lo, bias)
+    device_check()
+    m, k = a_hi.shape
+    n = b_hi.shape[0]
+    assert n == n_out and b_hi.shape[1] == k and a_hi.stride(1) == 1 and b_hi.stride(1) == 1
+    assert a_lo.stride() == a_hi.stride() and b_lo.stride() == b_hi.stride()
+    if out is None:
+        out = torch.empty(m, n_out, device=a_hi.device, dtype=torch.float32)
+    with _Timed(f"gemm_tf32x3[K={k},N={n}]"):
+        check(_lib.load().se_gemm_tf32x3(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(b_hi), _ptr(b_lo),
+                                         b_hi.stride(0), m, n, k, _ptr(bias), ACT[act], _ptr(out), out.stride(0),
+                                         _stream()), "se_gemm_tf32x3")
     return out

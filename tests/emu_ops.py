@@ -49,7 +49,7 @@ def linear(x2d, W, bias, n_out, act="none", out=None):
 
 def conv_in1(src, W, bias, cout, act, fout):
     b, t, fin = src.shape
-    dst = torch.empty(b, t, fout, cout)
+    dst = torch.empty(b, t, fout, cout, dtype=src.dtype)
     taps = [(kt - 1, kf) for kt in range(2) for kf in range(3)]
     return conv_gemm(src.unsqueeze(-1), None, b, t, fin, fout, taps, 2, W, bias, cout, act, dst, fout)
 
@@ -58,7 +58,7 @@ def deconv_out1(src0, src1, W, bias, act):
     b, t, fin, c0 = src0.shape
     x = src0 if src1 is None else torch.cat([src0, src1], dim=-1)
     ct = x.shape[-1]
-    out = torch.full((b, t, 2 * fin + 1), float(bias))
+    out = torch.full((b, t, 2 * fin + 1), float(bias), dtype=src0.dtype)
     for kt in range(2):
         xs = torch.zeros_like(x)
         xs[:, kt:] = x[:, :t - kt] if kt else x
@@ -71,8 +71,8 @@ def deconv_out1(src0, src1, W, bias, act):
 def lstm_seq(xproj, whh, hidden, out=None):
     b, t, _ = xproj.shape
     s = hidden // 8
-    h = torch.zeros(b, hidden)
-    c = torch.zeros(b, hidden)
+    h = torch.zeros(b, hidden, dtype=xproj.dtype)
+    c = torch.zeros(b, hidden, dtype=xproj.dtype)
     outs = []
     # whh [S, H, 32]: gates for slice s = h @ whh[s]  -> [b, 32] = (gate, j)
     for step in range(t):

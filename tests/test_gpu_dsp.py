@@ -98,7 +98,10 @@ def test_istft_spec_matches_oracle(geom, layout):
     out2 = torch.full((b, n + 500), 7.0, device=dev)
     ops.istft(ISTFT_SPEC, re, im, None, None, n_fft, win, hop, out2, n + 500, layout_a=layout)
     ref2 = np.stack([dsp.istft(s, n_fft, win, hop, length=n + 500) for s in spec])
-    assert np.abs(out2.cpu().numpy() - ref2).max() < 2e-5
+    # the last n_fft/2 samples divide by a vanishing window envelope (values ~1e4): relative gate
+    d2 = np.abs(out2.cpu().numpy() - ref2)
+    assert (d2 <= 2e-5 * np.maximum(1.0, np.abs(ref2))).all()
+    assert np.all(out2.cpu().numpy()[:, n + n_fft // 2:] == 0)
 
 
 def test_istft_prologue_modes():

@@ -116,3 +116,27 @@ def test_lstm_seq_matches_recurrence(b, t, h):
     err = (got.cpu().double() - ref).abs().max().item()
     print(f"lstm_seq B={b} T={t} H={h}: max err {err:.3e}")
     assert err < 2e-5
+
+
+@pytest.mark.parametrize("m,k,n,act", [(128, 32, 128, "none"), (300, 1024, 256, "none"), (1000, 256, 4096, "softplus"),
+                                       (77, 64, 161 + 3, "none")])
+def test_gemm_tf32x3_fp32_accuracy(m, k, n, act):
+    """tcgen05 3xTF32 GEMM: error must be fp32-class (<< single-pass TF32's ~5e-4 relative)."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / np.sqrt(k)
+    bias = torch.randn(n, generator=g)
+    ref = emu_ops._act(a.double() @ w.double().t() + bias.double(), act)
+    a_hi, a_lo = ops.split_tf32(a.to(dev))
+    w_hi, w_lo = ops.split_tf32(w.to(dev))
+    assert ((a_hi + a_lo).cpu() - a).abs().max().item() < 2e-6
+    got = ops.gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias.to(dev), n, act)
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - ref).abs().max().item()
+    one_pass = ((a_hi.cpu().double() @ w_hi.cpu().double().t() + bias.double()) -
+                (a.double() @ w.double().t() + bias.double())).abs().max().item()
+    print(f"gemm_tf32x3 {m}x{k}x{n}: max err {err:.3e} (single-pass TF32 would be {one_pass:.3e})")
+    assert err < 1e-5
