@@ -4,7 +4,7 @@ Package directory name follows the build contract
 (``sixty-years-of-frequency-domain-monaural-speech-enhancement_b200``); it is importable as
 ``se_b200`` through the alias module at the repository root.
 """
-from . import _lib, ops, packing, decode, shard   # noqa: F401
+from . import _lib, ops, packing, lstm_engine, decode, shard   # noqa: F401
 from .crn import crn_net                   # noqa: F401
 from .lstm import lstm_net                 # noqa: F401
 

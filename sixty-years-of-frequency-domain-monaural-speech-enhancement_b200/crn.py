@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops, packing
+from . import lstm_engine, ops, packing
 from .param_tree import bn_rows, build_param_tree, lstm_rows
 
 _ENC_CH = [1, 16, 32, 64, 128, 256]          # CRN.py:40-62
@@ -123,9 +123,7 @@ class crn_net(nn.Module):
         # LSTM: two layers, input projection hoisted over all T
         seq = h.view(b * t, 1024)
         for l in range(2):
-            wih, bih, whh = P[f"lstm{l}"]
-            xp = ops.linear(seq, wih, bih, 4096)
-            hs = ops.lstm_seq(xp.view(b, t, 4096), whh, 1024)
+            hs = lstm_engine.lstm_layer(seq, P[f"lstm{l}"], b, t)
             seq = hs.view(b * t, 1024)
         if taps is not None:
             taps["lstm_nhwc"] = hs

@@ -14,7 +14,11 @@
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
 //   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns), bias + activation, st.global
 //   smem ring: STAGES x {A_hi, A_lo, B_hi, B_lo} tiles of 128 rows x 32 fp32 (128-byte rows)
-//   TMEM     : 2 accumulators of 128 lanes x 128 columns (epilogue of tile i overlaps MMA of i+1)
+//   TMEM     : 2 accumulators of 128 lanes x 128 columns, used as a ping-pong over K-CHUNKS:
+//              the tensor core's fp32 accumulate truncates (measured: error grows linearly with
+//              the number of accumulation steps, 3.4e-5 at K=1024), so every TC_CHUNK_KB k-blocks
+//              the partial sum is promoted to fp32 registers of the epilogue warps (round-to-
+//              nearest adds on the CUDA cores) while the MMA warp fills the other accumulator.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -23,6 +27,7 @@ namespace se {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
 constexpr int TC_STAGES = 3;
+constexpr int TC_CHUNK_KB = 4;                              // k-blocks (of 32) per TMEM accumulation chunk
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;           // 16 KB (same for A and B tiles)
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 192;
@@ -209,10 +214,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
       int acc = 0;
       unsigned acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait_parity(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const unsigned d_tmem = tmem_base + (unsigned)(acc * TC_BN);
         for (int kb = 0; kb < kblocks; ++kb) {
+          const bool chunk_start = (kb % TC_CHUNK_KB) == 0;
+          if (chunk_start) {
+            mbar_wait_parity(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+          }
+          const unsigned d_tmem = tmem_base + (unsigned)(acc * TC_BN);
           mbar_wait_parity(&full[stage], phase);
           tc_fence_after();
           unsigned char* st = tiles + stage * TC_STAGE_BYTES;
@@ -223,7 +231,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 slice, in 16-byte units
-            umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
             umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
             umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
           }
@@ -232,11 +240,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             stage = 0;
             phase ^= 1;
           }
-        }
-        umma_commit(&tfull[acc]);  // accumulator complete
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+          if ((kb % TC_CHUNK_KB) == TC_CHUNK_KB - 1 || kb == kblocks - 1) {
+            umma_commit(&tfull[acc]);  // chunk accumulator complete
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1;
+            }
+          }
         }
       }
     }
@@ -248,43 +258,51 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int mb, nb;
       tile_coords(tile, mb, nb);
-      mbar_wait_parity(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int row = mb * TC_BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       float* crow = p.C + (long long)row * p.ldc;
-#pragma unroll 1
-      for (int ch = 0; ch < TC_BN / 32; ++ch) {
-        float v[32];
-        const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * TC_BN + ch * 32);
-        tmem_ld_32x32(taddr, v);
-        const int n0 = nb * TC_BN + ch * 32;
-        if (row_ok) {
+      float sum[TC_BN];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float o[4];
+      for (int j = 0; j < TC_BN; ++j) sum[j] = 0.f;
+      const int nchunks = (kblocks + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait_parity(&tfull[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int n = n0 + j + e;
-              const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
-              o[e] = apply_act(v[j + e] + bb, p.act);
-            }
-            if (n0 + j + 3 < p.N) {
-              *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+          float v[32];
+          const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * TC_BN + ch * 32);
+          tmem_ld_32x32(taddr, v);
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (n0 + j + e < p.N) crow[n0 + j + e] = o[e];
-            }
-          }
+          for (int j = 0; j < 32; ++j) sum[ch * 32 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+      if (row_ok) {
+        const int n0 = nb * TC_BN;
+#pragma unroll
+        for (int j = 0; j < TC_BN; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int n = n0 + j + e;
+            const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+            o[e] = apply_act(sum[j + e] + bb, p.act);
+          }
+          if (n0 + j + 3 < p.N) {
+            *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n0 + j + e < p.N) crow[n0 + j + e] = o[e];
+          }
+        }
       }
     }
   }

@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops, packing
+from . import lstm_engine, ops, packing
 from .param_tree import bn_rows, build_param_tree, lstm_rows
 
 
@@ -44,6 +44,7 @@ class lstm_net(nn.Module):
             P[f"l{l + 1}"] = packing.pack_lstm_layer(sd[f"lstm2.weight_ih_l{l}"], sd[f"lstm2.weight_hh_l{l}"],
                                                      sd[f"lstm2.bias_ih_l{l}"], sd[f"lstm2.bias_hh_l{l}"])
         P["fc_w"] = packing.pad_cols(sd["fc.0.weight"].t().contiguous())
+        P["fc_hi"], P["fc_lo"] = packing.split_tf32(sd["fc.0.weight"].contiguous())   # [161, 1024] K-major
         P["fc_b"] = sd["fc.0.bias"].contiguous()
         self._packed = P
 
@@ -71,11 +72,13 @@ class lstm_net(nn.Module):
         assert f == self.N_BINS
         seq = x.view(b * t, f)
         for l in range(3):
-            wih, bih, whh = P[f"l{l}"]
-            xp = ops.linear(seq, wih, bih, 4096)
-            hs = ops.lstm_seq(xp.view(b, t, 4096), whh, 1024)
+            hs = lstm_engine.lstm_layer(seq, P[f"l{l}"], b, t)
             seq = hs.view(b * t, 1024)
             if taps is not None:
                 taps[f"h{l}"] = hs
-        y = ops.linear(seq, P["fc_w"], P["fc_b"], 161, act="softplus")
+        if lstm_engine.USE_TENSOR_CORES and seq.shape[0] >= 128:
+            a_hi, a_lo = ops.split_tf32(seq)
+            y = ops.gemm_tf32x3(a_hi, a_lo, P["fc_hi"], P["fc_lo"], P["fc_b"], 161, act="softplus")
+        else:
+            y = ops.linear(seq, P["fc_w"], P["fc_b"], 161, act="softplus")
         return y.view(b, t, 161)

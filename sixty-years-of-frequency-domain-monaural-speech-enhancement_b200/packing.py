@@ -75,8 +75,19 @@ def slice_rows(hidden, unit_perm=None):
     return (g + u).reshape(-1)                             # [S*4*8]
 
 
+def split_tf32(x):
+    """x -> (hi, lo) with hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand format of the 3xTF32
+    tensor-core GEMM (csrc/gemm_tc.cu).  Bit arithmetic = cvt.rna.tf32.f32 (nearest, ties away)."""
+    def rna(v):
+        return ((v.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    hi = rna(x)
+    return hi, rna(x - hi)
+
+
 def pack_lstm_layer(w_ih, w_hh, b_ih, b_hh, in_perm=None, unit_perm=None, in_scale=None, in_shift=None):
-    """Returns (Wih [I, 4H] K-major slice-ordered cols, bias [4H], Whh [H/8, H, 32]).
+    """Returns a dict: wih_kn [I, 4H] (K-major, for the fp32 FMA GEMM), wih_hi / wih_lo [4H, I]
+    (TF32 split, for the tensor-core GEMM), bias [4H], whh [H/8, H, 32], hidden.
+    Gate columns / rows are in slice order (see slice_rows).
 
     in_perm:  new input index -> reference input index (when the producer's layout differs)
     unit_perm: new hidden-unit index -> reference unit index (to emit h in a consumer's layout)
@@ -96,4 +107,7 @@ def pack_lstm_layer(w_ih, w_hh, b_ih, b_hh, in_perm=None, unit_perm=None, in_sca
         wh = wh[:, unit_perm]
     s = hidden // HU
     whp = wh.reshape(s, 4 * HU, hidden).permute(0, 2, 1).contiguous()
-    return pad_cols(wi.t().contiguous()), bias.contiguous(), whp
+    wi = wi.contiguous()
+    hi, lo = split_tf32(wi)
+    return {"wih_kn": pad_cols(wi.t().contiguous()), "wih_hi": hi, "wih_lo": lo, "bias": bias.contiguous(),
+            "whh": whp, "hidden": hidden}

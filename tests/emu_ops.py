@@ -84,6 +84,18 @@ def lstm_seq(xproj, whh, hidden, out=None):
     return torch.stack(outs, dim=1)
 
 
+def split_tf32(x):
+    from se_b200 import packing
+    return packing.split_tf32(x)
+
+
+def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, n_out, act="none", out=None):
+    y = (a_hi + a_lo) @ (b_hi + b_lo).t()
+    if bias is not None:
+        y = y + bias
+    return _act(y, act)
+
+
 def install(ops_module, monkeypatch):
-    for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq"):
+    for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3"):
         monkeypatch.setattr(ops_module, name, globals()[name])
