@@ -195,6 +195,39 @@ int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const fl
                    long long ldb, int M, int N, int K, const float* bias, int act, float* C, long long ldc,
                    se_stream_t stream);
 
+/* One LSTM time step for MANY independent sequences, fused on the tensor cores:
+ *     gates[M, 4H] = [x_t | h_{t-1}] * W^T + bias ;  c, h updated in the GEMM epilogue.
+ *     FullSubNet's sub-band model runs B*257 sequences of width 384 (model.py:106-113): the
+ *     per-step contraction is a real GEMM (M = 8224 per GPU), so the recurrence is T launches of
+ *     this kernel instead of a persistent weight-stationary kernel.
+ *     x_hi/x_lo [M, Kx], h_hi/h_lo [M, H] (state in, TF32 split), W hi/lo [4H, Kx+H] K-major with
+ *     rows in TILE order: row j*128 + g*32 + u  <-  gate g (i,f,g,o) of unit 32j+u; bias likewise.
+ *     c_state [M, H] in/out; h_hi_out/h_lo_out [M, H] (must differ from the inputs: other CTAs
+ *     still read h_{t-1}); h_out [M, H] plain fp32 or NULL.  Kx %% 32 == 0, H %% 32 == 0. */
+int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long long ldx, int Kx, const float* h_hi,
+                        const float* h_lo, long long ldh, int H, const float* w_hi, const float* w_lo, long long ldw,
+                        const float* bias, int M, float* c_state, float* h_hi_out, float* h_lo_out, float* h_out,
+                        se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * FullSubNet glue (FullSubNet/fullsubnet_net_sa/model.py:68-118); see csrc/fullsubnet.cu.
+ *   se_fsn_clip_inv_mean: out_inv[b] = 1/((sum_{t<T,f<F} wgt[f]*x[b,t,f] + sum extra[b,:n_extra])/denom + 1e-5)
+ *                         -- offline_laplace_norm (base_model.py:196-209); wgt / extra may be NULL.
+ *   se_fsn_fb_input:      x [B,T,F] (strides) -> mag_tm [B,Tp,F] (zero look-ahead frames, model.py:79)
+ *                         and xn = mag_tm * inv[b] (the full-band model input, model.py:84).
+ *   se_fsn_sb_assemble:   rows [t][b*F+f] of 2n+2 features: reflect-unfolded noisy magnitude
+ *                         (base_model.py:12-42) ++ full-band output, times inv[b], TF32 hi/lo split.
+ *   se_fsn_sb_fc:         out[row][c] = bias[c] + h[row,:] . W[c,:], c in {0,1}  (Linear(384,2)).
+ * ------------------------------------------------------------------------------------- */
+int se_fsn_clip_inv_mean(const float* x, long long sb, long long st, long long sf, int B, int T, int F,
+                         const float* wgt, const float* extra, long long extra_sb, long long n_extra, double denom,
+                         float* out_inv, se_stream_t stream);
+int se_fsn_fb_input(const float* x, long long sb, long long st, long long sf, int B, int T, int Tp, int F,
+                    const float* inv, float* mag_tm, float* xn, se_stream_t stream);
+int se_fsn_sb_assemble(const float* mag_tm, const float* fb, int B, int Tp, int F, int num_neighbors,
+                       const float* inv, float* out_hi, float* out_lo, se_stream_t stream);
+int se_fsn_sb_fc(const float* h, int M, int H, const float* W, const float* bias, float* out, se_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

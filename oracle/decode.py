@@ -51,3 +51,29 @@ def dsp_identity(wav, geometry="fullsubnet"):
     spec = dsp.stft(x.astype(np.float32), n_fft, win, hop)
     y = dsp.istft(spec, n_fft, win, hop, length=len(x))
     return (y / c).astype(np.float32)
+
+
+def enhance_fullsubnet(sd, wav, p=0.5):
+    """``FullSubNet/fullsubnet_sa_decode.py:44-78`` (torch dialect, complex mask applied in the
+    script on the COMPRESSED spectrum, backend rule (iii); p = 0.5 for the cprs checkpoint the
+    script loads at :25, 1.0 for the noncprs twin)."""
+    from . import nets as _n
+    n_fft, win, hop = dsp.GEOMETRIES["fullsubnet"]
+    x, c = dsp.rms_scale(wav)                                               # :46-47
+    x32 = x.astype(np.float32)                                              # :52 FloatTensor
+    spec = dsp.stft(x32, n_fft, win, hop)                                   # :53  [F,T] complex64
+    mag = np.abs(spec) ** p                                                 # :57
+    ph = np.angle(spec)                                                     # :58
+    xr, xi = mag * np.cos(ph), mag * np.sin(ph)                             # :59
+    feat_mag = np.sqrt(xr ** 2 + xi ** 2).astype(np.float32)                # :61
+    with torch.no_grad():
+        m = _n.fullsubnet_forward(sd, torch.from_numpy(feat_mag)[None, None]).squeeze(0).numpy()   # :63
+    er = m[0] * xr - m[1] * xi                                              # :66
+    ei = m[0] * xi + m[1] * xr                                              # :67
+    emag = np.sqrt(er ** 2 + ei ** 2) ** (1.0 / p)                          # :71
+    eph = np.arctan2(ei, er)                                                # :72
+    est = emag * np.cos(eph) + 1j * emag * np.sin(eph)                      # :73
+    y = dsp.istft(est.astype(np.complex64), n_fft, win, hop, length=len(x)) # :76
+    y = y / c                                                               # :78
+    taps = {"c": c, "mag": feat_mag, "mask": m, "y_norm": (y * c).astype(np.float32)}
+    return y.astype(np.float32), taps

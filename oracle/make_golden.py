@@ -33,6 +33,47 @@ CASES = [
 ]
 
 
+FSN_ARGS = dict(sb_num_neighbors=15, fb_num_neighbors=0, num_freqs=257, look_ahead=2, sequence_model="LSTM",
+                fb_output_activate_function="ReLU", sb_output_activate_function=None, fb_model_hidden_size=512,
+                sb_model_hidden_size=384, weight_init=False, norm_type="offline_laplace_norm",
+                num_groups_in_drop_band=2)     # FullSubNet/fullsubnet_sa_decode.py:11-24
+
+FSN_CASES = [
+    ("fullsubnet_synth", None, 8192, (4, 5)),
+    ("fullsubnet_ckpt", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth", 16000, (4, 5)),
+]
+
+
+def make_fullsubnet():
+    mod = ref_shims.import_reference("FullSubNet", "fullsubnet_net_sa.model")
+    for name, ckpt, nsamp, clip_ids in FSN_CASES:
+        net = mod.Model(**FSN_ARGS).eval()
+        if ckpt is None:
+            sd = synth.synthetic_state_dict(templates.fullsubnet_template(), seed=0)
+        else:
+            sd = torch.load(ref_shims.checkpoint_path("FullSubNet", ckpt), map_location="cpu")
+        net.load_state_dict(sd)
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp)}
+        worst = 0.0
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = decode.enhance_fullsubnet(sd, wav.astype(np.float64))
+            with torch.no_grad():     # B = 1, exactly as the script calls it (no drop_band)
+                mask_ref = net(torch.from_numpy(taps["mag"])[None, None]).squeeze(0).numpy()
+            worst = max(worst, float(np.abs(mask_ref - taps["mask"]).max()))
+            rec[f"wav{j}"] = wav
+            rec[f"mag{j}"] = taps["mag"]
+            rec[f"mask{j}"] = mask_ref.astype(np.float32)
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        rec["ref_vs_oracle"] = np.array(worst)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: ref_vs_oracle max-abs {worst:.3e}, out rms "
+              f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def sd_digest(sd) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
@@ -75,4 +116,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) < 2 or sys.argv[1] == "mag":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "fullsubnet":
+        make_fullsubnet()

@@ -118,3 +118,53 @@ def lstm_net_forward(sd, x, taps=None):
         taps["lstm2"] = x
     x = F.softplus(F.linear(x, sd["fc.0.weight"], sd["fc.0.bias"]))
     return x
+
+
+# ----------------------------------------------------------------------------------------
+# FullSubNet  (FullSubNet/fullsubnet_net_sa/model.py)
+# ----------------------------------------------------------------------------------------
+def _fsn_unfold(x, num_neighbor):
+    """BaseModel.unfold, base_model.py:12-42.  x [B,1,F,T] -> [B,F,2n+1,T] (reflect pad on F)."""
+    b, _, f, t = x.shape
+    if num_neighbor < 1:
+        return x.permute(0, 2, 1, 3).reshape(b, f, 1, t)
+    p = F.pad(x, [0, 0, num_neighbor, num_neighbor], mode="reflect")        # [B,1,F+2n,T]
+    idx = torch.arange(f)[:, None] + torch.arange(2 * num_neighbor + 1)[None, :]   # [F, 2n+1]
+    return p[:, 0][:, idx]                                                   # [B,F,2n+1,T]
+
+
+def _fsn_norm(x):
+    """offline_laplace_norm, base_model.py:196-209: divide by the utterance mean (+1e-5)."""
+    mu = torch.mean(x, dim=(1, 2, 3), keepdim=True)
+    return x / (mu + 1e-5)
+
+
+def _fsn_sequence(sd, prefix, x, act):
+    """SequenceModel.forward, sequence_model.py:66-84.  x [N,F,T] -> [N,Fo,T]."""
+    o = lstm(x.permute(0, 2, 1).contiguous(), sd, prefix + ".sequence_model", 2)
+    o = F.linear(o, sd[prefix + ".fc_output_layer.weight"], sd[prefix + ".fc_output_layer.bias"])
+    if act == "relu":
+        o = F.relu(o)
+    return o.permute(0, 2, 1).contiguous()
+
+
+def fullsubnet_forward(sd, noisy_mag, look_ahead=2, sb_num_neighbors=15, fb_num_neighbors=0, taps=None):
+    """Model.forward, model.py:68-118, with PER-UTTERANCE semantics: the reference decodes one
+    file at a time (B=1), where the ``if batch_size > 1: drop_band`` branch (model.py:101-104)
+    never runs; a batched oracle must therefore skip it.
+    noisy_mag [B,1,257,T] -> complex mask [B,2,257,T]."""
+    x = F.pad(noisy_mag, [0, look_ahead])                                    # model.py:79
+    b, c, f, t = x.shape
+    fb_in = _fsn_norm(x).reshape(b, c * f, t)                                # :84
+    fb_out = _fsn_sequence(sd, "fb_model", fb_in, "relu").reshape(b, 1, f, t)   # :85
+    if taps is not None:
+        taps["fb_out"] = fb_out
+    fb_unf = _fsn_unfold(fb_out, fb_num_neighbors)                           # :88-89
+    nm_unf = _fsn_unfold(x, sb_num_neighbors)                                # :92-93
+    sb_in = _fsn_norm(torch.cat([nm_unf, fb_unf], dim=2))                    # :96-97
+    if taps is not None:
+        taps["sb_in"] = sb_in
+    sb_in = sb_in.reshape(b * f, sb_in.shape[2], t)                          # :106-110
+    mask = _fsn_sequence(sd, "sb_model", sb_in, None)                        # :113
+    mask = mask.reshape(b, f, 2, t).permute(0, 2, 1, 3).contiguous()         # :114
+    return mask[:, :, :, look_ahead:]                                        # :117

@@ -71,8 +71,10 @@ def import_reference(model_dir: str, module: str):
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     _install_stubs()
     path = os.path.join(REFERENCE_ROOT, model_dir)
-    for name in _COLLIDING + [module]:
-        sys.modules.pop(name, None)
+    top = module.split(".")[0]
+    for name in list(sys.modules):
+        if name in _COLLIDING or name == top or name.startswith(top + "."):
+            sys.modules.pop(name, None)
     sys.path.insert(0, path)
     try:
         with _scratch_cwd():
@@ -80,9 +82,9 @@ def import_reference(model_dir: str, module: str):
     finally:
         sys.path.remove(path)
     # leave no colliding names behind for the next import
-    for name in _COLLIDING:
-        sys.modules.pop(name, None)
-    sys.modules.pop(module, None)
+    for name in list(sys.modules):
+        if name in _COLLIDING or name == top or name.startswith(top + "."):
+            sys.modules.pop(name, None)
     return mod
 
 

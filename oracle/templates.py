@@ -42,3 +42,13 @@ def lstm_template():
     d["fc.0.weight"] = (161, 1024)
     d["fc.0.bias"] = (161,)
     return d
+
+
+def fullsubnet_template():
+    d = _lstm("fb_model.sequence_model", 257, 512, 2)
+    d["fb_model.fc_output_layer.weight"] = (257, 512)
+    d["fb_model.fc_output_layer.bias"] = (257,)
+    d.update(_lstm("sb_model.sequence_model", 32, 384, 2))
+    d["sb_model.fc_output_layer.weight"] = (2, 384)
+    d["sb_model.fc_output_layer.bias"] = (2,)
+    return d

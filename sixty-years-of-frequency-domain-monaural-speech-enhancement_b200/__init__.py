@@ -7,5 +7,6 @@ Package directory name follows the build contract
 from . import _lib, ops, packing, lstm_engine, decode, shard   # noqa: F401
 from .crn import crn_net                   # noqa: F401
 from .lstm import lstm_net                 # noqa: F401
+from . import fullsubnet                   # noqa: F401
 
-__all__ = ["crn_net", "lstm_net", "ops", "decode", "packing", "shard"]
+__all__ = ["crn_net", "lstm_net", "fullsubnet", "ops", "decode", "packing", "shard"]

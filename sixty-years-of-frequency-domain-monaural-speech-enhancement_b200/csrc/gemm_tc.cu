@@ -12,7 +12,8 @@
 // Structure (one CTA per SM, persistent over output tiles):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d, SWIZZLE_128B tiles, mbarrier tx
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
-//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns), bias + activation, st.global
+//   warps 2-9: epilogue      -- tcgen05.ld (32 lanes x 64 columns each: 4 lane quarters x 2 column
+//                              halves), fp32 promotion, bias + activation / LSTM cell, st.global
 //   smem ring: STAGES x {A_hi, A_lo, B_hi, B_lo} tiles of 128 rows x 32 fp32 (128-byte rows)
 //   TMEM     : 2 accumulators of 128 lanes x 128 columns, used as a ping-pong over K-CHUNKS:
 //              the tensor core's fp32 accumulate truncates (measured: error grows linearly with
@@ -30,7 +31,9 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_CHUNK_KB = 4;                              // k-blocks (of 32) per TMEM accumulation chunk
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;           // 16 KB (same for A and B tiles)
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                            // 2 control warps + 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_COLS = TC_BN / 2;                     // columns per epilogue warp
 constexpr int TC_TMEM_COLS = 256;                          // 2 x 128-column accumulators
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -109,6 +112,29 @@ __device__ __forceinline__ void tmem_ld_32x32(unsigned taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld_32x64(unsigned taddr, float (&v)[64]) {
+  unsigned r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO),
 // LBO is unused for swizzled K-major layouts (1, as CUTLASS sets it); version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
@@ -123,17 +149,29 @@ constexpr unsigned make_idesc_tf32(int m, int n) {
          | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
 
+enum { EPI_BIAS_ACT = 0, EPI_LSTM_CELL = 1 };
+
 struct TcParams {
-  int M, N, K;
+  int M, N;
+  int kb0, kb1;  // k-blocks (of 32) taken from A source 0 / A source 1  (A = [A0 | A1] along K)
   const float* bias;
   int act;
-  float* C;
+  float* C;      // EPI_BIAS_ACT: output [M, ldc]
   long long ldc;
-  int panel_m;  // m-blocks per L2 panel
+  int panel_m;   // m-blocks per L2 panel
+  // EPI_LSTM_CELL: N = 4H, column tile j holds units [32j, 32j+32): two 64-column halves, each
+  // [i | f | g | o] x 16 units  (column j*128 + hf*64 + g*16 + u  <-  gate g of unit 32j + 16hf + u)
+  float* c_state;   // [M, H] in/out
+  float* h_hi;      // [M, H] out: rna_tf32(h)
+  float* h_lo;      // [M, H] out: rna_tf32(h - h_hi)
+  float* h_out;     // [M, H] out (plain fp32) or NULL
+  int H;
 };
 
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
+                   const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                    const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -149,7 +187,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mblocks = ceil_div(p.M, TC_BM), nblocks = ceil_div(p.N, TC_BN);
   const int ntiles = mblocks * nblocks;
-  const int kblocks = p.K / TC_BK;
+  const int kblocks = p.kb0 + p.kb1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -158,11 +196,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[a], TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
-    tma_prefetch_desc(&map_ahi);
-    tma_prefetch_desc(&map_alo);
+    tma_prefetch_desc(&map_a0hi);
+    tma_prefetch_desc(&map_a0lo);
     tma_prefetch_desc(&map_bhi);
     tma_prefetch_desc(&map_blo);
   }
@@ -194,8 +232,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           mbar_wait_parity(&empty[stage], phase ^ 1);
           unsigned char* st = tiles + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
-          tma_load_2d(&map_ahi, &full[stage], st + 0 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
-          tma_load_2d(&map_alo, &full[stage], st + 1 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
+          if (kb < p.kb0) {
+            tma_load_2d(&map_a0hi, &full[stage], st + 0 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
+            tma_load_2d(&map_a0lo, &full[stage], st + 1 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
+          } else {
+            tma_load_2d(&map_a1hi, &full[stage], st + 0 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, mb * TC_BM);
+            tma_load_2d(&map_a1lo, &full[stage], st + 1 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, mb * TC_BM);
+          }
           tma_load_2d(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
           tma_load_2d(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
           if (++stage == TC_STAGES) {
@@ -252,7 +295,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int quarter = warp & 3;  // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
+    const int quarter = warp & 3;        // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
+    const int half = (warp - 2) >> 2;    // which 64 columns of the 128-column accumulator
     int acc = 0;
     unsigned acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -260,21 +304,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
       tile_coords(tile, mb, nb);
       const int row = mb * TC_BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      float* crow = p.C + (long long)row * p.ldc;
-      float sum[TC_BN];
+      float sum[TC_EPI_COLS];
 #pragma unroll
-      for (int j = 0; j < TC_BN; ++j) sum[j] = 0.f;
+      for (int j = 0; j < TC_EPI_COLS; ++j) sum[j] = 0.f;
       const int nchunks = (kblocks + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait_parity(&tfull[acc], acc_phase);
         tc_fence_after();
+        {
+          float v[TC_EPI_COLS];
+          const unsigned taddr =
+              tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * TC_BN + half * TC_EPI_COLS);
+          tmem_ld_32x64(taddr, v);
 #pragma unroll
-        for (int ch = 0; ch < TC_BN / 32; ++ch) {
-          float v[32];
-          const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * TC_BN + ch * 32);
-          tmem_ld_32x32(taddr, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sum[ch * 32 + j] += v[j];
+          for (int j = 0; j < TC_EPI_COLS; ++j) sum[j] += v[j];
         }
         tc_fence_before();
         __syncwarp();
@@ -284,10 +327,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           acc_phase ^= 1;
         }
       }
-      if (row_ok) {
-        const int n0 = nb * TC_BN;
+      if (!row_ok) continue;
+      const int n0 = nb * TC_BN + half * TC_EPI_COLS;
+      if constexpr (EPI == EPI_BIAS_ACT) {
+        float* crow = p.C + (long long)row * p.ldc;
+        const bool vec = (p.ldc & 3) == 0;
 #pragma unroll
-        for (int j = 0; j < TC_BN; j += 4) {
+        for (int j = 0; j < TC_EPI_COLS; j += 4) {
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -295,13 +341,42 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
             o[e] = apply_act(sum[j + e] + bb, p.act);
           }
-          if (n0 + j + 3 < p.N) {
+          if (vec && n0 + j + 3 < p.N) {
             *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (n0 + j + e < p.N) crow[n0 + j + e] = o[e];
           }
+        }
+      } else {
+        // fused LSTM cell: this thread holds all four gates of 16 hidden units of sequence `row`
+        const long long off = (long long)row * p.H + nb * 32 + half * 16;
+        const float* bias = p.bias + n0;
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) {
+          const float4 cold = *reinterpret_cast<const float4*>(p.c_state + off + u);
+          const float co[4] = {cold.x, cold.y, cold.z, cold.w};
+          float cn[4], hn[4], hh[4], hl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float ig = sigmoid_f(sum[u + e] + __ldg(bias + u + e));
+            const float fg = sigmoid_f(sum[16 + u + e] + __ldg(bias + 16 + u + e));
+            const float gg = tanhf(sum[32 + u + e] + __ldg(bias + 32 + u + e));
+            const float og = sigmoid_f(sum[48 + u + e] + __ldg(bias + 48 + u + e));
+            cn[e] = fg * co[e] + ig * gg;
+            hn[e] = og * tanhf(cn[e]);
+            unsigned hb, lb;
+            asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hb) : "f"(hn[e]));
+            hh[e] = __uint_as_float(hb);
+            const float r = hn[e] - hh[e];
+            asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lb) : "f"(r));
+            hl[e] = __uint_as_float(lb);
+          }
+          *reinterpret_cast<float4*>(p.c_state + off + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(p.h_hi + off + u) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<float4*>(p.h_lo + off + u) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+          if (p.h_out) *reinterpret_cast<float4*>(p.h_out + off + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
         }
       }
     }
@@ -386,32 +461,92 @@ extern "C" int se_split_tf32(const float* x, float* hi, float* lo, long long n, 
   return check_launch("se_split_tf32");
 }
 
+static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long lda0, int K0, const float* a1_hi,
+                     const float* a1_lo, long long lda1, int K1, const float* b_hi, const float* b_lo, long long ldb,
+                     TcParams p, cudaStream_t stream) {
+  CUtensorMap m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo;
+  int rc;
+  if ((rc = make_map(&m_a0hi, a0_hi, p.M, K0, lda0))) return rc;
+  if ((rc = make_map(&m_a0lo, a0_lo, p.M, K0, lda0))) return rc;
+  if (K1 > 0) {
+    if ((rc = make_map(&m_a1hi, a1_hi, p.M, K1, lda1))) return rc;
+    if ((rc = make_map(&m_a1lo, a1_lo, p.M, K1, lda1))) return rc;
+  } else {
+    m_a1hi = m_a0hi;
+    m_a1lo = m_a0lo;
+  }
+  if ((rc = make_map(&m_bhi, b_hi, p.N, K0 + K1, ldb))) return rc;
+  if ((rc = make_map(&m_blo, b_lo, p.N, K0 + K1, ldb))) return rc;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int mblocks = ceil_div(p.M, TC_BM), nblocks = ceil_div(p.N, TC_BN);
+  p.kb0 = K0 / TC_BK;
+  p.kb1 = K1 / TC_BK;
+  p.panel_m = min(16, mblocks);
+  const int grid = min(sms, mblocks * nblocks);
+  cudaError_t e;
+  if (epi == EPI_BIAS_ACT) {
+    e = cudaFuncSetAttribute(gemm_tf32x3_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e == cudaSuccess)
+      gemm_tf32x3_kernel<EPI_BIAS_ACT><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p);
+  } else {
+    e = cudaFuncSetAttribute(gemm_tf32x3_kernel<EPI_LSTM_CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e == cudaSuccess)
+      gemm_tf32x3_kernel<EPI_LSTM_CELL><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p);
+  }
+  if (e != cudaSuccess) {
+    set_error("tcgen05 gemm: smem attribute: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
 extern "C" int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const float* b_hi,
                               const float* b_lo, long long ldb, int M, int N, int K, const float* bias, int act,
                               float* C, long long ldc, se_stream_t stream) {
   SE_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "se_gemm_tf32x3: null pointer");
   SE_REQUIRE(M > 0 && N > 0 && K > 0 && K % TC_BK == 0, "se_gemm_tf32x3: K=%d must be a multiple of %d", K, TC_BK);
-  SE_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (ldc & 3) == 0, "se_gemm_tf32x3: leading dims must be %% 4");
-  SE_REQUIRE(((((uintptr_t)a_hi) | ((uintptr_t)a_lo) | ((uintptr_t)b_hi) | ((uintptr_t)b_lo) | ((uintptr_t)C)) & 15) == 0,
+  SE_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "se_gemm_tf32x3: operand leading dims must be %% 4");
+  SE_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && (((uintptr_t)C) & 3) == 0,
              "se_gemm_tf32x3: pointers must be 16-byte aligned");
-  CUtensorMap m_ahi, m_alo, m_bhi, m_blo;
-  int rc;
-  if ((rc = make_map(&m_ahi, a_hi, M, K, lda))) return rc;
-  if ((rc = make_map(&m_alo, a_lo, M, K, lda))) return rc;
-  if ((rc = make_map(&m_bhi, b_hi, N, K, ldb))) return rc;
-  if ((rc = make_map(&m_blo, b_lo, N, K, ldb))) return rc;
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int mblocks = ceil_div(M, TC_BM), nblocks = ceil_div(N, TC_BN);
-  TcParams p{M, N, K, bias, act, C, ldc, 16};
-  if (p.panel_m > mblocks) p.panel_m = mblocks;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (e != cudaSuccess) {
-    set_error("se_gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
-    return SE_ERR_CUDA;
-  }
-  const int grid = min(sms, mblocks * nblocks);
-  gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(m_ahi, m_alo, m_bhi, m_blo, p);
+  TcParams p{};
+  p.M = M;
+  p.N = N;
+  p.bias = bias;
+  p.act = act;
+  p.C = C;
+  p.ldc = ldc;
+  int rc = launch_tc(EPI_BIAS_ACT, a_hi, a_lo, lda, K, nullptr, nullptr, 0, 0, b_hi, b_lo, ldb, p, (cudaStream_t)stream);
+  if (rc) return rc;
   return check_launch("se_gemm_tf32x3");
+}
+
+extern "C" int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long long ldx, int Kx, const float* h_hi,
+                                   const float* h_lo, long long ldh, int H, const float* w_hi, const float* w_lo,
+                                   long long ldw, const float* bias, int M, float* c_state, float* h_hi_out,
+                                   float* h_lo_out, float* h_out, se_stream_t stream) {
+  SE_REQUIRE(x_hi && x_lo && h_hi && h_lo && w_hi && w_lo && bias && c_state && h_hi_out && h_lo_out,
+             "se_lstm_cell_tf32x3: null pointer");
+  SE_REQUIRE(M > 0 && Kx > 0 && Kx % TC_BK == 0 && H > 0 && H % 32 == 0, "se_lstm_cell_tf32x3: Kx=%d H=%d (%%32)", Kx, H);
+  SE_REQUIRE((ldx & 3) == 0 && (ldh & 3) == 0 && (ldw & 3) == 0, "se_lstm_cell_tf32x3: leading dims must be %% 4");
+  SE_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(h_hi) && aligned16(h_lo) && aligned16(w_hi) &&
+                 aligned16(w_lo) && aligned16(c_state) && aligned16(h_hi_out) && aligned16(h_lo_out) &&
+                 (!h_out || aligned16(h_out)),
+             "se_lstm_cell_tf32x3: pointers must be 16-byte aligned");
+  SE_REQUIRE(h_hi != h_hi_out && h_lo != h_lo_out, "se_lstm_cell_tf32x3: state must be double buffered");
+  TcParams p{};
+  p.M = M;
+  p.N = 4 * H;
+  p.bias = bias;
+  p.c_state = c_state;
+  p.h_hi = h_hi_out;
+  p.h_lo = h_lo_out;
+  p.h_out = h_out;
+  p.H = H;
+  int rc = launch_tc(EPI_LSTM_CELL, x_hi, x_lo, ldx, Kx, h_hi, h_lo, ldh, H, w_hi, w_lo, ldw, p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return check_launch("se_lstm_cell_tf32x3");
 }

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import ISTFT_MAG_PHASE
+from ._lib import ISTFT_CMASK, ISTFT_MAG_PHASE
 
 GEOM_320 = (320, 320, 160)   # LSTM/config.py:4-6, CRN/config.py:4-6
 
@@ -50,6 +50,33 @@ def enhance_crn(model, wav, p=1.0, taps=None):
 
 def enhance_lstm(model, wav, p=1.0, taps=None):
     return enhance_mag_mapping(model, wav, p=p, taps=taps)
+
+
+GEOM_FULLSUBNET = (512, 512, 256)   # FullSubNet/fullsubnet_sa_decode.py:53
+
+
+@torch.no_grad()
+def enhance_fullsubnet(model, wav, p=0.5, taps=None):
+    """FullSubNet/fullsubnet_sa_decode.py:44-78: |X|^p magnitude in, complex mask out, mask applied
+    to the COMPRESSED spectrum, decompressed, iSTFT(length=N), / c  (backend rule (iii)).
+    wav [B,N] float32 CUDA -> [B,N]."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    n_fft, win, hop = GEOM_FULLSUBNET
+    wav = wav.contiguous().float()
+    b, n = wav.shape
+    t, f = 1 + n // hop, n_fft // 2 + 1
+    c, inv_c = ops.rms_scale(wav)
+    mag = torch.empty(b, 1, f, t, device=wav.device, dtype=torch.float32)     # [B,1,F,T] as the script feeds
+    spec = torch.empty(b, 2, f, t, device=wav.device, dtype=torch.float32)    # uncompressed X
+    ops.stft(wav, c, n_fft, win, hop, mag=mag[:, 0], re=spec[:, 0], im=spec[:, 1], layout="bft", p_mag=p)
+    mask = model(mag)                                                          # [B,2,F,T] (strided view)
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_CMASK, mask[:, 0], mask[:, 1], spec[:, 0], spec[:, 1], n_fft, win, hop, out, n,
+              out_scale=inv_c, inv_p=1.0 / p, p_x=p, layout_a="bft", layout_b="bft")
+    if taps is not None:
+        taps.update(c=c, mag=mag, mask=mask)
+    return out
 
 
 @torch.no_grad()

@@ -244,3 +244,63 @@ def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, n_out, act="none", out=None):
                                          b_hi.stride(0), m, n, k, _ptr(bias), ACT[act], _ptr(out), out.stride(0),
                                          _stream()), "se_gemm_tf32x3")
     return out
+
+
+def lstm_cell_tf32x3(x_hi, x_lo, h_hi, h_lo, w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out=None):
+    """One fused LSTM step for M independent sequences (see se_lstm_cell_tf32x3 in the header)."""
+    _need_cuda(x_hi, x_lo, h_hi, h_lo, w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out)
+    device_check()
+    m, kx = x_hi.shape
+    hdim = h_hi.shape[1]
+    assert w_hi.shape == (4 * hdim, kx + hdim) and x_hi.stride(1) == 1 and h_hi.stride(1) == 1
+    assert c_state.is_contiguous() and h_hi_out.is_contiguous() and h_lo_out.is_contiguous()
+    with _Timed("lstm_cell_tf32x3"):
+        check(_lib.load().se_lstm_cell_tf32x3(_ptr(x_hi), _ptr(x_lo), x_hi.stride(0), kx, _ptr(h_hi), _ptr(h_lo),
+                                              h_hi.stride(0), hdim, _ptr(w_hi), _ptr(w_lo), w_hi.stride(0),
+                                              _ptr(bias), m, _ptr(c_state), _ptr(h_hi_out), _ptr(h_lo_out),
+                                              _ptr(h_out), _stream()), "se_lstm_cell_tf32x3")
+
+
+# ---- FullSubNet glue ----------------------------------------------------------------------------
+def fsn_clip_inv_mean(x, strides, B, T, F, denom, wgt=None, extra=None):
+    _need_cuda(x, wgt, extra)
+    device_check()
+    sb, st, sf = strides
+    out = torch.empty(B, device=x.device, dtype=torch.float32)
+    esb = extra.stride(0) if extra is not None else 0
+    ne = extra[0].numel() if extra is not None else 0
+    with _Timed("fsn_clip_inv_mean"):
+        check(_lib.load().se_fsn_clip_inv_mean(_ptr(x), sb, st, sf, B, T, F, _ptr(wgt), _ptr(extra), esb, ne,
+                                               float(denom), _ptr(out), _stream()), "se_fsn_clip_inv_mean")
+    return out
+
+
+def fsn_fb_input(x, strides, B, T, Tp, F, inv):
+    _need_cuda(x, inv)
+    sb, st, sf = strides
+    mag_tm = torch.empty(B, Tp, F, device=x.device, dtype=torch.float32)
+    xn = torch.empty_like(mag_tm)
+    with _Timed("fsn_fb_input"):
+        check(_lib.load().se_fsn_fb_input(_ptr(x), sb, st, sf, B, T, Tp, F, _ptr(inv), _ptr(mag_tm), _ptr(xn),
+                                          _stream()), "se_fsn_fb_input")
+    return mag_tm, xn
+
+
+def fsn_sb_assemble(mag_tm, fb, nn, inv):
+    _need_cuda(mag_tm, fb, inv)
+    B, Tp, F = mag_tm.shape
+    w = 2 * nn + 2
+    hi = torch.empty(Tp, B * F, w, device=mag_tm.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    with _Timed("fsn_sb_assemble"):
+        check(_lib.load().se_fsn_sb_assemble(_ptr(mag_tm), _ptr(fb), B, Tp, F, nn, _ptr(inv), _ptr(hi), _ptr(lo),
+                                             _stream()), "se_fsn_sb_assemble")
+    return hi, lo
+
+
+def fsn_sb_fc(h, W, bias, out):
+    _need_cuda(h, W, bias, out)
+    m, hd = h.shape
+    with _Timed("fsn_sb_fc"):
+        check(_lib.load().se_fsn_sb_fc(_ptr(h), m, hd, _ptr(W), _ptr(bias), _ptr(out), _stream()), "se_fsn_sb_fc")
+    return out

@@ -111,3 +111,27 @@ def pack_lstm_layer(w_ih, w_hh, b_ih, b_hh, in_perm=None, unit_perm=None, in_sca
     hi, lo = split_tf32(wi)
     return {"wih_kn": pad_cols(wi.t().contiguous()), "wih_hi": hi, "wih_lo": lo, "bias": bias.contiguous(),
             "whh": whp, "hidden": hidden}
+
+
+def tile_rows(hidden):
+    """Row permutation for the fused cell GEMM (csrc/gemm_tc.cu EPI_LSTM_CELL): output column
+    j*128 + hf*64 + g*16 + u  <-  torch gate row g*H + 32j + 16hf + u   (u < 16)."""
+    j = torch.arange(hidden // 32).view(-1, 1, 1, 1)
+    hf = torch.arange(2).view(1, 2, 1, 1)
+    g = torch.arange(4).view(1, 1, 4, 1)
+    u = torch.arange(16).view(1, 1, 1, 16)
+    return (g * hidden + 32 * j + 16 * hf + u).reshape(-1)
+
+
+def pack_lstm_cell(w_ih, w_hh, b_ih, b_hh, kx_pad=None):
+    """[W_ih | W_hh] concatenated along K, rows in tile order, TF32 split.  The input part is zero
+    padded to kx_pad columns (a multiple of 32).  Returns dict(w_hi, w_lo, bias, hidden, kx)."""
+    hidden = w_hh.shape[1]
+    kx = w_ih.shape[1]
+    kx_pad = kx_pad or (kx + 31) // 32 * 32
+    rows = tile_rows(hidden).to(w_ih.device)
+    w = w_ih.new_zeros(4 * hidden, kx_pad + hidden)
+    w[:, :kx] = w_ih[rows]
+    w[:, kx_pad:] = w_hh[rows]
+    hi, lo = split_tf32(w)
+    return {"w_hi": hi, "w_lo": lo, "bias": (b_ih + b_hh)[rows].contiguous(), "hidden": hidden, "kx": kx_pad}

@@ -96,6 +96,59 @@ def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, n_out, act="none", out=None):
     return _act(y, act)
 
 
+def lstm_cell_tf32x3(x_hi, x_lo, h_hi, h_lo, w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out=None):
+    from se_b200 import packing
+    m, kx = x_hi.shape
+    hd = h_hi.shape[1]
+    a = torch.cat([x_hi + x_lo, h_hi + h_lo], dim=1)
+    g = a @ (w_hi + w_lo).t() + bias                       # columns: (tile j, half, gate, 16 units)
+    g = g.view(m, hd // 16, 4, 16)
+    i, f, gg, o = g[:, :, 0], g[:, :, 1], g[:, :, 2], g[:, :, 3]
+    c = torch.sigmoid(f) * c_state.view(m, hd // 16, 16) + torch.sigmoid(i) * torch.tanh(gg)
+    h = (torch.sigmoid(o) * torch.tanh(c)).reshape(m, hd)
+    c_state.copy_(c.reshape(m, hd))
+    hi, lo = packing.split_tf32(h)
+    h_hi_out.copy_(hi)
+    h_lo_out.copy_(lo)
+    if h_out is not None:
+        h_out.copy_(h)
+
+
+def fsn_clip_inv_mean(x, strides, B, T, F, denom, wgt=None, extra=None):
+    sb, st, sf = strides
+    v = torch.as_strided(x, (B, T, F), (sb, st, sf))
+    s = (v * wgt).sum(dim=(1, 2)) if wgt is not None else v.sum(dim=(1, 2))
+    if extra is not None:
+        s = s + extra.reshape(B, -1).sum(dim=1)
+    return 1.0 / (s / denom + 1e-5)
+
+
+def fsn_fb_input(x, strides, B, T, Tp, F, inv):
+    sb, st, sf = strides
+    v = torch.as_strided(x, (B, T, F), (sb, st, sf))
+    mag_tm = torch.zeros(B, Tp, F)
+    mag_tm[:, :T] = v
+    return mag_tm, mag_tm * inv[:, None, None]
+
+
+def fsn_sb_assemble(mag_tm, fb, nn, inv):
+    from se_b200 import packing
+    B, Tp, F = mag_tm.shape
+    idx = torch.arange(F)[:, None] + torch.arange(2 * nn + 1)[None, :] - nn
+    idx = torch.where(idx < 0, -idx, idx)
+    idx = torch.where(idx >= F, 2 * (F - 1) - idx, idx)
+    unf = mag_tm[:, :, idx]                                # [B,Tp,F,31]
+    x = torch.cat([unf, fb[..., None]], dim=-1) * inv[:, None, None, None]
+    x = x.permute(1, 0, 2, 3).reshape(Tp, B * F, 2 * nn + 2).contiguous()
+    return packing.split_tf32(x)
+
+
+def fsn_sb_fc(h, W, bias, out):
+    out.copy_(h @ W.t() + bias)
+    return out
+
+
 def install(ops_module, monkeypatch):
-    for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3"):
+    for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3",
+                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc"):
         monkeypatch.setattr(ops_module, name, globals()[name])

@@ -140,3 +140,40 @@ def test_gemm_tf32x3_fp32_accuracy(m, k, n, act):
                 (a.double() @ w.double().t() + bias.double())).abs().max().item()
     print(f"gemm_tf32x3 {m}x{k}x{n}: max err {err:.3e} (single-pass TF32 would be {one_pass:.3e})")
     assert err < 1e-5
+
+
+@pytest.mark.parametrize("m,kx,h,steps", [(300, 32, 384, 3), (130, 64, 128, 2)])
+def test_lstm_cell_tf32x3_matches_recurrence(m, kx, h, steps):
+    """Fused per-step LSTM cell GEMM (FullSubNet sub-band regime) vs the textbook recurrence."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(m + h)
+    w_ih = torch.randn(4 * h, kx, generator=g) / np.sqrt(kx)
+    w_hh = torch.randn(4 * h, h, generator=g) / np.sqrt(h)
+    b_ih = torch.randn(4 * h, generator=g) * 0.1
+    b_hh = torch.randn(4 * h, generator=g) * 0.1
+    xs = torch.randn(steps, m, kx, generator=g)
+    P = packing.pack_lstm_cell(w_ih, w_hh, b_ih, b_hh)
+    P = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in P.items()}
+    c = torch.zeros(m, h, device=dev)
+    hbuf = [(torch.zeros(m, h, device=dev), torch.zeros(m, h, device=dev)) for _ in range(2)]
+    hout = torch.empty(m, h, device=dev)
+    # reference (float64)
+    hr = torch.zeros(m, h, dtype=torch.float64)
+    cr = torch.zeros(m, h, dtype=torch.float64)
+    for t in range(steps):
+        x_hi, x_lo = ops.split_tf32(xs[t].to(dev))
+        src, dst = hbuf[t & 1], hbuf[(t + 1) & 1]
+        ops.lstm_cell_tf32x3(x_hi, x_lo, src[0], src[1], P["w_hi"], P["w_lo"], P["bias"], c, dst[0], dst[1], hout)
+        gates = xs[t].double() @ w_ih.double().t() + hr @ w_hh.double().t() + (b_ih + b_hh).double()
+        i, f, gg, o = gates.chunk(4, dim=1)
+        cr = torch.sigmoid(f) * cr + torch.sigmoid(i) * torch.tanh(gg)
+        hr = torch.sigmoid(o) * torch.tanh(cr)
+    torch.cuda.synchronize()
+    e_h = (hout.cpu().double() - hr).abs().max().item()
+    e_c = (c.cpu().double() - cr).abs().max().item()
+    e_split = ((dst[0] + dst[1]).cpu().double() - hr).abs().max().item()
+    print(f"lstm_cell M={m} Kx={kx} H={h} steps={steps}: h err {e_h:.3e} c err {e_c:.3e} hi+lo err {e_split:.3e}")
+    assert e_h < 1e-5 and e_c < 1e-5 and e_split < 1e-5

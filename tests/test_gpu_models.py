@@ -113,3 +113,47 @@ def test_full_config_batch64_consistency():
     ys = se_b200.decode.enhance_mag_mapping(model, wav[:4])
     for r in range(16):
         assert (y[4 * r:4 * r + 4] - ys).abs().max().item() < 1e-6
+
+
+FSN_ARGS = dict(num_freqs=257, look_ahead=2, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=15,
+                fb_output_activate_function="ReLU", sb_output_activate_function=None, fb_model_hidden_size=512,
+                sb_model_hidden_size=384)
+
+
+@pytest.mark.parametrize("name,ckpt", [("fullsubnet_synth", None),
+                                       ("fullsubnet_ckpt", "FullSubNet__wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth")])
+def test_fullsubnet_matches_golden(name, ckpt):
+    """Config 4 model: mask vs the unmodified reference module (B=1 semantics) and the decoded
+    waveform vs the restated fullsubnet_sa_decode.py; batched run must equal per-clip runs."""
+    dev = _dev()
+    import se_b200
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if ckpt is None:
+        sd = synth.synthetic_state_dict(templates.fullsubnet_template(), seed=0)
+    else:
+        path = os.path.join(CKPT_DIR, ckpt)
+        if not os.path.exists(path):
+            pytest.skip("checkpoint copy not present")
+        sd = torch.load(path, map_location="cpu")
+    model = se_b200.fullsubnet.Model(**FSN_ARGS)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    k = len(g["clip_ids"])
+    mag = torch.from_numpy(np.stack([g[f"mag{j}"] for j in range(k)]))[:, None].to(dev)     # [B,1,F,T]
+    mask = model(mag).cpu().numpy()
+    ref = np.stack([g[f"mask{j}"] for j in range(k)])
+    e_net = np.abs(mask - ref).max()
+    wav = torch.from_numpy(np.stack([g[f"wav{j}"] for j in range(k)])).to(dev)
+    taps = {}
+    y = se_b200.decode.enhance_fullsubnet(model, wav, p=0.5, taps=taps)
+    c = taps["c"].cpu().numpy()
+    yn = y.cpu().numpy() * c[:, None]
+    refn = np.stack([g[f"ynorm{j}"] for j in range(k)])
+    rms = np.sqrt(np.mean((yn - refn) ** 2, axis=1))
+    rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
+    y1 = se_b200.decode.enhance_fullsubnet(model, wav[1:2], p=0.5)
+    binv = (y[1:2] - y1).abs().max().item()
+    print(f"{name}: mask max-abs {e_net:.3e} (|mask| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
+          f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
+    assert rms.max() <= RMS_GATE and rel.max() <= 2e-3
+    assert binv < 1e-5

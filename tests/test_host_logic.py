@@ -85,6 +85,24 @@ def test_lstm_net_host_logic_matches_oracle(monkeypatch):
     assert (y - yr).abs().max() < 1e-4
 
 
+def test_fullsubnet_host_logic_matches_oracle(monkeypatch):
+    from se_b200.fullsubnet import Model
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t = templates.fullsubnet_template()
+    sd = synth.synthetic_state_dict(t, seed=5)
+    m = Model(num_freqs=257, look_ahead=2, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=15,
+              fb_output_activate_function="ReLU", sb_output_activate_function=None, fb_model_hidden_size=512,
+              sb_model_hidden_size=384)
+    assert list(m.state_dict().keys()) == list(t.keys())
+    m.load_state_dict(sd)
+    x = torch.rand(2, 1, 257, 7, generator=torch.Generator().manual_seed(1)) * 3
+    y = m._forward_impl(x)
+    with torch.no_grad():
+        yr = nets.fullsubnet_forward(sd, x)
+    assert y.shape == yr.shape == (2, 2, 257, 7)
+    assert (y - yr).abs().max() < 2e-4 * max(1.0, yr.abs().max().item())
+
+
 def test_shard_range_partitions():
     from se_b200 import shard
     for b in (1, 7, 64, 256, 513):
