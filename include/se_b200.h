@@ -36,7 +36,8 @@ typedef enum se_act {
   SE_ACT_SOFTPLUS = 2, /* nn.Softplus(beta=1,thr=20)   CRN/CRN.py:102, LSTM/LSTM.py:22 */
   SE_ACT_RELU = 3,
   SE_ACT_SIGMOID = 4,
-  SE_ACT_TANH = 5
+  SE_ACT_TANH = 5,
+  SE_ACT_PRELU = 6     /* nn.PReLU() with one shared slope = act_param   DCCRN/DCCRN_cprs.py:76 */
 } se_act;
 
 typedef void* se_stream_t; /* cudaStream_t */
@@ -126,7 +127,7 @@ int se_istft(int mode, const float* a_re, const float* a_im, long long a_sb, lon
  *     fill_f >= 0 additionally writes act(fill[co]) into output column fill_f (the left F-pad
  *     of de4, CRN.py:92-97, which passes through BN+ELU).
  * ------------------------------------------------------------------------------------- */
-#define SE_MAX_TAPS 8
+#define SE_MAX_TAPS 16
 typedef struct se_conv_desc {
   const float* src0;
   const float* src1;
@@ -142,6 +143,7 @@ typedef struct se_conv_desc {
   const float* bias; /* [Cout] or NULL */
   int Cout;
   int act;        /* se_act */
+  float act_param; /* PReLU slope */
   float* dst;     /* [B, T, dstF, Cout] */
   int dstF, dst_f0, dst_fstep;
   int fill_f;     /* -1: none */
@@ -169,15 +171,16 @@ int se_deconv_out1(const float* src0, const float* src1, int C0, int C1, int B, 
  *     xproj [B, T, 4H] whose columns are in "slice order": column  s*4*HU + gate*HU + j
  *     is gate `gate` of hidden unit u = s*HU + j  (HU = H / nslices).  whh is packed the
  *     same way: whh[s][k][gate*HU + j] = W_hh[gate*H + s*HU + j][k]  (size nslices*H*4*HU).
- *     One persistent CTA per slice keeps its W_hh slice resident in shared memory for all
+ *     xproj_stride = floats between consecutive (b,t) rows (>= 4H; lets several LSTMs share one
+ *     projection GEMM output).  One persistent CTA per slice keeps its W_hh slice resident in shared memory for all
  *     T steps; steps are separated by a device-wide barrier on `sync` (>= 2 unsigned,
  *     zeroed by the caller before each call is NOT required: the kernel is given a base
  *     epoch).  hseq [B, T, H] receives h_t (natural unit order).  work: >= 2*H*Bpad floats,
  *     Bpad = 8*ceil(B/8), scratch for the transposed state.
  *     Requires H % nslices == 0, 4*HU == 32 (HU = 8), H % 128 == 0, B <= 64.
  * ------------------------------------------------------------------------------------- */
-int se_lstm_seq(const float* xproj, const float* whh, int B, int T, int H, float* hseq, long long hseq_sb,
-                long long hseq_st, float* work, unsigned* sync, se_stream_t stream);
+int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, int B, int T, int H, float* hseq,
+                long long hseq_sb, long long hseq_st, float* work, unsigned* sync, se_stream_t stream);
 /* Bytes of `work` se_lstm_seq needs. */
 long long se_lstm_seq_work_bytes(int B, int H);
 
@@ -227,6 +230,14 @@ int se_fsn_fb_input(const float* x, long long sb, long long st, long long sf, in
 int se_fsn_sb_assemble(const float* mag_tm, const float* fb, int B, int Tp, int F, int num_neighbors,
                        const float* inv, float* out_hi, float* out_lo, se_stream_t stream);
 int se_fsn_sb_fc(const float* h, int M, int H, const float* W, const float* bias, float* out, se_stream_t stream);
+
+/* DCCRN polar mask, masking_mode 'E' (DCCRN/DCCRN_cprs.py:201-220):
+ *     est = tanh(|M|) * |X| * exp(j(angle X + angle M)),  M = 0 at the DC bin (:203-204).
+ *     m [B,T,F-1,2] channels-last mask for bins 1..F-1; x / est: planes (re, im) addressed
+ *     plane[b*sb + t*st + f*sf] with their own strides. */
+int se_dccrn_mask(const float* m, const float* x_re, const float* x_im, long long x_sb, long long x_st, long long x_sf,
+                  int B, int T, int F, float* e_re, float* e_im, long long e_sb, long long e_st, long long e_sf,
+                  se_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -77,3 +77,27 @@ def enhance_fullsubnet(sd, wav, p=0.5):
     y = y / c                                                               # :78
     taps = {"c": c, "mag": feat_mag, "mask": m, "y_norm": (y * c).astype(np.float32)}
     return y.astype(np.float32), taps
+
+
+def enhance_dccrn(sd, wav, p=0.5):
+    """``DCCRN/dccrn_decode.py:30-60`` (torch dialect; zero-pad to a whole number of hops, compress,
+    DCCRN-E forward, decompress (rule (ii)), torch.istft without ``length`` then ``[:wav_len]``)."""
+    from . import nets as _n
+    n_fft, win, hop = dsp.GEOMETRIES["dccrn"]
+    x, c = dsp.rms_scale(wav)                                               # :31-32
+    wav_len = len(x)
+    frame_num = int(np.ceil((wav_len - 512 + 512) / 128 + 1))               # :36
+    fake_len = (frame_num - 1) * 128 + 512 - 512
+    x32 = np.concatenate((x, np.zeros(fake_len - wav_len))).astype(np.float32)   # :39
+    spec = dsp.stft(x32, n_fft, win, hop)                                   # :41 [F,T]
+    mag, ph = np.abs(spec) ** p, np.angle(spec)                             # :44
+    feat = np.stack((mag * np.cos(ph), mag * np.sin(ph))).astype(np.float32)     # :46 [2,F,T]
+    with torch.no_grad():
+        est = _n.dccrn_forward(sd, torch.from_numpy(feat)[None]).squeeze(0).numpy()   # :48
+    emag = np.sqrt(est[0] ** 2 + est[1] ** 2) ** (1.0 / p)                  # :49,52
+    eph = np.arctan2(est[1], est[0])                                        # :50
+    y = dsp.istft((emag * np.cos(eph) + 1j * emag * np.sin(eph)).astype(np.complex64), n_fft, win, hop, None)  # :56
+    y = y[:wav_len]                                                         # :59
+    y = y / c
+    taps = {"c": c, "feat": feat, "est": est, "y_norm": (y * c).astype(np.float32)}
+    return y.astype(np.float32), taps

@@ -168,3 +168,79 @@ def fullsubnet_forward(sd, noisy_mag, look_ahead=2, sb_num_neighbors=15, fb_num_
     mask = _fsn_sequence(sd, "sb_model", sb_in, None)                        # :113
     mask = mask.reshape(b, f, 2, t).permute(0, 2, 1, 3).contiguous()         # :114
     return mask[:, :, :, look_ahead:]                                        # :117
+
+
+# ----------------------------------------------------------------------------------------
+# DCCRN  (DCCRN/DCCRN_cprs.py + un-vendored complexnn, restated in oracle/complexnn_restated.py)
+# ----------------------------------------------------------------------------------------
+def _cconv(x, sd, pre, transpose):
+    """ComplexConv2d / ComplexConvTranspose2d k(5,2) s(2,1): DCCRN_cprs.py:66-72, 108-115."""
+    r, i = torch.chunk(x, 2, 1)
+    wr, br, wi, bi = (sd[pre + ".real_conv.weight"], sd[pre + ".real_conv.bias"], sd[pre + ".imag_conv.weight"],
+                      sd[pre + ".imag_conv.bias"])
+    if transpose:
+        f = lambda v, w, b: F.conv_transpose2d(v, w, b, stride=(2, 1), padding=(2, 0), output_padding=(1, 0))  # noqa
+    else:
+        f = lambda v, w, b: F.conv2d(v, w, b, stride=(2, 1), padding=(2, 0))  # noqa: E731
+    return torch.cat([f(r, wr, br) - f(i, wi, bi), f(r, wi, bi) + f(i, wr, br)], 1)
+
+
+def _lstm1(x, sd, pre):
+    """single-layer nn.LSTM, batch_first=False.  x [T,B,I]."""
+    return lstm(x.transpose(0, 1), {f"l.weight_ih_l0": sd[pre + ".weight_ih_l0"], "l.weight_hh_l0": sd[pre + ".weight_hh_l0"],
+                                    "l.bias_ih_l0": sd[pre + ".bias_ih_l0"], "l.bias_hh_l0": sd[pre + ".bias_hh_l0"]},
+                "l", 1).transpose(0, 1)
+
+
+def dccrn_forward(sd, inputs, crop_first=True, taps=None):
+    """DCCRN.forward with masking_mode='E', use_clstm=True (DCCRN_cprs.py:142-226).
+    inputs [B,2,257,T] compressed RI -> [B,2,257,T].  ``crop_first``: decoder keeps ``out[...,1:]``
+    (DCCRN_cprs.py:199); the DCCRN_SNR variant keeps ``[..., :-1]`` (DCCRN_SNR/DCCRN.py:159)."""
+    spec_mags = torch.norm(inputs, dim=1)                                   # :164
+    spec_phase = torch.atan2(inputs[:, -1], inputs[:, 0])                   # :165
+    out = inputs[:, :, 1:]                                                  # :166  drop DC
+    enc = []
+    for idx in range(6):
+        out = F.pad(out, [1, 0, 0, 0])                                      # causal pad (complexnn)
+        out = _cconv(out, sd, f"encoder.{idx}.0", False)
+        out = _bn(out, sd, f"encoder.{idx}.1")
+        out = F.prelu(out, sd[f"encoder.{idx}.2.weight"])
+        enc.append(out)
+        if taps is not None:
+            taps[f"enc{idx}"] = out
+    b, c, d, t = out.shape
+    out = out.permute(3, 0, 1, 2)                                           # :175
+    r = out[:, :, :c // 2].reshape(t, b, c // 2 * d)
+    i = out[:, :, c // 2:].reshape(t, b, c // 2 * d)
+    for l in range(2):                                                      # :182 NavieComplexLSTM x2
+        pre = f"enhance.{l}"
+        r2r, r2i = _lstm1(r, sd, pre + ".real_lstm"), _lstm1(r, sd, pre + ".imag_lstm")
+        i2r, i2i = _lstm1(i, sd, pre + ".real_lstm"), _lstm1(i, sd, pre + ".imag_lstm")
+        r, i = r2r - i2i, i2r + r2i
+        if pre + ".r_trans.weight" in sd:
+            r = F.linear(r, sd[pre + ".r_trans.weight"], sd[pre + ".r_trans.bias"])
+            i = F.linear(i, sd[pre + ".i_trans.weight"], sd[pre + ".i_trans.bias"])
+    if taps is not None:
+        taps["rnn_r"], taps["rnn_i"] = r, i
+    out = torch.cat([r.reshape(t, b, c // 2, d), i.reshape(t, b, c // 2, d)], 2).permute(1, 2, 3, 0)   # :183-194
+    for idx in range(6):
+        e = enc[-1 - idx]
+        orr, oi = torch.chunk(out, 2, 1)
+        er, ei = torch.chunk(e, 2, 1)
+        out = torch.cat([orr, er, oi, ei], 1)                               # complex_cat :197
+        out = _cconv(out, sd, f"decoder.{idx}.0", True)
+        if idx < 5:
+            out = _bn(out, sd, f"decoder.{idx}.1")
+            out = F.prelu(out, sd[f"decoder.{idx}.2.weight"])
+        out = out[..., 1:] if crop_first else out[..., :-1]                 # :199
+        if taps is not None:
+            taps[f"dec{idx}"] = out
+    mask_real = F.pad(out[:, 0], [0, 0, 1, 0])                              # :203-204
+    mask_imag = F.pad(out[:, 1], [0, 0, 1, 0])
+    mask_mags = (mask_real ** 2 + mask_imag ** 2) ** 0.5                    # :207
+    real_phase = mask_real / (mask_mags + 1e-8)
+    imag_phase = mask_imag / (mask_mags + 1e-8)
+    mask_phase = torch.atan2(imag_phase, real_phase)
+    est_mags = torch.tanh(mask_mags) * spec_mags                            # :216-217
+    est_phase = spec_phase + mask_phase
+    return torch.stack([est_mags * torch.cos(est_phase), est_mags * torch.sin(est_phase)], 1)

@@ -52,6 +52,11 @@ def _install_stubs():
     sys.modules["librosa"].filters = sys.modules["librosa.filters"]
     sys.modules["librosa"].util = sys.modules["librosa.util"]
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    # DCCRN imports `complexnn`, which the reference does not vendor: inject the restatement
+    from . import complexnn_restated
+    sys.modules["complexnn"] = complexnn_restated
+    sys.modules["conv_stft"].ConvSTFT = object
+    sys.modules["conv_stft"].ConviSTFT = object
 
 
 @contextlib.contextmanager

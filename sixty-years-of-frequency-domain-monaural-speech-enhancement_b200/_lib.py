@@ -11,9 +11,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libse_b200.so")
-SE_MAX_TAPS = 8
+SE_MAX_TAPS = 16
 
-ACT = {"none": 0, "elu": 1, "softplus": 2, "relu": 3, "sigmoid": 4, "tanh": 5}
+ACT = {"none": 0, "elu": 1, "softplus": 2, "relu": 3, "sigmoid": 4, "tanh": 5, "prelu": 6}
 ISTFT_SPEC, ISTFT_RI_DECOMP, ISTFT_MAG_PHASE, ISTFT_CMASK = 0, 1, 2, 3
 
 
@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
         ("src0", C.c_void_p), ("src1", C.c_void_p), ("C0", C.c_int), ("C1", C.c_int),
         ("B", C.c_int), ("T", C.c_int), ("Fin", C.c_int), ("Fout", C.c_int), ("ntaps", C.c_int),
         ("dt", C.c_int * SE_MAX_TAPS), ("df", C.c_int * SE_MAX_TAPS), ("sf", C.c_int),
-        ("W", C.c_void_p), ("ldw", C.c_int), ("bias", C.c_void_p), ("Cout", C.c_int), ("act", C.c_int),
+        ("W", C.c_void_p), ("ldw", C.c_int), ("bias", C.c_void_p), ("Cout", C.c_int), ("act", C.c_int), ("act_param", C.c_float),
         ("dst", C.c_void_p), ("dstF", C.c_int), ("dst_f0", C.c_int), ("dst_fstep", C.c_int),
         ("fill_f", C.c_int), ("fill", C.c_void_p),
     ]
@@ -42,7 +42,7 @@ PROTOTYPES = {
     "se_conv_gemm": (_I, [C.POINTER(ConvDesc), _P]),
     "se_conv_in1": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "se_deconv_out1": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _P]),
-    "se_lstm_seq": (_I, [_P, _P, _I, _I, _I, _P, _LL, _LL, _P, _P, _P]),
+    "se_lstm_seq": (_I, [_P, _LL, _P, _I, _I, _I, _P, _LL, _LL, _P, _P, _P]),
     "se_lstm_seq_work_bytes": (_LL, [_I, _I]),
     "se_split_tf32": (_I, [_P, _P, _P, _LL, _P]),
     "se_gemm_tf32x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _P, _LL, _P]),
@@ -51,6 +51,7 @@ PROTOTYPES = {
     "se_fsn_fb_input": (_I, [_P, _LL, _LL, _LL, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_assemble": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_fc": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
 }
 
 _lib = None

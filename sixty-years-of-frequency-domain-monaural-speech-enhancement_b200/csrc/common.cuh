@@ -30,8 +30,9 @@ __device__ __forceinline__ float elu_f(float x) { return x > 0.0f ? x : expm1f(x
 // torch.nn.Softplus(beta=1, threshold=20)
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
+__device__ __forceinline__ float apply_act(float x, int act, float param = 0.0f) {
   switch (act) {
+    case SE_ACT_PRELU: return x >= 0.0f ? x : param * x;
     case SE_ACT_ELU: return elu_f(x);
     case SE_ACT_SOFTPLUS: return softplus_f(x);
     case SE_ACT_RELU: return fmaxf(x, 0.0f);

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kGemmThreads) conv_gemm_kernel(const ConvParam
       for (int e = 0; e < 4; ++e) {
         if (n + e < d.Cout) {
           const float bb = d.bias ? __ldg(d.bias + n + e) : 0.f;
-          v[e] = apply_act(v[e] + bb, d.act);
+          v[e] = apply_act(v[e] + bb, d.act, d.act_param);
         }
       }
       if (vec_ok && n + 3 < d.Cout) {
@@ -229,12 +229,12 @@ __global__ void __launch_bounds__(kGemmThreads) conv_gemm_kernel(const ConvParam
 
 // left-pad column that still goes through BN + activation (CRN de4)
 __global__ void fill_col_kernel(float* dst, long long rows, int dstF, int Cout, int fill_f, const float* fill,
-                                int act) {
+                                int act, float act_param) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Cout) return;
   const long long r = idx / Cout;
   const int co = (int)(idx - r * Cout);
-  dst[(r * dstF + fill_f) * Cout + co] = apply_act(__ldg(fill + co), act);
+  dst[(r * dstF + fill_f) * Cout + co] = apply_act(__ldg(fill + co), act, act_param);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -377,7 +377,7 @@ extern "C" int se_conv_gemm(const se_conv_desc* desc, se_stream_t stream) {
     const long long rows = (long long)d.B * d.T;
     const long long n = rows * d.Cout;
     fill_col_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, s>>>(d.dst, rows, d.dstF, d.Cout, d.fill_f, d.fill,
-                                                                  d.act);
+                                                                  d.act, d.act_param);
     rc = check_launch("se_conv_gemm(fill)");
   }
   return rc;

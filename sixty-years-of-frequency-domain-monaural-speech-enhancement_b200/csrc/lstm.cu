@@ -25,7 +25,8 @@ constexpr int kBT = 64;      // batch tile (rows of the per-step GEMM)
 constexpr int kKC = 16;      // k rows per pipeline stage per warp
 
 struct LstmParams {
-  const float* xproj;  // [B, T, 4H] slice-ordered columns
+  const float* xproj;  // [B, T, xp_stride >= 4H] slice-ordered columns
+  long long xp_stride;
   const float* whh;    // [H/8][H][32]
   int B, T, H;
   float* hseq;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
       for (int g = 0; g < 4; ++g) {
         xg[r][g] = 0.f;
         if (b < p.B)
-          xg[r][g] = __ldg(p.xproj + ((size_t)b * p.T + t) * (size_t)(4 * H) + slice * kNC + g * kHU + j);
+          xg[r][g] = __ldg(p.xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * kNC + g * kHU + j);
       }
     }
 
@@ -199,8 +200,10 @@ extern "C" long long se_lstm_seq_work_bytes(int B, int H) {
   return 2ll * H * kBT * (long long)sizeof(float);
 }
 
-extern "C" int se_lstm_seq(const float* xproj, const float* whh, int B, int T, int H, float* hseq,
-                           long long hseq_sb, long long hseq_st, float* work, unsigned* sync, se_stream_t stream) {
+extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, int B, int T, int H,
+                           float* hseq, long long hseq_sb, long long hseq_st, float* work, unsigned* sync,
+                           se_stream_t stream) {
+  SE_REQUIRE(xproj_stride >= 4ll * H, "se_lstm_seq: xproj_stride=%lld < 4H", xproj_stride);
   SE_REQUIRE(xproj && whh && hseq && work && sync, "se_lstm_seq: null pointer");
   SE_REQUIRE(B > 0 && B <= kBT, "se_lstm_seq: B=%d (1..%d per call)", B, kBT);
   SE_REQUIRE(T > 0 && H > 0 && H % (kLstmWarps * kKC) == 0, "se_lstm_seq: H=%d must be a multiple of %d", H,
@@ -223,7 +226,7 @@ extern "C" int se_lstm_seq(const float* xproj, const float* whh, int B, int T, i
     set_error("se_lstm_seq: memset: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
-  LstmParams p{xproj, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync};
+  LstmParams p{xproj, xproj_stride, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync};
   void* args[] = {(void*)&p};
   e = cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(G), dim3(kLstmThreads), args, smem, s);
   if (e != cudaSuccess) {

@@ -135,7 +135,7 @@ def istft(mode, a_re, a_im, b_re, b_im, n_fft, win, hop, out, length, out_scale=
 
 
 def conv_gemm(src0, src1, B, T, Fin, Fout, taps, sf, W, bias, Cout, act, dst, dstF, dst_f0=0, dst_fstep=1,
-              fill_f=-1, fill=None):
+              fill_f=-1, fill=None, act_param=0.0):
     """Implicit-GEMM conv.  taps: list of (dt, df).  W [ntaps*(C0+C1), ldw] fp32 (K-major)."""
     _need_cuda(src0, src1, W, bias, dst, fill)
     device_check()
@@ -152,7 +152,7 @@ def conv_gemm(src0, src1, B, T, Fin, Fout, taps, sf, W, bias, Cout, act, dst, ds
     assert W.is_contiguous() and W.shape[0] == len(taps) * (c0 + c1), (W.shape, len(taps), c0, c1)
     d.W, d.ldw = W.data_ptr(), W.shape[1]
     d.bias = bias.data_ptr() if bias is not None else 0
-    d.Cout, d.act = Cout, ACT[act]
+    d.Cout, d.act, d.act_param = Cout, ACT[act], float(act_param)
     d.dst, d.dstF, d.dst_f0, d.dst_fstep = dst.data_ptr(), dstF, dst_f0, dst_fstep
     d.fill_f = fill_f
     d.fill = fill.data_ptr() if fill is not None else 0
@@ -198,11 +198,12 @@ _LSTM_MAX_B = 64
 
 
 def lstm_seq(xproj, whh, hidden, out=None):
-    """xproj [B,T,4H] (slice-ordered, bias included), whh packed [H/8, H, 32] -> hseq [B,T,H]."""
+    """xproj [B,T,4H] view (slice-ordered, bias included; rows may be strided), whh packed
+    [H/8, H, 32] -> hseq [B,T,H] (out may be a strided view)."""
     _need_cuda(xproj, whh)
     device_check()
     b, t, g4 = xproj.shape
-    assert g4 == 4 * hidden and xproj.is_contiguous()
+    assert g4 == 4 * hidden and xproj.stride(2) == 1 and xproj.stride(0) == t * xproj.stride(1)
     if out is None:
         out = torch.empty(b, t, hidden, device=xproj.device, dtype=torch.float32)
     lib = _lib.load()
@@ -213,8 +214,8 @@ def lstm_seq(xproj, whh, hidden, out=None):
         nb = min(_LSTM_MAX_B, b - b0)
         xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
         with _Timed("lstm_seq"):
-            check(lib.se_lstm_seq(_ptr(xs), _ptr(whh), nb, t, hidden, _ptr(os_), os_.stride(0), os_.stride(1),
-                                  _ptr(work), _ptr(sync), _stream()), "se_lstm_seq")
+            check(lib.se_lstm_seq(_ptr(xs), xproj.stride(1), _ptr(whh), nb, t, hidden, _ptr(os_), os_.stride(0),
+                                  os_.stride(1), _ptr(work), _ptr(sync), _stream()), "se_lstm_seq")
     return out
 
 
@@ -304,3 +305,16 @@ def fsn_sb_fc(h, W, bias, out):
     with _Timed("fsn_sb_fc"):
         check(_lib.load().se_fsn_sb_fc(_ptr(h), m, hd, _ptr(W), _ptr(bias), _ptr(out), _stream()), "se_fsn_sb_fc")
     return out
+
+
+def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
+    """DCCRN-E polar mask.  m [B,T,F-1,2] channels-last; x / e planes [B,T,F] ('btf') or [B,F,T]."""
+    _need_cuda(m, x_re, x_im, e_re, e_im)
+    device_check()
+    b, t, fm1, _ = m.shape
+    xs = _plane_strides(x_re, layout_x)
+    es = _plane_strides(e_re, layout_e)
+    assert _plane_strides(x_im, layout_x) == xs and _plane_strides(e_im, layout_e) == es and m.is_contiguous()
+    with _Timed("dccrn_mask"):
+        check(_lib.load().se_dccrn_mask(_ptr(m), _ptr(x_re), _ptr(x_im), *xs, b, t, fm1 + 1, _ptr(e_re), _ptr(e_im),
+                                        *es, _stream()), "se_dccrn_mask")
