@@ -74,6 +74,42 @@ def make_fullsubnet():
               f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+DCCRN_CASES = [
+    ("dccrn_synth", None, 8000, (6, 7)),
+    ("dccrn_ckpt", "wsj0_si84_300h_dccrn_cprs_model.pth", 16000, (6, 7)),
+]
+
+
+def make_dccrn():
+    mod = ref_shims.import_reference("DCCRN", "DCCRN_cprs")    # runs with the restated complexnn injected
+    for name, ckpt, nsamp, clip_ids in DCCRN_CASES:
+        net = mod.DCCRN(rnn_units=256, masking_mode='E', use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256]).eval()
+        if ckpt is None:
+            sd = synth.synthetic_state_dict(templates.dccrn_template(), seed=0)
+        else:
+            sd = torch.load(ref_shims.checkpoint_path("DCCRN", ckpt), map_location="cpu")
+        net.load_state_dict(sd)
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp)}
+        worst = 0.0
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = decode.enhance_dccrn(sd, wav.astype(np.float64))
+            with torch.no_grad():
+                est_ref = net(torch.from_numpy(taps["feat"])[None]).squeeze(0).numpy()
+            worst = max(worst, float(np.abs(est_ref - taps["est"]).max()))
+            rec[f"wav{j}"] = wav
+            rec[f"feat{j}"] = taps["feat"]
+            rec[f"est{j}"] = est_ref.astype(np.float32)
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        rec["ref_vs_oracle"] = np.array(worst)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: ref_vs_oracle max-abs {worst:.3e}, out rms "
+              f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def sd_digest(sd) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
@@ -121,3 +157,5 @@ if __name__ == "__main__":
         main()
     if len(sys.argv) < 2 or sys.argv[1] == "fullsubnet":
         make_fullsubnet()
+    if len(sys.argv) < 2 or sys.argv[1] == "dccrn":
+        make_dccrn()

@@ -73,6 +73,8 @@ def synthetic_state_dict(template: dict, seed: int = 0, gain: float = 2.0) -> di
         g = torch.Generator().manual_seed(_key_seed(name, seed))
         if name.endswith("num_batches_tracked"):
             out[name] = torch.tensor(1000, dtype=torch.int64)
+        elif len(shape) == 1 and shape[0] == 1 and name.endswith(".2.weight") and not _looks_like_norm(name, template):
+            out[name] = torch.full(shape, 0.25) + 0.1 * (torch.rand(shape, generator=g) - 0.5)   # nn.PReLU slope
         elif name.endswith("running_var"):
             out[name] = torch.rand(shape, generator=g) + 0.5
         elif name.endswith("running_mean"):

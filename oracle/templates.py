@@ -52,3 +52,37 @@ def fullsubnet_template():
     d["sb_model.fc_output_layer.weight"] = (2, 384)
     d["sb_model.fc_output_layer.bias"] = (2,)
     return d
+
+
+def dccrn_template(kernel_num=(32, 64, 128, 256, 256, 256), rnn_units=256):
+    """Key ORDER as torch.load lists the shipped DCCRN checkpoints (encoder, decoder, enhance)."""
+    kn = [2] + list(kernel_num)
+    d = {}
+    for i in range(6):
+        for part in ("real_conv", "imag_conv"):
+            d[f"encoder.{i}.0.{part}.weight"] = (kn[i + 1] // 2, kn[i] // 2, 5, 2)
+            d[f"encoder.{i}.0.{part}.bias"] = (kn[i + 1] // 2,)
+        d.update(_bn(f"encoder.{i}.1", kn[i + 1]))
+        d[f"encoder.{i}.2.weight"] = (1,)
+    di = 0
+    for idx in range(6, 0, -1):
+        for part in ("real_conv", "imag_conv"):
+            d[f"decoder.{di}.0.{part}.weight"] = (kn[idx], kn[idx - 1] // 2, 5, 2)
+            d[f"decoder.{di}.0.{part}.bias"] = (kn[idx - 1] // 2,)
+        if idx != 1:
+            d.update(_bn(f"decoder.{di}.1", kn[idx - 1]))
+            d[f"decoder.{di}.2.weight"] = (1,)
+        di += 1
+    h = rnn_units // 2
+    in0 = 4 * kn[-1] // 2
+    for l in range(2):
+        for part in ("real_lstm", "imag_lstm"):
+            d[f"enhance.{l}.{part}.weight_ih_l0"] = (4 * h, in0 if l == 0 else h)
+            d[f"enhance.{l}.{part}.weight_hh_l0"] = (4 * h, h)
+            d[f"enhance.{l}.{part}.bias_ih_l0"] = (4 * h,)
+            d[f"enhance.{l}.{part}.bias_hh_l0"] = (4 * h,)
+    d["enhance.1.r_trans.weight"] = (in0, h)
+    d["enhance.1.r_trans.bias"] = (in0,)
+    d["enhance.1.i_trans.weight"] = (in0, h)
+    d["enhance.1.i_trans.bias"] = (in0,)
+    return d

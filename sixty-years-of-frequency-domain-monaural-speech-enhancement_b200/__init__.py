@@ -8,5 +8,6 @@ from . import _lib, ops, packing, lstm_engine, decode, shard   # noqa: F401
 from .crn import crn_net                   # noqa: F401
 from .lstm import lstm_net                 # noqa: F401
 from . import fullsubnet                   # noqa: F401
+from .dccrn import DCCRN                   # noqa: F401
 
-__all__ = ["crn_net", "lstm_net", "fullsubnet", "ops", "decode", "packing", "shard"]
+__all__ = ["crn_net", "lstm_net", "fullsubnet", "DCCRN", "ops", "decode", "packing", "shard"]

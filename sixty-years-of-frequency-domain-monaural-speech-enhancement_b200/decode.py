@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import ISTFT_CMASK, ISTFT_MAG_PHASE
+from ._lib import ISTFT_CMASK, ISTFT_MAG_PHASE, ISTFT_RI_DECOMP
 
 GEOM_320 = (320, 320, 160)   # LSTM/config.py:4-6, CRN/config.py:4-6
 
@@ -53,6 +53,38 @@ def enhance_lstm(model, wav, p=1.0, taps=None):
 
 
 GEOM_FULLSUBNET = (512, 512, 256)   # FullSubNet/fullsubnet_sa_decode.py:53
+GEOM_DCCRN = (512, 512, 128)        # DCCRN/dccrn_decode.py:41
+
+
+@torch.no_grad()
+def enhance_dccrn(model, wav, p=0.5, taps=None):
+    """DCCRN/dccrn_decode.py:30-60: zero-pad to whole hops, STFT, compress |X|^p with the phase kept,
+    DCCRN-E forward (polar mask inside), decompress (rule (ii)), iSTFT without ``length`` then
+    ``[:wav_len]``, / c.  wav [B,N] float32 CUDA -> [B,N]."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    n_fft, win, hop = GEOM_DCCRN
+    wav = wav.contiguous().float()
+    b, n = wav.shape
+    c, inv_c = ops.rms_scale(wav)
+    frames = -(-n // hop) + 1                       # ceil(N/hop) + 1          (dccrn_decode.py:36)
+    fake = (frames - 1) * hop
+    if fake != n:                                   # :37-39 zero tail (a no-op when hop divides N)
+        padded = torch.zeros(b, fake, device=wav.device, dtype=torch.float32)
+        padded[:, :n] = wav
+        wav_in = padded
+    else:
+        wav_in = wav
+    t, f = 1 + fake // hop, n_fft // 2 + 1
+    x = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)        # compressed RI, channels-last
+    ops.stft(wav_in, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p)
+    est = model._forward_nhwc(x, taps)
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_RI_DECOMP, est[..., 0], est[..., 1], None, None, n_fft, win, hop, out, n, out_scale=inv_c,
+              inv_p=1.0 / p)
+    if taps is not None:
+        taps.update(c=c, x=x, est=est)
+    return out
 
 
 @torch.no_grad()

@@ -8,13 +8,15 @@ import torch
 import torch.nn.functional as F
 
 
-def _act(x, act):
+def _act(x, act, param=0.0):
+    if act == "prelu":
+        return torch.where(x >= 0, x, param * x)
     return {"none": lambda v: v, "elu": F.elu, "softplus": F.softplus, "relu": F.relu,
             "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](x)
 
 
 def conv_gemm(src0, src1, B, T, Fin, Fout, taps, sf, W, bias, Cout, act, dst, dstF, dst_f0=0, dst_fstep=1,
-              fill_f=-1, fill=None):
+              fill_f=-1, fill=None, act_param=0.0):
     s0 = src0.reshape(B, T, Fin, -1)
     x = s0 if src1 is None else torch.cat([s0, src1.reshape(B, T, Fin, -1)], dim=-1)
     ct = x.shape[-1]
@@ -32,11 +34,11 @@ def conv_gemm(src0, src1, B, T, Fin, Fout, taps, sf, W, bias, Cout, act, dst, ds
     out = acc[..., :Cout]
     if bias is not None:
         out = out + bias
-    out = _act(out, act)
+    out = _act(out, act, act_param)
     d = dst.view(B, T, dstF, Cout)
     d[:, :, dst_f0:dst_f0 + (Fout - 1) * dst_fstep + 1:dst_fstep] = out
     if fill_f >= 0:
-        d[:, :, fill_f] = _act(fill, act)
+        d[:, :, fill_f] = _act(fill, act, act_param)
     return dst
 
 
@@ -81,7 +83,23 @@ def lstm_seq(xproj, whh, hidden, out=None):
         c = (torch.sigmoid(f) * c.view(b, s, 8) + torch.sigmoid(i) * torch.tanh(gg)).reshape(b, hidden)
         h = (torch.sigmoid(o).reshape(b, hidden) * torch.tanh(c))
         outs.append(h)
-    return torch.stack(outs, dim=1)
+    res = torch.stack(outs, dim=1)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
+    assert layout_x == "btf" and layout_e == "btf"
+    M = torch.view_as_complex(m.contiguous())
+    X = torch.complex(x_re, x_im)
+    mm = M.abs()
+    g = torch.where(mm > 0, torch.tanh(mm) / mm.clamp_min(1e-30), torch.zeros_like(mm))
+    E = torch.zeros_like(X)
+    E[:, :, 1:] = X[:, :, 1:] * M * g
+    e_re.copy_(E.real)
+    e_im.copy_(E.imag)
 
 
 def split_tf32(x):
@@ -150,5 +168,5 @@ def fsn_sb_fc(h, W, bias, out):
 
 def install(ops_module, monkeypatch):
     for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3",
-                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc"):
+                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask"):
         monkeypatch.setattr(ops_module, name, globals()[name])

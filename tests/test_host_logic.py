@@ -142,3 +142,26 @@ def test_gather_over_gloo_world2(batch):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_dccrn_host_logic_matches_oracle(monkeypatch):
+    """Complex->real stacked-channel packing, cLSTM block matrices, look-ahead decoder taps."""
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t = templates.dccrn_template()
+    sd = synth.synthetic_state_dict(t, seed=4)
+    m = se_b200.DCCRN(rnn_units=256, masking_mode='E', use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256])
+    assert list(m.state_dict().keys()) == list(t.keys())
+    m.load_state_dict(sd)
+    x = torch.randn(2, 2, 257, 9, generator=torch.Generator().manual_seed(2))
+    est = m._forward_nhwc(x.permute(0, 3, 2, 1).contiguous()).permute(0, 3, 2, 1)
+    with torch.no_grad():
+        ref = nets.dccrn_forward(sd, x)
+    assert (est - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item())
+    # DCCRN_SNR variant: crop the other side (DCCRN_SNR/DCCRN.py:159)
+    m2 = se_b200.DCCRN(rnn_units=256, masking_mode='E', use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256],
+                       crop_first=False)
+    m2.load_state_dict(sd)
+    est2 = m2._forward_nhwc(x.permute(0, 3, 2, 1).contiguous()).permute(0, 3, 2, 1)
+    with torch.no_grad():
+        ref2 = nets.dccrn_forward(sd, x, crop_first=False)
+    assert (est2 - ref2).abs().max() < 2e-4 * max(1.0, ref2.abs().max().item())

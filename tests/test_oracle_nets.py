@@ -19,6 +19,8 @@ CASES = {
     "fullsubnet_synth": (templates.fullsubnet_template, decode.enhance_fullsubnet, None),
     "fullsubnet_ckpt": (templates.fullsubnet_template, decode.enhance_fullsubnet,
                         "FullSubNet__wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
+    "dccrn_synth": (templates.dccrn_template, decode.enhance_dccrn, None),
+    "dccrn_ckpt": (templates.dccrn_template, decode.enhance_dccrn, "DCCRN__wsj0_si84_300h_dccrn_cprs_model.pth"),
 }
 
 
