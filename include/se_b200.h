@@ -152,6 +152,11 @@ typedef struct se_conv_desc {
 
 int se_conv_gemm(const se_conv_desc* desc, se_stream_t stream);
 
+/* dst[b, t, fill_f, co] = act(fill[co]) for every (b,t): a zero-padded output column that still passes
+ * through BatchNorm + activation (the left F-pad of CRN de4, CRN/CRN.py:92-97). */
+int se_fill_column(float* dst, long long rows, int dstF, int Cout, int fill_f, const float* fill, int act,
+                   float act_param, se_stream_t stream);
+
 /* First encoder layer (C_in = 1): Conv2d(1,Cout,k(2,3),s(1,2)) + folded BN + act on a
  * [B,T,Fin] plane -> channels-last [B,T,Fout,Cout].  CRN/CRN.py:37-43.  W [6][Cout] (tap
  * major: kt*3+kf), Cout <= 64. */
@@ -230,6 +235,28 @@ int se_fsn_fb_input(const float* x, long long sb, long long st, long long sf, in
 int se_fsn_sb_assemble(const float* mag_tm, const float* fb, int B, int Tp, int F, int num_neighbors,
                        const float* inv, float* out_hi, float* out_lo, se_stream_t stream);
 int se_fsn_sb_fc(const float* h, int M, int H, const float* W, const float* bias, float* out, se_stream_t stream);
+
+/* Tensor-core twin of se_conv_gemm (tcgen05 3xTF32, 4-D TMA im2col-free A tiles; csrc/conv_tc.cu)
+ * for layers with C0, C1 multiples of 32 and Fout <= 128.  Activations and weights are TF32 hi/lo
+ * pairs (se_split_tf32); weights are K-major [Cout][ntaps*(C0+C1)] with the same (tap, channel)
+ * K order as se_conv_gemm.  Writes fp32 `out` and/or the hi/lo pair for the next layer. */
+typedef struct se_conv_tc_desc {
+  const float *src0_hi, *src0_lo, *src1_hi, *src1_lo;
+  int C0, C1;
+  int B, T, Fin, Fout;
+  int ntaps;
+  int dt[SE_MAX_TAPS];
+  int df[SE_MAX_TAPS];
+  int sf;
+  const float *w_hi, *w_lo;
+  const float* bias;
+  int Cout;
+  int act;
+  float act_param;
+  float *out, *out_hi, *out_lo;
+  int dstF, dst_f0, dst_fstep;
+} se_conv_tc_desc;
+int se_conv_tf32x3(const se_conv_tc_desc* desc, se_stream_t stream);
 
 /* DCCRN polar mask, masking_mode 'E' (DCCRN/DCCRN_cprs.py:201-220):
  *     est = tanh(|M|) * |X| * exp(j(angle X + angle M)),  M = 0 at the DC bin (:203-204).

@@ -28,6 +28,17 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ConvTcDesc(C.Structure):
+    _fields_ = [
+        ("src0_hi", C.c_void_p), ("src0_lo", C.c_void_p), ("src1_hi", C.c_void_p), ("src1_lo", C.c_void_p),
+        ("C0", C.c_int), ("C1", C.c_int), ("B", C.c_int), ("T", C.c_int), ("Fin", C.c_int), ("Fout", C.c_int),
+        ("ntaps", C.c_int), ("dt", C.c_int * SE_MAX_TAPS), ("df", C.c_int * SE_MAX_TAPS), ("sf", C.c_int),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p), ("Cout", C.c_int), ("act", C.c_int),
+        ("act_param", C.c_float), ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("dstF", C.c_int), ("dst_f0", C.c_int), ("dst_fstep", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list EVERY symbol include/se_b200.h declares
 _LL, _I, _F, _P = C.c_longlong, C.c_int, C.c_float, C.c_void_p
 PROTOTYPES = {
@@ -40,6 +51,7 @@ PROTOTYPES = {
     "se_istft": (_I, [_I, _P, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _I, _I, _I, _I, _I, _P, _P, _LL,
                       _I, _P]),
     "se_conv_gemm": (_I, [C.POINTER(ConvDesc), _P]),
+    "se_fill_column": (_I, [_P, _LL, _I, _I, _I, _P, _I, _F, _P]),
     "se_conv_in1": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "se_deconv_out1": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _P]),
     "se_lstm_seq": (_I, [_P, _LL, _P, _I, _I, _I, _P, _LL, _LL, _P, _P, _P]),
@@ -51,6 +63,7 @@ PROTOTYPES = {
     "se_fsn_fb_input": (_I, [_P, _LL, _LL, _LL, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_assemble": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_fc": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "se_conv_tf32x3": (_I, [C.POINTER(ConvTcDesc), _P]),
     "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
 }
 

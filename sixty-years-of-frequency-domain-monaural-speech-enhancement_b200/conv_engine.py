@@ -1,0 +1,80 @@
+"""Convolution dispatch shared by the CRN-family and DCCRN models: every causal Conv2d /
+ConvTranspose2d parity class goes either to the tensor-core implicit GEMM (csrc/conv_tc.cu, 3xTF32,
+needs channel counts that are multiples of 32) or to the fp32 FMA implicit GEMM (csrc/gemm.cu).
+
+Activations travel between layers as :class:`Act`: the fp32 tensor and/or its TF32 (hi, lo) split.
+A tensor-core layer writes the split of its output in its epilogue, so consecutive tensor-core
+layers need no separate split pass.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lstm_engine, ops, packing
+
+
+class Act:
+    """Channels-last activation [B,T,F,C] as fp32 and/or TF32 split pair."""
+    __slots__ = ("f32", "pair")
+
+    def __init__(self, f32=None, pair=None):
+        self.f32, self.pair = f32, pair
+
+    @property
+    def shape(self):
+        return (self.f32 if self.f32 is not None else self.pair[0]).shape
+
+    def get_pair(self):
+        if self.pair is None:
+            self.pair = ops.split_tf32(self.f32)
+        return self.pair
+
+    def get_f32(self):
+        if self.f32 is None:
+            raise RuntimeError("fp32 copy of this activation was not requested from its producer")
+        return self.f32
+
+
+class ConvWeights:
+    """One conv (or one output-column parity of a transposed conv): K-major fp32 for the FMA kernel
+    and [Cout, K] TF32 pair for the tensor-core kernel."""
+    __slots__ = ("kn", "hi", "lo", "cout")
+
+    def __init__(self, w_kn, cout):
+        self.kn = packing.pad_cols(w_kn)
+        self.hi, self.lo = packing.split_tf32(w_kn[:, :cout].t().contiguous())
+        self.cout = cout
+
+
+def tc_eligible(c0, c1, cout, fout, sf):
+    return (lstm_engine.USE_TENSOR_CORES and c0 % 32 == 0 and c1 % 32 == 0 and cout % 4 == 0 and cout >= 4
+            and fout <= 128 and (fout - 1) * sf + 1 <= 256)
+
+
+def conv(src: Act, skip, B, T, Fin, Fout, taps, sf, w: ConvWeights, bias, act, dst: Act, dstF, dst_f0=0, dst_fstep=1,
+         act_param=0.0, fill_f=-1, fill=None):
+    """Runs one implicit-GEMM launch writing into ``dst`` (whichever of dst.f32 / dst.pair exist)."""
+    c0 = src.shape[-1]
+    c1 = skip.shape[-1] if skip is not None else 0
+    if tc_eligible(c0, c1, w.cout, Fout, sf):
+        ops.conv_tf32x3(src.get_pair(), skip.get_pair() if skip is not None else None, B, T, Fin, Fout, taps, sf,
+                        w.hi, w.lo, bias, w.cout, act, dstF, dst_f0, dst_fstep, act_param=act_param, out=dst.f32,
+                        out_pair=dst.pair)
+        if fill_f >= 0:
+            if dst.f32 is not None:
+                ops.fill_column(dst.f32, fill, fill_f, act, act_param)
+            if dst.pair is not None:
+                raise NotImplementedError("fill column on a split-only output")
+    else:
+        if dst.f32 is None:
+            raise RuntimeError("fp32 FMA path needs an fp32 destination")
+        ops.conv_gemm(src.get_f32(), skip.get_f32() if skip is not None else None, B, T, Fin, Fout, taps, sf, w.kn,
+                      bias, w.cout, act, dst.f32, dstF, dst_f0, dst_fstep, fill_f=fill_f, fill=fill,
+                      act_param=act_param)
+        if dst.pair is not None:
+            raise RuntimeError("split output requested from the FMA path: allocate dst without a pair and split")
+
+
+def new_act(b, t, f, c, device, want_f32, want_pair):
+    mk = lambda: torch.empty(b, t, f, c, device=device, dtype=torch.float32)   # noqa: E731
+    return Act(mk() if want_f32 else None, (mk(), mk()) if want_pair else None)

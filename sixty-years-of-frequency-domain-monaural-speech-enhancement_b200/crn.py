@@ -16,7 +16,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import lstm_engine, ops, packing
+from . import conv_engine, lstm_engine, ops, packing
+from .conv_engine import Act, ConvWeights
 from .param_tree import bn_rows, build_param_tree, lstm_rows
 
 _ENC_CH = [1, 16, 32, 64, 128, 256]          # CRN.py:40-62
@@ -60,7 +61,8 @@ class crn_net(nn.Module):
         P = {}
         for i in range(5):
             bn = tuple(sd[f"en.en_module.{i}.2.{n}"] for n in ("weight", "bias", "running_mean", "running_var"))
-            P[f"en{i}"] = packing.pack_conv(sd[f"en.en_module.{i}.1.weight"], sd[f"en.en_module.{i}.1.bias"], bn)
+            w, bias = packing.pack_conv(sd[f"en.en_module.{i}.1.weight"], sd[f"en.en_module.{i}.1.bias"], bn)
+            P[f"en{i}"] = (w, bias) if i == 0 else (ConvWeights(w, _ENC_CH[i + 1]), bias)
         # NHWC flatten index q = f*256 + c  <->  reference feature index c*4 + f
         q = torch.arange(1024, device=dev)
         nhwc = (q % 256) * 4 + q // 256
@@ -73,7 +75,9 @@ class crn_net(nn.Module):
             bn = tuple(sd[f"de.de_module.{i}.{bnm}.{n}"] for n in ("weight", "bias", "running_mean", "running_var"))
             w, b = sd[f"de.de_module.{i}.0.weight"], sd[f"de.de_module.{i}.0.bias"]
             if i < 4:
-                P[f"de{i}"] = packing.pack_deconv_parity(w, b, bn)
+                we, wo, bias, fill = packing.pack_deconv_parity(w, b, bn)
+                co = _DEC_CH[i][1]
+                P[f"de{i}"] = (ConvWeights(we, co), ConvWeights(wo, co), bias, fill)
             else:
                 s, o = packing.bn_fold(*bn)
                 wf = w * s[None, :, None, None]
@@ -105,29 +109,34 @@ class crn_net(nn.Module):
         b, t, f = x.shape
         assert f == self.N_BINS, f"CRN checkpoints are hard-wired to 161 bins, got {f}"
         dev = x.device
+        tc = lambda c0, c1, co, fo, sf: conv_engine.tc_eligible(c0, c1, co, fo, sf)   # noqa: E731
         enc = []
         w, bias = P["en0"]
-        h = ops.conv_in1(x, w, bias, 16, "elu", _ENC_F[1])
+        h = Act(ops.conv_in1(x, w, bias, 16, "elu", _ENC_F[1]))
         enc.append(h)
         for i in range(1, 5):
             w, bias = P[f"en{i}"]
-            co = _ENC_CH[i + 1]
-            out = torch.empty(b, t, _ENC_F[i + 1], co, device=dev, dtype=torch.float32)
-            ops.conv_gemm(h, None, b, t, _ENC_F[i], _ENC_F[i + 1], packing.CONV23_TAPS, 2, w, bias, co, "elu", out,
-                          _ENC_F[i + 1])
+            ci, co = _ENC_CH[i], _ENC_CH[i + 1]
+            is_tc = tc(ci, 0, co, _ENC_F[i + 1], 2)
+            # every consumer of en2..en5 (next encoder layer / LSTM projection / decoder skip) is a
+            # tensor-core layer when tensor cores are on: emit the TF32 split only
+            out = conv_engine.new_act(b, t, _ENC_F[i + 1], co, dev, want_f32=not is_tc, want_pair=is_tc)
+            conv_engine.conv(h, None, b, t, _ENC_F[i], _ENC_F[i + 1], packing.CONV23_TAPS, 2, w, bias, "elu", out,
+                             _ENC_F[i + 1])
             h = out
             enc.append(h)
         if taps is not None:
             for i, e in enumerate(enc):
-                taps[f"en{i + 1}"] = e
+                taps[f"en{i + 1}"] = e.f32 if e.f32 is not None else e.pair[0] + e.pair[1]
         # LSTM: two layers, input projection hoisted over all T
-        seq = h.view(b * t, 1024)
+        seq, pair = (h.f32.view(b * t, 1024) if h.f32 is not None else None,
+                     (h.pair[0].view(b * t, 1024), h.pair[1].view(b * t, 1024)) if h.pair is not None else None)
         for l in range(2):
-            hs = lstm_engine.lstm_layer(seq, P[f"lstm{l}"], b, t)
-            seq = hs.view(b * t, 1024)
+            hs = lstm_engine.lstm_layer(seq, P[f"lstm{l}"], b, t, pair)
+            seq, pair = hs.view(b * t, 1024), None
         if taps is not None:
             taps["lstm_nhwc"] = hs
-        h = hs.view(b, t, 4, 256)
+        h = Act(hs.view(b, t, 4, 256))
         # decoder
         fin = 4
         for i in range(4):
@@ -136,14 +145,20 @@ class crn_net(nn.Module):
             skip = enc[4 - i]
             shift = 1 if i == 3 else 0                      # de4: left pad on F (CRN.py:92-97)
             fo = 2 * fin + 1 + shift
-            out = torch.empty(b, t, fo, co, device=dev, dtype=torch.float32)
-            ops.conv_gemm(h, skip, b, t, fin, fin + 1, packing.DECONV_EVEN_TAPS, 1, we, bias, co, "elu", out, fo,
-                          dst_f0=shift, dst_fstep=2)
-            ops.conv_gemm(h, skip, b, t, fin, fin, packing.DECONV_ODD_TAPS, 1, wo, bias, co, "elu", out, fo,
-                          dst_f0=shift + 1, dst_fstep=2, fill_f=(0 if shift else -1), fill=(fill if shift else None))
+            c0, c1 = h.shape[-1], skip.shape[-1]
+            is_tc = tc(c0, c1, co, fin + 1, 1)
+            last = i == 3                                   # de4 feeds the fp32 direct kernel
+            out = conv_engine.new_act(b, t, fo, co, dev, want_f32=(not is_tc) or last, want_pair=is_tc and not last)
+            conv_engine.conv(h, skip, b, t, fin, fin + 1, packing.DECONV_EVEN_TAPS, 1, we, bias, "elu", out, fo,
+                             dst_f0=shift, dst_fstep=2)
+            conv_engine.conv(h, skip, b, t, fin, fin, packing.DECONV_ODD_TAPS, 1, wo, bias, "elu", out, fo,
+                             dst_f0=shift + 1, dst_fstep=2, fill_f=(0 if shift else -1),
+                             fill=(fill if shift else None))
             h = out
             fin = fo
             if taps is not None:
-                taps[f"de{i + 1}"] = h
-        y = ops.deconv_out1(h, enc[0], P["de4_w"], P["de4_b"], "softplus")
+                taps[f"de{i + 1}"] = h.f32 if h.f32 is not None else h.pair[0] + h.pair[1]
+        h = h.f32
+        enc0 = enc[0].f32
+        y = ops.deconv_out1(h, enc0, P["de4_w"], P["de4_b"], "softplus")
         return y

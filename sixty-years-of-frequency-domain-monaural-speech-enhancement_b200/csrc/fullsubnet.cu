@@ -7,7 +7,7 @@
 //   se_fsn_sb_assemble     reflect-unfold(15) of the noisy magnitude ++ full-band output, norm,
 //                          TF32 split, laid out [T+la][B*F][32] for the per-step cell GEMM (:88-110)
 //   se_fsn_sb_fc           Linear(384,2) on the step's hidden state -> mask[t][b*F+f][2]   (:113-114)
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace se {
 
@@ -84,15 +84,6 @@ __global__ void __launch_bounds__(256) fsn_fb_input_kernel(const float* __restri
       xn[o] = v * s;
     }
   }
-}
-
-__device__ __forceinline__ void split_tf32_dev(float x, float& hi, float& lo) {
-  unsigned hb, lb;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hb) : "f"(x));
-  hi = __uint_as_float(hb);
-  const float r = x - hi;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lb) : "f"(r));
-  lo = __uint_as_float(lb);
 }
 
 // out[t][b*F+f][j] = inv[b] * (j < 2n+1 ? mag_tm[b,t,reflect(f+j-n)] : fb[b,t,f]),  split hi/lo.

@@ -383,6 +383,15 @@ extern "C" int se_conv_gemm(const se_conv_desc* desc, se_stream_t stream) {
   return rc;
 }
 
+extern "C" int se_fill_column(float* dst, long long rows, int dstF, int Cout, int fill_f, const float* fill, int act,
+                              float act_param, se_stream_t stream) {
+  SE_REQUIRE(dst && fill && rows > 0 && fill_f >= 0 && fill_f < dstF && Cout > 0, "se_fill_column: bad arguments");
+  const long long n = rows * Cout;
+  fill_col_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(dst, rows, dstF, Cout, fill_f, fill,
+                                                                                   act, act_param);
+  return check_launch("se_fill_column");
+}
+
 extern "C" int se_conv_in1(const float* src, int B, int T, int Fin, const float* W, const float* bias, int Cout,
                            int act, float* dst, int Fout, se_stream_t stream) {
   SE_REQUIRE(src && W && dst, "se_conv_in1: null pointer");

@@ -25,7 +25,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops, packing
+from . import conv_engine, ops, packing
+from .conv_engine import Act, ConvWeights
 from .param_tree import bn_rows, build_param_tree
 
 BINS = 257
@@ -117,7 +118,7 @@ class DCCRN(nn.Module):
                                [(kf, kt) for kf in range(5) for kt in range(2)], False)
             br, bi = sd[f"{pre}.0.real_conv.bias"], sd[f"{pre}.0.imag_conv.bias"]
             bias = torch.cat([br - bi, br + bi])
-            P[f"enc{i}"] = (packing.pad_cols(w * s[None, :]), (bias * s + o).contiguous(),
+            P[f"enc{i}"] = (ConvWeights(w * s[None, :], kn[i + 1]), (bias * s + o).contiguous(),
                             float(sd[f"{pre}.2.weight"].item()))
         # ---- complex LSTM ----
         h = self.rnn_units // 2
@@ -205,7 +206,7 @@ class DCCRN(nn.Module):
                         a0 = _stack_complex(wr_[:half], wi_[:half], [(kf, kt)], True)
                         a1 = _stack_complex(wr_[half:], wi_[half:], [(kf, kt)], True)
                         out += [a0, a1]
-                return packing.pad_cols(torch.cat(out, dim=0) * s[None, :])
+                return ConvWeights(torch.cat(out, dim=0) * s[None, :], 2 * co2)
             P[f"dec{i}"] = (parity((0, 2, 4)), parity((1, 3)), bias, slope)
         self._packed = P
 
@@ -240,37 +241,39 @@ class DCCRN(nn.Module):
         use_tc = self._use_tc()
         # encoder: drop the DC bin (DCCRN_cprs.py:166) by pointing at bin 1 with row stride 257
         enc = []
-        h = x[:, :, 1:, :]                                         # [B,T,256,2] view, stride over F is 2*1
-        h = h.contiguous()                                         # 256-bin tensor (small: 2 channels)
+        h = Act(x[:, :, 1:, :].contiguous())                       # [B,T,256,2] (small: 2 channels)
         fin = 256
+        f32_of = lambda a: a.f32 if a.f32 is not None else a.pair[0] + a.pair[1]   # noqa: E731 (debug taps only)
         for i in range(6):
             w, bias, slope = P[f"enc{i}"]
-            co = kn[i + 1]
+            ci, co = kn[i], kn[i + 1]
             fo = fin // 2
-            out = torch.empty(b, t, fo, co, device=dev, dtype=torch.float32)
-            ops.conv_gemm(h, None, b, t, fin, fo, ENC_TAPS, 2, w, bias, co, "prelu", out, fo, act_param=slope)
+            is_tc = conv_engine.tc_eligible(ci, 0, co, fo, 2)
+            out = conv_engine.new_act(b, t, fo, co, dev, want_f32=not is_tc, want_pair=is_tc)
+            conv_engine.conv(h, None, b, t, fin, fo, ENC_TAPS, 2, w, bias, "prelu", out, fo, act_param=slope)
             h, fin = out, fo
             enc.append(h)
             if taps is not None:
-                taps[f"enc{i}"] = h
+                taps[f"enc{i}"] = f32_of(h)
         # complex LSTM
         m = b * t
         hid = self.rnn_units // 2
-        seq = h.view(m, fin * kn[-1])
+        seq = h.f32.view(m, fin * kn[-1]) if h.f32 is not None else None
+        pair = (h.pair[0].view(m, -1), h.pair[1].view(m, -1)) if h.pair is not None else None
         hs = torch.empty(b, t, 4 * hid, device=dev, dtype=torch.float32)
         for l in range(2):
-            xp = self._proj(seq, P[f"l{l}_hi"], P[f"l{l}_lo"], P[f"l{l}_kn"], P[f"l{l}_b"], 16 * hid, use_tc)
+            xp = self._proj(seq, pair, P[f"l{l}_hi"], P[f"l{l}_lo"], P[f"l{l}_kn"], P[f"l{l}_b"], 16 * hid, use_tc)
             xp = xp.view(b, t, 16 * hid)
             for k in range(4):
                 ops.lstm_seq(xp[:, :, k * 4 * hid:(k + 1) * 4 * hid], P[f"whh{l}"][k], hid,
                              out=hs[:, :, k * hid:(k + 1) * hid])
-            seq = hs.view(m, 4 * hid)
+            seq, pair = hs.view(m, 4 * hid), None
             if l == 0:
                 hs = torch.empty(b, t, 4 * hid, device=dev, dtype=torch.float32)
-        dec_in = self._proj(seq, P["proj_hi"], P["proj_lo"], P["proj_kn"], P["proj_b"], fin * kn[-1], use_tc)
-        h = dec_in.view(b, t, fin, kn[-1])
+        dec_in = self._proj(seq, None, P["proj_hi"], P["proj_lo"], P["proj_kn"], P["proj_b"], fin * kn[-1], use_tc)
+        h = Act(dec_in.view(b, t, fin, kn[-1]))
         if taps is not None:
-            taps["rnn_out"] = h
+            taps["rnn_out"] = h.f32
         # decoder
         dt_shift = 0 if self.crop_first else -1
         for i in range(6):
@@ -279,16 +282,22 @@ class DCCRN(nn.Module):
             skip = enc[5 - i]
             fo = 2 * fin
             act = "prelu" if i < 5 else "none"
-            out = torch.empty(b, t, fo, co, device=dev, dtype=torch.float32)
+            c0, c1 = h.shape[-1], skip.shape[-1]
+            is_tc = conv_engine.tc_eligible(c0, c1, co, fin, 1)
+            # the consumer of dec4 (Cout=2 last layer) and of dec5 (mask kernel) run on fp32
+            nxt_tc = i < 4 and conv_engine.tc_eligible(co, kn[4 - i], kn[4 - i], fo, 1)
+            out = conv_engine.new_act(b, t, fo, co, dev, want_f32=(not is_tc) or (not nxt_tc),
+                                      want_pair=is_tc and nxt_tc)
             ev = [(dt + dt_shift, df) for dt, df in DEC_EVEN]
             od = [(dt + dt_shift, df) for dt, df in DEC_ODD]
-            ops.conv_gemm(h, skip, b, t, fin, fin, ev, 1, we, bias, co, act, out, fo, dst_f0=0, dst_fstep=2,
-                          act_param=slope)
-            ops.conv_gemm(h, skip, b, t, fin, fin, od, 1, wo, bias, co, act, out, fo, dst_f0=1, dst_fstep=2,
-                          act_param=slope)
+            conv_engine.conv(h, skip, b, t, fin, fin, ev, 1, we, bias, act, out, fo, dst_f0=0, dst_fstep=2,
+                             act_param=slope)
+            conv_engine.conv(h, skip, b, t, fin, fin, od, 1, wo, bias, act, out, fo, dst_f0=1, dst_fstep=2,
+                             act_param=slope)
             h, fin = out, fo
             if taps is not None:
-                taps[f"dec{i}"] = h
+                taps[f"dec{i}"] = f32_of(h)
+        h = h.f32
         est = torch.empty(b, t, BINS, 2, device=dev, dtype=torch.float32)
         ops.dccrn_mask(h, x[..., 0], x[..., 1], est[..., 0], est[..., 1])
         return est
@@ -299,8 +308,9 @@ class DCCRN(nn.Module):
         return lstm_engine.USE_TENSOR_CORES
 
     @staticmethod
-    def _proj(seq, w_hi, w_lo, w_kn, bias, n, use_tc):
-        if use_tc and seq.shape[0] >= 128 and seq.shape[1] % 32 == 0:
-            a_hi, a_lo = ops.split_tf32(seq)
+    def _proj(seq, pair, w_hi, w_lo, w_kn, bias, n, use_tc):
+        k = (seq if seq is not None else pair[0]).shape[1]
+        if use_tc and k % 32 == 0 and (pair is not None or seq.shape[0] >= 128):
+            a_hi, a_lo = pair if pair is not None else ops.split_tf32(seq)
             return ops.gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias, n)
         return ops.linear(seq, w_kn, bias, n)

@@ -11,17 +11,20 @@ from . import ops
 USE_TENSOR_CORES = True   # flipped by tests / bench A-B runs only
 
 
-def input_projection(seq2d, layer):
-    m, k = seq2d.shape
+def input_projection(seq2d, layer, pair=None):
+    """seq2d [M, K] fp32 (or None when ``pair`` = its TF32 (hi, lo) split is already available)."""
+    m, k = (seq2d if seq2d is not None else pair[0]).shape
     n = 4 * layer["hidden"]
-    if USE_TENSOR_CORES and k % 32 == 0 and m >= 128 and layer["wih_hi"].shape[1] == k:
-        a_hi, a_lo = ops.split_tf32(seq2d)
+    if USE_TENSOR_CORES and k % 32 == 0 and (m >= 128 or pair is not None) and layer["wih_hi"].shape[1] == k:
+        a_hi, a_lo = pair if pair is not None else ops.split_tf32(seq2d)
         return ops.gemm_tf32x3(a_hi, a_lo, layer["wih_hi"], layer["wih_lo"], layer["bias"], n)
+    if seq2d is None:
+        raise RuntimeError("fp32 activation needed for the FMA projection")
     return ops.linear(seq2d, layer["wih_kn"], layer["bias"], n)
 
 
-def lstm_layer(seq2d, layer, b, t):
+def lstm_layer(seq2d, layer, b, t, pair=None):
     """seq2d [B*T, I] -> hseq [B, T, H]."""
     h = layer["hidden"]
-    xp = input_projection(seq2d, layer)
+    xp = input_projection(seq2d, layer, pair)
     return ops.lstm_seq(xp.view(b, t, 4 * h), layer["whh"], h)

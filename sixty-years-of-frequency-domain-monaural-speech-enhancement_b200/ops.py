@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT, ConvDesc, check
+from ._lib import ACT, ConvDesc, ConvTcDesc, check
 
 
 def _stream():
@@ -318,3 +318,40 @@ def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
     with _Timed("dccrn_mask"):
         check(_lib.load().se_dccrn_mask(_ptr(m), _ptr(x_re), _ptr(x_im), *xs, b, t, fm1 + 1, _ptr(e_re), _ptr(e_im),
                                         *es, _stream()), "se_dccrn_mask")
+
+
+def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, act, dstF, dst_f0=0, dst_fstep=1,
+                act_param=0.0, out=None, out_pair=None):
+    """Tensor-core implicit-GEMM conv.  src0 / src1: (hi, lo) tuples of channels-last [B,T,Fin,C];
+    w_hi / w_lo [Cout, ntaps*(C0+C1)].  out: fp32 [B,T,dstF,Cout] or None; out_pair: (hi, lo) or None."""
+    device_check()
+    d = ConvTcDesc()
+    d.src0_hi, d.src0_lo = src0[0].data_ptr(), src0[1].data_ptr()
+    c0 = src0[0].shape[-1]
+    c1 = src1[0].shape[-1] if src1 is not None else 0
+    d.src1_hi = src1[0].data_ptr() if src1 is not None else 0
+    d.src1_lo = src1[1].data_ptr() if src1 is not None else 0
+    d.C0, d.C1, d.B, d.T, d.Fin, d.Fout = c0, c1, B, T, Fin, Fout
+    d.ntaps = len(taps)
+    for i, (dt, df) in enumerate(taps):
+        d.dt[i], d.df[i] = dt, df
+    d.sf = sf
+    assert w_hi.shape == (Cout, len(taps) * (c0 + c1)) and w_hi.is_contiguous() and w_lo.is_contiguous()
+    d.w_hi, d.w_lo = w_hi.data_ptr(), w_lo.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else 0
+    d.Cout, d.act, d.act_param = Cout, ACT[act], float(act_param)
+    d.out = out.data_ptr() if out is not None else 0
+    d.out_hi = out_pair[0].data_ptr() if out_pair is not None else 0
+    d.out_lo = out_pair[1].data_ptr() if out_pair is not None else 0
+    d.dstF, d.dst_f0, d.dst_fstep = dstF, dst_f0, dst_fstep
+    with _Timed(f"conv_tf32x3[K={len(taps) * (c0 + c1)},N={Cout}]"):
+        check(_lib.load().se_conv_tf32x3(C.byref(d), _stream()), "se_conv_tf32x3")
+
+
+def fill_column(dst, fill, fill_f, act, act_param=0.0):
+    """dst [B,T,F,C]: column fill_f <- act(fill[c])."""
+    _need_cuda(dst, fill)
+    b, t, f, c = dst.shape
+    with _Timed("fill_column"):
+        check(_lib.load().se_fill_column(_ptr(dst), b * t, f, c, fill_f, _ptr(fill), ACT[act], float(act_param),
+                                         _stream()), "se_fill_column")

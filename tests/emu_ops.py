@@ -102,6 +102,26 @@ def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
     e_im.copy_(E.imag)
 
 
+def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, act, dstF, dst_f0=0, dst_fstep=1,
+                act_param=0.0, out=None, out_pair=None):
+    from se_b200 import packing
+    x0 = src0[0] + src0[1]
+    x1 = (src1[0] + src1[1]) if src1 is not None else None
+    w = (w_hi + w_lo).t().contiguous()
+    tmp = out if out is not None else torch.zeros(B, T, dstF, Cout, dtype=x0.dtype)
+    if out is None and out_pair is not None:
+        tmp.copy_(out_pair[0] + out_pair[1])
+    conv_gemm(x0, x1, B, T, Fin, Fout, taps, sf, w, bias, Cout, act, tmp, dstF, dst_f0, dst_fstep, -1, None, act_param)
+    if out_pair is not None:
+        hi, lo = packing.split_tf32(tmp)
+        out_pair[0].copy_(hi)
+        out_pair[1].copy_(lo)
+
+
+def fill_column(dst, fill, fill_f, act, act_param=0.0):
+    dst[:, :, fill_f] = _act(fill, act, act_param)
+
+
 def split_tf32(x):
     from se_b200 import packing
     return packing.split_tf32(x)
@@ -168,5 +188,5 @@ def fsn_sb_fc(h, W, bias, out):
 
 def install(ops_module, monkeypatch):
     for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3",
-                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask"):
+                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask", "conv_tf32x3", "fill_column"):
         monkeypatch.setattr(ops_module, name, globals()[name])

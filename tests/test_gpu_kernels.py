@@ -177,3 +177,64 @@ def test_lstm_cell_tf32x3_matches_recurrence(m, kx, h, steps):
     e_split = ((dst[0] + dst[1]).cpu().double() - hr).abs().max().item()
     print(f"lstm_cell M={m} Kx={kx} H={h} steps={steps}: h err {e_h:.3e} c err {e_c:.3e} hi+lo err {e_split:.3e}")
     assert e_h < 1e-5 and e_c < 1e-5 and e_split < 1e-5
+
+
+TC_CONV_CASES = [
+    # B, T, Fin, C0, C1, Cout, kind
+    (2, 37, 19, 64, 0, 128, "crn_conv"),       # Fout 9  -> Tbox 14
+    (2, 70, 9, 128, 0, 256, "crn_conv"),       # Fout 4  -> Tbox 32, two n tiles
+    (1, 21, 39, 32, 0, 64, "crn_conv"),        # Fout 19 -> Tbox 6
+    (2, 33, 4, 256, 256, 128, "crn_deconv"),
+    (1, 17, 19, 64, 64, 32, "crn_deconv"),
+    (2, 9, 39, 32, 32, 16, "crn_deconv"),
+    (1, 11, 256, 32, 0, 64, "dccrn_conv"),     # Fout 128 -> Tbox 1, stride-2 box of 255
+    (2, 19, 8, 256, 0, 256, "dccrn_conv"),
+    (2, 13, 4, 256, 256, 256, "dccrn_deconv"),
+    (1, 7, 64, 64, 64, 32, "dccrn_deconv"),
+]
+
+
+@pytest.mark.parametrize("case", TC_CONV_CASES)
+def test_conv_tf32x3_matches_semantics(case):
+    """Tensor-core implicit-GEMM conv (4-D TMA A tiles) vs the declared conv semantics in fp64."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    from se_b200.dccrn import DEC_EVEN, DEC_ODD, ENC_TAPS
+    ops = se_b200.ops
+    b, t, fin, c0, c1, co, kind = case
+    g = torch.Generator().manual_seed(abs(hash(case)) % 1000)
+    x0 = torch.randn(b, t, fin, c0, generator=g)
+    x1 = torch.randn(b, t, fin, c1, generator=g) if c1 else None
+    ct = c0 + c1
+    bias = torch.randn(co, generator=g)
+    if kind == "crn_conv":
+        fout = (fin - 3) // 2 + 1
+        runs = [(packing.CONV23_TAPS, 2, fout, 0, 1)]
+        dstF = fout
+    elif kind == "crn_deconv":
+        dstF = 2 * fin + 1
+        runs = [(packing.DECONV_EVEN_TAPS, 1, fin + 1, 0, 2), (packing.DECONV_ODD_TAPS, 1, fin, 1, 2)]
+    elif kind == "dccrn_conv":
+        runs = [(ENC_TAPS, 2, fin // 2, 0, 1)]
+        dstF = fin // 2
+    else:
+        dstF = 2 * fin
+        runs = [(DEC_EVEN, 1, fin, 0, 2), (DEC_ODD, 1, fin, 1, 2)]
+    ref = torch.zeros(b, t, dstF, co, dtype=torch.float64)
+    got = torch.zeros(b, t, dstF, co, device=dev)
+    got_hi, got_lo = torch.zeros_like(got), torch.zeros_like(got)
+    s0 = ops.split_tf32(x0.to(dev))
+    s1 = ops.split_tf32(x1.to(dev)) if x1 is not None else None
+    for taps, sf, fout, f0, fstep in runs:
+        w = torch.randn(len(taps) * ct, co, generator=g) / np.sqrt(len(taps) * ct)
+        emu_ops.conv_gemm(x0.double(), None if x1 is None else x1.double(), b, t, fin, fout, taps, sf, w.double(),
+                          bias.double(), co, "prelu", ref, dstF, f0, fstep, -1, None, 0.2)
+        w_hi, w_lo = packing.split_tf32(w.t().contiguous())
+        ops.conv_tf32x3(s0, s1, b, t, fin, fout, taps, sf, w_hi.to(dev), w_lo.to(dev), bias.to(dev), co, "prelu", dstF,
+                        f0, fstep, act_param=0.2, out=got, out_pair=(got_hi, got_lo))
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - ref).abs().max().item()
+    err_pair = ((got_hi + got_lo).cpu().double() - ref).abs().max().item()
+    print(f"conv_tf32x3 {case}: max err {err:.3e} (hi+lo {err_pair:.3e})")
+    assert err < 2e-5 and err_pair < 2e-5
