@@ -14,7 +14,10 @@
 namespace se {
 
 constexpr int CT_BM = 128, CT_BK = 32;
-constexpr int CT_STAGES = 4;
+template <int BN>
+struct CtCfg {
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;   // 64 KB stages at BN=128 (227 KB smem limit)
+};
 constexpr int CT_CHUNK_KB = 4;
 constexpr int CT_A_BYTES = CT_BM * CT_BK * 4;  // 16 KB per A tile (hi or lo)
 constexpr int CT_THREADS = 320;
@@ -89,6 +92,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   constexpr int B_BYTES = BN * CT_BK * 4;
   constexpr int STAGE_BYTES = 2 * CT_A_BYTES + 2 * ((B_BYTES + 1023) / 1024 * 1024);
   constexpr int B_SLOT = (B_BYTES + 1023) / 1024 * 1024;
+  constexpr int CT_STAGES = CtCfg<BN>::STAGES;
   constexpr int EPI_COLS = BN / 2;
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   extern __shared__ unsigned char smem_dyn[];
@@ -321,7 +325,7 @@ template <int BN>
 static int launch_conv_tc(const CUtensorMap* m, const ConvTcParams& p, int sms, cudaStream_t s) {
   constexpr int B_SLOT = (BN * CT_BK * 4 + 1023) / 1024 * 1024;
   constexpr int STAGE_BYTES = 2 * CT_A_BYTES + 2 * B_SLOT;
-  constexpr int SMEM = CT_STAGES * STAGE_BYTES + 1024 + 256;
+  constexpr int SMEM = CtCfg<BN>::STAGES * STAGE_BYTES + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(conv_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   if (e != cudaSuccess) {
     set_error("se_conv_tf32x3: smem attribute: %s", cudaGetErrorString(e));
