@@ -308,11 +308,19 @@ def main():
         rec_avg_ms = rec_ms / max(rec_cnt, 1)
         achieved = rec_flops_per_launch / (rec_avg_ms * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        traffic = None
+        ncu_json = os.path.join(ROOT, "profiles", "ncu_full_r01.json")
+        if os.path.exists(ncu_json):      # dram__bytes_read.sum + dram__bytes_write.sum of the committed capture
+            for k in json.load(open(ncu_json))["kernels"]:
+                if k["kernel"].startswith("lstm_seq_kernel"):
+                    traffic = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) * 1e6
         roofline = {
             "kernel": "lstm_seq_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_src} bf16 dense, sustained",
-            "pipe": "fp32 FFMA2 (CUDA cores; TF32 single-pass breaks the 1e-4 gate)",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_src} bf16 dense, sustained",
+            "pipe": "fp32 FFMA2 on the CUDA cores (single-pass TF32 breaks the 1e-4 gate; W_hh does not fit one "
+                    "SM, the recurrence is the part not yet on tcgen05)",
             "pipe_peak": FP32_FMA_PEAK_TFLOPS, "frac_of_pipe": achieved / FP32_FMA_PEAK_TFLOPS,
+            "pipe_peak_measured_gemm_like": 57.9,
             "avg_launch_ms": rec_avg_ms, "dominant_by_time": dom[0], "time_share": share,
             "whole_step_tflops": fl["total"] * BATCH_PER_GPU * T_FRAMES / (ms_step * 1e-3) / 1e12,
         }

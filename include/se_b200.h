@@ -178,7 +178,7 @@ int se_deconv_out1(const float* src0, const float* src1, int C0, int C1, int B, 
  *     same way: whh[s][k][gate*HU + j] = W_hh[gate*H + s*HU + j][k]  (size nslices*H*4*HU).
  *     xproj_stride = floats between consecutive (b,t) rows (>= 4H; lets several LSTMs share one
  *     projection GEMM output).  One persistent CTA per slice keeps its W_hh slice resident in shared memory for all
- *     T steps; steps are separated by a device-wide barrier on `sync` (>= 2 unsigned,
+ *     T steps; steps are separated by a device-wide barrier on `sync` (>= 8 unsigned,
  *     zeroed by the caller before each call is NOT required: the kernel is given a base
  *     epoch).  hseq [B, T, H] receives h_t (natural unit order).  work: >= 2*H*Bpad floats,
  *     Bpad = 8*ceil(B/8), scratch for the transposed state.
@@ -186,7 +186,14 @@ int se_deconv_out1(const float* src0, const float* src1, int C0, int C1, int B, 
  * ------------------------------------------------------------------------------------- */
 int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, int B, int T, int H, float* hseq,
                 long long hseq_sb, long long hseq_st, float* work, unsigned* sync, se_stream_t stream);
-/* Bytes of `work` se_lstm_seq needs. */
+/* `ngroups` (<= 8) independent LSTMs of identical shape in ONE launch (DCCRN's four real passes per
+ * NavieComplexLSTM, complexnn): group g reads xproj columns [g*xproj_group_off, +4H), weights
+ * whh + g*whh_group_stride, writes hseq columns [g*hseq_group_off, +H).  work: ngroups x the single
+ * size; sync: >= 8 unsigned. */
+int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off, const float* whh,
+                      long long whh_group_stride, int ngroups, int B, int T, int H, float* hseq, long long hseq_sb,
+                      long long hseq_st, long long hseq_group_off, float* work, unsigned* sync, se_stream_t stream);
+/* Bytes of `work` se_lstm_seq needs (per group). */
 long long se_lstm_seq_work_bytes(int B, int H);
 
 /* ---------------------------------------------------------------------------------------

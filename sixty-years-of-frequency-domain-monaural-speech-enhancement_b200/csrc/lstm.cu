@@ -31,8 +31,13 @@ struct LstmParams {
   int B, T, H;
   float* hseq;
   long long hs_sb, hs_st;
-  float* hT;           // [2][H][64]
-  unsigned* sync;
+  float* hT;           // [ngroups][2][H][64]
+  unsigned* sync;      // [ngroups] step counters
+  // several independent LSTMs of the same shape in one launch (DCCRN's four real passes per complex
+  // LSTM layer): group g reads xproj columns [g*xp_goff, +4H), weights whh + g*whh_gstride, writes
+  // hseq columns [g*hs_goff, +H).  CTA = (group, slice).
+  int ngroups;
+  long long xp_goff, whh_gstride, hs_goff;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -50,13 +55,19 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
   float* stage = Ws + (size_t)p.H * kNC;                           // [8 warps][2][kKC][64]  (aliased by red)
   float* cst = stage + kLstmWarps * 2 * kKC * kBT;                 // [64][8] cell state
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slice = blockIdx.x;
-  const int G = gridDim.x;
   const int H = p.H;
+  const int G = H / kHU;                 // CTAs per group
+  const int group = blockIdx.x / G;
+  const int slice = blockIdx.x - group * G;
+  const float* xproj = p.xproj + group * p.xp_goff;
+  const float* whh = p.whh + group * p.whh_gstride;
+  float* hseq = p.hseq + group * p.hs_goff;
+  float* hT = p.hT + (size_t)group * 2 * H * kBT;
+  unsigned* sync = p.sync + group;
 
   // resident weights
   {
-    const float4* src = reinterpret_cast<const float4*>(p.whh + (size_t)slice * H * kNC);
+    const float4* src = reinterpret_cast<const float4*>(whh + (size_t)slice * H * kNC);
     float4* dst = reinterpret_cast<float4*>(Ws);
     for (int i = tid; i < H * kNC / 4; i += kLstmThreads) dst[i] = __ldg(src + i);
   }
@@ -80,7 +91,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
       for (int g = 0; g < 4; ++g) {
         xg[r][g] = 0.f;
         if (b < p.B)
-          xg[r][g] = __ldg(p.xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * kNC + g * kHU + j);
+          xg[r][g] = __ldg(xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * kNC + g * kHU + j);
       }
     }
 
@@ -88,12 +99,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
       // -- wait until every CTA has published h_{t-1} ------------------------------------------
       if (tid == 0) {
         const unsigned target = (unsigned)t * (unsigned)G;
-        while (ld_acquire_u32(p.sync) < target) {
+        while (ld_acquire_u32(sync) < target) {
         }
       }
       __syncthreads();
 
-      const float* hprev = p.hT + (size_t)((t - 1) & 1) * H * kBT;
+      const float* hprev = hT + (size_t)((t - 1) & 1) * H * kBT;
       float2 acc[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
     }
 
     // -- gates, cell and hidden update for this CTA's 8 units -------------------------------------
-    float* hcur = p.hT + (size_t)(t & 1) * H * kBT;
+    float* hcur = hT + (size_t)(t & 1) * H * kBT;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int idx = tid + r * kLstmThreads;
@@ -181,12 +192,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
       cst[idx] = c;
       const int u = slice * kHU + j;
       hcur[(size_t)u * kBT + b] = (b < p.B) ? h : 0.f;
-      if (b < p.B) p.hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
+      if (b < p.B) hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
     }
     __syncthreads();
     if (tid == 0 && t + 1 < p.T) {
       __threadfence();
-      red_release_add(p.sync, 1u);
+      red_release_add(sync, 1u);
     }
   }
 }
@@ -200,20 +211,24 @@ extern "C" long long se_lstm_seq_work_bytes(int B, int H) {
   return 2ll * H * kBT * (long long)sizeof(float);
 }
 
-extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, int B, int T, int H,
-                           float* hseq, long long hseq_sb, long long hseq_st, float* work, unsigned* sync,
-                           se_stream_t stream) {
-  SE_REQUIRE(xproj_stride >= 4ll * H, "se_lstm_seq: xproj_stride=%lld < 4H", xproj_stride);
+extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off,
+                                 const float* whh, long long whh_group_stride, int ngroups, int B, int T, int H,
+                                 float* hseq, long long hseq_sb, long long hseq_st, long long hseq_group_off,
+                                 float* work, unsigned* sync, se_stream_t stream) {
   SE_REQUIRE(xproj && whh && hseq && work && sync, "se_lstm_seq: null pointer");
+  SE_REQUIRE(ngroups >= 1 && ngroups <= 8, "se_lstm_seq: ngroups=%d (1..8)", ngroups);
   SE_REQUIRE(B > 0 && B <= kBT, "se_lstm_seq: B=%d (1..%d per call)", B, kBT);
   SE_REQUIRE(T > 0 && H > 0 && H % (kLstmWarps * kKC) == 0, "se_lstm_seq: H=%d must be a multiple of %d", H,
              kLstmWarps * kKC);
-  SE_REQUIRE((((uintptr_t)whh) & 15) == 0 && (((uintptr_t)work) & 15) == 0, "se_lstm_seq: unaligned buffers");
-  const int G = H / kHU;
+  SE_REQUIRE(xproj_stride >= 4ll * H, "se_lstm_seq: xproj_stride=%lld < 4H", xproj_stride);
+  SE_REQUIRE((((uintptr_t)whh) & 15) == 0 && (((uintptr_t)work) & 15) == 0 && (whh_group_stride & 3) == 0,
+             "se_lstm_seq: unaligned buffers");
+  const int G = ngroups * (H / kHU);
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  SE_REQUIRE(G <= sms, "se_lstm_seq: H=%d needs %d co-resident CTAs but the device has %d SMs", H, G, sms);
+  SE_REQUIRE(G <= sms, "se_lstm_seq: H=%d x %d groups needs %d co-resident CTAs but the device has %d SMs", H, ngroups,
+             G, sms);
   const size_t smem = ((size_t)H * kNC + kLstmWarps * 2 * kKC * kBT + kBT * kHU) * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -221,12 +236,13 @@ extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const flo
     set_error("se_lstm_seq: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
-  e = cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned), s);
+  e = cudaMemsetAsync(sync, 0, 8 * sizeof(unsigned), s);
   if (e != cudaSuccess) {
     set_error("se_lstm_seq: memset: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
-  LstmParams p{xproj, xproj_stride, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync};
+  LstmParams p{xproj, xproj_stride, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync, ngroups, xproj_group_off,
+               whh_group_stride, hseq_group_off};
   void* args[] = {(void*)&p};
   e = cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(G), dim3(kLstmThreads), args, smem, s);
   if (e != cudaSuccess) {
@@ -234,4 +250,10 @@ extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const flo
     return SE_ERR_CUDA;
   }
   return check_launch("se_lstm_seq");
+}
+
+extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, int B, int T, int H,
+                           float* hseq, long long hseq_sb, long long hseq_st, float* work, unsigned* sync,
+                           se_stream_t stream) {
+  return se_lstm_seq_multi(xproj, xproj_stride, 0, whh, 0, 1, B, T, H, hseq, hseq_sb, hseq_st, 0, work, sync, stream);
 }

@@ -154,7 +154,7 @@ class DCCRN(nn.Module):
         def whh_pack(wh):
             s_ = h // packing.HU
             return wh.reshape(s_, 4 * packing.HU, h).permute(0, 2, 1).contiguous()
-        P["whh0"] = [whh_pack(whr), whh_pack(whi), whh_pack(whr), whh_pack(whi)]
+        P["whh0"] = torch.stack([whh_pack(whr), whh_pack(whi), whh_pack(whr), whh_pack(whi)]).contiguous()
         # layer 1 input: the four hidden sequences [r2r | r2i | i2r | i2i]; real = r2r - i2i, imag = i2r + r2i
         wr1, whr1, br1 = lstm_block("real_lstm", 1)
         wi1, whi1, bi1 = lstm_block("imag_lstm", 1)
@@ -169,7 +169,7 @@ class DCCRN(nn.Module):
         P["l1_hi"], P["l1_lo"] = packing.split_tf32(w1)
         P["l1_kn"] = packing.pad_cols(w1.t().contiguous())
         P["l1_b"] = torch.cat([br1, bi1, br1, bi1]).contiguous()
-        P["whh1"] = [whh_pack(whr1), whh_pack(whi1), whh_pack(whr1), whh_pack(whi1)]
+        P["whh1"] = torch.stack([whh_pack(whr1), whh_pack(whi1), whh_pack(whr1), whh_pack(whi1)]).contiguous()
         # projection: real = r_trans(r2r - i2i), imag = i_trans(i2r + r2i) -> channels-last [4, 256] flatten
         rt, it = sd["enhance.1.r_trans.weight"], sd["enhance.1.i_trans.weight"]     # [512, 128]
         wp_r = torch.cat([rt, torch.zeros_like(rt), torch.zeros_like(rt), -rt], dim=1)   # [512, 512]
@@ -264,9 +264,7 @@ class DCCRN(nn.Module):
         for l in range(2):
             xp = self._proj(seq, pair, P[f"l{l}_hi"], P[f"l{l}_lo"], P[f"l{l}_kn"], P[f"l{l}_b"], 16 * hid, use_tc)
             xp = xp.view(b, t, 16 * hid)
-            for k in range(4):
-                ops.lstm_seq(xp[:, :, k * 4 * hid:(k + 1) * 4 * hid], P[f"whh{l}"][k], hid,
-                             out=hs[:, :, k * hid:(k + 1) * hid])
+            ops.lstm_seq_multi(xp, P[f"whh{l}"], hid, 4, hs)       # the four real LSTM passes, one launch
             seq, pair = hs.view(m, 4 * hid), None
             if l == 0:
                 hs = torch.empty(b, t, 4 * hid, device=dev, dtype=torch.float32)

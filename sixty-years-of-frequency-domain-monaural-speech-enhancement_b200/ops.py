@@ -209,7 +209,7 @@ def lstm_seq(xproj, whh, hidden, out=None):
     lib = _lib.load()
     work = torch.empty(lib.se_lstm_seq_work_bytes(min(b, _LSTM_MAX_B), hidden) // 4, device=xproj.device,
                        dtype=torch.float32)
-    sync = torch.zeros(2, device=xproj.device, dtype=torch.int32)
+    sync = torch.zeros(8, device=xproj.device, dtype=torch.int32)
     for b0 in range(0, b, _LSTM_MAX_B):
         nb = min(_LSTM_MAX_B, b - b0)
         xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
@@ -355,3 +355,25 @@ def fill_column(dst, fill, fill_f, act, act_param=0.0):
     with _Timed("fill_column"):
         check(_lib.load().se_fill_column(_ptr(dst), b * t, f, c, fill_f, _ptr(fill), ACT[act], float(act_param),
                                          _stream()), "se_fill_column")
+
+
+def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
+    """``ngroups`` same-shape LSTMs in one launch.  xproj [B,T,ngroups*4H] (group-major column blocks),
+    whh [ngroups, H/8, H, 32], out [B,T,ngroups*H]."""
+    _need_cuda(xproj, whh, out)
+    device_check()
+    b, t, cols = xproj.shape
+    assert cols == ngroups * 4 * hidden and xproj.is_contiguous() and out.is_contiguous() and whh.is_contiguous()
+    assert out.shape == (b, t, ngroups * hidden)
+    lib = _lib.load()
+    work = torch.empty(ngroups * lib.se_lstm_seq_work_bytes(min(b, _LSTM_MAX_B), hidden) // 4, device=xproj.device,
+                       dtype=torch.float32)
+    sync = torch.zeros(8, device=xproj.device, dtype=torch.int32)
+    for b0 in range(0, b, _LSTM_MAX_B):
+        nb = min(_LSTM_MAX_B, b - b0)
+        xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
+        with _Timed("lstm_seq_multi"):
+            check(lib.se_lstm_seq_multi(_ptr(xs), cols, 4 * hidden, _ptr(whh), whh[0].numel(), ngroups, nb, t, hidden,
+                                        _ptr(os_), os_.stride(0), os_.stride(1), hidden, _ptr(work), _ptr(sync),
+                                        _stream()), "se_lstm_seq_multi")
+    return out

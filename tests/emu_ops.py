@@ -90,6 +90,12 @@ def lstm_seq(xproj, whh, hidden, out=None):
     return res
 
 
+def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
+    for g in range(ngroups):
+        out[:, :, g * hidden:(g + 1) * hidden] = lstm_seq(xproj[:, :, g * 4 * hidden:(g + 1) * 4 * hidden], whh[g], hidden)
+    return out
+
+
 def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
     assert layout_x == "btf" and layout_e == "btf"
     M = torch.view_as_complex(m.contiguous())
@@ -188,5 +194,5 @@ def fsn_sb_fc(h, W, bias, out):
 
 def install(ops_module, monkeypatch):
     for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3",
-                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask", "conv_tf32x3", "fill_column"):
+                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask", "conv_tf32x3", "fill_column", "lstm_seq_multi"):
         monkeypatch.setattr(ops_module, name, globals()[name])

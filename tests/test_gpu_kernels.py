@@ -238,3 +238,18 @@ def test_conv_tf32x3_matches_semantics(case):
     err_pair = ((got_hi + got_lo).cpu().double() - ref).abs().max().item()
     print(f"conv_tf32x3 {case}: max err {err:.3e} (hi+lo {err_pair:.3e})")
     assert err < 2e-5 and err_pair < 2e-5
+
+
+def test_lstm_seq_multi_equals_separate_launches():
+    dev = _dev()
+    import se_b200
+    g = torch.Generator().manual_seed(11)
+    b, t, h, ng = 5, 9, 128, 4
+    xp = torch.randn(b, t, ng * 4 * h, generator=g).to(dev)
+    whh = (torch.randn(ng, h // 8, h, 32, generator=g) / np.sqrt(h)).to(dev)
+    out = torch.empty(b, t, ng * h, device=dev)
+    se_b200.ops.lstm_seq_multi(xp, whh, h, ng, out)
+    for k in range(ng):
+        ref = emu_ops.lstm_seq(xp[:, :, k * 4 * h:(k + 1) * 4 * h].cpu().double(), whh[k].cpu().double(), h)
+        err = (out[:, :, k * h:(k + 1) * h].cpu().double() - ref).abs().max().item()
+        assert err < 2e-5, (k, err)
