@@ -209,6 +209,13 @@ int se_split_tf32(const float* x, float* hi, float* lo, long long n, se_stream_t
 int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const float* b_hi, const float* b_lo,
                    long long ldb, int M, int N, int K, const float* bias, int act, float* C, long long ldc,
                    se_stream_t stream);
+/* Extended epilogue: C = alpha * act(A B^T + bias, act_param) + res (res [M, ldc] or NULL), optionally also the
+ * TF32 split of C (c_hi / c_lo, row stride ldc) for a following tensor-core layer.  C may be NULL when only
+ * the split is wanted.  Covers y*0.5 + x of the conformer feed-forward blocks (Uformer/ff_cplx.py:26-32) and the
+ * x + y residual of DSConv2d (dsconv2d_cplx.py:58-59). */
+int se_gemm_tf32x3_ex(const float* a_hi, const float* a_lo, long long lda, const float* b_hi, const float* b_lo,
+                      long long ldb, int M, int N, int K, const float* bias, int act, float act_param, float alpha,
+                      const float* res, float* C, float* c_hi, float* c_lo, long long ldc, se_stream_t stream);
 
 /* One LSTM time step for MANY independent sequences, fused on the tensor cores:
  *     gates[M, 4H] = [x_t | h_{t-1}] * W^T + bias ;  c, h updated in the GEMM epilogue.
@@ -272,6 +279,35 @@ int se_conv_tf32x3(const se_conv_tc_desc* desc, se_stream_t stream);
 int se_dccrn_mask(const float* m, const float* x_re, const float* x_im, long long x_sb, long long x_st, long long x_sf,
                   int B, int T, int F, float* e_re, float* e_im, long long e_sb, long long e_st, long long e_sf,
                   se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Uformer glue (Uformer/uformer.py:172-287, dilated_dualpath_conformer.py, fusion.py, t_att_*.py,
+ * f_att_*.py); see csrc/uformer.cu.  Tensors are channels-last; complex tensors carry (re C | im C).
+ *   se_uf_prep:   x [B,T,F,2] -> mag, phase [B,T,F] (sqrt(clamp(.,eps)), atan2(im+eps, re); uformer.py:197)
+ *                 and the network inputs for bins 1..F-1 (uformer.py:204-210).
+ *   se_uf_fusion: m' = m + sigmoid(|c|), c' = c + sigmoid(m)                         (fusion.py:13-19)
+ *   se_group_layernorm: nn.LayerNorm(C) over each of the G channel groups of every row (G = 2: the
+ *                 real and imaginary halves share gamma/beta, as x.transpose(1,4) does); optional
+ *                 gate (x * sigmoid(gate), dsconv2d_cplx.py:54), post op (1 PReLU, 2 swish), residual add,
+ *                 fp32 and/or TF32-split output.
+ *   se_attention: single-head-dim-16 attention for nheads (<= 8) heads whose outputs are combined with
+ *                 signs into nout (<= 2) groups (t_att_cplx.py:58-67).  qkv [R, ld] rows hold
+ *                 (q16|k16|v16) per head; sequence (o, i) starts at row o*outer_stride + i*inner_stride and
+ *                 advances lstride rows per position; out [R, ldo].
+ *   se_uf_mask:   sigmoid magnitude branch and tanh/phase mask branch averaged, DC bin zero padded
+ *                 (uformer.py:236-262) -> est [B,T,F,2].
+ * ------------------------------------------------------------------------------------- */
+int se_uf_prep(const float* x, int B, int T, int F, float* mag, float* phase, float* cplx_in, float* mag_in,
+               se_stream_t stream);
+int se_uf_fusion(const float* c, const float* m, long long rows, int C, float* c_out, float* m_out, se_stream_t stream);
+int se_group_layernorm(const float* x, const float* gate, long long rows, int G, int C, const float* gamma,
+                       const float* beta, float eps, int post, float slope, const float* res, float* out, float* out_hi,
+                       float* out_lo, se_stream_t stream);
+int se_attention(const float* qkv, int ld, int nheads, const int* head_out, const float* head_sign, int nout, int L,
+                 long long lstride, int n_outer, long long outer_stride, int n_inner, long long inner_stride, float scale,
+                 float* out, int ldo, se_stream_t stream);
+int se_uf_mask(const float* cmask, const float* mdec, const float* mag, const float* phase, int B, int T, int F,
+               float* est, se_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -101,3 +101,14 @@ def enhance_dccrn(sd, wav, p=0.5):
     y = y / c
     taps = {"c": c, "feat": feat, "est": est, "y_norm": (y * c).astype(np.float32)}
     return y.astype(np.float32), taps
+
+
+def enhance_uformer_ref(net, wav):
+    """``Uformer/uformer_decode.py:38-50`` around the UNMODIFIED reference module (oracle.uformer_ref;
+    build container only): c-normalise (float64), FloatTensor, model(x, x)[0], / c."""
+    from . import uformer_ref
+    x, c = dsp.rms_scale(wav)                                               # :40-41
+    y, est = uformer_ref.run(net, torch.from_numpy(x.astype(np.float32))[None])   # :43-45
+    y = y.squeeze(0).numpy()
+    taps = {"c": c, "est": est.squeeze(0).numpy(), "y_norm": y.astype(np.float32)}
+    return (y / c).astype(np.float32), taps                                 # :47-48

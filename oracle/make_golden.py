@@ -110,6 +110,41 @@ def make_dccrn():
               f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+UF_CASES = [
+    ("uformer_synth", None, 8000, (8, 9), 0),
+    ("uformer_ckpt", "wsj0_si84_300h_uformer_noncprs_model.pth", 16000, (8, 9), 64000),
+]
+
+
+def make_uformer():
+    """Fixtures from the UNMODIFIED reference Uformer (no travelling restatement exists yet)."""
+    from . import uformer_ref
+    for name, ckpt, nsamp, clip_ids, long_n in UF_CASES:
+        if ckpt is None:
+            sd = synth.synthetic_state_dict(templates.uformer_template(), seed=0, gain=1.0)
+        else:
+            sd = torch.load(ref_shims.checkpoint_path("Uformer", ckpt), map_location="cpu")
+        net = uformer_ref.build(sd)
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp)}
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = decode.enhance_uformer_ref(net, wav.astype(np.float64))
+            rec[f"wav{j}"] = wav
+            rec[f"est{j}"] = taps["est"].astype(np.float32)
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        if long_n:     # a 4 s clip exercises every dilation (up to 128 frames) and T = 401 attention
+            wav = synth.noisy_clip(40, long_n)
+            y, taps = decode.enhance_uformer_ref(net, wav.astype(np.float64))
+            rec["long_clip_id"] = np.array(40)
+            rec["long_ynorm"] = taps["y_norm"]
+        rec["ref_vs_oracle"] = np.array(0.0)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: out rms {float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def sd_digest(sd) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
@@ -159,3 +194,5 @@ if __name__ == "__main__":
         make_fullsubnet()
     if len(sys.argv) < 2 or sys.argv[1] == "dccrn":
         make_dccrn()
+    if len(sys.argv) < 2 or sys.argv[1] == "uformer":
+        make_uformer()

@@ -86,3 +86,12 @@ def dccrn_template(kernel_num=(32, 64, 128, 256, 256, 256), rnn_units=256):
     d["enhance.1.i_trans.weight"] = (in0, h)
     d["enhance.1.i_trans.bias"] = (in0,)
     return d
+
+
+def uformer_template():
+    """The 668 state-dict entries of the shipped Uformer checkpoints (names, shapes, order), as listed by
+    torch.load on Uformer/BEST_MODEL/*.pth and stored in oracle/uformer_keys.json."""
+    import json
+    import os
+    keys = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "uformer_keys.json")))
+    return {k: tuple(shape) for k, shape, _ in keys}

@@ -9,5 +9,6 @@ from .crn import crn_net                   # noqa: F401
 from .lstm import lstm_net                 # noqa: F401
 from . import fullsubnet                   # noqa: F401
 from .dccrn import DCCRN                   # noqa: F401
+from .uformer import Uformer               # noqa: F401
 
-__all__ = ["crn_net", "lstm_net", "fullsubnet", "DCCRN", "ops", "decode", "packing", "shard"]
+__all__ = ["crn_net", "lstm_net", "fullsubnet", "DCCRN", "Uformer", "ops", "decode", "packing", "shard"]

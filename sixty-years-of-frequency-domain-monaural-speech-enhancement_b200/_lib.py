@@ -59,12 +59,18 @@ PROTOTYPES = {
     "se_lstm_seq_work_bytes": (_LL, [_I, _I]),
     "se_split_tf32": (_I, [_P, _P, _P, _LL, _P]),
     "se_gemm_tf32x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _P, _LL, _P]),
+    "se_gemm_tf32x3_ex": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _F, _F, _P, _P, _P, _P, _LL, _P]),
     "se_lstm_cell_tf32x3": (_I, [_P, _P, _LL, _I, _P, _P, _LL, _I, _P, _P, _LL, _P, _I, _P, _P, _P, _P, _P]),
     "se_fsn_clip_inv_mean": (_I, [_P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, C.c_double, _P, _P]),
     "se_fsn_fb_input": (_I, [_P, _LL, _LL, _LL, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_assemble": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_fc": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "se_conv_tf32x3": (_I, [C.POINTER(ConvTcDesc), _P]),
+    "se_uf_prep": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "se_uf_fusion": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
+    "se_group_layernorm": (_I, [_P, _P, _LL, _I, _I, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P]),
+    "se_attention": (_I, [_P, _I, _I, _P, _P, _I, _I, _LL, _I, _LL, _I, _LL, _F, _P, _I, _P]),
+    "se_uf_mask": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
 }
 

@@ -42,8 +42,11 @@ struct TcParams {
   int kb0, kb1;  // k-blocks (of 32) taken from A source 0 / A source 1  (A = [A0 | A1] along K)
   const float* bias;
   int act;
-  float* C;      // EPI_BIAS_ACT: output [M, ldc]
+  float* C;      // EPI_BIAS_ACT: output [M, ldc] (may be NULL when only the split is wanted)
   long long ldc;
+  float act_param, alpha;   // C = alpha * act(acc + bias, act_param) + res
+  const float* res;
+  float *c_hi, *c_lo;
   int panel_m;   // m-blocks per L2 panel
   // EPI_LSTM_CELL: N = 4H, column tile j holds units [32j, 32j+32): two 64-column halves, each
   // [i | f | g | o] x 16 units  (column j*128 + hf*64 + g*16 + u  <-  gate g of unit 32j + 16hf + u)
@@ -216,7 +219,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       if (!row_ok) continue;
       const int n0 = nb * TC_BN + half * TC_EPI_COLS;
       if constexpr (EPI == EPI_BIAS_ACT) {
-        float* crow = p.C + (long long)row * p.ldc;
+        const long long roff = (long long)row * p.ldc;
         const bool vec = (p.ldc & 3) == 0;
 #pragma unroll
         for (int j = 0; j < TC_EPI_COLS; j += 4) {
@@ -225,14 +228,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
           for (int e = 0; e < 4; ++e) {
             const int n = n0 + j + e;
             const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
-            o[e] = apply_act(sum[j + e] + bb, p.act);
+            o[e] = apply_act(sum[j + e] + bb, p.act, p.act_param) * p.alpha;
+            if (p.res && n < p.N) o[e] += __ldg(p.res + roff + n);
           }
           if (vec && n0 + j + 3 < p.N) {
-            *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.C) *reinterpret_cast<float4*>(p.C + roff + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.c_hi) {
+              float hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+              *reinterpret_cast<float4*>(p.c_hi + roff + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(p.c_lo + roff + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (n0 + j + e < p.N) crow[n0 + j + e] = o[e];
+              if (n0 + j + e < p.N) {
+                if (p.C) p.C[roff + n0 + j + e] = o[e];
+                if (p.c_hi) split_tf32_dev(o[e], p.c_hi[roff + n0 + j + e], p.c_lo[roff + n0 + j + e]);
+              }
           }
         }
       } else {
@@ -343,6 +357,8 @@ extern "C" int se_split_tf32(const float* x, float* hi, float* lo, long long n, 
   return check_launch("se_split_tf32");
 }
 
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
 static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long lda0, int K0, const float* a1_hi,
                      const float* a1_lo, long long lda1, int K1, const float* b_hi, const float* b_lo, long long ldb,
                      TcParams p, cudaStream_t stream) {
@@ -384,26 +400,41 @@ static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long 
   return SE_OK;
 }
 
-static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
-
-extern "C" int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const float* b_hi,
-                              const float* b_lo, long long ldb, int M, int N, int K, const float* bias, int act,
-                              float* C, long long ldc, se_stream_t stream) {
-  SE_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "se_gemm_tf32x3: null pointer");
+extern "C" int se_gemm_tf32x3_ex(const float* a_hi, const float* a_lo, long long lda, const float* b_hi,
+                                 const float* b_lo, long long ldb, int M, int N, int K, const float* bias, int act,
+                                 float act_param, float alpha, const float* res, float* C, float* c_hi, float* c_lo,
+                                 long long ldc, se_stream_t stream) {
+  SE_REQUIRE(a_hi && a_lo && b_hi && b_lo && (C || c_hi), "se_gemm_tf32x3: null pointer");
+  SE_REQUIRE((c_hi == nullptr) == (c_lo == nullptr), "se_gemm_tf32x3: c_hi/c_lo go together");
   SE_REQUIRE(M > 0 && N > 0 && K > 0 && K % TC_BK == 0, "se_gemm_tf32x3: K=%d must be a multiple of %d", K, TC_BK);
   SE_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "se_gemm_tf32x3: operand leading dims must be %% 4");
   SE_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && (((uintptr_t)C) & 3) == 0,
              "se_gemm_tf32x3: pointers must be 16-byte aligned");
+  SE_REQUIRE((ldc & 3) != 0 || ((!C || aligned16(C)) && (!c_hi || (aligned16(c_hi) && aligned16(c_lo))) &&
+                                (!res || aligned16(res))),
+             "se_gemm_tf32x3: outputs must be 16-byte aligned when ldc %% 4 == 0");
   TcParams p{};
   p.M = M;
   p.N = N;
   p.bias = bias;
   p.act = act;
+  p.act_param = act_param;
+  p.alpha = alpha;
+  p.res = res;
   p.C = C;
+  p.c_hi = c_hi;
+  p.c_lo = c_lo;
   p.ldc = ldc;
   int rc = launch_tc(EPI_BIAS_ACT, a_hi, a_lo, lda, K, nullptr, nullptr, 0, 0, b_hi, b_lo, ldb, p, (cudaStream_t)stream);
   if (rc) return rc;
   return check_launch("se_gemm_tf32x3");
+}
+
+extern "C" int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const float* b_hi,
+                              const float* b_lo, long long ldb, int M, int N, int K, const float* bias, int act,
+                              float* C, long long ldc, se_stream_t stream) {
+  return se_gemm_tf32x3_ex(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, act, 0.f, 1.f, nullptr, C, nullptr, nullptr,
+                           ldc, stream);
 }
 
 extern "C" int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long long ldx, int Kx, const float* h_hi,

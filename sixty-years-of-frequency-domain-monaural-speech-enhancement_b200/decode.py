@@ -112,6 +112,20 @@ def enhance_fullsubnet(model, wav, p=0.5, taps=None):
 
 
 @torch.no_grad()
+def enhance_uformer(model, wav, taps=None):
+    """Uformer/uformer_decode.py:38-50: c-normalise, model(x, x) (STFT 512/400/160 and iSTFT inside the
+    model, output length hop*(T-1)), / c.  wav [B,N] -> [B, hop*(N//hop)]."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    wav = wav.contiguous().float()
+    c, inv_c = ops.rms_scale(wav)
+    out, _, est, _ = model(wav, None, scale=c, out_scale=inv_c)
+    if taps is not None:
+        taps.update(c=c, est=est)
+    return out
+
+
+@torch.no_grad()
 def dsp_roundtrip(wav, geom):
     """STFT -> identity -> iSTFT (the DSP-only run of SURVEY.md section 8(d))."""
     from ._lib import ISTFT_SPEC

@@ -377,3 +377,102 @@ def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
                                         _ptr(os_), os_.stride(0), os_.stride(1), hidden, _ptr(work), _ptr(sync),
                                         _stream()), "se_lstm_seq_multi")
     return out
+
+
+def gemm_tf32x3_ex(a_pair, b_hi, b_lo, bias, n_out, act="none", act_param=0.0, alpha=1.0, res=None, want_f32=True,
+                   want_pair=False):
+    """Extended tensor-core GEMM: returns (C or None, (c_hi, c_lo) or None); C = alpha*act(A B^T + bias) + res."""
+    a_hi, a_lo = a_pair
+    _need_cuda(a_hi, a_lo, b_hi, b_lo, bias, res)
+    device_check()
+    m, k = a_hi.shape
+    assert b_hi.shape == (n_out, k) and a_hi.stride(1) == 1 and a_lo.stride() == a_hi.stride()
+    mk = lambda: torch.empty(m, n_out, device=a_hi.device, dtype=torch.float32)   # noqa: E731
+    out = mk() if want_f32 else None
+    pair = (mk(), mk()) if want_pair else None
+    if res is not None:
+        assert res.shape == (m, n_out) and res.is_contiguous()
+    with _Timed(f"gemm_tf32x3[K={k},N={n_out}]"):
+        check(_lib.load().se_gemm_tf32x3_ex(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(b_hi), _ptr(b_lo),
+                                            b_hi.stride(0), m, n_out, k, _ptr(bias), ACT[act], float(act_param),
+                                            float(alpha), _ptr(res), _ptr(out), _ptr(pair[0] if pair else None),
+                                            _ptr(pair[1] if pair else None), n_out, _stream()), "se_gemm_tf32x3_ex")
+    return out, pair
+
+
+# ---- Uformer glue -----------------------------------------------------------------------------------
+def uf_prep(x):
+    """x [B,T,F,2] -> mag [B,T,F], phase [B,T,F], cplx_in [B,T,F-1,2], mag_in [B,T,F-1,1]."""
+    _need_cuda(x)
+    device_check()
+    b, t, f, _ = x.shape
+    assert x.is_contiguous()
+    mk = lambda *s: torch.empty(*s, device=x.device, dtype=torch.float32)   # noqa: E731
+    mag, phase, cin, min_ = mk(b, t, f), mk(b, t, f), mk(b, t, f - 1, 2), mk(b, t, f - 1, 1)
+    with _Timed("uf_prep"):
+        check(_lib.load().se_uf_prep(_ptr(x), b, t, f, _ptr(mag), _ptr(phase), _ptr(cin), _ptr(min_), _stream()),
+              "se_uf_prep")
+    return mag, phase, cin, min_
+
+
+def uf_fusion(c, m):
+    """c [..., 2C], m [..., C] -> (c', m') (fusion.py:13-19)."""
+    _need_cuda(c, m)
+    device_check()
+    ch = m.shape[-1]
+    rows = m.numel() // ch
+    assert c.shape[-1] == 2 * ch and c.is_contiguous() and m.is_contiguous()
+    co, mo = torch.empty_like(c), torch.empty_like(m)
+    with _Timed("uf_fusion"):
+        check(_lib.load().se_uf_fusion(_ptr(c), _ptr(m), rows, ch, _ptr(co), _ptr(mo), _stream()), "se_uf_fusion")
+    return co, mo
+
+
+_LN_POST = {"none": 0, "prelu": 1, "swish": 2}
+
+
+def group_layernorm(x, groups, gamma, beta, gate=None, post="none", slope=0.0, res=None, want_f32=True,
+                    want_pair=False, eps=1e-5):
+    """LayerNorm over each of ``groups`` channel groups of the last axis (see se_group_layernorm)."""
+    _need_cuda(x, gamma, beta, gate, res)
+    device_check()
+    ctot = x.shape[-1]
+    c = ctot // groups
+    rows = x.numel() // ctot
+    assert x.is_contiguous() and gamma.numel() == c
+    out = torch.empty_like(x) if want_f32 else None
+    pair = (torch.empty_like(x), torch.empty_like(x)) if want_pair else None
+    with _Timed(f"group_layernorm[C={c}]"):
+        check(_lib.load().se_group_layernorm(_ptr(x), _ptr(gate), rows, groups, c, _ptr(gamma), _ptr(beta), float(eps),
+                                             _LN_POST[post], float(slope), _ptr(res), _ptr(out),
+                                             _ptr(pair[0] if pair else None), _ptr(pair[1] if pair else None),
+                                             _stream()), "se_group_layernorm")
+    return out, pair
+
+
+def attention(qkv, nheads, head_out, head_sign, nout, L, lstride, n_outer, outer_stride, n_inner, inner_stride,
+              scale=0.25):
+    """qkv [R, nheads*48] -> out [R, nout*16]."""
+    _need_cuda(qkv)
+    device_check()
+    r, ld = qkv.shape
+    assert qkv.is_contiguous() and ld == nheads * 48
+    out = torch.empty(r, nout * 16, device=qkv.device, dtype=torch.float32)
+    ho = (C.c_int * 8)(*(list(head_out) + [0] * (8 - len(head_out))))
+    hs = (C.c_float * 8)(*(list(head_sign) + [0.0] * (8 - len(head_sign))))
+    with _Timed(f"attention[L={L},heads={nheads}]"):
+        check(_lib.load().se_attention(_ptr(qkv), ld, nheads, ho, hs, nout, L, lstride, n_outer, outer_stride, n_inner,
+                                       inner_stride, float(scale), _ptr(out), nout * 16, _stream()), "se_attention")
+    return out
+
+
+def uf_mask(cmask, mdec, mag, phase):
+    """cmask [B,T,F-1,2], mdec [B,T,F-1,1], mag/phase [B,T,F] -> est [B,T,F,2]."""
+    _need_cuda(cmask, mdec, mag, phase)
+    device_check()
+    b, t, f = mag.shape
+    est = torch.empty(b, t, f, 2, device=mag.device, dtype=torch.float32)
+    with _Timed("uf_mask"):
+        check(_lib.load().se_uf_mask(_ptr(cmask), _ptr(mdec), _ptr(mag), _ptr(phase), b, t, f, _ptr(est), _stream()),
+              "se_uf_mask")
+    return est

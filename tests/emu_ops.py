@@ -196,3 +196,89 @@ def install(ops_module, monkeypatch):
     for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3",
                  "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask", "conv_tf32x3", "fill_column", "lstm_seq_multi"):
         monkeypatch.setattr(ops_module, name, globals()[name])
+
+
+# ---- Uformer glue mirrors -----------------------------------------------------------------------------
+UF_EPS = torch.finfo(torch.float32).eps
+
+
+def gemm_tf32x3_ex(a_pair, b_hi, b_lo, bias, n_out, act="none", act_param=0.0, alpha=1.0, res=None, want_f32=True,
+                   want_pair=False):
+    from se_b200 import packing
+    y = (a_pair[0] + a_pair[1]) @ (b_hi + b_lo).t()
+    if bias is not None:
+        y = y + bias
+    y = _act(y, act, act_param) * alpha
+    if res is not None:
+        y = y + res
+    return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
+
+
+def uf_prep(x):
+    re, im = x[..., 0], x[..., 1]
+    mag = torch.sqrt(torch.clamp(re ** 2 + im ** 2, UF_EPS))
+    ph = torch.atan2(im + UF_EPS, re)
+    cin = torch.stack([mag * torch.cos(ph), mag * torch.sin(ph)], -1)[:, :, 1:].contiguous()
+    return mag, ph, cin, mag[:, :, 1:, None].contiguous()
+
+
+def uf_fusion(c, m):
+    ch = m.shape[-1]
+    cr, ci = c[..., :ch], c[..., ch:]
+    cm = torch.sqrt(torch.clamp(cr ** 2 + ci ** 2, UF_EPS))
+    sg = torch.sigmoid(m)
+    return torch.cat([cr + sg, ci + sg], -1), m + torch.sigmoid(cm)
+
+
+def group_layernorm(x, groups, gamma, beta, gate=None, post="none", slope=0.0, res=None, want_f32=True,
+                    want_pair=False, eps=1e-5):
+    from se_b200 import packing
+    v = x if gate is None else x * torch.sigmoid(gate)
+    shp = v.shape
+    c = shp[-1] // groups
+    y = F.layer_norm(v.reshape(-1, groups, c), (c,), gamma, beta, eps).reshape(shp)
+    if post == "prelu":
+        y = torch.where(y >= 0, y, slope * y)
+    elif post == "swish":
+        y = y * torch.sigmoid(y)
+    if res is not None:
+        y = y + res
+    return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
+
+
+def attention(qkv, nheads, head_out, head_sign, nout, L, lstride, n_outer, outer_stride, n_inner, inner_stride,
+              scale=0.25):
+    r = qkv.shape[0]
+    out = torch.zeros(r, nout * 16, dtype=qkv.dtype)
+    for o in range(n_outer):
+        for i in range(n_inner):
+            rows = o * outer_stride + i * inner_stride + torch.arange(L) * lstride
+            blk = qkv[rows]
+            for h in range(nheads):
+                q, k, v = blk[:, h * 48:h * 48 + 16], blk[:, h * 48 + 16:h * 48 + 32], blk[:, h * 48 + 32:h * 48 + 48]
+                a = torch.softmax((q @ k.t()) * scale, dim=-1) @ v
+                out[rows, head_out[h] * 16:(head_out[h] + 1) * 16] += head_sign[h] * a
+    return out
+
+
+def uf_mask(cmask, mdec, mag, phase):
+    b, t, f = mag.shape
+    mr, mi = cmask[..., 0], cmask[..., 1]
+    mm = torch.sqrt(torch.clamp(mr ** 2 + mi ** 2, UF_EPS))
+    rp, ip = mr / (mm + UF_EPS), mi / (mm + UF_EPS)
+    mmag = F.pad(torch.tanh(mm + UF_EPS), [1, 0])
+    mph = F.pad(torch.atan2(ip + UF_EPS, rp), [1, 0])
+    msig = F.pad(torch.sigmoid(mdec[..., 0]), [1, 0])
+    em = 0.5 * (mmag * mag + msig * mag)
+    ph = phase + mph
+    return torch.stack([em * torch.cos(ph), em * torch.sin(ph)], -1)
+
+
+_UF_NAMES = ("gemm_tf32x3_ex", "uf_prep", "uf_fusion", "group_layernorm", "attention", "uf_mask")
+_orig_install = install
+
+
+def install(ops_module, monkeypatch):   # noqa: F811
+    _orig_install(ops_module, monkeypatch)
+    for name in _UF_NAMES:
+        monkeypatch.setattr(ops_module, name, globals()[name])

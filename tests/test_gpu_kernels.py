@@ -253,3 +253,73 @@ def test_lstm_seq_multi_equals_separate_launches():
         ref = emu_ops.lstm_seq(xp[:, :, k * 4 * h:(k + 1) * 4 * h].cpu().double(), whh[k].cpu().double(), h)
         err = (out[:, :, k * h:(k + 1) * h].cpu().double() - ref).abs().max().item()
         assert err < 2e-5, (k, err)
+
+
+def test_uformer_glue_kernels():
+    """se_uf_prep / se_uf_fusion / se_group_layernorm / se_uf_mask / extended GEMM epilogue vs torch mirrors."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(3)
+    b, t, f = 2, 7, 257
+    x = torch.randn(b, t, f, 2, generator=g)
+    x[0, 0, 5] = 0.0
+    got = ops.uf_prep(x.to(dev))
+    ref = emu_ops.uf_prep(x.double())
+    for a, r in zip(got, ref):
+        assert (a.cpu().double() - r).abs().max() < 1e-5
+    c = torch.randn(b, t, 4, 64, generator=g)
+    m = torch.randn(b, t, 4, 32, generator=g)
+    gc, gm = ops.uf_fusion(c.to(dev), m.to(dev))
+    rc, rm = emu_ops.uf_fusion(c.double(), m.double())
+    assert (gc.cpu().double() - rc).abs().max() < 1e-6 and (gm.cpu().double() - rm).abs().max() < 1e-6
+    for groups, cc, post in ((2, 128, "prelu"), (1, 128, "none"), (2, 16, "none"), (2, 32, "swish"), (1, 32, "swish")):
+        v = torch.randn(50, groups * cc, generator=g) * 3
+        gate = torch.randn(50, groups * cc, generator=g)
+        res = torch.randn(50, groups * cc, generator=g)
+        gamma, beta = torch.rand(cc, generator=g) + 0.5, torch.randn(cc, generator=g)
+        o, pair = ops.group_layernorm(v.to(dev), groups, gamma.to(dev), beta.to(dev), gate=gate.to(dev), post=post,
+                                      slope=0.2, res=res.to(dev), want_f32=True, want_pair=True)
+        r, _ = emu_ops.group_layernorm(v.double(), groups, gamma.double(), beta.double(), gate=gate.double(), post=post,
+                                       slope=0.2, res=res.double())
+        assert (o.cpu().double() - r).abs().max() < 2e-5
+        assert ((pair[0] + pair[1]).cpu().double() - r).abs().max() < 2e-5
+    cm = torch.randn(b, t, f - 1, 2, generator=g)
+    md = torch.randn(b, t, f - 1, 1, generator=g)
+    mag, ph = torch.rand(b, t, f, generator=g) * 3, (torch.rand(b, t, f, generator=g) - 0.5) * 6
+    ge = ops.uf_mask(cm.to(dev), md.to(dev), mag.to(dev), ph.to(dev))
+    re_ = emu_ops.uf_mask(cm.double(), md.double(), mag.double(), ph.double())
+    assert (ge.cpu().double() - re_).abs().max() < 2e-5
+    # extended GEMM epilogue: alpha, residual, PReLU, split output
+    a = torch.randn(300, 64, generator=g)
+    w = torch.randn(160, 64, generator=g) / 8
+    bias = torch.randn(160, generator=g)
+    res = torch.randn(300, 160, generator=g)
+    ap = ops.split_tf32(a.to(dev))
+    wp = ops.split_tf32(w.to(dev))
+    o, pair = ops.gemm_tf32x3_ex(ap, wp[0], wp[1], bias.to(dev), 160, act="prelu", act_param=0.3, alpha=0.5,
+                                 res=res.to(dev), want_f32=True, want_pair=True)
+    y = a.double() @ w.double().t() + bias.double()
+    r = torch.where(y >= 0, y, 0.3 * y) * 0.5 + res.double()
+    assert (o.cpu().double() - r).abs().max() < 1e-5 and ((pair[0] + pair[1]).cpu().double() - r).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("over_t", [True, False])
+@pytest.mark.parametrize("cplx", [True, False])
+def test_attention_matches_softmax(over_t, cplx):
+    dev = _dev()
+    import se_b200
+    from se_b200.uformer import CPLX_HEADS
+    g = torch.Generator().manual_seed(5)
+    b, t, f = 2, 150, 4
+    nheads = 8 if cplx else 1
+    qkv = torch.randn(b * t * f, nheads * 48, generator=g)
+    ho = [o for _, o, _ in CPLX_HEADS] if cplx else [0]
+    hs = [s for _, _, s in CPLX_HEADS] if cplx else [1.0]
+    nout = 2 if cplx else 1
+    args = (t, f, b, t * f, f, 1) if over_t else (f, 1, b * t, f, 1, 0)
+    got = se_b200.ops.attention(qkv.to(dev), nheads, ho, hs, nout, *args)
+    ref = emu_ops.attention(qkv.double(), nheads, ho, hs, nout, *args)
+    err = (got.cpu().double() - ref).abs().max().item()
+    print(f"attention over_{'t' if over_t else 'f'} cplx={cplx}: max err {err:.3e}")
+    assert err < 2e-5

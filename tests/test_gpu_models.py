@@ -195,3 +195,47 @@ def test_dccrn_matches_golden(name, ckpt):
           f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
     assert rms.max() <= RMS_GATE and rel.max() <= 2e-3
     assert binv < 1e-5
+
+
+@pytest.mark.parametrize("name,ckpt", [("uformer_synth", None),
+                                       ("uformer_ckpt", "Uformer__wsj0_si84_300h_uformer_noncprs_model.pth")])
+def test_uformer_matches_golden(name, ckpt):
+    """Config 5 model: est spectrum and decoded waveform vs fixtures written by the UNMODIFIED reference
+    Uformer (uformer_decode.py loop); the 4 s clip covers all dilations and T = 401 attention."""
+    dev = _dev()
+    import se_b200
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    if ckpt is None:
+        sd = synth.synthetic_state_dict(templates.uformer_template(), seed=0, gain=1.0)
+    else:
+        path = os.path.join(CKPT_DIR, ckpt)
+        if not os.path.exists(path):
+            pytest.skip("checkpoint copy not present")
+        sd = torch.load(path, map_location="cpu")
+    model = se_b200.Uformer()
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    k = len(g["clip_ids"])
+    wav = torch.from_numpy(np.stack([g[f"wav{j}"] for j in range(k)])).to(dev)
+    taps = {}
+    y = se_b200.decode.enhance_uformer(model, wav, taps=taps)
+    c = taps["c"].cpu().numpy()
+    est = taps["est"].cpu().numpy()
+    e_net = np.abs(est - np.stack([g[f"est{j}"] for j in range(k)])).max()
+    yn = y.cpu().numpy() * c[:, None]
+    refn = np.stack([g[f"ynorm{j}"] for j in range(k)])
+    rms = np.sqrt(np.mean((yn - refn) ** 2, axis=1))
+    rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
+    y1 = se_b200.decode.enhance_uformer(model, wav[1:2])
+    binv = (y[1:2] - y1).abs().max().item()
+    msg = f"{name}: est max-abs {e_net:.3e}; wav RMS err {rms.max():.3e} rel {rel.max():.3e}; batch-vs-single {binv:.2e}"
+    if "long_ynorm" in g:
+        w4 = torch.from_numpy(synth.noisy_clip(int(g["long_clip_id"]), 64000))[None].to(dev)
+        t4 = {}
+        y4 = se_b200.decode.enhance_uformer(model, w4, taps=t4)
+        r4 = np.sqrt(np.mean((y4[0].cpu().numpy() * float(t4["c"][0]) - g["long_ynorm"]) ** 2))
+        msg += f"; 4 s clip RMS err {r4:.3e}"
+        assert r4 <= RMS_GATE
+    print(msg)
+    assert rms.max() <= RMS_GATE and rel.max() <= 2e-3
+    assert binv < 1e-5

@@ -165,3 +165,24 @@ def test_dccrn_host_logic_matches_oracle(monkeypatch):
     with torch.no_grad():
         ref2 = nets.dccrn_forward(sd, x, crop_first=False)
     assert (est2 - ref2).abs().max() < 2e-4 * max(1.0, ref2.abs().max().item())
+
+
+def test_uformer_host_logic_matches_reference_fixture(monkeypatch):
+    """668-entry state-dict drop-in + the whole Uformer orchestration (stacked complex convs, block QKV
+    projection, signed head combination, gated dilated convs, fusion) against the fixture written by the
+    UNMODIFIED reference module."""
+    import os
+    from conftest import GOLDEN
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t = templates.uformer_template()
+    sd = synth.synthetic_state_dict(t, seed=0, gain=1.0)
+    m = se_b200.Uformer()
+    assert list(m.state_dict().keys()) == list(t.keys()) and len(t) == 668
+    m.load_state_dict(sd)
+    g = np.load(os.path.join(GOLDEN, "uformer_synth.npz"))
+    wav = torch.from_numpy(g["wav0"])[None].double() * float(g["c0"])
+    X = torch.stft(wav.float(), 512, 160, 400, torch.hann_window(400), return_complex=True)
+    x = torch.view_as_real(X.permute(0, 2, 1).contiguous()).contiguous()
+    est = m._network(x).permute(0, 3, 2, 1)[0]
+    ref = torch.from_numpy(g["est0"])
+    assert (est - ref).abs().max() < 5e-4 * max(1.0, ref.abs().max().item())
