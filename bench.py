@@ -325,7 +325,7 @@ def main():
             "whole_step_tflops": fl["total"] * BATCH_PER_GPU * T_FRAMES / (ms_step * 1e-3) / 1e12,
         }
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed on rank 0 at N=1 only
             clips = synth.noisy_batch(8, N_SAMPLES)
             fps, ms_clip, threads = cpu_baseline(sd, list(clips), repeats=3)
             cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",

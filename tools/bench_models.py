@@ -28,6 +28,8 @@ CASES = {
               se_b200.decode.enhance_dccrn, odecode.enhance_dccrn, 32, 4, 128, dict(p=0.5)),
     "fullsubnet": (lambda: se_b200.fullsubnet.Model(**FSN_ARGS), templates.fullsubnet_template,
                    se_b200.decode.enhance_fullsubnet, odecode.enhance_fullsubnet, 32, 10, 256, dict(p=0.5)),
+    "uformer": (lambda: se_b200.Uformer(), templates.uformer_template, se_b200.decode.enhance_uformer, None,
+                64, 4, 160, dict()),
 }
 
 
@@ -37,7 +39,7 @@ def main():
     dev = torch.device("cuda")
     for name in which:
         ctor, tmpl, genh, oenh, bsz, secs, hop, kw = CASES[name]
-        sd = synth.synthetic_state_dict(tmpl(), seed=0)
+        sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name == "uformer" else 2.0)
         model = ctor()
         model.load_state_dict(sd)
         model.eval().cuda()
@@ -63,7 +65,7 @@ def main():
         rec = {"model": name, "batch": bsz, "clip_s": secs, "frames_per_clip": frames, "ms_per_batch": ms,
                "frames_per_s": bsz * frames / (ms * 1e-3), "rtf": ms * 1e-3 / (bsz * secs), "op_time_share": share,
                "weights": "seeded synthetic"}
-        if do_cpu:
+        if do_cpu and oenh is not None:
             torch.set_num_threads(16)
             x = base[0].astype(np.float64)
             oenh(sd, x, **kw)
