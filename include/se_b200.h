@@ -193,6 +193,10 @@ int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, in
 int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off, const float* whh,
                       long long whh_group_stride, int ngroups, int B, int T, int H, float* hseq, long long hseq_sb,
                       long long hseq_st, long long hseq_group_off, float* work, unsigned* sync, se_stream_t stream);
+/* Recurrence engine: 1 (default) = legacy mma.sync TF32 tensor path with the 3xTF32 split (W_hh hi part in
+ * registers, lo part in shared memory; H in {128, 512, 1024}), 0 = fp32 FMA kernel (any H %% 128 == 0).
+ * Process-global; for A/B measurements and tests. */
+int se_set_lstm_engine(int engine);
 /* Bytes of `work` se_lstm_seq needs (per group). */
 long long se_lstm_seq_work_bytes(int B, int H);
 

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "se_deconv_out1": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P, _P]),
     "se_lstm_seq": (_I, [_P, _LL, _P, _I, _I, _I, _P, _LL, _LL, _P, _P, _P]),
     "se_lstm_seq_multi": (_I, [_P, _LL, _LL, _P, _LL, _I, _I, _I, _I, _P, _LL, _LL, _LL, _P, _P, _P]),
+    "se_set_lstm_engine": (_I, [_I]),
     "se_lstm_seq_work_bytes": (_LL, [_I, _I]),
     "se_split_tf32": (_I, [_P, _P, _P, _LL, _P]),
     "se_gemm_tf32x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _P, _LL, _P]),

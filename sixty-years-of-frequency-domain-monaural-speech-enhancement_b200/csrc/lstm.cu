@@ -202,6 +202,214 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
   }
 }
 
+
+// ================================================================================================
+// Tensor-core variant of the same recurrence: legacy mma.sync m16n8k8 TF32 with the 3xTF32 split.
+//   * W_hh_hi (TF32) stays in REGISTERS for the whole sequence (A fragments: 2 m-tiles x KT k-tiles
+//     x 4 = 128 registers per thread at H = 1024), W_hh_lo in shared memory in fragment order;
+//   * h_{t-1} is split hi/lo on the fly while loading the B fragments from the staged chunk;
+//   * per step and warp: 3 x 2 x 8 x KT MMAs; accumulate in fp32 registers (only 3*KT accumulation
+//     steps per warp, then an exact fp32 cross-warp reduction) -> fp32-class accuracy.
+// tcgen05 is not used here: its M >= 64 tiles need a W_hh slice (hi + lo) of >= 512 KB per CTA, so it
+// only pays with W_hh split across a cluster and h multicast (planned); mma.sync measured 278 TFLOP/s
+// on this part (tools/microbench.cu), 5x the fp32 FMA rate this recurrence ran at.
+// ================================================================================================
+constexpr int kHS = 72;  // padded row stride of a staged h chunk (conflict-free B-fragment loads)
+
+__device__ __forceinline__ unsigned tf32_rna(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KT>  // k-tiles (of 8) per warp: H = 64 * KT
+__global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const LstmParams p) {
+  constexpr int H = 64 * KT;
+  constexpr int NCH = (KT + 1) / 2;        // chunks of up to 16 k rows
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* wlo = reinterpret_cast<float4*>(smem_raw);                         // [8 warps][2][KT][32 lanes]
+  float* stage = reinterpret_cast<float*>(wlo + kLstmWarps * 2 * KT * 32);   // [8 warps][2][16][kHS] (aliased by red)
+  float* cst = stage + kLstmWarps * 2 * kKC * kHS;                           // [64][8]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int G = H / kHU;
+  const int group = blockIdx.x / G;
+  const int slice = blockIdx.x - group * G;
+  const float* xproj = p.xproj + group * p.xp_goff;
+  const float* whh = p.whh + group * p.whh_gstride + (size_t)slice * H * kNC;   // [H][32]
+  float* hseq = p.hseq + group * p.hs_goff;
+  float* hT = p.hT + (size_t)group * 2 * H * kBT;
+  unsigned* sync = p.sync + group;
+  const int kbase = warp * (H / kLstmWarps);
+
+  // resident weights: hi fragments -> registers, lo fragments -> shared memory (fragment order)
+  unsigned ahi[2][KT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      float lo[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = kbase + kt * 8 + tig + ((r >> 1) << 2);      // a0,a1: k = tig ; a2,a3: k = tig + 4
+        const int m = mt * 16 + gid + ((r & 1) << 3);              // a0,a2: row gid ; a1,a3: row gid + 8
+        const float w = __ldg(whh + (size_t)k * kNC + m);
+        ahi[mt][kt][r] = tf32_rna(w);
+        lo[r] = __uint_as_float(tf32_rna(w - __uint_as_float(ahi[mt][kt][r])));
+      }
+      wlo[((warp * 2 + mt) * KT + kt) * 32 + lane] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  for (int i = tid; i < kBT * kHU; i += kLstmThreads) cst[i] = 0.f;
+  __syncthreads();
+
+  float* my_stage = stage + warp * (2 * kKC * kHS);
+
+  for (int t = 0; t < p.T; ++t) {
+    float xg[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int idx = tid + r * kLstmThreads;
+      const int b = idx >> 3, j = idx & 7;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        xg[r][g] = 0.f;
+        if (b < p.B) xg[r][g] = __ldg(xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * kNC + g * kHU + j);
+      }
+    }
+
+    if (t > 0) {
+      if (tid == 0) {
+        const unsigned target = (unsigned)t * (unsigned)G;
+        while (ld_acquire_u32(sync) < target) {
+        }
+      }
+      __syncthreads();
+      const float* hprev = hT + (size_t)((t - 1) & 1) * H * kBT;
+      float acc[2][8][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
+
+      auto issue = [&](int c, int buf) {
+        const int rows = min(kKC, KT * 8 - c * kKC);
+        const float* g = hprev + (size_t)(kbase + c * kKC) * kBT;
+        float* s = my_stage + buf * (kKC * kHS);
+        for (int piece = lane; piece < rows * 16; piece += 32) {   // 16-byte pieces: 16 per 64-float row
+          const int r = piece >> 4, q = piece & 15;
+          cp_async16(s + r * kHS + q * 4, g + r * kBT + q * 4);
+        }
+        cp_async_commit();
+      };
+
+      issue(0, 0);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < NCH) {
+          issue(c + 1, buf ^ 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float* hs = my_stage + buf * (kKC * kHS);
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int kt = c * 2 + k2;
+          if (kt < KT) {
+            unsigned alo[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const float4 v = wlo[((warp * 2 + mt) * KT + kt) * 32 + lane];
+              alo[mt][0] = __float_as_uint(v.x); alo[mt][1] = __float_as_uint(v.y);
+              alo[mt][2] = __float_as_uint(v.z); alo[mt][3] = __float_as_uint(v.w);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              const float h0 = hs[(k2 * 8 + tig) * kHS + nt * 8 + gid];
+              const float h1 = hs[(k2 * 8 + tig + 4) * kHS + nt * 8 + gid];
+              const unsigned b0h = tf32_rna(h0), b1h = tf32_rna(h1);
+              const unsigned b0l = tf32_rna(h0 - __uint_as_float(b0h)), b1l = tf32_rna(h1 - __uint_as_float(b1h));
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                mma_tf32(acc[mt][nt], alo[mt], b0h, b1h);
+                mma_tf32(acc[mt][nt], ahi[mt][kt], b0l, b1l);
+                mma_tf32(acc[mt][nt], ahi[mt][kt], b0h, b1h);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+
+      // partial tile -> red[warp][b][col'] (same swizzle as the FMA kernel; aliases this warp's stage)
+      float* red = my_stage;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int col = mt * 16 + gid + ((r >> 1) << 3);
+            const int b = nt * 8 + 2 * tig + (r & 1);
+            red[b * kNC + ((((col >> 3) ^ (b & 3)) << 3) | (col & 7))] = acc[mt][nt][r];
+          }
+      __syncthreads();
+    }
+
+    float* hcur = hT + (size_t)(t & 1) * H * kBT;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int idx = tid + r * kLstmThreads;
+      const int b = idx >> 3, j = idx & 7;
+      float g4[4] = {xg[r][0], xg[r][1], xg[r][2], xg[r][3]};
+      if (t > 0) {
+#pragma unroll
+        for (int w = 0; w < kLstmWarps; ++w) {
+          const float* red = stage + w * (2 * kKC * kHS) + b * kNC;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) g4[g] += red[((g ^ (b & 3)) << 3) + j];
+        }
+      }
+      const float ig = sigmoid_f(g4[0]);
+      const float fg = sigmoid_f(g4[1]);
+      const float gg = tanhf(g4[2]);
+      const float og = sigmoid_f(g4[3]);
+      const float c = fg * cst[idx] + ig * gg;
+      const float h = og * tanhf(c);
+      cst[idx] = c;
+      const int u = slice * kHU + j;
+      hcur[(size_t)u * kBT + b] = (b < p.B) ? h : 0.f;
+      if (b < p.B) hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
+    }
+    __syncthreads();
+    if (tid == 0 && t + 1 < p.T) {
+      __threadfence();
+      red_release_add(sync, 1u);
+    }
+  }
+}
+
+static int g_lstm_engine = 1;  // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel where instantiated
+
+template <int KT>
+static cudaError_t launch_lstm_mma(const LstmParams& p, int G, cudaStream_t s) {
+  const size_t smem = (size_t)kLstmWarps * 2 * KT * 32 * sizeof(float4) +
+                      ((size_t)kLstmWarps * 2 * kKC * kHS + kBT * kHU) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(lstm_seq_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = {(void*)&p};
+  return cudaLaunchCooperativeKernel((const void*)lstm_seq_mma_kernel<KT>, dim3(G), dim3(kLstmThreads), args, smem, s);
+}
+
 }  // namespace se
 
 using namespace se;
@@ -244,7 +452,11 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
   LstmParams p{xproj, xproj_stride, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync, ngroups, xproj_group_off,
                whh_group_stride, hseq_group_off};
   void* args[] = {(void*)&p};
-  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(G), dim3(kLstmThreads), args, smem, s);
+  if (g_lstm_engine == 1 && (H == 1024 || H == 512 || H == 128)) {
+    e = H == 1024 ? launch_lstm_mma<16>(p, G, s) : (H == 512 ? launch_lstm_mma<8>(p, G, s) : launch_lstm_mma<2>(p, G, s));
+  } else {
+    e = cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(G), dim3(kLstmThreads), args, smem, s);
+  }
   if (e != cudaSuccess) {
     set_error("se_lstm_seq: cooperative launch: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
@@ -256,4 +468,10 @@ extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const flo
                            float* hseq, long long hseq_sb, long long hseq_st, float* work, unsigned* sync,
                            se_stream_t stream) {
   return se_lstm_seq_multi(xproj, xproj_stride, 0, whh, 0, 1, B, T, H, hseq, hseq_sb, hseq_st, 0, work, sync, stream);
+}
+
+extern "C" int se_set_lstm_engine(int engine) {
+  SE_REQUIRE(engine == 0 || engine == 1, "se_set_lstm_engine: 0 (fp32 FMA) or 1 (mma.sync 3xTF32)");
+  g_lstm_engine = engine;
+  return SE_OK;
 }

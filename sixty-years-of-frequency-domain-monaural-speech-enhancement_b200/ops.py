@@ -476,3 +476,8 @@ def uf_mask(cmask, mdec, mag, phase):
         check(_lib.load().se_uf_mask(_ptr(cmask), _ptr(mdec), _ptr(mag), _ptr(phase), b, t, f, _ptr(est), _stream()),
               "se_uf_mask")
     return est
+
+
+def set_lstm_engine(engine: int):
+    """0 = fp32 FMA recurrence kernel, 1 = mma.sync 3xTF32 recurrence kernel (default)."""
+    check(_lib.load().se_set_lstm_engine(int(engine)), "se_set_lstm_engine")

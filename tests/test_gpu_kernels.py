@@ -323,3 +323,26 @@ def test_attention_matches_softmax(over_t, cplx):
     err = (got.cpu().double() - ref).abs().max().item()
     print(f"attention over_{'t' if over_t else 'f'} cplx={cplx}: max err {err:.3e}")
     assert err < 2e-5
+
+
+@pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (512, 7, 9), (128, 33, 15)])
+def test_lstm_engines_agree(h, b, t):
+    """fp32 FMA recurrence vs mma.sync 3xTF32 recurrence vs fp64 recurrence."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(h + b)
+    xp = torch.randn(b, t, 4 * h, generator=g)
+    whh = torch.randn(h // 8, h, 32, generator=g) / np.sqrt(h)
+    ref = emu_ops.lstm_seq(xp.double(), whh.double(), h)
+    errs = []
+    try:
+        for eng in (0, 1):
+            ops.set_lstm_engine(eng)
+            got = ops.lstm_seq(xp.to(dev), whh.to(dev), h)
+            torch.cuda.synchronize()
+            errs.append((got.cpu().double() - ref).abs().max().item())
+    finally:
+        ops.set_lstm_engine(1)
+    print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}")
+    assert errs[0] < 2e-5 and errs[1] < 2e-5
