@@ -112,3 +112,18 @@ def enhance_uformer_ref(net, wav):
     y = y.squeeze(0).numpy()
     taps = {"c": c, "est": est.squeeze(0).numpy(), "y_norm": y.astype(np.float32)}
     return (y / c).astype(np.float32), taps                                 # :47-48
+
+
+def enhance_uformer(sd, wav):
+    """``Uformer/uformer_decode.py:38-50`` with the functional restatement of the network
+    (oracle.nets.uformer_forward); STFT / iSTFT as uformer.py:178,276 (512/400/160, no ``length``)."""
+    from . import nets as _n
+    n_fft, win, hop = dsp.GEOMETRIES["uformer"]
+    x, c = dsp.rms_scale(wav)
+    spec = dsp.stft(x.astype(np.float32), n_fft, win, hop)                  # [F,T] complex64
+    with torch.no_grad():
+        er, ei = _n.uformer_forward(sd, torch.from_numpy(spec.real.copy())[None], torch.from_numpy(spec.imag.copy())[None])
+    est = (er[0].numpy() + 1j * ei[0].numpy()).astype(np.complex64)
+    y = dsp.istft(est, n_fft, win, hop, None)
+    taps = {"c": c, "est": np.stack([est.real, est.imag]), "y_norm": y.astype(np.float32)}
+    return (y / c).astype(np.float32), taps

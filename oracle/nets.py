@@ -244,3 +244,178 @@ def dccrn_forward(sd, inputs, crop_first=True, taps=None):
     est_mags = torch.tanh(mask_mags) * spec_mags                            # :216-217
     est_phase = spec_phase + mask_phase
     return torch.stack([est_mags * torch.cos(est_phase), est_mags * torch.sin(est_phase)], 1)
+
+
+# ----------------------------------------------------------------------------------------
+# Uformer  (Uformer/uformer.py and the block files it imports)
+# ----------------------------------------------------------------------------------------
+UF_EPS = torch.finfo(torch.float32).eps          # EPSILON in every Uformer file
+_UF_KN = [1, 8, 16, 32, 64, 128, 128]            # uformer.py:45
+_UF_DIL = [1, 2, 4, 8, 16, 32, 64, 128]          # dilated_dualpath_conformer.py:39
+
+
+def _uf_fusion(c, m):
+    """fusion.py:13-19.  c [N,C,F,T,2], m [N,C,F,T]."""
+    cm = torch.sqrt(torch.clamp(c[..., 0] ** 2 + c[..., 1] ** 2, UF_EPS))
+    sg = torch.sigmoid(m)
+    return torch.stack([c[..., 0] + sg, c[..., 1] + sg], -1), m + torch.sigmoid(cm)
+
+
+def _uf_cconv(x, sd, pre, transpose, **kw):
+    """ComplexConv2d_Encoder / _Decoder (conv2d_cplx.py:31-38, 62-68): real/imag cross terms, then
+    truncation to the input length on T."""
+    f = F.conv_transpose2d if transpose else F.conv2d
+    wr, br, wi, bi = (sd[pre + ".real_conv.weight"], sd[pre + ".real_conv.bias"], sd[pre + ".imag_conv.weight"],
+                      sd[pre + ".imag_conv.bias"])
+    xr, xi = x[..., 0], x[..., 1]
+    t = xr.shape[-1]
+    orr = f(xr, wr, br, **kw) - f(xi, wi, bi, **kw)
+    oi = f(xi, wr, br, **kw) + f(xr, wi, bi, **kw)
+    return torch.stack([orr[..., :t], oi[..., :t]], -1)
+
+
+def _uf_rconv(x, sd, pre, transpose, **kw):
+    """RealConv2d_Encoder / _Decoder (conv2d_real.py:33-36, 57-61)."""
+    f = F.conv_transpose2d if transpose else F.conv2d
+    return f(x, sd[pre + ".conv.weight"], sd[pre + ".conv.bias"], **kw)[..., :x.shape[-1]]
+
+
+def _uf_ln(x, sd, pre, dim):
+    """nn.LayerNorm over channel axis ``dim`` (the x.transpose(dim, -1) idiom, e.g. ff_cplx.py:23)."""
+    return F.layer_norm(x.transpose(dim, -1), (x.shape[dim],), sd[pre + ".weight"], sd[pre + ".bias"]).transpose(dim, -1)
+
+
+def _uf_clinear(x, sd, pre):
+    """Complex_Linear (linear_cplx.py:20-26) on [..., C, 2]-last-but-one layout [..., in, 2]."""
+    lr = lambda v: F.linear(v, sd[pre + ".real_linear.weight"], sd[pre + ".real_linear.bias"])   # noqa: E731
+    li = lambda v: F.linear(v, sd[pre + ".imag_linear.weight"], sd[pre + ".imag_linear.bias"])   # noqa: E731
+    xr, xi = x[..., 0], x[..., 1]
+    return torch.stack([lr(xr) - li(xi), lr(xi) + li(xr)], -1)
+
+
+def _uf_rlinear(x, sd, pre):
+    return F.linear(x, sd[pre + ".linear.weight"], sd[pre + ".linear.bias"])
+
+
+def _uf_ff(x, sd, pre, cplx):
+    """FF_Cplx / FF_Real (ff_cplx.py:21-33, ff_real.py:21-33)."""
+    y = _uf_ln(x, sd, pre + ".layernorm_linear", 1)
+    if cplx:
+        y = y.transpose(1, 3)                                   # N T F C 2
+        y = _uf_clinear(y, sd, pre + ".linear1")
+        y = F.prelu(y, sd[pre + ".prelu.weight"])
+        y = _uf_clinear(y, sd, pre + ".linear2").transpose(1, 3)
+    else:
+        y = y.transpose(1, 3)
+        y = _uf_rlinear(y, sd, pre + ".linear1")
+        y = F.prelu(y, sd[pre + ".prelu.weight"])
+        y = _uf_rlinear(y, sd, pre + ".linear2").transpose(1, 3)
+    return y * 0.5 + x
+
+
+def _uf_att1(q, k, v, sd, pre):
+    """T_att / F_att (t_att_cplx.py:21-38): softmax(q k^T / sqrt(16)) v with three Real_Linear(128,16)."""
+    qq, kk, vv = _uf_rlinear(q, sd, pre + ".query"), _uf_rlinear(k, sd, pre + ".key"), _uf_rlinear(v, sd, pre + ".value")
+    e = torch.softmax(qq @ kk.transpose(1, 2) / 16 ** 0.5, dim=-1)
+    return e @ vv
+
+
+def _uf_attention(x, sd, pre, cplx, over_t):
+    """Multihead_Attention_{T,F}_Branch[_real] (t_att_cplx.py:40-96, f_att_cplx.py:33-88, *_real.py)."""
+    letter = "T" if over_t else "F"
+    h0 = pre + ".attn_heads.0"
+    if cplx:
+        n, c, f, t, ri = x.shape
+        s = x.permute(0, 2, 3, 1, 4) if over_t else x.permute(0, 3, 2, 1, 4)      # N F T C 2 | N T F C 2
+        s = s.contiguous().view(-1, s.shape[2], c, ri)
+        s = F.layer_norm(s.transpose(2, 3), (c,), sd[h0 + ".layernorm1.weight"], sd[h0 + ".layernorm1.bias"]).transpose(2, 3)
+        re, im = s[..., 0], s[..., 1]
+        a = lambda i, q, k, v: _uf_att1(q, k, v, sd, f"{h0}.{letter}_att{i}")   # noqa: E731
+        real_att = a(1, re, re, re) - a(2, re, im, im) - a(3, im, re, im) - a(4, im, im, re)
+        imag_att = a(5, re, re, im) + a(6, re, im, re) + a(7, im, re, re) - a(8, im, im, im)
+        o = torch.stack([real_att, imag_att], -1)
+        o = F.layer_norm(o.transpose(2, 3), (16,), sd[h0 + ".layernorm2.weight"], sd[h0 + ".layernorm2.bias"]).transpose(2, 3)
+        o = _uf_clinear(o, sd, pre + ".transform_linear")
+        o = o.contiguous().view(n, f, t, c, ri).permute(0, 3, 1, 2, 4) if over_t else \
+            o.contiguous().view(n, t, f, c, ri).permute(0, 3, 2, 1, 4)
+        o = F.prelu(_uf_ln(o, sd, pre + ".layernorm3", 1), sd[pre + ".prelu.weight"])
+        return o + x
+    n, c, f, t = x.shape
+    s = x.permute(0, 2, 3, 1) if over_t else x.permute(0, 3, 2, 1)
+    s = s.contiguous().view(-1, s.shape[2], c)
+    o = F.layer_norm(s, (c,), sd[h0 + ".layernorm1.weight"], sd[h0 + ".layernorm1.bias"])
+    o = _uf_att1(o, o, o, sd, f"{h0}.{letter}_att")
+    o = F.layer_norm(o, (16,), sd[h0 + ".layernorm2.weight"], sd[h0 + ".layernorm2.bias"])
+    o = _uf_rlinear(o, sd, pre + ".transform_linear")
+    o = o.contiguous().view(n, f, t, c) if over_t else o.contiguous().view(n, t, f, c)
+    o = F.prelu(F.layer_norm(o, (c,), sd[pre + ".layernorm3.weight"], sd[pre + ".layernorm3.bias"]),
+                sd[pre + ".prelu.weight"])
+    o = o.permute(0, 3, 1, 2) if over_t else o.permute(0, 3, 2, 1)
+    return o + x
+
+
+def _uf_dsconv(x, sd, pre, cplx, d1, d2):
+    """DSConv2d / DSConv2d_Real (dsconv2d_cplx.py:44-60)."""
+    conv = _uf_cconv if cplx else _uf_rconv
+    y = _uf_ln(x, sd, pre + ".layernorm_conv1", 1)
+    y = conv(y, sd, pre + ".conv1x1", False)
+    y = F.prelu(y, sd[pre + ".prelu.weight"])
+    y1 = conv(y, sd, pre + ".dconv1", False, padding=(1, d1), dilation=(1, d1))
+    y2 = conv(y, sd, pre + ".dconv2", False, padding=(1, d2), dilation=(1, d2))
+    y = y1 * torch.sigmoid(y2)
+    y = _uf_ln(y, sd, pre + ".layernorm_conv2", 1)
+    y = y * torch.sigmoid(y)
+    return x + conv(y, sd, pre + ".sconv", False)
+
+
+def uformer_forward(sd, x_re, x_im, taps=None):
+    """Uformer.forward from the noisy spectrum on (uformer.py:197-262); the STFT / iSTFT around it live in
+    oracle.decode.  x_re, x_im [B,257,T] -> est (real, imag) [B,257,T]."""
+    x_re, x_im = x_re.unsqueeze(1), x_im.unsqueeze(1)
+    mag = torch.sqrt(torch.clamp(x_re ** 2 + x_im ** 2, UF_EPS))            # :197
+    phase = torch.atan2(x_im + UF_EPS, x_re)
+    mag0, phase0 = mag, phase
+    out = torch.stack([mag * torch.cos(phase), mag * torch.sin(phase)], -1)[:, :, 1:]   # :205-209
+    mag = mag[:, :, 1:]                                                      # :210
+    enc_c, enc_m = [], []
+    for i in range(6):                                                       # :214-219
+        out = _uf_cconv(out, sd, f"encoder.{i}.0", False, stride=(2, 1), padding=(2, 1))
+        out = F.batch_norm(out, sd[f"encoder.{i}.1.running_mean"], sd[f"encoder.{i}.1.running_var"],
+                           sd[f"encoder.{i}.1.weight"], sd[f"encoder.{i}.1.bias"], False, 0.0, BN_EPS)
+        out = F.prelu(out, sd[f"encoder.{i}.2.weight"])
+        mag = _uf_rconv(mag, sd, f"encoder_real.{i}.0", False, stride=(2, 1), padding=(2, 1))
+        mag = F.prelu(_bn(mag, sd, f"encoder_real.{i}.1"), sd[f"encoder_real.{i}.2.weight"])
+        out, mag = _uf_fusion(out, mag)
+        enc_c.append(out)
+        enc_m.append(mag)
+    c = "conformer."                                                         # dilated_dualpath_conformer.py:53-78
+    out, mag = _uf_fusion(_uf_ff(out, sd, c + "ff1_cplx", True), _uf_ff(mag, sd, c + "ff1_mag", False))
+    out, mag = _uf_fusion(_uf_attention(out, sd, c + "cplx_tatt", True, True), _uf_attention(mag, sd, c + "mag_tatt", False, True))
+    out, mag = _uf_fusion(_uf_attention(out, sd, c + "cplx_fatt", True, False), _uf_attention(mag, sd, c + "mag_fatt", False, False))
+    for i in range(8):
+        out = _uf_dsconv(out, sd, c + f"dsconv_cplx.{i}", True, _UF_DIL[i], _UF_DIL[7 - i])
+        mag = _uf_dsconv(mag, sd, c + f"dsconv_real.{i}", False, _UF_DIL[i], _UF_DIL[7 - i])
+        out, mag = _uf_fusion(out, mag)
+    out, mag = _uf_fusion(_uf_ff(out, sd, c + "ff2_cplx", True), _uf_ff(mag, sd, c + "ff2_mag", False))
+    out, mag = _uf_ln(out, sd, c + "ln_conformer_cplx", 1), _uf_ln(mag, sd, c + "ln_conformer_mag", 1)
+    if taps is not None:
+        taps["conf_c"], taps["conf_m"] = out, mag
+    for di in range(6):                                                      # uformer.py:225-232
+        kw = dict(stride=(2, 1), padding=(2, 0), output_padding=(1, 0))
+        out = _uf_cconv(torch.cat([enc_c[-1 - di], out], 1), sd, f"decoder.{di}.0", True, **kw)
+        mag = _uf_rconv(torch.cat([enc_m[-1 - di], mag], 1), sd, f"decoder_real.{di}.0", True, **kw)
+        if di < 5:
+            out = F.batch_norm(out, sd[f"decoder.{di}.1.running_mean"], sd[f"decoder.{di}.1.running_var"],
+                               sd[f"decoder.{di}.1.weight"], sd[f"decoder.{di}.1.bias"], False, 0.0, BN_EPS)
+            out = F.prelu(out, sd[f"decoder.{di}.2.weight"])
+            mag = F.prelu(_bn(mag, sd, f"decoder_real.{di}.1"), sd[f"decoder_real.{di}.2.weight"])
+        out, mag = _uf_fusion(out, mag)
+    mag = F.pad(torch.sigmoid(mag), [0, 0, 1, 0])[:, 0] * mag0[:, 0]          # :236-239
+    mr, mi = out[..., 0], out[..., 1]
+    mm = torch.sqrt(torch.clamp(mr ** 2 + mi ** 2, UF_EPS))                  # :244
+    rp, ip = mr / (mm + UF_EPS), mi / (mm + UF_EPS)
+    mmag = F.pad(torch.tanh(mm + UF_EPS), [0, 0, 1, 0])                      # :247,249
+    mph = F.pad(torch.atan2(ip + UF_EPS, rp), [0, 0, 1, 0])                  # :248,250
+    est_mag = (mmag[:, 0] * mag0[:, 0] + mag) * 0.5                          # :254,262
+    est_ph = phase0[:, 0] + mph[:, 0]                                        # :257
+    return est_mag * torch.cos(est_ph), est_mag * torch.sin(est_ph)

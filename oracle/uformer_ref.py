@@ -3,8 +3,8 @@
 TEST INFRASTRUCTURE.  The reference calls the pre-1.8 ``torch.stft/istft`` real-view API and
 ``.cuda()`` unconditionally (uformer.py:178-186,276); both are shimmed here.
 Used by oracle/make_golden.py to write tests/golden/uformer_*.npz (network taps + waveforms).
-A line-by-line functional restatement that can travel to the GPU box is still to be written:
-until then Uformer parity is pinned by these fixtures only.
+The travelling restatement is oracle.nets.uformer_forward / oracle.decode.enhance_uformer; this module pins
+it (make_golden records the waveform max-abs difference in ``ref_vs_oracle``).
 """
 from __future__ import annotations
 
