@@ -178,7 +178,7 @@ int se_deconv_out1(const float* src0, const float* src1, int C0, int C1, int B, 
  *     same way: whh[s][k][gate*HU + j] = W_hh[gate*H + s*HU + j][k]  (size nslices*H*4*HU).
  *     xproj_stride = floats between consecutive (b,t) rows (>= 4H; lets several LSTMs share one
  *     projection GEMM output).  One persistent CTA per slice keeps its W_hh slice resident in shared memory for all
- *     T steps; steps are separated by a device-wide barrier on `sync` (>= 8 unsigned,
+ *     T steps; steps are separated by a device-wide barrier on `sync` (>= 16 unsigned,
  *     zeroed by the caller before each call is NOT required: the kernel is given a base
  *     epoch).  hseq [B, T, H] receives h_t (natural unit order).  work: >= 2*H*Bpad floats,
  *     Bpad = 8*ceil(B/8), scratch for the transposed state.
@@ -189,13 +189,14 @@ int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, in
 /* `ngroups` (<= 8) independent LSTMs of identical shape in ONE launch (DCCRN's four real passes per
  * NavieComplexLSTM, complexnn): group g reads xproj columns [g*xproj_group_off, +4H), weights
  * whh + g*whh_group_stride, writes hseq columns [g*hseq_group_off, +H).  work: ngroups x the single
- * size; sync: >= 8 unsigned. */
+ * size; sync: >= 16 unsigned. */
 int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off, const float* whh,
                       long long whh_group_stride, int ngroups, int B, int T, int H, float* hseq, long long hseq_sb,
                       long long hseq_st, long long hseq_group_off, float* work, unsigned* sync, se_stream_t stream);
-/* Recurrence engine: 1 (default) = legacy mma.sync TF32 tensor path with the 3xTF32 split (W_hh hi part in
- * registers, lo part in shared memory; H in {128, 512, 1024}), 0 = fp32 FMA kernel (any H %% 128 == 0).
- * Process-global; for A/B measurements and tests. */
+/* Recurrence engine: 0 (default) = fp32 FMA kernel (any H %% 128 == 0); 1 = legacy mma.sync TF32 tensor path
+ * with the 3xTF32 split (W_hh hi part in registers, lo part in shared memory; H in {128, 512, 1024}).
+ * Measured on B200 (H=1024, B=64): 13.8 vs 14.4 us/step, see DESIGN.md.  Process-global; for A/B
+ * measurements and tests. */
 int se_set_lstm_engine(int engine);
 /* Bytes of `work` se_lstm_seq needs (per group). */
 long long se_lstm_seq_work_bytes(int B, int H);
@@ -275,6 +276,16 @@ typedef struct se_conv_tc_desc {
   int dstF, dst_f0, dst_fstep;
 } se_conv_tc_desc;
 int se_conv_tf32x3(const se_conv_tc_desc* desc, se_stream_t stream);
+
+/* GCRN gated-conv tail and skip re-activation (csrc/pointwise.cu):
+ *   se_glu_affine_act: x [rows, 2C] = [conv1 | conv2] -> act((conv1 * sigmoid(conv2)) * scale[c] + shift[c])
+ *                      (GluConv2d + eval BatchNorm2d + ELU, GCRN/GCRN_noncprs.py:55-57,138); scale/shift may be NULL.
+ *   se_unary:          y = act(x)  (the ELU applied to cat(BN(deconv), skip), :149-152, re-activates the skip).
+ *   Both write fp32 `out` and/or its TF32 split. */
+int se_glu_affine_act(const float* x, long long rows, int C, const float* scale, const float* shift, int act,
+                      float act_param, float* out, float* out_hi, float* out_lo, se_stream_t stream);
+int se_unary(const float* x, long long n, int act, float act_param, float* out, float* out_hi, float* out_lo,
+             se_stream_t stream);
 
 /* DCCRN polar mask, masking_mode 'E' (DCCRN/DCCRN_cprs.py:201-220):
  *     est = tanh(|M|) * |X| * exp(j(angle X + angle M)),  M = 0 at the DC bin (:203-204).

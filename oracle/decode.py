@@ -127,3 +127,22 @@ def enhance_uformer(sd, wav):
     y = dsp.istft(est, n_fft, win, hop, None)
     taps = {"c": c, "est": np.stack([est.real, est.imag]), "y_norm": y.astype(np.float32)}
     return (y / c).astype(np.float32), taps
+
+
+def enhance_gcrn(sd, wav, p=0.5):
+    """``GCRN/gcrn_decode_vb.py:34-58`` (librosa dialect, compressed RI in, RI out, backend rule (ii);
+    p = 0.5 in the vb script (:40,51), 1.0 in gcrn_decode.py)."""
+    from . import nets as _n
+    n_fft, win, hop = dsp.GEOMETRIES["320"]
+    x, c = dsp.rms_scale(wav)
+    spec = dsp.stft(x, n_fft, win, hop).T                                   # [T,161] complex64
+    mag, ph = (np.abs(spec) ** p).astype(np.float32), np.angle(spec).astype(np.float32)
+    feat = np.stack((mag * np.cos(ph), mag * np.sin(ph)))                   # [2,T,161]  (:45)
+    with torch.no_grad():
+        est = _n.gcrn_forward(sd, torch.from_numpy(feat)[None]).squeeze(0).numpy()
+    emag = np.sqrt(est[0] ** 2 + est[1] ** 2) ** (1.0 / p)                  # :48,51
+    eph = np.arctan2(est[1], est[0])                                        # :49
+    de = emag * np.exp(1j * eph)                                            # :55
+    y = dsp.istft(de.T, n_fft, win, hop, length=len(x))                     # :56-57
+    taps = {"c": c, "feat": feat, "est": est, "y_norm": y.astype(np.float32)}
+    return (y / c).astype(np.float32), taps

@@ -419,3 +419,54 @@ def uformer_forward(sd, x_re, x_im, taps=None):
     est_mag = (mmag[:, 0] * mag0[:, 0] + mag) * 0.5                          # :254,262
     est_ph = phase0[:, 0] + mph[:, 0]                                        # :257
     return est_mag * torch.cos(est_ph), est_mag * torch.sin(est_ph)
+
+
+# ----------------------------------------------------------------------------------------
+# GCRN  (GCRN/GCRN_noncprs.py)
+# ----------------------------------------------------------------------------------------
+def _gcrn_glu(x, sd, pre, transpose, output_padding=(0, 0)):
+    """GluConv2d / GluConvTranspose2d (GCRN_noncprs.py:42-83): conv1(x) * sigmoid(conv2(x)), k(1,3) s(1,2)."""
+    if transpose:
+        f = lambda n: F.conv_transpose2d(x, sd[f"{pre}.{n}.weight"], sd[f"{pre}.{n}.bias"], stride=(1, 2),   # noqa: E731
+                                         output_padding=output_padding)
+    else:
+        f = lambda n: F.conv2d(x, sd[f"{pre}.{n}.weight"], sd[f"{pre}.{n}.bias"], stride=(1, 2))   # noqa: E731
+    return f("conv1") * torch.sigmoid(f("conv2"))
+
+
+def gcrn_forward(sd, x, taps=None):
+    """Net.forward, GCRN_noncprs.py:136-165.  x [B,2,T,161] RI -> [B,2,T,161] RI."""
+    enc = []
+    out = x
+    for i in range(1, 6):                                                    # :138-142
+        out = F.elu(_bn(_gcrn_glu(out, sd, f"conv{i}", False), sd, f"bn{i}"))
+        enc.append(out)
+        if taps is not None:
+            taps[f"e{i}"] = out
+    e5 = out
+    # GLSTM.forward, :22-39
+    b, c, t, f = out.shape
+    o = out.transpose(1, 2).contiguous().view(b, t, -1)
+    o = torch.chunk(o, 2, dim=-1)
+    o = torch.stack([_lstm1(o[i].transpose(0, 1), sd, f"glstm.lstm_list1.{i}").transpose(0, 1) for i in range(2)], dim=-1)
+    o = torch.flatten(o, start_dim=-2, end_dim=-1)                           # interleaves the two groups (:28-29)
+    o = F.layer_norm(o, (1024,), sd["glstm.ln1.weight"], sd["glstm.ln1.bias"])
+    o = torch.chunk(o, 2, dim=-1)
+    o = torch.cat([_lstm1(o[i].transpose(0, 1), sd, f"glstm.lstm_list2.{i}").transpose(0, 1) for i in range(2)], dim=-1)
+    o = F.layer_norm(o, (1024,), sd["glstm.ln2.weight"], sd["glstm.ln2.bias"])
+    out = o.view(b, t, c, -1).transpose(1, 2).contiguous()
+    if taps is not None:
+        taps["glstm"] = out
+    out = torch.cat((out, e5), dim=1)                                        # :147
+    res = []
+    for br in (1, 2):                                                        # :149-159: skip is ELU'd a second time
+        d = out
+        for lvl, skip in ((5, enc[3]), (4, enc[2]), (3, enc[1]), (2, enc[0])):
+            op = (0, 1) if lvl == 2 else (0, 0)
+            d = _bn(_gcrn_glu(d, sd, f"conv{lvl}_t_{br}", True, op), sd, f"bn{lvl}_t_{br}")
+            d = F.elu(torch.cat((d, skip), dim=1))
+        d = F.elu(_bn(_gcrn_glu(d, sd, f"conv1_t_{br}", True), sd, f"bn1_t_{br}"))
+        if taps is not None:
+            taps[f"d1_{br}"] = d
+        res.append(F.linear(d, sd[f"fc{br}.weight"], sd[f"fc{br}.bias"]))     # :161-162
+    return torch.cat(res, dim=1)

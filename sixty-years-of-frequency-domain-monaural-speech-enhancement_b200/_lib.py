@@ -72,6 +72,8 @@ PROTOTYPES = {
     "se_group_layernorm": (_I, [_P, _P, _LL, _I, _I, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P]),
     "se_attention": (_I, [_P, _I, _I, _P, _P, _I, _I, _LL, _I, _LL, _I, _LL, _F, _P, _I, _P]),
     "se_uf_mask": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "se_glu_affine_act": (_I, [_P, _LL, _I, _P, _P, _I, _F, _P, _P, _P, _P]),
+    "se_unary": (_I, [_P, _LL, _I, _F, _P, _P, _P, _P]),
     "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
 }
 

@@ -23,6 +23,8 @@ constexpr int kHU = 8;       // hidden units per CTA
 constexpr int kNC = 4 * kHU; // gate columns per CTA
 constexpr int kBT = 64;      // batch tile (rows of the per-step GEMM)
 constexpr int kKC = 16;      // k rows per pipeline stage per warp
+constexpr int kRep = 1;      // replicas of the exchanged state h_t (CTA s reads copy s % kRep).  Measured on B200: 8 copies
+                             // do NOT help (13.7 -> 14.4 us/step): L2 same-line contention is not what bounds a step
 
 struct LstmParams {
   const float* xproj;  // [B, T, xp_stride >= 4H] slice-ordered columns
@@ -62,8 +64,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
   const float* xproj = p.xproj + group * p.xp_goff;
   const float* whh = p.whh + group * p.whh_gstride;
   float* hseq = p.hseq + group * p.hs_goff;
-  float* hT = p.hT + (size_t)group * 2 * H * kBT;
-  unsigned* sync = p.sync + group;
+  float* hT = p.hT + (size_t)group * kRep * 2 * H * kBT;
+  unsigned* sync = p.sync + 2 * group;
+  const float* hT_rd = hT + (size_t)(slice % kRep) * 2 * H * kBT;
 
   // resident weights
   {
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
       }
       __syncthreads();
 
-      const float* hprev = hT + (size_t)((t - 1) & 1) * H * kBT;
+      const float* hprev = hT_rd + (size_t)((t - 1) & 1) * H * kBT;
       float2 acc[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -191,7 +194,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
       const float h = og * tanhf(c);
       cst[idx] = c;
       const int u = slice * kHU + j;
-      hcur[(size_t)u * kBT + b] = (b < p.B) ? h : 0.f;
+#pragma unroll
+      for (int rep = 0; rep < kRep; ++rep) hcur[(size_t)rep * 2 * H * kBT + (size_t)u * kBT + b] = (b < p.B) ? h : 0.f;
       if (b < p.B) hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
     }
     __syncthreads();
@@ -206,7 +210,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
 // ================================================================================================
 // Tensor-core variant of the same recurrence: legacy mma.sync m16n8k8 TF32 with the 3xTF32 split.
 //   * W_hh_hi (TF32) stays in REGISTERS for the whole sequence (A fragments: 2 m-tiles x KT k-tiles
-//     x 4 = 128 registers per thread at H = 1024), W_hh_lo in shared memory in fragment order;
+//     x 4 = 128 registers per thread at H = 1024), W_hh_lo in shared memory in fragment order as
+//     bf16 (|lo| <= 2^-11 |w|, so its 8-bit mantissa costs 2^-20 relative: still fp32 class), which
+//     leaves room for a 4-deep cp.async ring on h (the step is L2-latency bound, not MMA bound);
 //   * h_{t-1} is split hi/lo on the fly while loading the B fragments from the staged chunk;
 //   * per step and warp: 3 x 2 x 8 x KT MMAs; accumulate in fp32 registers (only 3*KT accumulation
 //     steps per warp, then an exact fp32 cross-warp reduction) -> fp32-class accuracy.
@@ -215,6 +221,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
 // on this part (tools/microbench.cu), 5x the fp32 FMA rate this recurrence ran at.
 // ================================================================================================
 constexpr int kHS = 72;  // padded row stride of a staged h chunk (conflict-free B-fragment loads)
+constexpr int kNST = 4;  // cp.async ring depth of the mma kernel
 
 __device__ __forceinline__ unsigned tf32_rna(float x) {
   unsigned r;
@@ -227,14 +234,20 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+constexpr int kHB = 32;   // batch rows per half (the two halves of the 64-row tile ping-pong)
+constexpr int kHS2 = 40;  // padded row stride of a staged half-batch h chunk (conflict-free B fragments)
+
+// The 64-row batch tile is processed as two independent halves A and B that alternate inside a step:
+// while the device-wide barrier of half A (step t) propagates, the CTA computes half B, so the barrier
+// and first-fetch latency (~5 us of a 13.7 us step in the single-phase kernels) is hidden.
 template <int KT>  // k-tiles (of 8) per warp: H = 64 * KT
 __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const LstmParams p) {
   constexpr int H = 64 * KT;
   constexpr int NCH = (KT + 1) / 2;        // chunks of up to 16 k rows
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* wlo = reinterpret_cast<float4*>(smem_raw);                         // [8 warps][2][KT][32 lanes]
-  float* stage = reinterpret_cast<float*>(wlo + kLstmWarps * 2 * KT * 32);   // [8 warps][2][16][kHS] (aliased by red)
-  float* cst = stage + kLstmWarps * 2 * kKC * kHS;                           // [64][8]
+  uint2* wlo = reinterpret_cast<uint2*>(smem_raw);                           // [8 warps][2][KT][32 lanes] 4 x bf16
+  float* stage = reinterpret_cast<float*>(wlo + kLstmWarps * 2 * KT * 32);   // [8 warps][kNST][16][kHS2] (aliased by red)
+  float* cst = stage + kLstmWarps * kNST * kKC * kHS2;                       // [2 halves][32][8]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int G = H / kHU;
@@ -243,11 +256,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
   const float* xproj = p.xproj + group * p.xp_goff;
   const float* whh = p.whh + group * p.whh_gstride + (size_t)slice * H * kNC;   // [H][32]
   float* hseq = p.hseq + group * p.hs_goff;
-  float* hT = p.hT + (size_t)group * 2 * H * kBT;
-  unsigned* sync = p.sync + group;
+  float* hT = p.hT + (size_t)group * kRep * 2 * H * kBT;    // viewed as [half][parity][H][32]
+  unsigned* sync = p.sync + 2 * group;                      // one counter per half
   const int kbase = warp * (H / kLstmWarps);
+  const int nhalves = p.B > kHB ? 2 : 1;
 
-  // resident weights: hi fragments -> registers, lo fragments -> shared memory (fragment order)
   unsigned ahi[2][KT][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -256,154 +269,163 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
       float lo[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int k = kbase + kt * 8 + tig + ((r >> 1) << 2);      // a0,a1: k = tig ; a2,a3: k = tig + 4
-        const int m = mt * 16 + gid + ((r & 1) << 3);              // a0,a2: row gid ; a1,a3: row gid + 8
+        const int k = kbase + kt * 8 + tig + ((r >> 1) << 2);
+        const int m = mt * 16 + gid + ((r & 1) << 3);
         const float w = __ldg(whh + (size_t)k * kNC + m);
         ahi[mt][kt][r] = tf32_rna(w);
-        lo[r] = __uint_as_float(tf32_rna(w - __uint_as_float(ahi[mt][kt][r])));
+        lo[r] = w - __uint_as_float(ahi[mt][kt][r]);
       }
-      wlo[((warp * 2 + mt) * KT + kt) * 32 + lane] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      auto bf = [](float v) { unsigned u = __float_as_uint(v); u += 0x7FFFu + ((u >> 16) & 1u); return u >> 16; };
+      wlo[((warp * 2 + mt) * KT + kt) * 32 + lane] = make_uint2(bf(lo[0]) | (bf(lo[1]) << 16), bf(lo[2]) | (bf(lo[3]) << 16));
     }
-  for (int i = tid; i < kBT * kHU; i += kLstmThreads) cst[i] = 0.f;
+  for (int i = tid; i < 2 * kHB * kHU; i += kLstmThreads) cst[i] = 0.f;
   __syncthreads();
 
-  float* my_stage = stage + warp * (2 * kKC * kHS);
+  float* my_stage = stage + warp * (kNST * kKC * kHS2);
+  const int gb = tid >> 3, gj = tid & 7;   // gate phase: one (batch row, unit) pair per thread
 
   for (int t = 0; t < p.T; ++t) {
-    float xg[2][4];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int idx = tid + r * kLstmThreads;
-      const int b = idx >> 3, j = idx & 7;
+    for (int half = 0; half < nhalves; ++half) {
+      const int bglob = half * kHB + gb;
+      float xg[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        xg[r][g] = 0.f;
-        if (b < p.B) xg[r][g] = __ldg(xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * kNC + g * kHU + j);
+        xg[g] = 0.f;
+        if (bglob < p.B)
+          xg[g] = __ldg(xproj + ((size_t)bglob * p.T + t) * (size_t)p.xp_stride + slice * kNC + g * kHU + gj);
       }
-    }
+      float* hbase = hT + (size_t)half * 2 * H * kHB;      // [parity][H][32]
 
-    if (t > 0) {
-      if (tid == 0) {
-        const unsigned target = (unsigned)t * (unsigned)G;
-        while (ld_acquire_u32(sync) < target) {
+      if (t > 0) {
+        if (tid == 0) {
+          const unsigned target = (unsigned)t * (unsigned)G;
+          while (ld_acquire_u32(sync + half) < target) {
+          }
         }
-      }
-      __syncthreads();
-      const float* hprev = hT + (size_t)((t - 1) & 1) * H * kBT;
-      float acc[2][8][4];
+        __syncthreads();
+        const float* hprev = hbase + (size_t)((t - 1) & 1) * H * kHB;
+        float acc[2][4][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+          for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
+            for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
 
-      auto issue = [&](int c, int buf) {
-        const int rows = min(kKC, KT * 8 - c * kKC);
-        const float* g = hprev + (size_t)(kbase + c * kKC) * kBT;
-        float* s = my_stage + buf * (kKC * kHS);
-        for (int piece = lane; piece < rows * 16; piece += 32) {   // 16-byte pieces: 16 per 64-float row
-          const int r = piece >> 4, q = piece & 15;
-          cp_async16(s + r * kHS + q * 4, g + r * kBT + q * 4);
-        }
-        cp_async_commit();
-      };
-
-      issue(0, 0);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int buf = c & 1;
-        if (c + 1 < NCH) {
-          issue(c + 1, buf ^ 1);
-          cp_async_wait<1>();
-        } else {
-          cp_async_wait<0>();
-        }
-        __syncwarp();
-        const float* hs = my_stage + buf * (kKC * kHS);
-#pragma unroll
-        for (int k2 = 0; k2 < 2; ++k2) {
-          const int kt = c * 2 + k2;
-          if (kt < KT) {
-            unsigned alo[2][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              const float4 v = wlo[((warp * 2 + mt) * KT + kt) * 32 + lane];
-              alo[mt][0] = __float_as_uint(v.x); alo[mt][1] = __float_as_uint(v.y);
-              alo[mt][2] = __float_as_uint(v.z); alo[mt][3] = __float_as_uint(v.w);
+        auto issue = [&](int c) {   // always commits a group (possibly empty) so wait_group counts stay uniform
+          if (c < NCH) {
+            const int rows = min(kKC, KT * 8 - c * kKC);
+            const float* g = hprev + (size_t)(kbase + c * kKC) * kHB;
+            float* s = my_stage + (c % kNST) * (kKC * kHS2);
+            for (int piece = lane; piece < rows * 8; piece += 32) {   // 16-byte pieces: 8 per 32-float row
+              const int r = piece >> 3, q = piece & 7;
+              cp_async16(s + r * kHS2 + q * 4, g + r * kHB + q * 4);
             }
+          }
+          cp_async_commit();
+        };
+
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-              const float h0 = hs[(k2 * 8 + tig) * kHS + nt * 8 + gid];
-              const float h1 = hs[(k2 * 8 + tig + 4) * kHS + nt * 8 + gid];
-              const unsigned b0h = tf32_rna(h0), b1h = tf32_rna(h1);
-              const unsigned b0l = tf32_rna(h0 - __uint_as_float(b0h)), b1l = tf32_rna(h1 - __uint_as_float(b1h));
+        for (int c = 0; c < kNST - 1; ++c) issue(c);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          issue(c + kNST - 1);
+          cp_async_wait<kNST - 1>();
+          __syncwarp();
+          const float* hs = my_stage + (c % kNST) * (kKC * kHS2);
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const int kt = c * 2 + k2;
+            if (kt < KT) {
+              unsigned alo[2][4];
 #pragma unroll
               for (int mt = 0; mt < 2; ++mt) {
-                mma_tf32(acc[mt][nt], alo[mt], b0h, b1h);
-                mma_tf32(acc[mt][nt], ahi[mt][kt], b0l, b1l);
-                mma_tf32(acc[mt][nt], ahi[mt][kt], b0h, b1h);
+                const uint2 v = wlo[((warp * 2 + mt) * KT + kt) * 32 + lane];
+                alo[mt][0] = v.x << 16; alo[mt][1] = v.x & 0xFFFF0000u;
+                alo[mt][2] = v.y << 16; alo[mt][3] = v.y & 0xFFFF0000u;
+              }
+#pragma unroll
+              for (int np = 0; np < 2; ++np) {   // two batch tiles at a time: 12 MMAs on 4 independent accumulators
+                unsigned bh[2][2], bl[2][2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const int nt = np * 2 + q;
+                  const float h0 = hs[(k2 * 8 + tig) * kHS2 + nt * 8 + gid];
+                  const float h1 = hs[(k2 * 8 + tig + 4) * kHS2 + nt * 8 + gid];
+                  // hi = truncation to TF32 (bit mask, full-rate ALU); lo = exact remainder, the MMA ignores
+                  // its low 13 bits: together 21 mantissa bits
+                  bh[q][0] = __float_as_uint(h0) & 0xFFFFE000u; bh[q][1] = __float_as_uint(h1) & 0xFFFFE000u;
+                  bl[q][0] = __float_as_uint(h0 - __uint_as_float(bh[q][0]));
+                  bl[q][1] = __float_as_uint(h1 - __uint_as_float(bh[q][1]));
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][np * 2 + q], alo[mt], bh[q][0], bh[q][1]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][np * 2 + q], ahi[mt][kt], bl[q][0], bl[q][1]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][np * 2 + q], ahi[mt][kt], bh[q][0], bh[q][1]);
               }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
+        cp_async_wait<0>();
+
+        // partial tile -> red[warp][b][col'] (b < 32; swizzle as in the FMA kernel; aliases this warp's stage)
+        float* red = my_stage;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int col = mt * 16 + gid + ((r >> 1) << 3);
+              const int b = nt * 8 + 2 * tig + (r & 1);
+              red[b * kNC + ((((col >> 3) ^ (b & 3)) << 3) | (col & 7))] = acc[mt][nt][r];
+            }
+        __syncthreads();
       }
 
-      // partial tile -> red[warp][b][col'] (same swizzle as the FMA kernel; aliases this warp's stage)
-      float* red = my_stage;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int col = mt * 16 + gid + ((r >> 1) << 3);
-            const int b = nt * 8 + 2 * tig + (r & 1);
-            red[b * kNC + ((((col >> 3) ^ (b & 3)) << 3) | (col & 7))] = acc[mt][nt][r];
-          }
-      __syncthreads();
-    }
-
-    float* hcur = hT + (size_t)(t & 1) * H * kBT;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int idx = tid + r * kLstmThreads;
-      const int b = idx >> 3, j = idx & 7;
-      float g4[4] = {xg[r][0], xg[r][1], xg[r][2], xg[r][3]};
+      float g4[4] = {xg[0], xg[1], xg[2], xg[3]};
       if (t > 0) {
 #pragma unroll
         for (int w = 0; w < kLstmWarps; ++w) {
-          const float* red = stage + w * (2 * kKC * kHS) + b * kNC;
+          const float* red = stage + w * (kNST * kKC * kHS2) + gb * kNC;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) g4[g] += red[((g ^ (b & 3)) << 3) + j];
+          for (int g = 0; g < 4; ++g) g4[g] += red[((g ^ (gb & 3)) << 3) + gj];
         }
       }
       const float ig = sigmoid_f(g4[0]);
       const float fg = sigmoid_f(g4[1]);
       const float gg = tanhf(g4[2]);
       const float og = sigmoid_f(g4[3]);
-      const float c = fg * cst[idx] + ig * gg;
+      const float c = fg * cst[half * kHB * kHU + tid] + ig * gg;
       const float h = og * tanhf(c);
-      cst[idx] = c;
-      const int u = slice * kHU + j;
-      hcur[(size_t)u * kBT + b] = (b < p.B) ? h : 0.f;
-      if (b < p.B) hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
-    }
-    __syncthreads();
-    if (tid == 0 && t + 1 < p.T) {
-      __threadfence();
-      red_release_add(sync, 1u);
+      cst[half * kHB * kHU + tid] = c;
+      const int u = slice * kHU + gj;
+      hbase[(size_t)(t & 1) * H * kHB + (size_t)u * kHB + gb] = (bglob < p.B) ? h : 0.f;
+      if (bglob < p.B) hseq[(size_t)bglob * p.hs_sb + (size_t)t * p.hs_st + u] = h;
+      __syncthreads();
+      if (tid == 0 && t + 1 < p.T) {
+        __threadfence();
+        red_release_add(sync + half, 1u);
+      }
     }
   }
 }
 
-static int g_lstm_engine = 1;  // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel where instantiated
+static int g_lstm_engine = 0;  // 0: fp32 FMA kernel (default: measured 13.8 us/step vs 14.4), 1: mma.sync 3xTF32 kernel
 
 template <int KT>
 static cudaError_t launch_lstm_mma(const LstmParams& p, int G, cudaStream_t s) {
-  const size_t smem = (size_t)kLstmWarps * 2 * KT * 32 * sizeof(float4) +
-                      ((size_t)kLstmWarps * 2 * kKC * kHS + kBT * kHU) * sizeof(float);
+  const size_t smem = (size_t)kLstmWarps * 2 * KT * 32 * sizeof(uint2) +
+                      ((size_t)kLstmWarps * kNST * kKC * kHS2 + kBT * kHU) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(lstm_seq_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&p};
@@ -416,7 +438,7 @@ using namespace se;
 
 extern "C" long long se_lstm_seq_work_bytes(int B, int H) {
   (void)B;
-  return 2ll * H * kBT * (long long)sizeof(float);
+  return (long long)kRep * 2ll * H * kBT * (long long)sizeof(float);
 }
 
 extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off,
@@ -444,7 +466,7 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
     set_error("se_lstm_seq: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
-  e = cudaMemsetAsync(sync, 0, 8 * sizeof(unsigned), s);
+  e = cudaMemsetAsync(sync, 0, 16 * sizeof(unsigned), s);
   if (e != cudaSuccess) {
     set_error("se_lstm_seq: memset: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;

@@ -209,7 +209,7 @@ def lstm_seq(xproj, whh, hidden, out=None):
     lib = _lib.load()
     work = torch.empty(lib.se_lstm_seq_work_bytes(min(b, _LSTM_MAX_B), hidden) // 4, device=xproj.device,
                        dtype=torch.float32)
-    sync = torch.zeros(8, device=xproj.device, dtype=torch.int32)
+    sync = torch.zeros(16, device=xproj.device, dtype=torch.int32)
     for b0 in range(0, b, _LSTM_MAX_B):
         nb = min(_LSTM_MAX_B, b - b0)
         xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
@@ -368,7 +368,7 @@ def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
     lib = _lib.load()
     work = torch.empty(ngroups * lib.se_lstm_seq_work_bytes(min(b, _LSTM_MAX_B), hidden) // 4, device=xproj.device,
                        dtype=torch.float32)
-    sync = torch.zeros(8, device=xproj.device, dtype=torch.int32)
+    sync = torch.zeros(16, device=xproj.device, dtype=torch.int32)
     for b0 in range(0, b, _LSTM_MAX_B):
         nb = min(_LSTM_MAX_B, b - b0)
         xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
@@ -481,3 +481,33 @@ def uf_mask(cmask, mdec, mag, phase):
 def set_lstm_engine(engine: int):
     """0 = fp32 FMA recurrence kernel, 1 = mma.sync 3xTF32 recurrence kernel (default)."""
     check(_lib.load().se_set_lstm_engine(int(engine)), "se_set_lstm_engine")
+
+
+def glu_affine_act(x, scale, shift, act="elu", act_param=0.0, want_f32=True, want_pair=False):
+    """x [..., 2C] = [a | b] -> act((a * sigmoid(b)) * scale + shift) [..., C]."""
+    _need_cuda(x, scale, shift)
+    device_check()
+    c = x.shape[-1] // 2
+    rows = x.numel() // (2 * c)
+    assert x.is_contiguous()
+    mk = lambda: torch.empty(*x.shape[:-1], c, device=x.device, dtype=torch.float32)   # noqa: E731
+    out = mk() if want_f32 else None
+    pair = (mk(), mk()) if want_pair else None
+    with _Timed("glu_affine_act"):
+        check(_lib.load().se_glu_affine_act(_ptr(x), rows, c, _ptr(scale), _ptr(shift), ACT[act], float(act_param),
+                                            _ptr(out), _ptr(pair[0] if pair else None),
+                                            _ptr(pair[1] if pair else None), _stream()), "se_glu_affine_act")
+    return out, pair
+
+
+def unary(x, act, act_param=0.0, want_f32=True, want_pair=False):
+    _need_cuda(x)
+    device_check()
+    assert x.is_contiguous()
+    out = torch.empty_like(x) if want_f32 else None
+    pair = (torch.empty_like(x), torch.empty_like(x)) if want_pair else None
+    with _Timed("unary"):
+        check(_lib.load().se_unary(_ptr(x), x.numel(), ACT[act], float(act_param), _ptr(out),
+                                   _ptr(pair[0] if pair else None), _ptr(pair[1] if pair else None), _stream()),
+              "se_unary")
+    return out, pair

@@ -274,7 +274,25 @@ def uf_mask(cmask, mdec, mag, phase):
     return torch.stack([em * torch.cos(ph), em * torch.sin(ph)], -1)
 
 
-_UF_NAMES = ("gemm_tf32x3_ex", "uf_prep", "uf_fusion", "group_layernorm", "attention", "uf_mask")
+def glu_affine_act(x, scale, shift, act="elu", act_param=0.0, want_f32=True, want_pair=False):
+    from se_b200 import packing
+    c = x.shape[-1] // 2
+    y = x[..., :c] * torch.sigmoid(x[..., c:])
+    if scale is not None:
+        y = y * scale
+    if shift is not None:
+        y = y + shift
+    y = _act(y, act, act_param)
+    return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
+
+
+def unary(x, act, act_param=0.0, want_f32=True, want_pair=False):
+    from se_b200 import packing
+    y = _act(x, act, act_param)
+    return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
+
+
+_UF_NAMES = ("glu_affine_act", "unary", "gemm_tf32x3_ex", "uf_prep", "uf_fusion", "group_layernorm", "attention", "uf_mask")
 _orig_install = install
 
 
