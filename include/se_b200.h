@@ -198,6 +198,10 @@ int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xpro
  * Measured on B200 (H=1024, B=64): 13.8 vs 14.4 us/step, see DESIGN.md.  Process-global; for A/B
  * measurements and tests. */
 int se_set_lstm_engine(int engine);
+/* Measurement aid for the tcgen05 engine: dev_buf (device, 128 * nsteps * 10 int64, or NULL to switch off)
+ * receives clock64() stamps of 10 phase boundaries per CTA for steps [first_step, first_step + nsteps); see
+ * csrc/lstm_tc.cu for the event list and tools/lstm_tc_phases.py for the reader. */
+int se_debug_lstm_tc_profile(long long* dev_buf, int first_step, int nsteps);
 /* Bytes of `work` se_lstm_seq needs (per group). */
 long long se_lstm_seq_work_bytes(int B, int H);
 
@@ -304,7 +308,9 @@ int se_dccrn_mask(const float* m, const float* x_re, const float* x_im, long lon
  *   se_group_layernorm: nn.LayerNorm(C) over each of the G channel groups of every row (G = 2: the
  *                 real and imaginary halves share gamma/beta, as x.transpose(1,4) does); optional
  *                 gate (x * sigmoid(gate), dsconv2d_cplx.py:54), post op (1 PReLU, 2 swish), residual add,
- *                 fp32 and/or TF32-split output.
+ *                 fp32 and/or TF32-split output.  C <= 1024.  out_index (NULL = identity, else C ints): channel
+ *                 ch of a group is stored at position out_index[ch] (GCRN's (c,f) -> (f,c) view+transpose after
+ *                 the grouped LSTM, GCRN_noncprs.py:145, without a separate permute pass).
  *   se_attention: single-head-dim-16 attention for nheads (<= 8) heads whose outputs are combined with
  *                 signs into nout (<= 2) groups (t_att_cplx.py:58-67).  qkv [R, ld] rows hold
  *                 (q16|k16|v16) per head; sequence (o, i) starts at row o*outer_stride + i*inner_stride and
@@ -316,8 +322,8 @@ int se_uf_prep(const float* x, int B, int T, int F, float* mag, float* phase, fl
                se_stream_t stream);
 int se_uf_fusion(const float* c, const float* m, long long rows, int C, float* c_out, float* m_out, se_stream_t stream);
 int se_group_layernorm(const float* x, const float* gate, long long rows, int G, int C, const float* gamma,
-                       const float* beta, float eps, int post, float slope, const float* res, float* out, float* out_hi,
-                       float* out_lo, se_stream_t stream);
+                       const float* beta, float eps, int post, float slope, const float* res, const int* out_index,
+                       float* out, float* out_hi, float* out_lo, se_stream_t stream);
 int se_attention(const float* qkv, int ld, int nheads, const int* head_out, const float* head_sign, int nout, int L,
                  long long lstride, int n_outer, long long outer_stride, int n_inner, long long inner_stride, float scale,
                  float* out, int ldo, se_stream_t stream);

@@ -8,16 +8,20 @@ import shutil
 
 from . import ref_shims
 
-WANTED = [("CRN", "wsj0_si84_300h_crn_noncprs_model.pth"), ("LSTM", "vb_lstm_noncprs_model.pth"),
-          ("FullSubNet", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
+# The CRN (70 MB) and LSTM (87 MB) checkpoints are only fetched with --all: every gpurun push re-sends
+# checkpoints/_ref/ and their parity runs are on record in profiles/gpu_tests_ckpt_crn_lstm_r01.log.
+BIG = [("CRN", "wsj0_si84_300h_crn_noncprs_model.pth"), ("LSTM", "vb_lstm_noncprs_model.pth")]
+WANTED = [("FullSubNet", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
           ("DCCRN", "wsj0_si84_300h_dccrn_cprs_model.pth"),
-          ("Uformer", "wsj0_si84_300h_uformer_noncprs_model.pth")]
+          ("Uformer", "wsj0_si84_300h_uformer_noncprs_model.pth"),
+          ("GCRN", "vb_gcrn_cprs_model.pth")]
 DEST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "checkpoints", "_ref")
 
 
 def main():
     os.makedirs(DEST, exist_ok=True)
-    for mdir, name in WANTED:
+    import sys
+    for mdir, name in WANTED + (BIG if "--all" in sys.argv else []):
         src = ref_shims.checkpoint_path(mdir, name)
         dst = os.path.join(DEST, f"{mdir}__{name}")
         if not os.path.exists(dst):

@@ -88,6 +88,37 @@ def dccrn_template(kernel_num=(32, 64, 128, 256, 256, 256), rnn_units=256):
     return d
 
 
+def gcrn_template():
+    """GCRN/GCRN_noncprs.py:86-134 (``Net``): key order as ``Net().state_dict()`` lists it."""
+    d = {}
+    ch = [2, 16, 32, 64, 128, 256]
+    for i in range(1, 6):
+        for c in ("conv1", "conv2"):
+            d[f"conv{i}.{c}.weight"] = (ch[i], ch[i - 1], 1, 3)
+            d[f"conv{i}.{c}.bias"] = (ch[i],)
+    for st in (1, 2):
+        for g in range(2):
+            d.update(_lstm(f"glstm.lstm_list{st}.{g}", 512, 512, 1))
+    for n in ("ln1", "ln2"):
+        d[f"glstm.{n}.weight"] = (1024,)
+        d[f"glstm.{n}.bias"] = (1024,)
+    dec = {5: (512, 128), 4: (256, 64), 3: (128, 32), 2: (64, 16), 1: (32, 1)}
+    for br in (1, 2):
+        for lvl in (5, 4, 3, 2, 1):
+            for c in ("conv1", "conv2"):
+                d[f"conv{lvl}_t_{br}.{c}.weight"] = (dec[lvl][0], dec[lvl][1], 1, 3)
+                d[f"conv{lvl}_t_{br}.{c}.bias"] = (dec[lvl][1],)
+    for i in range(1, 6):
+        d.update(_bn(f"bn{i}", ch[i]))
+    for br in (1, 2):
+        for lvl in (5, 4, 3, 2, 1):
+            d.update(_bn(f"bn{lvl}_t_{br}", dec[lvl][1]))
+    for br in (1, 2):
+        d[f"fc{br}.weight"] = (161, 161)
+        d[f"fc{br}.bias"] = (161,)
+    return d
+
+
 def uformer_template():
     """The 668 state-dict entries of the shipped Uformer checkpoints (names, shapes, order), as listed by
     torch.load on Uformer/BEST_MODEL/*.pth and stored in oracle/uformer_keys.json."""

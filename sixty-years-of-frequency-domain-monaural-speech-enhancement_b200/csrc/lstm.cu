@@ -23,6 +23,7 @@ constexpr int kHU = 8;       // hidden units per CTA
 constexpr int kNC = 4 * kHU; // gate columns per CTA
 constexpr int kBT = 64;      // batch tile (rows of the per-step GEMM)
 constexpr int kKC = 16;      // k rows per pipeline stage per warp
+constexpr int LT_H_PUBLIC = 1024;   // hidden size the tcgen05 engine is built for
 constexpr int kRep = 1;      // replicas of the exchanged state h_t (CTA s reads copy s % kRep).  Measured on B200: 8 copies
                              // do NOT help (13.7 -> 14.4 us/step): L2 same-line contention is not what bounds a step
 
@@ -420,7 +421,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
   }
 }
 
-static int g_lstm_engine = 0;  // 0: fp32 FMA kernel (default: measured 13.8 us/step vs 14.4), 1: mma.sync 3xTF32 kernel
+static int g_lstm_engine = 0;  // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu, H = 1024)
+
+int lstm_tc_supported();
+void lstm_tc_set_profile(long long* dev_buf, int first_step, int nsteps);
+int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
+                       long long hs_sb, long long hs_st, float* work, unsigned* sync, cudaStream_t s);
 
 template <int KT>
 static cudaError_t launch_lstm_mma(const LstmParams& p, int G, cudaStream_t s) {
@@ -438,7 +444,7 @@ using namespace se;
 
 extern "C" long long se_lstm_seq_work_bytes(int B, int H) {
   (void)B;
-  return (long long)kRep * 2ll * H * kBT * (long long)sizeof(float);
+  return 4ll * H * kBT * (long long)sizeof(float);   // tcgen05 engine: {h_hi, h_lo} x 2 parities; others use half
 }
 
 extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off,
@@ -474,6 +480,8 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
   LstmParams p{xproj, xproj_stride, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync, ngroups, xproj_group_off,
                whh_group_stride, hseq_group_off};
   void* args[] = {(void*)&p};
+  if (g_lstm_engine == 2 && H == LT_H_PUBLIC && ngroups == 1 && lstm_tc_supported())
+    return lstm_seq_tc_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, sync, s);
   if (g_lstm_engine == 1 && (H == 1024 || H == 512 || H == 128)) {
     e = H == 1024 ? launch_lstm_mma<16>(p, G, s) : (H == 512 ? launch_lstm_mma<8>(p, G, s) : launch_lstm_mma<2>(p, G, s));
   } else {
@@ -492,8 +500,14 @@ extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const flo
   return se_lstm_seq_multi(xproj, xproj_stride, 0, whh, 0, 1, B, T, H, hseq, hseq_sb, hseq_st, 0, work, sync, stream);
 }
 
+extern "C" int se_debug_lstm_tc_profile(long long* dev_buf, int first_step, int nsteps) {
+  SE_REQUIRE(dev_buf == nullptr || (first_step >= 1 && nsteps >= 1), "se_debug_lstm_tc_profile: bad step range");
+  lstm_tc_set_profile(dev_buf, first_step, nsteps);
+  return SE_OK;
+}
+
 extern "C" int se_set_lstm_engine(int engine) {
-  SE_REQUIRE(engine == 0 || engine == 1, "se_set_lstm_engine: 0 (fp32 FMA) or 1 (mma.sync 3xTF32)");
+  SE_REQUIRE(engine >= 0 && engine <= 2, "se_set_lstm_engine: 0 (fp32 FMA), 1 (mma.sync 3xTF32) or 2 (tcgen05)");
   g_lstm_engine = engine;
   return SE_OK;
 }

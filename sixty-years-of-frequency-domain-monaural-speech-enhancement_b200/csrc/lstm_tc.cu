@@ -1,0 +1,443 @@
+// LSTM recurrence on the 5th-generation tensor cores (tcgen05 + TMEM + TMA + clusters), H = 1024.
+//
+// Same contract as lstm_seq_kernel (lstm.cu): T dependent steps  g_t = xproj_t + h_{t-1} W_hh^T  in
+// ONE launch, W_hh on chip for the whole sequence, h exchanged through L2, one device-wide counter
+// barrier per step.  What changes is where the 2*64*4096*1024 flop of a step run and how much of
+// h_{t-1} every SM has to pull out of L2:
+//
+//   * 128 CTAs = 32 clusters of 4.  Cluster c owns hidden units [32c, 32c+32) = 128 gate columns
+//     (the M of the MMA); CTA rank q of the cluster owns the K slice [256q, 256q+256) of them.
+//     So a CTA reads only a QUARTER of h_{t-1} per step (64 KB x {hi, lo} instead of 256 KB).
+//   * the CTA's W_hh block [128 x 256] is split once into TF32 hi + lo: hi lives in TENSOR MEMORY as
+//     the A operand (128 lanes x 256 columns, tcgen05.st at start-up), lo in shared memory as a
+//     K-major SWIZZLE_128B operand (128 KB).  Nothing of W_hh moves after start-up.
+//   * h_{t-1} is published already split (hi = rna_tf32(h), lo = rna_tf32(h - hi)) in batch-major
+//     [64][1024] so a 2-D TMA box [64 batch x 32 k] is directly the K-major B operand (N = 64).
+//   * 3xTF32:  D0 = W_hi h_hi            (32 accumulation steps -> truncation error of the tensor
+//              D1 = W_hi h_lo + W_lo h_hi  core's fp32 accumulate stays ~1e-6, see gemm_tc.cu)
+//     two TMEM accumulators of 64 columns; the small terms never meet the large one before fp32.
+//   * K-split reduction over distributed shared memory: each CTA drains its [128 x 64] partial with
+//     tcgen05.ld (lane = gate column) and stores the 32 columns of owner rank o into o's `red`
+//     buffer (st.shared::cluster, 128-byte coalesced); after barrier.cluster the owner adds the 4
+//     partials + xproj, runs the cell update for its 8 units x 64 batch rows (c in registers) and
+//     publishes h_t (hseq, h_hi, h_lo), then arrives on the device-wide step counter.
+//
+// Warp roles (192 threads): 0-3 epilogue/gates (TMEM lane quarter = warp), 4 TMA producer + step
+// barrier poller, 5 single-thread MMA issuer.  Every spin is bounded (trap after 4 s) so a protocol
+// bug ends in a launch error instead of a hung device.
+#include "tc_common.cuh"
+
+namespace se {
+
+constexpr int LT_H = 1024;
+constexpr int LT_CL = 4;                    // cluster size = K split
+constexpr int LT_KS = LT_H / LT_CL;         // 256 k per CTA
+constexpr int LT_NB = 64;                   // batch rows (MMA N)
+constexpr int LT_BK = 32;                   // k per TMA stage (128-byte rows)
+constexpr int LT_KB = LT_KS / LT_BK;        // 8 stages' worth per step
+constexpr int LT_STAGES = 4;
+constexpr int LT_CTAS = LT_H / 8;           // 128
+constexpr int LT_THREADS = 192;
+constexpr int LT_WLO_BYTES = 128 * LT_KS * 4;          // 131072
+constexpr int LT_BTILE = LT_NB * LT_BK * 4;            // 8192
+constexpr int LT_STAGE_BYTES = 2 * LT_BTILE;           // h_hi + h_lo
+constexpr int LT_RED_BYTES = LT_CL * LT_NB * 32 * 4;   // 32768
+constexpr int LT_SMEM_BYTES = LT_WLO_BYTES + LT_STAGES * LT_STAGE_BYTES + LT_RED_BYTES + 1024 + 256;
+constexpr unsigned LT_TMEM_COLS = 512;      // A: 0..255, D0: 256..319, D1: 320..383
+constexpr unsigned long long LT_SPIN_NS = 4000000000ull;
+
+struct LtParams {
+  const float* xproj;
+  long long xp_stride;
+  const float* whh;  // [128 slices][1024 k][32]
+  int B, T;
+  float* hseq;
+  long long hs_sb, hs_st;
+  float* h_hi;       // [2 parities][64][1024]
+  float* h_lo;
+  unsigned* sync;
+  // optional phase timestamps (se_debug_lstm_tc_profile): prof[(cta * prof_n + (t - prof_t0)) * LT_NEV + event]
+  long long* prof;
+  int prof_t0, prof_n;
+};
+constexpr int LT_NEV = 10;
+// events: 0 producer starts polling, 1 step barrier observed, 2 last TMA issued, 3 first stage landed (MMA warp),
+//         4 last stage landed, 5 accumulators complete (epilogue), 6 DSMEM partials sent, 7 cluster barrier passed,
+//         8 cell update + stores issued, 9 fences done / arrival on the step counter
+#define LT_STAMP(ev)                                                                                  \
+  do {                                                                                                \
+    if (p.prof && t >= p.prof_t0 && t < p.prof_t0 + p.prof_n)                                         \
+      p.prof[((long long)blockIdx.x * p.prof_n + (t - p.prof_t0)) * LT_NEV + (ev)] = clock64();       \
+  } while (0)
+
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity, unsigned long long t0) {
+  unsigned it = 0;
+  while (!mbar_try(bar, parity)) {
+    if (((++it) & 0xFFu) == 0 && gtimer_ns() - t0 > LT_SPIN_NS) __trap();
+  }
+}
+__device__ __forceinline__ unsigned lt_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lt_red_release(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned map_to_rank(unsigned smem_addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(unsigned addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, uint64_t bdesc, unsigned idesc,
+                                             unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(unsigned taddr, const unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
+    lstm_seq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                       const LtParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* wlo = base;                                         // 8 k-blocks x [128 rows x 128 B], SW128
+  unsigned char* stages = base + LT_WLO_BYTES;                       // LT_STAGES x {h_hi, h_lo} tiles [64 x 128 B]
+  float* red = reinterpret_cast<float*>(stages + LT_STAGES * LT_STAGE_BYTES);   // [4 src][64 b][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + LT_RED_BYTES);
+  uint64_t* full = bars;                 // [LT_STAGES]
+  uint64_t* empty = bars + LT_STAGES;    // [LT_STAGES]
+  uint64_t* accfull = bars + 2 * LT_STAGES;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(accfull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned q = cluster_rank();               // K slice of this CTA / owner rank of its 8 hidden units
+  const int slice = blockIdx.x;                    // hidden units [8*slice, +8): what this CTA's gate phase owns
+  const int cl = blockIdx.x / LT_CL;               // cluster: hidden units [32cl, +32)
+  const unsigned long long t0 = gtimer_ns();
+
+  if (tid == 0) {
+    for (int s = 0; s < LT_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accfull, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_hi);
+    tma_prefetch_desc(&map_lo);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, LT_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  const unsigned tmem_a = tmem_base, tmem_d0 = tmem_base + 256, tmem_d1 = tmem_base + 320;
+
+  // ---- resident weights: row m = 32*o + l  <-  W_hh slice (4cl + o), gate column l; k in this CTA's slice ----
+  if (warp < 4) {
+    const int m = warp * 32 + lane;
+    const float* wsrc = p.whh + ((size_t)(cl * LT_CL + warp) * LT_H + (size_t)q * LT_KS) * 32 + lane;
+    for (int k0 = 0; k0 < LT_KS; k0 += 32) {
+      unsigned hi[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float w = __ldg(wsrc + (size_t)(k0 + i) * 32);
+        float h, l;
+        split_tf32_dev(w, h, l);
+        hi[i] = __float_as_uint(h);
+        // k-block k0/32, row m, 16-byte chunk (i/4) swizzled by (m & 7)
+        unsigned char* dst = wlo + (k0 / 32) * (128 * 128) + m * 128 + ((((i >> 2) ^ (m & 7))) << 4) + ((i & 3) << 2);
+        *reinterpret_cast<float*>(dst) = l;
+      }
+      tmem_st_32x32(tmem_a + ((unsigned)(warp * 32) << 16) + (unsigned)k0, hi);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+  fence_proxy_async();          // generic-proxy smem writes (W_lo) -> visible to the tensor core's async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_arrive();             // every CTA of the cluster is running before anyone touches remote smem
+  cluster_wait();
+
+  if (warp == 4) {
+    // ===================== TMA producer + step-barrier poller =====================
+    int stage = 0;
+    unsigned phase = 0;
+    for (int t = 1; t < p.T; ++t) {
+      if (lane == 0) {
+        const unsigned target = (unsigned)t * (unsigned)LT_CTAS;
+        unsigned it = 0;
+        LT_STAMP(0);
+        while (lt_ld_acquire(p.sync) < target) {
+          if (((++it) & 0xFFu) == 0 && gtimer_ns() - t0 > LT_SPIN_NS) __trap();
+        }
+        LT_STAMP(1);
+        fence_proxy_async();    // h_{t-1} was written with generic stores by other SMs; TMA reads it
+        const int row0 = ((t - 1) & 1) * LT_NB;
+        for (int kb = 0; kb < LT_KB; ++kb) {
+          mbar_wait_bounded(&empty[stage], phase ^ 1, t0);
+          unsigned char* st = stages + stage * LT_STAGE_BYTES;
+          mbar_expect_tx(&full[stage], LT_STAGE_BYTES);
+          tma_load_2d(&map_hi, &full[stage], st, (int)q * LT_KS + kb * LT_BK, row0);
+          tma_load_2d(&map_lo, &full[stage], st + LT_BTILE, (int)q * LT_KS + kb * LT_BK, row0);
+          if (++stage == LT_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        LT_STAMP(2);
+      }
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    constexpr unsigned idesc = make_idesc_tf32(128, LT_NB);
+    int stage = 0;
+    unsigned phase = 0;
+    for (int t = 1; t < p.T; ++t) {
+      if (lane == 0) {
+        for (int kb = 0; kb < LT_KB; ++kb) {
+          mbar_wait_bounded(&full[stage], phase, t0);
+          if (kb == 0) LT_STAMP(3);
+          if (kb == LT_KB - 1) LT_STAMP(4);
+          tc_fence_after();
+          unsigned char* st = stages + stage * LT_STAGE_BYTES;
+          const uint64_t d_bhi = make_smem_desc(st);
+          const uint64_t d_blo = make_smem_desc(st + LT_BTILE);
+          const uint64_t d_alo = make_smem_desc(wlo + kb * (128 * 128));
+#pragma unroll
+          for (int k = 0; k < LT_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+            const unsigned a_t = tmem_a + (unsigned)(kb * LT_BK + k * 8);
+            const unsigned acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_tf32_ts(tmem_d0, a_t, d_bhi + adv, idesc, acc);
+            umma_tf32_ts(tmem_d1, a_t, d_blo + adv, idesc, acc);
+            umma_tf32(tmem_d1, d_alo + adv, d_bhi + adv, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == LT_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(accfull);
+      }
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+    }
+  } else {
+    // ===================== epilogue: K-split reduction over DSMEM, gates, publish =====================
+    float cstate[4] = {0.f, 0.f, 0.f, 0.f};
+    const unsigned red_remote = map_to_rank(smem_u32(red), (unsigned)warp);   // owner of my lane quarter = rank `warp`
+    for (int t = 0; t < p.T; ++t) {
+      float xg[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pr = tid + 128 * i, b = pr >> 3, j = pr & 7;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          xg[i][g] = 0.f;
+          if (b < p.B) xg[i][g] = __ldg(p.xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * 32 + g * 8 + j);
+        }
+      }
+      if (t > 0) {
+        mbar_wait_bounded(accfull, (unsigned)((t - 1) & 1), t0);
+        if (tid == 0) LT_STAMP(5);
+        tc_fence_after();
+        float d0[64], d1[64];
+        tmem_ld_32x64(tmem_d0 + ((unsigned)(warp * 32) << 16), d0);
+        tmem_ld_32x64(tmem_d1 + ((unsigned)(warp * 32) << 16), d1);
+        // lane = gate column (g = lane >> 3, unit j = lane & 7) of owner `warp`; register b = batch row
+#pragma unroll
+        for (int b = 0; b < 64; ++b) {
+          const unsigned off = ((unsigned)q * 2048u + (unsigned)b * 32u + (unsigned)((((lane >> 3) ^ (b & 3)) << 3) | (lane & 7))) * 4u;
+          st_cluster_f32(red_remote + off, d0[b] + d1[b]);
+        }
+        tc_fence_before();
+        if (tid == 0) LT_STAMP(6);
+        cluster_arrive();
+        cluster_wait();
+        if (tid == 0) LT_STAMP(7);
+      }
+      const int par = t & 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pr = tid + 128 * i, b = pr >> 3, j = pr & 7;
+        float g4[4] = {xg[i][0], xg[i][1], xg[i][2], xg[i][3]};
+        if (t > 0) {
+#pragma unroll
+          for (int s = 0; s < LT_CL; ++s)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) g4[g] += red[s * 2048 + b * 32 + (((g ^ (b & 3)) << 3) | j)];
+        }
+        const float ig = sigmoid_f(g4[0]);
+        const float fg = sigmoid_f(g4[1]);
+        const float gg = tanhf(g4[2]);
+        const float og = sigmoid_f(g4[3]);
+        const float c = fg * cstate[i] + ig * gg;
+        float h = og * tanhf(c);
+        cstate[i] = c;
+        const int u = slice * 8 + j;
+        if (b >= p.B) h = 0.f;
+        float hh, hl;
+        split_tf32_dev(h, hh, hl);
+        const size_t o = ((size_t)par * LT_NB + b) * LT_H + u;
+        p.h_hi[o] = hh;
+        p.h_lo[o] = hl;
+        if (b < p.B) p.hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
+      }
+      if (tid == 0) LT_STAMP(8);
+      if (t + 1 < p.T) {
+        fence_proxy_async();
+        __threadfence();
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (tid == 0) lt_red_release(p.sync, 1u);
+      }
+      if (tid == 0) LT_STAMP(9);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, LT_TMEM_COLS);
+}
+
+static int make_h_map(CUtensorMap* map, const float* ptr) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SE_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(2 * LT_NB)};
+  cuuint64_t strides[1] = {(cuuint64_t)LT_H * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)LT_BK, (cuuint32_t)LT_NB};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("se_lstm_seq (tcgen05): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
+// 1 when 32 clusters of 4 CTAs of this kernel can be co-resident on the current device
+int lstm_tc_supported() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cached = 0;
+  if (cudaFuncSetAttribute(lstm_seq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES) != cudaSuccess) {
+    cudaGetLastError();
+    return cached;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(LT_CTAS);
+  cfg.blockDim = dim3(LT_THREADS);
+  cfg.dynamicSmemBytes = LT_SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = LT_CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, lstm_seq_tc_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return cached;
+  }
+  cached = nclusters >= LT_CTAS / LT_CL ? 1 : 0;
+  return cached;
+}
+
+static long long* g_prof = nullptr;
+static int g_prof_t0 = 0, g_prof_n = 0;
+void lstm_tc_set_profile(long long* dev_buf, int first_step, int nsteps) {
+  g_prof = dev_buf;
+  g_prof_t0 = first_step;
+  g_prof_n = nsteps;
+}
+
+// work: [2 arrays][2 parities][64][1024] fp32; sync[0] zeroed by the caller on `s`
+int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
+                       long long hs_sb, long long hs_st, float* work, unsigned* sync, cudaStream_t s) {
+  CUtensorMap map_hi, map_lo;
+  float* h_hi = work;
+  float* h_lo = work + (size_t)2 * LT_NB * LT_H;
+  int rc = make_h_map(&map_hi, h_hi);
+  if (rc != SE_OK) return rc;
+  rc = make_h_map(&map_lo, h_lo);
+  if (rc != SE_OK) return rc;
+  cudaError_t e = cudaFuncSetAttribute(lstm_seq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES);
+  if (e != cudaSuccess) {
+    set_error("se_lstm_seq (tcgen05): %d bytes of shared memory: %s", LT_SMEM_BYTES, cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  LtParams p{xproj, xp_stride, whh, B, T, hseq, hs_sb, hs_st, h_hi, h_lo, sync, g_prof, g_prof_t0, g_prof_n};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(LT_CTAS);
+  cfg.blockDim = dim3(LT_THREADS);
+  cfg.dynamicSmemBytes = LT_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;   // all 128 CTAs co-resident or the launch fails (never a deadlock)
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, lstm_seq_tc_kernel, map_hi, map_lo, p);
+  if (e != cudaSuccess) {
+    set_error("se_lstm_seq (tcgen05): cooperative cluster launch: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return check_launch("se_lstm_seq (tcgen05)");
+}
+
+}  // namespace se

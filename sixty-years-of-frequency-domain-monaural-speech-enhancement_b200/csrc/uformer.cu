@@ -67,8 +67,10 @@ struct LnParams {
   float eps, slope;
   int post;
   float *out, *out_hi, *out_lo;
+  const int* out_index;
 };
 
+template <int PER_MAX>   // channels per lane: C <= 32 * PER_MAX
 __global__ void __launch_bounds__(256) group_layernorm_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -76,10 +78,12 @@ __global__ void __launch_bounds__(256) group_layernorm_kernel(const LnParams p) 
   const long long total = p.rows * p.G;
   for (long long w = warp; w < total; w += nwarps) {
     const long long base = w * p.C;
-    float v[8];  // C <= 256
+    float v[PER_MAX];
     float s = 0.f;
     const int per = (p.C + 31) / 32;
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER_MAX; ++i) {
+      if (i >= per) break;
       const int ch = lane + 32 * i;
       float t = 0.f;
       if (ch < p.C) {
@@ -92,14 +96,18 @@ __global__ void __launch_bounds__(256) group_layernorm_kernel(const LnParams p) 
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)p.C;
     float q = 0.f;
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER_MAX; ++i) {
+      if (i >= per) break;
       const int ch = lane + 32 * i;
       const float d = ch < p.C ? v[i] - mean : 0.f;
       q += d * d;
     }
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)p.C + p.eps);
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER_MAX; ++i) {
+      if (i >= per) break;
       const int ch = lane + 32 * i;
       if (ch >= p.C) continue;
       float y = (v[i] - mean) * rstd * __ldg(p.gamma + ch) + __ldg(p.beta + ch);
@@ -108,12 +116,13 @@ __global__ void __launch_bounds__(256) group_layernorm_kernel(const LnParams p) 
       else if (p.post == 2)
         y = y * sigmoid_f(y);
       if (p.res) y += __ldg(p.res + base + ch);
-      if (p.out) p.out[base + ch] = y;
+      const long long o = base + (p.out_index ? __ldg(p.out_index + ch) : ch);
+      if (p.out) p.out[o] = y;
       if (p.out_hi) {
         float hi, lo;
         split_tf32_dev(y, hi, lo);
-        p.out_hi[base + ch] = hi;
-        p.out_lo[base + ch] = lo;
+        p.out_hi[o] = hi;
+        p.out_lo[o] = lo;
       }
     }
   }
@@ -318,13 +327,16 @@ extern "C" int se_uf_fusion(const float* c, const float* m, long long rows, int 
 }
 
 extern "C" int se_group_layernorm(const float* x, const float* gate, long long rows, int G, int C, const float* gamma,
-                                  const float* beta, float eps, int post, float slope, const float* res, float* out,
-                                  float* out_hi, float* out_lo, se_stream_t stream) {
-  SE_REQUIRE(x && gamma && beta && rows > 0 && G > 0 && C > 0 && C <= 256, "se_group_layernorm: bad arguments (C=%d)", C);
+                                  const float* beta, float eps, int post, float slope, const float* res,
+                                  const int* out_index, float* out, float* out_hi, float* out_lo, se_stream_t stream) {
+  SE_REQUIRE(x && gamma && beta && rows > 0 && G > 0 && C > 0 && C <= 1024, "se_group_layernorm: bad arguments (C=%d)", C);
   SE_REQUIRE(out || out_hi, "se_group_layernorm: no output");
   SE_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "se_group_layernorm: out_hi/out_lo go together");
-  LnParams p{x, gate, gamma, beta, res, rows, G, C, eps, slope, post, out, out_hi, out_lo};
-  group_layernorm_kernel<<<grid_for(rows * G * 32, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  LnParams p{x, gate, gamma, beta, res, rows, G, C, eps, slope, post, out, out_hi, out_lo, out_index};
+  if (C <= 256)
+    group_layernorm_kernel<8><<<grid_for(rows * G * 32, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  else
+    group_layernorm_kernel<32><<<grid_for(rows * G * 32, 256), 256, 0, (cudaStream_t)stream>>>(p);
   return check_launch("se_group_layernorm");
 }
 

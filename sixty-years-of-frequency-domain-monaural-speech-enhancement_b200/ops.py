@@ -432,9 +432,13 @@ _LN_POST = {"none": 0, "prelu": 1, "swish": 2}
 
 
 def group_layernorm(x, groups, gamma, beta, gate=None, post="none", slope=0.0, res=None, want_f32=True,
-                    want_pair=False, eps=1e-5):
-    """LayerNorm over each of ``groups`` channel groups of the last axis (see se_group_layernorm)."""
+                    want_pair=False, eps=1e-5, out_index=None):
+    """LayerNorm over each of ``groups`` channel groups of the last axis (see se_group_layernorm).
+    out_index (int32 [C]): channel ch is stored at position out_index[ch] of its group."""
     _need_cuda(x, gamma, beta, gate, res)
+    if out_index is not None and not out_index.is_cuda:
+        raise _lib.SeB200Error("se_b200 ops need CUDA tensors (no CPU fallback)")
+    assert out_index is None or (out_index.dtype == torch.int32 and out_index.numel() == x.shape[-1] // groups)
     device_check()
     ctot = x.shape[-1]
     c = ctot // groups
@@ -444,7 +448,7 @@ def group_layernorm(x, groups, gamma, beta, gate=None, post="none", slope=0.0, r
     pair = (torch.empty_like(x), torch.empty_like(x)) if want_pair else None
     with _Timed(f"group_layernorm[C={c}]"):
         check(_lib.load().se_group_layernorm(_ptr(x), _ptr(gate), rows, groups, c, _ptr(gamma), _ptr(beta), float(eps),
-                                             _LN_POST[post], float(slope), _ptr(res), _ptr(out),
+                                             _LN_POST[post], float(slope), _ptr(res), _ptr(out_index), _ptr(out),
                                              _ptr(pair[0] if pair else None), _ptr(pair[1] if pair else None),
                                              _stream()), "se_group_layernorm")
     return out, pair
@@ -479,7 +483,7 @@ def uf_mask(cmask, mdec, mag, phase):
 
 
 def set_lstm_engine(engine: int):
-    """0 = fp32 FMA recurrence kernel, 1 = mma.sync 3xTF32 recurrence kernel (default)."""
+    """0 = fp32 FMA recurrence kernel, 1 = mma.sync 3xTF32 kernel, 2 = tcgen05 cluster kernel (H = 1024)."""
     check(_lib.load().se_set_lstm_engine(int(engine)), "se_set_lstm_engine")
 
 

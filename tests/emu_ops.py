@@ -231,7 +231,7 @@ def uf_fusion(c, m):
 
 
 def group_layernorm(x, groups, gamma, beta, gate=None, post="none", slope=0.0, res=None, want_f32=True,
-                    want_pair=False, eps=1e-5):
+                    want_pair=False, eps=1e-5, out_index=None):
     from se_b200 import packing
     v = x if gate is None else x * torch.sigmoid(gate)
     shp = v.shape
@@ -243,6 +243,10 @@ def group_layernorm(x, groups, gamma, beta, gate=None, post="none", slope=0.0, r
         y = y * torch.sigmoid(y)
     if res is not None:
         y = y + res
+    if out_index is not None:
+        z = torch.empty_like(y).reshape(-1, groups, c)
+        z[:, :, out_index.long()] = y.reshape(-1, groups, c)
+        y = z.reshape(shp)
     return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
 
 

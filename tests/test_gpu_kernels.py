@@ -325,9 +325,12 @@ def test_attention_matches_softmax(over_t, cplx):
     assert err < 2e-5
 
 
-@pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (512, 7, 9), (128, 33, 15)])
+DEFAULT_LSTM_ENGINE = 0
+
+
+@pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (1024, 5, 3), (512, 7, 9), (128, 33, 15)])
 def test_lstm_engines_agree(h, b, t):
-    """fp32 FMA recurrence vs mma.sync 3xTF32 recurrence vs fp64 recurrence."""
+    """fp32 FMA / mma.sync 3xTF32 / tcgen05 3xTF32 (H = 1024 only, else the FMA kernel) recurrences vs fp64."""
     dev = _dev()
     import se_b200
     ops = se_b200.ops
@@ -337,12 +340,12 @@ def test_lstm_engines_agree(h, b, t):
     ref = emu_ops.lstm_seq(xp.double(), whh.double(), h)
     errs = []
     try:
-        for eng in (0, 1):
+        for eng in (0, 1, 2):
             ops.set_lstm_engine(eng)
             got = ops.lstm_seq(xp.to(dev), whh.to(dev), h)
             torch.cuda.synchronize()
             errs.append((got.cpu().double() - ref).abs().max().item())
     finally:
-        ops.set_lstm_engine(1)
-    print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}")
-    assert errs[0] < 2e-5 and errs[1] < 2e-5
+        ops.set_lstm_engine(DEFAULT_LSTM_ENGINE)
+    print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}, tcgen05 err {errs[2]:.3e}")
+    assert max(errs) < 2e-5

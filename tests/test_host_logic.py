@@ -167,6 +167,26 @@ def test_dccrn_host_logic_matches_oracle(monkeypatch):
     assert (est2 - ref2).abs().max() < 2e-4 * max(1.0, ref2.abs().max().item())
 
 
+def test_gcrn_host_logic_matches_oracle(monkeypatch):
+    """Gated convs as [a | b] GEMMs, parity-class deconvs with output_padding, grouped-LSTM block weights and the
+    three layout permutations (channels-last flatten, stack+flatten interleave, LayerNorm store index)."""
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t = templates.gcrn_template()
+    sd = synth.synthetic_state_dict(t, seed=6)
+    m = se_b200.gcrn.Net()
+    assert list(m.state_dict().keys()) == list(t.keys())
+    m.load_state_dict(sd)
+    x = torch.randn(2, 2, 7, 161, generator=torch.Generator().manual_seed(3))
+    taps, rtaps = {}, {}
+    est = m._forward_impl(x, taps)
+    with torch.no_grad():
+        ref = nets.gcrn_forward(sd, x, rtaps)
+    for k in ("e1", "e5"):
+        assert (taps[k].permute(0, 3, 1, 2) - rtaps[k]).abs().max() < 1e-4 * max(1.0, rtaps[k].abs().max().item()), k
+    assert (taps["glstm_nhwc"].permute(0, 3, 1, 2) - rtaps["glstm"]).abs().max() < 2e-4
+    assert (est - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
 def test_uformer_host_logic_matches_reference_fixture(monkeypatch):
     """668-entry state-dict drop-in + the whole Uformer orchestration (stacked complex convs, block QKV
     projection, signed head combination, gated dilated convs, fusion) against the fixture written by the

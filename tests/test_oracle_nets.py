@@ -21,6 +21,8 @@ CASES = {
                         "FullSubNet__wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
     "dccrn_synth": (templates.dccrn_template, decode.enhance_dccrn, None),
     "dccrn_ckpt": (templates.dccrn_template, decode.enhance_dccrn, "DCCRN__wsj0_si84_300h_dccrn_cprs_model.pth"),
+    "gcrn_synth": (templates.gcrn_template, decode.enhance_gcrn, None),
+    "gcrn_ckpt": (templates.gcrn_template, decode.enhance_gcrn, "GCRN__vb_gcrn_cprs_model.pth"),
     "uformer_synth": (templates.uformer_template, decode.enhance_uformer, None),
     "uformer_ckpt": (templates.uformer_template, decode.enhance_uformer,
                      "Uformer__wsj0_si84_300h_uformer_noncprs_model.pth"),

@@ -46,7 +46,7 @@ def main():
     xp = torch.randn(B, T, 4 * H, generator=g).to(dev)
     whh = (torch.randn(H // 8, H, 32, generator=g) / 32).to(dev)
     hs = torch.empty(B, T, H, device=dev)
-    for eng, nm in ((0, "fma"), (1, "mma")):
+    for eng, nm in ((0, "fma"), (1, "mma"), (2, "tcgen05")):
         ops.set_lstm_engine(eng)
         ms = timeit(lambda: ops.lstm_seq(xp, whh, H, out=hs), iters=3, warm=1)
         res[f"lstm_seq_{nm}_B64_T401_H1024"] = {"ms": ms, "us_per_step": 1e3 * ms / T,
@@ -55,6 +55,7 @@ def main():
             ref_h = hs.clone()
         else:
             res[f"lstm_seq_{nm}_B64_T401_H1024"]["max_abs_diff_vs_fma"] = (hs - ref_h).abs().max().item()
+    ops.set_lstm_engine(0)
     # conv layers of CRN
     for (fin, c0, c1, co, kind) in [(9, 128, 0, 256, "conv"), (19, 64, 0, 128, "conv"), (4, 256, 256, 128, "deconv"),
                                     (9, 128, 128, 64, "deconv")]:

@@ -28,6 +28,8 @@ CASES = {
               se_b200.decode.enhance_dccrn, odecode.enhance_dccrn, 32, 4, 128, dict(p=0.5)),
     "fullsubnet": (lambda: se_b200.fullsubnet.Model(**FSN_ARGS), templates.fullsubnet_template,
                    se_b200.decode.enhance_fullsubnet, odecode.enhance_fullsubnet, 32, 10, 256, dict(p=0.5)),
+    "gcrn": (lambda: se_b200.gcrn.Net(), templates.gcrn_template, se_b200.decode.enhance_gcrn, odecode.enhance_gcrn,
+             64, 4, 160, dict(p=0.5)),
     "uformer": (lambda: se_b200.Uformer(), templates.uformer_template, se_b200.decode.enhance_uformer, None,
                 64, 4, 160, dict()),
 }
