@@ -311,17 +311,22 @@ def main():
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         traffic = None
         ncu_json = os.path.join(ROOT, "profiles", "ncu_full_r01.json")
+        kname = "lstm_seq_tc_kernel"
         if os.path.exists(ncu_json):      # dram__bytes_read.sum + dram__bytes_write.sum of the committed capture
             for k in json.load(open(ncu_json))["kernels"]:
-                if k["kernel"].startswith("lstm_seq_kernel"):
+                if k["kernel"].startswith(kname):
                     traffic = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) * 1e6
+        # the recurrence computes every product three times (3xTF32: hi*hi, hi*lo, lo*hi) on the TF32 tensor pipe
+        tf32_peak = peak / 2.0
         roofline = {
-            "kernel": "lstm_seq_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_src} bf16 dense, sustained",
-            "pipe": "fp32 FFMA2 on the CUDA cores (single-pass TF32 breaks the 1e-4 gate; W_hh does not fit one "
-                    "SM, the recurrence is the part not yet on tcgen05)",
-            "pipe_peak": FP32_FMA_PEAK_TFLOPS, "frac_of_pipe": achieved / FP32_FMA_PEAK_TFLOPS,
-            "pipe_peak_measured_gemm_like": 57.9,
+            "pipe": "tcgen05 kind::tf32, 3xTF32 split (3 tensor flops per algorithmic flop; single-pass TF32 breaks the "
+                    "1e-4 gate); W_hh hi part in tensor memory, K split over a 4-CTA cluster.  The step is a latency "
+                    "chain (device-wide barrier -> TMA -> MMA -> DSMEM reduce -> cell -> publish), not pipe-bound: "
+                    "profiles/lstm_tc_phases_r01.json",
+            "pipe_peak": tf32_peak / 3.0, "frac_of_pipe": achieved / (tf32_peak / 3.0),
+            "algorithmic_flops_per_launch": rec_flops_per_launch,
             "avg_launch_ms": rec_avg_ms, "dominant_by_time": dom[0], "time_share": share,
             "whole_step_tflops": fl["total"] * BATCH_PER_GPU * T_FRAMES / (ms_step * 1e-3) / 1e12,
         }

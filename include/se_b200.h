@@ -193,13 +193,16 @@ int se_lstm_seq(const float* xproj, long long xproj_stride, const float* whh, in
 int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off, const float* whh,
                       long long whh_group_stride, int ngroups, int B, int T, int H, float* hseq, long long hseq_sb,
                       long long hseq_st, long long hseq_group_off, float* work, unsigned* sync, se_stream_t stream);
-/* Recurrence engine: 0 (default) = fp32 FMA kernel (any H %% 128 == 0); 1 = legacy mma.sync TF32 tensor path
- * with the 3xTF32 split (W_hh hi part in registers, lo part in shared memory; H in {128, 512, 1024}).
- * Measured on B200 (H=1024, B=64): 13.8 vs 14.4 us/step, see DESIGN.md.  Process-global; for A/B
- * measurements and tests. */
+/* Recurrence engine (process-global; for A/B measurements and tests):
+ *   2 (default) = tcgen05 cluster kernel (csrc/lstm_tc.cu: W_hh hi part in tensor memory, K split over a cluster of
+ *       4 CTAs with a DSMEM reduction) where it applies -- H = 1024, one group, 32 clusters of 4 co-resident -- and
+ *       the FMA kernel elsewhere;
+ *   1 = legacy mma.sync TF32 path with the 3xTF32 split (H in {128, 512, 1024});
+ *   0 = fp32 FMA kernel (any H %% 128 == 0).
+ * Measured on B200 (H = 1024, B = 64): 7.9 / 14.4 / 13.8 us per step, see DESIGN.md. */
 int se_set_lstm_engine(int engine);
-/* Measurement aid for the tcgen05 engine: dev_buf (device, 128 * nsteps * 10 int64, or NULL to switch off)
- * receives clock64() stamps of 10 phase boundaries per CTA for steps [first_step, first_step + nsteps); see
+/* Measurement aid for the tcgen05 engine: dev_buf (device, 128 * nsteps * 12 int64, or NULL to switch off)
+ * receives clock64() stamps of 12 phase boundaries per CTA for steps [first_step, first_step + nsteps); see
  * csrc/lstm_tc.cu for the event list and tools/lstm_tc_phases.py for the reader. */
 int se_debug_lstm_tc_profile(long long* dev_buf, int first_step, int nsteps);
 /* Bytes of `work` se_lstm_seq needs (per group). */
@@ -239,6 +242,15 @@ int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long long ldx, int
                         const float* h_lo, long long ldh, int H, const float* w_hi, const float* w_lo, long long ldw,
                         const float* bias, int M, float* c_state, float* h_hi_out, float* h_lo_out, float* h_out,
                         se_stream_t stream);
+/* Same step with (a) a row stride ld_hout for the three h outputs, so a step can write straight into a
+ * [M, L, D*H] sequence buffer at (position, direction) -- the output of step l is the state input of step
+ * l+1 and the layer output at once (DPCRN's intra Bi-LSTM over F = 4, DPCRN/DPCRN.py:52,70); and (b)
+ * first_step = 1: h_{-1} = c_{-1} = 0, the recurrent part of K is skipped, h_hi / h_lo may be NULL and
+ * c_state is write-only. */
+int se_lstm_cell_tf32x3_ex(const float* x_hi, const float* x_lo, long long ldx, int Kx, const float* h_hi,
+                           const float* h_lo, long long ldh, int H, const float* w_hi, const float* w_lo, long long ldw,
+                           const float* bias, int M, float* c_state, float* h_hi_out, float* h_lo_out, float* h_out,
+                           long long ld_hout, int first_step, se_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * FullSubNet glue (FullSubNet/fullsubnet_net_sa/model.py:68-118); see csrc/fullsubnet.cu.
@@ -290,6 +302,9 @@ int se_glu_affine_act(const float* x, long long rows, int C, const float* scale,
                       float act_param, float* out, float* out_hi, float* out_lo, se_stream_t stream);
 int se_unary(const float* x, long long n, int act, float act_param, float* out, float* out_hi, float* out_lo,
              se_stream_t stream);
+/* out[i] = x[i] * m[i] for n interleaved (re, im) complex numbers: the complex ratio mask DPCRN applies inside
+ * forward (DPCRN/DPCRN.py:33-42). */
+int se_cmul(const float* x, const float* m, long long n, float* out, se_stream_t stream);
 
 /* DCCRN polar mask, masking_mode 'E' (DCCRN/DCCRN_cprs.py:201-220):
  *     est = tanh(|M|) * |X| * exp(j(angle X + angle M)),  M = 0 at the DC bin (:203-204).

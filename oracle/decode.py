@@ -146,3 +146,23 @@ def enhance_gcrn(sd, wav, p=0.5):
     y = dsp.istft(de.T, n_fft, win, hop, length=len(x))                     # :56-57
     taps = {"c": c, "feat": feat, "est": est, "y_norm": y.astype(np.float32)}
     return (y / c).astype(np.float32), taps
+
+
+def enhance_dpcrn(sd, wav, p=1.0):
+    """``DPCRN/dpcrn_decode_vb.py:33-60`` (librosa dialect; p = 1.0 in the vb script (:41,53), 0.5 in
+    drcrn_decode.py:45,56): compressed RI in, masked RI out (the mask multiply is inside forward),
+    backend rule (ii)."""
+    from . import nets as _n
+    n_fft, win, hop = dsp.GEOMETRIES["320"]
+    x, c = dsp.rms_scale(wav)
+    spec = dsp.stft(x, n_fft, win, hop).T
+    mag, ph = (np.abs(spec) ** p).astype(np.float32), np.angle(spec).astype(np.float32)
+    feat = np.stack((mag * np.cos(ph), mag * np.sin(ph)))
+    with torch.no_grad():
+        est = _n.dpcrn_forward(sd, torch.from_numpy(feat)[None]).squeeze(0).numpy()
+    emag = np.sqrt(est[0] ** 2 + est[1] ** 2) ** (1.0 / p)
+    eph = np.arctan2(est[1], est[0])
+    de = emag * np.exp(1j * eph)
+    y = dsp.istft(de.T, n_fft, win, hop, length=len(x))
+    taps = {"c": c, "feat": feat, "est": est, "y_norm": y.astype(np.float32)}
+    return (y / c).astype(np.float32), taps

@@ -148,6 +148,45 @@ def make_gcrn():
               f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+DPCRN_CASES = [
+    ("dpcrn_synth", None, 8000, (12, 13), 0.5),
+    ("dpcrn_ckpt", "vb_dpcrn_noncprs_model.pth", 16000, (12, 13), 1.0),       # as dpcrn_decode_vb.py runs it
+]
+
+
+def make_dpcrn():
+    """Fixtures from the UNMODIFIED DPCRN/DPCRN.py ``dpcrn`` (synthetic weights with p = 0.5 as drcrn_decode.py,
+    the shipped vb checkpoint with p = 1.0 as dpcrn_decode_vb.py)."""
+    mod = ref_shims.import_reference("DPCRN", "DPCRN")
+    for name, ckpt, nsamp, clip_ids, p in DPCRN_CASES:
+        net = mod.dpcrn().eval()
+        if ckpt is None:
+            sd = synth.synthetic_state_dict(templates.dpcrn_template(), seed=0, gain=1.0)
+        else:
+            sd = torch.load(ref_shims.checkpoint_path("DPCRN", ckpt), map_location="cpu")
+        net.load_state_dict(sd)
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp),
+               "p": np.array(p)}
+        worst = 0.0
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = decode.enhance_dpcrn(sd, wav.astype(np.float64), p=p)
+            with torch.no_grad():
+                est_ref = net(torch.from_numpy(taps["feat"])[None]).squeeze(0).numpy()
+            worst = max(worst, float(np.abs(est_ref - taps["est"]).max()))
+            rec[f"wav{j}"] = wav
+            rec[f"feat{j}"] = taps["feat"]
+            rec[f"est{j}"] = est_ref.astype(np.float32)
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        rec["ref_vs_oracle"] = np.array(worst)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: ref_vs_oracle max-abs {worst:.3e}, out rms "
+              f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 UF_CASES = [
     ("uformer_synth", None, 8000, (8, 9), 0),
     ("uformer_ckpt", "wsj0_si84_300h_uformer_noncprs_model.pth", 16000, (8, 9), 64000),
@@ -238,5 +277,7 @@ if __name__ == "__main__":
         make_dccrn()
     if len(sys.argv) < 2 or sys.argv[1] == "gcrn":
         make_gcrn()
+    if len(sys.argv) < 2 or sys.argv[1] == "dpcrn":
+        make_dpcrn()
     if len(sys.argv) < 2 or sys.argv[1] == "uformer":
         make_uformer()

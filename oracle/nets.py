@@ -470,3 +470,76 @@ def gcrn_forward(sd, x, taps=None):
             taps[f"d1_{br}"] = d
         res.append(F.linear(d, sd[f"fc{br}.weight"], sd[f"fc{br}.bias"]))     # :161-162
     return torch.cat(res, dim=1)
+
+
+# ----------------------------------------------------------------------------------------
+# DPCRN  (DPCRN/DPCRN.py)
+# ----------------------------------------------------------------------------------------
+def _lstm_dir(x, sd, prefix, layer, reverse):
+    """One direction of one nn.LSTM layer, batch_first.  x [B,L,I] -> [B,L,H] (outputs at their own positions)."""
+    sfx = f"_l{layer}" + ("_reverse" if reverse else "")
+    one = {"l.weight_ih_l0": sd[f"{prefix}.weight_ih{sfx}"], "l.weight_hh_l0": sd[f"{prefix}.weight_hh{sfx}"],
+           "l.bias_ih_l0": sd[f"{prefix}.bias_ih{sfx}"], "l.bias_hh_l0": sd[f"{prefix}.bias_hh{sfx}"]}
+    if reverse:
+        return lstm(x.flip(1), one, "l", 1).flip(1)
+    return lstm(x, one, "l", 1)
+
+
+def _bilstm(x, sd, prefix, num_layers):
+    """nn.LSTM(bidirectional=True, batch_first=True): layer l+1 sees cat(forward, backward) of layer l."""
+    for l in range(num_layers):
+        x = torch.cat((_lstm_dir(x, sd, prefix, l, False), _lstm_dir(x, sd, prefix, l, True)), dim=-1)
+    return x
+
+
+def _dprnn(sd, x):
+    """DPRNN.forward, DPCRN.py:60-98.  x [B,C=128,T,F=4] -> same shape."""
+    b, c, t, f = x.shape
+    xt = x.permute(0, 2, 3, 1).contiguous()                                   # [B,T,F,C]   (:64)
+    out = _bilstm(xt.view(-1, f, c), sd, "dprnn.intra_rnn", 2)                # over F      (:70-71)
+    out = F.linear(out, sd["dprnn.intra_fc.weight"], sd["dprnn.intra_fc.bias"]).view(b, -1, f, c)
+    out = F.layer_norm(out, (f, c), sd["dprnn.ln1.weight"], sd["dprnn.ln1.bias"])
+    intra = out + xt                                                          # :76
+    out = intra.permute(0, 2, 1, 3).contiguous().view(-1, t, c)               # [B*F,T,C]   (:80-81)
+    out = lstm(out, sd, "dprnn.inter_rnn", 2)
+    out = F.linear(out, sd["dprnn.inter_fc.weight"], sd["dprnn.inter_fc.bias"]).view(b, -1, t, c)
+    out = out.permute(0, 2, 1, 3).contiguous()                                # [B,T,F,C]   (:87-88)
+    out = F.layer_norm(out, (f, c), sd["dprnn.ln2.weight"], sd["dprnn.ln2.bias"]) + intra
+    return out.permute(0, 3, 1, 2).contiguous()
+
+
+def dpcrn_forward(sd, inpt, taps=None):
+    """dpcrn.forward, DPCRN.py:23-42.  inpt [B,2,T,161] RI -> [B,2,T,161] RI (complex ratio mask applied inside).
+
+    Encoder (:100-138): 5 x [pad one frame on top, Conv2d k(2,3) s(1,2), BN, PReLU(1)]; the SAME DPRNN twice
+    (:28-29); decoder (:140-179): 5 x [cat skip, ConvTranspose2d k(2,3) s(1,2), (de4: left-pad F by 1), drop
+    the last frame, BN, PReLU]; de5 has neither BN nor activation (:166-168)."""
+    x = inpt
+    skips = []
+    for i in range(5):
+        x = F.pad(x, (0, 0, 1, 0))
+        x = F.conv2d(x, sd[f"en.en_module.{i}.1.weight"], sd[f"en.en_module.{i}.1.bias"], stride=(1, 2))
+        x = F.prelu(_bn(x, sd, f"en.en_module.{i}.2"), sd[f"en.en_module.{i}.3.weight"])
+        skips.append(x)
+        if taps is not None:
+            taps[f"en{i + 1}"] = x
+    x = _dprnn(sd, x)
+    if taps is not None:
+        taps["dp1"] = x
+    x = _dprnn(sd, x)
+    if taps is not None:
+        taps["dp2"] = x
+    for i in range(5):
+        x = torch.cat((x, skips[-(i + 1)]), dim=1)
+        x = F.conv_transpose2d(x, sd[f"de.de_module.{i}.0.weight"], sd[f"de.de_module.{i}.0.bias"], stride=(1, 2))
+        if i == 3:
+            x = F.pad(x, (1, 0, 0, 0))
+        x = x[:, :, :-1, :]
+        if i < 4:
+            bn_idx, act_idx = (3, 4) if i == 3 else (2, 3)
+            x = F.prelu(_bn(x, sd, f"de.de_module.{i}.{bn_idx}"), sd[f"de.de_module.{i}.{act_idx}.weight"])
+        if taps is not None:
+            taps[f"de{i + 1}"] = x
+    mr, mi = x[:, 0], x[:, 1]
+    xr, xi = inpt[:, 0], inpt[:, 1]
+    return torch.stack((xr * mr - xi * mi, xr * mi + xi * mr), dim=1)        # :39-42

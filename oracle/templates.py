@@ -119,6 +119,39 @@ def gcrn_template():
     return d
 
 
+def dpcrn_template():
+    """DPCRN/DPCRN.py:16-179 (``dpcrn``): key order as ``dpcrn().state_dict()`` lists it."""
+    d = {}
+    ch = [2, 32, 32, 32, 64, 128]
+    for i in range(5):
+        d[f"en.en_module.{i}.1.weight"] = (ch[i + 1], ch[i], 2, 3)
+        d[f"en.en_module.{i}.1.bias"] = (ch[i + 1],)
+        d.update(_bn(f"en.en_module.{i}.2", ch[i + 1]))
+        d[f"en.en_module.{i}.3.weight"] = (1,)
+    for l in range(2):
+        for sfx in ("", "_reverse"):
+            d[f"dprnn.intra_rnn.weight_ih_l{l}{sfx}"] = (256, 128)
+            d[f"dprnn.intra_rnn.weight_hh_l{l}{sfx}"] = (256, 64)
+            d[f"dprnn.intra_rnn.bias_ih_l{l}{sfx}"] = (256,)
+            d[f"dprnn.intra_rnn.bias_hh_l{l}{sfx}"] = (256,)
+    d["dprnn.intra_fc.weight"] = (128, 128)
+    d["dprnn.intra_fc.bias"] = (128,)
+    d.update(_lstm("dprnn.inter_rnn", 128, 128, 2))
+    d["dprnn.inter_fc.weight"] = (128, 128)
+    d["dprnn.inter_fc.bias"] = (128,)
+    for n in ("ln1", "ln2"):
+        d[f"dprnn.{n}.weight"] = (4, 128)
+        d[f"dprnn.{n}.bias"] = (4, 128)
+    for i, (ci, co) in enumerate([(256, 64), (128, 32), (64, 32), (64, 32), (64, 2)]):
+        d[f"de.de_module.{i}.0.weight"] = (ci, co, 2, 3)
+        d[f"de.de_module.{i}.0.bias"] = (co,)
+        if i < 4:
+            bn = 3 if i == 3 else 2
+            d.update(_bn(f"de.de_module.{i}.{bn}", co))
+            d[f"de.de_module.{i}.{bn + 1}.weight"] = (1,)
+    return d
+
+
 def uformer_template():
     """The 668 state-dict entries of the shipped Uformer checkpoints (names, shapes, order), as listed by
     torch.load on Uformer/BEST_MODEL/*.pth and stored in oracle/uformer_keys.json."""

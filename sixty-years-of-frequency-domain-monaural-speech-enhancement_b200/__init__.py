@@ -10,6 +10,7 @@ from .lstm import lstm_net                 # noqa: F401
 from . import fullsubnet                   # noqa: F401
 from .dccrn import DCCRN                   # noqa: F401
 from .uformer import Uformer               # noqa: F401
+from .dpcrn import dpcrn                   # noqa: F401
 from . import gcrn                         # noqa: F401  (gcrn.Net, as GCRN/GCRN_noncprs.py names it)
 
-__all__ = ["crn_net", "lstm_net", "fullsubnet", "DCCRN", "Uformer", "gcrn", "ops", "decode", "packing", "shard"]
+__all__ = ["crn_net", "lstm_net", "fullsubnet", "DCCRN", "Uformer", "gcrn", "dpcrn", "ops", "decode", "packing", "shard"]

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "se_gemm_tf32x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _P, _LL, _P]),
     "se_gemm_tf32x3_ex": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _F, _F, _P, _P, _P, _P, _LL, _P]),
     "se_lstm_cell_tf32x3": (_I, [_P, _P, _LL, _I, _P, _P, _LL, _I, _P, _P, _LL, _P, _I, _P, _P, _P, _P, _P]),
+    "se_lstm_cell_tf32x3_ex": (_I, [_P, _P, _LL, _I, _P, _P, _LL, _I, _P, _P, _LL, _P, _I, _P, _P, _P, _P, _LL, _I, _P]),
     "se_fsn_clip_inv_mean": (_I, [_P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, C.c_double, _P, _P]),
     "se_fsn_fb_input": (_I, [_P, _LL, _LL, _LL, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_assemble": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -75,6 +76,7 @@ PROTOTYPES = {
     "se_debug_lstm_tc_profile": (_I, [_P, _I, _I]),
     "se_glu_affine_act": (_I, [_P, _LL, _I, _P, _P, _I, _F, _P, _P, _P, _P]),
     "se_unary": (_I, [_P, _LL, _I, _F, _P, _P, _P, _P]),
+    "se_cmul": (_I, [_P, _P, _LL, _P, _P]),
     "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
 }
 

@@ -55,6 +55,8 @@ struct TcParams {
   float* h_lo;      // [M, H] out: rna_tf32(h - h_hi)
   float* h_out;     // [M, H] out (plain fp32) or NULL
   int H;
+  long long ld_hout;   // row stride of h_hi / h_lo / h_out (>= H; c_state is always [M, H] contiguous)
+  int first_step;      // 1: h_{-1} = c_{-1} = 0 -- no recurrent k-blocks, c_state is not read
 };
 
 template <int EPI>
@@ -111,7 +113,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       unsigned phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -139,7 +141,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr unsigned idesc = make_idesc_tf32(TC_BM, TC_BN);
       int stage = 0;
       unsigned phase = 0;
@@ -252,10 +254,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       } else {
         // fused LSTM cell: this thread holds all four gates of 16 hidden units of sequence `row`
         const long long off = (long long)row * p.H + nb * 32 + half * 16;
+        const long long hoff = (long long)row * p.ld_hout + nb * 32 + half * 16;
         const float* bias = p.bias + n0;
 #pragma unroll
         for (int u = 0; u < 16; u += 4) {
-          const float4 cold = *reinterpret_cast<const float4*>(p.c_state + off + u);
+          const float4 cold = p.first_step ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                           : *reinterpret_cast<const float4*>(p.c_state + off + u);
           const float co[4] = {cold.x, cold.y, cold.z, cold.w};
           float cn[4], hn[4], hh[4], hl[4];
 #pragma unroll
@@ -274,9 +278,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
             hl[e] = __uint_as_float(lb);
           }
           *reinterpret_cast<float4*>(p.c_state + off + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(p.h_hi + off + u) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<float4*>(p.h_lo + off + u) = make_float4(hl[0], hl[1], hl[2], hl[3]);
-          if (p.h_out) *reinterpret_cast<float4*>(p.h_out + off + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(p.h_hi + hoff + u) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<float4*>(p.h_lo + hoff + u) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+          if (p.h_out) *reinterpret_cast<float4*>(p.h_out + hoff + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
         }
       }
     }
@@ -437,19 +441,21 @@ extern "C" int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long ld
                            ldc, stream);
 }
 
-extern "C" int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long long ldx, int Kx, const float* h_hi,
-                                   const float* h_lo, long long ldh, int H, const float* w_hi, const float* w_lo,
-                                   long long ldw, const float* bias, int M, float* c_state, float* h_hi_out,
-                                   float* h_lo_out, float* h_out, se_stream_t stream) {
-  SE_REQUIRE(x_hi && x_lo && h_hi && h_lo && w_hi && w_lo && bias && c_state && h_hi_out && h_lo_out,
-             "se_lstm_cell_tf32x3: null pointer");
+extern "C" int se_lstm_cell_tf32x3_ex(const float* x_hi, const float* x_lo, long long ldx, int Kx, const float* h_hi,
+                                      const float* h_lo, long long ldh, int H, const float* w_hi, const float* w_lo,
+                                      long long ldw, const float* bias, int M, float* c_state, float* h_hi_out,
+                                      float* h_lo_out, float* h_out, long long ld_hout, int first_step,
+                                      se_stream_t stream) {
+  SE_REQUIRE(x_hi && x_lo && w_hi && w_lo && bias && c_state && h_hi_out && h_lo_out, "se_lstm_cell_tf32x3: null pointer");
+  SE_REQUIRE(first_step || (h_hi && h_lo), "se_lstm_cell_tf32x3: state pointers are required after the first step");
   SE_REQUIRE(M > 0 && Kx > 0 && Kx % TC_BK == 0 && H > 0 && H % 32 == 0, "se_lstm_cell_tf32x3: Kx=%d H=%d (%%32)", Kx, H);
-  SE_REQUIRE((ldx & 3) == 0 && (ldh & 3) == 0 && (ldw & 3) == 0, "se_lstm_cell_tf32x3: leading dims must be %% 4");
+  SE_REQUIRE((ldx & 3) == 0 && (ldh & 3) == 0 && (ldw & 3) == 0 && (ld_hout & 3) == 0 && ld_hout >= H,
+             "se_lstm_cell_tf32x3: leading dims must be %% 4 (ld_hout=%lld)", ld_hout);
   SE_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(h_hi) && aligned16(h_lo) && aligned16(w_hi) &&
                  aligned16(w_lo) && aligned16(c_state) && aligned16(h_hi_out) && aligned16(h_lo_out) &&
                  (!h_out || aligned16(h_out)),
              "se_lstm_cell_tf32x3: pointers must be 16-byte aligned");
-  SE_REQUIRE(h_hi != h_hi_out && h_lo != h_lo_out, "se_lstm_cell_tf32x3: state must be double buffered");
+  SE_REQUIRE(first_step || (h_hi != h_hi_out && h_lo != h_lo_out), "se_lstm_cell_tf32x3: state must be double buffered");
   TcParams p{};
   p.M = M;
   p.N = 4 * H;
@@ -459,7 +465,18 @@ extern "C" int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long lo
   p.h_lo = h_lo_out;
   p.h_out = h_out;
   p.H = H;
-  int rc = launch_tc(EPI_LSTM_CELL, x_hi, x_lo, ldx, Kx, h_hi, h_lo, ldh, H, w_hi, w_lo, ldw, p, (cudaStream_t)stream);
+  p.ld_hout = ld_hout;
+  p.first_step = first_step ? 1 : 0;
+  int rc = launch_tc(EPI_LSTM_CELL, x_hi, x_lo, ldx, Kx, h_hi, h_lo, ldh, first_step ? 0 : H, w_hi, w_lo, ldw, p,
+                     (cudaStream_t)stream);
   if (rc) return rc;
   return check_launch("se_lstm_cell_tf32x3");
+}
+
+extern "C" int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long long ldx, int Kx, const float* h_hi,
+                                   const float* h_lo, long long ldh, int H, const float* w_hi, const float* w_lo,
+                                   long long ldw, const float* bias, int M, float* c_state, float* h_hi_out,
+                                   float* h_lo_out, float* h_out, se_stream_t stream) {
+  return se_lstm_cell_tf32x3_ex(x_hi, x_lo, ldx, Kx, h_hi, h_lo, ldh, H, w_hi, w_lo, ldw, bias, M, c_state, h_hi_out,
+                                h_lo_out, h_out, H, 0, stream);
 }

@@ -421,7 +421,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
   }
 }
 
-static int g_lstm_engine = 0;  // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu, H = 1024)
+static int g_lstm_engine = 2;  // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu) where it
+                               // applies (H = 1024, one group, clusters fit the device), the FMA kernel elsewhere
 
 int lstm_tc_supported();
 void lstm_tc_set_profile(long long* dev_buf, int first_step, int nsteps);
@@ -444,7 +445,7 @@ using namespace se;
 
 extern "C" long long se_lstm_seq_work_bytes(int B, int H) {
   (void)B;
-  return 4ll * H * kBT * (long long)sizeof(float);   // tcgen05 engine: {h_hi, h_lo} x 2 parities; others use half
+  return 16ll * H * kBT * (long long)sizeof(float);   // tcgen05 engine: {h_hi, h_lo} x 2 parities x up to 4 replicas
 }
 
 extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xproj_group_off,

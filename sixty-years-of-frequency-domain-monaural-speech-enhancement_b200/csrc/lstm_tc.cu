@@ -25,24 +25,29 @@
 // Warp roles (192 threads): 0-3 epilogue/gates (TMEM lane quarter = warp), 4 TMA producer + step
 // barrier poller, 5 single-thread MMA issuer.  Every spin is bounded (trap after 4 s) so a protocol
 // bug ends in a launch error instead of a hung device.
+#include <cstdio>
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace se {
 
 constexpr int LT_H = 1024;
-constexpr int LT_CL = 4;                    // cluster size = K split
+constexpr int LT_CL = 4;                    // K split (CTAs that reduce over DSMEM); cluster = LT_CL * multicast width
 constexpr int LT_KS = LT_H / LT_CL;         // 256 k per CTA
 constexpr int LT_NB = 64;                   // batch rows (MMA N)
 constexpr int LT_BK = 32;                   // k per TMA stage (128-byte rows)
 constexpr int LT_KB = LT_KS / LT_BK;        // 8 stages' worth per step
 constexpr int LT_STAGES = 4;
 constexpr int LT_CTAS = LT_H / 8;           // 128
-constexpr int LT_THREADS = 192;
+constexpr int LT_THREADS = 320;                 // 8 epilogue warps + TMA warp + MMA warp
+constexpr int LT_TMA_WARP = 8, LT_MMA_WARP = 9;
 constexpr int LT_WLO_BYTES = 128 * LT_KS * 4;          // 131072
 constexpr int LT_BTILE = LT_NB * LT_BK * 4;            // 8192
 constexpr int LT_STAGE_BYTES = 2 * LT_BTILE;           // h_hi + h_lo
 constexpr int LT_RED_BYTES = LT_CL * LT_NB * 32 * 4;   // 32768
 constexpr int LT_SMEM_BYTES = LT_WLO_BYTES + LT_STAGES * LT_STAGE_BYTES + LT_RED_BYTES + 1024 + 256;
+constexpr int LT_REPLICAS = 1, LT_MAX_REPLICAS = 4;   // copies of the published state (SE_LSTM_TC_REPLICAS overrides)
 constexpr unsigned LT_TMEM_COLS = 512;      // A: 0..255, D0: 256..319, D1: 320..383
 constexpr unsigned long long LT_SPIN_NS = 4000000000ull;
 
@@ -53,17 +58,20 @@ struct LtParams {
   int B, T;
   float* hseq;
   long long hs_sb, hs_st;
-  float* h_hi;       // [2 parities][64][1024]
+  float* h_hi;       // [R replicas][2 parities][64][1024]
   float* h_lo;
+  int writer_proxy_fence;   // 1: fence.proxy.async on the publishing side too (the reader always fences)
+  int R;             // replicas of the published state: cluster c reads copy c % R (spreads the 32 readers of every
+                     // line over R lines / L2 slices)
   unsigned* sync;
   // optional phase timestamps (se_debug_lstm_tc_profile): prof[(cta * prof_n + (t - prof_t0)) * LT_NEV + event]
   long long* prof;
   int prof_t0, prof_n;
 };
-constexpr int LT_NEV = 10;
+constexpr int LT_NEV = 12;
 // events: 0 producer starts polling, 1 step barrier observed, 2 last TMA issued, 3 first stage landed (MMA warp),
 //         4 last stage landed, 5 accumulators complete (epilogue), 6 DSMEM partials sent, 7 cluster barrier passed,
-//         8 cell update + stores issued, 9 fences done / arrival on the step counter
+//         8 cell update + stores issued, 10 proxy fence done, 11 CTA barrier passed, 9 release-arrival on the step counter issued
 #define LT_STAMP(ev)                                                                                  \
   do {                                                                                                \
     if (p.prof && t >= p.prof_t0 && t < p.prof_t0 + p.prof_n)                                         \
@@ -140,9 +148,37 @@ __device__ __forceinline__ void tmem_st_32x32(unsigned taddr, const unsigned (&r
       : "memory");
 }
 
-__global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// the mbarrier at the same offset in every CTA of `mask` gets one arrival when this thread's MMAs have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+                   "r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// fast-math gates: ex2.approx + approximate divide, |error| ~ 2e-7 (fp32 rounding class); the accurate expf/tanhf/IEEE
+// divide of common.cuh cost 2800 cycles of a 20000-cycle step here (profiles/lstm_tc_phases_v1_r01.json)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float t = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
+// MC = multicast width: the cluster has 4*MC CTAs, rank = ug*4 + q.  The MC CTAs with the same K slice q (different
+// unit groups ug) each fetch 1/MC of every h tile and multicast it to all of them, so L2 serves every byte of
+// h_{t-1} 32/MC times per step instead of 32 (the v1 kernel was bound by exactly that: 7200 of 20000 cycles).
+template <int MC>
+__global__ void __launch_bounds__(LT_THREADS, 1)
     lstm_seq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                        const LtParams p) {
+  constexpr int RS = LT_NB / MC;                 // rows of a tile this CTA fetches
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* wlo = base;                                         // 8 k-blocks x [128 rows x 128 B], SW128
@@ -155,32 +191,37 @@ __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(accfull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const unsigned q = cluster_rank();               // K slice of this CTA / owner rank of its 8 hidden units
+  const unsigned rank = cluster_rank();
+  const unsigned q = rank & 3u;                    // K slice of this CTA / owner index of its 8 hidden units in the group
+  const unsigned ug = rank >> 2;                   // unit group inside the cluster
   const int slice = blockIdx.x;                    // hidden units [8*slice, +8): what this CTA's gate phase owns
-  const int cl = blockIdx.x / LT_CL;               // cluster: hidden units [32cl, +32)
+  const int grp = blockIdx.x >> 2;                 // unit group: hidden units [32*grp, +32) = the M of this CTA's MMAs
+  unsigned short mc_mask = 0;
+#pragma unroll
+  for (int u = 0; u < MC; ++u) mc_mask |= (unsigned short)(1u << (u * 4 + q));
   const unsigned long long t0 = gtimer_ns();
 
   if (tid == 0) {
     for (int s = 0; s < LT_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MC);
     }
     mbar_init(accfull, 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_hi);
     tma_prefetch_desc(&map_lo);
   }
-  if (warp == 5) tmem_alloc(tmem_slot, LT_TMEM_COLS);
+  if (warp == LT_MMA_WARP) tmem_alloc(tmem_slot, LT_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
   const unsigned tmem_a = tmem_base, tmem_d0 = tmem_base + 256, tmem_d1 = tmem_base + 320;
 
-  // ---- resident weights: row m = 32*o + l  <-  W_hh slice (4cl + o), gate column l; k in this CTA's slice ----
+  // ---- resident weights: row m = 32*o + l  <-  W_hh slice (4*grp + o), gate column l; k in this CTA's slice ----
   if (warp < 4) {
     const int m = warp * 32 + lane;
-    const float* wsrc = p.whh + ((size_t)(cl * LT_CL + warp) * LT_H + (size_t)q * LT_KS) * 32 + lane;
+    const float* wsrc = p.whh + ((size_t)(grp * 4 + warp) * LT_H + (size_t)q * LT_KS) * 32 + lane;
     for (int k0 = 0; k0 < LT_KS; k0 += 32) {
       unsigned hi[32];
 #pragma unroll
@@ -201,15 +242,15 @@ __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  cluster_arrive();             // every CTA of the cluster is running before anyone touches remote smem
+  cluster_arrive();             // barriers initialised and every CTA running before anyone touches remote smem
   cluster_wait();
 
-  if (warp == 4) {
+  if (warp == LT_TMA_WARP) {
     // ===================== TMA producer + step-barrier poller =====================
     int stage = 0;
     unsigned phase = 0;
     for (int t = 1; t < p.T; ++t) {
-      if (lane == 0) {
+      if (elect_one()) {
         const unsigned target = (unsigned)t * (unsigned)LT_CTAS;
         unsigned it = 0;
         LT_STAMP(0);
@@ -218,13 +259,19 @@ __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
         }
         LT_STAMP(1);
         fence_proxy_async();    // h_{t-1} was written with generic stores by other SMs; TMA reads it
-        const int row0 = ((t - 1) & 1) * LT_NB;
+        const int row0 = (((grp % p.R) * 2 + ((t - 1) & 1)) * LT_NB) + (int)ug * RS;
         for (int kb = 0; kb < LT_KB; ++kb) {
-          mbar_wait_bounded(&empty[stage], phase ^ 1, t0);
-          unsigned char* st = stages + stage * LT_STAGE_BYTES;
-          mbar_expect_tx(&full[stage], LT_STAGE_BYTES);
-          tma_load_2d(&map_hi, &full[stage], st, (int)q * LT_KS + kb * LT_BK, row0);
-          tma_load_2d(&map_lo, &full[stage], st + LT_BTILE, (int)q * LT_KS + kb * LT_BK, row0);
+          mbar_wait_bounded(&empty[stage], phase ^ 1, t0);     // all MC consumers of this slot have drained it
+          unsigned char* st = stages + stage * LT_STAGE_BYTES + (int)ug * RS * 128;
+          mbar_expect_tx(&full[stage], LT_STAGE_BYTES);        // my share + the MC-1 shares multicast by my peers
+          const int kc = (int)q * LT_KS + kb * LT_BK;
+          if (MC == 1) {
+            tma_load_2d(&map_hi, &full[stage], st, kc, row0);
+            tma_load_2d(&map_lo, &full[stage], st + LT_BTILE, kc, row0);
+          } else {
+            tma_load_2d_mc(&map_hi, &full[stage], st, kc, row0, mc_mask);
+            tma_load_2d_mc(&map_lo, &full[stage], st + LT_BTILE, kc, row0, mc_mask);
+          }
           if (++stage == LT_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -236,32 +283,36 @@ __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
       cluster_arrive();
       cluster_wait();
     }
-  } else if (warp == 5) {
+  } else if (warp == LT_MMA_WARP) {
     // ===================== MMA issuer =====================
+    // h_hi and h_lo tiles of a stage are adjacent 64-row K-major tiles = ONE 128-row B operand: a single N = 128
+    // MMA computes [W_hi h_hi | W_hi h_lo] (D0 | D1 are adjacent TMEM columns); W_lo h_hi accumulates into D1.
+    // tcgen05.mma issue costs ~45-50 cycles whatever N is (tools/umma_bench.cu), so 2 MMAs per k-step beat 3.
+    constexpr unsigned idesc_wide = make_idesc_tf32(128, 2 * LT_NB);
     constexpr unsigned idesc = make_idesc_tf32(128, LT_NB);
     int stage = 0;
     unsigned phase = 0;
     for (int t = 1; t < p.T; ++t) {
-      if (lane == 0) {
+      if (elect_one()) {
         for (int kb = 0; kb < LT_KB; ++kb) {
           mbar_wait_bounded(&full[stage], phase, t0);
           if (kb == 0) LT_STAMP(3);
           if (kb == LT_KB - 1) LT_STAMP(4);
           tc_fence_after();
           unsigned char* st = stages + stage * LT_STAGE_BYTES;
-          const uint64_t d_bhi = make_smem_desc(st);
-          const uint64_t d_blo = make_smem_desc(st + LT_BTILE);
+          const uint64_t d_b = make_smem_desc(st);              // rows 0..63 h_hi, rows 64..127 h_lo
           const uint64_t d_alo = make_smem_desc(wlo + kb * (128 * 128));
 #pragma unroll
           for (int k = 0; k < LT_BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
             const unsigned a_t = tmem_a + (unsigned)(kb * LT_BK + k * 8);
-            const unsigned acc = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_tf32_ts(tmem_d0, a_t, d_bhi + adv, idesc, acc);
-            umma_tf32_ts(tmem_d1, a_t, d_blo + adv, idesc, acc);
-            umma_tf32(tmem_d1, d_alo + adv, d_bhi + adv, idesc, 1u);
+            umma_tf32_ts(tmem_d0, a_t, d_b + adv, idesc_wide, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_d1, d_alo + adv, d_b + adv, idesc, 1u);
           }
-          umma_commit(&empty[stage]);
+          if (MC == 1)
+            umma_commit(&empty[stage]);
+          else
+            umma_commit_mc(&empty[stage], mc_mask);   // frees the slot in every CTA that multicasts into mine
           if (++stage == LT_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -275,13 +326,15 @@ __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
     }
   } else {
     // ===================== epilogue: K-split reduction over DSMEM, gates, publish =====================
-    float cstate[4] = {0.f, 0.f, 0.f, 0.f};
-    const unsigned red_remote = map_to_rank(smem_u32(red), (unsigned)warp);   // owner of my lane quarter = rank `warp`
+    const int quarter = warp & 3;        // TMEM lanes 32*quarter .. +31 = gate columns owned by rank ug*4 + quarter
+    const int half = warp >> 2;          // batch rows [32*half, +32)
+    float cstate[2] = {0.f, 0.f};
+    const unsigned red_remote = map_to_rank(smem_u32(red), ug * 4u + (unsigned)quarter);
     for (int t = 0; t < p.T; ++t) {
-      float xg[4][4];
+      float xg[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pr = tid + 128 * i, b = pr >> 3, j = pr & 7;
+      for (int i = 0; i < 2; ++i) {
+        const int pr = tid + 256 * i, b = pr >> 3, j = pr & 7;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           xg[i][g] = 0.f;
@@ -292,14 +345,15 @@ __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
         mbar_wait_bounded(accfull, (unsigned)((t - 1) & 1), t0);
         if (tid == 0) LT_STAMP(5);
         tc_fence_after();
-        float d0[64], d1[64];
-        tmem_ld_32x64(tmem_d0 + ((unsigned)(warp * 32) << 16), d0);
-        tmem_ld_32x64(tmem_d1 + ((unsigned)(warp * 32) << 16), d1);
-        // lane = gate column (g = lane >> 3, unit j = lane & 7) of owner `warp`; register b = batch row
+        float d0[32], d1[32];
+        tmem_ld_32x32(tmem_d0 + ((unsigned)(quarter * 32) << 16) + (unsigned)(half * 32), d0);
+        tmem_ld_32x32(tmem_d1 + ((unsigned)(quarter * 32) << 16) + (unsigned)(half * 32), d1);
+        // lane = gate column (g = lane >> 3, unit j = lane & 7) of the owner; register i = batch row 32*half + i
 #pragma unroll
-        for (int b = 0; b < 64; ++b) {
-          const unsigned off = ((unsigned)q * 2048u + (unsigned)b * 32u + (unsigned)((((lane >> 3) ^ (b & 3)) << 3) | (lane & 7))) * 4u;
-          st_cluster_f32(red_remote + off, d0[b] + d1[b]);
+        for (int i = 0; i < 32; ++i) {
+          const int b = half * 32 + i;
+          const unsigned off = (q * 2048u + (unsigned)b * 32u + (unsigned)((((lane >> 3) ^ (b & 3)) << 3) | (lane & 7))) * 4u;
+          st_cluster_f32(red_remote + off, d0[i] + d1[i]);
         }
         tc_fence_before();
         if (tid == 0) LT_STAMP(6);
@@ -308,56 +362,68 @@ __global__ void __cluster_dims__(LT_CL, 1, 1) __launch_bounds__(LT_THREADS, 1)
         if (tid == 0) LT_STAMP(7);
       }
       const int par = t & 1;
+      float hv[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pr = tid + 128 * i, b = pr >> 3, j = pr & 7;
+      for (int i = 0; i < 2; ++i) {
+        const int pr = tid + 256 * i, b = pr >> 3, j = pr & 7;
         float g4[4] = {xg[i][0], xg[i][1], xg[i][2], xg[i][3]};
         if (t > 0) {
 #pragma unroll
-          for (int s = 0; s < LT_CL; ++s)
+          for (int s = 0; s < 4; ++s)
 #pragma unroll
             for (int g = 0; g < 4; ++g) g4[g] += red[s * 2048 + b * 32 + (((g ^ (b & 3)) << 3) | j)];
         }
-        const float ig = sigmoid_f(g4[0]);
-        const float fg = sigmoid_f(g4[1]);
-        const float gg = tanhf(g4[2]);
-        const float og = sigmoid_f(g4[3]);
+        const float ig = fast_sigmoid(g4[0]);
+        const float fg = fast_sigmoid(g4[1]);
+        const float gg = fast_tanh(g4[2]);
+        const float og = fast_sigmoid(g4[3]);
         const float c = fg * cstate[i] + ig * gg;
-        float h = og * tanhf(c);
+        float h = og * fast_tanh(c);
         cstate[i] = c;
         const int u = slice * 8 + j;
         if (b >= p.B) h = 0.f;
         float hh, hl;
         split_tf32_dev(h, hh, hl);
         const size_t o = ((size_t)par * LT_NB + b) * LT_H + u;
-        p.h_hi[o] = hh;
-        p.h_lo[o] = hl;
-        if (b < p.B) p.hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + u] = h;
+        for (int r = 0; r < p.R; ++r) {
+          p.h_hi[o + (size_t)r * (2 * LT_NB * LT_H)] = hh;
+          p.h_lo[o + (size_t)r * (2 * LT_NB * LT_H)] = hl;
+        }
+        hv[i] = h;
       }
       if (tid == 0) LT_STAMP(8);
       if (t + 1 < p.T) {
-        fence_proxy_async();
-        __threadfence();
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        if (tid == 0) lt_red_release(p.sync, 1u);
+        if (p.writer_proxy_fence) fence_proxy_async();   // generic-proxy stores -> async-proxy (TMA) readers
+        if (tid == 0) LT_STAMP(10);
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (tid == 0) LT_STAMP(11);
+        if (tid == 0) lt_red_release(p.sync, 1u);        // release is cumulative over the CTA's stores (bar.sync above)
       }
       if (tid == 0) LT_STAMP(9);
+      // the sequence output is not on the step's critical path: store it after the arrival
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pr = tid + 256 * i, b = pr >> 3, j = pr & 7;
+        if (b < p.B) p.hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + slice * 8 + j] = hv[i];
+      }
     }
   }
   tc_fence_before();
+  cluster_arrive();             // no CTA leaves while peers may still signal its barriers / write its smem
+  cluster_wait();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, LT_TMEM_COLS);
+  if (warp == LT_MMA_WARP) tmem_dealloc(tmem_base, LT_TMEM_COLS);
 }
 
-static int make_h_map(CUtensorMap* map, const float* ptr) {
+static int make_h_map(CUtensorMap* map, const float* ptr, int box_rows, int replicas) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return SE_ERR_CUDA;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(2 * LT_NB)};
+  cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(2 * LT_NB * replicas)};
   cuuint64_t strides[1] = {(cuuint64_t)LT_H * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)LT_BK, (cuuint32_t)LT_NB};
+  cuuint32_t box[2] = {(cuuint32_t)LT_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -369,14 +435,22 @@ static int make_h_map(CUtensorMap* map, const float* ptr) {
   return SE_OK;
 }
 
-// 1 when 32 clusters of 4 CTAs of this kernel can be co-resident on the current device
-int lstm_tc_supported() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  cached = 0;
-  if (cudaFuncSetAttribute(lstm_seq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES) != cudaSuccess) {
+typedef void (*LtKernel)(const CUtensorMap, const CUtensorMap, const LtParams);
+static LtKernel lt_kernel(int mc) {
+  return mc == 4 ? lstm_seq_tc_kernel<4> : (mc == 2 ? lstm_seq_tc_kernel<2> : lstm_seq_tc_kernel<1>);
+}
+
+// can LT_CTAS / (4*mc) clusters of 4*mc CTAs of this kernel be co-resident on the current device?
+static bool lt_fits(int mc) {
+  LtKernel k = lt_kernel(mc);
+  const bool verbose = getenv("SE_LSTM_TC_VERBOSE") != nullptr;
+  cudaError_t e1 = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES);
+  cudaError_t e2 = 4 * mc > 8 ? cudaFuncSetAttribute((const void*)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+                              : cudaSuccess;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    if (verbose) fprintf(stderr, "lstm_tc mc=%d: attributes: %s / %s\n", mc, cudaGetErrorString(e1), cudaGetErrorString(e2));
     cudaGetLastError();
-    return cached;
+    return false;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(LT_CTAS);
@@ -384,19 +458,43 @@ int lstm_tc_supported() {
   cfg.dynamicSmemBytes = LT_SMEM_BYTES;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = LT_CL;
+  at[0].val.clusterDim.x = 4 * mc;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int nclusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&nclusters, lstm_seq_tc_kernel, &cfg) != cudaSuccess) {
+  cudaError_t e3 = cudaOccupancyMaxActiveClusters(&nclusters, (const void*)k, &cfg);
+  if (verbose)
+    fprintf(stderr, "lstm_tc mc=%d: cudaOccupancyMaxActiveClusters -> %d clusters of %d (need %d): %s\n", mc, nclusters,
+            4 * mc, LT_CTAS / (4 * mc), cudaGetErrorString(e3));
+  if (e3 != cudaSuccess) {
     cudaGetLastError();
-    return cached;
+    return false;
   }
-  cached = nclusters >= LT_CTAS / LT_CL ? 1 : 0;
+  return nclusters >= LT_CTAS / (4 * mc);
+}
+
+// multicast width to run with: the widest of {4, 2, 1} whose clusters fit the device (0 = engine unavailable);
+// SE_LSTM_TC_MC=1|2|4 in the environment pins it (A/B measurements).
+static int lt_pick_mc() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cached = 0;
+  int want = 0;
+  if (const char* e = getenv("SE_LSTM_TC_MC")) want = atoi(e);
+  const int order[3] = {4, 2, 1};
+  for (int i = 0; i < 3; ++i) {
+    if (want && order[i] != want) continue;
+    if (lt_fits(order[i])) {
+      cached = order[i];
+      break;
+    }
+  }
   return cached;
 }
+
+int lstm_tc_supported() { return lt_pick_mc() > 0; }
 
 static long long* g_prof = nullptr;
 static int g_prof_t0 = 0, g_prof_n = 0;
@@ -406,35 +504,50 @@ void lstm_tc_set_profile(long long* dev_buf, int first_step, int nsteps) {
   g_prof_n = nsteps;
 }
 
-// work: [2 arrays][2 parities][64][1024] fp32; sync[0] zeroed by the caller on `s`
+// work: [2 arrays][R <= 4 replicas][2 parities][64][1024] fp32; sync[0] zeroed by the caller on `s`
 int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
                        long long hs_sb, long long hs_st, float* work, unsigned* sync, cudaStream_t s) {
-  CUtensorMap map_hi, map_lo;
-  float* h_hi = work;
-  float* h_lo = work + (size_t)2 * LT_NB * LT_H;
-  int rc = make_h_map(&map_hi, h_hi);
-  if (rc != SE_OK) return rc;
-  rc = make_h_map(&map_lo, h_lo);
-  if (rc != SE_OK) return rc;
-  cudaError_t e = cudaFuncSetAttribute(lstm_seq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES);
-  if (e != cudaSuccess) {
-    set_error("se_lstm_seq (tcgen05): %d bytes of shared memory: %s", LT_SMEM_BYTES, cudaGetErrorString(e));
+  const int mc = lt_pick_mc();
+  if (mc <= 0) {
+    set_error("se_lstm_seq (tcgen05): clusters of this kernel do not fit the device");
     return SE_ERR_CUDA;
   }
-  LtParams p{xproj, xp_stride, whh, B, T, hseq, hs_sb, hs_st, h_hi, h_lo, sync, g_prof, g_prof_t0, g_prof_n};
+  static int reps = -1;
+  if (reps < 0) {
+    reps = LT_REPLICAS;
+    if (const char* e = getenv("SE_LSTM_TC_REPLICAS")) reps = atoi(e);
+    if (reps < 1 || reps > LT_MAX_REPLICAS) reps = LT_REPLICAS;
+  }
+  CUtensorMap map_hi, map_lo;
+  float* h_hi = work;
+  float* h_lo = work + (size_t)reps * 2 * LT_NB * LT_H;
+  int rc = make_h_map(&map_hi, h_hi, LT_NB / mc, reps);
+  if (rc != SE_OK) return rc;
+  rc = make_h_map(&map_lo, h_lo, LT_NB / mc, reps);
+  if (rc != SE_OK) return rc;
+  static int wfence = -1;
+  if (wfence < 0) {
+    wfence = 1;
+    if (const char* e = getenv("SE_LSTM_TC_WRITER_FENCE")) wfence = atoi(e) ? 1 : 0;
+  }
+  LtParams p{xproj, xp_stride, whh, B, T, hseq, hs_sb, hs_st, h_hi, h_lo, wfence, reps, sync, g_prof, g_prof_t0, g_prof_n};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(LT_CTAS);
   cfg.blockDim = dim3(LT_THREADS);
   cfg.dynamicSmemBytes = LT_SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeCooperative;   // all 128 CTAs co-resident or the launch fails (never a deadlock)
   at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = 4 * mc;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, lstm_seq_tc_kernel, map_hi, map_lo, p);
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lt_kernel(mc), map_hi, map_lo, p);
   if (e != cudaSuccess) {
-    set_error("se_lstm_seq (tcgen05): cooperative cluster launch: %s", cudaGetErrorString(e));
+    set_error("se_lstm_seq (tcgen05, multicast %d): cooperative cluster launch: %s", mc, cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
   return check_launch("se_lstm_seq (tcgen05)");

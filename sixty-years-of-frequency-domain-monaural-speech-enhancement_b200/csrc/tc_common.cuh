@@ -9,6 +9,16 @@ namespace se {
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  Use this -- not `lane == 0` -- to guard single-thread tcgen05.mma / TMA issue:
+// ptxas only knows that exactly one thread is active behind an elect.sync predicate; behind `lane == 0` it wraps
+// every UTCHMMA / UTMALDG (uniform-register operands) in an ELECT ... BRA.U.ANY loop, which costs ~100 cycles
+// per instruction (tools/umma_bench.cu: 138 -> see profiles/umma_bench_r01.txt).
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -74,6 +74,29 @@ def enhance_gcrn(model, wav, p=0.5, taps=None):
     return out
 
 
+@torch.no_grad()
+def enhance_dpcrn(model, wav, p=1.0, taps=None):
+    """DPCRN/dpcrn_decode_vb.py:33-60 (p = 1.0; drcrn_decode.py uses p = 0.5): compressed real/imag spectrum in,
+    complex-ratio-masked spectrum out of forward, |.|^(1/p) with its own phase (backend rule (ii)),
+    iSTFT(length=N), / c.  wav [B,N] float32 CUDA -> [B,N]."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    n_fft, win, hop = GEOM_320
+    wav = wav.contiguous().float()
+    b, n = wav.shape
+    t, f = 1 + n // hop, n_fft // 2 + 1
+    c, inv_c = ops.rms_scale(wav)
+    x = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)        # compressed RI, channels-last
+    ops.stft(wav, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p)
+    est = model.forward_nhwc(x, taps)
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_RI_DECOMP, est[..., 0], est[..., 1], None, None, n_fft, win, hop, out, n, out_scale=inv_c,
+              inv_p=1.0 / p)
+    if taps is not None:
+        taps.update(c=c, x=x, est=est)
+    return out
+
+
 GEOM_FULLSUBNET = (512, 512, 256)   # FullSubNet/fullsubnet_sa_decode.py:53
 GEOM_DCCRN = (512, 512, 128)        # DCCRN/dccrn_decode.py:41
 

@@ -262,6 +262,40 @@ def lstm_cell_tf32x3(x_hi, x_lo, h_hi, h_lo, w_hi, w_lo, bias, c_state, h_hi_out
                                               _ptr(h_out), _stream()), "se_lstm_cell_tf32x3")
 
 
+def lstm_cell_tf32x3_ex(x_pair, h_pair, w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out=None):
+    """lstm_cell_tf32x3 with strided h outputs (row stride = .stride(0)) and ``h_pair=None`` for the first step
+    (zero initial state; see se_lstm_cell_tf32x3_ex)."""
+    x_hi, x_lo = x_pair
+    h_hi, h_lo = h_pair if h_pair is not None else (None, None)
+    _need_cuda(x_hi, x_lo, h_hi, h_lo, w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out)
+    device_check()
+    m, kx = x_hi.shape
+    hdim = h_hi_out.shape[1]
+    assert w_hi.shape == (4 * hdim, kx + hdim) and x_hi.stride(1) == 1 and x_lo.stride() == x_hi.stride()
+    assert c_state.is_contiguous() and c_state.shape == (m, hdim)
+    ldo = h_hi_out.stride(0)
+    assert h_hi_out.stride(1) == 1 and h_lo_out.stride() == h_hi_out.stride()
+    assert h_out is None or h_out.stride() == h_hi_out.stride()
+    assert h_hi is None or (h_hi.stride(1) == 1 and h_lo.stride() == h_hi.stride())
+    with _Timed("lstm_cell_tf32x3"):
+        check(_lib.load().se_lstm_cell_tf32x3_ex(_ptr(x_hi), _ptr(x_lo), x_hi.stride(0), kx, _ptr(h_hi), _ptr(h_lo),
+                                                 h_hi.stride(0) if h_hi is not None else hdim, hdim, _ptr(w_hi),
+                                                 _ptr(w_lo), w_hi.stride(0), _ptr(bias), m, _ptr(c_state),
+                                                 _ptr(h_hi_out), _ptr(h_lo_out), _ptr(h_out), ldo,
+                                                 1 if h_hi is None else 0, _stream()), "se_lstm_cell_tf32x3_ex")
+
+
+def cmul(x, m):
+    """x, m [..., 2] interleaved complex -> x * m."""
+    _need_cuda(x, m)
+    device_check()
+    assert x.is_contiguous() and m.is_contiguous() and x.shape == m.shape and x.shape[-1] == 2
+    out = torch.empty_like(x)
+    with _Timed("cmul"):
+        check(_lib.load().se_cmul(_ptr(x), _ptr(m), x.numel() // 2, _ptr(out), _stream()), "se_cmul")
+    return out
+
+
 # ---- FullSubNet glue ----------------------------------------------------------------------------
 def fsn_clip_inv_mean(x, strides, B, T, F, denom, wgt=None, extra=None):
     _need_cuda(x, wgt, extra)
@@ -359,12 +393,15 @@ def fill_column(dst, fill, fill_f, act, act_param=0.0):
 
 def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
     """``ngroups`` same-shape LSTMs in one launch.  xproj [B,T,ngroups*4H] (group-major column blocks),
-    whh [ngroups, H/8, H, 32], out [B,T,ngroups*H]."""
+    whh [ngroups, H/8, H, 32] -- or [H/8, H, 32] when all groups share one weight set (DPCRN's inter-LSTM:
+    the groups are the F = 4 frequency positions) --, out [B,T,ngroups*H]."""
     _need_cuda(xproj, whh, out)
     device_check()
     b, t, cols = xproj.shape
     assert cols == ngroups * 4 * hidden and xproj.is_contiguous() and out.is_contiguous() and whh.is_contiguous()
     assert out.shape == (b, t, ngroups * hidden)
+    shared = whh.dim() == 3
+    wstride = 0 if shared else whh[0].numel()
     lib = _lib.load()
     work = torch.empty(ngroups * lib.se_lstm_seq_work_bytes(min(b, _LSTM_MAX_B), hidden) // 4, device=xproj.device,
                        dtype=torch.float32)
@@ -373,7 +410,7 @@ def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
         nb = min(_LSTM_MAX_B, b - b0)
         xs, os_ = xproj[b0:b0 + nb], out[b0:b0 + nb]
         with _Timed("lstm_seq_multi"):
-            check(lib.se_lstm_seq_multi(_ptr(xs), cols, 4 * hidden, _ptr(whh), whh[0].numel(), ngroups, nb, t, hidden,
+            check(lib.se_lstm_seq_multi(_ptr(xs), cols, 4 * hidden, _ptr(whh), wstride, ngroups, nb, t, hidden,
                                         _ptr(os_), os_.stride(0), os_.stride(1), hidden, _ptr(work), _ptr(sync),
                                         _stream()), "se_lstm_seq_multi")
     return out

@@ -92,7 +92,8 @@ def lstm_seq(xproj, whh, hidden, out=None):
 
 def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
     for g in range(ngroups):
-        out[:, :, g * hidden:(g + 1) * hidden] = lstm_seq(xproj[:, :, g * 4 * hidden:(g + 1) * 4 * hidden], whh[g], hidden)
+        w = whh if whh.dim() == 3 else whh[g]
+        out[:, :, g * hidden:(g + 1) * hidden] = lstm_seq(xproj[:, :, g * 4 * hidden:(g + 1) * 4 * hidden], w, hidden)
     return out
 
 
@@ -156,6 +157,18 @@ def lstm_cell_tf32x3(x_hi, x_lo, h_hi, h_lo, w_hi, w_lo, bias, c_state, h_hi_out
     h_lo_out.copy_(lo)
     if h_out is not None:
         h_out.copy_(h)
+
+
+def lstm_cell_tf32x3_ex(x_pair, h_pair, w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out=None):
+    m, hd = c_state.shape
+    if h_pair is None:
+        h_pair = (torch.zeros(m, hd, dtype=c_state.dtype), torch.zeros(m, hd, dtype=c_state.dtype))
+        c_state.zero_()
+    lstm_cell_tf32x3(x_pair[0], x_pair[1], h_pair[0], h_pair[1], w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out)
+
+
+def cmul(x, m):
+    return torch.view_as_real(torch.view_as_complex(x.contiguous()) * torch.view_as_complex(m.contiguous()))
 
 
 def fsn_clip_inv_mean(x, strides, B, T, F, denom, wgt=None, extra=None):
@@ -296,7 +309,7 @@ def unary(x, act, act_param=0.0, want_f32=True, want_pair=False):
     return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
 
 
-_UF_NAMES = ("glu_affine_act", "unary", "gemm_tf32x3_ex", "uf_prep", "uf_fusion", "group_layernorm", "attention", "uf_mask")
+_UF_NAMES = ("glu_affine_act", "unary", "cmul", "lstm_cell_tf32x3_ex", "gemm_tf32x3_ex", "uf_prep", "uf_fusion", "group_layernorm", "attention", "uf_mask")
 _orig_install = install
 
 

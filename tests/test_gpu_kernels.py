@@ -325,7 +325,7 @@ def test_attention_matches_softmax(over_t, cplx):
     assert err < 2e-5
 
 
-DEFAULT_LSTM_ENGINE = 0
+DEFAULT_LSTM_ENGINE = 2
 
 
 @pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (1024, 5, 3), (512, 7, 9), (128, 33, 15)])
@@ -349,3 +349,100 @@ def test_lstm_engines_agree(h, b, t):
         ops.set_lstm_engine(DEFAULT_LSTM_ENGINE)
     print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}, tcgen05 err {errs[2]:.3e}")
     assert max(errs) < 2e-5
+
+
+@pytest.mark.parametrize("c", [1, 16, 130])
+def test_pointwise_kernels_match_semantics(c):
+    """se_glu_affine_act (vector and scalar paths, fp32 + TF32-split outputs), se_unary, se_cmul."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(3, 7, 5, 2 * c, generator=g)
+    sc, sh = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    got, pair = ops.glu_affine_act(x.to(dev), sc.to(dev), sh.to(dev), "elu", want_f32=True, want_pair=True)
+    ref, _ = emu_ops.glu_affine_act(x.double(), sc.double(), sh.double(), "elu")
+    assert (got.cpu().double() - ref).abs().max() < 1e-5
+    assert ((pair[0] + pair[1]).cpu().double() - ref).abs().max() < 1e-5
+    u, up = ops.unary(x.to(dev), "elu", want_f32=True, want_pair=True)
+    uref = torch.where(x > 0, x, torch.expm1(x))
+    assert (u.cpu() - uref).abs().max() < 1e-6 and ((up[0] + up[1]).cpu() - uref).abs().max() < 1e-5
+    a, m = torch.randn(4, 9, 161, 2, generator=g), torch.randn(4, 9, 161, 2, generator=g)
+    z = ops.cmul(a.to(dev), m.to(dev)).cpu()
+    zr = torch.view_as_real(torch.view_as_complex(a) * torch.view_as_complex(m))
+    assert (z - zr).abs().max() < 1e-5
+
+
+def test_group_layernorm_wide_with_store_index():
+    """C = 1024 (GCRN GLSTM LayerNorm) with the out_index permutation, and C = 512 + residual (DPCRN ln1/ln2)."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(37, 1024, generator=g) * 3 + 1
+    gam, bet = torch.randn(1024, generator=g), torch.randn(1024, generator=g)
+    idx = torch.randperm(1024, generator=g).to(torch.int32)
+    y, pair = ops.group_layernorm(x.to(dev), 1, gam.to(dev), bet.to(dev), want_f32=True, want_pair=True,
+                                  out_index=idx.to(dev))
+    ref, _ = emu_ops.group_layernorm(x.double(), 1, gam.double(), bet.double(), out_index=idx)
+    assert (y.cpu().double() - ref).abs().max() < 2e-5
+    assert ((pair[0] + pair[1]).cpu().double() - ref).abs().max() < 2e-5
+    x2, r2 = torch.randn(50, 512, generator=g), torch.randn(50, 512, generator=g)
+    y2, _ = ops.group_layernorm(x2.to(dev), 1, gam[:512].contiguous().to(dev), bet[:512].contiguous().to(dev),
+                                res=r2.to(dev))
+    ref2, _ = emu_ops.group_layernorm(x2.double(), 1, gam[:512].double(), bet[:512].double(), res=r2.double())
+    assert (y2.cpu().double() - ref2).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("m", [200, 1031])
+def test_lstm_cell_ex_strided_bidirectional(m):
+    """se_lstm_cell_tf32x3_ex as DPCRN's intra Bi-LSTM uses it: strided x / h views of [M, 4, 128] buffers, first
+    step without state, forward and reverse position order -- against a float64 bidirectional LSTM."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(m)
+    x = torch.randn(m, 4, 128, generator=g)
+    out_ref = torch.zeros(m, 4, 128, dtype=torch.float64)
+    dst = (torch.zeros(m, 4, 128, device=dev), torch.zeros(m, 4, 128, device=dev))
+    src = ops.split_tf32(x.to(dev))
+    cst = torch.empty(m, 64, device=dev)
+    for d in range(2):
+        w_ih = torch.randn(256, 128, generator=g) / np.sqrt(128)
+        w_hh = torch.randn(256, 64, generator=g) / 8
+        b_ih, b_hh = torch.randn(256, generator=g) * 0.1, torch.randn(256, generator=g) * 0.1
+        P = packing.pack_lstm_cell(w_ih, w_hh, b_ih, b_hh)
+        order = (0, 1, 2, 3) if d == 0 else (3, 2, 1, 0)
+        prev = None
+        hr = torch.zeros(m, 64, dtype=torch.float64)
+        cr = torch.zeros(m, 64, dtype=torch.float64)
+        for f in order:
+            hh, hl = dst[0][:, f, 64 * d:64 * d + 64], dst[1][:, f, 64 * d:64 * d + 64]
+            ops.lstm_cell_tf32x3_ex((src[0][:, f], src[1][:, f]), prev, P["w_hi"].to(dev), P["w_lo"].to(dev),
+                                    P["bias"].to(dev), cst, hh, hl)
+            prev = (hh, hl)
+            gates = x[:, f].double() @ w_ih.double().t() + hr @ w_hh.double().t() + (b_ih + b_hh).double()
+            i, ff, gg, o = gates.chunk(4, dim=1)
+            cr = torch.sigmoid(ff) * cr + torch.sigmoid(i) * torch.tanh(gg)
+            hr = torch.sigmoid(o) * torch.tanh(cr)
+            out_ref[:, f, 64 * d:64 * d + 64] = hr
+    torch.cuda.synchronize()
+    err = ((dst[0] + dst[1]).cpu().double() - out_ref).abs().max().item()
+    print(f"lstm_cell_ex M={m}: max err {err:.3e}")
+    assert err < 2e-5
+
+
+def test_lstm_seq_multi_shared_weights():
+    """Groups that share one W_hh (DPCRN inter-LSTM: the 4 frequency positions of a frame)."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(5)
+    b, t, h, ng = 9, 12, 128, 4
+    xp = torch.randn(b, t, ng * 4 * h, generator=g)
+    whh = torch.randn(h // 8, h, 32, generator=g) / np.sqrt(h)
+    out = torch.empty(b, t, ng * h, device=dev)
+    ops.lstm_seq_multi(xp.to(dev), whh.to(dev), h, ng, out)
+    ref = emu_ops.lstm_seq_multi(xp.double(), whh.double(), h, ng, torch.empty(b, t, ng * h, dtype=torch.float64))
+    assert (out.cpu().double() - ref).abs().max() < 2e-5

@@ -235,6 +235,45 @@ def test_gcrn_matches_golden(name, ckpt):
     assert binv < 1e-5
 
 
+@pytest.mark.parametrize("name,ckpt", [("dpcrn_synth", None), ("dpcrn_ckpt", "DPCRN__vb_dpcrn_noncprs_model.pth")])
+def test_dpcrn_matches_golden(name, ckpt):
+    """``dpcrn`` (DPRNN twice, Bi-LSTM over F, CRM inside forward) vs the unmodified
+    DPCRN/DPCRN.py module, and the decoded waveform vs the restated dpcrn_decode_vb.py / drcrn_decode.py."""
+    dev = _dev()
+    import se_b200
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    p = float(g["p"])
+    if ckpt is None:
+        sd = synth.synthetic_state_dict(templates.dpcrn_template(), seed=0, gain=1.0)
+    else:
+        path = os.path.join(CKPT_DIR, ckpt)
+        if not os.path.exists(path):
+            pytest.skip("checkpoint copy not present")
+        sd = torch.load(path, map_location="cpu")
+    model = se_b200.dpcrn()
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    k = len(g["clip_ids"])
+    feat = torch.from_numpy(np.stack([g[f"feat{j}"] for j in range(k)])).to(dev)        # [B,2,T,161]
+    est = model(feat).cpu().numpy()
+    ref = np.stack([g[f"est{j}"] for j in range(k)])
+    e_net = np.abs(est - ref).max()
+    wav = torch.from_numpy(np.stack([g[f"wav{j}"] for j in range(k)])).to(dev)
+    taps = {}
+    y = se_b200.decode.enhance_dpcrn(model, wav, p=p, taps=taps)
+    c = taps["c"].cpu().numpy()
+    yn = y.cpu().numpy() * c[:, None]
+    refn = np.stack([g[f"ynorm{j}"] for j in range(k)])
+    rms = np.sqrt(np.mean((yn - refn) ** 2, axis=1))
+    rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
+    y1 = se_b200.decode.enhance_dpcrn(model, wav[1:2], p=p)
+    binv = (y[1:2] - y1).abs().max().item()
+    print(f"{name}: net max-abs {e_net:.3e} (|est| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
+          f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
+    assert (rms.max() <= RMS_GATE or rel.max() <= 1e-5) and rel.max() <= 2e-3
+    assert binv < 1e-5 * max(1.0, float(np.abs(refn).max()))
+
+
 @pytest.mark.parametrize("name,ckpt", [("uformer_synth", None),
                                        ("uformer_ckpt", "Uformer__wsj0_si84_300h_uformer_noncprs_model.pth")])
 def test_uformer_matches_golden(name, ckpt):

@@ -187,6 +187,26 @@ def test_gcrn_host_logic_matches_oracle(monkeypatch):
     assert (est - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item())
 
 
+def test_dpcrn_host_logic_matches_oracle(monkeypatch):
+    """Bi-LSTM over F as strided cell steps (forward / reverse order, layer stacking), the inter-LSTM as a
+    shared-weight multi-group launch, LayerNorm([4,128]) + residual, PReLU convs, de4 pad, the CRM multiply."""
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t = templates.dpcrn_template()
+    sd = synth.synthetic_state_dict(t, seed=7, gain=1.0)
+    m = se_b200.dpcrn()
+    assert list(m.state_dict().keys()) == list(t.keys())
+    m.load_state_dict(sd)
+    x = torch.randn(2, 2, 6, 161, generator=torch.Generator().manual_seed(4))
+    taps, rtaps = {}, {}
+    est = m._forward_impl(x, taps)
+    with torch.no_grad():
+        ref = nets.dpcrn_forward(sd, x, rtaps)
+    for k in ("en1", "en5", "dp1", "dp2", "de4", "de5"):
+        a, r = taps[k].permute(0, 3, 1, 2), rtaps[k]
+        assert (a - r).abs().max() < 2e-4 * max(1.0, r.abs().max().item()), k
+    assert (est - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
 def test_uformer_host_logic_matches_reference_fixture(monkeypatch):
     """668-entry state-dict drop-in + the whole Uformer orchestration (stacked complex convs, block QKV
     projection, signed head combination, gated dilated convs, fusion) against the fixture written by the

@@ -23,6 +23,8 @@ CASES = {
     "dccrn_ckpt": (templates.dccrn_template, decode.enhance_dccrn, "DCCRN__wsj0_si84_300h_dccrn_cprs_model.pth"),
     "gcrn_synth": (templates.gcrn_template, decode.enhance_gcrn, None),
     "gcrn_ckpt": (templates.gcrn_template, decode.enhance_gcrn, "GCRN__vb_gcrn_cprs_model.pth"),
+    "dpcrn_synth": (templates.dpcrn_template, decode.enhance_dpcrn, None),
+    "dpcrn_ckpt": (templates.dpcrn_template, decode.enhance_dpcrn, "DPCRN__vb_dpcrn_noncprs_model.pth"),
     "uformer_synth": (templates.uformer_template, decode.enhance_uformer, None),
     "uformer_ckpt": (templates.uformer_template, decode.enhance_uformer,
                      "Uformer__wsj0_si84_300h_uformer_noncprs_model.pth"),
@@ -33,7 +35,7 @@ def load_case(name):
     tmpl, enh, ckpt = CASES[name]
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     if ckpt is None:
-        sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name.startswith("uformer") else 2.0)
+        sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name.startswith(("uformer", "dpcrn")) else 2.0)
     else:
         path = os.path.join(CKPT_DIR, ckpt)
         if not os.path.exists(path):
@@ -50,7 +52,8 @@ def test_oracle_reproduces_golden(name):
     for j in range(len(g["clip_ids"])):
         wav = synth.noisy_clip(int(g["clip_ids"][j]), int(g["nsamp"]))
         assert np.array_equal(wav, g[f"wav{j}"]), "synthetic clip generator is not reproducible"
-        y, taps = enh(sd, wav.astype(np.float64))
+        kw = {"p": float(g["p"])} if "p" in g.files else {}
+        y, taps = enh(sd, wav.astype(np.float64), **kw)
         key = "mask" if "mask" in taps else "est"
         # Uformer fixtures come from the unmodified module (different op order than the restatement)
         tol = 5e-4 if name.startswith("uformer") else 2e-5

@@ -55,7 +55,7 @@ def main():
             ref_h = hs.clone()
         else:
             res[f"lstm_seq_{nm}_B64_T401_H1024"]["max_abs_diff_vs_fma"] = (hs - ref_h).abs().max().item()
-    ops.set_lstm_engine(0)
+    ops.set_lstm_engine(2)
     # conv layers of CRN
     for (fin, c0, c1, co, kind) in [(9, 128, 0, 256, "conv"), (19, 64, 0, 128, "conv"), (4, 256, 256, 128, "deconv"),
                                     (9, 128, 128, 64, "deconv")]:

@@ -30,6 +30,8 @@ CASES = {
                    se_b200.decode.enhance_fullsubnet, odecode.enhance_fullsubnet, 32, 10, 256, dict(p=0.5)),
     "gcrn": (lambda: se_b200.gcrn.Net(), templates.gcrn_template, se_b200.decode.enhance_gcrn, odecode.enhance_gcrn,
              64, 4, 160, dict(p=0.5)),
+    "dpcrn": (lambda: se_b200.dpcrn(), templates.dpcrn_template, se_b200.decode.enhance_dpcrn, odecode.enhance_dpcrn,
+              64, 4, 160, dict(p=1.0)),
     "uformer": (lambda: se_b200.Uformer(), templates.uformer_template, se_b200.decode.enhance_uformer, None,
                 64, 4, 160, dict()),
 }
@@ -41,7 +43,7 @@ def main():
     dev = torch.device("cuda")
     for name in which:
         ctor, tmpl, genh, oenh, bsz, secs, hop, kw = CASES[name]
-        sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name == "uformer" else 2.0)
+        sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name in ("uformer", "dpcrn") else 2.0)
         model = ctor()
         model.load_state_dict(sd)
         model.eval().cuda()

@@ -14,7 +14,7 @@ import se_b200  # noqa: E402
 from se_b200 import _lib, ops  # noqa: E402
 
 EV = ["poll_start", "barrier_seen", "tma_issued", "first_stage", "last_stage", "acc_done", "dsmem_sent",
-      "cluster_passed", "cell_done", "arrived"]
+      "cluster_passed", "cell_done", "arrived", "proxy_fenced", "cta_synced"]
 
 
 def main():
@@ -39,7 +39,6 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     lib.se_debug_lstm_tc_profile(None, 1, 1)
-    ops.set_lstm_engine(0)
     ms = e0.elapsed_time(e1)
     st = buf.cpu().numpy().reshape(128, NS, len(EV)).astype(np.float64)
     # SM clocks are not synchronised across SMs: only per-CTA differences are meaningful
@@ -47,7 +46,7 @@ def main():
     out = {"T": T, "ms": ms, "us_per_step": 1e3 * ms / T, "cycles_per_step": step,
            "ghz_implied": step / (1e3 * ms / T) / 1e3}
     seg = {}
-    for a, b in [(0, 1), (1, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (1, 2)]:
+    for a, b in [(0, 1), (1, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (8, 10), (10, 11), (11, 9), (1, 2)]:
         d = st[:, 1:, b] - st[:, 1:, a]
         seg[f"{EV[a]}->{EV[b]}"] = {"mean": float(d.mean()), "p10": float(np.percentile(d, 10)),
                                     "p90": float(np.percentile(d, 90)), "max": float(d.max())}
