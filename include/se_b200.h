@@ -345,6 +345,48 @@ int se_attention(const float* qkv, int ld, int nheads, const int* head_out, cons
 int se_uf_mask(const float* cmask, const float* mdec, const float* mag, const float* phase, int B, int T, int F,
                float* est, se_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Utterance-level normalisations of the TCM family + CTSNet stage glue; see csrc/norm.cu.
+ *   nn.InstanceNorm{1,2}d(affine=True), statistics per (clip, channel) over T (x F) even in eval()
+ *       (CTSNet/Step1_network.py:48,164; Step2_network.py:44,131)           -> se_chan_stats + se_chan_norm
+ *   CumulativeLayerNorm{1,2}d, statistics over (C[,F]) of all frames <= t
+ *       (CTSNet_new/Step1_network.py:213-286)                              -> se_cum_stats  + se_chan_norm
+ * x is channels-last [B, rows, Cin] (rows = T*F).  `pre` is applied on the fly before the statistics / the
+ * normalisation (it is what the reference computes between the convolution and the norm):
+ *     NONE       v = x[r, c]                                   (Cin == C)
+ *     GLU        v = x[r, c] * sigmoid(x[r, C + c])            (Cin == 2C; Gate_Conv, Step1_network.py:150-151)
+ *     PRELU      v = prelu(x[r, c % Cin], pre_slope[c])        (C a multiple of Cin: several branches, each with
+ *                                                               its own PReLU, read the same tensor; :163,170)
+ *     GLU_PRELU  v = prelu(GLU, pre_slope[c])                  (TCM output path, :188-189)
+ * se_chan_norm: y = (v - mean) * rstd * gamma[c] + beta[c], then `post`:
+ *     PRELU  per-channel slopes (:49);   FIR  ShareSepConv (:195-209): y[t] = sum_k fir_w[g][k] y[t-(K-1)+k] with zero
+ *     history, one filter per channel group g (fir_groups groups of C/fir_groups channels); rows must be T.
+ *   stat_mode INSTANCE: mean/rstd [B, C];  CUMULATIVE: mean/rstd [B, T, G], T = rows / rows_per_t, one set per channel
+ *   group (G = `groups` / `stat_groups`: branches that were stacked on the channel axis keep their own statistics).
+ *   Outputs: fp32 `out` and/or the TF32 split pair.  eps as the reference module's (1e-5).
+ *   ws: se_chan_stats_ws_bytes(B, rows, C) bytes, ZERO-filled once by the caller (the kernels leave it zeroed);
+ *       se_cum_stats needs 16 * B * T * groups bytes (no initialisation).  C must divide 256 for se_chan_stats.
+ * se_add: out = a + b (x_acc of Step1_network.py:28-33).
+ * se_cts_glue1 / se_cts_glue2: CTSNet/two_stage_com_decode_vb.py:79-84 -- stage-1 magnitude x noisy phase,
+ *   cat(noisy RI, stage-1 RI) -> s2_in [n, 4];  est [n, 2] = stage-2 output + stage-1 RI.
+ * ------------------------------------------------------------------------------------- */
+enum { SE_NORM_PRE_NONE = 0, SE_NORM_PRE_GLU = 1, SE_NORM_PRE_PRELU = 2, SE_NORM_PRE_GLU_PRELU = 3 };
+enum { SE_NORM_POST_NONE = 0, SE_NORM_POST_PRELU = 1, SE_NORM_POST_FIR = 2 };
+enum { SE_NORM_STAT_INSTANCE = 0, SE_NORM_STAT_CUMULATIVE = 1 };
+long long se_chan_stats_ws_bytes(int B, long long rows, int C);
+int se_chan_stats(const float* x, int B, long long rows, int Cin, int C, int pre, const float* pre_slope, float eps,
+                  float* mean, float* rstd, void* ws, se_stream_t stream);
+int se_cum_stats(const float* x, int B, int T, int F, int Cin, int C, int groups, int pre, const float* pre_slope,
+                 float eps, float* mean, float* rstd, void* ws, se_stream_t stream);
+int se_chan_norm(const float* x, int B, long long rows, int Cin, int C, int pre, const float* pre_slope,
+                 const float* mean, const float* rstd, int stat_mode, int rows_per_t, int stat_groups,
+                 const float* gamma, const float* beta, int post, const float* post_slope, const float* fir_w, int fir_k, int fir_groups,
+                 float* out, float* out_hi, float* out_lo, se_stream_t stream);
+int se_add(const float* a, const float* b, long long n, float* out, float* out_hi, float* out_lo, se_stream_t stream);
+int se_cts_glue1(const float* x_ri, const float* est_mag, long long n, float* s2_in, se_stream_t stream);
+int se_cts_glue2(const float* out_r, const float* out_i, const float* s2_in, long long n, float* est,
+                 se_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

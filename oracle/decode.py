@@ -166,3 +166,34 @@ def enhance_dpcrn(sd, wav, p=1.0):
     y = dsp.istft(de.T, n_fft, win, hop, length=len(x))
     taps = {"c": c, "feat": feat, "est": est, "y_norm": y.astype(np.float32)}
     return (y / c).astype(np.float32), taps
+
+
+def enhance_ctsnet(sds, wav, p=1.0, cumulative=False):
+    """``CTSNet/two_stage_com_decode_vb.py:61-95`` (torch dialect; p = 1.0 there (:73,87), 0.5 for the cprs
+    checkpoints of two_stage_com_decode.py / CTSNet_new).  ``sds`` = (stage-1 state-dict, stage-2 state-dict).
+    Stage 1 maps the magnitude, its estimate takes the noisy phase, stage 2 sees cat(noisy RI, stage-1 RI) and
+    predicts a complex residual (backend rules (iv) + (ii)); iSTFT without ``length`` then ``[:wav_len]``."""
+    from . import nets as _n
+    sd1, sd2 = sds
+    n_fft, win, hop = dsp.GEOMETRIES["320"]
+    x, c = dsp.rms_scale(wav)                                               # :62-63
+    wav_len = len(x)
+    frame_num = int(np.ceil((wav_len - 320 + 320) / 160 + 1))               # :65
+    fake_len = (frame_num - 1) * 160 + 320 - 320
+    x32 = np.concatenate((x, np.zeros(fake_len - wav_len))).astype(np.float32)   # :68 FloatTensor
+    spec = dsp.stft(x32, n_fft, win, hop).T                                 # :69-70  [T,F] complex64
+    mag, ph = (np.abs(spec) ** p).astype(np.float32), np.angle(spec).astype(np.float32)   # :73
+    feat = np.stack((mag * np.cos(ph), mag * np.sin(ph))).astype(np.float32)             # :75  [2,T,F]
+    with torch.no_grad():
+        fx = torch.from_numpy(feat)[None]
+        phase = torch.from_numpy(ph)[None]
+        est1 = _n.ctsnet_step1_forward(sd1, torch.norm(fx, dim=1), cumulative)            # :79
+        s1 = torch.stack((est1 * torch.cos(phase), est1 * torch.sin(phase)), dim=1)       # :80-81
+        s2 = _n.ctsnet_step2_forward(sd2, torch.cat((fx, s1), dim=1), cumulative=cumulative) + s1   # :82-84
+    est = s2.squeeze(0).numpy()
+    emag = np.sqrt(est[0] ** 2 + est[1] ** 2) ** (1.0 / p)                  # :87
+    eph = np.arctan2(est[1], est[0])                                        # :89
+    y = dsp.istft((emag * np.cos(eph) + 1j * emag * np.sin(eph)).T.astype(np.complex64), n_fft, win, hop, None)  # :93
+    y = y[:wav_len]                                                         # :95
+    taps = {"c": c, "feat": feat, "est1": est1.squeeze(0).numpy(), "est": est, "y_norm": y.astype(np.float32)}
+    return (y / c).astype(np.float32), taps

@@ -226,6 +226,61 @@ def make_uformer():
         print(f"{name}: ref_vs_oracle (waveform max-abs) {worst:.3e}, out rms {float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+CTS_CASES = [
+    # name, model dir, stage-1 ckpt, stage-2 ckpt, samples, clip ids, p, cumulative
+    ("ctsnet_synth", "CTSNet", None, None, 8000, (14, 15), 0.5, False),
+    ("ctsnet_ckpt", "CTSNet", "step1_vb_cts_noncprs_model_final.pth", "step2_vb_cts_noncprs_model.pth", 16000, (14, 15),
+     1.0, False),                                                       # as CTSNet/two_stage_com_decode_vb.py runs it
+    ("ctsnet_new_synth", "CTSNet_new", None, None, 8000, (16, 17), 1.0, True),
+    ("ctsnet_new_ckpt", "CTSNet_new", "step1_vb_cts_cprs_model_final.pth", "step2_vb_cts_cprs_model.pth", 16000, (16, 17),
+     0.5, True),                                                        # as CTSNet_new/two_stage_com_decode_vb.py
+]
+
+
+def cts_state_dicts(mdir, ck1, ck2, cumulative, loader=None):
+    if ck1 is None:
+        return (synth.synthetic_state_dict(templates.ctsnet_step1_template(cumulative), seed=0, gain=1.0),
+                synth.synthetic_state_dict(templates.ctsnet_step2_template(cumulative=cumulative), seed=1, gain=1.0))
+    loader = loader or (lambda name: torch.load(ref_shims.checkpoint_path(mdir, name), map_location="cpu"))
+    return loader(ck1), loader(ck2)
+
+
+def make_ctsnet():
+    """Fixtures from the UNMODIFIED CTSNet{,_new}/Step{1,2}_network.py modules run through the two-stage glue of
+    two_stage_com_decode_vb.py (the oracle restatement supplies the DSP around them)."""
+    for name, mdir, ck1, ck2, nsamp, clip_ids, p, cum in CTS_CASES:
+        m1 = ref_shims.import_reference(mdir, "Step1_network").Step1_net().eval()
+        m2 = ref_shims.import_reference(mdir, "Step2_network").Step2_net(X=6, R=3).eval()
+        sd1, sd2 = cts_state_dicts(mdir, ck1, ck2, cum)
+        m1.load_state_dict(sd1)
+        m2.load_state_dict(sd2)
+        rec = {"digest": np.array(sd_digest(sd1) + sd_digest(sd2)), "clip_ids": np.array(clip_ids),
+               "nsamp": np.array(nsamp), "p": np.array(p)}
+        worst = 0.0
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = decode.enhance_ctsnet((sd1, sd2), wav.astype(np.float64), p=p, cumulative=cum)
+            with torch.no_grad():                                           # two_stage_com_decode_vb.py:79-84
+                fx = torch.from_numpy(taps["feat"])[None]
+                ph = torch.atan2(fx[:, 1], fx[:, 0])
+                e1 = m1(torch.norm(fx, dim=1))
+                s1 = torch.stack((e1 * torch.cos(ph), e1 * torch.sin(ph)), dim=1)
+                est_ref = (m2(torch.cat((fx, s1), dim=1)) + s1).squeeze(0).numpy()
+            worst = max(worst, float(np.abs(est_ref - taps["est"]).max()))
+            rec[f"wav{j}"] = wav
+            rec[f"feat{j}"] = taps["feat"]
+            rec[f"est1{j}"] = e1.squeeze(0).numpy().astype(np.float32)
+            rec[f"est{j}"] = est_ref.astype(np.float32)
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        rec["ref_vs_oracle"] = np.array(worst)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: ref_vs_oracle max-abs {worst:.3e}, |est| max {float(np.abs(rec['est0']).max()):.2f}, out rms "
+              f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def sd_digest(sd) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
@@ -281,3 +336,5 @@ if __name__ == "__main__":
         make_dpcrn()
     if len(sys.argv) < 2 or sys.argv[1] == "uformer":
         make_uformer()
+    if len(sys.argv) < 2 or sys.argv[1] == "ctsnet":
+        make_ctsnet()

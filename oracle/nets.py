@@ -543,3 +543,107 @@ def dpcrn_forward(sd, inpt, taps=None):
     mr, mi = x[:, 0], x[:, 1]
     xr, xi = inpt[:, 0], inpt[:, 1]
     return torch.stack((xr * mr - xi * mi, xr * mi + xi * mr), dim=1)        # :39-42
+
+
+# ----------------------------------------------------------------------------------------
+# CTSNet  (CTSNet/Step1_network.py, CTSNet/Step2_network.py; CTSNet_new/* swap the norms)
+# ----------------------------------------------------------------------------------------
+def _cts_norm(x, sd, pre, cumulative):
+    """nn.InstanceNorm{1,2}d(affine=True) -- per (clip, channel) statistics over (T[,F]) even in eval()
+    (track_running_stats=False; Step1_network.py:48,164) -- or, for the ``_new`` variants, the causal
+    CumulativeLayerNorm{1,2}d (CTSNet_new/Step1_network.py:213-286): statistics over (C[,F]) of all frames <= t."""
+    if not cumulative:
+        return F.instance_norm(x, None, None, sd[pre + ".weight"], sd[pre + ".bias"], True, 0.0, 1e-5)
+    red = [1, 3] if x.dim() == 4 else [1]
+    step_sum = x.sum(red, keepdim=True)
+    step_pow = x.pow(2).sum(red, keepdim=True)
+    cum_sum, cum_pow = torch.cumsum(step_sum, dim=2), torch.cumsum(step_pow, dim=2)
+    per = x.shape[1] * (x.shape[3] if x.dim() == 4 else 1)
+    cnt = torch.arange(per, per * (x.shape[2] + 1), per, dtype=x.dtype).view([1, 1, -1] + [1] * (x.dim() - 3))
+    mean = cum_sum / cnt
+    var = (cum_pow - 2 * mean * cum_sum) / cnt + mean.pow(2)
+    return (x - mean) / (var + 1e-5).sqrt() * sd[pre + ".gain"] + sd[pre + ".bias"]
+
+
+def _cts_gate_conv(x, sd, pre, transpose):
+    """Gate_Conv (Step1_network.py:127-151): conv(x) * sigmoid(gate_conv(x)); encoder convs pad one frame on top
+    (causal), decoder transposed convs drop the last output frame (Chomp_T(1))."""
+    if transpose:
+        f = lambda n: F.conv_transpose2d(x, sd[f"{pre}.{n}.0.weight"], sd[f"{pre}.{n}.0.bias"],   # noqa: E731
+                                         stride=(1, 2))[:, :, :-1, :]
+    else:
+        xp = F.pad(x, (0, 0, 1, 0))
+        f = lambda n: F.conv2d(xp, sd[f"{pre}.{n}.1.weight"], sd[f"{pre}.{n}.1.bias"], stride=(1, 2))   # noqa: E731
+    return f("conv") * torch.sigmoid(f("gate_conv"))
+
+
+def _cts_tcm(x, sd, pre, d, branches, cumulative):
+    """Glu / glu (Step1_network.py:163-193, Step2_network.py:124-156), dilation d.  x [B,256,T]."""
+    def branch(u, name):
+        u = F.prelu(u, sd[f"{pre}.{name}.0.weight"])
+        u = _cts_norm(u, sd, f"{pre}.{name}.1", cumulative)
+        w = sd[f"{pre}.{name}.2.weight"]                       # ShareSepConv: one FIR shared by all channels
+        k = w.shape[-1]
+        u = F.conv1d(F.pad(u, (k - 1, 0)), w.expand(u.shape[1], 1, k).contiguous(), None, groups=u.shape[1])
+        return F.conv1d(F.pad(u, (4 * d, 0)), sd[f"{pre}.{name}.4.weight"], None, dilation=d)
+    u = F.conv1d(x, sd[f"{pre}.in_conv.weight"])
+    u = branch(u, branches[0]) * torch.sigmoid(branch(u, branches[1]))
+    u = F.prelu(u, sd[f"{pre}.out_conv.0.weight"])
+    u = _cts_norm(u, sd, f"{pre}.out_conv.1", cumulative)
+    return F.conv1d(u, sd[f"{pre}.out_conv.2.weight"]) + x
+
+
+def _cts_encoder(sd, x, pre, cumulative, taps=None):
+    skips = []
+    for i in range(5):
+        x = _cts_gate_conv(x, sd, f"{pre}.{i}.0", False)
+        x = F.prelu(_cts_norm(x, sd, f"{pre}.{i}.1", cumulative), sd[f"{pre}.{i}.2.weight"])
+        skips.append(x)
+        if taps is not None:
+            taps[f"e{i + 1}"] = x
+    return x, skips
+
+
+def _cts_decoder(sd, x, skips, pre, cumulative):
+    for i in range(5):
+        x = torch.cat((x, skips[-(i + 1)]), dim=1)
+        x = _cts_gate_conv(x, sd, f"{pre}.{i}.0", True)
+        x = F.prelu(_cts_norm(x, sd, f"{pre}.{i}.1", cumulative), sd[f"{pre}.{i}.2.weight"])
+    return x.squeeze(1)
+
+
+def ctsnet_step1_forward(sd, x, cumulative=False, taps=None):
+    """Step1_net.forward, Step1_network.py:21-41.  x [B,T,161] magnitude -> [B,T,161] magnitude."""
+    x, skips = _cts_encoder(sd, x.unsqueeze(1), "en.en", cumulative, taps)
+    b, _, t, _ = x.shape
+    x = x.permute(0, 1, 3, 2).contiguous().view(b, -1, t)                    # [B, 64*4, T], feature = c*4 + f
+    acc = torch.zeros_like(x)
+    for s in (1, 2, 3):                                                      # :28-33
+        for j in range(6):
+            x = _cts_tcm(x, sd, f"tcm{s}.tcm_list.{j}", 2 ** j, ("left_conv", "right_conv"), cumulative)
+        acc = acc + x
+    if taps is not None:
+        taps["tcm"] = acc
+    x = acc.view(b, 64, 4, t).permute(0, 1, 3, 2).contiguous()
+    x = _cts_decoder(sd, x, skips, "de.de", cumulative)
+    return F.softplus(F.linear(x, sd["de.de6.0.weight"], sd["de.de6.0.bias"]))   # :113-115
+
+
+def ctsnet_step2_forward(sd, inpt, X=6, R=3, cumulative=False, taps=None):
+    """Step2_net.forward, Step2_network.py:23-37.  inpt [B,4,T,161] (noisy RI, stage-1 RI) -> [B,2,T,161]."""
+    x, skips = _cts_encoder(sd, inpt, "en.en_module", cumulative, taps)
+    b, _, t, _ = x.shape
+    x = x.permute(0, 1, 3, 2).contiguous().view(b, -1, t)
+    acc = torch.zeros_like(x)
+    for r in range(R):
+        for j in range(X):
+            x = _cts_tcm(x, sd, f"tcm_list.{r}.glu_list.{j}", 2 ** j, ("ori_conv", "att_ori"), cumulative)
+        acc = acc + x
+    if taps is not None:
+        taps["tcm"] = acc
+    x = acc.view(b, 64, 4, t).permute(0, 1, 3, 2).contiguous()
+    outs = []
+    for br in ("de_r", "de_i"):
+        d = _cts_decoder(sd, x, skips, f"{br}.de_list", cumulative)
+        outs.append(F.linear(d, sd[f"{br}.de6.0.weight"], sd[f"{br}.de6.0.bias"]))
+    return torch.stack(outs, dim=1)

@@ -159,3 +159,69 @@ def uformer_template():
     import os
     keys = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "uformer_keys.json")))
     return {k: tuple(shape) for k, shape, _ in keys}
+
+
+def _cts_norm_rows(d, pre, c, cumulative, dims):
+    if cumulative:
+        shape = (1, c) + (1,) * dims
+        d[pre + ".gain"], d[pre + ".bias"] = shape, shape
+    else:
+        d[pre + ".weight"], d[pre + ".bias"] = (c,), (c,)
+
+
+def _cts_codec(d, en_pre, de_pres, cin, cumulative):
+    for i in range(5):
+        ci, kf = (cin, 5) if i == 0 else (64, 3)
+        for n in ("conv", "gate_conv"):
+            d[f"{en_pre}.{i}.0.{n}.1.weight"] = (64, ci, 2, kf)
+            d[f"{en_pre}.{i}.0.{n}.1.bias"] = (64,)
+        _cts_norm_rows(d, f"{en_pre}.{i}.1", 64, cumulative, 2)
+        d[f"{en_pre}.{i}.2.weight"] = (64,)
+    for de_pre, fc in de_pres:
+        for i in range(5):
+            co, kf = (1, 5) if i == 4 else (64, 3)
+            for n in ("conv", "gate_conv"):
+                d[f"{de_pre}.{i}.0.{n}.0.weight"] = (128, co, 2, kf)
+                d[f"{de_pre}.{i}.0.{n}.0.bias"] = (co,)
+            _cts_norm_rows(d, f"{de_pre}.{i}.1", co, cumulative, 2)
+            d[f"{de_pre}.{i}.2.weight"] = (co,)
+        d[fc + ".weight"], d[fc + ".bias"] = (161, 161), (161,)
+
+
+def _cts_tcm(d, pre, j, branches, cumulative):
+    d[f"{pre}.in_conv.weight"] = (64, 256, 1)
+    for n in branches:
+        d[f"{pre}.{n}.0.weight"] = (64,)
+        _cts_norm_rows(d, f"{pre}.{n}.1", 64, cumulative, 1)
+        d[f"{pre}.{n}.2.weight"] = (1, 1, 2 * 2 ** j - 1)
+        d[f"{pre}.{n}.4.weight"] = (64, 64, 5)
+    d[f"{pre}.out_conv.0.weight"] = (64,)
+    _cts_norm_rows(d, f"{pre}.out_conv.1", 64, cumulative, 1)
+    d[f"{pre}.out_conv.2.weight"] = (256, 64, 1)
+
+
+def ctsnet_step1_template(cumulative=False):
+    """CTSNet/Step1_network.py:12-19 (``Step1_net``); cumulative=True: CTSNet_new (gain/bias of the cLN)."""
+    d = {}
+    _cts_codec(d, "en.en", [("de.de", "de.de6.0")], 1, cumulative)
+    # module registration order: en, de (de6 before the de list, Step1_network.py:110-115), tcm1..3
+    keys = list(d)
+    fc = [k for k in keys if k.startswith("de.de6")]
+    rest = [k for k in keys if not k.startswith("de.de6")]
+    first_de = next(i for i, k in enumerate(rest) if k.startswith("de.de."))
+    order = rest[:first_de] + fc + rest[first_de:]
+    d = {k: d[k] for k in order}
+    for s in (1, 2, 3):
+        for j in range(6):
+            _cts_tcm(d, f"tcm{s}.tcm_list.{j}", j, ("left_conv", "right_conv"), cumulative)
+    return d
+
+
+def ctsnet_step2_template(X=6, R=3, cumulative=False):
+    """CTSNet/Step2_network.py:13-21 (``Step2_net(X, R)``)."""
+    d = {}
+    _cts_codec(d, "en.en_module", [("de_r.de_list", "de_r.de6.0"), ("de_i.de_list", "de_i.de6.0")], 4, cumulative)
+    for r in range(R):
+        for j in range(X):
+            _cts_tcm(d, f"tcm_list.{r}.glu_list.{j}", j, ("ori_conv", "att_ori"), cumulative)
+    return d

@@ -78,7 +78,16 @@ PROTOTYPES = {
     "se_unary": (_I, [_P, _LL, _I, _F, _P, _P, _P, _P]),
     "se_cmul": (_I, [_P, _P, _LL, _P, _P]),
     "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
+    "se_chan_stats_ws_bytes": (_LL, [_I, _LL, _I]),
+    "se_chan_stats": (_I, [_P, _I, _LL, _I, _I, _I, _P, _F, _P, _P, _P, _P]),
+    "se_cum_stats": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P]),
+    "se_chan_norm": (_I, [_P, _I, _LL, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "se_add": (_I, [_P, _P, _LL, _P, _P, _P, _P]),
+    "se_cts_glue1": (_I, [_P, _P, _LL, _P, _P]),
+    "se_cts_glue2": (_I, [_P, _P, _P, _LL, _P, _P]),
 }
+NORM_PRE = {"none": 0, "glu": 1, "prelu": 2, "glu_prelu": 3}
+NORM_POST = {"none": 0, "prelu": 1, "fir": 2}
 
 _lib = None
 

@@ -536,15 +536,22 @@ int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh
   cfg.blockDim = dim3(LT_THREADS);
   cfg.dynamicSmemBytes = LT_SMEM_BYTES;
   cfg.stream = s;
+  // SE_LSTM_TC_COOP=0 drops the cooperative attribute: Nsight Compute cannot replay a cooperative CLUSTER launch
+  // (LaunchFailed under ncu), so profiling runs rely on the idle device + the bounded spins instead.
+  static int coop = -1;
+  if (coop < 0) {
+    coop = 1;
+    if (const char* e = getenv("SE_LSTM_TC_COOP")) coop = atoi(e) ? 1 : 0;
+  }
   cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeCooperative;   // all 128 CTAs co-resident or the launch fails (never a deadlock)
-  at[0].val.cooperative = 1;
-  at[1].id = cudaLaunchAttributeClusterDimension;
-  at[1].val.clusterDim.x = 4 * mc;
-  at[1].val.clusterDim.y = 1;
-  at[1].val.clusterDim.z = 1;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 4 * mc;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;   // all 128 CTAs co-resident or the launch fails (never a deadlock)
+  at[1].val.cooperative = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = coop ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, lt_kernel(mc), map_hi, map_lo, p);
   if (e != cudaSuccess) {
     set_error("se_lstm_seq (tcgen05, multicast %d): cooperative cluster launch: %s", mc, cudaGetErrorString(e));

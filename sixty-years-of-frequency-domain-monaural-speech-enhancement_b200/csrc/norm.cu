@@ -1,0 +1,367 @@
+// Utterance-level normalisations of the TCM family (CTSNet, TaylorSENet, G2Net) + the CTSNet two-stage glue.
+//
+//   nn.InstanceNorm{1,2}d(affine=True)  (CTSNet/Step1_network.py:48,164): statistics per (clip, channel) over the
+//       whole utterance (T or T x F) -- also in eval(), the reference never tracks running statistics -- so a tile
+//       cannot be normalised before the clip has been seen: two passes.
+//         se_chan_stats   pass 1: mean / rstd per (b, c) of pre(x)        (fp64 combination, deterministic)
+//         se_chan_norm    pass 2: post( (pre(x) - mean) * rstd * gamma + beta )
+//   CumulativeLayerNorm{1,2}d  (CTSNet_new/Step1_network.py:213-286): statistics over (C[,F]) of all frames <= t.
+//         se_cum_stats    per-frame sums -> prefix scan over T -> mean / rstd per (b, t); se_chan_norm applies them.
+//   pre  = what the reference computes between the convolution and the norm: the Gate_Conv product
+//          a * sigmoid(b) (Step1_network.py:150-151), a per-channel PReLU (:163,170,178), or both (the TCM output
+//          path: left * sigmoid(right) -> PReLU -> norm, :188-189);
+//   post = per-channel PReLU (encoder / decoder blocks, :49) or ShareSepConv (:195-209): ONE causal FIR shared by
+//          all channels of a branch, applied to the normalised signal with zero history.
+// All tensors are channels-last [B, rows, C]; rows = T * F (F = 1 inside the TCMs).  HBM-bound.
+#include "tc_common.cuh"
+
+namespace se {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x : a * x; }
+
+// value of pre(x) at (row r, channel c).  xr = x + r * Cin
+__device__ __forceinline__ float pre_value(const float* __restrict__ xr, int c, int Cin, int C, int pre,
+                                           const float* __restrict__ slope) {
+  switch (pre) {
+    case SE_NORM_PRE_GLU: return __ldg(xr + c) * sigmoid_f(__ldg(xr + C + c));
+    case SE_NORM_PRE_PRELU: return prelu_f(__ldg(xr + (c % Cin)), __ldg(slope + c));
+    case SE_NORM_PRE_GLU_PRELU: return prelu_f(__ldg(xr + c) * sigmoid_f(__ldg(xr + C + c)), __ldg(slope + c));
+    default: return __ldg(xr + c);
+  }
+}
+
+// ---- pass 1, instance statistics -----------------------------------------------------------------------------
+// grid (chunks, B).  Thread tid owns channel c = tid % CL (CL = C rounded so that NT % CL == 0) and row lane tid / CL.
+// ws: double partial[B][chunks][C][2], then unsigned ticket[B] (zero on entry, left zero on exit).
+__global__ void __launch_bounds__(NT) chan_stats_kernel(const float* __restrict__ x, long long rows, int Cin, int C,
+                                                       int pre, const float* __restrict__ slope, float eps,
+                                                       float* __restrict__ mean, float* __restrict__ rstd,
+                                                       double* __restrict__ partial, unsigned* __restrict__ ticket) {
+  __shared__ double sh[NT][2];
+  __shared__ bool last;
+  const int tid = threadIdx.x, b = blockIdx.y, chunks = gridDim.x;
+  const int lanes = NT / C, c = tid % C, lane = tid / C;
+  const long long per = (rows + chunks - 1) / chunks;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(rows, r0 + per);
+  const float* xb = x + (long long)b * rows * Cin;
+  double s = 0.0, ss = 0.0;
+  if (lane < lanes) {
+    float fs = 0.f, fss = 0.f;
+    int n = 0;
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+      const float v = pre_value(xb + r * Cin, c, Cin, C, pre, slope);
+      fs += v;
+      fss = fmaf(v, v, fss);
+      if (++n == 64) {          // short fp32 runs, combined in fp64
+        s += fs;
+        ss += fss;
+        fs = fss = 0.f;
+        n = 0;
+      }
+    }
+    s += fs;
+    ss += fss;
+  }
+  sh[tid][0] = s;
+  sh[tid][1] = ss;
+  __syncthreads();
+  if (tid < C) {
+    for (int l = 1; l < lanes; ++l) {
+      s += sh[tid + l * C][0];
+      ss += sh[tid + l * C][1];
+    }
+    double* p = partial + (((long long)b * chunks + blockIdx.x) * C + tid) * 2;
+    p[0] = s;
+    p[1] = ss;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(ticket + b, 1u);
+    last = prev == (unsigned)chunks - 1u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (tid < C) {
+    double ts = 0.0, tss = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+      const double* p = partial + (((long long)b * chunks + k) * C + tid) * 2;
+      ts += p[0];
+      tss += p[1];
+    }
+    const double m = ts / (double)rows;
+    double var = tss / (double)rows - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[(long long)b * C + tid] = (float)m;
+    rstd[(long long)b * C + tid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  if (tid == 0) ticket[b] = 0u;
+}
+
+// ---- pass 1, cumulative statistics -----------------------------------------------------------------------------
+// step sums: one block per (b, t): sum and sum of squares of pre(x) over the F x C elements of the frame.
+// grid (B*T, G): channel group g = channels [g*C/G, (g+1)*C/G) (branches that share a tensor keep their own statistics)
+__global__ void __launch_bounds__(NT) cum_step_kernel(const float* __restrict__ x, int F, int Cin, int C, int G, int pre,
+                                                     const float* __restrict__ slope, double* __restrict__ step) {
+  __shared__ double sh[NT / 32][2];
+  const long long bt = blockIdx.x;
+  const int g = blockIdx.y, cg = C / G;
+  const float* xb = x + bt * F * Cin;
+  const int n = F * cg;
+  float fs = 0.f, fss = 0.f;
+  for (int i = threadIdx.x; i < n; i += NT) {
+    const int f = i / cg, c = g * cg + (i - f * cg);
+    const float v = pre_value(xb + (long long)f * Cin, c, Cin, C, pre, slope);
+    fs += v;
+    fss = fmaf(v, v, fss);
+  }
+  double s = fs, ss = fss;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5][0] = s;
+    sh[threadIdx.x >> 5][1] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < NT / 32; ++w) {
+      s += sh[w][0];
+      ss += sh[w][1];
+    }
+    step[(bt * G + g) * 2] = s;
+    step[(bt * G + g) * 2 + 1] = ss;
+  }
+}
+// prefix over T (one warp per clip; T is a few hundred): mean_t, rstd_t of everything up to and including frame t
+__global__ void __launch_bounds__(32) cum_scan_kernel(const double* __restrict__ step, int T, int G, int per_frame,
+                                                     float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int b = blockIdx.x, g = blockIdx.y, lane = threadIdx.x;
+  double cs = 0.0, css = 0.0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    double s = t < T ? step[(((long long)b * T + t) * G + g) * 2] : 0.0;
+    double ss = t < T ? step[(((long long)b * T + t) * G + g) * 2 + 1] : 0.0;
+    for (int o = 1; o < 32; o <<= 1) {
+      const double a = __shfl_up_sync(0xffffffffu, s, o), a2 = __shfl_up_sync(0xffffffffu, ss, o);
+      if (lane >= o) {
+        s += a;
+        ss += a2;
+      }
+    }
+    s += cs;
+    ss += css;
+    if (t < T) {
+      const double cnt = (double)per_frame * (double)(t + 1);
+      const double m = s / cnt;
+      double var = ss / cnt - m * m;      // == (cum_pow - 2 mean cum_sum) / cnt + mean^2  (Step1_network.py:250)
+      if (var < 0.0) var = 0.0;
+      mean[((long long)b * T + t) * G + g] = (float)m;
+      rstd[((long long)b * T + t) * G + g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    cs = __shfl_sync(0xffffffffu, s, 31);
+    css = __shfl_sync(0xffffffffu, ss, 31);
+  }
+}
+
+// ---- pass 2 -----------------------------------------------------------------------------------------------------
+struct NormParams {
+  const float* x;
+  int B;
+  long long rows;
+  int Cin, C, pre;
+  const float* pre_slope;
+  const float *mean, *rstd;
+  int stat_mode, rows_per_t, stat_groups;
+  const float *gamma, *beta;
+  int post;
+  const float* post_slope;
+  const float* fir_w;
+  int fir_k, fir_groups;
+  float *out, *out_hi, *out_lo;
+};
+
+__global__ void __launch_bounds__(NT) chan_norm_kernel(const NormParams p) {
+  const long long n = (long long)p.B * p.rows * p.C;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const int c = (int)(i % p.C);
+    const long long br = i / p.C;
+    const int b = (int)(br / p.rows);
+    const long long r = br - (long long)b * p.rows;
+    const float g = __ldg(p.gamma + c), be = __ldg(p.beta + c);
+    float y;
+    if (p.post != SE_NORM_POST_FIR) {
+      const long long si = p.stat_mode == SE_NORM_STAT_INSTANCE
+                               ? (long long)b * p.C + c
+                               : ((long long)b * (p.rows / p.rows_per_t) + r / p.rows_per_t) * p.stat_groups +
+                                     c / (p.C / p.stat_groups);
+      const float v = pre_value(p.x + br * p.Cin, c, p.Cin, p.C, p.pre, p.pre_slope);
+      y = (v - __ldg(p.mean + si)) * __ldg(p.rstd + si) * g + be;
+      if (p.post == SE_NORM_POST_PRELU) y = prelu_f(y, __ldg(p.post_slope + c));
+    } else {
+      // ShareSepConv on the normalised signal: y[t] = sum_k w[k] z[t - (K-1) + k], z = 0 before the clip starts
+      const float* w = p.fir_w + (long long)(c / (p.C / p.fir_groups)) * p.fir_k;
+      float acc = 0.f;
+      for (int k = 0; k < p.fir_k; ++k) {
+        const long long rr = r - (p.fir_k - 1) + k;
+        if (rr < 0) continue;
+        const long long si = p.stat_mode == SE_NORM_STAT_INSTANCE
+                                 ? (long long)b * p.C + c
+                                 : ((long long)b * p.rows + rr) * p.stat_groups + c / (p.C / p.stat_groups);
+        const float v = pre_value(p.x + ((long long)b * p.rows + rr) * p.Cin, c, p.Cin, p.C, p.pre, p.pre_slope);
+        const float z = (v - __ldg(p.mean + si)) * __ldg(p.rstd + si) * g + be;
+        acc = fmaf(__ldg(w + k), z, acc);
+      }
+      y = acc;
+    }
+    if (p.out) p.out[i] = y;
+    if (p.out_hi) split_tf32_dev(y, p.out_hi[i], p.out_lo[i]);
+  }
+}
+
+// ---- small elementwise helpers -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) add_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                                float* __restrict__ out, float* __restrict__ out_hi,
+                                                float* __restrict__ out_lo) {
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const float y = __ldg(a + i) + __ldg(b + i);
+    if (out) out[i] = y;
+    if (out_hi) split_tf32_dev(y, out_hi[i], out_lo[i]);
+  }
+}
+
+// CTSNet stage glue (CTSNet/two_stage_com_decode_vb.py:79-84).
+//   stage 1 -> 2: s1 = est_mag * (cos, sin)(phase of the noisy spectrum); s2_in = cat(noisy RI, s1 RI) [.., 4]
+__global__ void __launch_bounds__(NT) cts_glue1_kernel(const float2* __restrict__ x, const float* __restrict__ est,
+                                                      long long n, float4* __restrict__ s2in) {
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const float2 v = __ldg(x + i);
+    const float ph = atan2f(v.y, v.x);      // :74 phase_x (0 for a zero bin, as torch.atan2)
+    float s, c;
+    sincosf(ph, &s, &c);
+    const float e = __ldg(est + i);
+    s2in[i] = make_float4(v.x, v.y, e * c, e * s);
+  }
+}
+//   stage 2 output: model2(s2_in) + s1  (:84), interleaved (re, im) for the iSTFT prologue
+__global__ void __launch_bounds__(NT) cts_glue2_kernel(const float* __restrict__ out_r, const float* __restrict__ out_i,
+                                                      const float4* __restrict__ s2in, long long n,
+                                                      float2* __restrict__ est) {
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const float4 s = __ldg(s2in + i);
+    est[i] = make_float2(__ldg(out_r + i) + s.z, __ldg(out_i + i) + s.w);
+  }
+}
+
+static int grid_for(long long n) {
+  long long g = (n + NT - 1) / NT;
+  return (int)(g < 148 * 16 ? (g < 1 ? 1 : g) : 148 * 16);
+}
+
+}  // namespace se
+
+using namespace se;
+
+static bool norm_c_ok(int C) { return C >= 1 && C <= NT && NT % C == 0; }
+
+extern "C" long long se_chan_stats_ws_bytes(int B, long long rows, int C) {
+  (void)rows;
+  // upper bound on chunks: 1184 / B + 1
+  const long long chunks = 148 * 8 / (B > 0 ? B : 1) + 1;
+  return (long long)B * chunks * C * 2 * 8 + (long long)B * 4 + 64;
+}
+
+extern "C" int se_chan_stats(const float* x, int B, long long rows, int Cin, int C, int pre, const float* pre_slope,
+                             float eps, float* mean, float* rstd, void* ws, se_stream_t stream) {
+  SE_REQUIRE(x && mean && rstd && ws && B > 0 && rows > 0, "se_chan_stats: bad arguments");
+  SE_REQUIRE(norm_c_ok(C), "se_chan_stats: C=%d must divide %d", C, NT);
+  SE_REQUIRE(pre >= SE_NORM_PRE_NONE && pre <= SE_NORM_PRE_GLU_PRELU, "se_chan_stats: pre=%d", pre);
+  SE_REQUIRE((pre == SE_NORM_PRE_GLU || pre == SE_NORM_PRE_GLU_PRELU) ? Cin == 2 * C
+                                                                      : (Cin >= 1 && C % Cin == 0 && (pre != SE_NORM_PRE_NONE || Cin == C)),
+             "se_chan_stats: Cin=%d C=%d pre=%d", Cin, C, pre);
+  SE_REQUIRE(!(pre == SE_NORM_PRE_PRELU || pre == SE_NORM_PRE_GLU_PRELU) || pre_slope, "se_chan_stats: slopes missing");
+  const int lanes = NT / C;
+  long long chunks = 148 * 8 / B;
+  const long long maxc = (rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+  if (chunks > maxc) chunks = maxc;
+  if (chunks < 1) chunks = 1;
+  double* partial = reinterpret_cast<double*>(ws);
+  unsigned* ticket = reinterpret_cast<unsigned*>(partial + (long long)B * (148 * 8 / B + 1) * C * 2);
+  chan_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), NT, 0, (cudaStream_t)stream>>>(
+      x, rows, Cin, C, pre, pre_slope, eps, mean, rstd, partial, ticket);
+  return check_launch("se_chan_stats");
+}
+
+extern "C" int se_cum_stats(const float* x, int B, int T, int F, int Cin, int C, int groups, int pre,
+                            const float* pre_slope, float eps, float* mean, float* rstd, void* ws, se_stream_t stream) {
+  SE_REQUIRE(x && mean && rstd && ws && B > 0 && T > 0 && F > 0 && C > 0, "se_cum_stats: bad arguments");
+  SE_REQUIRE(groups >= 1 && C % groups == 0, "se_cum_stats: groups=%d C=%d", groups, C);
+  SE_REQUIRE(pre >= SE_NORM_PRE_NONE && pre <= SE_NORM_PRE_GLU_PRELU, "se_cum_stats: pre=%d", pre);
+  SE_REQUIRE((pre == SE_NORM_PRE_GLU || pre == SE_NORM_PRE_GLU_PRELU) ? Cin == 2 * C
+                                                                      : (Cin >= 1 && C % Cin == 0 && (pre != SE_NORM_PRE_NONE || Cin == C)),
+             "se_cum_stats: Cin=%d C=%d pre=%d", Cin, C, pre);
+  SE_REQUIRE(!(pre == SE_NORM_PRE_PRELU || pre == SE_NORM_PRE_GLU_PRELU) || pre_slope, "se_cum_stats: slopes missing");
+  double* step = reinterpret_cast<double*>(ws);        // [B*T][G][2]
+  cum_step_kernel<<<dim3((unsigned)((long long)B * T), (unsigned)groups), NT, 0, (cudaStream_t)stream>>>(
+      x, F, Cin, C, groups, pre, pre_slope, step);
+  int rc = check_launch("se_cum_stats (step sums)");
+  if (rc) return rc;
+  cum_scan_kernel<<<dim3((unsigned)B, (unsigned)groups), 32, 0, (cudaStream_t)stream>>>(step, T, groups, F * (C / groups),
+                                                                                          eps, mean, rstd);
+  return check_launch("se_cum_stats (scan)");
+}
+
+extern "C" int se_chan_norm(const float* x, int B, long long rows, int Cin, int C, int pre, const float* pre_slope,
+                            const float* mean, const float* rstd, int stat_mode, int rows_per_t, int stat_groups,
+                            const float* gamma, const float* beta, int post, const float* post_slope, const float* fir_w, int fir_k,
+                            int fir_groups, float* out, float* out_hi, float* out_lo, se_stream_t stream) {
+  SE_REQUIRE(x && mean && rstd && gamma && beta && (out || out_hi) && B > 0 && rows > 0 && C > 0,
+             "se_chan_norm: bad arguments");
+  SE_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "se_chan_norm: out_hi/out_lo go together");
+  SE_REQUIRE(pre >= SE_NORM_PRE_NONE && pre <= SE_NORM_PRE_GLU_PRELU, "se_chan_norm: pre=%d", pre);
+  SE_REQUIRE((pre == SE_NORM_PRE_GLU || pre == SE_NORM_PRE_GLU_PRELU) ? Cin == 2 * C
+                                                                      : (Cin >= 1 && C % Cin == 0 && (pre != SE_NORM_PRE_NONE || Cin == C)),
+             "se_chan_norm: Cin=%d C=%d pre=%d", Cin, C, pre);
+  SE_REQUIRE(!(pre == SE_NORM_PRE_PRELU || pre == SE_NORM_PRE_GLU_PRELU) || pre_slope, "se_chan_norm: slopes missing");
+  SE_REQUIRE(stat_mode == SE_NORM_STAT_INSTANCE || (stat_mode == SE_NORM_STAT_CUMULATIVE && rows_per_t >= 1 &&
+                                                     rows % rows_per_t == 0 && stat_groups >= 1 && C % stat_groups == 0),
+             "se_chan_norm: stat_mode=%d rows_per_t=%d stat_groups=%d", stat_mode, rows_per_t, stat_groups);
+  SE_REQUIRE(post >= SE_NORM_POST_NONE && post <= SE_NORM_POST_FIR, "se_chan_norm: post=%d", post);
+  SE_REQUIRE(post != SE_NORM_POST_PRELU || post_slope, "se_chan_norm: post slopes missing");
+  SE_REQUIRE(post != SE_NORM_POST_FIR || (fir_w && fir_k >= 1 && fir_groups >= 1 && C % fir_groups == 0 &&
+                                          (stat_mode == SE_NORM_STAT_INSTANCE || rows_per_t == 1)),
+             "se_chan_norm: FIR arguments");
+  NormParams p{x, B, rows, Cin, C, pre, pre_slope, mean, rstd, stat_mode, rows_per_t, stat_groups, gamma, beta, post, post_slope,
+               fir_w, fir_k, fir_groups, out, out_hi, out_lo};
+  chan_norm_kernel<<<grid_for((long long)B * rows * C), NT, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("se_chan_norm");
+}
+
+extern "C" int se_add(const float* a, const float* b, long long n, float* out, float* out_hi, float* out_lo,
+                      se_stream_t stream) {
+  SE_REQUIRE(a && b && n > 0 && (out || out_hi), "se_add: bad arguments");
+  SE_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "se_add: out_hi/out_lo go together");
+  add_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(a, b, n, out, out_hi, out_lo);
+  return check_launch("se_add");
+}
+
+extern "C" int se_cts_glue1(const float* x_ri, const float* est_mag, long long n, float* s2_in, se_stream_t stream) {
+  SE_REQUIRE(x_ri && est_mag && s2_in && n > 0, "se_cts_glue1: bad arguments");
+  SE_REQUIRE(((((uintptr_t)x_ri) & 7) | (((uintptr_t)s2_in) & 15)) == 0, "se_cts_glue1: unaligned");
+  cts_glue1_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(x_ri), est_mag, n,
+                                                                 reinterpret_cast<float4*>(s2_in));
+  return check_launch("se_cts_glue1");
+}
+
+extern "C" int se_cts_glue2(const float* out_r, const float* out_i, const float* s2_in, long long n, float* est,
+                            se_stream_t stream) {
+  SE_REQUIRE(out_r && out_i && s2_in && est && n > 0, "se_cts_glue2: bad arguments");
+  SE_REQUIRE(((((uintptr_t)est) & 7) | (((uintptr_t)s2_in) & 15)) == 0, "se_cts_glue2: unaligned");
+  cts_glue2_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(out_r, out_i, reinterpret_cast<const float4*>(s2_in), n,
+                                                                 reinterpret_cast<float2*>(est));
+  return check_launch("se_cts_glue2");
+}

@@ -133,6 +133,43 @@ def enhance_dccrn(model, wav, p=0.5, taps=None):
 
 
 @torch.no_grad()
+def enhance_ctsnet(models, wav, p=1.0, taps=None):
+    """CTSNet/two_stage_com_decode_vb.py:61-95 (p = 1.0; 0.5 for the cprs checkpoints): ``models`` =
+    (Step1_net, Step2_net).  Zero-pad to whole hops, STFT (compressed RI + magnitude), stage 1 on the magnitude,
+    its estimate with the noisy phase, stage 2 on cat(noisy RI, stage-1 RI) + stage-1 RI, decompress (rule (ii)),
+    iSTFT without ``length`` then ``[:wav_len]``, / c.  wav [B,N] float32 CUDA -> [B,N]."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    model1, model2 = models
+    n_fft, win, hop = GEOM_320
+    wav = wav.contiguous().float()
+    b, n = wav.shape
+    c, inv_c = ops.rms_scale(wav)
+    frames = -(-n // hop) + 1                       # ceil(N/hop) + 1   (:65)
+    fake = (frames - 1) * hop
+    if fake != n:
+        padded = torch.zeros(b, fake, device=wav.device, dtype=torch.float32)
+        padded[:, :n] = wav
+        wav_in = padded
+    else:
+        wav_in = wav
+    t, f = 1 + fake // hop, n_fft // 2 + 1
+    x = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)        # compressed RI, channels-last
+    mag = torch.empty(b, t, f, device=wav.device, dtype=torch.float32)
+    ops.stft(wav_in, c, n_fft, win, hop, mag=mag, re=x[..., 0], im=x[..., 1], p_mag=p, p_ri=p)
+    est1 = model1(mag)                                                         # :79
+    s2_in = ops.cts_glue1(x, est1)                                             # :80-82
+    out_r, out_i = model2.forward_nhwc(s2_in)                                  # :83
+    est = ops.cts_glue2(out_r, out_i, s2_in)                                   # :84
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_RI_DECOMP, est[..., 0], est[..., 1], None, None, n_fft, win, hop, out, n, out_scale=inv_c,
+              inv_p=1.0 / p)
+    if taps is not None:
+        taps.update(c=c, x=x, est1=est1, est=est)
+    return out
+
+
+@torch.no_grad()
 def enhance_fullsubnet(model, wav, p=0.5, taps=None):
     """FullSubNet/fullsubnet_sa_decode.py:44-78: |X|^p magnitude in, complex mask out, mask applied
     to the COMPRESSED spectrum, decompressed, iSTFT(length=N), / c  (backend rule (iii)).

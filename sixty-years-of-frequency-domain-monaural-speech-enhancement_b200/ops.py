@@ -552,3 +552,104 @@ def unary(x, act, act_param=0.0, want_f32=True, want_pair=False):
                                    _ptr(pair[0] if pair else None), _ptr(pair[1] if pair else None), _stream()),
               "se_unary")
     return out, pair
+
+
+# ---- utterance-level norms of the TCM family (csrc/norm.cu) ------------------------------------------
+_norm_ws = {}    # device -> zero-initialised workspace (se_chan_stats leaves it zeroed)
+
+
+def _stats_ws(device, nbytes):
+    ws = _norm_ws.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, device=device, dtype=torch.uint8)
+        _norm_ws[device] = ws
+    return ws
+
+
+def chan_stats(x, B, rows, C, pre="none", pre_slope=None, eps=1e-5):
+    """InstanceNorm statistics of pre(x) per (clip, channel).  x [B, rows, Cin] -> (mean [B,C], rstd [B,C])."""
+    _need_cuda(x, pre_slope)
+    device_check()
+    assert x.is_contiguous() and x.numel() % (B * rows) == 0
+    cin = x.numel() // (B * rows)
+    lib = _lib.load()
+    ws = _stats_ws(x.device, int(lib.se_chan_stats_ws_bytes(B, rows, C)))
+    mean = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    with _Timed(f"chan_stats[C={C}]"):
+        check(lib.se_chan_stats(_ptr(x), B, rows, cin, C, _lib.NORM_PRE[pre], _ptr(pre_slope), float(eps), _ptr(mean),
+                                _ptr(rstd), _ptr(ws), _stream()), "se_chan_stats")
+    return mean, rstd
+
+
+def cum_stats(x, B, T, F, C, pre="none", pre_slope=None, eps=1e-5, groups=1):
+    """Cumulative-LayerNorm statistics of pre(x): x [B, T, F, Cin] -> (mean [B,T,G], rstd [B,T,G])."""
+    _need_cuda(x, pre_slope)
+    device_check()
+    assert x.is_contiguous() and x.numel() % (B * T * F) == 0
+    cin = x.numel() // (B * T * F)
+    ws = torch.empty(2 * B * T * groups, device=x.device, dtype=torch.float64)
+    mean = torch.empty(B, T, groups, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    with _Timed(f"cum_stats[C={C}]"):
+        check(_lib.load().se_cum_stats(_ptr(x), B, T, F, cin, C, groups, _lib.NORM_PRE[pre], _ptr(pre_slope), float(eps),
+                                       _ptr(mean), _ptr(rstd), C.c_void_p(ws.data_ptr()), _stream()), "se_cum_stats")
+    return mean, rstd
+
+
+def chan_norm(x, B, rows, C, mean, rstd, gamma, beta, pre="none", pre_slope=None, cumulative=False, rows_per_t=1,
+              post="none", post_slope=None, fir_w=None, fir_groups=1, want_f32=True, want_pair=False, stat_groups=1):
+    """post((pre(x) - mean) * rstd * gamma + beta); x [B, rows, Cin] -> [B, rows, C] fp32 and/or TF32 pair."""
+    _need_cuda(x, pre_slope, mean, rstd, gamma, beta, post_slope, fir_w)
+    device_check()
+    assert x.is_contiguous() and x.numel() % (B * rows) == 0
+    cin = x.numel() // (B * rows)
+    mk = lambda: torch.empty(B, rows, C, device=x.device, dtype=torch.float32)   # noqa: E731
+    out = mk() if want_f32 else None
+    pair = (mk(), mk()) if want_pair else None
+    fir_k = 0
+    if fir_w is not None:
+        assert fir_w.is_contiguous() and fir_w.dim() == 2 and fir_w.shape[0] == fir_groups
+        fir_k = fir_w.shape[1]
+    with _Timed(f"chan_norm[C={C},{post}]"):
+        check(_lib.load().se_chan_norm(_ptr(x), B, rows, cin, C, _lib.NORM_PRE[pre], _ptr(pre_slope), _ptr(mean),
+                                       _ptr(rstd), 1 if cumulative else 0, rows_per_t, stat_groups, _ptr(gamma), _ptr(beta),
+                                       _lib.NORM_POST[post], _ptr(post_slope), _ptr(fir_w), fir_k, fir_groups,
+                                       _ptr(out), _ptr(pair[0] if pair else None), _ptr(pair[1] if pair else None),
+                                       _stream()), "se_chan_norm")
+    return out, pair
+
+
+def add(a, b, want_f32=True, want_pair=False):
+    _need_cuda(a, b)
+    device_check()
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a) if want_f32 else None
+    pair = (torch.empty_like(a), torch.empty_like(a)) if want_pair else None
+    with _Timed("add"):
+        check(_lib.load().se_add(_ptr(a), _ptr(b), a.numel(), _ptr(out), _ptr(pair[0] if pair else None),
+                                 _ptr(pair[1] if pair else None), _stream()), "se_add")
+    return out, pair
+
+
+def cts_glue1(x_ri, est_mag):
+    """x_ri [B,T,F,2] noisy (compressed) RI, est_mag [B,T,F] -> s2_in [B,T,F,4] (two_stage_com_decode_vb.py:79-82)."""
+    _need_cuda(x_ri, est_mag)
+    device_check()
+    assert x_ri.is_contiguous() and est_mag.is_contiguous() and x_ri.shape[:-1] == est_mag.shape
+    out = torch.empty(*est_mag.shape, 4, device=x_ri.device, dtype=torch.float32)
+    with _Timed("cts_glue1"):
+        check(_lib.load().se_cts_glue1(_ptr(x_ri), _ptr(est_mag), est_mag.numel(), _ptr(out), _stream()), "se_cts_glue1")
+    return out
+
+
+def cts_glue2(out_r, out_i, s2_in):
+    """stage-2 output + stage-1 RI (two_stage_com_decode_vb.py:84) -> est [B,T,F,2]."""
+    _need_cuda(out_r, out_i, s2_in)
+    device_check()
+    assert out_r.is_contiguous() and out_i.is_contiguous() and s2_in.is_contiguous()
+    est = torch.empty(*out_r.shape, 2, device=out_r.device, dtype=torch.float32)
+    with _Timed("cts_glue2"):
+        check(_lib.load().se_cts_glue2(_ptr(out_r), _ptr(out_i), _ptr(s2_in), out_r.numel(), _ptr(est), _stream()),
+              "se_cts_glue2")
+    return est

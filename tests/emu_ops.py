@@ -317,3 +317,79 @@ def install(ops_module, monkeypatch):   # noqa: F811
     _orig_install(ops_module, monkeypatch)
     for name in _UF_NAMES:
         monkeypatch.setattr(ops_module, name, globals()[name])
+
+
+# ---- TCM-family norm mirrors (csrc/norm.cu) ---------------------------------------------------------------
+def _norm_pre(x, B, rows, C, pre, pre_slope):
+    x = x.reshape(B, rows, -1)
+    cin = x.shape[-1]
+    if pre in ("glu", "glu_prelu"):
+        v = x[..., :C] * torch.sigmoid(x[..., C:])
+    elif pre == "prelu":
+        v = x.repeat(1, 1, C // cin)
+    else:
+        v = x
+    if pre in ("prelu", "glu_prelu"):
+        v = torch.where(v >= 0, v, pre_slope * v)
+    return v
+
+
+def chan_stats(x, B, rows, C, pre="none", pre_slope=None, eps=1e-5):
+    v = _norm_pre(x, B, rows, C, pre, pre_slope).double()
+    m = v.mean(1)
+    var = (v * v).mean(1) - m * m
+    return m.float(), (1.0 / torch.sqrt(var.clamp_min(0) + eps)).float()
+
+
+def cum_stats(x, B, T, F, C, pre="none", pre_slope=None, eps=1e-5, groups=1):
+    v = _norm_pre(x, B, T * F, C, pre, pre_slope).double().reshape(B, T, F, groups, C // groups)
+    cs, css = torch.cumsum(v.sum((2, 4)), 1), torch.cumsum((v * v).sum((2, 4)), 1)          # [B,T,G]
+    cnt = (torch.arange(1, T + 1, dtype=torch.float64) * (F * C // groups))[None, :, None]
+    m = cs / cnt
+    var = css / cnt - m * m
+    return m.float(), (1.0 / torch.sqrt(var.clamp_min(0) + eps)).float()
+
+
+def chan_norm(x, B, rows, C, mean, rstd, gamma, beta, pre="none", pre_slope=None, cumulative=False, rows_per_t=1,
+              post="none", post_slope=None, fir_w=None, fir_groups=1, want_f32=True, want_pair=False, stat_groups=1):
+    from se_b200 import packing
+    v = _norm_pre(x, B, rows, C, pre, pre_slope)
+    if cumulative:
+        m = mean.repeat_interleave(rows_per_t, dim=1).repeat_interleave(C // stat_groups, dim=2)
+        r = rstd.repeat_interleave(rows_per_t, dim=1).repeat_interleave(C // stat_groups, dim=2)
+    else:
+        m, r = mean[:, None, :], rstd[:, None, :]
+    y = (v - m) * r * gamma + beta
+    if post == "prelu":
+        y = torch.where(y >= 0, y, post_slope * y)
+    elif post == "fir":
+        k = fir_w.shape[1]
+        w = fir_w.repeat_interleave(C // fir_groups, dim=0)          # [C, K]
+        yp = F.pad(y.transpose(1, 2), (k - 1, 0))                    # [B, C, rows + K - 1]
+        y = F.conv1d(yp, w[:, None, :], None, groups=C).transpose(1, 2).contiguous()
+    return (y if want_f32 else None), (packing.split_tf32(y.contiguous()) if want_pair else None)
+
+
+def add(a, b, want_f32=True, want_pair=False):
+    from se_b200 import packing
+    y = a + b
+    return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
+
+
+def cts_glue1(x_ri, est_mag):
+    ph = torch.atan2(x_ri[..., 1], x_ri[..., 0])
+    return torch.stack([x_ri[..., 0], x_ri[..., 1], est_mag * torch.cos(ph), est_mag * torch.sin(ph)], -1)
+
+
+def cts_glue2(out_r, out_i, s2_in):
+    return torch.stack([out_r + s2_in[..., 2], out_i + s2_in[..., 3]], -1)
+
+
+_NORM_NAMES = ("chan_stats", "cum_stats", "chan_norm", "add", "cts_glue1", "cts_glue2")
+_orig_install2 = install
+
+
+def install(ops_module, monkeypatch):   # noqa: F811
+    _orig_install2(ops_module, monkeypatch)
+    for name in _NORM_NAMES:
+        monkeypatch.setattr(ops_module, name, globals()[name])

@@ -446,3 +446,88 @@ def test_lstm_seq_multi_shared_weights():
     ops.lstm_seq_multi(xp.to(dev), whh.to(dev), h, ng, out)
     ref = emu_ops.lstm_seq_multi(xp.double(), whh.double(), h, ng, torch.empty(b, t, ng * h, dtype=torch.float64))
     assert (out.cpu().double() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("b,rows,c,pre", [(3, 401 * 79, 64, "glu"), (2, 401, 128, "prelu"), (5, 161 * 50, 1, "glu"),
+                                          (2, 700, 64, "glu_prelu"), (1, 33, 64, "none")])
+def test_chan_stats_and_norm_instance(b, rows, c, pre):
+    """InstanceNorm statistics + normalise/PReLU pass vs the fp64 mirror."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(rows % 97)
+    cin = {"glu": 2 * c, "glu_prelu": 2 * c, "prelu": c // 2 if c > 1 else c, "none": c}[pre]
+    x = torch.randn(b, rows, cin, generator=g) * 2 + 0.3
+    slope = torch.rand(c, generator=g) * 0.5
+    gamma, beta, ps = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.2, torch.rand(c, generator=g)
+    m_ref, r_ref = emu_ops.chan_stats(x, b, rows, c, pre, slope)
+    y_ref, _ = emu_ops.chan_norm(x.double(), b, rows, c, m_ref.double(), r_ref.double(), gamma.double(), beta.double(),
+                                 pre=pre, pre_slope=slope.double(), post="prelu", post_slope=ps.double())
+    xd, sd_ = x.to(dev), slope.to(dev)
+    for rep in range(2):                      # the second call checks that the workspace ticket was left at zero
+        m, r = ops.chan_stats(xd, b, rows, c, pre, sd_)
+    y, pair = ops.chan_norm(xd, b, rows, c, m, r, gamma.to(dev), beta.to(dev), pre=pre, pre_slope=sd_, post="prelu",
+                            post_slope=ps.to(dev), want_f32=True, want_pair=True)
+    em, er = (m.cpu() - m_ref).abs().max().item(), ((r.cpu() - r_ref).abs() / r_ref).max().item()
+    ey = (y.cpu().double() - y_ref).abs().max().item()
+    ep = ((pair[0] + pair[1]).cpu().double() - y_ref).abs().max().item()
+    print(f"chan_stats/norm B={b} rows={rows} C={c} pre={pre}: mean err {em:.2e}, rstd rel err {er:.2e}, y err {ey:.2e}")
+    assert em < 1e-6 and er < 1e-6 and ey < 2e-5 and ep < 2e-5
+
+
+@pytest.mark.parametrize("k", [1, 3, 63])
+@pytest.mark.parametrize("cumulative", [False, True])
+def test_chan_norm_fir_and_cumulative(k, cumulative):
+    """TCM branch prologue: two PReLU/norm/ShareSepConv branches read one 64-channel tensor -> 128 channels."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    b, t, c = 3, 150, 128
+    g = torch.Generator().manual_seed(k)
+    x = torch.randn(b, t, 64, generator=g)
+    slope, gamma, beta = torch.rand(c, generator=g) * 0.5, torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    fir = torch.randn(2, k, generator=g) * 0.5
+    xd = x.to(dev)
+    if cumulative:
+        m_ref, r_ref = emu_ops.cum_stats(x, b, t, 1, c, "prelu", slope, groups=2)
+        m, r = ops.cum_stats(xd, b, t, 1, c, "prelu", slope.to(dev), groups=2)
+    else:
+        m_ref, r_ref = emu_ops.chan_stats(x, b, t, c, "prelu", slope)
+        m, r = ops.chan_stats(xd, b, t, c, "prelu", slope.to(dev))
+    kw = dict(pre="prelu", cumulative=cumulative, rows_per_t=1, stat_groups=2, post="fir", fir_groups=2)
+    y_ref, _ = emu_ops.chan_norm(x.double(), b, t, c, m_ref.double(), r_ref.double(), gamma.double(), beta.double(),
+                                 pre_slope=slope.double(), fir_w=fir.double(), **kw)
+    _, pair = ops.chan_norm(xd, b, t, c, m, r, gamma.to(dev), beta.to(dev), pre_slope=slope.to(dev), fir_w=fir.to(dev),
+                            want_f32=False, want_pair=True, **kw)
+    es = ((r.cpu() - r_ref).abs() / r_ref).max().item()
+    ey = ((pair[0] + pair[1]).cpu().double() - y_ref).abs().max().item()
+    print(f"chan_norm FIR k={k} cumulative={cumulative}: rstd rel err {es:.2e}, y err {ey:.2e} (|y| max {y_ref.abs().max():.2f})")
+    assert es < 1e-5 and ey < 1e-5 * max(1.0, y_ref.abs().max().item())
+
+
+def test_cum_stats_2d_and_cts_glue():
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(11)
+    b, t, f, c = 2, 60, 19, 64
+    x = torch.randn(b, t, f, 2 * c, generator=g)
+    m_ref, r_ref = emu_ops.cum_stats(x, b, t, f, c, "glu")
+    m, r = ops.cum_stats(x.to(dev), b, t, f, c, "glu")
+    gamma, beta, ps = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1, torch.rand(c, generator=g)
+    y_ref, _ = emu_ops.chan_norm(x, b, t * f, c, m_ref, r_ref, gamma, beta, pre="glu", cumulative=True, rows_per_t=f,
+                                 post="prelu", post_slope=ps)
+    y, _ = ops.chan_norm(x.to(dev), b, t * f, c, m, r, gamma.to(dev), beta.to(dev), pre="glu", cumulative=True,
+                         rows_per_t=f, post="prelu", post_slope=ps.to(dev))
+    assert ((r.cpu() - r_ref).abs() / r_ref).max() < 1e-5 and (y.cpu() - y_ref).abs().max() < 2e-5
+    xr = torch.randn(b, t, 161, 2, generator=g)
+    xr[0, 0, 0] = 0.0                                          # atan2(0, 0) = 0 -> (cos, sin) = (1, 0)
+    e = torch.rand(b, t, 161, generator=g)
+    s2 = ops.cts_glue1(xr.to(dev), e.to(dev))
+    assert (s2.cpu() - emu_ops.cts_glue1(xr, e)).abs().max() < 1e-6
+    o_r, o_i = torch.randn(b, t, 161, generator=g), torch.randn(b, t, 161, generator=g)
+    est = ops.cts_glue2(o_r.to(dev), o_i.to(dev), s2)
+    assert (est.cpu() - emu_ops.cts_glue2(o_r, o_i, s2.cpu())).abs().max() < 1e-6
+    a, bb = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    s, pr = ops.add(a.to(dev), bb.to(dev), want_pair=True)
+    assert torch.equal(s.cpu(), a + bb) and torch.equal((pr[0] + pr[1]).cpu(), a + bb)

@@ -316,3 +316,42 @@ def test_uformer_matches_golden(name, ckpt):
     print(msg)
     assert rms.max() <= RMS_GATE and rel.max() <= 2e-3
     assert binv < 1e-5
+
+
+@pytest.mark.parametrize("name", ["ctsnet_synth", "ctsnet_ckpt", "ctsnet_new_synth", "ctsnet_new_ckpt"])
+def test_ctsnet_matches_golden(name):
+    """two-stage CTSNet (InstanceNorm) / CTSNet_new (cumulative LayerNorm) vs the UNMODIFIED
+    Step1_net / Step2_net modules run through the glue of two_stage_com_decode_vb.py, and the decoded waveform."""
+    dev = _dev()
+    import se_b200
+    from test_oracle_nets import load_cts_case
+    g, sds, p, cum = load_cts_case(name)
+    m1 = se_b200.ctsnet.Step1_net(cumulative=cum)
+    m2 = se_b200.ctsnet.Step2_net(X=6, R=3, cumulative=cum)
+    m1.load_state_dict(sds[0])
+    m2.load_state_dict(sds[1])
+    m1.eval().cuda()
+    m2.eval().cuda()
+    k = len(g["clip_ids"])
+    feat = torch.from_numpy(np.stack([g[f"feat{j}"] for j in range(k)])).to(dev)        # [B,2,T,161] compressed RI
+    est1 = m1(torch.norm(feat, dim=1)).cpu().numpy()
+    ref1 = np.stack([g[f"est1{j}"] for j in range(k)])
+    e1 = np.abs(est1 - ref1).max()
+    wav = torch.from_numpy(np.stack([g[f"wav{j}"] for j in range(k)])).to(dev)
+    taps = {}
+    y = se_b200.decode.enhance_ctsnet((m1, m2), wav, p=p, taps=taps)
+    est = taps["est"].permute(0, 3, 1, 2).cpu().numpy()
+    ref = np.stack([g[f"est{j}"] for j in range(k)])
+    e_net = np.abs(est - ref).max()
+    c = taps["c"].cpu().numpy()
+    yn = y.cpu().numpy() * c[:, None]
+    refn = np.stack([g[f"ynorm{j}"] for j in range(k)])
+    rms = np.sqrt(np.mean((yn - refn) ** 2, axis=1))
+    rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
+    y1 = se_b200.decode.enhance_ctsnet((m1, m2), wav[1:2], p=p)
+    binv = (y[1:2] - y1).abs().max().item()
+    print(f"{name}: stage-1 max-abs {e1:.3e} (|est1| max {np.abs(ref1).max():.2f}); net max-abs {e_net:.3e} "
+          f"(|est| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} rel {rel.max():.3e}; "
+          f"batch-vs-single {binv:.2e}")
+    assert (rms.max() <= RMS_GATE or rel.max() <= 1e-5) and rel.max() <= 2e-3
+    assert binv < 1e-5 * max(1.0, float(np.abs(refn).max()))

@@ -226,3 +226,32 @@ def test_uformer_host_logic_matches_reference_fixture(monkeypatch):
     est = m._network(x).permute(0, 3, 2, 1)[0]
     ref = torch.from_numpy(g["est0"])
     assert (est - ref).abs().max() < 5e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cum", [False, True])
+def test_ctsnet_host_logic_matches_oracle(monkeypatch, cum):
+    """CTSNet / CTSNet_new: gated convs as [a | b] GEMMs, k(2,5) / k(2,3) transposed-conv parity classes with the
+    chomp folded into the taps, the two TCM branches as one 128-channel tensor + block-diagonal dilated conv,
+    (c,f) <-> (f,c) flatten permutations, InstanceNorm vs cumulative LayerNorm statistics (per branch)."""
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t1, t2 = templates.ctsnet_step1_template(cum), templates.ctsnet_step2_template(cumulative=cum)
+    sd1 = synth.synthetic_state_dict(t1, seed=8, gain=1.0)
+    sd2 = synth.synthetic_state_dict(t2, seed=9, gain=1.0)
+    m1, m2 = se_b200.ctsnet.Step1_net(cumulative=cum), se_b200.ctsnet.Step2_net(X=6, R=3, cumulative=cum)
+    assert list(m1.state_dict().keys()) == list(t1.keys()) and list(m2.state_dict().keys()) == list(t2.keys())
+    m1.load_state_dict(sd1)
+    m2.load_state_dict(sd2)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 37, 161, generator=g) * 2
+    taps, rtaps = {}, {}
+    est = m1._forward_impl(x, taps)
+    with torch.no_grad():
+        ref = nets.ctsnet_step1_forward(sd1, x, cum, rtaps)
+    for k in ("e1", "e5"):
+        assert (taps[k].permute(0, 3, 1, 2) - rtaps[k]).abs().max() < 1e-5 * max(1.0, rtaps[k].abs().max().item()), k
+    assert (taps["tcm"].permute(0, 3, 2, 1).reshape(2, 256, 37) - rtaps["tcm"]).abs().max() < 5e-5
+    assert (est - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
+    z = torch.randn(2, 4, 37, 161, generator=g)
+    with torch.no_grad():
+        ref2 = nets.ctsnet_step2_forward(sd2, z, cumulative=cum)
+    assert (m2._forward_impl(z) - ref2).abs().max() < 2e-5 * max(1.0, ref2.abs().max().item())

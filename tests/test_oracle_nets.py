@@ -82,3 +82,54 @@ def test_oracle_equals_reference_module(mdir, module, cls, tmpl, fwd):
     x = torch.rand(2, 23, 161, generator=torch.Generator().manual_seed(5)) * 4
     with torch.no_grad():
         assert (net(x) - fwd(sd, x)).abs().max() < 1e-6   # same ATen ops; threading may reassociate
+
+
+CTS_CKPTS = {"ctsnet_ckpt": ("CTSNet__step1_vb_cts_noncprs_model_final.pth", "CTSNet__step2_vb_cts_noncprs_model.pth"),
+             "ctsnet_new_ckpt": ("CTSNet_new__step1_vb_cts_cprs_model_final.pth", "CTSNet_new__step2_vb_cts_cprs_model.pth")}
+
+
+def load_cts_case(name):
+    """(fixture, (sd1, sd2), p, cumulative) of a CTSNet fixture; skips when the checkpoint copy is absent."""
+    from oracle.make_golden import cts_state_dicts
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cum = "_new" in name
+    if name in CTS_CKPTS:
+        paths = [os.path.join(CKPT_DIR, f) for f in CTS_CKPTS[name]]
+        if not all(os.path.exists(p) for p in paths):
+            pytest.skip("checkpoint copy not present (oracle/fetch_checkpoints.py)")
+        sds = tuple(torch.load(p, map_location="cpu") for p in paths)
+    else:
+        sds = cts_state_dicts(None, None, None, cum)
+    return g, sds, float(g["p"]), cum
+
+
+@pytest.mark.parametrize("name", ["ctsnet_synth", "ctsnet_ckpt", "ctsnet_new_synth", "ctsnet_new_ckpt"])
+def test_ctsnet_oracle_reproduces_golden(name):
+    """Two-stage CTSNet (InstanceNorm) and CTSNet_new (cumulative LayerNorm): the restated decode loop reproduces
+    the fixtures whose network outputs came from the UNMODIFIED Step1_net / Step2_net modules."""
+    g, sds, p, cum = load_cts_case(name)
+    assert sd_digest(sds[0]) + sd_digest(sds[1]) == str(g["digest"])
+    assert float(g["ref_vs_oracle"]) < 1e-4
+    for j in range(len(g["clip_ids"])):
+        wav = synth.noisy_clip(int(g["clip_ids"][j]), int(g["nsamp"]))
+        assert np.array_equal(wav, g[f"wav{j}"])
+        y, taps = decode.enhance_ctsnet(sds, wav.astype(np.float64), p=p, cumulative=cum)
+        assert np.abs(taps["est"] - g[f"est{j}"]).max() < 1e-4 * max(1.0, np.abs(g[f"est{j}"]).max())
+        assert np.sqrt(np.mean((taps["y_norm"] - g[f"ynorm{j}"]) ** 2)) < 2e-6
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("mdir,cum", [("CTSNet", False), ("CTSNet_new", True)])
+def test_ctsnet_oracle_equals_reference_modules(mdir, cum):
+    m1 = ref_shims.import_reference(mdir, "Step1_network").Step1_net().eval()
+    m2 = ref_shims.import_reference(mdir, "Step2_network").Step2_net(X=6, R=3).eval()
+    sd1 = synth.synthetic_state_dict(templates.ctsnet_step1_template(cum), seed=4, gain=1.0)
+    sd2 = synth.synthetic_state_dict(templates.ctsnet_step2_template(cumulative=cum), seed=5, gain=1.0)
+    m1.load_state_dict(sd1)
+    m2.load_state_dict(sd2)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(2, 21, 161, generator=g) * 3
+    z = torch.randn(2, 4, 21, 161, generator=g)
+    with torch.no_grad():
+        assert (m1(x) - nets.ctsnet_step1_forward(sd1, x, cum)).abs().max() < 1e-5
+        assert (m2(z) - nets.ctsnet_step2_forward(sd2, z, cumulative=cum)).abs().max() < 1e-5

@@ -32,6 +32,9 @@ CASES = {
              64, 4, 160, dict(p=0.5)),
     "dpcrn": (lambda: se_b200.dpcrn(), templates.dpcrn_template, se_b200.decode.enhance_dpcrn, odecode.enhance_dpcrn,
               64, 4, 160, dict(p=1.0)),
+    "ctsnet": (lambda: (se_b200.ctsnet.Step1_net(), se_b200.ctsnet.Step2_net(X=6, R=3)),
+               lambda: (templates.ctsnet_step1_template(), templates.ctsnet_step2_template()),
+               se_b200.decode.enhance_ctsnet, odecode.enhance_ctsnet, 64, 4, 160, dict(p=1.0)),
     "uformer": (lambda: se_b200.Uformer(), templates.uformer_template, se_b200.decode.enhance_uformer, None,
                 64, 4, 160, dict()),
 }
@@ -43,10 +46,17 @@ def main():
     dev = torch.device("cuda")
     for name in which:
         ctor, tmpl, genh, oenh, bsz, secs, hop, kw = CASES[name]
-        sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name in ("uformer", "dpcrn") else 2.0)
-        model = ctor()
-        model.load_state_dict(sd)
-        model.eval().cuda()
+        if name == "ctsnet":                      # two stages: tuples of templates / state-dicts / modules
+            sd = tuple(synth.synthetic_state_dict(t, seed=i, gain=1.0) for i, t in enumerate(tmpl()))
+            model = ctor()
+            for m, s in zip(model, sd):
+                m.load_state_dict(s)
+                m.eval().cuda()
+        else:
+            sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name in ("uformer", "dpcrn") else 2.0)
+            model = ctor()
+            model.load_state_dict(sd)
+            model.eval().cuda()
         n = 16000 * secs
         frames = 1 + n // hop
         base = synth.noisy_batch(min(bsz, 8), n)
