@@ -197,6 +197,7 @@ int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xpro
  *   2 (default) = tcgen05 cluster kernel (csrc/lstm_tc.cu: W_hh hi part in tensor memory, K split over a cluster of
  *       4 CTAs with a DSMEM reduction) where it applies -- H = 1024, one group, 32 clusters of 4 co-resident -- and
  *       the FMA kernel elsewhere;
+ *       (SE_LSTM_ENGINE=0..2 in the environment picks the start-up value for A/B runs);
  *   1 = legacy mma.sync TF32 path with the 3xTF32 split (H in {128, 512, 1024});
  *   0 = fp32 FMA kernel (any H %% 128 == 0).
  * Measured on B200 (H = 1024, B = 64): 7.9 / 14.4 / 13.8 us per step, see DESIGN.md. */
@@ -364,7 +365,8 @@ int se_uf_mask(const float* cmask, const float* mdec, const float* mag, const fl
  *   stat_mode INSTANCE: mean/rstd [B, C];  CUMULATIVE: mean/rstd [B, T, G], T = rows / rows_per_t, one set per channel
  *   group (G = `groups` / `stat_groups`: branches that were stacked on the channel axis keep their own statistics).
  *   Outputs: fp32 `out` and/or the TF32 split pair.  eps as the reference module's (1e-5).
- *   ws: se_chan_stats_ws_bytes(B, rows, C) bytes, ZERO-filled once by the caller (the kernels leave it zeroed);
+ *   ws: se_chan_stats_ws_bytes(B, rows, C) bytes whose first 4096 (the per-clip tickets; B <= 1024) are ZERO-filled
+ *       once by the caller -- the kernel leaves them zeroed, so one buffer serves every later call;
  *       se_cum_stats needs 16 * B * T * groups bytes (no initialisation).  C must divide 256 for se_chan_stats.
  * se_add: out = a + b (x_acc of Step1_network.py:28-33).
  * se_cts_glue1 / se_cts_glue2: CTSNet/two_stage_com_decode_vb.py:79-84 -- stage-1 magnitude x noisy phase,

@@ -647,3 +647,122 @@ def ctsnet_step2_forward(sd, inpt, X=6, R=3, cumulative=False, taps=None):
         d = _cts_decoder(sd, x, skips, f"{br}.de_list", cumulative)
         outs.append(F.linear(d, sd[f"{br}.de6.0.weight"], sd[f"{br}.de6.0.bias"]))
     return torch.stack(outs, dim=1)
+
+
+# ----------------------------------------------------------------------------------------
+# TaylorSENet  (TaylorSENet/TaylorSENet.py; TaylorSENet_new swaps InstanceNorm for cumulative LayerNorm)
+# configuration of taylorsenet_decode_vb.py:11-13: cin=2, k1=(1,3), k2=(2,3), c=64, kd1=5, cd1=64, d_feat=256,
+# dilations=[1,2,5,9], p=2, order_num=3, intra/inter_connect='cat', causal, no conformer, U2-Net, nothing shared.
+# ----------------------------------------------------------------------------------------
+TAYLOR_DILATIONS = (1, 2, 5, 9)
+
+
+def _ty_gate_conv(x, sd, pre, kt, transpose):
+    """GateConv2d / GateConvTranspose2d (TaylorSENet.py:549-603): ONE conv with 2*C outputs, chunk, a * sigmoid(b).
+    kt > 1: causal top pad (conv, key ``conv.1``) or Chomp_T (transposed conv, key ``conv.0``)."""
+    if transpose:
+        key = f"{pre}.conv.0" if kt > 1 else f"{pre}.conv"
+        y = F.conv_transpose2d(x, sd[key + ".weight"], sd[key + ".bias"], stride=(1, 2))
+        if kt > 1:
+            y = y[:, :, :-(kt - 1), :]
+    else:
+        key = f"{pre}.conv.1" if kt > 1 else f"{pre}.conv"
+        y = F.conv2d(F.pad(x, (0, 0, kt - 1, 0)), sd[key + ".weight"], sd[key + ".bias"], stride=(1, 2))
+    a, b = y.chunk(2, dim=1)
+    return a * torch.sigmoid(b)
+
+
+def _ty_unet_module(x, sd, pre, kt_in, scale, transpose, cum):
+    """En_unet_module (TaylorSENet.py:441-496): gated in_conv + norm + PReLU, then a small U-Net of ``scale``
+    Conv2dunit / Deconv2dunit levels (k2 = (2,3), stride (1,2), intra_connect = 'cat'), residual."""
+    r = _ty_gate_conv(x, sd, f"{pre}.in_conv.0", kt_in, transpose)
+    r = F.prelu(_cts_norm(r, sd, f"{pre}.in_conv.1", cum), sd[f"{pre}.in_conv.2.weight"])
+    x, xs = r, []
+    for i in range(scale):                                                   # Conv2dunit :498-519
+        x = F.conv2d(F.pad(x, (0, 0, 1, 0)), sd[f"{pre}.enco.{i}.conv.1.weight"], sd[f"{pre}.enco.{i}.conv.1.bias"],
+                     stride=(1, 2))
+        x = F.prelu(_cts_norm(x, sd, f"{pre}.enco.{i}.conv.2", cum), sd[f"{pre}.enco.{i}.conv.3.weight"])
+        xs.append(x)
+    for i in range(scale):                                                   # Deconv2dunit :521-547
+        if i > 0:
+            x = torch.cat((x, xs[-(i + 1)]), dim=1)
+        x = F.conv_transpose2d(x, sd[f"{pre}.deco.{i}.deconv.0.weight"], sd[f"{pre}.deco.{i}.deconv.0.bias"],
+                               stride=(1, 2))[:, :, :-1, :]
+        x = F.prelu(_cts_norm(x, sd, f"{pre}.deco.{i}.deconv.2", cum), sd[f"{pre}.deco.{i}.deconv.3.weight"])
+    return r + x
+
+
+def _ty_u2_encoder(x, sd, pre, cum):
+    """U2Net_Encoder (TaylorSENet.py:336-370): 4 modules (scale 4..1; the first has the (2,5) kernel) + last_conv."""
+    outs = []
+    for i, scale in enumerate((4, 3, 2, 1)):
+        x = _ty_unet_module(x, sd, f"{pre}.meta_unet_list.{i}", 2 if i == 0 else 1, scale, False, cum)
+        outs.append(x)
+    x = _ty_gate_conv(x, sd, f"{pre}.last_conv.0", 1, False)
+    x = F.prelu(_cts_norm(x, sd, f"{pre}.last_conv.1", cum), sd[f"{pre}.last_conv.2.weight"])
+    outs.append(x)
+    return x, outs
+
+
+def _ty_u2_decoder(x, en, sd, pre, cum):
+    """U2Net_Decoder, inter_connect='cat' (TaylorSENet.py:404-438): 4 modules (scale 1..4) + gated (2,5) deconv to 16
+    channels + norm + PReLU + 1x1 conv + sigmoid -> gain [B,T,161]."""
+    for i, scale in enumerate((1, 2, 3, 4)):
+        x = _ty_unet_module(torch.cat((x, en[-(i + 1)]), dim=1), sd, f"{pre}.meta_unet_list.{i}", 1, scale, True, cum)
+    x = torch.cat((x, en[0]), dim=1)
+    x = _ty_gate_conv(x, sd, f"{pre}.last_conv.0", 2, True)
+    x = F.prelu(_cts_norm(x, sd, f"{pre}.last_conv.1", cum), sd[f"{pre}.last_conv.2.weight"])
+    x = torch.sigmoid(F.conv2d(x, sd[f"{pre}.last_conv.3.weight"], sd[f"{pre}.last_conv.3.bias"]))
+    return x.squeeze(1)
+
+
+def _ty_tcm(x, sd, pre, d, cum, kd=5):
+    """SqueezedTCM (TaylorSENet.py:641-685), causal."""
+    def branch(u, name):
+        u = F.prelu(u, sd[f"{pre}.{name}.0.weight"])
+        u = _cts_norm(u, sd, f"{pre}.{name}.1", cum)
+        return F.conv1d(F.pad(u, ((kd - 1) * d, 0)), sd[f"{pre}.{name}.3.weight"], None, dilation=d)
+    u = F.conv1d(x, sd[f"{pre}.in_conv.weight"])
+    u = branch(u, "left_conv") * torch.sigmoid(branch(u, "right_conv"))
+    u = _cts_norm(F.prelu(u, sd[f"{pre}.out_conv.0.weight"]), sd, f"{pre}.out_conv.1", cum)
+    return F.conv1d(u, sd[f"{pre}.out_conv.2.weight"]) + x
+
+
+def _ty_tcms(x, sd, pre, cum, p=2):
+    for i in range(p):
+        for j, d in enumerate(TAYLOR_DILATIONS):
+            x = _ty_tcm(x, sd, f"{pre}.{i}.tcm_list.{j}", d, cum)
+    return x
+
+
+def taylorsenet_forward(sd, inputs, cumulative=False, order_num=3, taps=None):
+    """TaylorSENet.forward, TaylorSENet.py:66-94.  inputs [B,2,T,161] (compressed) RI -> [B,2,T,161]."""
+    import math
+    cum = cumulative
+    mag, phase = torch.norm(inputs, dim=1), torch.atan2(inputs[:, -1], inputs[:, 0])       # :73
+    # ZeroOrderBlock.forward :139-153
+    en_x, en_list = _ty_u2_encoder(inputs, sd, "zeroorderblock.en", cum)
+    b, c, t, f = en_x.shape
+    x = en_x.transpose(-2, -1).contiguous().view(b, c * f, t)
+    x = _ty_tcms(x, sd, "zeroorderblock.tcms", cum)
+    gain = _ty_u2_decoder(x.view(b, c, f, t).transpose(-2, -1).contiguous(), en_list, sd, "zeroorderblock.de", cum)
+    if taps is not None:
+        taps["gain"] = gain
+    zmag = gain * mag                                                                       # :75
+    zero = torch.stack((zmag * torch.cos(phase), zmag * torch.sin(phase)), dim=1)           # :76
+    head, _ = _ty_u2_encoder(inputs, sd, "separate_en", cum)                                # :79
+    head = head.transpose(-2, -1).contiguous().view(b, -1, t)
+    if taps is not None:
+        taps["head"] = head
+    out, pre_term = zero, zero
+    for k in range(order_num):                                                              # :84-93
+        hp = f"highorderblock_list.{k}"
+        x1 = pre_term.transpose(-2, -1).contiguous().view(b, -1, t)                         # HighOrderBlock.forward :191-214
+        x = F.conv1d(torch.cat((head, x1), dim=1), sd[hp + ".in_conv.weight"], sd[hp + ".in_conv.bias"])
+        x = _ty_tcms(x, sd, hp + ".tcms", cum)
+        xr = F.conv1d(x, sd[hp + ".real_resi.weight"], sd[hp + ".real_resi.bias"]).transpose(-2, -1)
+        xi = F.conv1d(x, sd[hp + ".imag_resi.weight"], sd[hp + ".imag_resi.bias"]).transpose(-2, -1)
+        update = torch.stack((xr, xi), dim=1) + k * pre_term
+        pre_term = update
+        out = out + update / math.factorial(k + 1)
+    return out

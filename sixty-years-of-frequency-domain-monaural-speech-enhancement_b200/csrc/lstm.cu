@@ -13,6 +13,8 @@
 //     shared memory, gates/cell update fused, h_t written to hseq and hT;
 //   * steps are separated by a device-wide counter barrier (release/acquire).
 // FP32 throughout: see gemm.cu for why tensor cores are not used on this path yet.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace se {
@@ -421,8 +423,21 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
   }
 }
 
-static int g_lstm_engine = 2;  // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu) where it
-                               // applies (H = 1024, one group, clusters fit the device), the FMA kernel elsewhere
+// 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu) where it applies (H = 1024, one
+// group, clusters fit the device), the FMA kernel elsewhere.
+// -1 = not chosen yet: SE_LSTM_ENGINE in the environment (A/B runs), else the default.
+static int g_lstm_engine = -1;
+constexpr int kDefaultLstmEngine = 2;
+static int lstm_engine() {
+  if (g_lstm_engine < 0) {
+    g_lstm_engine = kDefaultLstmEngine;
+    if (const char* e = getenv("SE_LSTM_ENGINE")) {
+      const int v = atoi(e);
+      if (v >= 0 && v <= 2) g_lstm_engine = v;
+    }
+  }
+  return g_lstm_engine;
+}
 
 int lstm_tc_supported();
 void lstm_tc_set_profile(long long* dev_buf, int first_step, int nsteps);
@@ -481,9 +496,10 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
   LstmParams p{xproj, xproj_stride, whh, B, T, H, hseq, hseq_sb, hseq_st, work, sync, ngroups, xproj_group_off,
                whh_group_stride, hseq_group_off};
   void* args[] = {(void*)&p};
-  if (g_lstm_engine == 2 && H == LT_H_PUBLIC && ngroups == 1 && lstm_tc_supported())
+  const int engine = lstm_engine();
+  if (engine == 2 && H == LT_H_PUBLIC && ngroups == 1 && lstm_tc_supported())
     return lstm_seq_tc_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, sync, s);
-  if (g_lstm_engine == 1 && (H == 1024 || H == 512 || H == 128)) {
+  if (engine == 1 && (H == 1024 || H == 512 || H == 128)) {
     e = H == 1024 ? launch_lstm_mma<16>(p, G, s) : (H == 512 ? launch_lstm_mma<8>(p, G, s) : launch_lstm_mma<2>(p, G, s));
   } else {
     e = cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel, dim3(G), dim3(kLstmThreads), args, smem, s);

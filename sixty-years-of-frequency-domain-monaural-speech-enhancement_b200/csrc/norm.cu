@@ -34,7 +34,7 @@ __device__ __forceinline__ float pre_value(const float* __restrict__ xr, int c, 
 
 // ---- pass 1, instance statistics -----------------------------------------------------------------------------
 // grid (chunks, B).  Thread tid owns channel c = tid % CL (CL = C rounded so that NT % CL == 0) and row lane tid / CL.
-// ws: double partial[B][chunks][C][2], then unsigned ticket[B] (zero on entry, left zero on exit).
+// ws: unsigned ticket[1024] (zero on entry, left zero on exit), then double partial[B][chunks][C][2].
 __global__ void __launch_bounds__(NT) chan_stats_kernel(const float* __restrict__ x, long long rows, int Cin, int C,
                                                        int pre, const float* __restrict__ slope, float eps,
                                                        float* __restrict__ mean, float* __restrict__ rstd,
@@ -272,12 +272,12 @@ extern "C" long long se_chan_stats_ws_bytes(int B, long long rows, int C) {
   (void)rows;
   // upper bound on chunks: 1184 / B + 1
   const long long chunks = 148 * 8 / (B > 0 ? B : 1) + 1;
-  return (long long)B * chunks * C * 2 * 8 + (long long)B * 4 + 64;
+  return 4096 + (long long)B * chunks * C * 2 * 8;
 }
 
 extern "C" int se_chan_stats(const float* x, int B, long long rows, int Cin, int C, int pre, const float* pre_slope,
                              float eps, float* mean, float* rstd, void* ws, se_stream_t stream) {
-  SE_REQUIRE(x && mean && rstd && ws && B > 0 && rows > 0, "se_chan_stats: bad arguments");
+  SE_REQUIRE(x && mean && rstd && ws && B > 0 && B <= 1024 && rows > 0, "se_chan_stats: bad arguments (B <= 1024)");
   SE_REQUIRE(norm_c_ok(C), "se_chan_stats: C=%d must divide %d", C, NT);
   SE_REQUIRE(pre >= SE_NORM_PRE_NONE && pre <= SE_NORM_PRE_GLU_PRELU, "se_chan_stats: pre=%d", pre);
   SE_REQUIRE((pre == SE_NORM_PRE_GLU || pre == SE_NORM_PRE_GLU_PRELU) ? Cin == 2 * C
@@ -289,8 +289,9 @@ extern "C" int se_chan_stats(const float* x, int B, long long rows, int Cin, int
   const long long maxc = (rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
-  double* partial = reinterpret_cast<double*>(ws);
-  unsigned* ticket = reinterpret_cast<unsigned*>(partial + (long long)B * (148 * 8 / B + 1) * C * 2);
+  // tickets FIRST, at a fixed place: a workspace reused across shapes must find them zero wherever the partials were
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + 4096);
   chan_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), NT, 0, (cudaStream_t)stream>>>(
       x, rows, Cin, C, pre, pre_slope, eps, mean, rstd, partial, ticket);
   return check_launch("se_chan_stats");

@@ -582,7 +582,7 @@ def chan_stats(x, B, rows, C, pre="none", pre_slope=None, eps=1e-5):
     return mean, rstd
 
 
-def cum_stats(x, B, T, F, C, pre="none", pre_slope=None, eps=1e-5, groups=1):
+def cum_stats(x, B, T, F, C, pre="none", pre_slope=None, eps=1e-5, groups=1):   # noqa: N803 (C shadows the ctypes alias)
     """Cumulative-LayerNorm statistics of pre(x): x [B, T, F, Cin] -> (mean [B,T,G], rstd [B,T,G])."""
     _need_cuda(x, pre_slope)
     device_check()
@@ -593,7 +593,7 @@ def cum_stats(x, B, T, F, C, pre="none", pre_slope=None, eps=1e-5, groups=1):
     rstd = torch.empty_like(mean)
     with _Timed(f"cum_stats[C={C}]"):
         check(_lib.load().se_cum_stats(_ptr(x), B, T, F, cin, C, groups, _lib.NORM_PRE[pre], _ptr(pre_slope), float(eps),
-                                       _ptr(mean), _ptr(rstd), C.c_void_p(ws.data_ptr()), _stream()), "se_cum_stats")
+                                       _ptr(mean), _ptr(rstd), _ptr(ws), _stream()), "se_cum_stats")
     return mean, rstd
 
 

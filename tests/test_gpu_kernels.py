@@ -328,7 +328,7 @@ def test_attention_matches_softmax(over_t, cplx):
 DEFAULT_LSTM_ENGINE = 2
 
 
-@pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (1024, 5, 3), (512, 7, 9), (128, 33, 15)])
+@pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (1024, 5, 3), (1024, 64, 401), (512, 7, 9), (128, 33, 15)])
 def test_lstm_engines_agree(h, b, t):
     """fp32 FMA / mma.sync 3xTF32 / tcgen05 3xTF32 (H = 1024 only, else the FMA kernel) recurrences vs fp64."""
     dev = _dev()
@@ -530,4 +530,4 @@ def test_cum_stats_2d_and_cts_glue():
     assert (est.cpu() - emu_ops.cts_glue2(o_r, o_i, s2.cpu())).abs().max() < 1e-6
     a, bb = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
     s, pr = ops.add(a.to(dev), bb.to(dev), want_pair=True)
-    assert torch.equal(s.cpu(), a + bb) and torch.equal((pr[0] + pr[1]).cpu(), a + bb)
+    assert torch.equal(s.cpu(), a + bb) and ((pr[0] + pr[1]).cpu() - (a + bb)).abs().max() < 1e-6   # hi+lo: 21+ bits

@@ -19,13 +19,14 @@ EV = ["poll_start", "barrier_seen", "tma_issued", "first_stage", "last_stage", "
 
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 401
+    engine = int(sys.argv[2]) if len(sys.argv) > 2 else 2          # 2 = csrc/lstm_tc.cu
     B, H, NS = 64, 1024, 8
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
     xp = torch.randn(B, T, 4 * H, generator=g).to(dev)
     whh = (torch.randn(H // 8, H, 32, generator=g) / 32).to(dev)
     hs = torch.empty(B, T, H, device=dev)
-    ops.set_lstm_engine(2)
+    ops.set_lstm_engine(engine)
     for _ in range(2):
         ops.lstm_seq(xp, whh, H, out=hs)
     torch.cuda.synchronize()
@@ -43,7 +44,7 @@ def main():
     st = buf.cpu().numpy().reshape(128, NS, len(EV)).astype(np.float64)
     # SM clocks are not synchronised across SMs: only per-CTA differences are meaningful
     step = np.diff(st[:, :, 9], axis=1).mean()            # arrival -> arrival, cycles
-    out = {"T": T, "ms": ms, "us_per_step": 1e3 * ms / T, "cycles_per_step": step,
+    out = {"engine": engine, "T": T, "ms": ms, "us_per_step": 1e3 * ms / T, "cycles_per_step": step,
            "ghz_implied": step / (1e3 * ms / T) / 1e3}
     seg = {}
     for a, b in [(0, 1), (1, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (8, 10), (10, 11), (11, 9), (1, 2)]:
