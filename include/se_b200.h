@@ -368,7 +368,10 @@ int se_uf_mask(const float* cmask, const float* mdec, const float* mag, const fl
  *   ws: se_chan_stats_ws_bytes(B, rows, C) bytes whose first 4096 (the per-clip tickets; B <= 1024) are ZERO-filled
  *       once by the caller -- the kernel leaves them zeroed, so one buffer serves every later call;
  *       se_cum_stats needs 16 * B * T * groups bytes (no initialisation).  C must divide 256 for se_chan_stats.
- * se_add: out = a + b (x_acc of Step1_network.py:28-33).
+ * se_add: out = a + b (x_acc of Step1_network.py:28-33);  se_axpby: out = ca*a + cb*b (the Taylor recursion
+ *   update = block(..) + k * pre_term, out += update / (k+1)!, TaylorSENet/TaylorSENet.py:84-93).
+ * se_taylor_zero: TaylorSENet's zeroth-order term gain * |X| * (cos, sin)(angle X) (TaylorSENet.py:73-76) from
+ *   x_ri [rows, F, 2] and gain [rows, F], written as "RI rows" [rows, ld] = [re(F) | im(F) | zero pad].
  * se_cts_glue1 / se_cts_glue2: CTSNet/two_stage_com_decode_vb.py:79-84 -- stage-1 magnitude x noisy phase,
  *   cat(noisy RI, stage-1 RI) -> s2_in [n, 4];  est [n, 2] = stage-2 output + stage-1 RI.
  * ------------------------------------------------------------------------------------- */
@@ -385,6 +388,10 @@ int se_chan_norm(const float* x, int B, long long rows, int Cin, int C, int pre,
                  const float* gamma, const float* beta, int post, const float* post_slope, const float* fir_w, int fir_k, int fir_groups,
                  float* out, float* out_hi, float* out_lo, se_stream_t stream);
 int se_add(const float* a, const float* b, long long n, float* out, float* out_hi, float* out_lo, se_stream_t stream);
+int se_axpby(const float* a, const float* b, float ca, float cb, long long n, float* out, float* out_hi, float* out_lo,
+             se_stream_t stream);
+int se_taylor_zero(const float* x_ri, const float* gain, long long rows, int F, int ld, float* out, float* out_hi,
+                   float* out_lo, se_stream_t stream);
 int se_cts_glue1(const float* x_ri, const float* est_mag, long long n, float* s2_in, se_stream_t stream);
 int se_cts_glue2(const float* out_r, const float* out_i, const float* s2_in, long long n, float* est,
                  se_stream_t stream);

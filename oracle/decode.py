@@ -197,3 +197,27 @@ def enhance_ctsnet(sds, wav, p=1.0, cumulative=False):
     y = y[:wav_len]                                                         # :95
     taps = {"c": c, "feat": feat, "est1": est1.squeeze(0).numpy(), "est": est, "y_norm": y.astype(np.float32)}
     return (y / c).astype(np.float32), taps
+
+
+def enhance_taylorsenet(sd, wav, p=1.0, cumulative=False):
+    """``TaylorSENet/taylorsenet_decode_vb.py:27-52`` (torch dialect; p = 1.0 there (:40,44), 0.5 in TaylorSENet_new and
+    for the cprs checkpoints): zero-pad to whole hops, STFT, compressed RI in, RI out (the Taylor recursion is inside
+    forward), decompress (rule (ii)), iSTFT(length=N)."""
+    from . import nets as _n
+    n_fft, win, hop = dsp.GEOMETRIES["320"]
+    x, c = dsp.rms_scale(wav)                                               # :29-30
+    wav_len = len(x)
+    frame_num = int(np.ceil((wav_len - 320 + 320) / 160 + 1))               # :32
+    fake_len = (frame_num - 1) * 160 + 320 - 320
+    x32 = np.concatenate((x, np.zeros(fake_len - wav_len))).astype(np.float32)   # :35
+    spec = dsp.stft(x32, n_fft, win, hop).T                                 # :36-37  [T,F]
+    mag, ph = (np.abs(spec) ** p).astype(np.float32), np.angle(spec).astype(np.float32)   # :40
+    feat = np.stack((mag * np.cos(ph), mag * np.sin(ph))).astype(np.float32)             # :41
+    with torch.no_grad():
+        est = _n.taylorsenet_forward(sd, torch.from_numpy(feat)[None], cumulative).squeeze(0).numpy()   # :42
+    emag = np.sqrt(est[0] ** 2 + est[1] ** 2) ** (1.0 / p)                  # :44
+    eph = np.arctan2(est[1], est[0])
+    y = dsp.istft((emag * np.cos(eph) + 1j * emag * np.sin(eph)).T.astype(np.complex64), n_fft, win, hop,
+                  length=wav_len)                                           # :48
+    taps = {"c": c, "feat": feat, "est": est, "y_norm": y.astype(np.float32)}
+    return (y / c).astype(np.float32), taps

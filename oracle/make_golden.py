@@ -281,6 +281,47 @@ def make_ctsnet():
               f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+TAYLOR_KW = dict(cin=2, k1=(1, 3), k2=(2, 3), c=64, kd1=5, cd1=64, d_feat=256, dilations=[1, 2, 5, 9], p=2, fft_num=320,
+                 order_num=3, intra_connect='cat', inter_connect='cat', is_causal=True, is_conformer=False, is_u2=True,
+                 is_param_share=False, is_encoder_share=False)     # TaylorSENet/taylorsenet_decode_vb.py:11-13
+TAYLOR_CASES = [
+    # name, model dir, checkpoint, samples, clip ids, p, cumulative
+    ("taylor_synth", "TaylorSENet", None, 8000, (18, 19), 0.5, False),
+    ("taylor_ckpt", "TaylorSENet", "vb_taylor_noncprs_model.pth", 16000, (18, 19), 1.0, False),
+    ("taylor_new_ckpt", "TaylorSENet_new", "vb_taylor_cprs_model.pth", 16000, (20, 21), 0.5, True),
+]
+
+
+def make_taylor():
+    """Fixtures from the UNMODIFIED TaylorSENet{,_new}/TaylorSENet.py module."""
+    for name, mdir, ckpt, nsamp, clip_ids, p, cum in TAYLOR_CASES:
+        net = ref_shims.import_reference(mdir, "TaylorSENet").TaylorSENet(**TAYLOR_KW).eval()
+        if ckpt is None:
+            sd = synth.synthetic_state_dict(templates.taylorsenet_template(cum), seed=0, gain=1.0)
+        else:
+            sd = torch.load(ref_shims.checkpoint_path(mdir, ckpt), map_location="cpu")
+        net.load_state_dict(sd)
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp), "p": np.array(p)}
+        worst = 0.0
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = decode.enhance_taylorsenet(sd, wav.astype(np.float64), p=p, cumulative=cum)
+            with torch.no_grad():
+                est_ref = net(torch.from_numpy(taps["feat"])[None]).squeeze(0).numpy()
+            worst = max(worst, float(np.abs(est_ref - taps["est"]).max()))
+            rec[f"wav{j}"] = wav
+            rec[f"feat{j}"] = taps["feat"]
+            rec[f"est{j}"] = est_ref.astype(np.float32)
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        rec["ref_vs_oracle"] = np.array(worst)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: ref_vs_oracle max-abs {worst:.3e}, |est| max {float(np.abs(rec['est0']).max()):.2f}, out rms "
+              f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def sd_digest(sd) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
@@ -338,3 +379,5 @@ if __name__ == "__main__":
         make_uformer()
     if len(sys.argv) < 2 or sys.argv[1] == "ctsnet":
         make_ctsnet()
+    if len(sys.argv) < 2 or sys.argv[1] == "taylor":
+        make_taylor()

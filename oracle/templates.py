@@ -225,3 +225,13 @@ def ctsnet_step2_template(X=6, R=3, cumulative=False):
         for j in range(X):
             _cts_tcm(d, f"tcm_list.{r}.glu_list.{j}", j, ("ori_conv", "att_ori"), cumulative)
     return d
+
+
+def taylorsenet_template(cumulative=False):
+    """TaylorSENet/TaylorSENet.py:8-64 in the configuration of taylorsenet_decode_vb.py:11-13 (811 entries, key order as
+    ``TaylorSENet(...).state_dict()`` lists it; recorded from the reference module in oracle/taylor*_keys.json)."""
+    import json
+    import os
+    name = "taylor_new_keys.json" if cumulative else "taylor_keys.json"
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), name)) as f:
+        return {k: tuple(v) for k, v in json.load(f).items()}

@@ -224,11 +224,12 @@ __global__ void __launch_bounds__(NT) chan_norm_kernel(const NormParams p) {
 }
 
 // ---- small elementwise helpers -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) add_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
-                                                float* __restrict__ out, float* __restrict__ out_hi,
-                                                float* __restrict__ out_lo) {
+__global__ void __launch_bounds__(NT) axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float ca,
+                                                  float cb, long long n, float* __restrict__ out,
+                                                  float* __restrict__ out_hi, float* __restrict__ out_lo) {
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
-    const float y = __ldg(a + i) + __ldg(b + i);
+    // ca == cb == 1 is the plain sum (no multiply, so it rounds exactly like torch's a + b)
+    const float y = (ca == 1.f && cb == 1.f) ? __ldg(a + i) + __ldg(b + i) : ca * __ldg(a + i) + cb * __ldg(b + i);
     if (out) out[i] = y;
     if (out_hi) split_tf32_dev(y, out_hi[i], out_lo[i]);
   }
@@ -254,6 +255,29 @@ __global__ void __launch_bounds__(NT) cts_glue2_kernel(const float* __restrict__
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
     const float4 s = __ldg(s2in + i);
     est[i] = make_float2(__ldg(out_r + i) + s.z, __ldg(out_i + i) + s.w);
+  }
+}
+
+// TaylorSENet zeroth-order term (TaylorSENet/TaylorSENet.py:73-76): gain * |X| * (cos, sin)(angle X) written as one
+// "RI row" per frame: [re(F) | im(F) | zero pad] of width ld (the layout the high-order GEMMs read and write).
+__global__ void __launch_bounds__(NT) taylor_zero_kernel(const float2* __restrict__ x, const float* __restrict__ gain,
+                                                        long long rows, int F, int ld, float* __restrict__ out,
+                                                        float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  const long long n = rows * ld;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const long long r = i / ld;
+    const int c = (int)(i - r * ld);
+    float y = 0.f;
+    if (c < 2 * F) {
+      const int f = c < F ? c : c - F;
+      const float2 v = __ldg(x + r * F + f);
+      const float mag = sqrtf(v.x * v.x + v.y * v.y);          // torch.norm(inputs, dim=1)
+      const float ph = atan2f(v.y, v.x);
+      const float zm = __ldg(gain + r * F + f) * mag;
+      y = c < F ? zm * cosf(ph) : zm * sinf(ph);
+    }
+    out[i] = y;
+    if (out_hi) split_tf32_dev(y, out_hi[i], out_lo[i]);
   }
 }
 
@@ -342,12 +366,27 @@ extern "C" int se_chan_norm(const float* x, int B, long long rows, int Cin, int 
   return check_launch("se_chan_norm");
 }
 
+extern "C" int se_axpby(const float* a, const float* b, float ca, float cb, long long n, float* out, float* out_hi,
+                        float* out_lo, se_stream_t stream) {
+  SE_REQUIRE(a && b && n > 0 && (out || out_hi), "se_axpby: bad arguments");
+  SE_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "se_axpby: out_hi/out_lo go together");
+  axpby_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(a, b, ca, cb, n, out, out_hi, out_lo);
+  return check_launch("se_axpby");
+}
+
 extern "C" int se_add(const float* a, const float* b, long long n, float* out, float* out_hi, float* out_lo,
                       se_stream_t stream) {
-  SE_REQUIRE(a && b && n > 0 && (out || out_hi), "se_add: bad arguments");
-  SE_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "se_add: out_hi/out_lo go together");
-  add_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(a, b, n, out, out_hi, out_lo);
-  return check_launch("se_add");
+  return se_axpby(a, b, 1.f, 1.f, n, out, out_hi, out_lo, stream);
+}
+
+extern "C" int se_taylor_zero(const float* x_ri, const float* gain, long long rows, int F, int ld, float* out,
+                              float* out_hi, float* out_lo, se_stream_t stream) {
+  SE_REQUIRE(x_ri && gain && out && rows > 0 && F > 0 && ld >= 2 * F, "se_taylor_zero: bad arguments");
+  SE_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "se_taylor_zero: out_hi/out_lo go together");
+  SE_REQUIRE((((uintptr_t)x_ri) & 7) == 0, "se_taylor_zero: unaligned");
+  taylor_zero_kernel<<<grid_for(rows * ld), NT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(x_ri), gain,
+                                                                           rows, F, ld, out, out_hi, out_lo);
+  return check_launch("se_taylor_zero");
 }
 
 extern "C" int se_cts_glue1(const float* x_ri, const float* est_mag, long long n, float* s2_in, se_stream_t stream) {

@@ -135,27 +135,32 @@ class _CtsBase(nn.Module):
                                *self._norm_params(sd, f"{de_pre}.{i}.1"), sd[f"{de_pre}.{i}.2.weight"].contiguous())
         P[f"{name}_fc"] = (packing.pad_cols(sd[fc + ".weight"].t().contiguous()), sd[fc + ".bias"].contiguous())
 
-    def _pack_tcm(self, sd, P, pre, name, d, branches):
+    def _pack_tcm(self, sd, P, pre, name, d, branches, conv_idx=4, fir_idx=2):
+        """conv_idx / fir_idx: positions of the dilated conv and of ShareSepConv inside the branch nn.Sequential
+        (CTSNet: 4 / 2; TaylorSENet's SqueezedTCM has no ShareSepConv: 3 / None)."""
         dev = sd[f"{pre}.in_conv.weight"].device
         q = torch.arange(256, device=dev)
         ref_of_q = (q % 64) * 4 + q // 64              # channels-last column f*64 + c  <-  reference feature c*4 + f
         w_in = sd[f"{pre}.in_conv.weight"][:, :, 0][:, ref_of_q].contiguous()                # [64, 256]  (N, K)
         w_out = sd[f"{pre}.out_conv.2.weight"][:, :, 0][ref_of_q].contiguous()              # [256, 64]
-        wl, wr = sd[f"{pre}.{branches[0]}.4.weight"], sd[f"{pre}.{branches[1]}.4.weight"]    # [64, 64, 5]
+        wl, wr = sd[f"{pre}.{branches[0]}.{conv_idx}.weight"], sd[f"{pre}.{branches[1]}.{conv_idx}.weight"]    # [64, 64, 5]
         wd = torch.zeros(128, 5, 128, device=dev)                                            # [co, tap, ci] block diagonal
         wd[:64, :, :64] = wl.permute(0, 2, 1)
         wd[64:, :, 64:] = wr.permute(0, 2, 1)
         gl, bl = self._norm_params(sd, f"{pre}.{branches[0]}.1")
         gr, br = self._norm_params(sd, f"{pre}.{branches[1]}.1")
         go, bo = self._norm_params(sd, f"{pre}.out_conv.1")
-        fir = torch.stack([sd[f"{pre}.{branches[0]}.2.weight"].reshape(-1), sd[f"{pre}.{branches[1]}.2.weight"].reshape(-1)])
+        fir = None
+        if fir_idx is not None:
+            fir = torch.stack([sd[f"{pre}.{branches[0]}.{fir_idx}.weight"].reshape(-1),
+                               sd[f"{pre}.{branches[1]}.{fir_idx}.weight"].reshape(-1)]).contiguous()
         P[name] = {
             "in": packing.split_tf32(w_in), "out": packing.split_tf32(w_out),
             "dil": packing.split_tf32(wd.reshape(128, 640).contiguous()),
             "taps": [((j - 4) * d, 0) for j in range(5)],
             "slope_lr": torch.cat([sd[f"{pre}.{branches[0]}.0.weight"], sd[f"{pre}.{branches[1]}.0.weight"]]).contiguous(),
             "gamma_lr": torch.cat([gl, gr]).contiguous(), "beta_lr": torch.cat([bl, br]).contiguous(),
-            "fir": fir.contiguous(),
+            "fir": fir,
             "slope_o": sd[f"{pre}.out_conv.0.weight"].contiguous(), "gamma_o": go, "beta_o": bo,
         }
 
@@ -201,8 +206,9 @@ class _CtsBase(nn.Module):
         xf, xp = x
         u, _ = ops.gemm_tf32x3_ex(xp, p["in"][0], p["in"][1], None, 64)                        # in_conv
         st = self._stats(u, b, t, 1, 128, "prelu", p["slope_lr"], groups=2)
+        post = dict(post="fir", fir_w=p["fir"], fir_groups=2) if p["fir"] is not None else dict(post="none")
         _, y = self._norm(u, b, t, 1, 128, st, p["gamma_lr"], p["beta_lr"], "prelu", p["slope_lr"], groups=2,
-                          post="fir", fir_w=p["fir"], fir_groups=2, want_f32=False, want_pair=True)
+                          want_f32=False, want_pair=True, **post)
         v = torch.empty(b, t, 1, 128, device=u.device, dtype=torch.float32)                  # [l | r]
         ops.conv_tf32x3((y[0].view(b, t, 1, 128), y[1].view(b, t, 1, 128)), None, b, t, 1, 1, p["taps"], 1,
                         p["dil"][0], p["dil"][1], None, 128, "none", 1, out=v)

@@ -169,6 +169,42 @@ def enhance_ctsnet(models, wav, p=1.0, taps=None):
     return out
 
 
+def _padded_to_hops(wav, hop):
+    """Zero tail to a whole number of hops (ceil(N/hop) + 1 frames), as the torch-dialect scripts do
+    (DCCRN/dccrn_decode.py:36-39, CTSNet/two_stage_com_decode_vb.py:65-68, TaylorSENet/taylorsenet_decode_vb.py:32-35)."""
+    b, n = wav.shape
+    fake = (-(-n // hop)) * hop
+    if fake == n:
+        return wav, fake
+    padded = torch.zeros(b, fake, device=wav.device, dtype=torch.float32)
+    padded[:, :n] = wav
+    return padded, fake
+
+
+@torch.no_grad()
+def enhance_taylorsenet(model, wav, p=1.0, taps=None):
+    """TaylorSENet/taylorsenet_decode_vb.py:27-52 (p = 1.0; 0.5 for the cprs checkpoints / TaylorSENet_new): STFT
+    (compressed RI, channels-last), forward (RI rows out), decompress (rule (ii)), iSTFT(length=N), / c."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    from .taylor import N_BINS, RI_LD
+    n_fft, win, hop = GEOM_320
+    wav = wav.contiguous().float()
+    b, n = wav.shape
+    c, inv_c = ops.rms_scale(wav)
+    wav_in, fake = _padded_to_hops(wav, hop)
+    t, f = 1 + fake // hop, n_fft // 2 + 1
+    x = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)
+    ops.stft(wav_in, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p)
+    rows = model.forward_nhwc(x, taps).view(b, t, RI_LD)
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_RI_DECOMP, rows[..., :N_BINS], rows[..., N_BINS:2 * N_BINS], None, None, n_fft, win, hop, out, n,
+              out_scale=inv_c, inv_p=1.0 / p)
+    if taps is not None:
+        taps.update(c=c, x=x, est=rows)
+    return out
+
+
 @torch.no_grad()
 def enhance_fullsubnet(model, wav, p=0.5, taps=None):
     """FullSubNet/fullsubnet_sa_decode.py:44-78: |X|^p magnitude in, complex mask out, mask applied

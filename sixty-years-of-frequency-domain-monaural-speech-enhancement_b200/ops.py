@@ -632,6 +632,35 @@ def add(a, b, want_f32=True, want_pair=False):
     return out, pair
 
 
+def axpby(a, b, ca, cb, want_f32=True, want_pair=False):
+    """ca * a + cb * b."""
+    _need_cuda(a, b)
+    device_check()
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a) if want_f32 else None
+    pair = (torch.empty_like(a), torch.empty_like(a)) if want_pair else None
+    with _Timed("axpby"):
+        check(_lib.load().se_axpby(_ptr(a), _ptr(b), float(ca), float(cb), a.numel(), _ptr(out),
+                                   _ptr(pair[0] if pair else None), _ptr(pair[1] if pair else None), _stream()),
+              "se_axpby")
+    return out, pair
+
+
+def taylor_zero(x_ri, gain, ld, want_pair=True):
+    """x_ri [B,T,F,2], gain [B,T,F] -> zeroth-order term as RI rows [B*T, ld] (fp32, TF32 pair)."""
+    _need_cuda(x_ri, gain)
+    device_check()
+    assert x_ri.is_contiguous() and gain.is_contiguous() and x_ri.shape[:-1] == gain.shape
+    f = gain.shape[-1]
+    rows = gain.numel() // f
+    out = torch.empty(rows, ld, device=gain.device, dtype=torch.float32)
+    pair = (torch.empty_like(out), torch.empty_like(out)) if want_pair else None
+    with _Timed("taylor_zero"):
+        check(_lib.load().se_taylor_zero(_ptr(x_ri), _ptr(gain), rows, f, ld, _ptr(out), _ptr(pair[0] if pair else None),
+                                         _ptr(pair[1] if pair else None), _stream()), "se_taylor_zero")
+    return out, pair
+
+
 def cts_glue1(x_ri, est_mag):
     """x_ri [B,T,F,2] noisy (compressed) RI, est_mag [B,T,F] -> s2_in [B,T,F,4] (two_stage_com_decode_vb.py:79-82)."""
     _need_cuda(x_ri, est_mag)

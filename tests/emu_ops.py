@@ -376,6 +376,24 @@ def add(a, b, want_f32=True, want_pair=False):
     return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
 
 
+def axpby(a, b, ca, cb, want_f32=True, want_pair=False):
+    from se_b200 import packing
+    y = a + b if ca == 1 and cb == 1 else ca * a + cb * b
+    return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
+
+
+def taylor_zero(x_ri, gain, ld, want_pair=True):
+    from se_b200 import packing
+    f = gain.shape[-1]
+    mag = torch.sqrt(x_ri[..., 0] ** 2 + x_ri[..., 1] ** 2)
+    ph = torch.atan2(x_ri[..., 1], x_ri[..., 0])
+    zm = gain * mag
+    out = torch.zeros(gain.numel() // f, ld, dtype=gain.dtype)
+    out[:, :f] = (zm * torch.cos(ph)).reshape(-1, f)
+    out[:, f:2 * f] = (zm * torch.sin(ph)).reshape(-1, f)
+    return out, (packing.split_tf32(out) if want_pair else None)
+
+
 def cts_glue1(x_ri, est_mag):
     ph = torch.atan2(x_ri[..., 1], x_ri[..., 0])
     return torch.stack([x_ri[..., 0], x_ri[..., 1], est_mag * torch.cos(ph), est_mag * torch.sin(ph)], -1)
@@ -385,7 +403,7 @@ def cts_glue2(out_r, out_i, s2_in):
     return torch.stack([out_r + s2_in[..., 2], out_i + s2_in[..., 3]], -1)
 
 
-_NORM_NAMES = ("chan_stats", "cum_stats", "chan_norm", "add", "cts_glue1", "cts_glue2")
+_NORM_NAMES = ("chan_stats", "cum_stats", "chan_norm", "add", "axpby", "taylor_zero", "cts_glue1", "cts_glue2")
 _orig_install2 = install
 
 

@@ -531,3 +531,10 @@ def test_cum_stats_2d_and_cts_glue():
     a, bb = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
     s, pr = ops.add(a.to(dev), bb.to(dev), want_pair=True)
     assert torch.equal(s.cpu(), a + bb) and ((pr[0] + pr[1]).cpu() - (a + bb)).abs().max() < 1e-6   # hi+lo: 21+ bits
+    z, _ = ops.axpby(a.to(dev), bb.to(dev), 1.0, 1.0 / 6.0)
+    assert (z.cpu() - (a + bb / 6.0)).abs().max() < 1e-6
+    gain = torch.rand(b, t, 161, generator=g)
+    rows, rp = ops.taylor_zero(xr.to(dev), gain.to(dev), 352)
+    ref_rows, _ = emu_ops.taylor_zero(xr, gain, 352)
+    assert (rows.cpu() - ref_rows).abs().max() < 2e-6 and ((rp[0] + rp[1]).cpu() - ref_rows).abs().max() < 2e-6
+    assert rows[:, 322:].abs().max().item() == 0.0

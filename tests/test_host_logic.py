@@ -255,3 +255,26 @@ def test_ctsnet_host_logic_matches_oracle(monkeypatch, cum):
     with torch.no_grad():
         ref2 = nets.ctsnet_step2_forward(sd2, z, cumulative=cum)
     assert (m2._forward_impl(z) - ref2).abs().max() < 2e-5 * max(1.0, ref2.abs().max().item())
+
+
+@pytest.mark.parametrize("cum", [False, True])
+def test_taylorsenet_host_logic_matches_oracle(monkeypatch, cum):
+    """TaylorSENet / TaylorSENet_new: U2-Net modules (gated in_conv, inner U-Net with 'cat' skips, residual), transposed
+    convs as parity classes, the zeroth-order gain path, the high-order recursion on RI rows (split in_conv GEMMs,
+    stacked real/imag residual GEMM, k * pre_term and 1/k! accumulation)."""
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t = templates.taylorsenet_template(cum)
+    sd = synth.synthetic_state_dict(t, seed=8, gain=1.0)
+    m = se_b200.TaylorSENet(cumulative=cum)
+    assert list(m.state_dict().keys()) == list(t.keys())
+    m.load_state_dict(sd)
+    x = torch.randn(2, 2, 23, 161, generator=torch.Generator().manual_seed(5))
+    taps, rtaps = {}, {}
+    est = m._forward_impl(x, taps)
+    with torch.no_grad():
+        ref = nets.taylorsenet_forward(sd, x, cum, taps=rtaps)
+    assert (taps["gain"] - rtaps["gain"]).abs().max() < 1e-5
+    assert (taps["head"].permute(0, 3, 2, 1).reshape(2, 256, 23) - rtaps["head"]).abs().max() < 1e-5
+    assert (est - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
+    with pytest.raises(NotImplementedError):
+        se_b200.TaylorSENet(order_num=2)

@@ -133,3 +133,46 @@ def test_ctsnet_oracle_equals_reference_modules(mdir, cum):
     with torch.no_grad():
         assert (m1(x) - nets.ctsnet_step1_forward(sd1, x, cum)).abs().max() < 1e-5
         assert (m2(z) - nets.ctsnet_step2_forward(sd2, z, cumulative=cum)).abs().max() < 1e-5
+
+
+TAYLOR_CKPTS = {"taylor_ckpt": "TaylorSENet__vb_taylor_noncprs_model.pth",
+                "taylor_new_ckpt": "TaylorSENet_new__vb_taylor_cprs_model.pth"}
+
+
+def load_taylor_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cum = "_new" in name
+    if name in TAYLOR_CKPTS:
+        path = os.path.join(CKPT_DIR, TAYLOR_CKPTS[name])
+        if not os.path.exists(path):
+            pytest.skip("checkpoint copy not present (oracle/fetch_checkpoints.py)")
+        sd = torch.load(path, map_location="cpu")
+    else:
+        sd = synth.synthetic_state_dict(templates.taylorsenet_template(cum), seed=0, gain=1.0)
+    return g, sd, float(g["p"]), cum
+
+
+@pytest.mark.parametrize("name", ["taylor_synth", "taylor_ckpt", "taylor_new_ckpt"])
+def test_taylorsenet_oracle_reproduces_golden(name):
+    g, sd, p, cum = load_taylor_case(name)
+    assert sd_digest(sd) == str(g["digest"])
+    assert float(g["ref_vs_oracle"]) < 1e-4
+    for j in range(len(g["clip_ids"])):
+        wav = synth.noisy_clip(int(g["clip_ids"][j]), int(g["nsamp"]))
+        assert np.array_equal(wav, g[f"wav{j}"])
+        y, taps = decode.enhance_taylorsenet(sd, wav.astype(np.float64), p=p, cumulative=cum)
+        assert np.abs(taps["est"] - g[f"est{j}"]).max() < 1e-4 * max(1.0, np.abs(g[f"est{j}"]).max())
+        assert np.sqrt(np.mean((taps["y_norm"] - g[f"ynorm{j}"]) ** 2)) < 2e-6
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("mdir,cum", [("TaylorSENet", False), ("TaylorSENet_new", True)])
+def test_taylorsenet_oracle_equals_reference_module(mdir, cum):
+    from oracle.make_golden import TAYLOR_KW
+    net = ref_shims.import_reference(mdir, "TaylorSENet").TaylorSENet(**TAYLOR_KW).eval()
+    sd = synth.synthetic_state_dict(templates.taylorsenet_template(cum), seed=4, gain=1.0)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd)
+    x = torch.randn(2, 2, 19, 161, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        assert (net(x) - nets.taylorsenet_forward(sd, x, cum)).abs().max() < 1e-5

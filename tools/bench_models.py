@@ -35,6 +35,8 @@ CASES = {
     "ctsnet": (lambda: (se_b200.ctsnet.Step1_net(), se_b200.ctsnet.Step2_net(X=6, R=3)),
                lambda: (templates.ctsnet_step1_template(), templates.ctsnet_step2_template()),
                se_b200.decode.enhance_ctsnet, odecode.enhance_ctsnet, 64, 4, 160, dict(p=1.0)),
+    "taylor": (lambda: se_b200.TaylorSENet(), templates.taylorsenet_template, se_b200.decode.enhance_taylorsenet,
+               odecode.enhance_taylorsenet, 64, 4, 160, dict(p=1.0)),
     "uformer": (lambda: se_b200.Uformer(), templates.uformer_template, se_b200.decode.enhance_uformer, None,
                 64, 4, 160, dict()),
 }
@@ -53,7 +55,7 @@ def main():
                 m.load_state_dict(s)
                 m.eval().cuda()
         else:
-            sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name in ("uformer", "dpcrn") else 2.0)
+            sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name in ("uformer", "dpcrn", "taylor") else 2.0)
             model = ctor()
             model.load_state_dict(sd)
             model.eval().cuda()
