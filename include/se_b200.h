@@ -392,6 +392,12 @@ int se_axpby(const float* a, const float* b, float ca, float cb, long long n, fl
              se_stream_t stream);
 int se_taylor_zero(const float* x_ri, const float* gain, long long rows, int F, int ld, float* out, float* out_hi,
                    float* out_lo, se_stream_t stream);
+ /* se_gaf_update: G2Net stage update x' = gain * |pre| * (cos, sin)(angle pre) + com_resi
+ *   (G2Net_new/gaf_net_320.py:104-115) on RI rows [rows, ld] (re at column 0, im at column im_off, zero elsewhere);
+ *   pre is addressed as x_re/x_im[r * xs_r + f * xs_f]; gain == resi == NULL: relayout of pre into RI rows. */
+int se_gaf_update(const float* x_re, const float* x_im, long long xs_r, int xs_f, const float* gain, const float* resi,
+                  long long rows, int F, int ld, int im_off, float* out, float* out_hi, float* out_lo,
+                  se_stream_t stream);
 int se_cts_glue1(const float* x_ri, const float* est_mag, long long n, float* s2_in, se_stream_t stream);
 int se_cts_glue2(const float* out_r, const float* out_i, const float* s2_in, long long n, float* est,
                  se_stream_t stream);

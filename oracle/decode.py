@@ -221,3 +221,26 @@ def enhance_taylorsenet(sd, wav, p=1.0, cumulative=False):
                   length=wav_len)                                           # :48
     taps = {"c": c, "feat": feat, "est": est, "y_norm": y.astype(np.float32)}
     return (y / c).astype(np.float32), taps
+
+
+def enhance_g2net(sd, wav, p=0.5, cumulative=True):
+    """``G2Net_new/com_decode.py:36-88`` (librosa dialect; RECIPROCAL scale convention: c = sqrt(sum x^2 / N), x / c,
+    result * c (:43-44,88); p = 0.5 there (:53,76), 1.0 in G2Net_VB/com_decode.py with the InstanceNorm graph):
+    compressed RI in, list of stage outputs, the last one decompressed (rule (ii)), iSTFT(length=N)."""
+    from . import nets as _n
+    n_fft, win, hop = dsp.GEOMETRIES["320"]
+    wav = np.asarray(wav, dtype=np.float64)
+    c = np.sqrt(np.sum(wav ** 2.0) / len(wav))                              # :43
+    x = wav / c                                                             # :44
+    spec = dsp.stft(x, n_fft, win, hop).T                                   # :49   [T,161] complex64
+    mag, ph = np.abs(spec) ** p, np.angle(spec)                             # :53
+    feat = np.stack(((mag * np.cos(ph)).astype(np.float32), (mag * np.sin(ph)).astype(np.float32)))   # :55-56
+    with torch.no_grad():
+        est = _n.g2net_forward(sd, torch.from_numpy(feat)[None], cumulative)[-1].squeeze(0)   # :68-69  [2,F,T]
+    est = est.permute(0, 2, 1).numpy()                                      # :70  [2,T,F]
+    emag = np.sqrt(est[0] ** 2 + est[1] ** 2) ** (1.0 / p)                  # :76
+    eph = np.arctan2(est[1], est[0])
+    de = emag * np.cos(eph) + 1j * emag * np.sin(eph)                       # :77-83
+    y = dsp.istft(de.T, n_fft, win, hop, length=len(x))                     # :86-87
+    taps = {"c": 1.0 / c, "feat": feat, "est": est, "y_norm": y.astype(np.float32)}   # c in the sqrt(N/sum) convention
+    return (y * c).astype(np.float32), taps                                 # :88

@@ -17,7 +17,8 @@ WANTED = [("FullSubNet", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
           ("GCRN", "vb_gcrn_cprs_model.pth"), ("DPCRN", "vb_dpcrn_noncprs_model.pth"),
           ("CTSNet", "step1_vb_cts_noncprs_model_final.pth"), ("CTSNet", "step2_vb_cts_noncprs_model.pth"),
           ("CTSNet_new", "step1_vb_cts_cprs_model_final.pth"), ("CTSNet_new", "step2_vb_cts_cprs_model.pth"),
-          ("TaylorSENet", "vb_taylor_noncprs_model.pth"), ("TaylorSENet_new", "vb_taylor_cprs_model.pth")]
+          ("TaylorSENet", "vb_taylor_noncprs_model.pth"), ("TaylorSENet_new", "vb_taylor_cprs_model.pth"),
+          ("G2Net_new", "vb_gaf_cprs_model.pth"), ("G2Net_VB", "vb_gaf_noncprs_model.pth")]
 DEST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "checkpoints", "_ref")
 
 

@@ -322,6 +322,46 @@ def make_taylor():
               f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+G2_ARGS = (3, 64, 2, 4, 4, [1, 2, 5, 9], 256 + 161 * 2, 256, 256, (2, 3), (1, 3), 64, 'cat', 3)   # com_decode.py:23
+G2_KW = dict(is_aux=False, encoder_type='U2Net', tcm_type='full-band')
+G2_CASES = [
+    # name, model dir, checkpoint, samples, clip ids, p, cumulative
+    ("g2net_synth", "G2Net_new", None, 8000, (22, 23), 1.0, True),
+    ("g2net_new_ckpt", "G2Net_new", "vb_gaf_cprs_model.pth", 16000, (22, 23), 0.5, True),       # G2Net_new/com_decode.py
+    ("g2net_vb_ckpt", "G2Net_VB", "vb_gaf_noncprs_model.pth", 16000, (24, 25), 1.0, False),    # G2Net_VB/com_decode.py
+]
+
+
+def make_g2net():
+    """Fixtures from the UNMODIFIED G2Net_{new,VB}/gaf_net_320.py ``gaf_base`` module."""
+    for name, mdir, ckpt, nsamp, clip_ids, p, cum in G2_CASES:
+        net = ref_shims.import_reference(mdir, "gaf_net_320").gaf_base(*G2_ARGS, **G2_KW).eval()
+        if ckpt is None:
+            sd = synth.synthetic_state_dict(templates.g2net_template(cum), seed=0, gain=1.0)
+        else:
+            sd = torch.load(ref_shims.checkpoint_path(mdir, ckpt), map_location="cpu")
+        net.load_state_dict(sd)
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp), "p": np.array(p)}
+        worst = 0.0
+        for j, cid in enumerate(clip_ids):
+            wav = synth.noisy_clip(cid, nsamp)
+            y, taps = decode.enhance_g2net(sd, wav.astype(np.float64), p=p, cumulative=cum)
+            with torch.no_grad():
+                est_ref = net(torch.from_numpy(taps["feat"])[None])[-1].squeeze(0).permute(0, 2, 1).numpy()
+            worst = max(worst, float(np.abs(est_ref - taps["est"]).max()))
+            rec[f"wav{j}"] = wav
+            rec[f"feat{j}"] = taps["feat"]
+            rec[f"est{j}"] = est_ref.astype(np.float32)          # [2,T,F]
+            rec[f"ynorm{j}"] = taps["y_norm"]
+            rec[f"y{j}"] = y
+            rec[f"c{j}"] = np.array(taps["c"])
+        rec["ref_vs_oracle"] = np.array(worst)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: ref_vs_oracle max-abs {worst:.3e}, |est| max {float(np.abs(rec['est0']).max()):.2f}, out rms "
+              f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def sd_digest(sd) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
@@ -381,3 +421,5 @@ if __name__ == "__main__":
         make_ctsnet()
     if len(sys.argv) < 2 or sys.argv[1] == "taylor":
         make_taylor()
+    if len(sys.argv) < 2 or sys.argv[1] == "g2net":
+        make_g2net()

@@ -766,3 +766,77 @@ def taylorsenet_forward(sd, inputs, cumulative=False, order_num=3, taps=None):
         pre_term = update
         out = out + update / math.factorial(k + 1)
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# G2Net  (G2Net_new/gaf_net_320.py: cumulative LayerNorm; G2Net_VB/gaf_net_320.py: InstanceNorm)
+# configuration of com_decode.py:23: gaf_base(3, 64, 2, 4, 4, [1,2,5,9], 256+161*2, 256, 256, (2,3), (1,3), 64, 'cat', 3,
+# is_aux=False, encoder_type='U2Net', tcm_type='full-band')
+# ----------------------------------------------------------------------------------------
+G2_DILAS = (1, 2, 5, 9)
+
+
+def _g2_unet_module(x, sd, pre, scale, cum):
+    """En_unet_module (gaf_net_320.py:384-431): gated (2,3)/(2,5) in_conv (two convs, causal) + norm + PReLU, then a
+    U-Net of ``scale`` Conv2dunit / Deconv2dunit levels with k2 = (1,3) (no time kernel), intra 'cat', residual."""
+    r = _cts_gate_conv(x, sd, f"{pre}.in_conv.0", False)
+    r = F.prelu(_cts_norm(r, sd, f"{pre}.in_conv.1", cum), sd[f"{pre}.in_conv.2.weight"])
+    x, xs = r, []
+    for i in range(scale):
+        x = F.conv2d(x, sd[f"{pre}.enco.{i}.conv.0.weight"], sd[f"{pre}.enco.{i}.conv.0.bias"], stride=(1, 2))
+        x = F.prelu(_cts_norm(x, sd, f"{pre}.enco.{i}.conv.1", cum), sd[f"{pre}.enco.{i}.conv.2.weight"])
+        xs.append(x)
+    for i in range(scale):
+        if i > 0:
+            x = torch.cat((x, xs[-(i + 1)]), dim=1)
+        x = F.conv_transpose2d(x, sd[f"{pre}.deco.{i}.deconv.0.weight"], sd[f"{pre}.deco.{i}.deconv.0.bias"], stride=(1, 2))
+        x = F.prelu(_cts_norm(x, sd, f"{pre}.deco.{i}.deconv.1", cum), sd[f"{pre}.deco.{i}.deconv.2.weight"])
+    return r + x
+
+
+def _g2_glu(x, sd, pre, d, cum):
+    """Glu (gaf_net_320.py:245-274): single-branch squeezed TCM, k = 3, causal."""
+    u = F.conv1d(x, sd[f"{pre}.in_conv.weight"])
+    u = _cts_norm(F.prelu(u, sd[f"{pre}.left_conv.0.weight"]), sd, f"{pre}.left_conv.1", cum)
+    u = F.conv1d(F.pad(u, (2 * d, 0)), sd[f"{pre}.left_conv.3.weight"], None, dilation=d)
+    u = _cts_norm(F.prelu(u, sd[f"{pre}.out_conv.0.weight"]), sd, f"{pre}.out_conv.1", cum)
+    return F.conv1d(u, sd[f"{pre}.out_conv.2.weight"]) + x
+
+
+def _g2_tcm_head(x, sd, pre, cum, tcm_num=2):
+    """nn.Sequential(*Tcm_list x tcm_num, Conv1d(256, 161, 1)[, Sigmoid])  (:135-139, :170-177)."""
+    for i in range(tcm_num):
+        for j, d in enumerate(G2_DILAS):
+            x = _g2_glu(x, sd, f"{pre}.{i}.tcm_list.{j}", d, cum)
+    return F.conv1d(x, sd[f"{pre}.{tcm_num}.weight"], sd[f"{pre}.{tcm_num}.bias"])
+
+
+def g2net_forward(sd, inpt, cumulative=True, stage_num=3, taps=None):
+    """gaf_base.forward, gaf_net_320.py:73-87 (is_aux=False).  inpt [B,2,T,161] -> list of stage outputs [B,2,161,T]."""
+    cum = cumulative
+    b, _, t, _ = inpt.shape
+    x = inpt
+    for i, scale in enumerate((4, 3, 2, 1)):                                 # U2Net_Encoder :277-303
+        x = _g2_unet_module(x, sd, f"en.meta_unet_list.{i}", scale, cum)
+    x = _cts_gate_conv(x, sd, "en.last_conv.0", False)
+    x = F.prelu(_cts_norm(x, sd, "en.last_conv.1", cum), sd["en.last_conv.2.weight"])
+    feat = x.transpose(-2, -1).contiguous().view(b, -1, t)
+    if taps is not None:
+        taps["feat"] = feat
+    pre_x = inpt.transpose(-2, -1).contiguous()                              # [B,2,F,T]
+    outs = []
+    for s in range(stage_num):                                               # GAF_module.forward :104-115
+        g = f"gafs.{s}"
+        pre_mag, pre_phase = torch.norm(pre_x, dim=1), torch.atan2(pre_x[:, -1], pre_x[:, 0])
+        xin = torch.cat((feat, pre_x.view(b, -1, t)), 1)
+        gb, fb = g + ".glance_branch", g + ".focus_branch"
+        xg = F.conv1d(xin, sd[gb + ".in_conv_main.weight"], sd[gb + ".in_conv_main.bias"]) * \
+            torch.sigmoid(F.conv1d(xin, sd[gb + ".in_conv_gate.0.weight"], sd[gb + ".in_conv_gate.0.bias"]))
+        gain = torch.sigmoid(_g2_tcm_head(xg, sd, gb + ".mstcm_filter", cum))
+        xf = F.conv1d(xin, sd[fb + ".in_conv_main.weight"], sd[fb + ".in_conv_main.bias"]) * \
+            torch.sigmoid(F.conv1d(xin, sd[fb + ".in_conv_gate.0.weight"], sd[fb + ".in_conv_gate.0.bias"]))
+        resi = torch.stack((_g2_tcm_head(xf, sd, fb + ".mstcm_r", cum), _g2_tcm_head(xf, sd, fb + ".mstcm_i", cum)), 1)
+        x_mag = pre_mag * gain
+        pre_x = torch.stack((x_mag * torch.cos(pre_phase), x_mag * torch.sin(pre_phase)), 1) + resi
+        outs.append(pre_x)
+    return outs

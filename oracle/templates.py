@@ -235,3 +235,13 @@ def taylorsenet_template(cumulative=False):
     name = "taylor_new_keys.json" if cumulative else "taylor_keys.json"
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), name)) as f:
         return {k: tuple(v) for k, v in json.load(f).items()}
+
+
+def g2net_template(cumulative=True):
+    """G2Net_new/gaf_net_320.py:10-71 (cumulative LayerNorm) / G2Net_VB (InstanceNorm) in the configuration of
+    com_decode.py:23 (825 entries; recorded from the reference module in oracle/g2net_*_keys.json)."""
+    import json
+    import os
+    name = "g2net_new_keys.json" if cumulative else "g2net_vb_keys.json"
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), name)) as f:
+        return {k: tuple(v) for k, v in json.load(f).items()}

@@ -14,5 +14,6 @@ from .dpcrn import dpcrn                   # noqa: F401
 from . import gcrn                         # noqa: F401  (gcrn.Net, as GCRN/GCRN_noncprs.py names it)
 from . import ctsnet                       # noqa: F401  (ctsnet.Step1_net / ctsnet.Step2_net)
 from .taylor import TaylorSENet            # noqa: F401
+from . import g2net                        # noqa: F401  (g2net.gaf_base)
 
-__all__ = ["crn_net", "lstm_net", "fullsubnet", "DCCRN", "Uformer", "gcrn", "dpcrn", "ctsnet", "TaylorSENet", "ops", "decode", "packing", "shard"]
+__all__ = ["crn_net", "lstm_net", "fullsubnet", "DCCRN", "Uformer", "gcrn", "dpcrn", "ctsnet", "TaylorSENet", "g2net", "ops", "decode", "packing", "shard"]

@@ -84,6 +84,7 @@ PROTOTYPES = {
     "se_chan_norm": (_I, [_P, _I, _LL, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
     "se_add": (_I, [_P, _P, _LL, _P, _P, _P, _P]),
     "se_axpby": (_I, [_P, _P, _F, _F, _LL, _P, _P, _P, _P]),
+    "se_gaf_update": (_I, [_P, _P, _LL, _I, _P, _P, _LL, _I, _I, _I, _P, _P, _P, _P]),
     "se_taylor_zero": (_I, [_P, _P, _LL, _I, _I, _P, _P, _P, _P]),
     "se_cts_glue1": (_I, [_P, _P, _LL, _P, _P]),
     "se_cts_glue2": (_I, [_P, _P, _P, _LL, _P, _P]),

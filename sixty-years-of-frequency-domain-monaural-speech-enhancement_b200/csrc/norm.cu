@@ -281,6 +281,38 @@ __global__ void __launch_bounds__(NT) taylor_zero_kernel(const float2* __restric
   }
 }
 
+// G2Net stage update (G2Net_new/gaf_net_320.py:104-115): x' = gain * |pre| * (cos, sin)(angle pre) + com_resi, with
+// every complex tensor held as "RI rows" [rows, ld]: re at column 0, im at column im_off, zeros elsewhere.  pre is read
+// through (pointer, row stride, element stride) so that the very first stage can read the channels-last network input
+// [rows, F, 2] directly.  gain == NULL: plain relayout of pre into RI rows (feature for the first in_conv GEMM).
+__global__ void __launch_bounds__(NT) gaf_update_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im,
+                                                       long long xs_r, int xs_f, const float* __restrict__ gain,
+                                                       const float* __restrict__ resi, long long rows, int F, int ld,
+                                                       int im_off, float* __restrict__ out, float* __restrict__ out_hi,
+                                                       float* __restrict__ out_lo) {
+  const long long n = rows * ld;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const long long r = i / ld;
+    const int c = (int)(i - r * ld);
+    float y = 0.f;
+    const bool is_re = c < F, is_im = c >= im_off && c < im_off + F;
+    if (is_re || is_im) {
+      const int f = is_re ? c : c - im_off;
+      const float re = __ldg(x_re + r * xs_r + (long long)f * xs_f), im = __ldg(x_im + r * xs_r + (long long)f * xs_f);
+      if (gain) {
+        const float mag = sqrtf(re * re + im * im);             // torch.norm(pre_x, dim=1)
+        const float ph = atan2f(im, re);
+        const float xm = mag * __ldg(gain + r * F + f);
+        y = (is_re ? xm * cosf(ph) : xm * sinf(ph)) + __ldg(resi + i);
+      } else {
+        y = is_re ? re : im;
+      }
+    }
+    if (out) out[i] = y;
+    if (out_hi) split_tf32_dev(y, out_hi[i], out_lo[i]);
+  }
+}
+
 static int grid_for(long long n) {
   long long g = (n + NT - 1) / NT;
   return (int)(g < 148 * 16 ? (g < 1 ? 1 : g) : 148 * 16);
@@ -404,4 +436,16 @@ extern "C" int se_cts_glue2(const float* out_r, const float* out_i, const float*
   cts_glue2_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(out_r, out_i, reinterpret_cast<const float4*>(s2_in), n,
                                                                  reinterpret_cast<float2*>(est));
   return check_launch("se_cts_glue2");
+}
+
+extern "C" int se_gaf_update(const float* x_re, const float* x_im, long long xs_r, int xs_f, const float* gain,
+                             const float* resi, long long rows, int F, int ld, int im_off, float* out, float* out_hi,
+                             float* out_lo, se_stream_t stream) {
+  SE_REQUIRE(x_re && x_im && (out || out_hi) && rows > 0 && F > 0 && im_off >= F && ld >= im_off + F,
+             "se_gaf_update: bad arguments");
+  SE_REQUIRE((gain == nullptr) == (resi == nullptr), "se_gaf_update: gain and resi go together");
+  SE_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "se_gaf_update: out_hi/out_lo go together");
+  gaf_update_kernel<<<grid_for(rows * ld), NT, 0, (cudaStream_t)stream>>>(x_re, x_im, xs_r, xs_f, gain, resi, rows, F, ld,
+                                                                          im_off, out, out_hi, out_lo);
+  return check_launch("se_gaf_update");
 }

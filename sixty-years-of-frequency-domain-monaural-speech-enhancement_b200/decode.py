@@ -206,6 +206,30 @@ def enhance_taylorsenet(model, wav, p=1.0, taps=None):
 
 
 @torch.no_grad()
+def enhance_g2net(model, wav, p=0.5, taps=None):
+    """G2Net_new/com_decode.py:36-88 (p = 0.5; 1.0 for G2Net_VB): x / sqrt(sum x^2 / N) (the reciprocal spelling of the
+    same RMS scale), STFT (compressed RI), gaf_base forward, last stage decompressed (rule (ii)), iSTFT(length=N), * c.
+    wav [B,N] float32 CUDA -> [B,N]."""
+    if not wav.is_cuda:
+        raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+    from .g2net import IM_OFF, N_BINS, RI_LD
+    n_fft, win, hop = GEOM_320
+    wav = wav.contiguous().float()
+    b, n = wav.shape
+    t, f = 1 + n // hop, n_fft // 2 + 1
+    c, inv_c = ops.rms_scale(wav)                    # c = sqrt(N / sum x^2) = 1 / (the script's c); inv_c = the script's c
+    x = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)
+    ops.stft(wav, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p)
+    rows = model.forward_nhwc(x, taps).view(b, t, RI_LD)
+    out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
+    ops.istft(ISTFT_RI_DECOMP, rows[..., :N_BINS], rows[..., IM_OFF:IM_OFF + N_BINS], None, None, n_fft, win, hop, out, n,
+              out_scale=inv_c, inv_p=1.0 / p)
+    if taps is not None:
+        taps.update(c=c, x=x, est=rows)
+    return out
+
+
+@torch.no_grad()
 def enhance_fullsubnet(model, wav, p=0.5, taps=None):
     """FullSubNet/fullsubnet_sa_decode.py:44-78: |X|^p magnitude in, complex mask out, mask applied
     to the COMPRESSED spectrum, decompressed, iSTFT(length=N), / c  (backend rule (iii)).

@@ -661,6 +661,21 @@ def taylor_zero(x_ri, gain, ld, want_pair=True):
     return out, pair
 
 
+def gaf_update(x_re, x_im, xs_r, xs_f, gain, resi, rows, f, ld, im_off, want_f32=True, want_pair=True):
+    """G2Net stage update on RI rows (see se_gaf_update).  x_re / x_im: tensors whose data_ptr is element (0, 0) of the
+    real / imaginary plane of ``pre``; gain [rows, F] and resi [rows, ld] or both None (relayout only)."""
+    _need_cuda(x_re, x_im, gain, resi)
+    device_check()
+    out = torch.empty(rows, ld, device=x_re.device, dtype=torch.float32) if want_f32 else None
+    pair = (torch.empty(rows, ld, device=x_re.device, dtype=torch.float32),
+            torch.empty(rows, ld, device=x_re.device, dtype=torch.float32)) if want_pair else None
+    with _Timed("gaf_update"):
+        check(_lib.load().se_gaf_update(_ptr(x_re), _ptr(x_im), xs_r, xs_f, _ptr(gain), _ptr(resi), rows, f, ld, im_off,
+                                        _ptr(out), _ptr(pair[0] if pair else None), _ptr(pair[1] if pair else None),
+                                        _stream()), "se_gaf_update")
+    return out, pair
+
+
 def cts_glue1(x_ri, est_mag):
     """x_ri [B,T,F,2] noisy (compressed) RI, est_mag [B,T,F] -> s2_in [B,T,F,4] (two_stage_com_decode_vb.py:79-82)."""
     _need_cuda(x_ri, est_mag)

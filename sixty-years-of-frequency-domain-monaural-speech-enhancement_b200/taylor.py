@@ -48,7 +48,80 @@ def _keys(cumulative):
         return json.load(f)
 
 
-class TaylorSENet(_CtsBase):
+class _U2Base(_CtsBase):
+    """U2-Net machinery shared by TaylorSENet and G2Net: gated convs, En_unet_module, the encoder loop."""
+
+    def _inner_taps(self):
+        """Tap tables of the inner Conv2dunit / Deconv2dunit levels (k2 = (2,3) here; G2Net overrides with (1,3))."""
+        return packing.CONV23_TAPS, DEC23_EVEN, DEC23_ODD
+
+    def _plain_block(self, tmp, b, t, f, c, gamma, beta, slope, want_f32, want_pair):
+        st = self._stats(tmp, b, t, f, c, "none")
+        f32, pair = self._norm(tmp, b, t, f, c, st, gamma, beta, "none", post="prelu", post_slope=slope,
+                               want_f32=want_f32, want_pair=want_pair)
+        v = lambda z: z.view(b, t, f, c)      # noqa: E731
+        return Act(v(f32) if f32 is not None else None, (v(pair[0]), v(pair[1])) if pair is not None else None)
+
+    def _gate_conv(self, src, skip, b, t, fin, packed, transpose, kf_full):
+        """Runs the (parity classes of the) gated conv into a fresh [B,T,fout,2C] fp32 tensor."""
+        classes, bias = packed
+        dev = (src.f32 if src.f32 is not None else src.pair[0]).device
+        if not transpose:
+            fout = (fin - kf_full) // 2 + 1
+            w, tp = classes[0]
+            tmp = Act(torch.empty(b, t, fout, w.cout, device=dev, dtype=torch.float32))
+            conv_engine.conv(src, skip, b, t, fin, fout, tp, 2, w, bias, "none", tmp, fout)
+            return tmp.f32, fout
+        fout = 2 * (fin - 1) + kf_full
+        tmp = Act(torch.empty(b, t, fout, classes[0][0].cout, device=dev, dtype=torch.float32))
+        for par, (w, tp) in enumerate(classes):
+            conv_engine.conv(src, skip, b, t, fin, (fout - par + 1) // 2, tp, 1, w, bias, "none", tmp, fout, dst_f0=par,
+                             dst_fstep=2)
+        return tmp.f32, fout
+
+    def _module(self, src, skip, b, t, fin, name, kf_in, want_f32=False):
+        """En_unet_module.forward (:480-496).  Returns (Act, fout)."""
+        m = self._packed[name]
+        tmp, f0 = self._gate_conv(src, skip, b, t, fin, m["in"], m["transpose"], kf_in)
+        r = self._gated_block(tmp, b, t, f0, 64, *m["in_norm"], m["in_slope"], want_f32=True, want_pair=True)
+        x, xs, f = r, [], f0
+        dev = tmp.device
+        enc_taps, dec_even, dec_odd = self._inner_taps()
+        for j in range(m["scale"]):                                                   # Conv2dunit
+            w, bias, gamma, beta, slope = m["enco"][j]
+            f2 = (f - 3) // 2 + 1
+            tmp = Act(torch.empty(b, t, f2, 64, device=dev, dtype=torch.float32))
+            conv_engine.conv(x, None, b, t, f, f2, enc_taps, 2, w, bias, "none", tmp, f2)
+            x = self._plain_block(tmp.f32, b, t, f2, 64, gamma, beta, slope, want_f32=False, want_pair=True)
+            xs.append(x)
+            f = f2
+        for j in range(m["scale"]):                                                   # Deconv2dunit (+ intra 'cat')
+            even, odd, bias, gamma, beta, slope = m["deco"][j]
+            sk = xs[-(j + 1)] if j > 0 else None
+            f2 = 2 * f + 1
+            tmp = Act(torch.empty(b, t, f2, 64, device=dev, dtype=torch.float32))
+            conv_engine.conv(x, sk, b, t, f, f + 1, dec_even, 1, even, bias, "none", tmp, f2, dst_f0=0, dst_fstep=2)
+            conv_engine.conv(x, sk, b, t, f, f, dec_odd, 1, odd, bias, "none", tmp, f2, dst_f0=1, dst_fstep=2)
+            last = j == m["scale"] - 1
+            x = self._plain_block(tmp.f32, b, t, f2, 64, gamma, beta, slope, want_f32=last, want_pair=not last)
+            f = f2
+        assert f == f0
+        f32, pair = ops.add(r.f32, x.f32, want_f32=want_f32, want_pair=True)          # x_resi + x  (:494)
+        return Act(f32, pair), f0
+
+    def _u2_encoder(self, x, b, t, name, want_last_f32, taps=None):
+        h, f, outs = Act(x), N_BINS, []
+        for i in range(4):
+            h, f = self._module(h, None, b, t, f, f"{name}{i}", 5 if i == 0 else 3)
+            outs.append(h)
+        packed, (gamma, beta), slope = self._packed[f"{name}_last"]
+        tmp, f = self._gate_conv(h, None, b, t, f, packed, False, 3)
+        h = self._gated_block(tmp, b, t, f, 64, gamma, beta, slope, want_f32=want_last_f32, want_pair=True)
+        outs.append(h)
+        return outs
+
+
+class TaylorSENet(_U2Base):
     def __init__(self, cin=2, k1=(1, 3), k2=(2, 3), c=64, kd1=5, cd1=64, d_feat=256, dilations=(1, 2, 5, 9), p=2,
                  fft_num=320, order_num=3, intra_connect="cat", inter_connect="cat", is_causal=True,
                  is_conformer=False, is_u2=True, is_param_share=False, is_encoder_share=False, cumulative=False):
@@ -140,70 +213,6 @@ class TaylorSENet(_CtsBase):
         self._packed = P
 
     # -- runners ---------------------------------------------------------------------------------
-    def _plain_block(self, tmp, b, t, f, c, gamma, beta, slope, want_f32, want_pair):
-        st = self._stats(tmp, b, t, f, c, "none")
-        f32, pair = self._norm(tmp, b, t, f, c, st, gamma, beta, "none", post="prelu", post_slope=slope,
-                               want_f32=want_f32, want_pair=want_pair)
-        v = lambda z: z.view(b, t, f, c)      # noqa: E731
-        return Act(v(f32) if f32 is not None else None, (v(pair[0]), v(pair[1])) if pair is not None else None)
-
-    def _gate_conv(self, src, skip, b, t, fin, packed, transpose, kf_full):
-        """Runs the (parity classes of the) gated conv into a fresh [B,T,fout,2C] fp32 tensor."""
-        classes, bias = packed
-        dev = (src.f32 if src.f32 is not None else src.pair[0]).device
-        if not transpose:
-            fout = (fin - kf_full) // 2 + 1
-            w, tp = classes[0]
-            tmp = Act(torch.empty(b, t, fout, w.cout, device=dev, dtype=torch.float32))
-            conv_engine.conv(src, skip, b, t, fin, fout, tp, 2, w, bias, "none", tmp, fout)
-            return tmp.f32, fout
-        fout = 2 * (fin - 1) + kf_full
-        tmp = Act(torch.empty(b, t, fout, classes[0][0].cout, device=dev, dtype=torch.float32))
-        for par, (w, tp) in enumerate(classes):
-            conv_engine.conv(src, skip, b, t, fin, (fout - par + 1) // 2, tp, 1, w, bias, "none", tmp, fout, dst_f0=par,
-                             dst_fstep=2)
-        return tmp.f32, fout
-
-    def _module(self, src, skip, b, t, fin, name, kf_in, want_f32=False):
-        """En_unet_module.forward (:480-496).  Returns (Act, fout)."""
-        m = self._packed[name]
-        tmp, f0 = self._gate_conv(src, skip, b, t, fin, m["in"], m["transpose"], kf_in)
-        r = self._gated_block(tmp, b, t, f0, 64, *m["in_norm"], m["in_slope"], want_f32=True, want_pair=True)
-        x, xs, f = r, [], f0
-        dev = tmp.device
-        for j in range(m["scale"]):                                                   # Conv2dunit
-            w, bias, gamma, beta, slope = m["enco"][j]
-            f2 = (f - 3) // 2 + 1
-            tmp = Act(torch.empty(b, t, f2, 64, device=dev, dtype=torch.float32))
-            conv_engine.conv(x, None, b, t, f, f2, packing.CONV23_TAPS, 2, w, bias, "none", tmp, f2)
-            x = self._plain_block(tmp.f32, b, t, f2, 64, gamma, beta, slope, want_f32=False, want_pair=True)
-            xs.append(x)
-            f = f2
-        for j in range(m["scale"]):                                                   # Deconv2dunit (+ intra 'cat')
-            even, odd, bias, gamma, beta, slope = m["deco"][j]
-            sk = xs[-(j + 1)] if j > 0 else None
-            f2 = 2 * f + 1
-            tmp = Act(torch.empty(b, t, f2, 64, device=dev, dtype=torch.float32))
-            conv_engine.conv(x, sk, b, t, f, f + 1, DEC23_EVEN, 1, even, bias, "none", tmp, f2, dst_f0=0, dst_fstep=2)
-            conv_engine.conv(x, sk, b, t, f, f, DEC23_ODD, 1, odd, bias, "none", tmp, f2, dst_f0=1, dst_fstep=2)
-            last = j == m["scale"] - 1
-            x = self._plain_block(tmp.f32, b, t, f2, 64, gamma, beta, slope, want_f32=last, want_pair=not last)
-            f = f2
-        assert f == f0
-        f32, pair = ops.add(r.f32, x.f32, want_f32=want_f32, want_pair=True)          # x_resi + x  (:494)
-        return Act(f32, pair), f0
-
-    def _u2_encoder(self, x, b, t, name, want_last_f32, taps=None):
-        h, f, outs = Act(x), N_BINS, []
-        for i in range(4):
-            h, f = self._module(h, None, b, t, f, f"{name}{i}", 5 if i == 0 else 3)
-            outs.append(h)
-        packed, (gamma, beta), slope = self._packed[f"{name}_last"]
-        tmp, f = self._gate_conv(h, None, b, t, f, packed, False, 3)
-        h = self._gated_block(tmp, b, t, f, 64, gamma, beta, slope, want_f32=want_last_f32, want_pair=True)
-        outs.append(h)
-        return outs
-
     def _tcms(self, x, b, t, prefix):
         for i in range(self.p):
             for j in range(len(DILATIONS)):

@@ -138,7 +138,11 @@ def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, n_out, act="none", out=None):
     y = (a_hi + a_lo) @ (b_hi + b_lo).t()
     if bias is not None:
         y = y + bias
-    return _act(y, act)
+    y = _act(y, act)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 def lstm_cell_tf32x3(x_hi, x_lo, h_hi, h_lo, w_hi, w_lo, bias, c_state, h_hi_out, h_lo_out, h_out=None):
@@ -394,6 +398,21 @@ def taylor_zero(x_ri, gain, ld, want_pair=True):
     return out, (packing.split_tf32(out) if want_pair else None)
 
 
+def gaf_update(x_re, x_im, xs_r, xs_f, gain, resi, rows, f, ld, im_off, want_f32=True, want_pair=True):
+    from se_b200 import packing
+    re = torch.as_strided(x_re, (rows, f), (xs_r, xs_f))
+    im = torch.as_strided(x_im, (rows, f), (xs_r, xs_f))
+    out = torch.zeros(rows, ld, dtype=re.dtype)
+    if gain is None:
+        out[:, :f], out[:, im_off:im_off + f] = re, im
+    else:
+        mag, ph = torch.sqrt(re * re + im * im), torch.atan2(im, re)
+        xm = mag * gain.reshape(rows, f)
+        out[:, :f] = xm * torch.cos(ph) + resi[:, :f]
+        out[:, im_off:im_off + f] = xm * torch.sin(ph) + resi[:, im_off:im_off + f]
+    return (out if want_f32 else None), (packing.split_tf32(out) if want_pair else None)
+
+
 def cts_glue1(x_ri, est_mag):
     ph = torch.atan2(x_ri[..., 1], x_ri[..., 0])
     return torch.stack([x_ri[..., 0], x_ri[..., 1], est_mag * torch.cos(ph), est_mag * torch.sin(ph)], -1)
@@ -403,7 +422,7 @@ def cts_glue2(out_r, out_i, s2_in):
     return torch.stack([out_r + s2_in[..., 2], out_i + s2_in[..., 3]], -1)
 
 
-_NORM_NAMES = ("chan_stats", "cum_stats", "chan_norm", "add", "axpby", "taylor_zero", "cts_glue1", "cts_glue2")
+_NORM_NAMES = ("chan_stats", "cum_stats", "chan_norm", "add", "axpby", "taylor_zero", "gaf_update", "cts_glue1", "cts_glue2")
 _orig_install2 = install
 
 

@@ -538,3 +538,13 @@ def test_cum_stats_2d_and_cts_glue():
     ref_rows, _ = emu_ops.taylor_zero(xr, gain, 352)
     assert (rows.cpu() - ref_rows).abs().max() < 2e-6 and ((rp[0] + rp[1]).cpu() - ref_rows).abs().max() < 2e-6
     assert rows[:, 322:].abs().max().item() == 0.0
+    # G2Net stage update on RI rows (re at 0, im at 176): relayout of the channels-last input, then gain / residual
+    n = b * t
+    r0, p0 = ops.gaf_update(xr.to(dev), xr.to(dev)[..., 1], 322, 2, None, None, n, 161, 352, 176)
+    e0, _ = emu_ops.gaf_update(xr, xr[..., 1], 322, 2, None, None, n, 161, 352, 176)
+    assert torch.equal(r0.cpu(), e0)
+    resi = torch.zeros(n, 352)
+    resi[:, :161], resi[:, 176:337] = torch.randn(n, 161, generator=g), torch.randn(n, 161, generator=g)
+    r1, p1 = ops.gaf_update(r0, r0[:, 176:], 352, 1, gain.to(dev).view(n, 161), resi.to(dev), n, 161, 352, 176)
+    e1, _ = emu_ops.gaf_update(e0, e0[:, 176:], 352, 1, gain.view(n, 161), resi, n, 161, 352, 176)
+    assert (r1.cpu() - e1).abs().max() < 2e-6 and ((p1[0] + p1[1]).cpu() - e1).abs().max() < 2e-6

@@ -387,3 +387,36 @@ def test_taylorsenet_matches_golden(name):
           f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
     assert (rms.max() <= RMS_GATE or rel.max() <= 1e-5) and rel.max() <= 2e-3
     assert binv < 1e-5 * max(1.0, float(np.abs(refn).max()))
+
+
+@pytest.mark.parametrize("name", ["g2net_synth", "g2net_new_ckpt", "g2net_vb_ckpt"])
+def test_g2net_matches_golden(name):
+    """G2Net ``gaf_base`` (cumulative LayerNorm / InstanceNorm twins) vs the UNMODIFIED reference
+    module, and the decoded waveform vs the restated com_decode.py (reciprocal RMS-scale convention)."""
+    dev = _dev()
+    import se_b200
+    from test_oracle_nets import load_g2net_case
+    g, sd, p, cum = load_g2net_case(name)
+    model = se_b200.g2net.gaf_base(3, 64, 2, 4, 4, [1, 2, 5, 9], 256 + 161 * 2, 256, 256, (2, 3), (1, 3), 64, 'cat', 3,
+                                   is_aux=False, encoder_type='U2Net', tcm_type='full-band', cumulative=cum)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    k = len(g["clip_ids"])
+    feat = torch.from_numpy(np.stack([g[f"feat{j}"] for j in range(k)])).to(dev)        # [B,2,T,161]
+    est = model(feat)[-1].permute(0, 1, 3, 2).cpu().numpy()                             # [B,2,T,F]
+    ref = np.stack([g[f"est{j}"] for j in range(k)])
+    e_net = np.abs(est - ref).max()
+    wav = torch.from_numpy(np.stack([g[f"wav{j}"] for j in range(k)])).to(dev)
+    taps = {}
+    y = se_b200.decode.enhance_g2net(model, wav, p=p, taps=taps)
+    c = taps["c"].cpu().numpy()
+    yn = y.cpu().numpy() * c[:, None]
+    refn = np.stack([g[f"ynorm{j}"] for j in range(k)])
+    rms = np.sqrt(np.mean((yn - refn) ** 2, axis=1))
+    rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
+    y1 = se_b200.decode.enhance_g2net(model, wav[1:2], p=p)
+    binv = (y[1:2] - y1).abs().max().item()
+    print(f"{name}: net max-abs {e_net:.3e} (|est| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
+          f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
+    assert (rms.max() <= RMS_GATE or rel.max() <= 1e-5) and rel.max() <= 2e-3
+    assert binv < 1e-5 * max(1.0, float(np.abs(refn).max()))

@@ -278,3 +278,27 @@ def test_taylorsenet_host_logic_matches_oracle(monkeypatch, cum):
     assert (est - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
     with pytest.raises(NotImplementedError):
         se_b200.TaylorSENet(order_num=2)
+
+
+@pytest.mark.parametrize("cum", [True, False])
+def test_g2net_host_logic_matches_oracle(monkeypatch, cum):
+    """G2Net_new / G2Net_VB: U2-Net encoder with k(1,3) inner units, the split 578-wide in_conv GEMMs with stacked
+    main | gate outputs, single-branch Glu TCMs, gain / residual heads written into RI rows, the stage update."""
+    emu_ops.install(se_b200.ops, monkeypatch)
+    t = templates.g2net_template(cum)
+    sd = synth.synthetic_state_dict(t, seed=8, gain=1.0)
+    m = se_b200.g2net.gaf_base(3, 64, 2, 4, 4, [1, 2, 5, 9], 256 + 161 * 2, 256, 256, (2, 3), (1, 3), 64, 'cat', 3,
+                               is_aux=False, encoder_type='U2Net', tcm_type='full-band', cumulative=cum)
+    assert list(m.state_dict().keys()) == list(t.keys())
+    m.load_state_dict(sd)
+    x = torch.randn(2, 2, 21, 161, generator=torch.Generator().manual_seed(5))
+    taps, rtaps = {}, {}
+    est = m._forward_impl(x, taps)
+    with torch.no_grad():
+        ref = nets.g2net_forward(sd, x, cum, taps=rtaps)
+    assert (taps["feat"].permute(0, 3, 2, 1).reshape(2, 256, 21) - rtaps["feat"]).abs().max() < 1e-5
+    assert len(est) == 3
+    for a, r in zip(est, ref):
+        assert a.shape == r.shape and (a - r).abs().max() < 2e-5 * max(1.0, r.abs().max().item())
+    with pytest.raises(NotImplementedError):
+        se_b200.g2net.gaf_base(is_aux=True)

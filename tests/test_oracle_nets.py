@@ -176,3 +176,46 @@ def test_taylorsenet_oracle_equals_reference_module(mdir, cum):
     x = torch.randn(2, 2, 19, 161, generator=torch.Generator().manual_seed(6))
     with torch.no_grad():
         assert (net(x) - nets.taylorsenet_forward(sd, x, cum)).abs().max() < 1e-5
+
+
+G2_CKPTS = {"g2net_new_ckpt": "G2Net_new__vb_gaf_cprs_model.pth", "g2net_vb_ckpt": "G2Net_VB__vb_gaf_noncprs_model.pth"}
+
+
+def load_g2net_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cum = "_vb" not in name
+    if name in G2_CKPTS:
+        path = os.path.join(CKPT_DIR, G2_CKPTS[name])
+        if not os.path.exists(path):
+            pytest.skip("checkpoint copy not present (oracle/fetch_checkpoints.py)")
+        sd = torch.load(path, map_location="cpu")
+    else:
+        sd = synth.synthetic_state_dict(templates.g2net_template(cum), seed=0, gain=1.0)
+    return g, sd, float(g["p"]), cum
+
+
+@pytest.mark.parametrize("name", ["g2net_synth", "g2net_new_ckpt", "g2net_vb_ckpt"])
+def test_g2net_oracle_reproduces_golden(name):
+    g, sd, p, cum = load_g2net_case(name)
+    assert sd_digest(sd) == str(g["digest"])
+    assert float(g["ref_vs_oracle"]) < 1e-4
+    for j in range(len(g["clip_ids"])):
+        wav = synth.noisy_clip(int(g["clip_ids"][j]), int(g["nsamp"]))
+        assert np.array_equal(wav, g[f"wav{j}"])
+        y, taps = decode.enhance_g2net(sd, wav.astype(np.float64), p=p, cumulative=cum)
+        assert np.abs(taps["est"] - g[f"est{j}"]).max() < 1e-4 * max(1.0, np.abs(g[f"est{j}"]).max())
+        assert np.sqrt(np.mean((taps["y_norm"] - g[f"ynorm{j}"]) ** 2)) < 2e-6
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("mdir,cum", [("G2Net_new", True), ("G2Net_VB", False)])
+def test_g2net_oracle_equals_reference_module(mdir, cum):
+    from oracle.make_golden import G2_ARGS, G2_KW
+    net = ref_shims.import_reference(mdir, "gaf_net_320").gaf_base(*G2_ARGS, **G2_KW).eval()
+    sd = synth.synthetic_state_dict(templates.g2net_template(cum), seed=4, gain=1.0)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd)
+    x = torch.randn(2, 2, 19, 161, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        for a, b in zip(net(x), nets.g2net_forward(sd, x, cum)):
+            assert (a - b).abs().max() < 1e-5

@@ -37,6 +37,9 @@ CASES = {
                se_b200.decode.enhance_ctsnet, odecode.enhance_ctsnet, 64, 4, 160, dict(p=1.0)),
     "taylor": (lambda: se_b200.TaylorSENet(), templates.taylorsenet_template, se_b200.decode.enhance_taylorsenet,
                odecode.enhance_taylorsenet, 64, 4, 160, dict(p=1.0)),
+    "g2net": (lambda: se_b200.g2net.gaf_base(3, 64, 2, 4, 4, [1, 2, 5, 9], 256 + 161 * 2, 256, 256, (2, 3), (1, 3), 64, 'cat',
+                                             3, is_aux=False, encoder_type='U2Net', tcm_type='full-band'),
+              templates.g2net_template, se_b200.decode.enhance_g2net, odecode.enhance_g2net, 64, 4, 160, dict(p=0.5)),
     "uformer": (lambda: se_b200.Uformer(), templates.uformer_template, se_b200.decode.enhance_uformer, None,
                 64, 4, 160, dict()),
 }
@@ -55,7 +58,7 @@ def main():
                 m.load_state_dict(s)
                 m.eval().cuda()
         else:
-            sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name in ("uformer", "dpcrn", "taylor") else 2.0)
+            sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0 if name in ("uformer", "dpcrn", "taylor", "g2net") else 2.0)
             model = ctor()
             model.load_state_dict(sd)
             model.eval().cuda()
