@@ -101,6 +101,108 @@ __global__ void __launch_bounds__(NT) chan_stats_kernel(const float* __restrict_
   if (tid == 0) ticket[b] = 0u;
 }
 
+
+// four consecutive channels of pre(x) at once (C, Cin multiples of 4; 16-byte loads)
+__device__ __forceinline__ void pre_value4(const float* __restrict__ xr, int c, int Cin, int C, int pre,
+                                           const float* __restrict__ slope, float (&v)[4]) {
+  float4 a, g = make_float4(0.f, 0.f, 0.f, 0.f), sl = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool glu = pre == SE_NORM_PRE_GLU || pre == SE_NORM_PRE_GLU_PRELU;
+  const bool pr = pre == SE_NORM_PRE_PRELU || pre == SE_NORM_PRE_GLU_PRELU;
+  a = __ldg(reinterpret_cast<const float4*>(xr + (glu ? c : c % Cin)));
+  if (glu) g = __ldg(reinterpret_cast<const float4*>(xr + C + c));
+  if (pr) sl = __ldg(reinterpret_cast<const float4*>(slope + c));
+  const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w}, sv[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float t = av[e];
+    if (glu) t *= sigmoid_f(gv[e]);
+    if (pr) t = prelu_f(t, sv[e]);
+    v[e] = t;
+  }
+}
+
+// pass 1, instance statistics, 4 channels per thread: thread tid owns channels 4*(tid % C4) .. +3 and row lane tid / C4
+__global__ void __launch_bounds__(NT) chan_stats_vec_kernel(const float* __restrict__ x, long long rows, int Cin, int C,
+                                                           int pre, const float* __restrict__ slope, float eps,
+                                                           float* __restrict__ mean, float* __restrict__ rstd,
+                                                           double* __restrict__ partial, unsigned* __restrict__ ticket) {
+  __shared__ double sh[NT][8];
+  __shared__ bool last;
+  const int tid = threadIdx.x, b = blockIdx.y, chunks = gridDim.x;
+  const int C4 = C >> 2, lanes = NT / C4, cq = tid % C4, lane = tid / C4;
+  const long long per = (rows + chunks - 1) / chunks;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(rows, r0 + per);
+  const float* xb = x + (long long)b * rows * Cin;
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  {
+    float fs[4] = {0, 0, 0, 0}, fss[4] = {0, 0, 0, 0};
+    int n = 0;
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+      float v[4];
+      pre_value4(xb + r * Cin, 4 * cq, Cin, C, pre, slope, v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        fs[e] += v[e];
+        fss[e] = fmaf(v[e], v[e], fss[e]);
+      }
+      if (++n == 64) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s[e] += fs[e];
+          ss[e] += fss[e];
+          fs[e] = fss[e] = 0.f;
+        }
+        n = 0;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s[e] += fs[e];
+      ss[e] += fss[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    sh[tid][e] = s[e];
+    sh[tid][4 + e] = ss[e];
+  }
+  __syncthreads();
+  if (tid < C) {                         // channel tid: quad tid / 4, component tid % 4, summed over the row lanes
+    const int q = tid >> 2, e = tid & 3;
+    double ts = 0.0, tss = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      ts += sh[q + l * C4][e];
+      tss += sh[q + l * C4][4 + e];
+    }
+    double* p = partial + (((long long)b * chunks + blockIdx.x) * C + tid) * 2;
+    p[0] = ts;
+    p[1] = tss;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(ticket + b, 1u);
+    last = prev == (unsigned)chunks - 1u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (tid < C) {
+    double ts = 0.0, tss = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+      const double* p = partial + (((long long)b * chunks + k) * C + tid) * 2;
+      ts += p[0];
+      tss += p[1];
+    }
+    const double m = ts / (double)rows;
+    double var = tss / (double)rows - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[(long long)b * C + tid] = (float)m;
+    rstd[(long long)b * C + tid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  if (tid == 0) ticket[b] = 0u;
+}
+
 // ---- pass 1, cumulative statistics -----------------------------------------------------------------------------
 // step sums: one block per (b, t): sum and sum of squares of pre(x) over the F x C elements of the frame.
 // grid (B*T, G): channel group g = channels [g*C/G, (g+1)*C/G) (branches that share a tensor keep their own statistics)
@@ -220,6 +322,55 @@ __global__ void __launch_bounds__(NT) chan_norm_kernel(const NormParams p) {
     }
     if (p.out) p.out[i] = y;
     if (p.out_hi) split_tf32_dev(y, p.out_hi[i], p.out_lo[i]);
+  }
+}
+
+
+// pass 2 without FIR, 4 channels per thread (C, Cin, C / stat_groups multiples of 4)
+__global__ void __launch_bounds__(NT) chan_norm_vec_kernel(const NormParams p) {
+  const int C4 = p.C >> 2;
+  const long long n = (long long)p.B * p.rows * C4;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const int c = 4 * (int)(i % C4);
+    const long long br = i / C4;
+    const int b = (int)(br / p.rows);
+    const long long r = br - (long long)b * p.rows;
+    float v[4];
+    pre_value4(p.x + br * p.Cin, c, p.Cin, p.C, p.pre, p.pre_slope, v);
+    float m[4], rs[4];
+    if (p.stat_mode == SE_NORM_STAT_INSTANCE) {
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mean + (long long)b * p.C + c));
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.rstd + (long long)b * p.C + c));
+      m[0] = m4.x, m[1] = m4.y, m[2] = m4.z, m[3] = m4.w;
+      rs[0] = r4.x, rs[1] = r4.y, rs[2] = r4.z, rs[3] = r4.w;
+    } else {
+      const long long si = ((long long)b * (p.rows / p.rows_per_t) + r / p.rows_per_t) * p.stat_groups +
+                           c / (p.C / p.stat_groups);
+      const float mm = __ldg(p.mean + si), rr = __ldg(p.rstd + si);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m[e] = mm, rs[e] = rr;
+    }
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float sv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.post == SE_NORM_POST_PRELU) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.post_slope + c));
+      sv[0] = s4.x, sv[1] = s4.y, sv[2] = s4.z, sv[3] = s4.w;
+    }
+    float y[4], hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      y[e] = (v[e] - m[e]) * rs[e] * gv[e] + bv[e];
+      if (p.post == SE_NORM_POST_PRELU) y[e] = prelu_f(y[e], sv[e]);
+      if (p.out_hi) split_tf32_dev(y[e], hi[e], lo[e]);
+    }
+    const long long o = br * p.C + c;
+    if (p.out) *reinterpret_cast<float4*>(p.out + o) = make_float4(y[0], y[1], y[2], y[3]);
+    if (p.out_hi) {
+      *reinterpret_cast<float4*>(p.out_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(p.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
@@ -348,8 +499,13 @@ extern "C" int se_chan_stats(const float* x, int B, long long rows, int Cin, int
   // tickets FIRST, at a fixed place: a workspace reused across shapes must find them zero wherever the partials were
   unsigned* ticket = reinterpret_cast<unsigned*>(ws);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + 4096);
-  chan_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), NT, 0, (cudaStream_t)stream>>>(
-      x, rows, Cin, C, pre, pre_slope, eps, mean, rstd, partial, ticket);
+  const bool vec = (C & 3) == 0 && (Cin & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)pre_slope)) & 15) == 0;
+  if (vec)
+    chan_stats_vec_kernel<<<dim3((unsigned)chunks, (unsigned)B), NT, 0, (cudaStream_t)stream>>>(
+        x, rows, Cin, C, pre, pre_slope, eps, mean, rstd, partial, ticket);
+  else
+    chan_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), NT, 0, (cudaStream_t)stream>>>(
+        x, rows, Cin, C, pre, pre_slope, eps, mean, rstd, partial, ticket);
   return check_launch("se_chan_stats");
 }
 
@@ -394,7 +550,15 @@ extern "C" int se_chan_norm(const float* x, int B, long long rows, int Cin, int 
              "se_chan_norm: FIR arguments");
   NormParams p{x, B, rows, Cin, C, pre, pre_slope, mean, rstd, stat_mode, rows_per_t, stat_groups, gamma, beta, post, post_slope,
                fir_w, fir_k, fir_groups, out, out_hi, out_lo};
-  chan_norm_kernel<<<grid_for((long long)B * rows * C), NT, 0, (cudaStream_t)stream>>>(p);
+  auto al16 = [](const void* q) { return (((uintptr_t)q) & 15) == 0; };
+  const bool vec = post != SE_NORM_POST_FIR && (C & 3) == 0 && (Cin & 3) == 0 &&
+                   (stat_mode == SE_NORM_STAT_INSTANCE || ((C / stat_groups) & 3) == 0) && al16(x) && al16(pre_slope) &&
+                   al16(mean) && al16(rstd) && al16(gamma) && al16(beta) && al16(post_slope) && al16(out) && al16(out_hi) &&
+                   al16(out_lo);
+  if (vec)
+    chan_norm_vec_kernel<<<grid_for((long long)B * rows * (C / 4)), NT, 0, (cudaStream_t)stream>>>(p);
+  else
+    chan_norm_kernel<<<grid_for((long long)B * rows * C), NT, 0, (cudaStream_t)stream>>>(p);
   return check_launch("se_chan_norm");
 }
 
