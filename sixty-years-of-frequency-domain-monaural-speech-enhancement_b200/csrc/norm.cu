@@ -204,39 +204,57 @@ __global__ void __launch_bounds__(NT) chan_stats_vec_kernel(const float* __restr
 }
 
 // ---- pass 1, cumulative statistics -----------------------------------------------------------------------------
-// step sums: one block per (b, t): sum and sum of squares of pre(x) over the F x C elements of the frame.
-// grid (B*T, G): channel group g = channels [g*C/G, (g+1)*C/G) (branches that share a tensor keep their own statistics)
-__global__ void __launch_bounds__(NT) cum_step_kernel(const float* __restrict__ x, int F, int Cin, int C, int G, int pre,
-                                                     const float* __restrict__ slope, double* __restrict__ step) {
-  __shared__ double sh[NT / 32][2];
-  const long long bt = blockIdx.x;
-  const int g = blockIdx.y, cg = C / G;
+// step sums: sum and sum of squares of pre(x) over the F x C elements of every frame.
+// one WARP per (frame, channel group): group g = channels [g*C/G, (g+1)*C/G) (branches that share a tensor keep their
+// own statistics).  Inside the TCMs a frame is only 64 values, so a block per frame would be 7/8 idle.
+__global__ void __launch_bounds__(NT) cum_step_kernel(const float* __restrict__ x, long long frames, int F, int Cin, int C,
+                                                     int G, int pre, const float* __restrict__ slope,
+                                                     double* __restrict__ step) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (w >= frames * G) return;
+  const long long bt = w / G;
+  const int g = (int)(w - bt * G), cg = C / G;
   const float* xb = x + bt * F * Cin;
   const int n = F * cg;
   float fs = 0.f, fss = 0.f;
-  for (int i = threadIdx.x; i < n; i += NT) {
-    const int f = i / cg, c = g * cg + (i - f * cg);
-    const float v = pre_value(xb + (long long)f * Cin, c, Cin, C, pre, slope);
-    fs += v;
-    fss = fmaf(v, v, fss);
+  double s = 0.0, ss = 0.0;
+  if (((cg | Cin) & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)slope)) & 15) == 0) {
+    int cnt = 0;
+    for (int i = 4 * lane; i < n; i += 128) {
+      const int f = i / cg, c = g * cg + (i - f * cg);
+      float v[4];
+      pre_value4(xb + (long long)f * Cin, c, Cin, C, pre, slope, v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        fs += v[e];
+        fss = fmaf(v[e], v[e], fss);
+      }
+      if (++cnt == 16) {
+        s += fs, ss += fss, fs = fss = 0.f, cnt = 0;
+      }
+    }
+  } else {
+    int cnt = 0;
+    for (int i = lane; i < n; i += 32) {
+      const int f = i / cg, c = g * cg + (i - f * cg);
+      const float v = pre_value(xb + (long long)f * Cin, c, Cin, C, pre, slope);
+      fs += v;
+      fss = fmaf(v, v, fss);
+      if (++cnt == 64) {
+        s += fs, ss += fss, fs = fss = 0.f, cnt = 0;
+      }
+    }
   }
-  double s = fs, ss = fss;
+  s += fs;
+  ss += fss;
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    sh[threadIdx.x >> 5][0] = s;
-    sh[threadIdx.x >> 5][1] = ss;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < NT / 32; ++w) {
-      s += sh[w][0];
-      ss += sh[w][1];
-    }
-    step[(bt * G + g) * 2] = s;
-    step[(bt * G + g) * 2 + 1] = ss;
+  if (lane == 0) {
+    step[w * 2] = s;
+    step[w * 2 + 1] = ss;
   }
 }
 // prefix over T (one warp per clip; T is a few hundred): mean_t, rstd_t of everything up to and including frame t
@@ -519,8 +537,9 @@ extern "C" int se_cum_stats(const float* x, int B, int T, int F, int Cin, int C,
              "se_cum_stats: Cin=%d C=%d pre=%d", Cin, C, pre);
   SE_REQUIRE(!(pre == SE_NORM_PRE_PRELU || pre == SE_NORM_PRE_GLU_PRELU) || pre_slope, "se_cum_stats: slopes missing");
   double* step = reinterpret_cast<double*>(ws);        // [B*T][G][2]
-  cum_step_kernel<<<dim3((unsigned)((long long)B * T), (unsigned)groups), NT, 0, (cudaStream_t)stream>>>(
-      x, F, Cin, C, groups, pre, pre_slope, step);
+  const long long frames = (long long)B * T;
+  cum_step_kernel<<<(unsigned)((frames * groups + NT / 32 - 1) / (NT / 32)), NT, 0, (cudaStream_t)stream>>>(
+      x, frames, F, Cin, C, groups, pre, pre_slope, step);
   int rc = check_launch("se_cum_stats (step sums)");
   if (rc) return rc;
   cum_scan_kernel<<<dim3((unsigned)B, (unsigned)groups), 32, 0, (cudaStream_t)stream>>>(step, T, groups, F * (C / groups),

@@ -288,30 +288,75 @@ def dsp_roundtrip(wav, geom):
 # soundfile is not available here; 16-bit PCM wav I/O through scipy (sf.write's default
 # subtype for .wav is PCM_16 too, CRN/crn_decode.py:67).
 # ---------------------------------------------------------------------------------------------
-def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, p=1.0, batch=64, device="cuda"):
+def enhancer_for(model):
+    """The decode loop that goes with a drop-in model instance (or the (Step1_net, Step2_net) pair of CTSNet)."""
+    import sys
+    pkg = sys.modules[__package__]          # class names as the package exports them (dpcrn is the class, as in DPCRN.py)
+    if isinstance(model, (tuple, list)):
+        return enhance_ctsnet
+    table = [(pkg.crn_net, enhance_crn), (pkg.lstm_net, enhance_lstm), (pkg.gcrn.Net, enhance_gcrn),
+             (pkg.dpcrn, enhance_dpcrn), (pkg.DCCRN, enhance_dccrn), (pkg.fullsubnet.Model, enhance_fullsubnet),
+             (pkg.Uformer, enhance_uformer), (pkg.TaylorSENet, enhance_taylorsenet),
+             (pkg.g2net.gaf_base, enhance_g2net)]
+    for cls, fn in table:
+        if isinstance(model, cls):
+            return fn
+    raise TypeError(f"no decode loop registered for {type(model).__name__}")
+
+
+def read_wav(path, fs):
+    """``soundfile.read`` as the scripts use it (CRN/crn_decode.py:38): float64 in [-1, 1), mono."""
     from scipy.io import wavfile
+    sr, x = wavfile.read(path)
+    if sr != fs:
+        raise ValueError(f"{path}: sample rate {sr} != {fs} (the 48k->16k resample of lstm_decode_vb.py:34 sits before "
+                         "this path)")
+    if x.ndim != 1:
+        raise ValueError(f"{path}: {x.ndim}-D audio; the decode scripts handle mono files only")
+    if x.dtype.kind == "i":
+        x = x.astype(np.float64) / float(np.iinfo(x.dtype).max + 1)
+    elif x.dtype.kind == "u":                                      # 8-bit PCM is unsigned
+        x = (x.astype(np.float64) - 128.0) / 128.0
+    return x.astype(np.float64)
+
+
+def write_wav(path, y, fs):
+    """``soundfile.write(path, y, fs)`` with its default subtype for .wav: 16-bit PCM (CRN/crn_decode.py:67)."""
+    from scipy.io import wavfile
+    pcm = np.clip(np.round(np.asarray(y, dtype=np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    wavfile.write(path, fs, pcm)
+
+
+def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, batch=64, device="cuda", enhance_fn=None, **kw):
+    """wav directory in -> wav directory out: the ``enhance(args)`` surface of the decode scripts (``args.mix_file_path``,
+    ``args.esti_clean_file_path`` / ``args.esti_file_path``, ``args.fs``; e.g. CRN/crn_decode_vb.py:17-64).  The
+    reference loops one file at a time; here files of equal length are batched (no model in the reference has a padding
+    mask, so clips of different lengths never share a batch) and a batch stays on the device from the noisy waveform to
+    the enhanced one.  ``kw`` goes to the decode loop (``p=0.5`` for the compressed checkpoints)."""
+    fn = enhance_fn or enhancer_for(model)
     os.makedirs(esti_file_path, exist_ok=True)
-    files = sorted(os.listdir(mix_file_path))
-    clips = []
-    for name in files:
-        sr, x = wavfile.read(os.path.join(mix_file_path, name))
-        if sr != fs:
-            raise ValueError(f"{name}: sample rate {sr} != {fs} (resampling sits before this path)")
-        if x.dtype.kind == "i":
-            x = x.astype(np.float64) / float(np.iinfo(x.dtype).max + 1)
-        clips.append((name, x.astype(np.float32)))
-    # equal-length clips batch together (no model in the reference has a padding mask)
     by_len = {}
-    for name, x in clips:
-        by_len.setdefault(len(x), []).append((name, x))
+    for name in sorted(os.listdir(mix_file_path)):
+        x = read_wav(os.path.join(mix_file_path, name), fs)
+        by_len.setdefault(len(x), []).append((name, x.astype(np.float32)))
     count = 0
-    for n, group in by_len.items():
+    for _, group in sorted(by_len.items()):
         for i in range(0, len(group), batch):
             chunk = group[i:i + batch]
             wav = torch.from_numpy(np.stack([x for _, x in chunk])).to(device)
-            out = enhance_mag_mapping(model, wav, p=p).cpu().numpy()
+            out = fn(model, wav, **kw).cpu().numpy()
             for (name, _), y in zip(chunk, out):
-                pcm = np.clip(np.round(y * 32768.0), -32768, 32767).astype(np.int16)
-                wavfile.write(os.path.join(esti_file_path, name), fs, pcm)
+                write_wav(os.path.join(esti_file_path, name), y, fs)
                 count += 1
     return count
+
+
+def enhance(args, model, **kw):
+    """Drop-in for the scripts' ``enhance(args)`` given an already constructed / loaded model (the scripts hard-code the
+    checkpoint path, e.g. CRN/crn_decode.py:19): reads ``args.mix_file_path``, writes ``args.esti_clean_file_path`` (or
+    ``args.esti_file_path``, as FullSubNet / CTSNet / G2Net / TaylorSENet spell it) at ``args.fs``."""
+    out_dir = getattr(args, "esti_clean_file_path", None) or getattr(args, "esti_file_path")
+    n = enhance_dir(model, args.mix_file_path, out_dir, fs=getattr(args, "fs", 16000), **kw)
+    for i in range(n):
+        print(' The %d utterance has been decoded!' % (i + 1))
+    return n

@@ -302,3 +302,40 @@ def test_g2net_host_logic_matches_oracle(monkeypatch, cum):
         assert a.shape == r.shape and (a - r).abs().max() < 2e-5 * max(1.0, r.abs().max().item())
     with pytest.raises(NotImplementedError):
         se_b200.g2net.gaf_base(is_aux=True)
+
+
+def test_enhance_dir_batches_equal_lengths_and_writes_pcm16(tmp_path):
+    """wav-dir -> wav-dir surface (CRN/crn_decode_vb.py:17-64): files are grouped by length, every file comes back under
+    its own name as 16-bit PCM, and ``enhance(args)`` accepts both spellings of the output directory."""
+    from types import SimpleNamespace
+    from scipy.io import wavfile
+    decode = se_b200.decode
+    src, dst = tmp_path / "noisy", tmp_path / "out"
+    src.mkdir()
+    rng = np.random.default_rng(0)
+    clips = {"a.wav": 800, "b.wav": 1200, "c.wav": 800, "d.wav": 800}
+    ref = {}
+    for name, n in clips.items():
+        x = np.clip(rng.normal(0, 0.1, n), -0.9, 0.9)
+        decode.write_wav(str(src / name), x, 16000)
+        ref[name] = decode.read_wav(str(src / name), 16000)
+        assert np.abs(ref[name] - x).max() <= 0.5 / 32768 + 1e-12
+    seen = []
+
+    def fake_enhance(model, wav, gain=1.0):
+        seen.append(tuple(wav.shape))
+        return wav * gain
+
+    n = decode.enhance_dir(None, str(src), str(dst), fs=16000, batch=2, device="cpu", enhance_fn=fake_enhance, gain=0.5)
+    assert n == 4 and sorted(seen) == [(1, 800), (1, 1200), (2, 800)]
+    for name in clips:
+        sr, y = wavfile.read(str(dst / name))
+        assert sr == 16000 and y.dtype == np.int16
+        assert np.abs(y / 32768.0 - 0.5 * ref[name]).max() <= 0.5 / 32768 + 1e-7
+    args = SimpleNamespace(mix_file_path=str(src), esti_file_path=str(tmp_path / "out2"), fs=16000)
+    assert decode.enhance(args, None, device="cpu", enhance_fn=fake_enhance) == 4
+    with pytest.raises(ValueError):
+        decode.read_wav(str(src / "a.wav"), 48000)
+    assert decode.enhancer_for(se_b200.crn_net()) is decode.enhance_crn
+    assert decode.enhancer_for((None, None)) is decode.enhance_ctsnet
+    assert decode.enhancer_for(se_b200.gcrn.Net()) is decode.enhance_gcrn
