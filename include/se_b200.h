@@ -202,6 +202,12 @@ int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xpro
  *   0 = fp32 FMA kernel (any H %% 128 == 0).
  * Measured on B200 (H = 1024, B = 64): 7.9 / 14.4 / 13.8 us per step, see DESIGN.md. */
 int se_set_lstm_engine(int engine);
+/* tcgen05 GEMM engine (process-global; se_gemm_tf32x3*, se_lstm_cell_tf32x3*):
+ *   0 = one CTA per 128 x 128 output tile (csrc/gemm_tc.cu: gemm_tf32x3_kernel) for every shape;
+ *   1 = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, each SM stages half of the operands) where M >= 256 and
+ *       N >= 256, the one-CTA kernel elsewhere.
+ * SE_GEMM_ENGINE in the environment picks the start-up value. */
+int se_set_gemm_engine(int engine);
 /* Measurement aid for the tcgen05 engine: dev_buf (device, 128 * nsteps * 12 int64, or NULL to switch off)
  * receives clock64() stamps of 12 phase boundaries per CTA for steps [first_step, first_step + nsteps); see
  * csrc/lstm_tc.cu for the event list and tools/lstm_tc_phases.py for the reader. */
@@ -314,6 +320,27 @@ int se_cmul(const float* x, const float* m, long long n, float* out, se_stream_t
 int se_dccrn_mask(const float* m, const float* x_re, const float* x_im, long long x_sb, long long x_st, long long x_sf,
                   int B, int T, int F, float* e_re, float* e_im, long long e_sb, long long e_st, long long e_sf,
                   se_stream_t stream);
+/* The same with the other two mask rules of DCCRN.forward (DCCRN/DCCRN_cprs.py:221-224; no shipped checkpoint uses
+ * them): 'C' est = X * M (complex product), 'R' est = (X_r M_r, X_i M_i). */
+enum { SE_DCCRN_MASK_E = 0, SE_DCCRN_MASK_C = 1, SE_DCCRN_MASK_R = 2 };
+int se_dccrn_mask_ex(const float* m, const float* x_re, const float* x_im, long long x_sb, long long x_st,
+                     long long x_sf, int B, int T, int F, int mode, float* e_re, float* e_im, long long e_sb,
+                     long long e_st, long long e_sf, se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Front step of the *_decode_vb.py scripts: librosa.resample(x, orig_fs, 16000, fix=True, scale=False)
+ * (LSTM/lstm_decode_vb.py:33-34, DCCRN/dccrn_decode_vb.py:25-26) = resampy 'kaiser_best' band-limited
+ * interpolation (un-vendored dependency; published algorithm restated, see oracle/resample.py):
+ *     y[b, t] = sum_i (win[o_l + i*step] + eta_l * delta[o_l + i*step]) * x[b, n - i]            (left wing)
+ *             + sum_k (win[o_r + k*step] + eta_r * delta[o_r + k*step]) * x[b, n + k + 1]        (right wing)
+ *     time = t / ratio, n = floor(time), step = int(min(1, ratio) * num_table), offsets / eta from the fractional
+ *     part as resampy.interpn.resample_f computes them (float64 index arithmetic).
+ * x [B, n_in] (row stride x_stride), y [B, n_out] (row stride y_stride); samples t >= n_valid = int(n_in * ratio)
+ * are zero (librosa's fix_length to ceil(n_in * ratio)).  win / delta: device tables of nwin floats (the half
+ * window, already multiplied by ratio when decimating, and its forward difference). */
+int se_resample(const float* x, long long x_stride, int B, int n_in, float* y, long long y_stride, int n_out,
+                int n_valid, double ratio, const float* win, const float* delta, int nwin, int num_table,
+                se_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Uformer glue (Uformer/uformer.py:172-287, dilated_dualpath_conformer.py, fusion.py, t_att_*.py,

@@ -192,8 +192,9 @@ def _lstm1(x, sd, pre):
                 "l", 1).transpose(0, 1)
 
 
-def dccrn_forward(sd, inputs, crop_first=True, taps=None):
-    """DCCRN.forward with masking_mode='E', use_clstm=True (DCCRN_cprs.py:142-226).
+def dccrn_forward(sd, inputs, crop_first=True, taps=None, masking_mode='E'):
+    """DCCRN.forward with use_clstm=True (DCCRN_cprs.py:142-226); masking_mode 'E' is what every script uses, 'C' and
+    'R' are the other two branches (:221-224).
     inputs [B,2,257,T] compressed RI -> [B,2,257,T].  ``crop_first``: decoder keeps ``out[...,1:]``
     (DCCRN_cprs.py:199); the DCCRN_SNR variant keeps ``[..., :-1]`` (DCCRN_SNR/DCCRN.py:159)."""
     spec_mags = torch.norm(inputs, dim=1)                                   # :164
@@ -237,6 +238,11 @@ def dccrn_forward(sd, inputs, crop_first=True, taps=None):
             taps[f"dec{idx}"] = out
     mask_real = F.pad(out[:, 0], [0, 0, 1, 0])                              # :203-204
     mask_imag = F.pad(out[:, 1], [0, 0, 1, 0])
+    if masking_mode != 'E':
+        real, imag = inputs[:, 0], inputs[:, -1]                            # :163
+        if masking_mode == 'C':                                             # :221-222
+            return torch.stack([real * mask_real - imag * mask_imag, real * mask_imag + imag * mask_real], 1)
+        return torch.stack([real * mask_real, imag * mask_imag], 1)         # :223-224 'R'
     mask_mags = (mask_real ** 2 + mask_imag ** 2) ** 0.5                    # :207
     real_phase = mask_real / (mask_mags + 1e-8)
     imag_phase = mask_imag / (mask_mags + 1e-8)

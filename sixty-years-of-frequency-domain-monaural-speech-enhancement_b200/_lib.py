@@ -57,6 +57,7 @@ PROTOTYPES = {
     "se_lstm_seq": (_I, [_P, _LL, _P, _I, _I, _I, _P, _LL, _LL, _P, _P, _P]),
     "se_lstm_seq_multi": (_I, [_P, _LL, _LL, _P, _LL, _I, _I, _I, _I, _P, _LL, _LL, _LL, _P, _P, _P]),
     "se_set_lstm_engine": (_I, [_I]),
+    "se_set_gemm_engine": (_I, [_I]),
     "se_lstm_seq_work_bytes": (_LL, [_I, _I]),
     "se_split_tf32": (_I, [_P, _P, _P, _LL, _P]),
     "se_gemm_tf32x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _P, _LL, _P]),
@@ -78,6 +79,8 @@ PROTOTYPES = {
     "se_unary": (_I, [_P, _LL, _I, _F, _P, _P, _P, _P]),
     "se_cmul": (_I, [_P, _P, _LL, _P, _P]),
     "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
+    "se_dccrn_mask_ex": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
+    "se_resample": (_I, [_P, _LL, _I, _I, _P, _LL, _I, _I, C.c_double, _P, _P, _I, _I, _P]),
     "se_chan_stats_ws_bytes": (_LL, [_I, _LL, _I]),
     "se_chan_stats": (_I, [_P, _I, _LL, _I, _I, _I, _P, _F, _P, _P, _P, _P]),
     "se_cum_stats": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P]),

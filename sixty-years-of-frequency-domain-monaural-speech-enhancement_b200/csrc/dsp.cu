@@ -347,6 +347,50 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
   }
 }
 
+// -------------------------------------------------------------------------------------------
+// front step: band-limited resampling (resampy.interpn.resample_f restated; one output sample per thread)
+// -------------------------------------------------------------------------------------------
+// HBM-bound in principle (reads 4/ratio bytes, writes 4 bytes per output sample); the ~2 * num_zeros / min(1, ratio)
+// taps per sample (385 at 48k -> 16k) re-read the input and the 128 KB table from L1/L2.
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, long long x_stride, int n_in,
+                                                      float* __restrict__ y, long long y_stride, int n_out, int n_valid,
+                                                      double ratio, const float* __restrict__ win,
+                                                      const float* __restrict__ delta, int nwin, int num_table) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_out) return;
+  const float* xb = x + (long long)blockIdx.y * x_stride;
+  float* yb = y + (long long)blockIdx.y * y_stride;
+  if (t >= n_valid) {
+    yb[t] = 0.f;
+    return;
+  }
+  const double scale = ratio < 1.0 ? ratio : 1.0;
+  const int step = (int)(scale * (double)num_table);
+  // resample_f accumulates time_register += 1/ratio in float64; t * (1/ratio) differs from that sum by a few ulp
+  const double time_reg = (double)t * (1.0 / ratio);
+  const int n = (int)time_reg;
+  double frac = scale * (time_reg - (double)n);
+  double index_frac = frac * (double)num_table;
+  int offset = (int)index_frac;
+  float eta = (float)(index_frac - (double)offset);
+  float acc = 0.f;
+  const int i_max = min(n + 1, (nwin - offset) / step);
+  for (int i = 0; i < i_max; ++i) {
+    const int idx = offset + i * step;
+    acc = fmaf(__ldg(win + idx) + eta * __ldg(delta + idx), __ldg(xb + n - i), acc);
+  }
+  frac = scale - frac;
+  index_frac = frac * (double)num_table;
+  offset = (int)index_frac;
+  eta = (float)(index_frac - (double)offset);
+  const int k_max = min(n_in - n - 1, (nwin - offset) / step);
+  for (int k = 0; k < k_max; ++k) {
+    const int idx = offset + k * step;
+    acc = fmaf(__ldg(win + idx) + eta * __ldg(delta + idx), __ldg(xb + n + k + 1), acc);
+  }
+  yb[t] = acc;
+}
+
 static int dsp_smem_stft(int R, int hop) {
   const int nfft = 64 * R;
   const int tile = (kFramesPerCta - 1) * hop + nfft;
@@ -432,4 +476,19 @@ extern "C" int se_istft(int mode, const float* a_re, const float* a_im, long lon
     return SE_ERR_CUDA;
   }
   return check_launch("se_istft");
+}
+
+extern "C" int se_resample(const float* x, long long x_stride, int B, int n_in, float* y, long long y_stride, int n_out,
+                           int n_valid, double ratio, const float* win, const float* delta, int nwin, int num_table,
+                           se_stream_t stream) {
+  SE_REQUIRE(x && y && win && delta && B > 0 && n_in > 0 && n_out > 0, "se_resample: bad arguments");
+  SE_REQUIRE(ratio > 0.0 && num_table > 0 && nwin > num_table, "se_resample: ratio=%g num_table=%d nwin=%d", ratio,
+             num_table, nwin);
+  SE_REQUIRE((int)((ratio < 1.0 ? ratio : 1.0) * num_table) >= 1, "se_resample: ratio %g too small for the table", ratio);
+  SE_REQUIRE(n_valid >= 0 && n_valid <= n_out && (double)(n_valid - 1) / ratio < (double)n_in,
+             "se_resample: n_valid=%d reads past the input (n_in=%d ratio=%g)", n_valid, n_in, ratio);
+  dim3 grid(ceil_div(n_out, 256), B);
+  resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride, n_in, y, y_stride, n_out, n_valid, ratio, win,
+                                                         delta, nwin, num_table);
+  return check_launch("se_resample");
 }

@@ -20,6 +20,8 @@
 //              the number of accumulation steps, 3.4e-5 at K=1024), so every TC_CHUNK_KB k-blocks
 //              the partial sum is promoted to fp32 registers of the epilogue warps (round-to-
 //              nearest adds on the CUDA cores) while the MMA warp fills the other accumulator.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace se {
@@ -58,6 +60,79 @@ struct TcParams {
   long long ld_hout;   // row stride of h_hi / h_lo / h_out (>= H; c_state is always [M, H] contiguous)
   int first_step;      // 1: h_{-1} = c_{-1} = 0 -- no recurrent k-blocks, c_state is not read
 };
+
+// Final epilogue of one thread: NC consecutive columns [n0, n0 + NC) of output row `row`, fp32 sums in registers.
+//   EPI_BIAS_ACT : C = alpha * act(sum + bias) + res, optional TF32 split of the result
+//   EPI_LSTM_CELL: every 64-column group g64 = n / 64 holds [i | f | g | o] x 16 hidden units [16 g64, 16 g64 + 16)
+//                  of sequence `row`: gates -> c, h, and the TF32 split of h for the next step's GEMM
+template <int EPI, int NC>
+__device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float (&sum)[NC], int row, int n0) {
+  if constexpr (EPI == EPI_BIAS_ACT) {
+    const long long roff = (long long)row * p.ldc;
+    const bool vec = (p.ldc & 3) == 0;
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + j + e;
+        const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        o[e] = apply_act(sum[j + e] + bb, p.act, p.act_param) * p.alpha;
+        if (p.res && n < p.N) o[e] += __ldg(p.res + roff + n);
+      }
+      if (vec && n0 + j + 3 < p.N) {
+        if (p.C) *reinterpret_cast<float4*>(p.C + roff + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        if (p.c_hi) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+          *reinterpret_cast<float4*>(p.c_hi + roff + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(p.c_lo + roff + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n0 + j + e < p.N) {
+            if (p.C) p.C[roff + n0 + j + e] = o[e];
+            if (p.c_hi) split_tf32_dev(o[e], p.c_hi[roff + n0 + j + e], p.c_lo[roff + n0 + j + e]);
+          }
+      }
+    }
+  } else {
+    static_assert(NC % 64 == 0, "the fused LSTM cell works on whole 64-column gate groups");
+#pragma unroll
+    for (int q = 0; q < NC / 64; ++q) {
+      const int nq = n0 + q * 64;
+      if (nq >= p.N) break;                 // N = 4H, H % 32 == 0 (checked on the host): whole groups only
+      const int unit0 = (nq >> 6) * 16;
+      const long long off = (long long)row * p.H + unit0;
+      const long long hoff = (long long)row * p.ld_hout + unit0;
+      const float* bias = p.bias + nq;
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        const float4 cold = p.first_step ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                         : *reinterpret_cast<const float4*>(p.c_state + off + u);
+        const float co[4] = {cold.x, cold.y, cold.z, cold.w};
+        float cn[4], hn[4], hh[4], hl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ig = sigmoid_f(sum[q * 64 + u + e] + __ldg(bias + u + e));
+          const float fg = sigmoid_f(sum[q * 64 + 16 + u + e] + __ldg(bias + 16 + u + e));
+          const float gg = tanhf(sum[q * 64 + 32 + u + e] + __ldg(bias + 32 + u + e));
+          const float og = sigmoid_f(sum[q * 64 + 48 + u + e] + __ldg(bias + 48 + u + e));
+          cn[e] = fg * co[e] + ig * gg;
+          hn[e] = og * tanhf(cn[e]);
+          split_tf32_dev(hn[e], hh[e], hl[e]);
+        }
+        *reinterpret_cast<float4*>(p.c_state + off + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(p.h_hi + hoff + u) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<float4*>(p.h_lo + hoff + u) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+        if (p.h_out) *reinterpret_cast<float4*>(p.h_out + hoff + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      }
+    }
+  }
+}
+
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -219,70 +294,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
         }
       }
       if (!row_ok) continue;
-      const int n0 = nb * TC_BN + half * TC_EPI_COLS;
-      if constexpr (EPI == EPI_BIAS_ACT) {
-        const long long roff = (long long)row * p.ldc;
-        const bool vec = (p.ldc & 3) == 0;
-#pragma unroll
-        for (int j = 0; j < TC_EPI_COLS; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int n = n0 + j + e;
-            const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
-            o[e] = apply_act(sum[j + e] + bb, p.act, p.act_param) * p.alpha;
-            if (p.res && n < p.N) o[e] += __ldg(p.res + roff + n);
-          }
-          if (vec && n0 + j + 3 < p.N) {
-            if (p.C) *reinterpret_cast<float4*>(p.C + roff + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-            if (p.c_hi) {
-              float hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
-              *reinterpret_cast<float4*>(p.c_hi + roff + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<float4*>(p.c_lo + roff + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n0 + j + e < p.N) {
-                if (p.C) p.C[roff + n0 + j + e] = o[e];
-                if (p.c_hi) split_tf32_dev(o[e], p.c_hi[roff + n0 + j + e], p.c_lo[roff + n0 + j + e]);
-              }
-          }
-        }
-      } else {
-        // fused LSTM cell: this thread holds all four gates of 16 hidden units of sequence `row`
-        const long long off = (long long)row * p.H + nb * 32 + half * 16;
-        const long long hoff = (long long)row * p.ld_hout + nb * 32 + half * 16;
-        const float* bias = p.bias + n0;
-#pragma unroll
-        for (int u = 0; u < 16; u += 4) {
-          const float4 cold = p.first_step ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                           : *reinterpret_cast<const float4*>(p.c_state + off + u);
-          const float co[4] = {cold.x, cold.y, cold.z, cold.w};
-          float cn[4], hn[4], hh[4], hl[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float ig = sigmoid_f(sum[u + e] + __ldg(bias + u + e));
-            const float fg = sigmoid_f(sum[16 + u + e] + __ldg(bias + 16 + u + e));
-            const float gg = tanhf(sum[32 + u + e] + __ldg(bias + 32 + u + e));
-            const float og = sigmoid_f(sum[48 + u + e] + __ldg(bias + 48 + u + e));
-            cn[e] = fg * co[e] + ig * gg;
-            hn[e] = og * tanhf(cn[e]);
-            unsigned hb, lb;
-            asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hb) : "f"(hn[e]));
-            hh[e] = __uint_as_float(hb);
-            const float r = hn[e] - hh[e];
-            asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lb) : "f"(r));
-            hl[e] = __uint_as_float(lb);
-          }
-          *reinterpret_cast<float4*>(p.c_state + off + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(p.h_hi + hoff + u) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<float4*>(p.h_lo + hoff + u) = make_float4(hl[0], hl[1], hl[2], hl[3]);
-          if (p.h_out) *reinterpret_cast<float4*>(p.h_out + hoff + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        }
-      }
+      tc_epilogue_store<EPI, TC_EPI_COLS>(p, sum, row, nb * TC_BN + half * TC_EPI_COLS);
     }
   }
   tc_fence_before();
@@ -290,6 +302,262 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): one 256 x 256 output tile per pair of CTAs (two SMs of a TPC).
+//
+// Why: the 128 x 128 kernel above is bound by L2 -> SM operand traffic, not by the tensor pipe (four 16 KB tiles per
+// 12 MMAs: 69 B/clk/SM wanted, ~37 delivered; profiles/ncu_full_r01_summary.txt).  A pair multiplies M = 256 rows
+// (128 per CTA) by N = 256 columns with each CTA staging only ITS 128 A rows and ITS 128 of the 256 B rows: the same
+// 64 KB per k-block per SM now feeds twice the MMA work.
+//
+//   * both CTAs: TMA producer warp loads the CTA's own tiles into its own smem; the transaction bytes of BOTH CTAs are
+//     counted on the LEADER's (cluster rank 0) `full` barrier (.cta_group::2 TMA, barrier address with the peer bit
+//     cleared -- the addressing CUTLASS' SM100_TMA_2SM_LOAD uses);
+//   * leader only: one thread issues tcgen05.mma.cta_group::2 (reads A/B from both CTAs' smem at the same offsets,
+//     writes rows 0-127 to its own TMEM and rows 128-255 to the peer's); tcgen05.commit ... multicast::cluster arrives
+//     on the `empty` / `tfull` barriers of both CTAs;
+//   * both CTAs: 8 epilogue warps drain their own TMEM (32 lanes x 128 columns each), promote chunk sums to fp32
+//     registers as above, and arrive REMOTELY on the leader's `tempty` barrier (count 16).
+constexpr int T2_BN = 256;
+constexpr int T2_EPI_COLS = T2_BN / 2;                     // 128 columns per epilogue warp
+constexpr int T2_TMEM_COLS = 512;                          // 2 accumulators x 256 columns: all of tensor memory
+constexpr unsigned T2_PEER_BIT_MASK = 0xFEFFFFFFu;         // shared::cluster address of the same offset in CTA rank 0
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, unsigned leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc,
+                                               unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this smem offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const unsigned short mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+                   "r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, unsigned rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remote;\n"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(unsigned* smem_slot, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
+                        const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
+                        const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                        const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = base;                                        // STAGES x {A_hi, A_lo, B_hi, B_lo} x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                   // [STAGES]  used in the leader CTA only
+  uint64_t* empty = bars + TC_STAGES;      // [STAGES]  one per CTA (multicast commit)
+  uint64_t* tfull = bars + 2 * TC_STAGES;  // [2]       one per CTA (multicast commit)
+  uint64_t* tempty = tfull + 2;            // [2]       used in the leader CTA only
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();            // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int mblocks = ceil_div(p.M, 2 * TC_BM), nblocks = ceil_div(p.N, T2_BN);
+  const int ntiles = mblocks * nblocks;
+  const int kblocks = p.kb0 + p.kb1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 2 * TC_EPI_WARPS);  // one arrive per epilogue warp of either CTA
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a0hi);
+    tma_prefetch_desc(&map_a0lo);
+    tma_prefetch_desc(&map_bhi);
+    tma_prefetch_desc(&map_blo);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, T2_TMEM_COLS);   // the same warp of both CTAs, same smem slot
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();     // barriers of both CTAs initialised and both allocations done before any remote signal
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& mb, int& nb) {
+    const int per_panel = p.panel_m * nblocks;
+    const int panel = tile / per_panel;
+    const int r = tile - panel * per_panel;
+    const int pm = min(p.panel_m, mblocks - panel * p.panel_m);
+    nb = r / pm;
+    mb = panel * p.panel_m + (r - nb * pm);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own A rows, own half of the B rows) =====================
+    if (elect_one()) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (int tile = pair; tile < ntiles; tile += npairs) {
+        int mb, nb;
+        tile_coords(tile, mb, nb);
+        const int arow = mb * 2 * TC_BM + (int)rank * TC_BM;
+        const int brow = nb * T2_BN + (int)rank * (T2_BN / 2);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait_parity(&empty[stage], phase ^ 1);
+          unsigned char* st = tiles + stage * TC_STAGE_BYTES;
+          const unsigned lbar = smem_u32(&full[stage]) & T2_PEER_BIT_MASK;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * TC_STAGE_BYTES);   // both CTAs' bytes land on this barrier
+          if (kb < p.kb0) {
+            tma_load_2d_pair(&map_a0hi, lbar, st + 0 * TC_TILE_BYTES, kb * TC_BK, arow);
+            tma_load_2d_pair(&map_a0lo, lbar, st + 1 * TC_TILE_BYTES, kb * TC_BK, arow);
+          } else {
+            tma_load_2d_pair(&map_a1hi, lbar, st + 0 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, arow);
+            tma_load_2d_pair(&map_a1lo, lbar, st + 1 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, arow);
+          }
+          tma_load_2d_pair(&map_bhi, lbar, st + 2 * TC_TILE_BYTES, kb * TC_BK, brow);
+          tma_load_2d_pair(&map_blo, lbar, st + 3 * TC_TILE_BYTES, kb * TC_BK, brow);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (rank == 0 && elect_one()) {
+      constexpr unsigned idesc = make_idesc_tf32(2 * TC_BM, T2_BN);
+      int stage = 0;
+      unsigned phase = 0;
+      int acc = 0;
+      unsigned acc_phase = 0;
+      for (int tile = pair; tile < ntiles; tile += npairs) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const bool chunk_start = (kb % TC_CHUNK_KB) == 0;
+          if (chunk_start) {
+            mbar_wait_parity(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+            tc_fence_after();
+          }
+          const unsigned d_tmem = tmem_base + (unsigned)(acc * T2_BN);
+          mbar_wait_parity(&full[stage], phase);
+          tc_fence_after();
+          unsigned char* st = tiles + stage * TC_STAGE_BYTES;
+          const uint64_t d_ahi = make_smem_desc(st + 0 * TC_TILE_BYTES);
+          const uint64_t d_alo = make_smem_desc(st + 1 * TC_TILE_BYTES);
+          const uint64_t d_bhi = make_smem_desc(st + 2 * TC_TILE_BYTES);
+          const uint64_t d_blo = make_smem_desc(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+            umma_tf32_pair(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+            umma_tf32_pair(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+            umma_tf32_pair(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+          }
+          umma_commit_pair(&empty[stage]);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if ((kb % TC_CHUNK_KB) == TC_CHUNK_KB - 1 || kb == kblocks - 1) {
+            umma_commit_pair(&tfull[acc]);
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): own TMEM rows -> registers -> global =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;    // which 128 columns of the 256-column accumulator
+    int acc = 0;
+    unsigned acc_phase = 0;
+    const int nchunks = (kblocks + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+    for (int tile = pair; tile < ntiles; tile += npairs) {
+      int mb, nb;
+      tile_coords(tile, mb, nb);
+      const int row = mb * 2 * TC_BM + (int)rank * TC_BM + quarter * 32 + lane;
+      float sum[T2_EPI_COLS];
+#pragma unroll
+      for (int j = 0; j < T2_EPI_COLS; ++j) sum[j] = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait_parity(&tfull[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int piece = 0; piece < T2_EPI_COLS / 32; ++piece) {
+          float v[32];
+          const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) +
+                                 (unsigned)(acc * T2_BN + half * T2_EPI_COLS + piece * 32);
+          tmem_ld_32x32(taddr, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[piece * 32 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (row >= p.M) continue;
+      tc_epilogue_store<EPI, T2_EPI_COLS>(p, sum, row, nb * T2_BN + half * T2_EPI_COLS);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();     // the peer's TMEM / barriers stay alive until the leader's last MMA and commit have landed
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, T2_TMEM_COLS);
   }
 }
 
@@ -363,6 +631,60 @@ extern "C" int se_split_tf32(const float* x, float* hi, float* lo, long long n, 
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+// 0: gemm_tf32x3_kernel for every shape; 1: gemm_tf32x3_pair_kernel where M >= 256 and N >= 256.
+// SE_GEMM_ENGINE in the environment overrides the default; se_set_gemm_engine() overrides both.
+constexpr int kDefaultGemmEngine = 0;
+static int g_gemm_engine = -1;
+static int gemm_engine() {
+  if (g_gemm_engine < 0) {
+    g_gemm_engine = kDefaultGemmEngine;
+    if (const char* e = getenv("SE_GEMM_ENGINE")) {
+      const int v = atoi(e);
+      if (v == 0 || v == 1) g_gemm_engine = v;
+    }
+  }
+  return g_gemm_engine;
+}
+
+template <int EPI>
+static int launch_pair_kernel(const CUtensorMap& a0hi, const CUtensorMap& a0lo, const CUtensorMap& a1hi,
+                              const CUtensorMap& a1lo, const CUtensorMap& bhi, const CUtensorMap& blo, const TcParams& p,
+                              int grid, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e != cudaSuccess) {
+    set_error("tcgen05 pair gemm: smem attribute: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<EPI>, a0hi, a0lo, a1hi, a1lo, bhi, blo, p);
+  if (e != cudaSuccess) {
+    set_error("tcgen05 pair gemm: cluster launch: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
+static int launch_tc_pair(int epi, const CUtensorMap& a0hi, const CUtensorMap& a0lo, const CUtensorMap& a1hi,
+                          const CUtensorMap& a1lo, const CUtensorMap& bhi, const CUtensorMap& blo, TcParams p, int sms,
+                          cudaStream_t stream) {
+  const int mblocks = ceil_div(p.M, 2 * TC_BM), nblocks = ceil_div(p.N, T2_BN);
+  p.panel_m = min(8, mblocks);                    // 8 x 256 rows: the same A panel as 16 x 128
+  const int grid = 2 * min(sms / 2, mblocks * nblocks);
+  return epi == EPI_BIAS_ACT ? launch_pair_kernel<EPI_BIAS_ACT>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream)
+                             : launch_pair_kernel<EPI_LSTM_CELL>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
+}
+
 static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long lda0, int K0, const float* a1_hi,
                      const float* a1_lo, long long lda1, int K1, const float* b_hi, const float* b_lo, long long ldb,
                      TcParams p, cudaStream_t stream) {
@@ -382,9 +704,10 @@ static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long 
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int mblocks = ceil_div(p.M, TC_BM), nblocks = ceil_div(p.N, TC_BN);
   p.kb0 = K0 / TC_BK;
   p.kb1 = K1 / TC_BK;
+  if (gemm_engine() == 1 && p.M >= 2 * TC_BM && p.N >= T2_BN) return launch_tc_pair(epi, m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p, sms, stream);
+  const int mblocks = ceil_div(p.M, TC_BM), nblocks = ceil_div(p.N, TC_BN);
   p.panel_m = min(16, mblocks);
   const int grid = min(sms, mblocks * nblocks);
   cudaError_t e;
@@ -401,6 +724,12 @@ static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long 
     set_error("tcgen05 gemm: smem attribute: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
+  return SE_OK;
+}
+
+extern "C" int se_set_gemm_engine(int engine) {
+  SE_REQUIRE(engine == 0 || engine == 1, "se_set_gemm_engine: 0 (one CTA per 128x128 tile) or 1 (CTA pairs, 256x256 tiles)");
+  g_gemm_engine = engine;
   return SE_OK;
 }
 

@@ -92,9 +92,11 @@ class DCCRN(nn.Module):
                  masking_mode='E', use_clstm=False, use_cbn=False, kernel_size=5,
                  kernel_num=[16, 32, 64, 128, 256, 256], crop_first=True):
         super().__init__()
-        if masking_mode != 'E' or not use_clstm or use_cbn or rnn_layers != 2 or kernel_size != 5 or fft_len != 512:
-            raise NotImplementedError("se_b200 DCCRN covers the decode scripts' configuration: masking_mode='E', "
-                                      "use_clstm=True, use_cbn=False, 2 rnn layers, kernel 5, 512-point FFT")
+        if masking_mode not in ('E', 'C', 'R') or not use_clstm or use_cbn or rnn_layers != 2 or kernel_size != 5 \
+                or fft_len != 512:
+            raise NotImplementedError("se_b200 DCCRN covers the decode scripts' configuration: masking_mode 'E' (or "
+                                      "'C' / 'R'), use_clstm=True, use_cbn=False, 2 rnn layers, kernel 5, 512-point FFT")
+        self.masking_mode = masking_mode    # DCCRN_cprs.py:206-224
         self.kernel_num = [2] + list(kernel_num)
         self.rnn_units = rnn_units
         self.crop_first = crop_first        # False reproduces DCCRN_SNR/DCCRN.py:159 (``[..., :-1]``)
@@ -297,7 +299,7 @@ class DCCRN(nn.Module):
                 taps[f"dec{i}"] = f32_of(h)
         h = h.f32
         est = torch.empty(b, t, BINS, 2, device=dev, dtype=torch.float32)
-        ops.dccrn_mask(h, x[..., 0], x[..., 1], est[..., 0], est[..., 1])
+        ops.dccrn_mask(h, x[..., 0], x[..., 1], est[..., 0], est[..., 1], mode=self.masking_mode)
         return est
 
     @staticmethod

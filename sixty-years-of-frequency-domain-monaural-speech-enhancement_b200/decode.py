@@ -304,20 +304,26 @@ def enhancer_for(model):
     raise TypeError(f"no decode loop registered for {type(model).__name__}")
 
 
-def read_wav(path, fs):
-    """``soundfile.read`` as the scripts use it (CRN/crn_decode.py:38): float64 in [-1, 1), mono."""
+def read_wav_any(path):
+    """``soundfile.read`` as the scripts use it (CRN/crn_decode.py:38): (float64 samples in [-1, 1), sample rate)."""
     from scipy.io import wavfile
     sr, x = wavfile.read(path)
-    if sr != fs:
-        raise ValueError(f"{path}: sample rate {sr} != {fs} (the 48k->16k resample of lstm_decode_vb.py:34 sits before "
-                         "this path)")
     if x.ndim != 1:
         raise ValueError(f"{path}: {x.ndim}-D audio; the decode scripts handle mono files only")
     if x.dtype.kind == "i":
         x = x.astype(np.float64) / float(np.iinfo(x.dtype).max + 1)
     elif x.dtype.kind == "u":                                      # 8-bit PCM is unsigned
         x = (x.astype(np.float64) - 128.0) / 128.0
-    return x.astype(np.float64)
+    return x.astype(np.float64), int(sr)
+
+
+def read_wav(path, fs):
+    """read_wav_any for the scripts that do not resample (CRN/crn_decode.py:38): the file must already be at ``fs``."""
+    x, sr = read_wav_any(path)
+    if sr != fs:
+        raise ValueError(f"{path}: sample rate {sr} != {fs} (pass resample_to= for the librosa.resample front step of "
+                         "the *_decode_vb.py scripts, lstm_decode_vb.py:34)")
+    return x
 
 
 def write_wav(path, y, fs):
@@ -327,23 +333,33 @@ def write_wav(path, y, fs):
     wavfile.write(path, fs, pcm)
 
 
-def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, batch=64, device="cuda", enhance_fn=None, **kw):
+def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, batch=64, device="cuda", enhance_fn=None,
+                resample_to=None, **kw):
     """wav directory in -> wav directory out: the ``enhance(args)`` surface of the decode scripts (``args.mix_file_path``,
     ``args.esti_clean_file_path`` / ``args.esti_file_path``, ``args.fs``; e.g. CRN/crn_decode_vb.py:17-64).  The
     reference loops one file at a time; here files of equal length are batched (no model in the reference has a padding
     mask, so clips of different lengths never share a batch) and a batch stays on the device from the noisy waveform to
-    the enhanced one.  ``kw`` goes to the decode loop (``p=0.5`` for the compressed checkpoints)."""
+    the enhanced one.  ``resample_to=16000`` adds the front step of the ``*_decode_vb.py`` scripts
+    (``librosa.resample(x, orig_fs, 16000, fix=True, scale=False)``, LSTM/lstm_decode_vb.py:33-34) on the device:
+    files are then grouped by (sample rate, length).  ``kw`` goes to the decode loop (``p=0.5`` for the compressed
+    checkpoints)."""
     fn = enhance_fn or enhancer_for(model)
     os.makedirs(esti_file_path, exist_ok=True)
-    by_len = {}
+    groups = {}
     for name in sorted(os.listdir(mix_file_path)):
-        x = read_wav(os.path.join(mix_file_path, name), fs)
-        by_len.setdefault(len(x), []).append((name, x.astype(np.float32)))
+        path = os.path.join(mix_file_path, name)
+        if resample_to is None:
+            x, sr = read_wav(path, fs), fs
+        else:
+            x, sr = read_wav_any(path)
+        groups.setdefault((sr, len(x)), []).append((name, x.astype(np.float32)))
     count = 0
-    for _, group in sorted(by_len.items()):
+    for (sr, _), group in sorted(groups.items()):
         for i in range(0, len(group), batch):
             chunk = group[i:i + batch]
             wav = torch.from_numpy(np.stack([x for _, x in chunk])).to(device)
+            if resample_to is not None:
+                wav = ops.resample(wav, sr, resample_to)
             out = fn(model, wav, **kw).cpu().numpy()
             for (name, _), y in zip(chunk, out):
                 write_wav(os.path.join(esti_file_path, name), y, fs)

@@ -3,6 +3,7 @@ no arithmetic happens in Python."""
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 
@@ -341,8 +342,12 @@ def fsn_sb_fc(h, W, bias, out):
     return out
 
 
-def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
-    """DCCRN-E polar mask.  m [B,T,F-1,2] channels-last; x / e planes [B,T,F] ('btf') or [B,F,T]."""
+DCCRN_MASK_MODES = {"E": 0, "C": 1, "R": 2}      # SE_DCCRN_MASK_* in include/se_b200.h
+
+
+def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf", mode="E"):
+    """DCCRN mask application (DCCRN_cprs.py:201-224): 'E' polar, 'C' complex product, 'R' per-component.
+    m [B,T,F-1,2] channels-last; x / e planes [B,T,F] ('btf') or [B,F,T]."""
     _need_cuda(m, x_re, x_im, e_re, e_im)
     device_check()
     b, t, fm1, _ = m.shape
@@ -350,8 +355,53 @@ def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
     es = _plane_strides(e_re, layout_e)
     assert _plane_strides(x_im, layout_x) == xs and _plane_strides(e_im, layout_e) == es and m.is_contiguous()
     with _Timed("dccrn_mask"):
-        check(_lib.load().se_dccrn_mask(_ptr(m), _ptr(x_re), _ptr(x_im), *xs, b, t, fm1 + 1, _ptr(e_re), _ptr(e_im),
-                                        *es, _stream()), "se_dccrn_mask")
+        check(_lib.load().se_dccrn_mask_ex(_ptr(m), _ptr(x_re), _ptr(x_im), *xs, b, t, fm1 + 1, DCCRN_MASK_MODES[mode],
+                                           _ptr(e_re), _ptr(e_im), *es, _stream()), "se_dccrn_mask_ex")
+
+
+_RESAMPLE_TABLES = {}
+
+
+def resample_tables(ratio, device):
+    """(win, delta, num_table) device tables of resampy's 'kaiser_best' filter for ``ratio = sr_new / sr_orig``:
+    right wing of rolloff * sinc(rolloff * t) on 2**9 samples per zero crossing over 64 zero crossings, tapered by a
+    Kaiser window (beta 14.769656459379492, rolloff 0.9475937167399596 -- the parameters resampy documents for the
+    table it ships), scaled by ``ratio`` when decimating, and its forward difference (resampy/core.py)."""
+    key = (float(ratio), str(device))
+    if key not in _RESAMPLE_TABLES:
+        import numpy as np
+        zeros, bits, rolloff, beta = 64, 512, 0.9475937167399596, 14.769656459379492
+        n = bits * zeros
+        half = np.kaiser(2 * n + 1, beta)[n:] * rolloff * np.sinc(rolloff * np.linspace(0.0, zeros, n + 1))
+        if ratio < 1:
+            half = half * ratio
+        delta = np.append(np.diff(half), 0.0)
+        _RESAMPLE_TABLES[key] = (torch.from_numpy(half.astype(np.float32)).to(device),
+                                 torch.from_numpy(delta.astype(np.float32)).to(device), bits)
+    return _RESAMPLE_TABLES[key]
+
+
+def resample(x, sr_orig, sr_new, out=None):
+    """librosa.resample(x, sr_orig, sr_new, fix=True, scale=False) for a batch (LSTM/lstm_decode_vb.py:34).
+    x [B, n_in] float32 CUDA -> [B, ceil(n_in * sr_new / sr_orig)]; identity when the rates agree."""
+    _need_cuda(x)
+    device_check()
+    if int(sr_orig) == int(sr_new):
+        return x
+    assert x.dim() == 2 and x.stride(1) == 1
+    ratio = float(sr_new) / float(sr_orig)
+    b, n_in = x.shape
+    n_valid = int(n_in * ratio)                       # resampy.core.resample: int(shape * sample_ratio)
+    n_out = int(math.ceil(n_in * ratio))              # librosa: fix_length(y_hat, ceil(n * ratio))
+    if n_valid < 1:
+        raise ValueError("input too short to resample")
+    win, delta, bits = resample_tables(ratio, x.device)
+    if out is None:
+        out = torch.empty(b, n_out, device=x.device, dtype=torch.float32)
+    with _Timed("resample"):
+        check(_lib.load().se_resample(_ptr(x), x.stride(0), b, n_in, _ptr(out), out.stride(0), n_out, n_valid, ratio,
+                                      _ptr(win), _ptr(delta), win.numel(), bits, _stream()), "se_resample")
+    return out
 
 
 def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, act, dstF, dst_f0=0, dst_fstep=1,
@@ -522,6 +572,11 @@ def uf_mask(cmask, mdec, mag, phase):
 def set_lstm_engine(engine: int):
     """0 = fp32 FMA recurrence kernel, 1 = mma.sync 3xTF32 kernel, 2 = tcgen05 cluster kernel (H = 1024)."""
     check(_lib.load().se_set_lstm_engine(int(engine)), "se_set_lstm_engine")
+
+
+def set_gemm_engine(engine: int):
+    """0 = one CTA per 128x128 tile, 1 = CTA pairs (cta_group::2, 256x256 tiles) where M, N >= 256."""
+    check(_lib.load().se_set_gemm_engine(int(engine)), "se_set_gemm_engine")
 
 
 def glu_affine_act(x, scale, shift, act="elu", act_param=0.0, want_f32=True, want_pair=False):

@@ -97,14 +97,19 @@ def lstm_seq_multi(xproj, whh, hidden, ngroups, out):
     return out
 
 
-def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf"):
+def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf", mode="E"):
     assert layout_x == "btf" and layout_e == "btf"
     M = torch.view_as_complex(m.contiguous())
     X = torch.complex(x_re, x_im)
-    mm = M.abs()
-    g = torch.where(mm > 0, torch.tanh(mm) / mm.clamp_min(1e-30), torch.zeros_like(mm))
     E = torch.zeros_like(X)
-    E[:, :, 1:] = X[:, :, 1:] * M * g
+    if mode == "E":
+        mm = M.abs()
+        g = torch.where(mm > 0, torch.tanh(mm) / mm.clamp_min(1e-30), torch.zeros_like(mm))
+        E[:, :, 1:] = X[:, :, 1:] * M * g
+    elif mode == "C":
+        E[:, :, 1:] = X[:, :, 1:] * M
+    else:
+        E[:, :, 1:] = torch.complex(X.real[:, :, 1:] * M.real, X.imag[:, :, 1:] * M.imag)
     e_re.copy_(E.real)
     e_im.copy_(E.imag)
 

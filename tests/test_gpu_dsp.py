@@ -179,3 +179,41 @@ def test_dsp_rejects_bad_geometry():
     out = torch.empty(1, 26, 129, device=dev)
     with pytest.raises(se_b200._lib.SeB200Error):
         ops.stft(w, None, 256, 256, 160, mag=out)
+
+
+@pytest.mark.parametrize("sr,n", [(48000, 48000 + 77), (44100, 30011), (8000, 9000), (32000, 4000)])
+def test_resample_matches_oracle(sr, n):
+    """se_resample (front step of the *_decode_vb.py scripts) vs the restated librosa/resampy algorithm.  fp32 table
+    and accumulation against the float64 oracle: 1e-5 on unit-scale noise."""
+    dev = _dev()
+    import se_b200
+    from oracle import resample as R
+    rng = np.random.default_rng(sr + n)
+    x = (rng.standard_normal((3, n)) * 0.3).astype(np.float32)
+    y = se_b200.ops.resample(torch.from_numpy(x).to(dev), sr, 16000).cpu().numpy()
+    for b in range(3):
+        ref = R.librosa_resample(x[b].astype(np.float64), sr, 16000)
+        assert y.shape[1] == len(ref)
+        err = np.abs(y[b] - ref).max()
+        assert err < 1e-5, (b, err)
+    x16 = torch.from_numpy(x).to(dev)
+    assert se_b200.ops.resample(x16, 16000, 16000) is x16
+
+
+def test_resample_full_size_batch_properties():
+    """64 x 4 s at 48 kHz: linearity and agreement with the oracle on two clips."""
+    dev = _dev()
+    import se_b200
+    from oracle import resample as R, synth
+    base = synth.noisy_batch(4, 64000)
+    x = np.repeat(base, 3, axis=1).astype(np.float32)                  # crude 48 kHz material, 192 000 samples
+    x = np.tile(x, (16, 1)) * np.linspace(0.5, 1.5, 64, dtype=np.float32)[:, None]
+    xt = torch.from_numpy(x).to(dev)
+    y = se_b200.ops.resample(xt, 48000, 16000)
+    assert y.shape == (64, 64000)
+    y2 = se_b200.ops.resample(2.0 * xt[:8] + xt[8:16], 48000, 16000)
+    assert (y2 - (2.0 * y[:8] + y[8:16])).abs().max().item() < 1e-5
+    for b in (0, 63):
+        ref = R.librosa_resample(x[b].astype(np.float64), 48000, 16000)
+        assert np.abs(y[b].cpu().numpy() - ref).max() < 1e-5
+

@@ -1,5 +1,7 @@
 """GPU parity of the network building blocks (implicit-GEMM conv, LSTM recurrence) through the
 C ABI against the torch mirror of their declared semantics (tests/emu_ops.py, CPU fp32/fp64)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,6 +16,8 @@ def _dev():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
 
+
+DEFAULT_GEMM_ENGINE = int(os.environ.get("SE_GEMM_ENGINE", "0"))   # csrc/gemm_tc.cu: kDefaultGemmEngine
 
 CONV_CASES = [
     # B, T, Fin, C0, C1, Cout, kind
@@ -177,6 +181,71 @@ def test_lstm_cell_tf32x3_matches_recurrence(m, kx, h, steps):
     e_split = ((dst[0] + dst[1]).cpu().double() - hr).abs().max().item()
     print(f"lstm_cell M={m} Kx={kx} H={h} steps={steps}: h err {e_h:.3e} c err {e_c:.3e} hi+lo err {e_split:.3e}")
     assert e_h < 1e-5 and e_c < 1e-5 and e_split < 1e-5
+
+
+@pytest.mark.parametrize("m,k,n,act", [(256, 32, 256, "none"), (300, 1024, 256, "none"), (1000, 256, 4096, "softplus"),
+                                       (2309, 2048, 512 + 164, "none"), (25664, 1024, 4096, "none")])
+def test_gemm_pair_engine_matches_fp64_and_single_cta(m, k, n, act):
+    """CTA-pair (cta_group::2, 256x256 tiles) engine: fp32-class error vs fp64 on a row sample (first / last rows and a
+    random draw), and agreement with the one-CTA engine on the WHOLE output (both add the same products in the same
+    k order, promoted to fp32 registers every 4 k-blocks)."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / np.sqrt(k)
+    bias = torch.randn(n, generator=g)
+    a_hi, a_lo = ops.split_tf32(a.to(dev))
+    w_hi, w_lo = ops.split_tf32(w.to(dev))
+    try:
+        ops.set_gemm_engine(0)
+        one = ops.gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias.to(dev), n, act)
+        ops.set_gemm_engine(1)
+        two = ops.gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias.to(dev), n, act)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
+    rows = torch.unique(torch.cat([torch.arange(0, min(m, 300)), torch.arange(max(0, m - 300), m),
+                                   torch.randint(0, m, (256,), generator=g)]))
+    ref = emu_ops._act(a[rows].double() @ w.double().t() + bias.double(), act)
+    err = (two.cpu()[rows].double() - ref).abs().max().item()
+    diff = (two - one).abs().max().item()
+    print(f"gemm pair engine {m}x{k}x{n}: max err vs fp64 {err:.3e}, vs one-CTA engine {diff:.3e}")
+    assert err < 1e-5 and diff < 1e-5
+
+
+@pytest.mark.parametrize("m,kx,h,steps", [(300, 32, 384, 3), (8224, 32, 384, 2), (1031, 64, 128, 2)])
+def test_lstm_cell_pair_engine_matches_single_cta(m, kx, h, steps):
+    """Fused LSTM cell epilogue on the CTA-pair engine vs the one-CTA engine (same packing, 64-column gate groups)."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(m + h)
+    P = packing.pack_lstm_cell(torch.randn(4 * h, kx, generator=g) / np.sqrt(kx), torch.randn(4 * h, h, generator=g) / np.sqrt(h),
+                               torch.randn(4 * h, generator=g) * 0.1, torch.randn(4 * h, generator=g) * 0.1)
+    P = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in P.items()}
+    xs = torch.randn(steps, m, kx, generator=g).to(dev)
+    res = []
+    try:
+        for eng in (0, 1):
+            ops.set_gemm_engine(eng)
+            c = torch.zeros(m, h, device=dev)
+            hbuf = [(torch.zeros(m, h, device=dev), torch.zeros(m, h, device=dev)) for _ in range(2)]
+            hout = torch.empty(m, h, device=dev)
+            for t in range(steps):
+                x_hi, x_lo = ops.split_tf32(xs[t])
+                src, dst = hbuf[t & 1], hbuf[(t + 1) & 1]
+                ops.lstm_cell_tf32x3(x_hi, x_lo, src[0], src[1], P["w_hi"], P["w_lo"], P["bias"], c, dst[0], dst[1], hout)
+            torch.cuda.synchronize()
+            res.append((hout.clone(), c.clone(), (dst[0] + dst[1]).clone()))
+    finally:
+        ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
+    for a, b, nm in zip(res[0], res[1], ("h", "c", "hi+lo")):
+        d = (a - b).abs().max().item()
+        print(f"lstm_cell pair engine M={m} H={h}: {nm} diff {d:.3e}")
+        assert d < 1e-5
 
 
 TC_CONV_CASES = [
@@ -548,3 +617,20 @@ def test_cum_stats_2d_and_cts_glue():
     r1, p1 = ops.gaf_update(r0, r0[:, 176:], 352, 1, gain.to(dev).view(n, 161), resi.to(dev), n, 161, 352, 176)
     e1, _ = emu_ops.gaf_update(e0, e0[:, 176:], 352, 1, gain.view(n, 161), resi, n, 161, 352, 176)
     assert (r1.cpu() - e1).abs().max() < 2e-6 and ((p1[0] + p1[1]).cpu() - e1).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["E", "C", "R"])
+def test_dccrn_mask_modes(mode):
+    """se_dccrn_mask_ex vs the three branches of DCCRN.forward (DCCRN_cprs.py:206-224) on random tensors."""
+    dev = _dev()
+    import se_b200
+    g = torch.Generator().manual_seed(11)
+    b, t, f = 2, 9, 257
+    m = torch.randn(b, t, f - 1, 2, generator=g)
+    x = torch.randn(b, t, f, 2, generator=g)
+    e = torch.empty(b, t, f, 2, device=dev)
+    se_b200.ops.dccrn_mask(m.to(dev), x[..., 0].to(dev), x[..., 1].to(dev), e[..., 0], e[..., 1], mode=mode)
+    er, ei = torch.empty(b, t, f), torch.empty(b, t, f)
+    emu_ops.dccrn_mask(m, x[..., 0], x[..., 1], er, ei, mode=mode)
+    assert (e[..., 0].cpu() - er).abs().max() < 2e-6 and (e[..., 1].cpu() - ei).abs().max() < 2e-6
+

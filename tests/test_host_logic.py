@@ -167,6 +167,20 @@ def test_dccrn_host_logic_matches_oracle(monkeypatch):
     assert (est2 - ref2).abs().max() < 2e-4 * max(1.0, ref2.abs().max().item())
 
 
+@pytest.mark.parametrize("mode", ["C", "R"])
+def test_dccrn_mask_modes_host_logic(monkeypatch, mode):
+    """masking_mode 'C' / 'R' (DCCRN_cprs.py:221-224): same network, different mask rule."""
+    emu_ops.install(se_b200.ops, monkeypatch)
+    sd = synth.synthetic_state_dict(templates.dccrn_template(), seed=4)
+    m = se_b200.DCCRN(rnn_units=256, masking_mode=mode, use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256])
+    m.load_state_dict(sd)
+    x = torch.randn(1, 2, 257, 6, generator=torch.Generator().manual_seed(8))
+    est = m._forward_nhwc(x.permute(0, 3, 2, 1).contiguous()).permute(0, 3, 2, 1)
+    with torch.no_grad():
+        ref = nets.dccrn_forward(sd, x, masking_mode=mode)
+    assert (est - ref).abs().max() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
 def test_gcrn_host_logic_matches_oracle(monkeypatch):
     """Gated convs as [a | b] GEMMs, parity-class deconvs with output_padding, grouped-LSTM block weights and the
     three layout permutations (channels-last flatten, stack+flatten interleave, LayerNorm store index)."""
@@ -339,3 +353,36 @@ def test_enhance_dir_batches_equal_lengths_and_writes_pcm16(tmp_path):
     assert decode.enhancer_for(se_b200.crn_net()) is decode.enhance_crn
     assert decode.enhancer_for((None, None)) is decode.enhance_ctsnet
     assert decode.enhancer_for(se_b200.gcrn.Net()) is decode.enhance_gcrn
+
+
+def test_enhance_dir_resamples_mixed_rates(tmp_path, monkeypatch):
+    """``resample_to=16000`` (the *_decode_vb.py front step, lstm_decode_vb.py:33-34): files of different rates are
+    grouped by (rate, length), resampled before the decode loop, and written at ``fs``."""
+    from scipy.io import wavfile
+    from oracle import resample as R
+    decode = se_b200.decode
+    src, dst = tmp_path / "noisy", tmp_path / "out"
+    src.mkdir()
+    rng = np.random.default_rng(1)
+    files = {"a.wav": (48000, 2400), "b.wav": (16000, 800), "c.wav": (48000, 2400), "d.wav": (44100, 2205)}
+    for name, (sr, n) in files.items():
+        decode.write_wav(str(src / name), np.clip(rng.normal(0, 0.1, n), -0.9, 0.9), sr)
+
+    def fake_resample(x, sr_orig, sr_new, out=None):
+        return torch.from_numpy(np.stack([R.librosa_resample(r.double().numpy(), sr_orig, sr_new) for r in x])).float()
+
+    monkeypatch.setattr(se_b200.ops, "resample", fake_resample)
+    seen = []
+
+    def fake_enhance(model, wav):
+        seen.append(tuple(wav.shape))
+        return wav
+
+    n = decode.enhance_dir(None, str(src), str(dst), fs=16000, batch=8, device="cpu", enhance_fn=fake_enhance,
+                           resample_to=16000)
+    assert n == 4 and sorted(seen) == [(1, 800), (1, 800), (2, 800)]
+    for name, (sr, _) in files.items():
+        out_sr, y = wavfile.read(str(dst / name))
+        assert out_sr == 16000 and len(y) == 800
+        x, _ = decode.read_wav_any(str(src / name))
+        assert np.abs(y / 32768.0 - R.librosa_resample(x, sr, 16000)).max() <= 0.5 / 32768 + 1e-6

@@ -43,3 +43,65 @@ def test_rms_scale_and_length_rules():
     s = dsp.stft(xs, 320, 320, 160)
     y = dsp.istft(s, 320, 320, 160, length=9000)
     assert len(y) == 9000 and np.all(y[8160:] == 0)
+
+
+# ---- 48 kHz -> 16 kHz front step (oracle/resample.py; parity unpinned: resampy / librosa are not vendored) ---------
+def test_resample_oracle_lengths_and_identity():
+    from oracle import resample as R
+    x = np.random.default_rng(0).standard_normal(4801)
+    assert R.librosa_resample(x, 16000, 16000) is not None and np.array_equal(R.librosa_resample(x, 16000, 16000), x)
+    y = R.librosa_resample(x, 48000, 16000)
+    assert len(y) == int(np.ceil(4801 / 3)) == 1601 and y[-1] == 0.0        # resampy gives int(4801/3)=1600, fix pads
+    assert len(R.librosa_resample(x, 44100, 16000)) == int(np.ceil(4801 * 16000 / 44100))
+    assert len(R.librosa_resample(x[:800], 8000, 16000)) == 1600
+
+
+def test_resample_oracle_scalar_loop_equals_vectorised():
+    """The vectorised restatement against a literal transcription of the per-sample loop (short input)."""
+    from oracle import resample as R
+    x = np.random.default_rng(1).standard_normal(700)
+    for sr in (48000, 44100, 8000):
+        ratio = 16000.0 / sr
+        win, delta, nt = R.filter_tables(ratio)
+        n_out = int(len(x) * ratio)
+        got = R.resample_f(x, n_out, ratio, win, delta, nt)
+        scale = min(1.0, ratio)
+        step = int(scale * nt)
+        treg, ref = 0.0, np.zeros(n_out)
+        for t in range(n_out):
+            n = int(treg)
+            frac = scale * (treg - n)
+            off = int(frac * nt)
+            eta = frac * nt - off
+            for i in range(min(n + 1, (len(win) - off) // step)):
+                ref[t] += (win[off + i * step] + eta * delta[off + i * step]) * x[n - i]
+            frac = scale - frac
+            off = int(frac * nt)
+            eta = frac * nt - off
+            for k in range(min(len(x) - n - 1, (len(win) - off) // step)):
+                ref[t] += (win[off + k * step] + eta * delta[off + k * step]) * x[n + k + 1]
+            treg += 1.0 / ratio
+        assert np.abs(got - ref).max() < 1e-12
+
+
+def test_resample_oracle_properties():
+    """What any correct band-limited 3:1 decimator must do: pass-band tones land on the analytic 16 kHz tone (up to
+    the 0.3 % pass-band gain resampy's integer table stride gives), tones above 8 kHz vanish, and the result agrees
+    with scipy's polyphase resampler as far as two different anti-aliasing filters can."""
+    from scipy.signal import resample_poly
+    from oracle import resample as R
+    n = 24000
+    t = np.arange(n) / 48000.0
+    mid = slice(300, n // 3 - 300)
+    for f in (440.0, 3000.0, 6500.0):
+        y = R.librosa_resample(np.sin(2 * np.pi * f * t), 48000, 16000)
+        ref = np.sin(2 * np.pi * f * np.arange(len(y)) / 16000.0)
+        assert np.abs(y[mid] - ref[mid]).max() < 6e-3
+    y = R.librosa_resample(np.sin(2 * np.pi * 12000.0 * t), 48000, 16000)
+    assert np.abs(y[mid]).max() < 1e-3
+    x = np.random.default_rng(2).standard_normal(n)
+    for _ in range(3):
+        x = np.convolve(x, np.ones(16) / 16, mode="same")                      # -40 dB and falling above 4.5 kHz
+    y = R.librosa_resample(x, 48000, 16000)
+    assert np.sqrt(np.mean((y[mid] - resample_poly(x, 1, 3)[mid]) ** 2)) < 0.02 * np.sqrt(np.mean(y[mid] ** 2))
+

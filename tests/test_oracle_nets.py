@@ -84,6 +84,22 @@ def test_oracle_equals_reference_module(mdir, module, cls, tmpl, fwd):
         assert (net(x) - fwd(sd, x)).abs().max() < 1e-6   # same ATen ops; threading may reassociate
 
 
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("mode", ["E", "C", "R"])
+def test_dccrn_oracle_mask_modes_equal_reference_module(mode):
+    """All three masking modes of DCCRN.forward (DCCRN_cprs.py:206-224; the scripts only use 'E') against the
+    unmodified class (run with the restated complexnn)."""
+    mod = ref_shims.import_reference("DCCRN", "DCCRN_cprs")
+    net = mod.DCCRN(rnn_units=256, masking_mode=mode, use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256]).eval()
+    sd = synth.synthetic_state_dict(templates.dccrn_template(), seed=2)
+    net.load_state_dict(sd)
+    x = torch.randn(1, 2, 257, 7, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        ref = net(x)
+        got = nets.dccrn_forward(sd, x, masking_mode=mode)
+    assert (ref - got).abs().max() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
 CTS_CKPTS = {"ctsnet_ckpt": ("CTSNet__step1_vb_cts_noncprs_model_final.pth", "CTSNet__step2_vb_cts_noncprs_model.pth"),
              "ctsnet_new_ckpt": ("CTSNet_new__step1_vb_cts_cprs_model_final.pth", "CTSNet_new__step2_vb_cts_cprs_model.pth")}
 

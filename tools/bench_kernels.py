@@ -43,6 +43,26 @@ def main():
         ms = timeit(lambda: ops.gemm_tf32x3(x_hi, x_lo, w_hi, w_lo, bias, 4096, out=out2))
         res["gemm_tf32x3_25664x1024x4096"] = {"ms": ms, "tflops_fp32_equiv": fl / ms / 1e9, "split_ms": ms_split,
                                               "max_abs_diff_vs_simt": (out2 - ref).abs().max().item()}
+        # CTA-pair engine (cta_group::2, 256x256 tiles) on the same shape and on the FullSubNet sub-band cell GEMM
+        ops.set_gemm_engine(1)
+        out3 = torch.empty(M, 4096, device=dev)
+        ms = timeit(lambda: ops.gemm_tf32x3(x_hi, x_lo, w_hi, w_lo, bias, 4096, out=out3))
+        res["gemm_tf32x3_pair_25664x1024x4096"] = {"ms": ms, "tflops_fp32_equiv": fl / ms / 1e9,
+                                                   "max_abs_diff_vs_one_cta": (out3 - out2).abs().max().item()}
+        for eng in (0, 1):
+            ops.set_gemm_engine(eng)
+            m2, kx, h2 = 32 * 257, 384, 384
+            Pc = packing.pack_lstm_cell(torch.randn(4 * h2, kx, generator=g) / 20, torch.randn(4 * h2, h2, generator=g) / 20,
+                                        torch.zeros(4 * h2), torch.zeros(4 * h2))
+            Pc = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in Pc.items()}
+            xh, xl = ops.split_tf32(torch.randn(m2, kx, generator=g).to(dev))
+            hh, hl = ops.split_tf32(torch.randn(m2, h2, generator=g).to(dev) * 0.1)
+            c = torch.zeros(m2, h2, device=dev)
+            oh, ol, ho = (torch.empty(m2, h2, device=dev) for _ in range(3))
+            ms = timeit(lambda: ops.lstm_cell_tf32x3(xh, xl, hh, hl, Pc["w_hi"], Pc["w_lo"], Pc["bias"], c, oh, ol, ho), iters=10)
+            res[f"lstm_cell_tf32x3_engine{eng}_M{m2}_K{kx + h2}_H{h2}"] = {
+                "ms": ms, "tflops_fp32_equiv": 2.0 * m2 * (kx + h2) * 4 * h2 / ms / 1e9}
+        ops.set_gemm_engine(int(os.environ.get("SE_GEMM_ENGINE", "0")))
     xp = torch.randn(B, T, 4 * H, generator=g).to(dev)
     whh = (torch.randn(H // 8, H, 32, generator=g) / 32).to(dev)
     hs = torch.empty(B, T, H, device=dev)
