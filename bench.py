@@ -310,12 +310,15 @@ def main():
         achieved = rec_flops_per_launch / (rec_avg_ms * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         traffic = None
-        ncu_json = os.path.join(ROOT, "profiles", "ncu_full_r01.json")
         kname = "lstm_seq_tc_kernel"
-        if os.path.exists(ncu_json):      # dram__bytes_read.sum + dram__bytes_write.sum of the committed capture
-            for k in json.load(open(ncu_json))["kernels"]:
-                if k["kernel"].startswith(kname):
-                    traffic = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) * 1e6
+        # dram__bytes_read.sum + dram__bytes_write.sum (MB per launch) of the committed `ncu --set full` capture
+        for ncu_json in ("ncu_lstm_tc_r01b.json", "ncu_full_r01b.json", "ncu_full_r01.json"):
+            path = os.path.join(ROOT, "profiles", ncu_json)
+            if traffic is None and os.path.exists(path):
+                for k in json.load(open(path))["kernels"]:
+                    if kname in k["kernel"]:
+                        traffic = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) * 1e6
+                        break
         # the recurrence computes every product three times (3xTF32: hi*hi, hi*lo, lo*hi) on the TF32 tensor pipe
         tf32_peak = peak / 2.0
         roofline = {

@@ -202,10 +202,12 @@ int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xpro
  *   0 = fp32 FMA kernel (any H %% 128 == 0).
  * Measured on B200 (H = 1024, B = 64): 7.9 / 14.4 / 13.8 us per step, see DESIGN.md. */
 int se_set_lstm_engine(int engine);
-/* tcgen05 GEMM engine (process-global; se_gemm_tf32x3*, se_lstm_cell_tf32x3*):
+/* tcgen05 GEMM engine (process-global; se_gemm_tf32x3*, se_lstm_cell_tf32x3*, se_conv_tf32x3):
  *   0 = one CTA per 128 x 128 output tile (csrc/gemm_tc.cu: gemm_tf32x3_kernel) for every shape;
  *   1 = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, each SM stages half of the operands) where M >= 256 and
- *       N >= 256, the one-CTA kernel elsewhere.
+ *       N >= 256 (GEMM) / two activation tiles exist and Cout > 32 (conv), the one-CTA kernel elsewhere;
+ *   2 / 3 / 4 = the one-CTA MMA in clusters of 2 x 2 / 1 x 2 / 2 x 1 CTAs that read the operand tiles they have in
+ *       common from L2 once (TMA multicast): GEMM only, the conv kernel stays on engine 0.
  * SE_GEMM_ENGINE in the environment picks the start-up value. */
 int se_set_gemm_engine(int engine);
 /* Measurement aid for the tcgen05 engine: dev_buf (device, 128 * nsteps * 12 int64, or NULL to switch off)
@@ -337,10 +339,13 @@ int se_dccrn_mask_ex(const float* m, const float* x_re, const float* x_im, long 
  *     part as resampy.interpn.resample_f computes them (float64 index arithmetic).
  * x [B, n_in] (row stride x_stride), y [B, n_out] (row stride y_stride); samples t >= n_valid = int(n_in * ratio)
  * are zero (librosa's fix_length to ceil(n_in * ratio)).  win / delta: device tables of nwin floats (the half
- * window, already multiplied by ratio when decimating, and its forward difference). */
+ * window, already multiplied by ratio when decimating, and its forward difference).  time_reg: device table of
+ * n_valid doubles holding resample_f's time register (0, then += 1/ratio sequentially in float64) or NULL to use
+ * t * (1/ratio) -- identical when 1/ratio is exactly representable (48 k -> 16 k); at 44.1 k -> 16 k the exact
+ * time is an integer every 160 samples and the rounding of the running sum decides floor(time). */
 int se_resample(const float* x, long long x_stride, int B, int n_in, float* y, long long y_stride, int n_out,
-                int n_valid, double ratio, const float* win, const float* delta, int nwin, int num_table,
-                se_stream_t stream);
+                int n_valid, double ratio, const double* time_reg, const float* win, const float* delta, int nwin,
+                int num_table, se_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Uformer glue (Uformer/uformer.py:172-287, dilated_dualpath_conformer.py, fusion.py, t_att_*.py,

@@ -80,7 +80,7 @@ PROTOTYPES = {
     "se_cmul": (_I, [_P, _P, _LL, _P, _P]),
     "se_dccrn_mask": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
     "se_dccrn_mask_ex": (_I, [_P, _P, _P, _LL, _LL, _LL, _I, _I, _I, _I, _P, _P, _LL, _LL, _LL, _P]),
-    "se_resample": (_I, [_P, _LL, _I, _I, _P, _LL, _I, _I, C.c_double, _P, _P, _I, _I, _P]),
+    "se_resample": (_I, [_P, _LL, _I, _I, _P, _LL, _I, _I, C.c_double, _P, _P, _P, _I, _I, _P]),
     "se_chan_stats_ws_bytes": (_LL, [_I, _LL, _I]),
     "se_chan_stats": (_I, [_P, _I, _LL, _I, _I, _I, _P, _F, _P, _P, _P, _P]),
     "se_cum_stats": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P]),

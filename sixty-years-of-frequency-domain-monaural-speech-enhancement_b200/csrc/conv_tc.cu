@@ -14,12 +14,21 @@
 namespace se {
 
 constexpr int CT_BM = 128, CT_BK = 32;
-template <int BN>
-struct CtCfg {
-  static constexpr int STAGES = BN >= 128 ? 3 : 4;   // 64 KB stages at BN=128 (227 KB smem limit)
-};
 constexpr int CT_CHUNK_KB = 4;
 constexpr int CT_A_BYTES = CT_BM * CT_BK * 4;  // 16 KB per A tile (hi or lo)
+// PAIR = 1: CTA pairs (tcgen05 cta_group::2, see tc_common.cuh and gemm_tc.cu): the pair multiplies TWO activation
+// tiles (256 rows) by BN output channels, each CTA staging its own activation tile and HALF of the weight rows, so the
+// weight traffic per SM halves and Cout = 256 layers get a 256-wide tile (otherwise two 128-wide passes over the
+// activation).
+template <int BN, int PAIR>
+struct CtCfg {
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                   // weight rows this CTA stages
+  static constexpr int B_BYTES = B_ROWS * CT_BK * 4;
+  static constexpr int B_SLOT = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = 2 * CT_A_BYTES + 2 * B_SLOT;
+  static constexpr int STAGES = STAGE_BYTES >= 64 * 1024 ? 3 : 4;     // 227 KB smem limit
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
 constexpr int CT_THREADS = 320;
 constexpr int CT_EPI_WARPS = 8;
 
@@ -37,6 +46,14 @@ struct ConvTcParams {
   int a_bytes;                // bytes one A box writes (Tbox*Fout*128)
 };
 
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, unsigned leader_bar, void* dst, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -83,16 +100,18 @@ __device__ __forceinline__ void tmem_ld_cols<8>(unsigned taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int BN>
+template <int BN, int PAIR>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
                    const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                    const ConvTcParams p) {
-  constexpr int B_BYTES = BN * CT_BK * 4;
-  constexpr int STAGE_BYTES = 2 * CT_A_BYTES + 2 * ((B_BYTES + 1023) / 1024 * 1024);
-  constexpr int B_SLOT = (B_BYTES + 1023) / 1024 * 1024;
-  constexpr int CT_STAGES = CtCfg<BN>::STAGES;
+  using Cfg = CtCfg<BN, PAIR>;
+  constexpr int B_ROWS = Cfg::B_ROWS;
+  constexpr int B_BYTES = Cfg::B_BYTES;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int B_SLOT = Cfg::B_SLOT;
+  constexpr int CT_STAGES = Cfg::STAGES;
   constexpr int EPI_COLS = BN / 2;
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   extern __shared__ unsigned char smem_dyn[];
@@ -106,10 +125,14 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs of the pair)
+  const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int ttiles = ceil_div(p.T, p.Tbox);
-  const int mtiles = p.B * ttiles;
+  const int mtiles = p.B * ttiles;                              // activation tiles (Tbox frames of one clip)
+  const int munits = PAIR ? ceil_div(mtiles, 2) : mtiles;       // a pair takes tiles 2u (leader) and 2u + 1 (peer)
   const int ntiles_n = ceil_div(p.Cout, BN);
-  const int ntiles = mtiles * ntiles_n;
+  const int ntiles = munits * ntiles_n;
   const int kb_per_tap = p.kb0 + p.kb1;
   const int kblocks = p.ntaps * kb_per_tap;
 
@@ -120,7 +143,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], CT_EPI_WARPS);
+      mbar_init(&tempty[a], (PAIR ? 2 : 1) * CT_EPI_WARPS);
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_a0hi);
@@ -128,16 +151,25 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     tma_prefetch_desc(&map_bhi);
     tma_prefetch_desc(&map_blo);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);   // the same warp of both CTAs, same smem slot
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();   // barriers of both CTAs initialised, both allocations done, before any remote signal
+  }
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
-  // n fastest: consecutive CTAs share the same activation tile (L2) across output-channel tiles
+  // n fastest: consecutive CTAs share the same activation tile (L2) across output-channel tiles.  In pair mode an odd
+  // tile count leaves the last peer without a tile: b == B then, its TMA boxes are out of bounds (zero filled) and its
+  // epilogue skips the store.
   auto tile_coords = [&](int tile, int& b, int& t0, int& nb) {
     nb = tile % ntiles_n;
-    const int mt = tile / ntiles_n;
+    const int mt = (tile / ntiles_n) * (PAIR ? 2 : 1) + (int)rank;
     b = mt / ttiles;
     t0 = (mt - b * ttiles) * p.Tbox;
   };
@@ -146,7 +178,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     if (elect_one()) {
       int stage = 0;
       unsigned phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = cta; tile < ntiles; tile += nctas) {
         int b, t0, nb;
         tile_coords(tile, b, t0, nb);
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -154,17 +186,33 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
           const int r = kb - tap * kb_per_tap;
           mbar_wait_parity(&empty[stage], phase ^ 1);
           unsigned char* st = tiles + stage * STAGE_BYTES;
-          mbar_expect_tx(&full[stage], 2u * (unsigned)p.a_bytes + 2u * (unsigned)B_BYTES);
+          const unsigned stage_tx = 2u * (unsigned)p.a_bytes + 2u * (unsigned)B_BYTES;
           const int tt = t0 + p.dt[tap], ff = p.df[tap];
-          if (r < p.kb0) {
-            tma_load_4d(&map_a0hi, &full[stage], st, r * CT_BK, ff, tt, b);
-            tma_load_4d(&map_a0lo, &full[stage], st + CT_A_BYTES, r * CT_BK, ff, tt, b);
+          if constexpr (PAIR) {
+            const unsigned lbar = smem_u32(&full[stage]) & T2_PEER_BIT_MASK;
+            if (rank == 0) mbar_expect_tx(&full[stage], 2u * stage_tx);   // both CTAs' bytes land on this barrier
+            if (r < p.kb0) {
+              tma_load_4d_pair(&map_a0hi, lbar, st, r * CT_BK, ff, tt, b);
+              tma_load_4d_pair(&map_a0lo, lbar, st + CT_A_BYTES, r * CT_BK, ff, tt, b);
+            } else {
+              tma_load_4d_pair(&map_a1hi, lbar, st, (r - p.kb0) * CT_BK, ff, tt, b);
+              tma_load_4d_pair(&map_a1lo, lbar, st + CT_A_BYTES, (r - p.kb0) * CT_BK, ff, tt, b);
+            }
+            const int brow = nb * BN + (int)rank * B_ROWS;
+            tma_load_2d_pair(&map_bhi, lbar, st + 2 * CT_A_BYTES, kb * CT_BK, brow);
+            tma_load_2d_pair(&map_blo, lbar, st + 2 * CT_A_BYTES + B_SLOT, kb * CT_BK, brow);
           } else {
-            tma_load_4d(&map_a1hi, &full[stage], st, (r - p.kb0) * CT_BK, ff, tt, b);
-            tma_load_4d(&map_a1lo, &full[stage], st + CT_A_BYTES, (r - p.kb0) * CT_BK, ff, tt, b);
+            mbar_expect_tx(&full[stage], stage_tx);
+            if (r < p.kb0) {
+              tma_load_4d(&map_a0hi, &full[stage], st, r * CT_BK, ff, tt, b);
+              tma_load_4d(&map_a0lo, &full[stage], st + CT_A_BYTES, r * CT_BK, ff, tt, b);
+            } else {
+              tma_load_4d(&map_a1hi, &full[stage], st, (r - p.kb0) * CT_BK, ff, tt, b);
+              tma_load_4d(&map_a1lo, &full[stage], st + CT_A_BYTES, (r - p.kb0) * CT_BK, ff, tt, b);
+            }
+            tma_load_2d(&map_bhi, &full[stage], st + 2 * CT_A_BYTES, kb * CT_BK, nb * BN);
+            tma_load_2d(&map_blo, &full[stage], st + 2 * CT_A_BYTES + B_SLOT, kb * CT_BK, nb * BN);
           }
-          tma_load_2d(&map_bhi, &full[stage], st + 2 * CT_A_BYTES, kb * CT_BK, nb * BN);
-          tma_load_2d(&map_blo, &full[stage], st + 2 * CT_A_BYTES + B_SLOT, kb * CT_BK, nb * BN);
           if (++stage == CT_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -173,13 +221,13 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr unsigned idesc = make_idesc_tf32(CT_BM, BN);
+    if (rank == 0 && elect_one()) {
+      constexpr unsigned idesc = make_idesc_tf32(PAIR ? 2 * CT_BM : CT_BM, BN);
       int stage = 0;
       unsigned phase = 0;
       int acc = 0;
       unsigned acc_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = cta; tile < ntiles; tile += nctas) {
         for (int kb = 0; kb < kblocks; ++kb) {
           const bool chunk_start = (kb % CT_CHUNK_KB) == 0;
           if (chunk_start) {
@@ -197,17 +245,25 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
 #pragma unroll
           for (int k = 0; k < CT_BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-            umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
-            umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
-            umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            if constexpr (PAIR) {
+              umma_tf32_pair(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+              umma_tf32_pair(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_tf32_pair(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+              umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            }
           }
-          umma_commit(&empty[stage]);
+          if constexpr (PAIR) umma_commit_pair(&empty[stage]);
+          else umma_commit(&empty[stage]);
           if (++stage == CT_STAGES) {
             stage = 0;
             phase ^= 1;
           }
           if ((kb % CT_CHUNK_KB) == CT_CHUNK_KB - 1 || kb == kblocks - 1) {
-            umma_commit(&tfull[acc]);
+            if constexpr (PAIR) umma_commit_pair(&tfull[acc]);
+            else umma_commit(&tfull[acc]);
             if (++acc == 2) {
               acc = 0;
               acc_phase ^= 1;
@@ -222,7 +278,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     int acc = 0;
     unsigned acc_phase = 0;
     const int nchunks = (kblocks + CT_CHUNK_KB - 1) / CT_CHUNK_KB;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = cta; tile < ntiles; tile += nctas) {
       int b, t0, nb;
       tile_coords(tile, b, t0, nb);
       float sum[EPI_COLS];
@@ -232,15 +288,23 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
         mbar_wait_parity(&tfull[acc], acc_phase);
         tc_fence_after();
         {
-          float v[EPI_COLS];
-          const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN + half * EPI_COLS);
-          tmem_ld_cols<EPI_COLS>(taddr, v);
+          constexpr int PIECE = EPI_COLS > 64 ? 32 : EPI_COLS;   // 128 columns go through registers 32 at a time
 #pragma unroll
-          for (int j = 0; j < EPI_COLS; ++j) sum[j] += v[j];
+          for (int piece = 0; piece < EPI_COLS / PIECE; ++piece) {
+            float v[PIECE];
+            const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) +
+                                   (unsigned)(acc * BN + half * EPI_COLS + piece * PIECE);
+            tmem_ld_cols<PIECE>(taddr, v);
+#pragma unroll
+            for (int j = 0; j < PIECE; ++j) sum[piece * PIECE + j] += v[j];
+          }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(&tempty[acc], 0);   // the leader's MMA thread waits for both CTAs
+          else mbar_arrive(&tempty[acc]);
+        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -250,7 +314,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       const int tl = r / p.Fout;
       const int fo = r - tl * p.Fout;
       const int t = t0 + tl;
-      if (tl >= p.Tbox || t >= p.T) continue;
+      if (tl >= p.Tbox || t >= p.T || b >= p.B) continue;
       const long long orow =
           (((long long)b * p.T + t) * p.dstF + p.dst_f0 + (long long)fo * p.dst_fstep) * (long long)p.Cout;
       const int n0 = nb * BN + half * EPI_COLS;
@@ -274,9 +338,14 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();   // the peer's TMEM / barriers stay alive until the leader's last MMA and commit have landed
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -321,18 +390,38 @@ static int make_w_map(CUtensorMap* map, const float* ptr, int rows, int K, int b
   return SE_OK;
 }
 
-template <int BN>
+template <int BN, int PAIR>
 static int launch_conv_tc(const CUtensorMap* m, const ConvTcParams& p, int sms, cudaStream_t s) {
-  constexpr int B_SLOT = (BN * CT_BK * 4 + 1023) / 1024 * 1024;
-  constexpr int STAGE_BYTES = 2 * CT_A_BYTES + 2 * B_SLOT;
-  constexpr int SMEM = CtCfg<BN>::STAGES * STAGE_BYTES + 1024 + 256;
-  cudaError_t e = cudaFuncSetAttribute(conv_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  constexpr int SMEM = CtCfg<BN, PAIR>::SMEM;
+  cudaError_t e = cudaFuncSetAttribute(conv_tf32x3_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   if (e != cudaSuccess) {
     set_error("se_conv_tf32x3: smem attribute: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
-  const int tiles = p.B * ceil_div(p.T, p.Tbox) * ceil_div(p.Cout, BN);
-  conv_tf32x3_kernel<BN><<<min(sms, tiles), CT_THREADS, SMEM, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+  const int mtiles = p.B * ceil_div(p.T, p.Tbox);
+  if constexpr (PAIR) {
+    const int tiles = ceil_div(mtiles, 2) * ceil_div(p.Cout, BN);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * min(sms / 2, tiles)));
+    cfg.blockDim = dim3(CT_THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, conv_tf32x3_kernel<BN, PAIR>, m[0], m[1], m[2], m[3], m[4], m[5], p);
+    if (e != cudaSuccess) {
+      set_error("se_conv_tf32x3 (CTA pairs): cluster launch: %s", cudaGetErrorString(e));
+      return SE_ERR_CUDA;
+    }
+  } else {
+    const int tiles = mtiles * ceil_div(p.Cout, BN);
+    conv_tf32x3_kernel<BN, PAIR><<<min(sms, tiles), CT_THREADS, SMEM, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+  }
   return SE_OK;
 }
 
@@ -377,7 +466,9 @@ extern "C" int se_conv_tf32x3(const se_conv_tc_desc* d, se_stream_t stream) {
   p.dst_fstep = d->dst_fstep;
   p.a_bytes = p.Tbox * p.Fout * CT_BK * 4;
   const int K = d->ntaps * (d->C0 + d->C1);
-  const int BN = d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : (d->Cout > 16 ? 32 : 16));
+  // engine 1 (se_set_gemm_engine): CTA pairs where at least two activation tiles exist and the tile is >= 64 wide
+  const bool pair = gemm_engine_is_pair() && d->Cout > 32 && (long long)d->B * ceil_div(d->T, p.Tbox) >= 2;
+  const int BN = (pair && d->Cout > 128) ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : (d->Cout > 16 ? 32 : 16)));
   CUtensorMap m[6];
   int rc;
   if ((rc = make_act_map(&m[0], d->src0_hi, d->B, d->T, d->Fin, d->C0, d->Fout, d->sf, p.Tbox))) return rc;
@@ -389,17 +480,18 @@ extern "C" int se_conv_tf32x3(const se_conv_tc_desc* d, se_stream_t stream) {
     m[2] = m[0];
     m[3] = m[1];
   }
-  if ((rc = make_w_map(&m[4], d->w_hi, d->Cout, K, BN))) return rc;
-  if ((rc = make_w_map(&m[5], d->w_lo, d->Cout, K, BN))) return rc;
+  if ((rc = make_w_map(&m[4], d->w_hi, d->Cout, K, pair ? BN / 2 : BN))) return rc;
+  if ((rc = make_w_map(&m[5], d->w_lo, d->Cout, K, pair ? BN / 2 : BN))) return rc;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaStream_t s = (cudaStream_t)stream;
   switch (BN) {
-    case 128: rc = launch_conv_tc<128>(m, p, sms, s); break;
-    case 64: rc = launch_conv_tc<64>(m, p, sms, s); break;
-    case 32: rc = launch_conv_tc<32>(m, p, sms, s); break;
-    default: rc = launch_conv_tc<16>(m, p, sms, s); break;
+    case 256: rc = launch_conv_tc<256, 1>(m, p, sms, s); break;
+    case 128: rc = pair ? launch_conv_tc<128, 1>(m, p, sms, s) : launch_conv_tc<128, 0>(m, p, sms, s); break;
+    case 64: rc = pair ? launch_conv_tc<64, 1>(m, p, sms, s) : launch_conv_tc<64, 0>(m, p, sms, s); break;
+    case 32: rc = launch_conv_tc<32, 0>(m, p, sms, s); break;
+    default: rc = launch_conv_tc<16, 0>(m, p, sms, s); break;
   }
   if (rc) return rc;
   return check_launch("se_conv_tf32x3");

@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
 // taps per sample (385 at 48k -> 16k) re-read the input and the 128 KB table from L1/L2.
 __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, long long x_stride, int n_in,
                                                       float* __restrict__ y, long long y_stride, int n_out, int n_valid,
-                                                      double ratio, const float* __restrict__ win,
+                                                      double ratio, const double* __restrict__ time_reg_tab,
+                                                      const float* __restrict__ win,
                                                       const float* __restrict__ delta, int nwin, int num_table) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_out) return;
@@ -366,8 +367,11 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
   }
   const double scale = ratio < 1.0 ? ratio : 1.0;
   const int step = (int)(scale * (double)num_table);
-  // resample_f accumulates time_register += 1/ratio in float64; t * (1/ratio) differs from that sum by a few ulp
-  const double time_reg = (double)t * (1.0 / ratio);
+  // resample_f accumulates time_register += 1/ratio in float64.  Where the exact time is an integer (t = 160 k at
+  // 44.1 -> 16 kHz) the rounding of that sum decides floor(time), and with it which table entries are used (the table
+  // stride is truncated to an integer, so the two choices differ by ~1e-3): the caller passes the sequentially
+  // accumulated register; without it t * (1/ratio) is used (identical for exactly representable increments).
+  const double time_reg = time_reg_tab ? __ldg(time_reg_tab + t) : (double)t * (1.0 / ratio);
   const int n = (int)time_reg;
   double frac = scale * (time_reg - (double)n);
   double index_frac = frac * (double)num_table;
@@ -479,8 +483,8 @@ extern "C" int se_istft(int mode, const float* a_re, const float* a_im, long lon
 }
 
 extern "C" int se_resample(const float* x, long long x_stride, int B, int n_in, float* y, long long y_stride, int n_out,
-                           int n_valid, double ratio, const float* win, const float* delta, int nwin, int num_table,
-                           se_stream_t stream) {
+                           int n_valid, double ratio, const double* time_reg, const float* win, const float* delta,
+                           int nwin, int num_table, se_stream_t stream) {
   SE_REQUIRE(x && y && win && delta && B > 0 && n_in > 0 && n_out > 0, "se_resample: bad arguments");
   SE_REQUIRE(ratio > 0.0 && num_table > 0 && nwin > num_table, "se_resample: ratio=%g num_table=%d nwin=%d", ratio,
              num_table, nwin);
@@ -488,7 +492,7 @@ extern "C" int se_resample(const float* x, long long x_stride, int B, int n_in, 
   SE_REQUIRE(n_valid >= 0 && n_valid <= n_out && (double)(n_valid - 1) / ratio < (double)n_in,
              "se_resample: n_valid=%d reads past the input (n_in=%d ratio=%g)", n_valid, n_in, ratio);
   dim3 grid(ceil_div(n_out, 256), B);
-  resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride, n_in, y, y_stride, n_out, n_valid, ratio, win,
-                                                         delta, nwin, num_table);
+  resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride, n_in, y, y_stride, n_out, n_valid, ratio,
+                                                         time_reg, win, delta, nwin, num_table);
   return check_launch("se_resample");
 }

@@ -134,7 +134,14 @@ __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float
 }
 
 
-template <int EPI>
+// CM x CN > 1: a thread-block CLUSTER of CM x CN CTAs computes a (128 CM) x (128 CN) super-tile, every CTA its own
+// 128 x 128 tile with the one-CTA MMA.  The operand tiles the CTAs of a cluster row / column have in common are read
+// from L2 ONCE and TMA-multicast: with CN = 2 the CTA with rn = 0 loads A_hi and the one with rn = 1 loads A_lo of the
+// row's A tile, each into both CTAs; with CM = 2 likewise B_hi / B_lo down a column.  The kernel is bound by L2 -> SM
+// operand traffic (~8 TB/s aggregate: profiles/), which this cuts from 64 KB to 48 KB (1 x 2) or 32 KB (2 x 2) per
+// k-block and CTA.  A stage may be refilled only when every CTA that receives this CTA's multicast has consumed it:
+// `empty` counts CM + CN - 1 arrivals, each MMA thread commits to its row and column peers.
+template <int EPI, int CM, int CN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
                    const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
@@ -151,14 +158,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mblocks = ceil_div(p.M, TC_BM), nblocks = ceil_div(p.N, TC_BN);
+  constexpr int CSIZE = CM * CN;
+  const unsigned rank = CSIZE > 1 ? cluster_ctarank() : 0u;
+  const int rm = (int)rank / CN, rn = (int)rank % CN;             // position of this CTA in the cluster
+  const int cl = (int)blockIdx.x / CSIZE, ncl = (int)gridDim.x / CSIZE;
+  const int mblocks = ceil_div(p.M, TC_BM * CM), nblocks = ceil_div(p.N, TC_BN * CN);   // in super-tiles
   const int ntiles = mblocks * nblocks;
   const int kblocks = p.kb0 + p.kb1;
+  unsigned short row_mask = 0, col_mask = 0;                      // CTAs sharing my A tile / my B tile
+#pragma unroll
+  for (int j = 0; j < CN; ++j) row_mask |= (unsigned short)(1u << (rm * CN + j));
+#pragma unroll
+  for (int i = 0; i < CM; ++i) col_mask |= (unsigned short)(1u << (i * CN + rn));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CM + CN - 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -173,6 +189,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CSIZE > 1) {
+    __syncwarp();
+    cluster_sync_all();   // every CTA's barriers are initialised before a peer multicasts into it / signals them
+  }
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
@@ -182,8 +202,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     const int panel = tile / per_panel;
     const int r = tile - panel * per_panel;
     const int pm = min(p.panel_m, mblocks - panel * p.panel_m);
-    nb = r / pm;
-    mb = panel * p.panel_m + (r - nb * pm);
+    nb = (r / pm) * CN + rn;                                       // this CTA's 128 x 128 tile of the super-tile
+    mb = (panel * p.panel_m + (r - (r / pm) * pm)) * CM + rm;
   };
 
   if (warp == 0) {
@@ -191,22 +211,31 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     if (elect_one()) {
       int stage = 0;
       unsigned phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = cl; tile < ntiles; tile += ncl) {
         int mb, nb;
         tile_coords(tile, mb, nb);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait_parity(&empty[stage], phase ^ 1);
           unsigned char* st = tiles + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
-          if (kb < p.kb0) {
-            tma_load_2d(&map_a0hi, &full[stage], st + 0 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
-            tma_load_2d(&map_a0lo, &full[stage], st + 1 * TC_TILE_BYTES, kb * TC_BK, mb * TC_BM);
+          const bool src0 = kb < p.kb0;
+          const int ak = (src0 ? kb : kb - p.kb0) * TC_BK;
+          if constexpr (CN == 1) {
+            tma_load_2d(src0 ? &map_a0hi : &map_a1hi, &full[stage], st + 0 * TC_TILE_BYTES, ak, mb * TC_BM);
+            tma_load_2d(src0 ? &map_a0lo : &map_a1lo, &full[stage], st + 1 * TC_TILE_BYTES, ak, mb * TC_BM);
+          } else if (rn == 0) {   // my row's A_hi, into every CTA of the row (the rn = 1 CTA sends A_lo)
+            tma_load_2d_mc(src0 ? &map_a0hi : &map_a1hi, &full[stage], st + 0 * TC_TILE_BYTES, ak, mb * TC_BM, row_mask);
           } else {
-            tma_load_2d(&map_a1hi, &full[stage], st + 0 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, mb * TC_BM);
-            tma_load_2d(&map_a1lo, &full[stage], st + 1 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, mb * TC_BM);
+            tma_load_2d_mc(src0 ? &map_a0lo : &map_a1lo, &full[stage], st + 1 * TC_TILE_BYTES, ak, mb * TC_BM, row_mask);
           }
-          tma_load_2d(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
-          tma_load_2d(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
+          if constexpr (CM == 1) {
+            tma_load_2d(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
+            tma_load_2d(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
+          } else if (rm == 0) {   // my column's B_hi, into every CTA of the column (the rm = 1 CTA sends B_lo)
+            tma_load_2d_mc(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN, col_mask);
+          } else {
+            tma_load_2d_mc(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN, col_mask);
+          }
           if (++stage == TC_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -222,7 +251,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       unsigned phase = 0;
       int acc = 0;
       unsigned acc_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = cl; tile < ntiles; tile += ncl) {
         for (int kb = 0; kb < kblocks; ++kb) {
           const bool chunk_start = (kb % TC_CHUNK_KB) == 0;
           if (chunk_start) {
@@ -244,7 +273,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
             umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
             umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
           }
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it: tell every CTA that multicasts into this one
+          if constexpr (CSIZE > 1) umma_commit_mc(&empty[stage], (unsigned short)(row_mask | col_mask));
+          else umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -265,7 +296,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
     const int half = (warp - 2) >> 2;    // which 64 columns of the 128-column accumulator
     int acc = 0;
     unsigned acc_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = cl; tile < ntiles; tile += ncl) {
       int mb, nb;
       tile_coords(tile, mb, nb);
       const int row = mb * TC_BM + quarter * 32 + lane;
@@ -299,6 +330,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CSIZE > 1) {
+    __syncwarp();
+    cluster_sync_all();   // no CTA leaves while a peer may still multicast into its smem or signal its barriers
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
@@ -324,64 +359,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
 constexpr int T2_BN = 256;
 constexpr int T2_EPI_COLS = T2_BN / 2;                     // 128 columns per epilogue warp
 constexpr int T2_TMEM_COLS = 512;                          // 2 accumulators x 256 columns: all of tensor memory
-constexpr unsigned T2_PEER_BIT_MASK = 0xFEFFFFFFu;         // shared::cluster address of the same offset in CTA rank 0
-
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, unsigned leader_bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
-          "r"(smem_u32(dst)),
-      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32_pair(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc,
-                                               unsigned accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the barrier at this smem offset in BOTH CTAs of the pair once the MMAs issued so far have completed
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  const unsigned short mask = 3;
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
-                   "r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, unsigned rank) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 remote;\n"
-      "mapa.shared::cluster.u32 remote, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(rank)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(unsigned* smem_slot, unsigned ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(unsigned taddr, unsigned ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
@@ -631,20 +608,25 @@ extern "C" int se_split_tf32(const float* x, float* hi, float* lo, long long n, 
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
-// 0: gemm_tf32x3_kernel for every shape; 1: gemm_tf32x3_pair_kernel where M >= 256 and N >= 256.
-// SE_GEMM_ENGINE in the environment overrides the default; se_set_gemm_engine() overrides both.
+// 0: gemm_tf32x3_kernel<.., 1, 1> for every shape; 1: gemm_tf32x3_pair_kernel where M >= 256 and N >= 256;
+// 2 / 3 / 4: gemm_tf32x3_kernel in clusters of 2 x 2 / 1 x 2 / 2 x 1 CTAs with TMA-multicast operand tiles where the
+// problem has at least one full super-tile.  SE_GEMM_ENGINE in the environment overrides the default;
+// se_set_gemm_engine() overrides both.
 constexpr int kDefaultGemmEngine = 0;
+constexpr int kMaxGemmEngine = 4;
 static int g_gemm_engine = -1;
 static int gemm_engine() {
   if (g_gemm_engine < 0) {
     g_gemm_engine = kDefaultGemmEngine;
     if (const char* e = getenv("SE_GEMM_ENGINE")) {
       const int v = atoi(e);
-      if (v == 0 || v == 1) g_gemm_engine = v;
+      if (v >= 0 && v <= kMaxGemmEngine) g_gemm_engine = v;
     }
   }
   return g_gemm_engine;
 }
+
+int se::gemm_engine_is_pair() { return gemm_engine() == 1; }     // conv_tc.cu follows the same switch
 
 template <int EPI>
 static int launch_pair_kernel(const CUtensorMap& a0hi, const CUtensorMap& a0lo, const CUtensorMap& a1hi,
@@ -685,6 +667,54 @@ static int launch_tc_pair(int epi, const CUtensorMap& a0hi, const CUtensorMap& a
                              : launch_pair_kernel<EPI_LSTM_CELL>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
 }
 
+// gemm_tf32x3_kernel<EPI, CM, CN>: persistent grid of as many CM x CN clusters as are co-resident on the device (a
+// cluster that had to wait for a second wave would double the run time).
+template <int EPI, int CM, int CN>
+static int launch_tc_cluster(const CUtensorMap* const* m, TcParams p, int sms, cudaStream_t stream) {
+  constexpr int CSIZE = CM * CN;
+  auto kernel = gemm_tf32x3_kernel<EPI, CM, CN>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e != cudaSuccess) {
+    set_error("tcgen05 gemm: smem attribute: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  const int mblocks = ceil_div(p.M, TC_BM * CM), nblocks = ceil_div(p.N, TC_BN * CN);
+  p.panel_m = min(16 / CM, mblocks);
+  if constexpr (CSIZE == 1) {
+    const int grid = min(sms, mblocks * nblocks);
+    kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(*m[0], *m[1], *m[2], *m[3], *m[4], *m[5], p);
+    return SE_OK;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CSIZE;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  static int max_clusters = -1;           // per instantiation: co-resident clusters of this kernel on this device
+  if (max_clusters < 0) {
+    cfg.gridDim = dim3((unsigned)(sms / CSIZE * CSIZE));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)kernel, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = sms / CSIZE;
+    }
+    max_clusters = n;
+  }
+  cfg.gridDim = dim3((unsigned)(CSIZE * min(max_clusters, mblocks * nblocks)));
+  e = cudaLaunchKernelEx(&cfg, kernel, *m[0], *m[1], *m[2], *m[3], *m[4], *m[5], p);
+  if (e != cudaSuccess) {
+    set_error("tcgen05 gemm (%d x %d cluster): launch: %s", CM, CN, cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
 static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long lda0, int K0, const float* a1_hi,
                      const float* a1_lo, long long lda1, int K1, const float* b_hi, const float* b_lo, long long ldb,
                      TcParams p, cudaStream_t stream) {
@@ -706,29 +736,21 @@ static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   p.kb0 = K0 / TC_BK;
   p.kb1 = K1 / TC_BK;
-  if (gemm_engine() == 1 && p.M >= 2 * TC_BM && p.N >= T2_BN) return launch_tc_pair(epi, m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p, sms, stream);
-  const int mblocks = ceil_div(p.M, TC_BM), nblocks = ceil_div(p.N, TC_BN);
-  p.panel_m = min(16, mblocks);
-  const int grid = min(sms, mblocks * nblocks);
-  cudaError_t e;
-  if (epi == EPI_BIAS_ACT) {
-    e = cudaFuncSetAttribute(gemm_tf32x3_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (e == cudaSuccess)
-      gemm_tf32x3_kernel<EPI_BIAS_ACT><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p);
-  } else {
-    e = cudaFuncSetAttribute(gemm_tf32x3_kernel<EPI_LSTM_CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (e == cudaSuccess)
-      gemm_tf32x3_kernel<EPI_LSTM_CELL><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p);
-  }
-  if (e != cudaSuccess) {
-    set_error("tcgen05 gemm: smem attribute: %s", cudaGetErrorString(e));
-    return SE_ERR_CUDA;
-  }
-  return SE_OK;
+  const int engine = gemm_engine();
+  if (engine == 1 && p.M >= 2 * TC_BM && p.N >= T2_BN) return launch_tc_pair(epi, m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p, sms, stream);
+  const CUtensorMap* maps[6] = {&m_a0hi, &m_a0lo, &m_a1hi, &m_a1lo, &m_bhi, &m_blo};
+  if (engine == 2 && p.M >= 2 * TC_BM && p.N >= 2 * TC_BN)
+    return epi == EPI_BIAS_ACT ? launch_tc_cluster<EPI_BIAS_ACT, 2, 2>(maps, p, sms, stream) : launch_tc_cluster<EPI_LSTM_CELL, 2, 2>(maps, p, sms, stream);
+  if (engine == 3 && p.N >= 2 * TC_BN)
+    return epi == EPI_BIAS_ACT ? launch_tc_cluster<EPI_BIAS_ACT, 1, 2>(maps, p, sms, stream) : launch_tc_cluster<EPI_LSTM_CELL, 1, 2>(maps, p, sms, stream);
+  if (engine == 4 && p.M >= 2 * TC_BM)
+    return epi == EPI_BIAS_ACT ? launch_tc_cluster<EPI_BIAS_ACT, 2, 1>(maps, p, sms, stream) : launch_tc_cluster<EPI_LSTM_CELL, 2, 1>(maps, p, sms, stream);
+  return epi == EPI_BIAS_ACT ? launch_tc_cluster<EPI_BIAS_ACT, 1, 1>(maps, p, sms, stream) : launch_tc_cluster<EPI_LSTM_CELL, 1, 1>(maps, p, sms, stream);
 }
 
 extern "C" int se_set_gemm_engine(int engine) {
-  SE_REQUIRE(engine == 0 || engine == 1, "se_set_gemm_engine: 0 (one CTA per 128x128 tile) or 1 (CTA pairs, 256x256 tiles)");
+  SE_REQUIRE(engine >= 0 && engine <= kMaxGemmEngine,
+             "se_set_gemm_engine: 0 (one CTA per tile), 1 (CTA pairs), 2 / 3 / 4 (multicast clusters 2x2 / 1x2 / 2x1)");
   g_gemm_engine = engine;
   return SE_OK;
 }

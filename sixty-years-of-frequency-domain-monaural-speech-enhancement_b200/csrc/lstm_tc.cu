@@ -148,21 +148,6 @@ __device__ __forceinline__ void tmem_st_32x32(unsigned taddr, const unsigned (&r
       : "memory");
 }
 
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                               unsigned short mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-// the mbarrier at the same offset in every CTA of `mask` gets one arrival when this thread's MMAs have completed
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, unsigned short mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
-                   "r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
 // fast-math gates: ex2.approx + approximate divide, |error| ~ 2e-7 (fp32 rounding class); the accurate expf/tanhf/IEEE
 // divide of common.cuh cost 2800 cycles of a 20000-cycle step here (profiles/lstm_tc_phases_v1_r01.json)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }

@@ -360,6 +360,7 @@ def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf", mode="
 
 
 _RESAMPLE_TABLES = {}
+_RESAMPLE_TIME = {}
 
 
 def resample_tables(ratio, device):
@@ -396,11 +397,18 @@ def resample(x, sr_orig, sr_new, out=None):
     if n_valid < 1:
         raise ValueError("input too short to resample")
     win, delta, bits = resample_tables(ratio, x.device)
+    tkey = (float(ratio), n_valid, str(x.device))
+    if tkey not in _RESAMPLE_TIME:           # resample_f's time register: 0, += 1/ratio (sequential float64 adds)
+        import numpy as np
+        treg = np.concatenate([[0.0], np.cumsum(np.full(n_valid - 1, 1.0 / ratio, dtype=np.float64))])
+        _RESAMPLE_TIME.clear()               # one (ratio, length) at a time: corpora are processed group by group
+        _RESAMPLE_TIME[tkey] = torch.from_numpy(treg).to(x.device)
+    treg = _RESAMPLE_TIME[tkey]
     if out is None:
         out = torch.empty(b, n_out, device=x.device, dtype=torch.float32)
     with _Timed("resample"):
         check(_lib.load().se_resample(_ptr(x), x.stride(0), b, n_in, _ptr(out), out.stride(0), n_out, n_valid, ratio,
-                                      _ptr(win), _ptr(delta), win.numel(), bits, _stream()), "se_resample")
+                                      _ptr(treg), _ptr(win), _ptr(delta), win.numel(), bits, _stream()), "se_resample")
     return out
 
 
@@ -575,7 +583,8 @@ def set_lstm_engine(engine: int):
 
 
 def set_gemm_engine(engine: int):
-    """0 = one CTA per 128x128 tile, 1 = CTA pairs (cta_group::2, 256x256 tiles) where M, N >= 256."""
+    """0 = one CTA per 128x128 tile, 1 = CTA pairs (cta_group::2, 256x256 tiles) where M, N >= 256, 2 / 3 / 4 = multicast
+    clusters of 2x2 / 1x2 / 2x1 CTAs (see se_set_gemm_engine in the header)."""
     check(_lib.load().se_set_gemm_engine(int(engine)), "se_set_gemm_engine")
 
 

@@ -185,9 +185,11 @@ def test_lstm_cell_tf32x3_matches_recurrence(m, kx, h, steps):
 
 @pytest.mark.parametrize("m,k,n,act", [(256, 32, 256, "none"), (300, 1024, 256, "none"), (1000, 256, 4096, "softplus"),
                                        (2309, 2048, 512 + 164, "none"), (25664, 1024, 4096, "none")])
-def test_gemm_pair_engine_matches_fp64_and_single_cta(m, k, n, act):
-    """CTA-pair (cta_group::2, 256x256 tiles) engine: fp32-class error vs fp64 on a row sample (first / last rows and a
-    random draw), and agreement with the one-CTA engine on the WHOLE output (both add the same products in the same
+@pytest.mark.parametrize("engine", [1, 2, 3, 4])
+def test_gemm_pair_engine_matches_fp64_and_single_cta(m, k, n, act, engine):
+    """CTA-pair (engine 1: cta_group::2, 256x256 tiles) and multicast-cluster (engines 2 / 3 / 4: 2x2, 1x2, 2x1 CTAs
+    sharing TMA-multicast operand tiles) engines: fp32-class error vs fp64 on a row sample (first / last rows and a
+    random draw), and agreement with the one-CTA engine on the WHOLE output (all add the same products in the same
     k order, promoted to fp32 registers every 4 k-blocks)."""
     dev = _dev()
     import se_b200
@@ -201,7 +203,7 @@ def test_gemm_pair_engine_matches_fp64_and_single_cta(m, k, n, act):
     try:
         ops.set_gemm_engine(0)
         one = ops.gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias.to(dev), n, act)
-        ops.set_gemm_engine(1)
+        ops.set_gemm_engine(engine)
         two = ops.gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias.to(dev), n, act)
         torch.cuda.synchronize()
     finally:
@@ -211,7 +213,7 @@ def test_gemm_pair_engine_matches_fp64_and_single_cta(m, k, n, act):
     ref = emu_ops._act(a[rows].double() @ w.double().t() + bias.double(), act)
     err = (two.cpu()[rows].double() - ref).abs().max().item()
     diff = (two - one).abs().max().item()
-    print(f"gemm pair engine {m}x{k}x{n}: max err vs fp64 {err:.3e}, vs one-CTA engine {diff:.3e}")
+    print(f"gemm engine {engine} {m}x{k}x{n}: max err vs fp64 {err:.3e}, vs one-CTA engine {diff:.3e}")
     assert err < 1e-5 and diff < 1e-5
 
 
@@ -229,7 +231,7 @@ def test_lstm_cell_pair_engine_matches_single_cta(m, kx, h, steps):
     xs = torch.randn(steps, m, kx, generator=g).to(dev)
     res = []
     try:
-        for eng in (0, 1):
+        for eng in (0, 1, 2, 3, 4):
             ops.set_gemm_engine(eng)
             c = torch.zeros(m, h, device=dev)
             hbuf = [(torch.zeros(m, h, device=dev), torch.zeros(m, h, device=dev)) for _ in range(2)]
@@ -242,10 +244,11 @@ def test_lstm_cell_pair_engine_matches_single_cta(m, kx, h, steps):
             res.append((hout.clone(), c.clone(), (dst[0] + dst[1]).clone()))
     finally:
         ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
-    for a, b, nm in zip(res[0], res[1], ("h", "c", "hi+lo")):
-        d = (a - b).abs().max().item()
-        print(f"lstm_cell pair engine M={m} H={h}: {nm} diff {d:.3e}")
-        assert d < 1e-5
+    for eng in (1, 2, 3, 4):
+        for a, b, nm in zip(res[0], res[eng], ("h", "c", "hi+lo")):
+            d = (a - b).abs().max().item()
+            print(f"lstm_cell engine {eng} M={m} H={h}: {nm} diff {d:.3e}")
+            assert d < 1e-5
 
 
 TC_CONV_CASES = [
@@ -263,9 +266,21 @@ TC_CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", TC_CONV_CASES)
-def test_conv_tf32x3_matches_semantics(case):
-    """Tensor-core implicit-GEMM conv (4-D TMA A tiles) vs the declared conv semantics in fp64."""
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("case", TC_CONV_CASES + [(3, 5, 9, 128, 0, 256, "crn_conv"),     # odd tile count, one 256 tile
+                                                  (1, 1, 8, 256, 0, 192, "dccrn_conv")])  # a single activation tile
+def test_conv_tf32x3_matches_semantics(case, engine):
+    """Tensor-core implicit-GEMM conv (4-D TMA A tiles) vs the declared conv semantics in fp64; engine 1 = CTA pairs
+    (cta_group::2: two activation tiles per MMA, 256-wide tiles for Cout > 128)."""
+    import se_b200
+    try:
+        se_b200.ops.set_gemm_engine(engine)
+        _conv_tf32x3_case(case)
+    finally:
+        se_b200.ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
+
+
+def _conv_tf32x3_case(case):
     dev = _dev()
     import se_b200
     from se_b200 import packing

@@ -43,13 +43,14 @@ def main():
         ms = timeit(lambda: ops.gemm_tf32x3(x_hi, x_lo, w_hi, w_lo, bias, 4096, out=out2))
         res["gemm_tf32x3_25664x1024x4096"] = {"ms": ms, "tflops_fp32_equiv": fl / ms / 1e9, "split_ms": ms_split,
                                               "max_abs_diff_vs_simt": (out2 - ref).abs().max().item()}
-        # CTA-pair engine (cta_group::2, 256x256 tiles) on the same shape and on the FullSubNet sub-band cell GEMM
-        ops.set_gemm_engine(1)
-        out3 = torch.empty(M, 4096, device=dev)
-        ms = timeit(lambda: ops.gemm_tf32x3(x_hi, x_lo, w_hi, w_lo, bias, 4096, out=out3))
-        res["gemm_tf32x3_pair_25664x1024x4096"] = {"ms": ms, "tflops_fp32_equiv": fl / ms / 1e9,
-                                                   "max_abs_diff_vs_one_cta": (out3 - out2).abs().max().item()}
-        for eng in (0, 1):
+        # other engines on the same shape: 1 = CTA pairs (cta_group::2, 256x256 tiles), 2 / 3 / 4 = multicast clusters
+        for eng in (1, 2, 3, 4):
+            ops.set_gemm_engine(eng)
+            out3 = torch.empty(M, 4096, device=dev)
+            ms = timeit(lambda: ops.gemm_tf32x3(x_hi, x_lo, w_hi, w_lo, bias, 4096, out=out3))
+            res[f"gemm_tf32x3_engine{eng}_25664x1024x4096"] = {"ms": ms, "tflops_fp32_equiv": fl / ms / 1e9,
+                                                             "max_abs_diff_vs_one_cta": (out3 - out2).abs().max().item()}
+        for eng in (0, 1, 2, 3, 4):
             ops.set_gemm_engine(eng)
             m2, kx, h2 = 32 * 257, 384, 384
             Pc = packing.pack_lstm_cell(torch.randn(4 * h2, kx, generator=g) / 20, torch.randn(4 * h2, h2, generator=g) / 20,
