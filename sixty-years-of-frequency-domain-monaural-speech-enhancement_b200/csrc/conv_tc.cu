@@ -100,6 +100,33 @@ __device__ __forceinline__ void tmem_ld_cols<8>(unsigned taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Store epilogue of one thread: NC consecutive output channels [n0, n0 + NC) of one output position (row offset
+// `orow`): bias + activation, fp32 and / or the TF32 split for the next layer.  Cout % 4 == 0 (host check), so the
+// channels go four at a time; like the GEMM epilogue (gemm_tc.cu) this code runs on the warps that drain the TMEM chunk
+// sums, so it is kept short: activation as a template parameter, float4 bias loads.
+template <int NC, int ACT>
+__device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float (&sum)[NC], long long orow, int n0) {
+  const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) {
+    if (n0 + j >= p.Cout) break;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias_vec) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+    else if (p.bias) bb = make_float4(__ldg(p.bias + n0 + j), __ldg(p.bias + n0 + j + 1), __ldg(p.bias + n0 + j + 2),
+                                      __ldg(p.bias + n0 + j + 3));
+    const float o[4] = {tc_act<ACT>(sum[j] + bb.x, p.act_param), tc_act<ACT>(sum[j + 1] + bb.y, p.act_param),
+                        tc_act<ACT>(sum[j + 2] + bb.z, p.act_param), tc_act<ACT>(sum[j + 3] + bb.w, p.act_param)};
+    if (p.out) *reinterpret_cast<float4*>(p.out + orow + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+    if (p.out_hi) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+      *reinterpret_cast<float4*>(p.out_hi + orow + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(p.out_lo + orow + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 template <int BN, int PAIR>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
@@ -113,7 +140,8 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   constexpr int B_SLOT = Cfg::B_SLOT;
   constexpr int CT_STAGES = Cfg::STAGES;
   constexpr int EPI_COLS = BN / 2;
-  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int NACC = BN >= 256 ? 2 : 4;                       // TMEM accumulator ring (512 columns in all)
+  constexpr int TMEM_COLS = (NACC * BN < 32) ? 32 : NACC * BN;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = base;
@@ -121,8 +149,8 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   uint64_t* full = bars;
   uint64_t* empty = bars + CT_STAGES;
   uint64_t* tfull = bars + 2 * CT_STAGES;
-  uint64_t* tempty = tfull + 2;
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + 2);
+  uint64_t* tempty = tfull + NACC;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + NACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs of the pair)
@@ -141,7 +169,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], (PAIR ? 2 : 1) * CT_EPI_WARPS);
     }
@@ -264,7 +292,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
           if ((kb % CT_CHUNK_KB) == CT_CHUNK_KB - 1 || kb == kblocks - 1) {
             if constexpr (PAIR) umma_commit_pair(&tfull[acc]);
             else umma_commit(&tfull[acc]);
-            if (++acc == 2) {
+            if (++acc == NACC) {
               acc = 0;
               acc_phase ^= 1;
             }
@@ -305,7 +333,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
           if constexpr (PAIR) mbar_arrive_cluster(&tempty[acc], 0);   // the leader's MMA thread waits for both CTAs
           else mbar_arrive(&tempty[acc]);
         }
-        if (++acc == 2) {
+        if (++acc == NACC) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -318,21 +346,14 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       const long long orow =
           (((long long)b * p.T + t) * p.dstF + p.dst_f0 + (long long)fo * p.dst_fstep) * (long long)p.Cout;
       const int n0 = nb * BN + half * EPI_COLS;
-#pragma unroll
-      for (int j = 0; j < EPI_COLS; j += 4) {
-        float o[4], hi[4], lo[4];
-        if (n0 + j >= p.Cout) break;  // Cout is a multiple of 4 (checked on the host)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float bb = p.bias ? __ldg(p.bias + n0 + j + e) : 0.f;
-          o[e] = apply_act(sum[j + e] + bb, p.act, p.act_param);
-          split_tf32_dev(o[e], hi[e], lo[e]);
-        }
-        if (p.out) *reinterpret_cast<float4*>(p.out + orow + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-        if (p.out_hi) {
-          *reinterpret_cast<float4*>(p.out_hi + orow + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(p.out_lo + orow + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
+      switch (p.act) {   // uniform: one branch per tile, the activation itself is a template parameter
+        case SE_ACT_PRELU: conv_tc_store<EPI_COLS, SE_ACT_PRELU>(p, sum, orow, n0); break;
+        case SE_ACT_ELU: conv_tc_store<EPI_COLS, SE_ACT_ELU>(p, sum, orow, n0); break;
+        case SE_ACT_SOFTPLUS: conv_tc_store<EPI_COLS, SE_ACT_SOFTPLUS>(p, sum, orow, n0); break;
+        case SE_ACT_RELU: conv_tc_store<EPI_COLS, SE_ACT_RELU>(p, sum, orow, n0); break;
+        case SE_ACT_SIGMOID: conv_tc_store<EPI_COLS, SE_ACT_SIGMOID>(p, sum, orow, n0); break;
+        case SE_ACT_TANH: conv_tc_store<EPI_COLS, SE_ACT_TANH>(p, sum, orow, n0); break;
+        default: conv_tc_store<EPI_COLS, SE_ACT_NONE>(p, sum, orow, n0); break;
       }
     }
   }

@@ -15,7 +15,7 @@
 //   warps 2-9: epilogue      -- tcgen05.ld (32 lanes x 64 columns each: 4 lane quarters x 2 column
 //                              halves), fp32 promotion, bias + activation / LSTM cell, st.global
 //   smem ring: STAGES x {A_hi, A_lo, B_hi, B_lo} tiles of 128 rows x 32 fp32 (128-byte rows)
-//   TMEM     : 2 accumulators of 128 lanes x 128 columns, used as a ping-pong over K-CHUNKS:
+//   TMEM     : a ring of 4 accumulators of 128 lanes x 128 columns, one per K-CHUNK in flight:
 //              the tensor core's fp32 accumulate truncates (measured: error grows linearly with
 //              the number of accumulation steps, 3.4e-5 at K=1024), so every TC_CHUNK_KB k-blocks
 //              the partial sum is promoted to fp32 registers of the epilogue warps (round-to-
@@ -34,7 +34,9 @@ constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;          // A_hi, A_lo, B_hi, 
 constexpr int TC_THREADS = 320;                            // 2 control warps + 8 epilogue warps
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_COLS = TC_BN / 2;                     // columns per epilogue warp
-constexpr int TC_TMEM_COLS = 256;                          // 2 x 128-column accumulators
+constexpr int TC_NACC = 4;                                 // TMEM accumulators in the ring: the MMA thread runs up to 4 chunks
+                                                           // ahead of the epilogue warps (which also run the store epilogue)
+constexpr int TC_TMEM_COLS = TC_NACC * TC_BN;              // 4 x 128 columns: all of tensor memory (one CTA per SM)
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum { EPI_BIAS_ACT = 0, EPI_LSTM_CELL = 1 };
@@ -65,38 +67,74 @@ struct TcParams {
 //   EPI_BIAS_ACT : C = alpha * act(sum + bias) + res, optional TF32 split of the result
 //   EPI_LSTM_CELL: every 64-column group g64 = n / 64 holds [i | f | g | o] x 16 hidden units [16 g64, 16 g64 + 16)
 //                  of sequence `row`: gates -> c, h, and the TF32 split of h for the next step's GEMM
+// The 8 epilogue warps are also the ones that drain the TMEM chunk sums, and the MMA thread can only run as far ahead
+// as there are free accumulators, so the instruction count here bounds the whole kernel (ncu, round 1: 57 % of all
+// samples sat in a per-element version of this code -- activation switch, scalar bias loads and range checks for each
+// of the 64 columns -- while the tensor pipe idled at 36 %).  Hence: the activation is a template parameter, the
+// in-range aligned case moves bias / residual as float4, and the gates use ex2.approx + fast divide (|err| ~ 2e-7,
+// the forms the recurrence kernel csrc/lstm_tc.cu has been parity-tested with).
+template <int NC, int ACT>
+__device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float (&sum)[NC], int row, int n0) {
+  const long long roff = (long long)row * p.ldc;
+  const bool vec = (p.ldc & 3) == 0;
+  const float* bias = p.bias;
+  const float* res = p.res ? p.res + roff : nullptr;
+  if (vec && n0 + NC <= p.N && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+    // whole span in range, 16-byte aligned rows: float4 traffic only, no per-element checks
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      const float4 bb = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float o[4] = {tc_act<ACT>(sum[j] + bb.x, p.act_param) * p.alpha, tc_act<ACT>(sum[j + 1] + bb.y, p.act_param) * p.alpha,
+                    tc_act<ACT>(sum[j + 2] + bb.z, p.act_param) * p.alpha, tc_act<ACT>(sum[j + 3] + bb.w, p.act_param) * p.alpha};
+      if (res) {
+        const float4 rr = __ldg(reinterpret_cast<const float4*>(res + n0 + j));
+        o[0] += rr.x;
+        o[1] += rr.y;
+        o[2] += rr.z;
+        o[3] += rr.w;
+      }
+      if (p.C) *reinterpret_cast<float4*>(p.C + roff + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+      if (p.c_hi) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+        *reinterpret_cast<float4*>(p.c_hi + roff + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(p.c_lo + roff + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    return;
+  }
+  // ragged edge (N not a multiple of the span, or rows that are not 16-byte aligned): element by element
+#pragma unroll   // fully unrolled: a dynamic index would move sum[] to local memory for the whole kernel
+  for (int j = 0; j < NC; ++j) {
+    const int n = n0 + j;
+    if (n < p.N) {
+      float o = tc_act<ACT>(sum[j] + (bias ? __ldg(bias + n) : 0.f), p.act_param) * p.alpha;
+      if (res) o += __ldg(res + n);
+      if (p.C) p.C[roff + n] = o;
+      if (p.c_hi) split_tf32_dev(o, p.c_hi[roff + n], p.c_lo[roff + n]);
+    }
+  }
+}
+
+// ex2.approx + approximate divide; the accurate expf / tanhf / IEEE divide cost ~4x the instructions
+__device__ __forceinline__ float tc_fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tc_fast_tanh(float x) {
+  const float t = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
 template <int EPI, int NC>
 __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float (&sum)[NC], int row, int n0) {
   if constexpr (EPI == EPI_BIAS_ACT) {
-    const long long roff = (long long)row * p.ldc;
-    const bool vec = (p.ldc & 3) == 0;
-#pragma unroll
-    for (int j = 0; j < NC; j += 4) {
-      float o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = n0 + j + e;
-        const float bb = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
-        o[e] = apply_act(sum[j + e] + bb, p.act, p.act_param) * p.alpha;
-        if (p.res && n < p.N) o[e] += __ldg(p.res + roff + n);
-      }
-      if (vec && n0 + j + 3 < p.N) {
-        if (p.C) *reinterpret_cast<float4*>(p.C + roff + n0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-        if (p.c_hi) {
-          float hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
-          *reinterpret_cast<float4*>(p.c_hi + roff + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(p.c_lo + roff + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n0 + j + e < p.N) {
-            if (p.C) p.C[roff + n0 + j + e] = o[e];
-            if (p.c_hi) split_tf32_dev(o[e], p.c_hi[roff + n0 + j + e], p.c_lo[roff + n0 + j + e]);
-          }
-      }
+    switch (p.act) {   // uniform across the grid: one predictable branch per tile instead of one per element
+      case SE_ACT_PRELU: tc_store_bias_act<NC, SE_ACT_PRELU>(p, sum, row, n0); break;
+      case SE_ACT_ELU: tc_store_bias_act<NC, SE_ACT_ELU>(p, sum, row, n0); break;
+      case SE_ACT_SOFTPLUS: tc_store_bias_act<NC, SE_ACT_SOFTPLUS>(p, sum, row, n0); break;
+      case SE_ACT_RELU: tc_store_bias_act<NC, SE_ACT_RELU>(p, sum, row, n0); break;
+      case SE_ACT_SIGMOID: tc_store_bias_act<NC, SE_ACT_SIGMOID>(p, sum, row, n0); break;
+      case SE_ACT_TANH: tc_store_bias_act<NC, SE_ACT_TANH>(p, sum, row, n0); break;
+      default: tc_store_bias_act<NC, SE_ACT_NONE>(p, sum, row, n0); break;
     }
   } else {
     static_assert(NC % 64 == 0, "the fused LSTM cell works on whole 64-column gate groups");
@@ -107,21 +145,25 @@ __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float
       const int unit0 = (nq >> 6) * 16;
       const long long off = (long long)row * p.H + unit0;
       const long long hoff = (long long)row * p.ld_hout + unit0;
-      const float* bias = p.bias + nq;
+      const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nq);   // 16-byte aligned (checked on the host)
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
         const float4 cold = p.first_step ? make_float4(0.f, 0.f, 0.f, 0.f)
                                          : *reinterpret_cast<const float4*>(p.c_state + off + u);
+        const float4 bi = __ldg(bias4 + (u >> 2)), bf = __ldg(bias4 + 4 + (u >> 2)), bg = __ldg(bias4 + 8 + (u >> 2)),
+                     bo = __ldg(bias4 + 12 + (u >> 2));
         const float co[4] = {cold.x, cold.y, cold.z, cold.w};
+        const float vbi[4] = {bi.x, bi.y, bi.z, bi.w}, vbf[4] = {bf.x, bf.y, bf.z, bf.w}, vbg[4] = {bg.x, bg.y, bg.z, bg.w},
+                    vbo[4] = {bo.x, bo.y, bo.z, bo.w};
         float cn[4], hn[4], hh[4], hl[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float ig = sigmoid_f(sum[q * 64 + u + e] + __ldg(bias + u + e));
-          const float fg = sigmoid_f(sum[q * 64 + 16 + u + e] + __ldg(bias + 16 + u + e));
-          const float gg = tanhf(sum[q * 64 + 32 + u + e] + __ldg(bias + 32 + u + e));
-          const float og = sigmoid_f(sum[q * 64 + 48 + u + e] + __ldg(bias + 48 + u + e));
+          const float ig = tc_fast_sigmoid(sum[q * 64 + u + e] + vbi[e]);
+          const float fg = tc_fast_sigmoid(sum[q * 64 + 16 + u + e] + vbf[e]);
+          const float gg = tc_fast_tanh(sum[q * 64 + 32 + u + e] + vbg[e]);
+          const float og = tc_fast_sigmoid(sum[q * 64 + 48 + u + e] + vbo[e]);
           cn[e] = fg * co[e] + ig * gg;
-          hn[e] = og * tanhf(cn[e]);
+          hn[e] = og * tc_fast_tanh(cn[e]);
           split_tf32_dev(hn[e], hh[e], hl[e]);
         }
         *reinterpret_cast<float4*>(p.c_state + off + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
@@ -132,7 +174,6 @@ __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float
     }
   }
 }
-
 
 // CM x CN > 1: a thread-block CLUSTER of CM x CN CTAs computes a (128 CM) x (128 CN) super-tile, every CTA its own
 // 128 x 128 tile with the one-CTA MMA.  The operand tiles the CTAs of a cluster row / column have in common are read
@@ -153,9 +194,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* full = bars;                   // [STAGES]
   uint64_t* empty = bars + TC_STAGES;      // [STAGES]
-  uint64_t* tfull = bars + 2 * TC_STAGES;  // [2]
-  uint64_t* tempty = tfull + 2;            // [2]
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + 2);
+  uint64_t* tfull = bars + 2 * TC_STAGES;  // [TC_NACC]
+  uint64_t* tempty = tfull + TC_NACC;      // [TC_NACC]
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + TC_NACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int CSIZE = CM * CN;
@@ -176,7 +217,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CM + CN - 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < TC_NACC; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], TC_EPI_WARPS);  // one arrive per epilogue warp
     }
@@ -282,7 +323,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
           }
           if ((kb % TC_CHUNK_KB) == TC_CHUNK_KB - 1 || kb == kblocks - 1) {
             umma_commit(&tfull[acc]);  // chunk accumulator complete
-            if (++acc == 2) {
+            if (++acc == TC_NACC) {
               acc = 0;
               acc_phase ^= 1;
             }
@@ -319,7 +360,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
-        if (++acc == 2) {
+        if (++acc == TC_NACC) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -804,7 +845,7 @@ extern "C" int se_lstm_cell_tf32x3_ex(const float* x_hi, const float* x_lo, long
              "se_lstm_cell_tf32x3: leading dims must be %% 4 (ld_hout=%lld)", ld_hout);
   SE_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(h_hi) && aligned16(h_lo) && aligned16(w_hi) &&
                  aligned16(w_lo) && aligned16(c_state) && aligned16(h_hi_out) && aligned16(h_lo_out) &&
-                 (!h_out || aligned16(h_out)),
+                 (!h_out || aligned16(h_out)) && aligned16(bias),
              "se_lstm_cell_tf32x3: pointers must be 16-byte aligned");
   SE_REQUIRE(first_step || (h_hi != h_hi_out && h_lo != h_lo_out), "se_lstm_cell_tf32x3: state must be double buffered");
   TcParams p{};

@@ -217,6 +217,18 @@ __device__ __forceinline__ void split_tf32_dev(float x, float& hi, float& lo) {
   lo = __uint_as_float(lb);
 }
 
+// activation selected at compile time (the epilogues branch once per tile, not once per element)
+template <int ACT>
+__device__ __forceinline__ float tc_act(float x, float param) {
+  if constexpr (ACT == SE_ACT_PRELU) return x >= 0.0f ? x : param * x;
+  else if constexpr (ACT == SE_ACT_ELU) return elu_f(x);
+  else if constexpr (ACT == SE_ACT_SOFTPLUS) return softplus_f(x);
+  else if constexpr (ACT == SE_ACT_RELU) return fmaxf(x, 0.0f);
+  else if constexpr (ACT == SE_ACT_SIGMOID) return sigmoid_f(x);
+  else if constexpr (ACT == SE_ACT_TANH) return tanhf(x);
+  else return x;
+}
+
 // driver entry point for tensor-map encoding (no link-time libcuda dependency); defined in gemm_tc.cu
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
