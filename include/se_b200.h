@@ -194,10 +194,13 @@ int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xpro
                       long long whh_group_stride, int ngroups, int B, int T, int H, float* hseq, long long hseq_sb,
                       long long hseq_st, long long hseq_group_off, float* work, unsigned* sync, se_stream_t stream);
 /* Recurrence engine (process-global; for A/B measurements and tests):
- *   2 (default) = tcgen05 cluster kernel (csrc/lstm_tc.cu: W_hh hi part in tensor memory, K split over a cluster of
+ *   3 (default) = as 2, plus the sequence-parallel kernel for H = 128 (csrc/lstm.cu: lstm_seq_small_kernel -- all of
+ *       W_hh resident in one CTA's registers + shared memory, 1 / 2 / 4 whole sequences per CTA, no device-wide
+ *       barrier): DPCRN's inter-chunk LSTM, DCCRN's real / imaginary LSTMs;
+ *   2 = tcgen05 cluster kernel (csrc/lstm_tc.cu: W_hh hi part in tensor memory, K split over a cluster of
  *       4 CTAs with a DSMEM reduction) where it applies -- H = 1024, one group, 32 clusters of 4 co-resident -- and
  *       the FMA kernel elsewhere;
- *       (SE_LSTM_ENGINE=0..2 in the environment picks the start-up value for A/B runs);
+ *       (SE_LSTM_ENGINE=0..3 in the environment picks the start-up value for A/B runs);
  *   1 = legacy mma.sync TF32 path with the 3xTF32 split (H in {128, 512, 1024});
  *   0 = fp32 FMA kernel (any H %% 128 == 0).
  * Measured on B200 (H = 1024, B = 64): 7.9 / 14.4 / 13.8 us per step, see DESIGN.md. */
@@ -207,7 +210,8 @@ int se_set_lstm_engine(int engine);
  *   1 = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, each SM stages half of the operands) where M >= 256 and
  *       N >= 256 (GEMM) / two activation tiles exist and Cout > 32 (conv), the one-CTA kernel elsewhere;
  *   2 / 3 / 4 = the one-CTA MMA in clusters of 2 x 2 / 1 x 2 / 2 x 1 CTAs that read the operand tiles they have in
- *       common from L2 once (TMA multicast): GEMM only, the conv kernel stays on engine 0.
+ *       common from L2 once (TMA multicast): GEMM only, the conv kernel stays on engine 0;
+ *   5 (default) = CTA pairs for GEMMs with K >= 384, M >= 256 and N >= 256, engine 0 for everything else.
  * SE_GEMM_ENGINE in the environment picks the start-up value. */
 int se_set_gemm_engine(int engine);
 /* Measurement aid for the tcgen05 engine: dev_buf (device, 128 * nsteps * 12 int64, or NULL to switch off)

@@ -651,10 +651,14 @@ static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 // 0: gemm_tf32x3_kernel<.., 1, 1> for every shape; 1: gemm_tf32x3_pair_kernel where M >= 256 and N >= 256;
 // 2 / 3 / 4: gemm_tf32x3_kernel in clusters of 2 x 2 / 1 x 2 / 2 x 1 CTAs with TMA-multicast operand tiles where the
-// problem has at least one full super-tile.  SE_GEMM_ENGINE in the environment overrides the default;
+// problem has at least one full super-tile; 5 (default): the pair kernel for GEMMs with K >= 384 (12 k-blocks), M >= 256
+// and N >= 256, the one-CTA kernel elsewhere -- what measured fastest per shape on B200 after the epilogue rewrite
+// (profiles/kbench_r01f.json: 0.83 vs 0.89 ms on the CRN projection, FullSubNet +7 %; short-K GEMMs and the convs of the
+// TCM models were 2-6 % slower on pairs).  SE_GEMM_ENGINE in the environment overrides the default;
 // se_set_gemm_engine() overrides both.
-constexpr int kDefaultGemmEngine = 0;
-constexpr int kMaxGemmEngine = 4;
+constexpr int kDefaultGemmEngine = 5;
+constexpr int kMaxGemmEngine = 5;
+constexpr int kAutoPairMinKBlocks = 12;
 static int g_gemm_engine = -1;
 static int gemm_engine() {
   if (g_gemm_engine < 0) {
@@ -778,7 +782,8 @@ static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long 
   p.kb0 = K0 / TC_BK;
   p.kb1 = K1 / TC_BK;
   const int engine = gemm_engine();
-  if (engine == 1 && p.M >= 2 * TC_BM && p.N >= T2_BN) return launch_tc_pair(epi, m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p, sms, stream);
+  if ((engine == 1 || (engine == 5 && p.kb0 + p.kb1 >= kAutoPairMinKBlocks)) && p.M >= 2 * TC_BM && p.N >= T2_BN)
+    return launch_tc_pair(epi, m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p, sms, stream);
   const CUtensorMap* maps[6] = {&m_a0hi, &m_a0lo, &m_a1hi, &m_a1lo, &m_bhi, &m_blo};
   if (engine == 2 && p.M >= 2 * TC_BM && p.N >= 2 * TC_BN)
     return epi == EPI_BIAS_ACT ? launch_tc_cluster<EPI_BIAS_ACT, 2, 2>(maps, p, sms, stream) : launch_tc_cluster<EPI_LSTM_CELL, 2, 2>(maps, p, sms, stream);
@@ -791,7 +796,7 @@ static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long 
 
 extern "C" int se_set_gemm_engine(int engine) {
   SE_REQUIRE(engine >= 0 && engine <= kMaxGemmEngine,
-             "se_set_gemm_engine: 0 (one CTA per tile), 1 (CTA pairs), 2 / 3 / 4 (multicast clusters 2x2 / 1x2 / 2x1)");
+             "se_set_gemm_engine: 0 (one CTA per tile), 1 (CTA pairs), 2 / 3 / 4 (multicast clusters 2x2 / 1x2 / 2x1), 5 (auto)");
   g_gemm_engine = engine;
   return SE_OK;
 }

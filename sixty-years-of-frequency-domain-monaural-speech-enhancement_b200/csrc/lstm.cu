@@ -211,6 +211,117 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_kernel(const LstmPar
 
 
 // ================================================================================================
+// Sequence-parallel recurrence for SMALL hidden sizes (H = 128: DPCRN's inter-chunk LSTM, DCCRN's real / imaginary
+// LSTMs).  W_hh is only 4H x H x 4 B = 256 KB there, so ONE CTA can hold all of it -- half in registers (64 per
+// thread: thread j owns gate column j, k = 0..63), half in shared memory ([64][512] floats, conflict-free) -- and run
+// NS whole sequences through all T steps on its own: no device-wide barrier, no h exchange through L2.  The slice
+// kernel above spends ~9 us per step on those (barrier + L2 round trip) for 33 MFLOP of work; here a step is the
+// matvec (128 FFMA per sequence and thread) plus two __syncthreads.
+// Same contract as lstm_seq_kernel (packed whh / xproj column order, groups); grid = groups x ceil(B / NS).
+// ================================================================================================
+constexpr int kSmallH = 128;
+constexpr int kSmallThreads = 4 * kSmallH;          // one thread per gate column
+constexpr int kSmallKReg = kSmallH / 2;             // k rows of W_hh kept in registers
+
+template <int NS>
+__global__ void __launch_bounds__(kSmallThreads, 1) lstm_seq_small_kernel(const LstmParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = kSmallH, NCOL = 4 * kSmallH;
+  float* Ws = reinterpret_cast<float*>(smem_raw);              // [H - kSmallKReg][NCOL]   k = 64..127
+  float* hs = Ws + (size_t)(H - kSmallKReg) * NCOL;            // [NS][H]     h_{t-1}
+  float* gs = hs + NS * H;                                     // [NS][NCOL]  gate pre-activations
+  const int j = threadIdx.x;                                   // packed gate column: slice * 32 + gate * 8 + unit
+  const int per_group = (p.B + NS - 1) / NS;
+  const int group = blockIdx.x / per_group;
+  const int b0 = (blockIdx.x - group * per_group) * NS;        // first sequence of this CTA
+  const float* xproj = p.xproj + group * p.xp_goff;
+  const float* whh = p.whh + group * p.whh_gstride;
+  float* hseq = p.hseq + group * p.hs_goff;
+
+  // resident weights: whh[(slice * H + k) * 32 + (j % 32)], slice = j / 32
+  const float* wcol = whh + (size_t)(j >> 5) * H * kNC + (j & 31);
+  float wreg[kSmallKReg];
+#pragma unroll
+  for (int k = 0; k < kSmallKReg; ++k) wreg[k] = __ldg(wcol + (size_t)k * kNC);
+  for (int k = kSmallKReg; k < H; ++k) Ws[(size_t)(k - kSmallKReg) * NCOL + j] = __ldg(wcol + (size_t)k * kNC);
+
+  // gate phase: thread (s, u) = (j / H, j % H) for j < NS * H owns cell state c of unit u of sequence s
+  const int gs_s = j / H, gs_u = j - gs_s * H;
+  const bool gate_thread = j < NS * H && b0 + gs_s < p.B;
+  const int gcol = (gs_u >> 3) * kNC + (gs_u & 7);             // column of gate 0 of unit u; gate g at + 8 g
+  float c_state = 0.f;
+
+  float xg[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    xg[s] = (b0 + s < p.B) ? __ldg(xproj + ((size_t)(b0 + s) * p.T) * (size_t)p.xp_stride + j) : 0.f;
+  __syncthreads();
+
+  for (int t = 0; t < p.T; ++t) {
+    float acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = xg[s];
+    if (t + 1 < p.T) {   // next step's input projection: independent of the recurrence, in flight during the matvec
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (b0 + s < p.B) xg[s] = __ldg(xproj + ((size_t)(b0 + s) * p.T + t + 1) * (size_t)p.xp_stride + j);
+    }
+    if (t > 0) {
+#pragma unroll
+      for (int k = 0; k < kSmallKReg; k += 4) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float4 h4 = *reinterpret_cast<const float4*>(hs + s * H + k);     // broadcast
+          acc[s] = fmaf(wreg[k], h4.x, acc[s]);
+          acc[s] = fmaf(wreg[k + 1], h4.y, acc[s]);
+          acc[s] = fmaf(wreg[k + 2], h4.z, acc[s]);
+          acc[s] = fmaf(wreg[k + 3], h4.w, acc[s]);
+        }
+      }
+#pragma unroll 4
+      for (int k = kSmallKReg; k < H; k += 4) {
+        const float w0 = Ws[(size_t)(k - kSmallKReg) * NCOL + j], w1 = Ws[(size_t)(k + 1 - kSmallKReg) * NCOL + j],
+                    w2 = Ws[(size_t)(k + 2 - kSmallKReg) * NCOL + j], w3 = Ws[(size_t)(k + 3 - kSmallKReg) * NCOL + j];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float4 h4 = *reinterpret_cast<const float4*>(hs + s * H + k);
+          acc[s] = fmaf(w0, h4.x, acc[s]);
+          acc[s] = fmaf(w1, h4.y, acc[s]);
+          acc[s] = fmaf(w2, h4.z, acc[s]);
+          acc[s] = fmaf(w3, h4.w, acc[s]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) gs[s * NCOL + j] = acc[s];
+    __syncthreads();              // all pre-activations written; every thread is done reading h_{t-1}
+    if (gate_thread) {
+      const float* g = gs + gs_s * NCOL + gcol;
+      const float ig = sigmoid_f(g[0]);
+      const float fg = sigmoid_f(g[kHU]);
+      const float gg = tanhf(g[2 * kHU]);
+      const float og = sigmoid_f(g[3 * kHU]);
+      c_state = fg * c_state + ig * gg;
+      const float h = og * tanhf(c_state);
+      hs[gs_s * H + gs_u] = h;
+      hseq[(size_t)(b0 + gs_s) * p.hs_sb + (size_t)t * p.hs_st + gs_u] = h;
+    }
+    __syncthreads();              // h_t visible before the next matvec
+  }
+}
+
+template <int NS>
+static cudaError_t launch_lstm_small(const LstmParams& p, cudaStream_t s) {
+  const size_t smem = ((size_t)(kSmallH - kSmallKReg) * 4 * kSmallH + (size_t)NS * kSmallH + (size_t)NS * 4 * kSmallH) *
+                      sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(lstm_seq_small_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = p.ngroups * ((p.B + NS - 1) / NS);
+  lstm_seq_small_kernel<NS><<<grid, kSmallThreads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ================================================================================================
 // Tensor-core variant of the same recurrence: legacy mma.sync m16n8k8 TF32 with the 3xTF32 split.
 //   * W_hh_hi (TF32) stays in REGISTERS for the whole sequence (A fragments: 2 m-tiles x KT k-tiles
 //     x 4 = 128 registers per thread at H = 1024), W_hh_lo in shared memory in fragment order as
@@ -424,16 +535,18 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
 }
 
 // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu) where it applies (H = 1024, one
-// group, clusters fit the device), the FMA kernel elsewhere.
+// group, clusters fit the device), the FMA kernel elsewhere; 3 (default): as 2, plus the sequence-parallel kernel
+// (lstm_seq_small_kernel) for H = 128.
 // -1 = not chosen yet: SE_LSTM_ENGINE in the environment (A/B runs), else the default.
 static int g_lstm_engine = -1;
-constexpr int kDefaultLstmEngine = 2;
+constexpr int kDefaultLstmEngine = 3;
+constexpr int kMaxLstmEngine = 3;
 static int lstm_engine() {
   if (g_lstm_engine < 0) {
     g_lstm_engine = kDefaultLstmEngine;
     if (const char* e = getenv("SE_LSTM_ENGINE")) {
       const int v = atoi(e);
-      if (v >= 0 && v <= 2) g_lstm_engine = v;
+      if (v >= 0 && v <= kMaxLstmEngine) g_lstm_engine = v;
     }
   }
   return g_lstm_engine;
@@ -497,7 +610,17 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
                whh_group_stride, hseq_group_off};
   void* args[] = {(void*)&p};
   const int engine = lstm_engine();
-  if (engine == 2 && H == LT_H_PUBLIC && ngroups == 1 && lstm_tc_supported())
+  if (engine == 3 && H == kSmallH) {
+    // sequences per CTA: as few as keep the grid within one wave (fewer sequences = shorter steps)
+    const int ns = ngroups * B <= sms ? 1 : (ngroups * ((B + 1) / 2) <= sms ? 2 : 4);
+    e = ns == 1 ? launch_lstm_small<1>(p, s) : (ns == 2 ? launch_lstm_small<2>(p, s) : launch_lstm_small<4>(p, s));
+    if (e != cudaSuccess) {
+      set_error("se_lstm_seq (sequence-parallel, H = 128): launch: %s", cudaGetErrorString(e));
+      return SE_ERR_CUDA;
+    }
+    return SE_OK;
+  }
+  if (engine >= 2 && H == LT_H_PUBLIC && ngroups == 1 && lstm_tc_supported())
     return lstm_seq_tc_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, sync, s);
   if (engine == 1 && (H == 1024 || H == 512 || H == 128)) {
     e = H == 1024 ? launch_lstm_mma<16>(p, G, s) : (H == 512 ? launch_lstm_mma<8>(p, G, s) : launch_lstm_mma<2>(p, G, s));
@@ -524,7 +647,8 @@ extern "C" int se_debug_lstm_tc_profile(long long* dev_buf, int first_step, int 
 }
 
 extern "C" int se_set_lstm_engine(int engine) {
-  SE_REQUIRE(engine >= 0 && engine <= 2, "se_set_lstm_engine: 0 (fp32 FMA), 1 (mma.sync 3xTF32) or 2 (tcgen05)");
+  SE_REQUIRE(engine >= 0 && engine <= kMaxLstmEngine,
+             "se_set_lstm_engine: 0 (fp32 FMA), 1 (mma.sync 3xTF32), 2 (tcgen05) or 3 (tcgen05 + sequence-parallel H = 128)");
   g_lstm_engine = engine;
   return SE_OK;
 }

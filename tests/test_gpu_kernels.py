@@ -17,7 +17,7 @@ def _dev():
     return torch.device("cuda:0")
 
 
-DEFAULT_GEMM_ENGINE = int(os.environ.get("SE_GEMM_ENGINE", "0"))   # csrc/gemm_tc.cu: kDefaultGemmEngine
+DEFAULT_GEMM_ENGINE = int(os.environ.get("SE_GEMM_ENGINE", "5"))   # csrc/gemm_tc.cu: kDefaultGemmEngine
 
 CONV_CASES = [
     # B, T, Fin, C0, C1, Cout, kind
@@ -409,12 +409,14 @@ def test_attention_matches_softmax(over_t, cplx):
     assert err < 2e-5
 
 
-DEFAULT_LSTM_ENGINE = 2
+DEFAULT_LSTM_ENGINE = 3
 
 
-@pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (1024, 5, 3), (1024, 64, 401), (512, 7, 9), (128, 33, 15)])
+@pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (1024, 5, 3), (1024, 64, 401), (512, 7, 9), (128, 33, 15), (128, 64, 401),
+                                   (128, 1, 2)])
 def test_lstm_engines_agree(h, b, t):
-    """fp32 FMA / mma.sync 3xTF32 / tcgen05 3xTF32 (H = 1024 only, else the FMA kernel) recurrences vs fp64."""
+    """fp32 FMA / mma.sync 3xTF32 / tcgen05 3xTF32 (H = 1024 only, else the FMA kernel) / default (3: tcgen05 at H = 1024,
+    the sequence-parallel kernel at H = 128) recurrences vs fp64."""
     dev = _dev()
     import se_b200
     ops = se_b200.ops
@@ -424,14 +426,15 @@ def test_lstm_engines_agree(h, b, t):
     ref = emu_ops.lstm_seq(xp.double(), whh.double(), h)
     errs = []
     try:
-        for eng in (0, 1, 2):
+        for eng in (0, 1, 2, 3):
             ops.set_lstm_engine(eng)
             got = ops.lstm_seq(xp.to(dev), whh.to(dev), h)
             torch.cuda.synchronize()
             errs.append((got.cpu().double() - ref).abs().max().item())
     finally:
         ops.set_lstm_engine(DEFAULT_LSTM_ENGINE)
-    print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}, tcgen05 err {errs[2]:.3e}")
+    print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}, tcgen05 err {errs[2]:.3e}, "
+          f"default err {errs[3]:.3e}")
     assert max(errs) < 2e-5
 
 
@@ -517,19 +520,41 @@ def test_lstm_cell_ex_strided_bidirectional(m):
     assert err < 2e-5
 
 
-def test_lstm_seq_multi_shared_weights():
+@pytest.mark.parametrize("engine", [0, 3])
+@pytest.mark.parametrize("b", [9, 37, 64])       # engine 3 at H = 128: 1 / 1 / 2 sequences per CTA with 4 groups
+def test_lstm_seq_multi_shared_weights(b, engine):
     """Groups that share one W_hh (DPCRN inter-LSTM: the 4 frequency positions of a frame)."""
     dev = _dev()
     import se_b200
     ops = se_b200.ops
     g = torch.Generator().manual_seed(5)
-    b, t, h, ng = 9, 12, 128, 4
+    t, h, ng = 12, 128, 4
     xp = torch.randn(b, t, ng * 4 * h, generator=g)
     whh = torch.randn(h // 8, h, 32, generator=g) / np.sqrt(h)
     out = torch.empty(b, t, ng * h, device=dev)
-    ops.lstm_seq_multi(xp.to(dev), whh.to(dev), h, ng, out)
+    try:
+        ops.set_lstm_engine(engine)
+        ops.lstm_seq_multi(xp.to(dev), whh.to(dev), h, ng, out)
+    finally:
+        ops.set_lstm_engine(DEFAULT_LSTM_ENGINE)
     ref = emu_ops.lstm_seq_multi(xp.double(), whh.double(), h, ng, torch.empty(b, t, ng * h, dtype=torch.float64))
     assert (out.cpu().double() - ref).abs().max() < 2e-5
+
+
+def test_lstm_seq_small_eight_groups_four_sequences_per_cta():
+    """Sequence-parallel H = 128 kernel with 8 groups x 64 sequences = 512 sequences: 4 per CTA (128 CTAs)."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(6)
+    b, t, h, ng = 64, 7, 128, 8
+    xp = torch.randn(b, t, ng * 4 * h, generator=g)
+    whh = torch.randn(ng, h // 8, h, 32, generator=g) / np.sqrt(h)
+    out = torch.empty(b, t, ng * h, device=dev)
+    ops.lstm_seq_multi(xp.to(dev), whh.to(dev), h, ng, out)
+    for k in range(ng):
+        ref = emu_ops.lstm_seq(xp[:, :, k * 4 * h:(k + 1) * 4 * h].double(), whh[k].double(), h)
+        assert (out[:, :, k * h:(k + 1) * h].cpu().double() - ref).abs().max() < 2e-5
 
 
 @pytest.mark.parametrize("b,rows,c,pre", [(3, 401 * 79, 64, "glu"), (2, 401, 128, "prelu"), (5, 161 * 50, 1, "glu"),

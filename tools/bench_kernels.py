@@ -63,7 +63,7 @@ def main():
             ms = timeit(lambda: ops.lstm_cell_tf32x3(xh, xl, hh, hl, Pc["w_hi"], Pc["w_lo"], Pc["bias"], c, oh, ol, ho), iters=10)
             res[f"lstm_cell_tf32x3_engine{eng}_M{m2}_K{kx + h2}_H{h2}"] = {
                 "ms": ms, "tflops_fp32_equiv": 2.0 * m2 * (kx + h2) * 4 * h2 / ms / 1e9}
-        ops.set_gemm_engine(int(os.environ.get("SE_GEMM_ENGINE", "0")))
+        ops.set_gemm_engine(int(os.environ.get("SE_GEMM_ENGINE", "5")))
     xp = torch.randn(B, T, 4 * H, generator=g).to(dev)
     whh = (torch.randn(H // 8, H, 32, generator=g) / 32).to(dev)
     hs = torch.empty(B, T, H, device=dev)
@@ -76,7 +76,21 @@ def main():
             ref_h = hs.clone()
         else:
             res[f"lstm_seq_{nm}_B64_T401_H1024"]["max_abs_diff_vs_fma"] = (hs - ref_h).abs().max().item()
-    ops.set_lstm_engine(2)
+    # H = 128 recurrences: DPCRN inter-chunk LSTM (4 frequency positions x 64 clips, shared weights) and DCCRN's four real
+    # LSTMs (32 clips): slice kernel with a device-wide barrier per step (engine 0) vs the sequence-parallel kernel (3)
+    for nm, ng, bb, tt, shared in (("dpcrn_inter", 4, 64, 401, True), ("dccrn_clstm", 4, 32, 501, False)):
+        xp2 = torch.randn(bb, tt, ng * 512, generator=g).to(dev)
+        w2 = (torch.randn(*(() if shared else (ng,)), 16, 128, 32, generator=g) / 11.3).to(dev)
+        o2 = torch.empty(bb, tt, ng * 128, device=dev)
+        for eng in (0, 3):
+            ops.set_lstm_engine(eng)
+            ms = timeit(lambda: ops.lstm_seq_multi(xp2, w2, 128, ng, o2), iters=3, warm=1)
+            res[f"lstm_seq_multi_{nm}_engine{eng}"] = {"ms": ms, "us_per_step": 1e3 * ms / tt}
+            if eng == 0:
+                ref2 = o2.clone()
+            else:
+                res[f"lstm_seq_multi_{nm}_engine{eng}"]["max_abs_diff_vs_engine0"] = (o2 - ref2).abs().max().item()
+    ops.set_lstm_engine(3)
     # conv layers of CRN
     for (fin, c0, c1, co, kind) in [(9, 128, 0, 256, "conv"), (19, 64, 0, 128, "conv"), (4, 256, 256, 128, "deconv"),
                                     (9, 128, 128, 64, "deconv")]:
