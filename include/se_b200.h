@@ -231,6 +231,10 @@ long long se_lstm_seq_work_bytes(int B, int H);
  *                     weight_ih_l* [4H, K] (CRN/CRN.py:20).
  * ------------------------------------------------------------------------------------- */
 int se_split_tf32(const float* x, float* hi, float* lo, long long n, se_stream_t stream);
+/* The same for rows of K floats that are zero-padded to Kpad >= K (Kpad %% 4 == 0) on the way: x [rows, K] ->
+ * hi / lo [rows, Kpad].  Lets a K that is not a multiple of 32 (the 161 bins entering LSTM/LSTM.py:17) use
+ * se_gemm_tf32x3 against weights padded the same way. */
+int se_pad_split_tf32(const float* x, long long rows, int K, int Kpad, float* hi, float* lo, se_stream_t stream);
 int se_gemm_tf32x3(const float* a_hi, const float* a_lo, long long lda, const float* b_hi, const float* b_lo,
                    long long ldb, int M, int N, int K, const float* bias, int act, float* C, long long ldc,
                    se_stream_t stream);

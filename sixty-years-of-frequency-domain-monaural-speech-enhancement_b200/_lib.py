@@ -60,6 +60,7 @@ PROTOTYPES = {
     "se_set_gemm_engine": (_I, [_I]),
     "se_lstm_seq_work_bytes": (_LL, [_I, _I]),
     "se_split_tf32": (_I, [_P, _P, _P, _LL, _P]),
+    "se_pad_split_tf32": (_I, [_P, _LL, _I, _I, _P, _P, _P]),
     "se_gemm_tf32x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _P, _LL, _P]),
     "se_gemm_tf32x3_ex": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _P, _I, _F, _F, _P, _P, _P, _P, _LL, _P]),
     "se_lstm_cell_tf32x3": (_I, [_P, _P, _LL, _I, _P, _P, _LL, _I, _P, _P, _LL, _P, _I, _P, _P, _P, _P, _P]),

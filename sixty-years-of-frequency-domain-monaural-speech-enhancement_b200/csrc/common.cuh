@@ -42,6 +42,14 @@ __device__ __forceinline__ float apply_act(float x, int act, float param = 0.0f)
   }
 }
 
+// fast-math gates: ex2.approx + approximate divide, |error| ~ 2e-7 (fp32 rounding class); the accurate expf/tanhf/IEEE
+// divide of common.cuh cost 2800 cycles of a 20000-cycle step here (profiles/lstm_tc_phases_v1_r01.json)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float t = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
 // ---- packed fp32x2 FMA (Blackwell FFMA2) -----------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(SE_NO_FFMA2)

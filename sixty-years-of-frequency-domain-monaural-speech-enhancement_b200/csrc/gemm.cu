@@ -330,6 +330,96 @@ __global__ void __launch_bounds__(256) deconv_out1_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Narrow-output variant of the same contract (Cout <= 4: the last decoder layers that emit the 2-channel RI spectrum
+// or a 1-channel mask -- CTSNet/Step2_network.py de5, DCCRN decoder.5, DPCRN's CRM head).  The tiled kernel above
+// computes a 16- or 32-wide column tile whatever Cout is, i.e. 8-16x the useful FMAs.  Here one WARP owns one output
+// position: the lanes stride over the channels of every tap with float4 loads (one coalesced 512-byte request per
+// tap and 128 channels), keep NCO partial sums each, and finish with a shuffle reduction.  The weights (K x NCO
+// floats) sit in shared memory.  HBM / L2-bound: every activation element is read ntaps / sf times, mostly from L1/L2.
+// ---------------------------------------------------------------------------------------------
+template <int NCO>
+__global__ void __launch_bounds__(256) conv_narrow_kernel(const ConvParams P) {
+  extern __shared__ __align__(16) float wsm[];   // [K][NCO]
+  const se_conv_desc& d = P.d;
+  for (int i = threadIdx.x; i < P.K * NCO; i += blockDim.x) {
+    const int k = i / NCO, co = i - k * NCO;
+    wsm[i] = co < d.Cout ? __ldg(d.W + (size_t)k * d.ldw + co) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const long long warp0 = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * warps_per_cta;
+  for (long long m = warp0; m < P.M; m += nwarps) {
+    const int fo = (int)(m % d.Fout);
+    const long long bt = m / d.Fout;
+    const int t = (int)(bt % d.T);
+    const long long bT = bt - t;
+    float acc[NCO];
+#pragma unroll
+    for (int co = 0; co < NCO; ++co) acc[co] = 0.f;
+    for (int tap = 0; tap < d.ntaps; ++tap) {
+      const int ti = t + d.dt[tap];
+      const int fi = fo * d.sf + d.df[tap];
+      if (ti < 0 || ti >= d.T || fi < 0 || fi >= d.Fin) continue;      // zero outside the tensor (warp-uniform)
+      const long long pos = (bT + ti) * d.Fin + fi;
+      const float* w = wsm + (size_t)tap * P.Ctot * NCO;
+#pragma unroll
+      for (int srcsel = 0; srcsel < 2; ++srcsel) {
+        const int C = srcsel == 0 ? d.C0 : d.C1;
+        if (C == 0) continue;
+        const float* x = (srcsel == 0 ? d.src0 : d.src1) + pos * C;
+        const float* ws = w + (srcsel == 0 ? 0 : d.C0 * NCO);
+        for (int c = lane * 4; c < C; c += 128) {                       // C % 4 == 0, 16-byte aligned (host check)
+          const float4 v = __ldg(reinterpret_cast<const float4*>(x + c));
+          const float xv[4] = {v.x, v.y, v.z, v.w};
+          float wv[4 * NCO];                                            // weights of channels c..c+3: NCO float4 loads
+#pragma unroll
+          for (int i = 0; i < NCO; ++i) {
+            const float4 w4 = *reinterpret_cast<const float4*>(ws + c * NCO + 4 * i);
+            wv[4 * i] = w4.x;
+            wv[4 * i + 1] = w4.y;
+            wv[4 * i + 2] = w4.z;
+            wv[4 * i + 3] = w4.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int co = 0; co < NCO; ++co) acc[co] = fmaf(xv[e], wv[e * NCO + co], acc[co]);
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < NCO; ++co)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+    if (lane < d.Cout) {
+      float v = acc[0];
+#pragma unroll
+      for (int co = 1; co < NCO; ++co)
+        if (lane == co) v = acc[co];
+      v = apply_act(v + (d.bias ? __ldg(d.bias + lane) : 0.f), d.act, d.act_param);
+      d.dst[((bt * d.dstF) + d.dst_f0 + (long long)fo * d.dst_fstep) * d.Cout + lane] = v;
+    }
+  }
+}
+
+template <int NCO>
+static int launch_conv_narrow(const ConvParams& P, cudaStream_t s) {
+  const size_t smem = (size_t)P.K * NCO * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(conv_narrow_kernel<NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("se_conv_gemm (narrow): %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return SE_ERR_CUDA;
+    }
+  }
+  const int blocks = (int)min((long long)148 * 8, ceil_div_ll(P.M, 8));
+  conv_narrow_kernel<NCO><<<blocks, 256, smem, s>>>(P);
+  return SE_OK;
+}
+
 template <int BM, int BN, int TM, int TN>
 static void launch_conv(const ConvParams& P, bool aligned, cudaStream_t s) {
   dim3 grid(ceil_div(P.M, BM), ceil_div(P.d.Cout, BN));
@@ -362,7 +452,13 @@ extern "C" int se_conv_gemm(const se_conv_desc* desc, se_stream_t stream) {
   const bool aligned = (d.C0 % BK == 0) && (d.C1 % BK == 0) && ((((uintptr_t)d.src0) & 15) == 0) &&
                        (d.C1 == 0 || (((uintptr_t)d.src1) & 15) == 0);
   cudaStream_t s = (cudaStream_t)stream;
-  if (d.Cout > 64)
+  // Cout <= 4 with float4-addressable channels: one warp per output position instead of a 16-wide column tile
+  const bool narrow = d.Cout <= 4 && (d.C0 & 3) == 0 && (d.C1 & 3) == 0 && ((((uintptr_t)d.src0) & 15) == 0) &&
+                      (d.C1 == 0 || (((uintptr_t)d.src1) & 15) == 0) && (size_t)P.K * 4 * sizeof(float) <= 200 * 1024;
+  if (narrow) {
+    const int rcn = d.Cout <= 2 ? launch_conv_narrow<2>(P, s) : launch_conv_narrow<4>(P, s);
+    if (rcn) return rcn;
+  } else if (d.Cout > 64)
     launch_conv<128, 128, 8, 8>(P, aligned, s);
   else if (d.Cout > 32)
     launch_conv<128, 64, 8, 4>(P, aligned, s);

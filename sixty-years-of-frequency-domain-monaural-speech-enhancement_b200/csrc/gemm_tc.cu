@@ -117,13 +117,6 @@ __device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float
   }
 }
 
-// ex2.approx + approximate divide; the accurate expf / tanhf / IEEE divide cost ~4x the instructions
-__device__ __forceinline__ float tc_fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tc_fast_tanh(float x) {
-  const float t = __expf(-2.0f * fabsf(x));
-  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
-}
-
 template <int EPI, int NC>
 __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float (&sum)[NC], int row, int n0) {
   if constexpr (EPI == EPI_BIAS_ACT) {
@@ -158,12 +151,12 @@ __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float
         float cn[4], hn[4], hh[4], hl[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float ig = tc_fast_sigmoid(sum[q * 64 + u + e] + vbi[e]);
-          const float fg = tc_fast_sigmoid(sum[q * 64 + 16 + u + e] + vbf[e]);
-          const float gg = tc_fast_tanh(sum[q * 64 + 32 + u + e] + vbg[e]);
-          const float og = tc_fast_sigmoid(sum[q * 64 + 48 + u + e] + vbo[e]);
+          const float ig = fast_sigmoid(sum[q * 64 + u + e] + vbi[e]);
+          const float fg = fast_sigmoid(sum[q * 64 + 16 + u + e] + vbf[e]);
+          const float gg = fast_tanh(sum[q * 64 + 32 + u + e] + vbg[e]);
+          const float og = fast_sigmoid(sum[q * 64 + 48 + u + e] + vbo[e]);
           cn[e] = fg * co[e] + ig * gg;
-          hn[e] = og * tc_fast_tanh(cn[e]);
+          hn[e] = og * fast_tanh(cn[e]);
           split_tf32_dev(hn[e], hh[e], hl[e]);
         }
         *reinterpret_cast<float4*>(p.c_state + off + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
@@ -599,6 +592,21 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
   }
 }
 
+// rows of K floats -> rows of Kpad >= K floats (zero tail), split into (hi, lo): lets a K that is not a multiple of 32
+// (the 161 bins of LSTM/LSTM.py:17) run on the tensor-core GEMM against weights padded the same way
+__global__ void __launch_bounds__(256) pad_split_tf32_kernel(const float* __restrict__ x, long long rows, int K, int Kpad,
+                                                            float* __restrict__ hi, float* __restrict__ lo) {
+  const long long total = rows * Kpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Kpad;
+    const int c = (int)(i - r * Kpad);
+    float h = 0.f, l = 0.f;
+    if (c < K) split_tf32_dev(__ldg(x + r * K + c), h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 // ---- host: tensor maps through the driver entry point (no link-time libcuda dependency) ----------
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -645,6 +653,15 @@ extern "C" int se_split_tf32(const float* x, float* hi, float* lo, long long n, 
                                                               reinterpret_cast<float4*>(hi),
                                                               reinterpret_cast<float4*>(lo), n4);
   return check_launch("se_split_tf32");
+}
+
+extern "C" int se_pad_split_tf32(const float* x, long long rows, int K, int Kpad, float* hi, float* lo,
+                                 se_stream_t stream) {
+  SE_REQUIRE(x && hi && lo && rows > 0 && K > 0 && Kpad >= K && (Kpad & 3) == 0, "se_pad_split_tf32: rows=%lld K=%d Kpad=%d",
+             rows, K, Kpad);
+  const int blocks = (int)min((long long)148 * 8, ceil_div_ll(rows * Kpad, 256));
+  pad_split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, K, Kpad, hi, lo);
+  return check_launch("se_pad_split_tf32");
 }
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }

@@ -258,9 +258,12 @@ __global__ void __launch_bounds__(kSmallThreads, 1) lstm_seq_small_kernel(const 
   __syncthreads();
 
   for (int t = 0; t < p.T; ++t) {
-    float acc[NS];
+    float acc[NS], acc2[NS];      // two partial sums per sequence: halves the dependent-FMA chain
 #pragma unroll
-    for (int s = 0; s < NS; ++s) acc[s] = xg[s];
+    for (int s = 0; s < NS; ++s) {
+      acc[s] = xg[s];
+      acc2[s] = 0.f;
+    }
     if (t + 1 < p.T) {   // next step's input projection: independent of the recurrence, in flight during the matvec
 #pragma unroll
       for (int s = 0; s < NS; ++s)
@@ -273,9 +276,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1) lstm_seq_small_kernel(const 
         for (int s = 0; s < NS; ++s) {
           const float4 h4 = *reinterpret_cast<const float4*>(hs + s * H + k);     // broadcast
           acc[s] = fmaf(wreg[k], h4.x, acc[s]);
-          acc[s] = fmaf(wreg[k + 1], h4.y, acc[s]);
+          acc2[s] = fmaf(wreg[k + 1], h4.y, acc2[s]);
           acc[s] = fmaf(wreg[k + 2], h4.z, acc[s]);
-          acc[s] = fmaf(wreg[k + 3], h4.w, acc[s]);
+          acc2[s] = fmaf(wreg[k + 3], h4.w, acc2[s]);
         }
       }
 #pragma unroll 4
@@ -286,23 +289,25 @@ __global__ void __launch_bounds__(kSmallThreads, 1) lstm_seq_small_kernel(const 
         for (int s = 0; s < NS; ++s) {
           const float4 h4 = *reinterpret_cast<const float4*>(hs + s * H + k);
           acc[s] = fmaf(w0, h4.x, acc[s]);
-          acc[s] = fmaf(w1, h4.y, acc[s]);
+          acc2[s] = fmaf(w1, h4.y, acc2[s]);
           acc[s] = fmaf(w2, h4.z, acc[s]);
-          acc[s] = fmaf(w3, h4.w, acc[s]);
+          acc2[s] = fmaf(w3, h4.w, acc2[s]);
         }
       }
     }
 #pragma unroll
-    for (int s = 0; s < NS; ++s) gs[s * NCOL + j] = acc[s];
+    for (int s = 0; s < NS; ++s) gs[s * NCOL + j] = acc[s] + acc2[s];
     __syncthreads();              // all pre-activations written; every thread is done reading h_{t-1}
     if (gate_thread) {
+      // ex2.approx gates (|err| ~ 2e-7, as in the tcgen05 recurrence): this phase is a dependent chain on a quarter of
+      // the warps while the rest wait at the barrier
       const float* g = gs + gs_s * NCOL + gcol;
-      const float ig = sigmoid_f(g[0]);
-      const float fg = sigmoid_f(g[kHU]);
-      const float gg = tanhf(g[2 * kHU]);
-      const float og = sigmoid_f(g[3 * kHU]);
+      const float ig = fast_sigmoid(g[0]);
+      const float fg = fast_sigmoid(g[kHU]);
+      const float gg = fast_tanh(g[2 * kHU]);
+      const float og = fast_sigmoid(g[3 * kHU]);
       c_state = fg * c_state + ig * gg;
-      const float h = og * tanhf(c_state);
+      const float h = og * fast_tanh(c_state);
       hs[gs_s * H + gs_u] = h;
       hseq[(size_t)(b0 + gs_s) * p.hs_sb + (size_t)t * p.hs_st + gs_u] = h;
     }

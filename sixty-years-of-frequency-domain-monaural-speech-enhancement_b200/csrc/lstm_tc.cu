@@ -148,14 +148,6 @@ __device__ __forceinline__ void tmem_st_32x32(unsigned taddr, const unsigned (&r
       : "memory");
 }
 
-// fast-math gates: ex2.approx + approximate divide, |error| ~ 2e-7 (fp32 rounding class); the accurate expf/tanhf/IEEE
-// divide of common.cuh cost 2800 cycles of a 20000-cycle step here (profiles/lstm_tc_phases_v1_r01.json)
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) {
-  const float t = __expf(-2.0f * fabsf(x));
-  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
-}
-
 // MC = multicast width: the cluster has 4*MC CTAs, rank = ug*4 + q.  The MC CTAs with the same K slice q (different
 // unit groups ug) each fetch 1/MC of every h tile and multicast it to all of them, so L2 serves every byte of
 // h_{t-1} 32/MC times per step instead of 32 (the v1 kernel was bound by exactly that: 7200 of 20000 cycles).

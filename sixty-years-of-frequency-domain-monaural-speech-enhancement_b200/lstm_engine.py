@@ -1,7 +1,7 @@
 """One nn.LSTM layer = hoisted input projection (one GEMM over all T) + persistent recurrence.
 
-Input projection: 3xTF32 on tcgen05 (csrc/gemm_tc.cu) whenever the shape allows (K % 32 == 0,
-at least one 128-row tile), else the fp32 FMA implicit-GEMM kernel.  Recurrence: csrc/lstm.cu.
+Input projection: 3xTF32 on tcgen05 (csrc/gemm_tc.cu) whenever there is at least one 128-row tile (an input width that is
+not a multiple of 32 is zero-padded while it is split), else the fp32 FMA implicit-GEMM kernel.  Recurrence: csrc/lstm.cu.
 Reference: nn.LSTM in CRN/CRN.py:20,29 and LSTM/LSTM.py:17-18,26-27.
 """
 from __future__ import annotations
@@ -15,8 +15,14 @@ def input_projection(seq2d, layer, pair=None):
     """seq2d [M, K] fp32 (or None when ``pair`` = its TF32 (hi, lo) split is already available)."""
     m, k = (seq2d if seq2d is not None else pair[0]).shape
     n = 4 * layer["hidden"]
-    if USE_TENSOR_CORES and k % 32 == 0 and (m >= 128 or pair is not None) and layer["wih_hi"].shape[1] == k:
-        a_hi, a_lo = pair if pair is not None else ops.split_tf32(seq2d)
+    kw = layer["wih_hi"].shape[1]                # K of the packed tensor-core weights: the input width rounded up to 32
+    if USE_TENSOR_CORES and (m >= 128 or pair is not None) and (kw == k or (pair is None and layer.get("kin") == k)):
+        if pair is not None:
+            a_hi, a_lo = pair
+        elif kw == k:
+            a_hi, a_lo = ops.split_tf32(seq2d)
+        else:                                    # zero-pad the rows on the way to the split (161 -> 192 bins)
+            a_hi, a_lo = ops.pad_split_tf32(seq2d, kw)
         return ops.gemm_tf32x3(a_hi, a_lo, layer["wih_hi"], layer["wih_lo"], layer["bias"], n)
     if seq2d is None:
         raise RuntimeError("fp32 activation needed for the FMA projection")

@@ -231,6 +231,19 @@ def split_tf32(x):
     return hi, lo
 
 
+def pad_split_tf32(x, kpad):
+    """x [rows, K] (contiguous fp32) -> (hi, lo) [rows, kpad] TF32 pair, columns K.. zero (see se_pad_split_tf32)."""
+    _need_cuda(x)
+    device_check()
+    rows, k = x.shape
+    assert x.is_contiguous() and kpad >= k and kpad % 4 == 0
+    hi = torch.empty(rows, kpad, device=x.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    with _Timed("split_tf32"):
+        check(_lib.load().se_pad_split_tf32(_ptr(x), rows, k, kpad, _ptr(hi), _ptr(lo), _stream()), "se_pad_split_tf32")
+    return hi, lo
+
+
 def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, n_out, act="none", out=None):
     """(a_hi+a_lo) [M,K] @ (b_hi+b_lo) [N,K]^T (+bias, act) -> [M, n_out] on tcgen05 (3xTF32)."""
     _need_cuda(a_hi, a_lo, b_hi, b_lo, bias)

@@ -108,9 +108,12 @@ def pack_lstm_layer(w_ih, w_hh, b_ih, b_hh, in_perm=None, unit_perm=None, in_sca
     s = hidden // HU
     whp = wh.reshape(s, 4 * HU, hidden).permute(0, 2, 1).contiguous()
     wi = wi.contiguous()
-    hi, lo = split_tf32(wi)
+    kin = wi.shape[1]
+    kpad = -(-kin // 32) * 32          # the tensor-core GEMM wants K % 32 == 0: zero columns (LSTM.py:17 has K = 161)
+    wi_tc = wi if kpad == kin else torch.cat([wi, wi.new_zeros(wi.shape[0], kpad - kin)], dim=1).contiguous()
+    hi, lo = split_tf32(wi_tc)
     return {"wih_kn": pad_cols(wi.t().contiguous()), "wih_hi": hi, "wih_lo": lo, "bias": bias.contiguous(),
-            "whh": whp, "hidden": hidden}
+            "whh": whp, "hidden": hidden, "kin": kin}
 
 
 def tile_rows(hidden):

@@ -139,6 +139,12 @@ def split_tf32(x):
     return packing.split_tf32(x)
 
 
+def pad_split_tf32(x, kpad):
+    from se_b200 import packing
+    xp = torch.cat([x, x.new_zeros(x.shape[0], kpad - x.shape[1])], dim=1)
+    return packing.split_tf32(xp)
+
+
 def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, n_out, act="none", out=None):
     y = (a_hi + a_lo) @ (b_hi + b_lo).t()
     if bias is not None:
@@ -215,7 +221,7 @@ def fsn_sb_fc(h, W, bias, out):
 
 
 def install(ops_module, monkeypatch):
-    for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "gemm_tf32x3",
+    for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "pad_split_tf32", "gemm_tf32x3",
                  "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask", "conv_tf32x3", "fill_column", "lstm_seq_multi"):
         monkeypatch.setattr(ops_module, name, globals()[name])
 

@@ -29,6 +29,12 @@ CONV_CASES = [
     (2, 11, 9, 128, 128, 64, "deconv"),
     (1, 5, 19, 64, 64, 32, "deconv"),
     (2, 6, 39, 32, 32, 16, "deconv_shift"),
+    # narrow outputs (Cout <= 4: conv_narrow_kernel, one warp per output position)
+    (2, 9, 39, 64, 64, 2, "deconv"),           # CTSNet / DPCRN style RI head with a skip source
+    (1, 7, 80, 128, 0, 2, "conv"),
+    (3, 5, 19, 32, 32, 1, "deconv_shift"),     # fill column + one channel
+    (2, 4, 9, 256, 128, 4, "deconv"),          # uneven sources, two channel passes per lane
+    (1, 3, 11, 36, 0, 3, "conv"),              # channel count that is not a multiple of 128
 ]
 
 
@@ -673,4 +679,29 @@ def test_dccrn_mask_modes(mode):
     er, ei = torch.empty(b, t, f), torch.empty(b, t, f)
     emu_ops.dccrn_mask(m, x[..., 0], x[..., 1], er, ei, mode=mode)
     assert (e[..., 0].cpu() - er).abs().max() < 2e-6 and (e[..., 1].cpu() - ei).abs().max() < 2e-6
+
+
+def test_pad_split_tf32_and_odd_k_projection():
+    """se_pad_split_tf32: rows of 161 floats -> 192 with a zero tail, split hi / lo; the LSTM-net layer-0 projection
+    (K = 161, LSTM/LSTM.py:17) through the tensor-core GEMM on the padded operands vs fp64."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import lstm_engine, packing
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(21)
+    m, k, h = 401 * 3, 161, 1024
+    x = torch.randn(m, k, generator=g)
+    hi, lo = ops.pad_split_tf32(x.to(dev), 192)
+    assert hi.shape == (m, 192) and (hi[:, k:] == 0).all() and (lo[:, k:] == 0).all()
+    assert ((hi + lo)[:, :k].cpu() - x).abs().max() < 2e-6
+    w_ih = torch.randn(4 * h, k, generator=g) / np.sqrt(k)
+    w_hh = torch.randn(4 * h, h, generator=g) / np.sqrt(h)
+    b_ih, b_hh = torch.randn(4 * h, generator=g), torch.randn(4 * h, generator=g)
+    layer = packing.pack_lstm_layer(w_ih, w_hh, b_ih, b_hh)
+    assert layer["wih_hi"].shape == (4 * h, 192) and layer["kin"] == k
+    layer = {kk: (v.to(dev) if torch.is_tensor(v) else v) for kk, v in layer.items()}
+    got = lstm_engine.input_projection(x.to(dev), layer)
+    rows = packing.slice_rows(h)
+    ref = x.double() @ w_ih.double()[rows].t() + (b_ih + b_hh).double()[rows]
+    assert (got.cpu().double() - ref).abs().max() < 1e-5
 
