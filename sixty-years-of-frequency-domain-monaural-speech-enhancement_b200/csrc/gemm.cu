@@ -332,92 +332,139 @@ __global__ void __launch_bounds__(256) deconv_out1_kernel(const float* __restric
 
 // ---------------------------------------------------------------------------------------------
 // Narrow-output variant of the same contract (Cout <= 4: the last decoder layers that emit the 2-channel RI spectrum
-// or a 1-channel mask -- CTSNet/Step2_network.py de5, DCCRN decoder.5, DPCRN's CRM head).  The tiled kernel above
-// computes a 16- or 32-wide column tile whatever Cout is, i.e. 8-16x the useful FMAs.  Here one WARP owns one output
-// position: the lanes stride over the channels of every tap with float4 loads (one coalesced 512-byte request per
-// tap and 128 channels), keep NCO partial sums each, and finish with a shuffle reduction.  The weights (K x NCO
-// floats) sit in shared memory.  HBM / L2-bound: every activation element is read ntaps / sf times, mostly from L1/L2.
+// or a 1-channel mask -- CTSNet/Step2_network.py de5, DCCRN decoder.5, DPCRN's CRM head, Uformer's mask heads).  The
+// tiled kernel above computes a 16- or 32-wide column tile whatever Cout is, i.e. 8-16x the useful FMAs, and re-reads
+// every activation once per tap from L2.  Here one CTA owns one output frame (b, t):
+//   * the <= 4 input frames it needs (distinct dt of the taps) are staged ONCE in shared memory as [Fin][C0 + C1] rows
+//     (float4, coalesced; frames outside the tensor are zero), the K x NCO weights next to them;
+//   * a warp computes 4 neighbouring output columns at a time: lanes stride over the channels (float4 from shared
+//     memory, conflict-free), each weight vector is loaded once for the 4 columns, 4 x NCO partial sums per lane,
+//     butterfly reduction, lanes 0 .. 4 NCO - 1 store.
+// A first version with one warp per output and global loads (no staging) was 1.4-2x SLOWER than the tiled kernel: the
+// im2col-expanded L2 -> SM traffic, not the FMAs, is what these layers cost (profiles/models_r01h.jsonl).
 // ---------------------------------------------------------------------------------------------
+constexpr int kRowsMaxDt = 4;
+struct ConvRowsParams {
+  ConvParams c;
+  int ndt;
+  int dtv[kRowsMaxDt];          // distinct time offsets of the taps
+  int tap_dti[SE_MAX_TAPS];     // tap -> index into dtv
+};
+
 template <int NCO>
-__global__ void __launch_bounds__(256) conv_narrow_kernel(const ConvParams P) {
-  extern __shared__ __align__(16) float wsm[];   // [K][NCO]
+__global__ void __launch_bounds__(256) conv_rows_kernel(const ConvRowsParams R) {
+  extern __shared__ __align__(16) float smem_rows[];
+  const ConvParams& P = R.c;
   const se_conv_desc& d = P.d;
+  const int Ct = P.Ctot;
+  float* rows = smem_rows;                                   // [ndt][Fin][Ct]
+  float* wsm = rows + (size_t)R.ndt * d.Fin * Ct;            // [K][NCO]
+  const int bt = blockIdx.x;                                 // b * T + t
+  const int t = bt % d.T;
   for (int i = threadIdx.x; i < P.K * NCO; i += blockDim.x) {
     const int k = i / NCO, co = i - k * NCO;
     wsm[i] = co < d.Cout ? __ldg(d.W + (size_t)k * d.ldw + co) : 0.f;
   }
+  const int c4 = Ct >> 2, c04 = d.C0 >> 2;
+  for (int di = 0; di < R.ndt; ++di) {
+    const int ti = t + R.dtv[di];
+    const bool ok = ti >= 0 && ti < d.T;
+    const long long pos0 = (long long)(bt - t + ti) * d.Fin;
+    float4* dst = reinterpret_cast<float4*>(rows + (size_t)di * d.Fin * Ct);
+    for (int i = threadIdx.x; i < d.Fin * c4; i += blockDim.x) {
+      const int f = i / c4, q = i - f * c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok)
+        v = q < c04 ? __ldg(reinterpret_cast<const float4*>(d.src0 + (pos0 + f) * d.C0) + q)
+                    : __ldg(reinterpret_cast<const float4*>(d.src1 + (pos0 + f) * d.C1) + (q - c04));
+      dst[i] = v;
+    }
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps_per_cta = blockDim.x >> 5;
-  const long long warp0 = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * warps_per_cta;
-  for (long long m = warp0; m < P.M; m += nwarps) {
-    const int fo = (int)(m % d.Fout);
-    const long long bt = m / d.Fout;
-    const int t = (int)(bt % d.T);
-    const long long bT = bt - t;
-    float acc[NCO];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int fo0 = warp * 4; fo0 < d.Fout; fo0 += nwarp * 4) {
+    float acc[4][NCO];
 #pragma unroll
-    for (int co = 0; co < NCO; ++co) acc[co] = 0.f;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int co = 0; co < NCO; ++co) acc[r][co] = 0.f;
     for (int tap = 0; tap < d.ntaps; ++tap) {
-      const int ti = t + d.dt[tap];
-      const int fi = fo * d.sf + d.df[tap];
-      if (ti < 0 || ti >= d.T || fi < 0 || fi >= d.Fin) continue;      // zero outside the tensor (warp-uniform)
-      const long long pos = (bT + ti) * d.Fin + fi;
-      const float* w = wsm + (size_t)tap * P.Ctot * NCO;
+      const float* xr = rows + (size_t)R.tap_dti[tap] * d.Fin * Ct;
+      const float* wt = wsm + (size_t)tap * Ct * NCO;
+      int fi[4];
+      bool fok[4];
 #pragma unroll
-      for (int srcsel = 0; srcsel < 2; ++srcsel) {
-        const int C = srcsel == 0 ? d.C0 : d.C1;
-        if (C == 0) continue;
-        const float* x = (srcsel == 0 ? d.src0 : d.src1) + pos * C;
-        const float* ws = w + (srcsel == 0 ? 0 : d.C0 * NCO);
-        for (int c = lane * 4; c < C; c += 128) {                       // C % 4 == 0, 16-byte aligned (host check)
-          const float4 v = __ldg(reinterpret_cast<const float4*>(x + c));
+      for (int r = 0; r < 4; ++r) {
+        fi[r] = (fo0 + r) * d.sf + d.df[tap];
+        fok[r] = fo0 + r < d.Fout && fi[r] >= 0 && fi[r] < d.Fin;
+      }
+      for (int c = lane * 4; c < Ct; c += 128) {
+        float wv[4 * NCO];
+#pragma unroll
+        for (int i = 0; i < NCO; ++i) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wt + c * NCO + 4 * i);
+          wv[4 * i] = w4.x;
+          wv[4 * i + 1] = w4.y;
+          wv[4 * i + 2] = w4.z;
+          wv[4 * i + 3] = w4.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (!fok[r]) continue;                                       // warp-uniform
+          const float4 v = *reinterpret_cast<const float4*>(xr + (size_t)fi[r] * Ct + c);
           const float xv[4] = {v.x, v.y, v.z, v.w};
-          float wv[4 * NCO];                                            // weights of channels c..c+3: NCO float4 loads
-#pragma unroll
-          for (int i = 0; i < NCO; ++i) {
-            const float4 w4 = *reinterpret_cast<const float4*>(ws + c * NCO + 4 * i);
-            wv[4 * i] = w4.x;
-            wv[4 * i + 1] = w4.y;
-            wv[4 * i + 2] = w4.z;
-            wv[4 * i + 3] = w4.w;
-          }
 #pragma unroll
           for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int co = 0; co < NCO; ++co) acc[co] = fmaf(xv[e], wv[e * NCO + co], acc[co]);
+            for (int co = 0; co < NCO; ++co) acc[r][co] = fmaf(xv[e], wv[e * NCO + co], acc[r][co]);
         }
       }
     }
+    float mine = 0.f;                                                  // lane r * NCO + co keeps sum (r, co)
 #pragma unroll
-    for (int co = 0; co < NCO; ++co)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
-    if (lane < d.Cout) {
-      float v = acc[0];
+      for (int co = 0; co < NCO; ++co) {
+        float v = acc[r][co];
 #pragma unroll
-      for (int co = 1; co < NCO; ++co)
-        if (lane == co) v = acc[co];
-      v = apply_act(v + (d.bias ? __ldg(d.bias + lane) : 0.f), d.act, d.act_param);
-      d.dst[((bt * d.dstF) + d.dst_f0 + (long long)fo * d.dst_fstep) * d.Cout + lane] = v;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == r * NCO + co) mine = v;
+      }
+    const int r = lane / NCO, co = lane - r * NCO;
+    if (lane < 4 * NCO && fo0 + r < d.Fout && co < d.Cout) {
+      const float v = apply_act(mine + (d.bias ? __ldg(d.bias + co) : 0.f), d.act, d.act_param);
+      d.dst[(((long long)bt * d.dstF) + d.dst_f0 + (long long)(fo0 + r) * d.dst_fstep) * d.Cout + co] = v;
     }
   }
 }
 
+// returns 1 when the launch was made, 0 when the shape does not fit (caller falls back to the tiled kernel)
 template <int NCO>
-static int launch_conv_narrow(const ConvParams& P, cudaStream_t s) {
-  const size_t smem = (size_t)P.K * NCO * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(conv_narrow_kernel<NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("se_conv_gemm (narrow): %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-      return SE_ERR_CUDA;
+static int launch_conv_rows(const ConvParams& P, cudaStream_t s, int* rc) {
+  ConvRowsParams R;
+  R.c = P;
+  R.ndt = 0;
+  const se_conv_desc& d = P.d;
+  for (int tap = 0; tap < d.ntaps; ++tap) {
+    int di = 0;
+    while (di < R.ndt && R.dtv[di] != d.dt[tap]) ++di;
+    if (di == R.ndt) {
+      if (R.ndt == kRowsMaxDt) return 0;
+      R.dtv[R.ndt++] = d.dt[tap];
     }
+    R.tap_dti[tap] = di;
   }
-  const int blocks = (int)min((long long)148 * 8, ceil_div_ll(P.M, 8));
-  conv_narrow_kernel<NCO><<<blocks, 256, smem, s>>>(P);
-  return SE_OK;
+  const size_t smem = ((size_t)R.ndt * d.Fin * P.Ctot + (size_t)P.K * NCO) * sizeof(float);
+  if (smem > 200 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("se_conv_gemm (rows): %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    *rc = SE_ERR_CUDA;
+    return 1;
+  }
+  conv_rows_kernel<NCO><<<d.B * d.T, 256, smem, s>>>(R);
+  *rc = SE_OK;
+  return 1;
 }
 
 template <int BM, int BN, int TM, int TN>
@@ -452,11 +499,11 @@ extern "C" int se_conv_gemm(const se_conv_desc* desc, se_stream_t stream) {
   const bool aligned = (d.C0 % BK == 0) && (d.C1 % BK == 0) && ((((uintptr_t)d.src0) & 15) == 0) &&
                        (d.C1 == 0 || (((uintptr_t)d.src1) & 15) == 0);
   cudaStream_t s = (cudaStream_t)stream;
-  // Cout <= 4 with float4-addressable channels: one warp per output position instead of a 16-wide column tile
+  // Cout <= 4 with float4-addressable channels: frame-per-CTA kernel with the input frames staged in shared memory
   const bool narrow = d.Cout <= 4 && (d.C0 & 3) == 0 && (d.C1 & 3) == 0 && ((((uintptr_t)d.src0) & 15) == 0) &&
-                      (d.C1 == 0 || (((uintptr_t)d.src1) & 15) == 0) && (size_t)P.K * 4 * sizeof(float) <= 200 * 1024;
-  if (narrow) {
-    const int rcn = d.Cout <= 2 ? launch_conv_narrow<2>(P, s) : launch_conv_narrow<4>(P, s);
+                      (d.C1 == 0 || (((uintptr_t)d.src1) & 15) == 0) && d.Fout >= 16;
+  int rcn = SE_OK;
+  if (narrow && (d.Cout <= 2 ? launch_conv_rows<2>(P, s, &rcn) : launch_conv_rows<4>(P, s, &rcn))) {
     if (rcn) return rcn;
   } else if (d.Cout > 64)
     launch_conv<128, 128, 8, 8>(P, aligned, s);

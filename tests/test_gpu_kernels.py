@@ -29,12 +29,13 @@ CONV_CASES = [
     (2, 11, 9, 128, 128, 64, "deconv"),
     (1, 5, 19, 64, 64, 32, "deconv"),
     (2, 6, 39, 32, 32, 16, "deconv_shift"),
-    # narrow outputs (Cout <= 4: conv_narrow_kernel, one warp per output position)
+    # narrow outputs (Cout <= 4 and Fout >= 16: conv_rows_kernel, one CTA per output frame, input frames in smem)
     (2, 9, 39, 64, 64, 2, "deconv"),           # CTSNet / DPCRN style RI head with a skip source
     (1, 7, 80, 128, 0, 2, "conv"),
     (3, 5, 19, 32, 32, 1, "deconv_shift"),     # fill column + one channel
-    (2, 4, 9, 256, 128, 4, "deconv"),          # uneven sources, two channel passes per lane
-    (1, 3, 11, 36, 0, 3, "conv"),              # channel count that is not a multiple of 128
+    (2, 4, 19, 256, 128, 4, "deconv"),         # uneven sources, three channel passes per lane
+    (1, 3, 40, 36, 0, 3, "conv"),              # channel count that is not a multiple of 128
+    (2, 4, 9, 64, 0, 2, "conv"),               # Fout < 16: stays on the tiled kernel
 ]
 
 
