@@ -304,6 +304,52 @@ def enhancer_for(model):
     raise TypeError(f"no decode loop registered for {type(model).__name__}")
 
 
+def enhance_host_stream(model, host_batches, enhance_fn=None, depth=2, device=None, **kw):
+    """Pipelined host -> host decode: for every pinned host batch [B,N] float32 of ``host_batches`` yields the enhanced
+    batch as a pinned host tensor (valid until ``depth`` more batches have been drawn).  The upload of batch i+1 and
+    the download of batch i-1 run on their own CUDA streams while batch i is in the decode loop, so the PCIe copies the
+    reference pays serially per utterance (CRN/crn_decode.py:46-47,53) disappear behind the compute.  All batches must
+    have the same shape (one ring of ``depth`` device / host buffers)."""
+    fn = enhance_fn or enhancer_for(model)
+    dev = torch.device(device if device is not None else "cuda", torch.cuda.current_device()) \
+        if not isinstance(device, torch.device) else device
+    compute = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dev_in, host_out = [None] * depth, [None] * depth
+    ev_in = [torch.cuda.Event() for _ in range(depth)]
+    ev_done = [None] * depth
+    ev_out = [None] * depth
+    pending = []                                    # slots whose download has been queued, oldest first
+    for i, host in enumerate(host_batches):
+        slot = i % depth
+        if ev_out[slot] is not None:                # the consumer gets batch i - depth before its buffers are reused
+            ev_out[slot].synchronize()
+            pending.remove(slot)
+            yield host_out[slot]
+        if dev_in[slot] is None:
+            dev_in[slot] = torch.empty(host.shape, device=dev, dtype=torch.float32)
+            host_out[slot] = torch.empty(host.shape, dtype=torch.float32).pin_memory()
+        with torch.cuda.stream(s_in):
+            if ev_done[slot] is not None:
+                s_in.wait_event(ev_done[slot])      # the decode loop of batch i - depth has finished reading this buffer
+            dev_in[slot].copy_(host, non_blocking=True)
+            ev_in[slot].record(s_in)
+        compute.wait_event(ev_in[slot])
+        y = fn(model, dev_in[slot], **kw)
+        ev_done[slot] = torch.cuda.Event()
+        ev_done[slot].record(compute)
+        y.record_stream(s_out)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[slot])
+            host_out[slot].copy_(y, non_blocking=True)
+            ev_out[slot] = torch.cuda.Event()
+            ev_out[slot].record(s_out)
+        pending.append(slot)
+    for slot in pending:
+        ev_out[slot].synchronize()
+        yield host_out[slot]
+
+
 def read_wav_any(path):
     """``soundfile.read`` as the scripts use it (CRN/crn_decode.py:38): (float64 samples in [-1, 1), sample rate)."""
     from scipy.io import wavfile

@@ -135,8 +135,15 @@ class Net(nn.Module):
                 whh.append(lay["whh"])
             w = torch.cat(blocks, 0).contiguous()                          # [2 * 2048, 1024]  (N, K)
             hi, lo = packing.split_tf32(w)
+            # the two H = 512 groups as ONE block-diagonal H = 1024 recurrence: slice 64 g + s of the big LSTM is slice s
+            # of group g and only sees k in [512 g, 512 g + 512).  Twice the FLOPs, but the tcgen05 cluster recurrence
+            # (H = 1024 only; 6.9 us/step, latency-bound) beats the fp32 slice kernel the grouped call runs on (8.9)
+            whh_bd = torch.zeros(128, 1024, 32, device=dev)
+            for g in range(2):
+                whh_bd[64 * g:64 * g + 64, 512 * g:512 * g + 512] = whh[g]
             return {"wih_hi": hi, "wih_lo": lo, "wih_kn": packing.pad_cols(w.t().contiguous()),
                     "bias": torch.cat(biases).contiguous(), "whh": torch.stack(whh).contiguous(),
+                    "whh_bd": whh_bd.contiguous(),
                     "hidden": 1024}      # 2 groups x 512: the projection has 4 * 1024 output columns
 
         P["st1"] = stage(1, [col_of_ref[512 * g:512 * g + 512] for g in range(2)])
@@ -206,8 +213,11 @@ class Net(nn.Module):
         for st in (1, 2):
             lay = P[f"st{st}"]
             xp = lstm_engine.input_projection(seq, lay, pair)                      # [B*T, 2 * 2048]
-            hs = torch.empty(b, t, 1024, device=dev, dtype=torch.float32)
-            ops.lstm_seq_multi(xp.view(b, t, 4096), lay["whh"], 512, 2, hs)
+            if tcl:      # block-diagonal H = 1024 recurrence on the tcgen05 cluster kernel
+                hs = ops.lstm_seq(xp.view(b, t, 4096), lay["whh_bd"], 1024)
+            else:
+                hs = torch.empty(b, t, 1024, device=dev, dtype=torch.float32)
+                ops.lstm_seq_multi(xp.view(b, t, 4096), lay["whh"], 512, 2, hs)
             g, be = P[f"ln{st}"]
             seq, pair = ops.group_layernorm(hs.view(b * t, 1024), 1, g, be, want_f32=not tcl, want_pair=tcl,
                                             out_index=P["ln2_index"] if st == 2 else None)
