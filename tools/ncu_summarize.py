@@ -74,7 +74,7 @@ def full(src, dst, cmd):
             out.append(rec)
     json.dump({"source": cmd, "kernels": out}, open(dst, "w"), indent=1)
     for k in out:
-        print(f"{k['kernel'][:40]:40s} {k.get('gpu__time_duration.sum', 0):8.3f} ms  DRAM r+w "
+        print(f"{k['kernel'][:40]:40s} {k.get('gpu__time_duration.sum', 0):8.3f} {k.get('gpu__time_duration.sum__unit', 'ms')}  DRAM r+w "
               f"{k.get('dram__bytes_read.sum', 0) + k.get('dram__bytes_write.sum', 0):8.1f} "
               f"{k.get('dram__bytes_read.sum__unit', '')}  dram% "
               f"{k.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 0):5.1f}  tensor% "
