@@ -461,3 +461,39 @@ def test_enhance_host_stream_matches_direct_calls():
     assert len(got) == 5
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+FULL_SIZE_CONFIGS = {
+    # BASELINE.json configs[2..4] at their per-GPU shard: (constructor, template, decode loop, clips, seconds, kwargs)
+    "dccrn_32x4s": (lambda m: m.DCCRN(rnn_units=256, masking_mode='E', use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256]),
+                    templates.dccrn_template, "enhance_dccrn", 32, 4, dict(p=0.5)),
+    "fullsubnet_32x10s": (lambda m: m.fullsubnet.Model(**FSN_ARGS), templates.fullsubnet_template, "enhance_fullsubnet",
+                          32, 10, dict(p=0.5)),
+    "uformer_64x4s": (lambda m: m.Uformer(), templates.uformer_template, "enhance_uformer", 64, 4, dict()),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE_CONFIGS))
+def test_full_size_configs_are_per_utterance_and_deterministic(name):
+    """BASELINE.json configs[2], [3], [4] at the size one GPU gets (256 / 8, 128 / 4, 512 / 8 clips): size-independent
+    properties of the decode path -- the output is finite, keeps the clip length, a clip decoded inside the full batch
+    equals the same clip decoded in a batch of two (per-utterance semantics at any batch size: FullSubNet's reference
+    changes behaviour for B > 1), and a second call reproduces the first bit for bit."""
+    dev = _dev()
+    import se_b200
+    ctor, tmpl, loop, clips, secs, kw = FULL_SIZE_CONFIGS[name]
+    model = ctor(se_b200)
+    model.load_state_dict(synth.synthetic_state_dict(tmpl(), seed=0, gain=1.0))
+    model.eval().cuda()
+    n = 16000 * secs
+    base = synth.noisy_batch(8, n, first_index=40)
+    wav = torch.from_numpy(np.concatenate([base] * (clips // 8), axis=0)).to(dev)
+    fn = getattr(se_b200.decode, loop)
+    y = fn(model, wav, **kw)
+    assert y.shape == (clips, n) and torch.isfinite(y).all()
+    y2 = fn(model, wav, **kw)
+    assert torch.equal(y, y2)
+    small = fn(model, wav[6:8], **kw)
+    scale = max(1.0, y.abs().max().item())
+    for r in range(clips // 8):
+        assert (y[8 * r + 6:8 * r + 8] - small).abs().max().item() < 2e-5 * scale
