@@ -67,6 +67,7 @@ struct StftParams {
   long long msb, mst, msf;
   long long sb, st, sf;
   float p_mag, p_ri;
+  const float2* twiddles;   // [32][2R + 5], see WarpFFT<R>::fill_table
 };
 
 __device__ __forceinline__ float pow_pos(float m, float p) {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
     }
   }
   WarpFFT<R> fft;
-  fft.init(lane);
+  fft.init(lane, p.twiddles);
   if (interior) mbar_wait(bar, 0);
   __syncthreads();
 
@@ -213,6 +214,7 @@ struct IstftParams {
   long long out_stride;
   int L;
   int nf_max;
+  const float2* twiddles;   // [32][2R + 5], see WarpFFT<R>::fill_table
 };
 
 template <int R>
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
   if (nf > 0) {
     const bool time_major = (p.a_sf <= p.a_st);
     const int total = nf * F;
+#pragma unroll 4   // independent global loads of 4 bins in flight per thread (the loop was long-scoreboard bound)
     for (int idx = tid; idx < total; idx += kDspThreads) {
       int i, k;
       if (time_major) {
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
     }
   }
   WarpFFT<R> fft;
-  fft.init(lane);
+  fft.init(lane, p.twiddles);
   __syncthreads();
 
   // --- stage 2: one warp per frame: irFFT, window, time-domain frame back into its buffer ---
@@ -395,6 +398,36 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
   yb[t] = acc;
 }
 
+// Twiddle tables of the two FFT sizes in static device memory (no allocation behind the caller's back), filled on the
+// first call per device: 32 lanes x (2 R + 5) float2.
+__device__ float2 g_twiddles5[32 * WarpFFT<5>::kTwPerLane];
+__device__ float2 g_twiddles8[32 * WarpFFT<8>::kTwPerLane];
+
+static const float2* dsp_twiddles(int R, cudaStream_t s) {
+  constexpr int kMaxDev = 64;
+  static bool ready[kMaxDev][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int which = R == 5 ? 0 : 1;
+  void* sym = nullptr;
+  if (cudaGetSymbolAddress(&sym, R == 5 ? (const void*)g_twiddles5 : (const void*)g_twiddles8) != cudaSuccess) return nullptr;
+  if (dev < 0 || dev >= kMaxDev || !ready[dev][which]) {
+    float2 host[32 * WarpFFT<8>::kTwPerLane];
+    size_t bytes;
+    if (R == 5) {
+      WarpFFT<5>::fill_table(host);
+      bytes = sizeof(float2) * 32 * WarpFFT<5>::kTwPerLane;
+    } else {
+      WarpFFT<8>::fill_table(host);
+      bytes = sizeof(float2) * 32 * WarpFFT<8>::kTwPerLane;
+    }
+    // pageable source: the copy is staged before the call returns; ordered before the launch that follows on `s`
+    if (cudaMemcpyAsync(sym, host, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return nullptr;
+    if (dev >= 0 && dev < kMaxDev) ready[dev][which] = true;
+  }
+  return reinterpret_cast<const float2*>(sym);
+}
+
 static int dsp_smem_stft(int R, int hop) {
   const int nfft = 64 * R;
   const int tile = (kFramesPerCta - 1) * hop + nfft;
@@ -433,7 +466,9 @@ extern "C" int se_stft(const float* wav, long long wav_stride, int B, int N, con
   SE_REQUIRE(T == 1 + N / hop, "se_stft: T=%d but 1+N/hop=%d", T, 1 + N / hop);
   SE_REQUIRE((re == nullptr) == (im == nullptr), "se_stft: re and im must both be given or both NULL");
   SE_REQUIRE(mag || re, "se_stft: no output plane");
-  StftParams p{wav, wav_stride, B, N, scale, win, hop, T, mag, re, im, msb, mst, msf, sb, st, sf, p_mag, p_ri};
+  StftParams p{wav, wav_stride, B, N, scale, win, hop, T, mag, re, im, msb, mst, msf, sb, st, sf, p_mag, p_ri, nullptr};
+  p.twiddles = dsp_twiddles(n_fft / 64, (cudaStream_t)stream);
+  SE_REQUIRE(p.twiddles != nullptr, "se_stft: twiddle table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   dim3 grid(ceil_div(T, kFramesPerCta), B);
   const int R = n_fft / 64;
   const int smem = dsp_smem_stft(R, hop);
@@ -462,7 +497,9 @@ extern "C" int se_istft(int mode, const float* a_re, const float* a_im, long lon
   SE_REQUIRE(mode == SE_ISTFT_MAG_PHASE || a_im, "se_istft: a_im required for mode %d", mode);
   SE_REQUIRE(mode < SE_ISTFT_MAG_PHASE || (b_re && b_im), "se_istft: noisy spectrum (b_re,b_im) required");
   IstftParams p{mode, a_re, a_im, a_sb, a_st, a_sf, b_re, b_im, b_sb, b_st, b_sf, inv_p, p_x, B, T, win, hop,
-                out_scale, out, out_stride, L, 0};
+                out_scale, out, out_stride, L, 0, nullptr};
+  p.twiddles = dsp_twiddles(n_fft / 64, (cudaStream_t)stream);
+  SE_REQUIRE(p.twiddles != nullptr, "se_istft: twiddle table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   p.nf_max = kHopBlocksPerCta + ceil_div(n_fft, hop) + 1;
   const int R = n_fft / 64;
   const int smem = n_fft * 4 + ((p.nf_max + 3) & ~3) * 4 + p.nf_max * R * 66 * 4;

@@ -90,24 +90,42 @@ struct WarpFFT {
   float2 tws[5];  // stage h = 16,8,4,2,1: exp(-2 pi i (lane&(h-1)) / (2h))
   int lane, src0;
 
-  __device__ __forceinline__ void init(int lane_) {
+  // Twiddles of one lane: kTwPerLane float2 = tw2[0..R) | twp[0..R) | tws[0..5), rounded from float64.  They are computed
+  // ONCE per device on the host (fill_table) and read back with 2 R + 5 cached 8-byte loads: evaluating them in the
+  // kernel cost 15 double-precision sincospi per thread and CTA, 43 % of all instructions of the STFT (ncu, round 1).
+  static constexpr int kTwPerLane = 2 * R + 5;
+
+  static void fill_table(float2* tab /* [32][kTwPerLane] */) {
+    const double pi = 3.14159265358979323846;
+    for (int l = 0; l < 32; ++l) {
+      int br = 0;
+      for (int bit = 0; bit < 5; ++bit) br |= ((l >> bit) & 1) << (4 - bit);
+      float2* t = tab + l * kTwPerLane;
+      for (int k1 = 0; k1 < R; ++k1) {
+        const double a = 2.0 * pi * (double)((l * k1) % N2) / (double)N2;
+        const double b = 2.0 * pi * (double)(k1 + R * br) / (double)N;
+        t[k1] = make_float2((float)cos(a), (float)-sin(a));
+        t[R + k1] = make_float2((float)cos(b), (float)-sin(b));
+      }
+      for (int si = 0; si < 5; ++si) {
+        const int h = 16 >> si;
+        const double a = pi * (double)(l & (h - 1)) / (double)h;
+        t[2 * R + si] = make_float2((float)cos(a), (float)-sin(a));
+      }
+    }
+  }
+
+  __device__ __forceinline__ void init(int lane_, const float2* __restrict__ tab) {
     lane = lane_;
     const int br = bitrev5(lane);
+    const float2* t = tab + lane * kTwPerLane;
 #pragma unroll
     for (int k1 = 0; k1 < R; ++k1) {
-      double s, c;
-      sincospi(2.0 * (double)(lane * k1) / (double)N2, &s, &c);
-      tw2[k1] = make_float2((float)c, (float)-s);
-      sincospi(2.0 * (double)(k1 + R * br) / (double)N, &s, &c);
-      twp[k1] = make_float2((float)c, (float)-s);
+      tw2[k1] = __ldg(t + k1);
+      twp[k1] = __ldg(t + R + k1);
     }
 #pragma unroll
-    for (int si = 0; si < 5; ++si) {
-      const int h = 16 >> si;
-      double s, c;
-      sincospi((double)(lane & (h - 1)) / (double)h, &s, &c);
-      tws[si] = make_float2((float)c, (float)-s);
-    }
+    for (int si = 0; si < 5; ++si) tws[si] = __ldg(t + 2 * R + si);
     src0 = bitrev5((32 - br) & 31);
   }
 
