@@ -311,8 +311,7 @@ def enhance_host_stream(model, host_batches, enhance_fn=None, depth=2, device=No
     reference pays serially per utterance (CRN/crn_decode.py:46-47,53) disappear behind the compute.  All batches must
     have the same shape (one ring of ``depth`` device / host buffers)."""
     fn = enhance_fn or enhancer_for(model)
-    dev = torch.device(device if device is not None else "cuda", torch.cuda.current_device()) \
-        if not isinstance(device, torch.device) else device
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     compute = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     dev_in, host_out = [None] * depth, [None] * depth
