@@ -377,6 +377,10 @@ int se_resample(const float* x, long long x_stride, int B, int n_in, float* y, l
 int se_uf_prep(const float* x, int B, int T, int F, float* mag, float* phase, float* cplx_in, float* mag_in,
                se_stream_t stream);
 int se_uf_fusion(const float* c, const float* m, long long rows, int C, float* c_out, float* m_out, se_stream_t stream);
+/* The same with each result as fp32 (c_out / m_out) and / or as the TF32 (hi, lo) pair the tensor-core convs read
+ * (c_hi, c_lo / m_hi, m_lo); unused outputs NULL.  Saves the split pass between a fusion and the next U-Net conv. */
+int se_uf_fusion_ex(const float* c, const float* m, long long rows, int C, float* c_out, float* c_hi, float* c_lo,
+                    float* m_out, float* m_hi, float* m_lo, se_stream_t stream);
 int se_group_layernorm(const float* x, const float* gate, long long rows, int G, int C, const float* gamma,
                        const float* beta, float eps, int post, float slope, const float* res, const int* out_index,
                        float* out, float* out_hi, float* out_lo, se_stream_t stream);

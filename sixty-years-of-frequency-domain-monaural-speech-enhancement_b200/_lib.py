@@ -72,6 +72,7 @@ PROTOTYPES = {
     "se_conv_tf32x3": (_I, [C.POINTER(ConvTcDesc), _P]),
     "se_uf_prep": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "se_uf_fusion": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
+    "se_uf_fusion_ex": (_I, [_P, _P, _LL, _I, _P, _P, _P, _P, _P, _P, _P]),
     "se_group_layernorm": (_I, [_P, _P, _LL, _I, _I, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P]),
     "se_attention": (_I, [_P, _I, _I, _P, _P, _I, _I, _LL, _I, _LL, _I, _LL, _F, _P, _I, _P]),
     "se_uf_mask": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),

@@ -40,20 +40,64 @@ __global__ void __launch_bounds__(256) uf_prep_kernel(const float2* __restrict__
 }
 
 // c [rows, 2C] = (re C | im C), m [rows, C]:  m' = m + sigmoid(|c|);  c' = c + sigmoid(m)   (fusion.py:13-19)
-__global__ void __launch_bounds__(256) uf_fusion_kernel(const float* __restrict__ c, const float* __restrict__ m,
-                                                       long long rows, int C, float* __restrict__ c_out,
-                                                       float* __restrict__ m_out) {
-  const long long n = rows * C;
+// V channels per thread (V = 4: float4 traffic, C % 4 == 0).  Each result goes out as fp32 and / or as the TF32 (hi, lo)
+// pair the tensor-core convs read, so the U-Net levels need no separate split pass after the fusion.
+struct FusionParams {
+  const float *c, *m;
+  long long rows;
+  int C;
+  float *c_out, *c_hi, *c_lo, *m_out, *m_hi, *m_lo;
+};
+
+template <int V>
+__device__ __forceinline__ void fusion_store(float* out, float* hi, float* lo, long long off, const float (&v)[V]) {
+  if constexpr (V == 4) {
+    if (out) *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+    if (hi) {
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32_dev(v[e], h[e], l[e]);
+      *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  } else {
+    if (out) out[off] = v[0];
+    if (hi) split_tf32_dev(v[0], hi[off], lo[off]);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) uf_fusion_kernel(const FusionParams p) {
+  const int C = p.C, CV = C / V;
+  const long long n = p.rows * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C;
-    const int ch = (int)(i - r * C);
-    const float cr = __ldg(c + r * 2 * C + ch), ci = __ldg(c + r * 2 * C + C + ch);
-    const float mv = __ldg(m + i);
-    const float cm = sqrtf(fmaxf(cr * cr + ci * ci, UF_EPS));
-    const float sg = sigmoid_f(mv);
-    m_out[i] = mv + sigmoid_f(cm);
-    c_out[r * 2 * C + ch] = cr + sg;
-    c_out[r * 2 * C + C + ch] = ci + sg;
+    const long long r = i / CV;
+    const int ch = (int)(i - r * CV) * V;
+    float cr[V], ci[V], mv[V];
+    if constexpr (V == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.c + r * 2 * C + ch));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.c + r * 2 * C + C + ch));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(p.m + r * C + ch));
+      cr[0] = a.x; cr[1] = a.y; cr[2] = a.z; cr[3] = a.w;
+      ci[0] = b.x; ci[1] = b.y; ci[2] = b.z; ci[3] = b.w;
+      mv[0] = d.x; mv[1] = d.y; mv[2] = d.z; mv[3] = d.w;
+    } else {
+      cr[0] = __ldg(p.c + r * 2 * C + ch);
+      ci[0] = __ldg(p.c + r * 2 * C + C + ch);
+      mv[0] = __ldg(p.m + r * C + ch);
+    }
+    float mo[V], cro[V], cio[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float cm = sqrtf(fmaxf(cr[e] * cr[e] + ci[e] * ci[e], UF_EPS));
+      const float sg = sigmoid_f(mv[e]);
+      mo[e] = mv[e] + sigmoid_f(cm);
+      cro[e] = cr[e] + sg;
+      cio[e] = ci[e] + sg;
+    }
+    fusion_store<V>(p.m_out, p.m_hi, p.m_lo, r * C + ch, mo);
+    fusion_store<V>(p.c_out, p.c_hi, p.c_lo, r * 2 * C + ch, cro);
+    fusion_store<V>(p.c_out, p.c_hi, p.c_lo, r * 2 * C + C + ch, cio);
   }
 }
 
@@ -319,11 +363,25 @@ extern "C" int se_uf_prep(const float* x, int B, int T, int F, float* mag, float
   return check_launch("se_uf_prep");
 }
 
+extern "C" int se_uf_fusion_ex(const float* c, const float* m, long long rows, int C, float* c_out, float* c_hi,
+                               float* c_lo, float* m_out, float* m_hi, float* m_lo, se_stream_t stream) {
+  SE_REQUIRE(c && m && rows > 0 && C > 0, "se_uf_fusion: bad arguments");
+  SE_REQUIRE((c_out || c_hi) && (m_out || m_hi), "se_uf_fusion: every result needs an fp32 or a split output");
+  SE_REQUIRE((c_hi == nullptr) == (c_lo == nullptr) && (m_hi == nullptr) == (m_lo == nullptr),
+             "se_uf_fusion: hi / lo outputs go together");
+  const FusionParams p{c, m, rows, C, c_out, c_hi, c_lo, m_out, m_hi, m_lo};
+  const uintptr_t all = (uintptr_t)c | (uintptr_t)m | (uintptr_t)c_out | (uintptr_t)c_hi | (uintptr_t)c_lo |
+                        (uintptr_t)m_out | (uintptr_t)m_hi | (uintptr_t)m_lo;
+  if ((C & 3) == 0 && (all & 15) == 0)
+    uf_fusion_kernel<4><<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(p);
+  else
+    uf_fusion_kernel<1><<<grid_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("se_uf_fusion");
+}
+
 extern "C" int se_uf_fusion(const float* c, const float* m, long long rows, int C, float* c_out, float* m_out,
                             se_stream_t stream) {
-  SE_REQUIRE(c && m && c_out && m_out && rows > 0 && C > 0, "se_uf_fusion: bad arguments");
-  uf_fusion_kernel<<<grid_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(c, m, rows, C, c_out, m_out);
-  return check_launch("se_uf_fusion");
+  return se_uf_fusion_ex(c, m, rows, C, c_out, nullptr, nullptr, m_out, nullptr, nullptr, stream);
 }
 
 extern "C" int se_group_layernorm(const float* x, const float* gate, long long rows, int G, int C, const float* gamma,

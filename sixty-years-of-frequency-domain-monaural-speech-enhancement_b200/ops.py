@@ -536,6 +536,26 @@ def uf_fusion(c, m):
     return co, mo
 
 
+def uf_fusion_ex(c, m, c_f32=True, c_pair=False, m_f32=True, m_pair=False):
+    """uf_fusion with every result as fp32 and / or TF32 (hi, lo) pair: returns (c_f32 | None, c_pair | None,
+    m_f32 | None, m_pair | None)."""
+    _need_cuda(c, m)
+    device_check()
+    ch = m.shape[-1]
+    rows = m.numel() // ch
+    assert c.shape[-1] == 2 * ch and c.is_contiguous() and m.is_contiguous()
+    assert (c_f32 or c_pair) and (m_f32 or m_pair)
+    co = torch.empty_like(c) if c_f32 else None
+    mo = torch.empty_like(m) if m_f32 else None
+    cp = (torch.empty_like(c), torch.empty_like(c)) if c_pair else None
+    mp = (torch.empty_like(m), torch.empty_like(m)) if m_pair else None
+    with _Timed("uf_fusion"):
+        check(_lib.load().se_uf_fusion_ex(_ptr(c), _ptr(m), rows, ch, _ptr(co), _ptr(cp[0] if cp else None),
+                                          _ptr(cp[1] if cp else None), _ptr(mo), _ptr(mp[0] if mp else None),
+                                          _ptr(mp[1] if mp else None), _stream()), "se_uf_fusion_ex")
+    return co, cp, mo, mp
+
+
 _LN_POST = {"none": 0, "prelu": 1, "swish": 2}
 
 

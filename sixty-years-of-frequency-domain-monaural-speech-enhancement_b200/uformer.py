@@ -334,23 +334,46 @@ class Uformer(nn.Module):
         b, t, fb, _ = x.shape
         dev = x.device
         mag, phase, c, m = ops.uf_prep(x)                       # c [B,T,256,2], m [B,T,256,1]
+        c, m = Act(c), Act(m)
         fin = 256
         enc_c, enc_m = [], []
+        tc = conv_engine.tc_eligible
+
+        def fuse(oc, om, forms):
+            """Cross-branch fusion whose results leave in the form(s) their consumers read: fp32 for the FMA convs and the
+            conformer, the TF32 pair for tensor-core convs (no separate split pass).  forms = ((c_f32, c_pair),
+            (m_f32, m_pair))."""
+            (cf, cp), (mf, mp) = forms
+            rcf, rcp, rmf, rmp = ops.uf_fusion_ex(oc, om, c_f32=cf, c_pair=cp, m_f32=mf, m_pair=mp)
+            return Act(rcf, rcp), Act(rmf, rmp)
+
         for i in range(6):
             fo = fin // 2
             outs = []
             for src, key, ci, co in ((c, f"enc_c{i}", 2 * KN[i], 2 * KN[i + 1]), (m, f"enc_m{i}", KN[i], KN[i + 1])):
                 w, bias, slope = P[key]
                 out = conv_engine.new_act(b, t, fo, co, dev, want_f32=True, want_pair=False)
-                conv_engine.conv(Act(src), None, b, t, fin, fo, ENC_TAPS, 2, w, bias, "prelu", out, fo, act_param=slope)
+                conv_engine.conv(src, None, b, t, fin, fo, ENC_TAPS, 2, w, bias, "prelu", out, fo, act_param=slope)
                 outs.append(out.f32)
             if taps is not None:
                 taps[f"encraw{i}_c"], taps[f"encraw{i}_m"] = outs
-            c, m = ops.uf_fusion(outs[0], outs[1])
+            forms = []
+            for ch, nxt, dec_co in ((2 * KN[i + 1], 2 * KN[i + 2] if i < 5 else 0, 2 * KN[i]),
+                                    (KN[i + 1], KN[i + 2] if i < 5 else 0, KN[i])):
+                # consumers: the next encoder conv (or the conformer after the last level) and decoder level 5 - i, which
+                # takes this level as its skip source (C0 = C1 = ch, Cout = dec_co, Fout = fo)
+                users_tc = [tc(ch, ch, dec_co, fo, 1)]
+                if i < 5:
+                    users_tc.append(tc(ch, 0, nxt, fo // 2, 2))
+                want_pair = any(users_tc)
+                want_f32 = (not all(users_tc)) or i == 5 or taps is not None
+                forms.append((want_f32, want_pair))
+            c, m = fuse(outs[0], outs[1], forms)
             enc_c.append(c)
             enc_m.append(m)
             fin = fo
-        c, m = self._conformer(c, m, b, t, fin, taps)
+        c, m = self._conformer(c.get_f32(), m.get_f32(), b, t, fin, taps)
+        c, m = Act(c), Act(m)
         for di in range(6):
             fo = 2 * fin
             last = di == 5
@@ -360,7 +383,7 @@ class Uformer(nn.Module):
                 we, wo, bias, slope = P[key]
                 act = "none" if last else "prelu"
                 out = conv_engine.new_act(b, t, fo, co, dev, want_f32=True, want_pair=False)
-                s0, s1 = Act(skip), Act(cur)
+                s0, s1 = skip, cur
                 conv_engine.conv(s0, s1, b, t, fin, fin, DEC_EVEN, 1, we, bias, act, out, fo, dst_f0=0, dst_fstep=2,
                                  act_param=slope)
                 conv_engine.conv(s0, s1, b, t, fin, fin, DEC_ODD, 1, wo, bias, act, out, fo, dst_f0=1, dst_fstep=2,
@@ -368,9 +391,16 @@ class Uformer(nn.Module):
                 outs.append(out.f32)
             if taps is not None:
                 taps[f"decraw{di}_c"], taps[f"decraw{di}_m"] = outs
-            c, m = ops.uf_fusion(outs[0], outs[1])
+            if last:
+                c, m = fuse(outs[0], outs[1], ((True, False), (True, False)))
+            else:
+                forms = []
+                for ch, nco in ((2 * KN[5 - di], 2 * KN[4 - di]), (KN[5 - di], KN[4 - di])):
+                    nxt_tc = tc(ch, ch, nco, fo, 1)                       # the next decoder conv: C0 = skip, C1 = this
+                    forms.append((not nxt_tc, nxt_tc))
+                c, m = fuse(outs[0], outs[1], forms)
             fin = fo
-        return ops.uf_mask(c, m, mag, phase)
+        return ops.uf_mask(c.get_f32(), m.get_f32(), mag, phase)
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()

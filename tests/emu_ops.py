@@ -258,6 +258,13 @@ def uf_fusion(c, m):
     return torch.cat([cr + sg, ci + sg], -1), m + torch.sigmoid(cm)
 
 
+def uf_fusion_ex(c, m, c_f32=True, c_pair=False, m_f32=True, m_pair=False):
+    from se_b200 import packing
+    co, mo = uf_fusion(c, m)
+    return (co if c_f32 else None, packing.split_tf32(co.float()) if c_pair else None,
+            mo if m_f32 else None, packing.split_tf32(mo.float()) if m_pair else None)
+
+
 def group_layernorm(x, groups, gamma, beta, gate=None, post="none", slope=0.0, res=None, want_f32=True,
                     want_pair=False, eps=1e-5, out_index=None):
     from se_b200 import packing
@@ -324,7 +331,7 @@ def unary(x, act, act_param=0.0, want_f32=True, want_pair=False):
     return (y if want_f32 else None), (packing.split_tf32(y) if want_pair else None)
 
 
-_UF_NAMES = ("glu_affine_act", "unary", "cmul", "lstm_cell_tf32x3_ex", "gemm_tf32x3_ex", "uf_prep", "uf_fusion", "group_layernorm", "attention", "uf_mask")
+_UF_NAMES = ("glu_affine_act", "unary", "cmul", "lstm_cell_tf32x3_ex", "gemm_tf32x3_ex", "uf_prep", "uf_fusion", "uf_fusion_ex", "group_layernorm", "attention", "uf_mask")
 _orig_install = install
 
 

@@ -706,3 +706,23 @@ def test_pad_split_tf32_and_odd_k_projection():
     ref = x.double() @ w_ih.double()[rows].t() + (b_ih + b_hh).double()[rows]
     assert (got.cpu().double() - ref).abs().max() < 1e-5
 
+
+@pytest.mark.parametrize("ch", [1, 8, 32, 130])
+def test_uf_fusion_ex_outputs(ch):
+    """se_uf_fusion_ex: fp32 and TF32-pair outputs of the cross-branch fusion (vector path for C % 4 == 0, scalar else)."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(ch)
+    c = torch.randn(3, 5, 7, 2 * ch, generator=g)
+    m = torch.randn(3, 5, 7, ch, generator=g)
+    rc, rm = emu_ops.uf_fusion(c.double(), m.double())
+    cf, cp, mf, mp = ops.uf_fusion_ex(c.to(dev), m.to(dev), c_f32=True, c_pair=True, m_f32=True, m_pair=True)
+    assert (cf.cpu().double() - rc).abs().max() < 2e-6 and (mf.cpu().double() - rm).abs().max() < 2e-6
+    for f32, pair in ((cf, cp), (mf, mp)):
+        hi, lo = packing.split_tf32(f32.cpu())
+        assert torch.equal(pair[0].cpu(), hi) and torch.equal(pair[1].cpu(), lo)
+    cf2, cp2, mf2, mp2 = ops.uf_fusion_ex(c.to(dev), m.to(dev), c_f32=False, c_pair=True, m_f32=True, m_pair=False)
+    assert cf2 is None and mp2 is None and torch.equal(cp2[0], cp[0]) and torch.equal(mf2, mf)
+
