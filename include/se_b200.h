@@ -307,6 +307,12 @@ typedef struct se_conv_tc_desc {
   float act_param;
   float *out, *out_hi, *out_lo;
   int dstF, dst_f0, dst_fstep;
+  /* gated conv (GluConv2d / GluConvTranspose2d, GCRN/GCRN_noncprs.py:42-83): when glu != 0 the Cout GEMM columns are
+   * (conv1, conv2) pairs -- column 2j = conv1 of channel j, 2j+1 = conv2 -- and the outputs have Cout / 2 channels:
+   * act((conv1 * sigmoid(conv2)) * glu_scale[j] + glu_shift[j])  (gate, eval BatchNorm, ELU in the epilogue;
+   * scale / shift may be NULL).  Cout %% 8 == 0, act ELU or none. */
+  int glu;
+  const float *glu_scale, *glu_shift;
 } se_conv_tc_desc;
 int se_conv_tf32x3(const se_conv_tc_desc* desc, se_stream_t stream);
 

@@ -36,6 +36,7 @@ class ConvTcDesc(C.Structure):
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p), ("Cout", C.c_int), ("act", C.c_int),
         ("act_param", C.c_float), ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
         ("dstF", C.c_int), ("dst_f0", C.c_int), ("dst_fstep", C.c_int),
+        ("glu", C.c_int), ("glu_scale", C.c_void_p), ("glu_shift", C.c_void_p),
     ]
 
 

@@ -52,14 +52,18 @@ def tc_eligible(c0, c1, cout, fout, sf):
 
 
 def conv(src: Act, skip, B, T, Fin, Fout, taps, sf, w: ConvWeights, bias, act, dst: Act, dstF, dst_f0=0, dst_fstep=1,
-         act_param=0.0, fill_f=-1, fill=None):
-    """Runs one implicit-GEMM launch writing into ``dst`` (whichever of dst.f32 / dst.pair exist)."""
+         act_param=0.0, fill_f=-1, fill=None, glu=None):
+    """Runs one implicit-GEMM launch writing into ``dst`` (whichever of dst.f32 / dst.pair exist).  ``glu`` = (scale,
+    shift): gated conv fused into the tensor-core epilogue (``w`` / ``bias`` with interleaved (conv1, conv2) columns,
+    ``dst`` with w.cout / 2 channels); tensor-core layers only."""
     c0 = src.shape[-1]
     c1 = skip.shape[-1] if skip is not None else 0
+    if glu is not None and not tc_eligible(c0, c1, w.cout, Fout, sf):
+        raise RuntimeError("the fused gate needs a tensor-core eligible layer")
     if tc_eligible(c0, c1, w.cout, Fout, sf):
         ops.conv_tf32x3(src.get_pair(), skip.get_pair() if skip is not None else None, B, T, Fin, Fout, taps, sf,
                         w.hi, w.lo, bias, w.cout, act, dstF, dst_f0, dst_fstep, act_param=act_param, out=dst.f32,
-                        out_pair=dst.pair)
+                        out_pair=dst.pair, glu=glu)
         if fill_f >= 0:
             if dst.f32 is not None:
                 ops.fill_column(dst.f32, fill, fill_f, act, act_param)

@@ -44,6 +44,10 @@ struct ConvTcParams {
   float *out, *out_hi, *out_lo;  // any may be NULL
   int dstF, dst_f0, dst_fstep;
   int a_bytes;                // bytes one A box writes (Tbox*Fout*128)
+  // gated conv (GCRN/GCRN_noncprs.py:42-57): GEMM columns (2j, 2j+1) = (conv1, conv2) of output channel j; the epilogue
+  // writes act((a * sigmoid(b)) * glu_scale[j] + glu_shift[j]) into a tensor of Cout / 2 channels
+  int glu;
+  const float *glu_scale, *glu_shift;
 };
 
 __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, unsigned leader_bar, void* dst, int c0, int c1,
@@ -123,6 +127,40 @@ __device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float
       for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
       *reinterpret_cast<float4*>(p.out_hi + orow + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<float4*>(p.out_lo + orow + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// Gated variant: the thread's NC columns are NC / 2 (conv1, conv2) pairs -> NC / 2 output channels starting at n0 / 2.
+// `orow` is the row offset in the OUTPUT tensor (Cout / 2 channels).
+template <int NC, int ACT>
+__device__ __forceinline__ void conv_tc_store_glu(const ConvTcParams& p, const float (&sum)[NC], long long orow, int n0) {
+  if constexpr (NC >= 8) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 8) {
+      if (n0 + j >= p.Cout) break;          // Cout % 8 == 0 (host check)
+      float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bb[e] = __ldg(p.bias + n0 + j + e);
+      }
+      const int co = (n0 + j) >> 1;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = sum[j + 2 * e] + bb[2 * e], g = sum[j + 2 * e + 1] + bb[2 * e + 1];
+        float v = a * sigmoid_f(g);
+        v = v * (p.glu_scale ? __ldg(p.glu_scale + co + e) : 1.f) + (p.glu_shift ? __ldg(p.glu_shift + co + e) : 0.f);
+        o[e] = tc_act<ACT>(v, p.act_param);
+      }
+      if (p.out) *reinterpret_cast<float4*>(p.out + orow + co) = make_float4(o[0], o[1], o[2], o[3]);
+      if (p.out_hi) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+        *reinterpret_cast<float4*>(p.out_hi + orow + co) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(p.out_lo + orow + co) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
   }
 }
@@ -343,9 +381,15 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       const int fo = r - tl * p.Fout;
       const int t = t0 + tl;
       if (tl >= p.Tbox || t >= p.T || b >= p.B) continue;
-      const long long orow =
-          (((long long)b * p.T + t) * p.dstF + p.dst_f0 + (long long)fo * p.dst_fstep) * (long long)p.Cout;
+      const long long opos = ((long long)b * p.T + t) * p.dstF + p.dst_f0 + (long long)fo * p.dst_fstep;
+      const long long orow = opos * (long long)p.Cout;
       const int n0 = nb * BN + half * EPI_COLS;
+      if (p.glu) {
+        const long long grow = opos * (long long)(p.Cout >> 1);
+        if (p.act == SE_ACT_ELU) conv_tc_store_glu<EPI_COLS, SE_ACT_ELU>(p, sum, grow, n0);
+        else conv_tc_store_glu<EPI_COLS, SE_ACT_NONE>(p, sum, grow, n0);
+        continue;
+      }
       switch (p.act) {   // uniform: one branch per tile, the activation itself is a template parameter
         case SE_ACT_PRELU: conv_tc_store<EPI_COLS, SE_ACT_PRELU>(p, sum, orow, n0); break;
         case SE_ACT_ELU: conv_tc_store<EPI_COLS, SE_ACT_ELU>(p, sum, orow, n0); break;
@@ -486,6 +530,11 @@ extern "C" int se_conv_tf32x3(const se_conv_tc_desc* d, se_stream_t stream) {
   p.dst_f0 = d->dst_f0;
   p.dst_fstep = d->dst_fstep;
   p.a_bytes = p.Tbox * p.Fout * CT_BK * 4;
+  p.glu = d->glu;
+  p.glu_scale = d->glu_scale;
+  p.glu_shift = d->glu_shift;
+  SE_REQUIRE(!d->glu || (d->Cout % 8 == 0 && d->Cout >= 32 && (d->act == SE_ACT_ELU || d->act == SE_ACT_NONE)),
+             "se_conv_tf32x3 (gated): Cout=%d must be a multiple of 8 and >= 32, act ELU or none", d->Cout);
   const int K = d->ntaps * (d->C0 + d->C1);
   // engine 1 (se_set_gemm_engine): CTA pairs where at least two activation tiles exist and the tile is >= 64 wide
   const bool pair = gemm_engine_is_pair() && d->Cout > 32 && (long long)d->B * ceil_div(d->T, p.Tbox) >= 2;

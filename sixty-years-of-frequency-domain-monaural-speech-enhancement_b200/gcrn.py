@@ -99,11 +99,18 @@ class Net(nn.Module):
                                    sd[pre + ".running_var"])
             return s.contiguous(), o.contiguous()
 
+        def interleaved(w_ab, bias_ab):
+            """[a | b] columns -> (a_0, b_0, a_1, b_1, ...): the layout of the fused gate epilogue (se_conv_tc_desc.glu)."""
+            c = w_ab.shape[1] // 2
+            perm = torch.stack([torch.arange(c), torch.arange(c) + c], 1).reshape(-1).to(w_ab.device)
+            return ConvWeights(w_ab[:, perm].contiguous(), 2 * c), bias_ab[perm].contiguous()
+
         for i in range(1, 6):
             w1, w2 = sd[f"conv{i}.conv1.weight"], sd[f"conv{i}.conv2.weight"]             # [Co, Ci, 1, 3]
             w = torch.cat([torch.cat([w1[:, :, 0, kf].t(), w2[:, :, 0, kf].t()], 1) for kf in range(3)], 0)
             bias = torch.cat([sd[f"conv{i}.conv1.bias"], sd[f"conv{i}.conv2.bias"]]).contiguous()
             P[f"enc{i}"] = (ConvWeights(w.contiguous(), 2 * _CH[i]), bias, *bn(f"bn{i}"))   # K = (kf, ci), N = [a | b]
+            P[f"enc{i}_il"] = interleaved(w, bias)
         for br in (1, 2):
             for lvl in (5, 4, 3, 2, 1):
                 w1, w2 = sd[f"conv{lvl}_t_{br}.conv1.weight"], sd[f"conv{lvl}_t_{br}.conv2.weight"]   # [Ci, Co, 1, 3]
@@ -112,6 +119,8 @@ class Net(nn.Module):
                 bias = torch.cat([sd[f"conv{lvl}_t_{br}.conv1.bias"], sd[f"conv{lvl}_t_{br}.conv2.bias"]]).contiguous()
                 P[f"dec{lvl}_{br}"] = (ConvWeights(torch.cat([tap(0), tap(2)], 0).contiguous(), 2 * co),
                                        ConvWeights(tap(1).contiguous(), 2 * co), bias, *bn(f"bn{lvl}_t_{br}"))
+                P[f"dec{lvl}_{br}_il"] = (interleaved(torch.cat([tap(0), tap(2)], 0), bias)[0],
+                                          *interleaved(tap(1), bias))
             P[f"fc{br}"] = (packing.pad_cols(sd[f"fc{br}.weight"].t().contiguous()), sd[f"fc{br}.bias"].contiguous())
 
         # ---- GLSTM -----------------------------------------------------------------------------------
@@ -181,9 +190,20 @@ class Net(nn.Module):
         tc = conv_engine.tc_eligible
 
         def glu_layer(src, skip, fin, fout_classes, w_classes, bias, scale, shift, fout, taps_classes, sf, cons_tc,
-                      want_f32):
-            """One gated conv (all parity classes) + gate/BN/ELU.  cons_tc: the consumer reads the TF32 split."""
+                      want_f32, il=None):
+            """One gated conv (all parity classes) + gate/BN/ELU.  cons_tc: the consumer reads the TF32 split.
+            il = (interleaved weights per class, interleaved bias): on tensor-core layers gate, BatchNorm and ELU run in
+            the conv epilogue and the [a | b] intermediate never exists."""
             co2 = w_classes[0].cout
+            c0 = src.shape[-1]
+            c1 = skip.shape[-1] if skip is not None else 0
+            if il is not None and all(tc(c0, c1, co2, fo, sf) for fo in fout_classes):
+                wil, bil = il
+                out = conv_engine.new_act(b, t, fout, co2 // 2, dev, want_f32=want_f32 or not cons_tc, want_pair=cons_tc)
+                for cls, (w, tp, fo) in enumerate(zip(wil, taps_classes, fout_classes)):
+                    conv_engine.conv(src, skip, b, t, fin, fo, tp, sf, w, bil, "elu", out, fout, dst_f0=cls,
+                                     dst_fstep=len(wil), glu=(scale, shift))
+                return out
             tmp = Act(torch.empty(b, t, fout, co2, device=dev, dtype=torch.float32))
             for cls, (w, tp, fo) in enumerate(zip(w_classes, taps_classes, fout_classes)):
                 step = len(w_classes)
@@ -200,7 +220,8 @@ class Net(nn.Module):
             # consumers of e_i: conv_{i+1} (or the LSTM projection / first decoder layer for e5) and ELU(e_i)
             cons_tc = tc(_CH[i], 0, 2 * _CH[i + 1], _F[i + 1], 2) if i < 5 else lstm_engine.USE_TENSOR_CORES
             h = glu_layer(h, None, _F[i - 1], [_F[i]], [w], bias, s, o, _F[i], [ENC_TAPS], 2, cons_tc,
-                          want_f32=(i < 5))          # ELU(e_i) (se_unary) reads the fp32 copy
+                          want_f32=(i < 5),          # ELU(e_i) (se_unary) reads the fp32 copy
+                          il=([P[f"enc{i}_il"][0]], P[f"enc{i}_il"][1]))
             enc.append(h)
             if taps is not None:
                 taps[f"e{i}"] = h.f32 if h.f32 is not None else h.pair[0] + h.pair[1]
@@ -246,8 +267,9 @@ class Net(nn.Module):
                     cons_tc = tc(nco, nco, 2 * _DEC[lvl - 1][1], (_DEC_FOUT[lvl - 1] + 1) // 2, 1)
                 else:
                     cons_tc = False
+                wie, wio, bil = P[f"dec{lvl}_{br}_il"]
                 d = glu_layer(d, skips[lvl], fin, [(fout + 1) // 2, fout // 2], [we, wo], bias, s, o, fout,
-                              [DEC_EVEN, DEC_ODD], 1, cons_tc, want_f32=False)
+                              [DEC_EVEN, DEC_ODD], 1, cons_tc, want_f32=False, il=([wie, wio], bil))
             if taps is not None:
                 taps[f"d1_{br}"] = d.f32
             wfc, bfc = P[f"fc{br}"]

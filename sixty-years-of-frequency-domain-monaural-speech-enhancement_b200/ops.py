@@ -426,9 +426,11 @@ def resample(x, sr_orig, sr_new, out=None):
 
 
 def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, act, dstF, dst_f0=0, dst_fstep=1,
-                act_param=0.0, out=None, out_pair=None):
+                act_param=0.0, out=None, out_pair=None, glu=None):
     """Tensor-core implicit-GEMM conv.  src0 / src1: (hi, lo) tuples of channels-last [B,T,Fin,C];
-    w_hi / w_lo [Cout, ntaps*(C0+C1)].  out: fp32 [B,T,dstF,Cout] or None; out_pair: (hi, lo) or None."""
+    w_hi / w_lo [Cout, ntaps*(C0+C1)].  out: fp32 [B,T,dstF,Cout] or None; out_pair: (hi, lo) or None.
+    glu = (scale, shift) (either may be None): gated conv, GEMM columns are (conv1, conv2) pairs and the outputs have
+    Cout / 2 channels (see se_conv_tc_desc)."""
     device_check()
     d = ConvTcDesc()
     d.src0_hi, d.src0_lo = src0[0].data_ptr(), src0[1].data_ptr()
@@ -449,6 +451,9 @@ def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, a
     d.out_hi = out_pair[0].data_ptr() if out_pair is not None else 0
     d.out_lo = out_pair[1].data_ptr() if out_pair is not None else 0
     d.dstF, d.dst_f0, d.dst_fstep = dstF, dst_f0, dst_fstep
+    d.glu = 0 if glu is None else 1
+    d.glu_scale = glu[0].data_ptr() if glu is not None and glu[0] is not None else 0
+    d.glu_shift = glu[1].data_ptr() if glu is not None and glu[1] is not None else 0
     with _Timed(f"conv_tf32x3[K={len(taps) * (c0 + c1)},N={Cout}]"):
         check(_lib.load().se_conv_tf32x3(C.byref(d), _stream()), "se_conv_tf32x3")
 

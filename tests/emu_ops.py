@@ -115,11 +115,28 @@ def dccrn_mask(m, x_re, x_im, e_re, e_im, layout_x="btf", layout_e="btf", mode="
 
 
 def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, act, dstF, dst_f0=0, dst_fstep=1,
-                act_param=0.0, out=None, out_pair=None):
+                act_param=0.0, out=None, out_pair=None, glu=None):
     from se_b200 import packing
     x0 = src0[0] + src0[1]
     x1 = (src1[0] + src1[1]) if src1 is not None else None
     w = (w_hi + w_lo).t().contiguous()
+    if glu is not None:      # gated: columns (2j, 2j+1) = (conv1, conv2) of channel j, outputs have Cout / 2 channels
+        full = torch.zeros(B, T, dstF, Cout, dtype=x0.dtype)
+        conv_gemm(x0, x1, B, T, Fin, Fout, taps, sf, w, bias, Cout, "none", full, dstF, dst_f0, dst_fstep, -1, None, 0.0)
+        fs = torch.arange(Fout) * dst_fstep + dst_f0
+        v = full[:, :, fs, 0::2] * torch.sigmoid(full[:, :, fs, 1::2])
+        if glu[0] is not None:
+            v = v * glu[0]
+        if glu[1] is not None:
+            v = v + glu[1]
+        v = _act(v, act, act_param)
+        if out is not None:
+            out[:, :, fs] = v
+        if out_pair is not None:
+            hi, lo = packing.split_tf32(v.float().contiguous())
+            out_pair[0][:, :, fs] = hi
+            out_pair[1][:, :, fs] = lo
+        return
     tmp = out if out is not None else torch.zeros(B, T, dstF, Cout, dtype=x0.dtype)
     if out is None and out_pair is not None:
         tmp.copy_(out_pair[0] + out_pair[1])

@@ -726,3 +726,48 @@ def test_uf_fusion_ex_outputs(ch):
     cf2, cp2, mf2, mp2 = ops.uf_fusion_ex(c.to(dev), m.to(dev), c_f32=False, c_pair=True, m_f32=True, m_pair=False)
     assert cf2 is None and mp2 is None and torch.equal(cp2[0], cp[0]) and torch.equal(mf2, mf)
 
+
+
+@pytest.mark.parametrize("case", [(2, 9, 39, 32, 0, 64, "conv"), (1, 7, 19, 64, 64, 128, "deconv"),
+                                  (2, 5, 9, 128, 128, 256, "deconv")])
+def test_conv_tf32x3_gated_epilogue(case):
+    """Gated conv fused into the tensor-core epilogue (se_conv_tc_desc.glu): columns (2j, 2j+1) = (conv1, conv2),
+    out = ELU((conv1 * sigmoid(conv2)) * scale + shift) with Cout / 2 channels, fp32 and TF32-pair outputs."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    from se_b200.gcrn import DEC_EVEN, DEC_ODD, ENC_TAPS
+    ops = se_b200.ops
+    b, t, fin, c0, c1, co2, kind = case
+    g = torch.Generator().manual_seed(co2 + fin)
+    x0 = torch.randn(b, t, fin, c0, generator=g)
+    x1 = torch.randn(b, t, fin, c1, generator=g) if c1 else None
+    ct = c0 + c1
+    bias = torch.randn(co2, generator=g)
+    scale = torch.rand(co2 // 2, generator=g) + 0.5
+    shift = torch.randn(co2 // 2, generator=g)
+    if kind == "conv":
+        fout = (fin - 3) // 2 + 1
+        runs, dstF = [(ENC_TAPS, 2, fout, 0, 1)], fout
+    else:
+        dstF = 2 * fin + 1
+        runs = [(DEC_EVEN, 1, fin + 1, 0, 2), (DEC_ODD, 1, fin, 1, 2)]
+    ref = torch.zeros(b, t, dstF, co2 // 2, dtype=torch.float64)
+    got = torch.zeros(b, t, dstF, co2 // 2, device=dev)
+    got_hi, got_lo = torch.zeros_like(got), torch.zeros_like(got)
+    s0 = ops.split_tf32(x0.to(dev))
+    s1 = ops.split_tf32(x1.to(dev)) if x1 is not None else None
+    for taps, sf, fo, f0, fstep in runs:
+        w = torch.randn(len(taps) * ct, co2, generator=g) / np.sqrt(len(taps) * ct)
+        w_hi, w_lo = packing.split_tf32(w.t().contiguous())
+        emu_ops.conv_tf32x3((x0.double(), torch.zeros_like(x0).double()),
+                            None if x1 is None else (x1.double(), torch.zeros_like(x1).double()), b, t, fin, fo, taps, sf,
+                            w.t().contiguous().double(), torch.zeros(co2, len(taps) * ct, dtype=torch.float64),
+                            bias.double(), co2, "elu", dstF, f0, fstep, out=ref, glu=(scale.double(), shift.double()))
+        ops.conv_tf32x3(s0, s1, b, t, fin, fo, taps, sf, w_hi.to(dev), w_lo.to(dev), bias.to(dev), co2, "elu", dstF, f0,
+                        fstep, out=got, out_pair=(got_hi, got_lo), glu=(scale.to(dev), shift.to(dev)))
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - ref).abs().max().item()
+    err_pair = ((got_hi + got_lo).cpu().double() - ref).abs().max().item()
+    print(f"gated conv {case}: max err {err:.3e} (hi+lo {err_pair:.3e})")
+    assert err < 2e-5 and err_pair < 2e-5
