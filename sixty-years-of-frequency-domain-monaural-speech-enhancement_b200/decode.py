@@ -379,15 +379,26 @@ def write_wav(path, y, fs):
 
 
 def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, batch=64, device="cuda", enhance_fn=None,
-                resample_to=None, **kw):
+                resample_to=None, rank=None, world=None, **kw):
     """wav directory in -> wav directory out: the ``enhance(args)`` surface of the decode scripts (``args.mix_file_path``,
     ``args.esti_clean_file_path`` / ``args.esti_file_path``, ``args.fs``; e.g. CRN/crn_decode_vb.py:17-64).  The
     reference loops one file at a time; here files of equal length are batched (no model in the reference has a padding
     mask, so clips of different lengths never share a batch) and a batch stays on the device from the noisy waveform to
     the enhanced one.  ``resample_to=16000`` adds the front step of the ``*_decode_vb.py`` scripts
     (``librosa.resample(x, orig_fs, 16000, fix=True, scale=False)``, LSTM/lstm_decode_vb.py:33-34) on the device:
-    files are then grouped by (sample rate, length).  ``kw`` goes to the decode loop (``p=0.5`` for the compressed
-    checkpoints)."""
+    files are then grouped by (sample rate, length).  ``rank`` / ``world`` (default: the initialised
+    ``torch.distributed`` group, else one rank) shard the work over processes, one per GPU: every rank builds the same
+    list of batches and decodes batches ``rank, rank + world, ...``; utterances are independent and every rank writes
+    its own files, so no collective is involved.  Returns the number of files THIS rank wrote.
+    ``kw`` goes to the decode loop (``p=0.5`` for the compressed checkpoints)."""
+    if world is None:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        else:
+            rank, world = 0, 1
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
     fn = enhance_fn or enhancer_for(model)
     os.makedirs(esti_file_path, exist_ok=True)
     groups = {}
@@ -399,8 +410,12 @@ def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, batch=64, device
             x, sr = read_wav_any(path)
         groups.setdefault((sr, len(x)), []).append((name, x.astype(np.float32)))
     count = 0
+    ibatch = -1
     for (sr, _), group in sorted(groups.items()):
         for i in range(0, len(group), batch):
+            ibatch += 1
+            if ibatch % world != rank:
+                continue
             chunk = group[i:i + batch]
             wav = torch.from_numpy(np.stack([x for _, x in chunk])).to(device)
             if resample_to is not None:

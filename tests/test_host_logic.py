@@ -407,3 +407,26 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_enhance_dir_shards_batches_over_ranks(tmp_path):
+    """rank / world: every rank builds the same batch list and takes batches rank, rank + world, ...; together the
+    ranks write every file exactly once (utterances are independent: no collective)."""
+    decode = se_b200.decode
+    src = tmp_path / "noisy"
+    src.mkdir()
+    rng = np.random.default_rng(3)
+    names = {f"u{i:02d}.wav": (800 if i % 3 else 1200) for i in range(11)}
+    for name, n in names.items():
+        decode.write_wav(str(src / name), np.clip(rng.normal(0, 0.1, n), -0.9, 0.9), 16000)
+    written = []
+    for r in range(3):
+        dst = tmp_path / f"out{r}"
+        n = decode.enhance_dir(None, str(src), str(dst), fs=16000, batch=2, device="cpu",
+                               enhance_fn=lambda m, w: w, rank=r, world=3)
+        got = sorted(os.listdir(dst))
+        assert n == len(got)
+        written += got
+    assert sorted(written) == sorted(names)          # disjoint and complete
+    with pytest.raises(ValueError):
+        decode.enhance_dir(None, str(src), str(tmp_path / "bad"), device="cpu", enhance_fn=lambda m, w: w, rank=3, world=3)
