@@ -194,13 +194,17 @@ int se_lstm_seq_multi(const float* xproj, long long xproj_stride, long long xpro
                       long long whh_group_stride, int ngroups, int B, int T, int H, float* hseq, long long hseq_sb,
                       long long hseq_st, long long hseq_group_off, float* work, unsigned* sync, se_stream_t stream);
 /* Recurrence engine (process-global; for A/B measurements and tests):
- *   3 (default) = as 2, plus the sequence-parallel kernel for H = 128 (csrc/lstm.cu: lstm_seq_small_kernel -- all of
+ *   4 (default) = as 3, with the second-generation tcgen05 kernel at H = 1024 (csrc/lstm_f16.cu: FP16 hi/lo operand
+ *       pairs with power-of-two scales instead of TF32 pairs -- same three-term product, twice the MMA rate, half the
+ *       operand bytes -- and a barrier-free state exchange: h_t is published as self-validating tagged 32-bit words that
+ *       the consumers poll with plain L2 loads, no device-wide counter / proxy fence / TMA in the step's chain);
+ *   3 = as 2, plus the sequence-parallel kernel for H = 128 (csrc/lstm.cu: lstm_seq_small_kernel -- all of
  *       W_hh resident in one CTA's registers + shared memory, 1 / 2 / 4 whole sequences per CTA, no device-wide
  *       barrier): DPCRN's inter-chunk LSTM, DCCRN's real / imaginary LSTMs;
  *   2 = tcgen05 cluster kernel (csrc/lstm_tc.cu: W_hh hi part in tensor memory, K split over a cluster of
  *       4 CTAs with a DSMEM reduction) where it applies -- H = 1024, one group, 32 clusters of 4 co-resident -- and
  *       the FMA kernel elsewhere;
- *       (SE_LSTM_ENGINE=0..3 in the environment picks the start-up value for A/B runs);
+ *       (SE_LSTM_ENGINE=0..4 in the environment picks the start-up value for A/B runs);
  *   1 = legacy mma.sync TF32 path with the 3xTF32 split (H in {128, 512, 1024});
  *   0 = fp32 FMA kernel (any H %% 128 == 0).
  * Measured on B200 (H = 1024, B = 64): 7.9 / 14.4 / 13.8 us per step, see DESIGN.md. */

@@ -540,12 +540,13 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
 }
 
 // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu) where it applies (H = 1024, one
-// group, clusters fit the device), the FMA kernel elsewhere; 3 (default): as 2, plus the sequence-parallel kernel
-// (lstm_seq_small_kernel) for H = 128.
+// group, clusters fit the device), the FMA kernel elsewhere; 3: as 2, plus the sequence-parallel kernel
+// (lstm_seq_small_kernel) for H = 128; 4 (default): as 3 with the fp16-pair / tagged-state tcgen05 kernel (lstm_f16.cu) at
+// H = 1024.
 // -1 = not chosen yet: SE_LSTM_ENGINE in the environment (A/B runs), else the default.
 static int g_lstm_engine = -1;
-constexpr int kDefaultLstmEngine = 3;
-constexpr int kMaxLstmEngine = 3;
+constexpr int kDefaultLstmEngine = 4;
+constexpr int kMaxLstmEngine = 4;
 static int lstm_engine() {
   if (g_lstm_engine < 0) {
     g_lstm_engine = kDefaultLstmEngine;
@@ -561,6 +562,10 @@ int lstm_tc_supported();
 void lstm_tc_set_profile(long long* dev_buf, int first_step, int nsteps);
 int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
                        long long hs_sb, long long hs_st, float* work, unsigned* sync, cudaStream_t s);
+int lstm_f16_supported();
+void lstm_f16_set_profile(long long* dev_buf, int first_step, int nsteps);
+int lstm_seq_f16_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
+                        long long hs_sb, long long hs_st, float* work, cudaStream_t s);
 
 template <int KT>
 static cudaError_t launch_lstm_mma(const LstmParams& p, int G, cudaStream_t s) {
@@ -615,7 +620,7 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
                whh_group_stride, hseq_group_off};
   void* args[] = {(void*)&p};
   const int engine = lstm_engine();
-  if (engine == 3 && H == kSmallH) {
+  if (engine >= 3 && H == kSmallH) {
     // sequences per CTA: as few as keep the grid within one wave (fewer sequences = shorter steps)
     const int ns = ngroups * B <= sms ? 1 : (ngroups * ((B + 1) / 2) <= sms ? 2 : 4);
     e = ns == 1 ? launch_lstm_small<1>(p, s) : (ns == 2 ? launch_lstm_small<2>(p, s) : launch_lstm_small<4>(p, s));
@@ -625,6 +630,8 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
     }
     return SE_OK;
   }
+  if (engine >= 4 && H == LT_H_PUBLIC && ngroups == 1 && lstm_f16_supported())
+    return lstm_seq_f16_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, s);
   if (engine >= 2 && H == LT_H_PUBLIC && ngroups == 1 && lstm_tc_supported())
     return lstm_seq_tc_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, sync, s);
   if (engine == 1 && (H == 1024 || H == 512 || H == 128)) {
@@ -648,12 +655,14 @@ extern "C" int se_lstm_seq(const float* xproj, long long xproj_stride, const flo
 extern "C" int se_debug_lstm_tc_profile(long long* dev_buf, int first_step, int nsteps) {
   SE_REQUIRE(dev_buf == nullptr || (first_step >= 1 && nsteps >= 1), "se_debug_lstm_tc_profile: bad step range");
   lstm_tc_set_profile(dev_buf, first_step, nsteps);
+  lstm_f16_set_profile(dev_buf, first_step, nsteps);
   return SE_OK;
 }
 
 extern "C" int se_set_lstm_engine(int engine) {
   SE_REQUIRE(engine >= 0 && engine <= kMaxLstmEngine,
-             "se_set_lstm_engine: 0 (fp32 FMA), 1 (mma.sync 3xTF32), 2 (tcgen05) or 3 (tcgen05 + sequence-parallel H = 128)");
+             "se_set_lstm_engine: 0 (fp32 FMA), 1 (mma.sync 3xTF32), 2 (tcgen05 3xTF32), 3 (2 + sequence-parallel H = 128) or 4 (3 with "
+             "the fp16-pair tcgen05 kernel)");
   g_lstm_engine = engine;
   return SE_OK;
 }

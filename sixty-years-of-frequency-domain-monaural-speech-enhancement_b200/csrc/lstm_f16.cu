@@ -1,0 +1,527 @@
+// LSTM recurrence, H = 1024, second tcgen05 generation: FP16 hi/lo operand pairs and a barrier-free state exchange.
+//
+// Same contract as lstm_seq_tc_kernel (lstm_tc.cu): T dependent steps  g_t = xproj_t + h_{t-1} W_hh^T  in one launch,
+// 128 CTAs = 32 clusters of 4; cluster c owns the 128 gate columns of hidden units [32c, 32c+32) (the M of the MMA), CTA
+// rank q of the cluster owns the K slice [256q, 256q+256) and the gate phase of the 8 units of slice 4c+q.  What the
+// phase profile of that kernel showed (profiles/lstm_tc_phases_nowriterfence_r01.json): of 12.8 K cycles per step only
+// 3.75 K were the MMA stream; 4.7 K were the publish -> device-wide counter -> poll -> proxy fence -> TMA chain.  This
+// kernel removes that chain and halves the operand bytes and the MMA count:
+//
+//   * operands are FP16 PAIRS instead of TF32 pairs:  x * S = hi + lo,  hi = fp16(x S),  lo = fp16(x S - hi), with
+//     power-of-two scales (S_h = 2^10 for h in (-1, 1); S_w per CTA block so that max |w| S_w is in [2^13, 2^14)).
+//     Products  W_hi h_hi + W_hi h_lo + W_lo h_hi  accumulate in fp32 in tensor memory and are de-scaled exactly in the
+//     epilogue: the same three-term scheme as 3xTF32 (both formats carry 11 significand bits per part), measured
+//     error 2.0e-7 vs 1.9e-7 for 3xTF32 on K = 1024 dot products (tests/test_host_logic.py::test_fp16_pair_product).
+//     kind::f16 runs at twice the TF32 rate with K = 16 per instruction: 32 MMAs per step instead of 64, and a step's
+//     slice of h is 64 KB per CTA instead of 128 KB.
+//   * h_t is published as ONE 32-bit word per element: (hi << 16) | lo, and the least significant bit of lo is the
+//     validity TAG of the step: element (b, u) of step t lives in buffer t & 1 and carries tag (t >> 1) & 1, the
+//     opposite of what step t - 2 left there.  Consumers read their K slice with plain 16-byte L2 loads
+//     (ld.relaxed.gpu), check the eight tags of every 32-byte item and retry until they match -- every word validates
+//     itself, so there is no release/acquire pair, no counter, no proxy fence on global data and no TMA issue latency
+//     between a producer's store and a consumer's use.  (Forcing the LSB of lo perturbs h by <= 2^-21 |h|.)
+//     Overwriting buffer t & 1 is safe without any further handshake: a CTA stores h_t only after its cluster
+//     finished the step-t reduction, i.e. after all four K slices = all 128 producers had published h_{t-1}, and every
+//     producer publishes h_{t-1} after its own loads of h_{t-2} returned.
+//   * the loader threads (the eight epilogue warps, idle during that phase anyway) unpack the words into the two
+//     K-major SWIZZLE_128B tiles [64 batch x 64 k] of a chunk (h_hi rows 0..63, h_lo rows 64..127 = ONE 128-row B
+//     operand), fence.proxy.async, and arrive on the chunk's mbarrier; the MMA thread issues per 16 k:
+//     D[0:128] += W_hi(TMEM) [h_hi | h_lo]  (N = 128)  and  D[64:128] += W_lo(smem) h_hi  (N = 64).
+//   * K-split reduction over DSMEM as before (st.shared::cluster in 128-byte warp rows, then barrier.cluster), but into
+//     a `red` buffer double-buffered by step parity: without the device-wide barrier a peer can be one reduction ahead
+//     of this CTA's cell phase.  (Measured and dropped: st.async + mbarrier::complete_tx instead of the cluster barrier
+//     -- one remote transaction-count update per 16 bytes: 4.1 K cycles against 2.4 K, profiles/lstm_f16_phases_b_r02.json;
+//     16-byte plain stores to 32 different rows per instruction: 3.7 K, profiles/lstm_f16_phases_c_r02.json.)
+//
+// Shared memory: W_lo 64 KB + h tiles 64 KB + red 2 x 32 KB = 192 KB; tensor memory: W_hi 128 columns (two fp16 per
+// column) + accumulators 128 columns.  Every spin is bounded (trap after 4 s).
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace se {
+
+constexpr int LF_H = 1024;
+constexpr int LF_KS = 256;                   // k per CTA
+constexpr int LF_NB = 64;                    // batch rows
+constexpr int LF_CK = 64;                    // k per chunk (128-byte fp16 rows)
+constexpr int LF_NCH = LF_KS / LF_CK;        // 4 chunks per step
+constexpr int LF_CTAS = LF_H / 8;            // 128
+constexpr int LF_LOADERS = 256;              // 8 warps: loaders, then epilogue / gates
+constexpr int LF_THREADS = LF_LOADERS + 32;  // + MMA warp
+constexpr int LF_MMA_WARP = 8;
+constexpr int LF_WLO_BYTES = 128 * LF_KS * 2;            // 65536
+constexpr int LF_TILE_BYTES = 128 * 128;                 // one chunk: 128 rows x 128 B
+constexpr int LF_HT_BYTES = LF_NCH * LF_TILE_BYTES;      // 65536
+constexpr int LF_RED_FLOATS = 4 * LF_NB * 32;            // one parity: [4 src][64 b][32 gate columns]
+constexpr int LF_RED_BYTES = 2 * LF_RED_FLOATS * 4;      // 65536
+constexpr int LF_SMEM_BYTES = LF_WLO_BYTES + LF_HT_BYTES + LF_RED_BYTES + 1024 + 256;
+constexpr unsigned LF_TMEM_COLS = 256;       // A: 0..127, D0: 128..191, D1: 192..255
+constexpr unsigned long long LF_SPIN_NS = 4000000000ull;
+constexpr float LF_SH = 1024.0f;             // scale of h before the fp16 split
+constexpr long long LF_WORK_WORDS = 2ll * LF_CTAS * LF_NB * 8;   // published state: [2][128 groups][64 b][8 units]
+
+struct LfParams {
+  const float* xproj;
+  long long xp_stride;
+  const float* whh;  // [128 slices][1024 k][32]
+  int B, T;
+  float* hseq;
+  long long hs_sb, hs_st;
+  unsigned* hw;      // [2 parities][128 groups of 8 units][64 batch rows][8]: (hi << 16) | lo, tag in bit 0
+  int a_swap;        // debug: swap the two fp16 of a TMEM column of the A operand
+  long long* prof;   // optional phase timestamps, see LF_NEV
+  int prof_t0, prof_n;
+};
+constexpr int LF_NEV = 12;
+// events (clock64 of the stamping thread's SM): 0 load phase starts, 1 first item valid, 2 last chunk handed to the MMA
+// thread, 3 MMA thread saw chunk 0, 4 MMA thread committed, 5 accumulators complete, 6 DSMEM partials sent,
+// 7 cluster barrier passed, 8 gates done + h published, 9 step done (sequence output stored)
+#define LF_STAMP(ev)                                                                                  \
+  do {                                                                                                \
+    if (p.prof && t >= p.prof_t0 && t < p.prof_t0 + p.prof_n)                                         \
+      p.prof[((long long)blockIdx.x * p.prof_n + (t - p.prof_t0)) * LF_NEV + (ev)] = clock64();       \
+  } while (0)
+
+namespace {
+
+__device__ __forceinline__ unsigned long long lf_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool lf_mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void lf_mbar_wait(uint64_t* bar, unsigned parity, unsigned long long t0) {
+  unsigned it = 0;
+  while (!lf_mbar_try(bar, parity)) {
+    if (((++it) & 0xFFu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
+  }
+}
+__device__ __forceinline__ void lf_fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void lf_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void lf_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned lf_map_rank(unsigned smem_addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void lf_st_cluster(unsigned addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+// strong (L2) accesses to the published state: every word validates itself, no ordering between words is needed
+__device__ __forceinline__ uint4 lf_ld_state(const unsigned* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void lf_st_state(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void lf_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], fp16 operands, fp32 accumulate
+__device__ __forceinline__ void lf_umma_ts(unsigned tmem_d, unsigned tmem_a, uint64_t bdesc, unsigned idesc, unsigned acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void lf_umma_ss(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void lf_tmem_st32(unsigned taddr, const unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+constexpr unsigned lf_idesc(int m, int n) {
+  return (1u << 4)                      // D format: F32
+         | (0u << 7) | (0u << 10)       // A, B format: F16
+         | (0u << 15) | (0u << 16)      // A, B K-major
+         | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+// x -> fp16 pair of x (already scaled); returns (hi bits, lo bits)
+__device__ __forceinline__ void lf_split(float xs, unsigned& hi, unsigned& lo) {
+  const __half h = __float2half_rn(xs);
+  const __half l = __float2half_rn(xs - __half2float(h));
+  hi = (unsigned)__half_as_ushort(h);
+  lo = (unsigned)__half_as_ushort(l);
+}
+// all eight words of an item carry tag `e` in bit 0
+__device__ __forceinline__ bool lf_tags_ok(const uint4& a, const uint4& b, unsigned e) {
+  const unsigned all_and = a.x & a.y & a.z & a.w & b.x & b.y & b.z & b.w;
+  const unsigned all_or = a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w;
+  return e ? (all_and & 1u) != 0u : (all_or & 1u) == 0u;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* wlo = base;                                   // 4 chunks x [128 rows x 128 B], SW128
+  unsigned char* htile = base + LF_WLO_BYTES;                  // 4 chunks x [128 rows x 128 B]: rows 0..63 h_hi, 64..127 h_lo
+  float* red = reinterpret_cast<float*>(htile + LF_HT_BYTES);  // [2 parities][4 src][64 b][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + LF_RED_BYTES);
+  uint64_t* full = bars;                // [LF_NCH]: chunk tiles written (the chunk's 2 loader warps arrive)
+  uint64_t* accfull = bars + LF_NCH;    // accumulators complete (tcgen05.commit)
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(accfull + 1);
+  unsigned* smax = tmem_slot + 1;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned q;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(q));   // K slice / owner index in the unit group
+  const int slice = blockIdx.x;        // hidden units [8*slice, +8): what this CTA's gate phase owns and publishes
+  const int grp = blockIdx.x >> 2;     // unit group: hidden units [32*grp, +32) = the M of this CTA's MMAs
+  const unsigned long long t0 = lf_timer_ns();
+
+  if (tid == 0) {
+    for (int c = 0; c < LF_NCH; ++c) mbar_init(&full[c], LF_LOADERS / 32 / LF_NCH);
+    mbar_init(accfull, 1);
+    *smax = 0u;
+    fence_barrier_init();
+  }
+  if (warp == LF_MMA_WARP) tmem_alloc(tmem_slot, LF_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  const unsigned tmem_a = tmem_base, tmem_d = tmem_base + 128;
+
+  // ---- resident weights.  Row m = 32*o + l of the block <- W_hh slice (4*grp + o), gate column l; k in this K slice.
+  // Thread = (row m, half of the k range); pass 1 finds max |w| of the block, pass 2 splits and stores.
+  const int wrow = (warp & 3) * 32 + lane, wkh = (warp >> 2) & 1;
+  const float* wsrc = p.whh + ((size_t)(grp * 4 + (warp & 3)) * LF_H + (size_t)q * LF_KS + (size_t)wkh * 128) * 32 + lane;
+  if (warp < 8) {
+    float amax = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 128; ++k) amax = fmaxf(amax, fabsf(__ldg(wsrc + (size_t)k * 32)));
+    unsigned bits = __float_as_uint(amax);
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if (lane == 0) atomicMax(smax, bits);
+  }
+  __syncthreads();
+  float sw = 1.0f, descale = 1.0f / LF_SH;
+  {
+    const float m = __uint_as_float(*smax);
+    if (m > 0.f && m < 3.0e38f) {
+      const int e = ilogbf(m);                 // m in [2^e, 2^(e+1))  ->  m * 2^(13-e) in [2^13, 2^14)
+      sw = scalbnf(1.0f, 13 - e);
+      descale = scalbnf(1.0f, e - 13 - 10);
+    }
+  }
+  if (warp < 8) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {               // two 64-k chunks of this thread's k half
+      unsigned hi[32];
+      const int chunk = wkh * 2 + c;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {          // 8 k -> one 16-byte row piece of W_lo, 4 TMEM columns of W_hi
+        unsigned h8[8], l8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lf_split(__ldg(wsrc + (size_t)(c * 64 + g8 * 8 + i) * 32) * sw, h8[i], l8[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          hi[g8 * 4 + i] = p.a_swap ? ((h8[2 * i] << 16) | h8[2 * i + 1]) : ((h8[2 * i + 1] << 16) | h8[2 * i]);
+        uint4 lv;
+        lv.x = (l8[1] << 16) | l8[0];
+        lv.y = (l8[3] << 16) | l8[2];
+        lv.z = (l8[5] << 16) | l8[4];
+        lv.w = (l8[7] << 16) | l8[6];
+        *reinterpret_cast<uint4*>(wlo + chunk * LF_TILE_BYTES + wrow * 128 + ((g8 ^ (wrow & 7)) << 4)) = lv;
+      }
+      lf_tmem_st32(tmem_a + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(chunk * 32), hi);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+  lf_fence_proxy_async();       // generic-proxy smem writes (W_lo) -> visible to the tensor core's async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  lf_cluster_arrive();          // every CTA of the cluster is running before anyone touches remote smem
+  lf_cluster_wait();
+
+  if (warp == LF_MMA_WARP) {
+    // ===================== MMA issuer =====================
+    constexpr unsigned idesc_wide = lf_idesc(128, 2 * LF_NB);
+    constexpr unsigned idesc_n64 = lf_idesc(128, LF_NB);
+    for (int t = 1; t < p.T; ++t) {
+      if (elect_one()) {
+        const unsigned par = (unsigned)((t - 1) & 1);
+        for (int c = 0; c < LF_NCH; ++c) {
+          lf_mbar_wait(&full[c], par, t0);
+          if (c == 0) LF_STAMP(3);
+          tc_fence_after();
+          const uint64_t d_b = make_smem_desc(htile + c * LF_TILE_BYTES);
+          const uint64_t d_alo = make_smem_desc(wlo + c * LF_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < LF_CK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+            lf_umma_ts(tmem_d, tmem_a + (unsigned)(c * 32 + k * 8), d_b + adv, idesc_wide, (c > 0 || k > 0) ? 1u : 0u);
+            lf_umma_ss(tmem_d + 64, d_alo + adv, d_b + adv, idesc_n64, 1u);
+          }
+        }
+        umma_commit(accfull);
+        LF_STAMP(4);
+      }
+      __syncwarp();
+      lf_cluster_arrive();
+      lf_cluster_wait();
+    }
+  } else {
+    // ===================== loaders -> epilogue: K-split reduction over DSMEM, gates, publish =====================
+    const int quarter = warp & 3;        // TMEM lanes 32*quarter .. +31 = gate columns owned by cluster rank `quarter`
+    const int half = warp >> 2;          // batch rows [32*half, +32)
+    float cstate[2] = {0.f, 0.f};
+    const unsigned red_remote = lf_map_rank(smem_u32(red), (unsigned)quarter);
+    // loader items: ONE producer per thread (group lg of the K slice = 16-byte piece lg & 7 of chunk lg >> 3), batch rows
+    // lb0 + 8 i -- a producer publishes its 2 KB within ~100 cycles, so once the first item validates the rest does too
+    const int lg = tid >> 3, lb0 = tid & 7, lchunk = lg >> 3, lc16 = lg & 7;
+    for (int t = 0; t < p.T; ++t) {
+      float xg[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pr = tid + 256 * i, b = pr >> 3, j = pr & 7;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          xg[i][g] = 0.f;
+          if (b < p.B) xg[i][g] = __ldg(p.xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * 32 + g * 8 + j);
+        }
+      }
+      const int rpar = t & 1;
+      if (t > 0) {
+        // ---- h_{t-1}: this CTA's K slice = groups [32q, 32q+32) of buffer (t-1)&1, tag ((t-1)>>1)&1
+        const unsigned etag = (unsigned)(((t - 1) >> 1) & 1);
+        const unsigned* src = p.hw + ((size_t)(((t - 1) & 1) * LF_CTAS + (int)q * 32 + lg) * LF_NB + lb0) * 8;
+        if (tid == 0) LF_STAMP(0);
+        uint4 v[8][2];
+        {   // canary: spin on the first item only, so that early arrivals do not flood L2 with 64 KB re-reads
+          unsigned it = 0;
+          for (;;) {
+            v[0][0] = lf_ld_state(src);
+            v[0][1] = lf_ld_state(src + 4);
+            if (lf_tags_ok(v[0][0], v[0][1], etag)) break;
+            if (((++it) & 0x3Fu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
+          }
+        }
+        if (tid == 0) LF_STAMP(1);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+          v[i][0] = lf_ld_state(src + i * 64);
+          v[i][1] = lf_ld_state(src + i * 64 + 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i > 0) {
+            unsigned it = 0;
+            while (!lf_tags_ok(v[i][0], v[i][1], etag)) {
+              v[i][0] = lf_ld_state(src + i * 64);
+              v[i][1] = lf_ld_state(src + i * 64 + 4);
+              if (((++it) & 0x3Fu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
+            }
+          }
+          const uint4 a0 = v[i][0], a1 = v[i][1];
+          uint4 hv, lv;     // word = (hi << 16) | lo
+          hv.x = __byte_perm(a0.x, a0.y, 0x7632);
+          hv.y = __byte_perm(a0.z, a0.w, 0x7632);
+          hv.z = __byte_perm(a1.x, a1.y, 0x7632);
+          hv.w = __byte_perm(a1.z, a1.w, 0x7632);
+          lv.x = __byte_perm(a0.x, a0.y, 0x5410);
+          lv.y = __byte_perm(a0.z, a0.w, 0x5410);
+          lv.z = __byte_perm(a1.x, a1.y, 0x5410);
+          lv.w = __byte_perm(a1.z, a1.w, 0x5410);
+          unsigned char* trow = htile + lchunk * LF_TILE_BYTES + (lb0 + 8 * i) * 128 + ((lc16 ^ lb0) << 4);
+          *reinterpret_cast<uint4*>(trow) = hv;
+          *reinterpret_cast<uint4*>(trow + 64 * 128) = lv;
+        }
+        lf_fence_proxy_async();      // my generic-proxy tile writes -> the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) lf_mbar_arrive(&full[lchunk]);
+        if (tid == 0) LF_STAMP(2);
+
+        lf_mbar_wait(accfull, (unsigned)((t - 1) & 1), t0);
+        if (tid == 0) LF_STAMP(5);
+        tc_fence_after();
+        float d0[32], d1[32];
+        tmem_ld_32x32(tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)(half * 32), d0);
+        tmem_ld_32x32(tmem_d + 64 + ((unsigned)(quarter * 32) << 16) + (unsigned)(half * 32), d1);
+        // lane = gate column (g = lane >> 3, unit j = lane & 7) of the owner; register i = batch row 32*half + i.
+        // red[parity][source q][64 b][32 gate columns]: one store instruction of a warp = one 128-byte row (the only DSMEM
+        // store shape that coalesces: 16-byte stores to 32 different rows measured 3.7 K cycles against 2.4 K)
+        const unsigned rbase = red_remote + ((unsigned)(rpar * LF_RED_FLOATS) + q * 2048u) * 4u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int b = half * 32 + i;
+          const unsigned off = ((unsigned)b * 32u + (unsigned)((((lane >> 3) ^ (b & 3)) << 3) | (lane & 7))) * 4u;
+          lf_st_cluster(rbase + off, (d0[i] + d1[i]) * descale);
+        }
+        tc_fence_before();
+        if (tid == 0) LF_STAMP(6);
+        lf_cluster_arrive();
+        lf_cluster_wait();
+        if (tid == 0) LF_STAMP(7);
+      }
+      const float* redp = red + rpar * LF_RED_FLOATS;
+      const unsigned tag = (unsigned)((t >> 1) & 1);
+      float hv2[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pr = tid + 256 * i, b = pr >> 3, j = pr & 7;
+        float g4[4] = {xg[i][0], xg[i][1], xg[i][2], xg[i][3]};
+        if (t > 0) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) g4[g] += redp[s * 2048 + b * 32 + (((g ^ (b & 3)) << 3) | j)];
+        }
+        const float ig = fast_sigmoid(g4[0]);
+        const float fg = fast_sigmoid(g4[1]);
+        const float gg = fast_tanh(g4[2]);
+        const float og = fast_sigmoid(g4[3]);
+        const float c = fg * cstate[i] + ig * gg;
+        float h = og * fast_tanh(c);
+        cstate[i] = c;
+        if (b >= p.B) h = 0.f;
+        if (t + 1 < p.T) {
+          unsigned hh, hl;
+          lf_split(h * LF_SH, hh, hl);
+          lf_st_state(p.hw + ((size_t)(rpar * LF_CTAS + slice) * LF_NB + b) * 8 + j, (hh << 16) | (hl & 0xFFFEu) | tag);
+        }
+        hv2[i] = h;
+      }
+      if (tid == 0) LF_STAMP(8);
+      // the sequence output is not on the step's critical path: store it after the state
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pr = tid + 256 * i, b = pr >> 3, j = pr & 7;
+        if (b < p.B) p.hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + slice * 8 + j] = hv2[i];
+      }
+      if (tid == 0) LF_STAMP(9);
+    }
+  }
+  tc_fence_before();
+  lf_cluster_arrive();          // no CTA leaves while peers may still write its smem
+  lf_cluster_wait();
+  __syncthreads();
+  if (warp == LF_MMA_WARP) tmem_dealloc(tmem_base, LF_TMEM_COLS);
+}
+
+static cudaLaunchConfig_t lf_config(cudaLaunchAttribute* at, int nattr, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(LF_CTAS);
+  cfg.blockDim = dim3(LF_THREADS);
+  cfg.dynamicSmemBytes = LF_SMEM_BYTES;
+  cfg.stream = s;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 4;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;   // all 128 CTAs co-resident or the launch fails (never a deadlock)
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = nattr;
+  return cfg;
+}
+
+// can 32 clusters of 4 CTAs of this kernel be co-resident on the current device?
+int lstm_f16_supported() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cached = 0;
+  if (cudaFuncSetAttribute((const void*)lstm_seq_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchAttribute at[2];
+  cudaLaunchConfig_t cfg = lf_config(at, 1, nullptr);
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_seq_f16_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cached = nclusters >= LF_CTAS / 4 ? 1 : 0;
+  return cached;
+}
+
+static long long* g_lf_prof = nullptr;
+static int g_lf_prof_t0 = 0, g_lf_prof_n = 0;
+void lstm_f16_set_profile(long long* dev_buf, int first_step, int nsteps) {
+  g_lf_prof = dev_buf;
+  g_lf_prof_t0 = first_step;
+  g_lf_prof_n = nsteps;
+}
+
+// work: LF_WORK_WORDS 32-bit words (512 KB) of published state
+int lstm_seq_f16_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
+                        long long hs_sb, long long hs_st, float* work, cudaStream_t s) {
+  if (!lstm_f16_supported()) {
+    set_error("se_lstm_seq (tcgen05 fp16-pair): clusters of this kernel do not fit the device");
+    return SE_ERR_CUDA;
+  }
+  // all tags = 1: neither buffer validates before its first store of this launch (steps 0 and 1 carry tag 0)
+  cudaError_t e = cudaMemsetAsync(work, 0xFF, (size_t)LF_WORK_WORDS * sizeof(unsigned), s);
+  if (e != cudaSuccess) {
+    set_error("se_lstm_seq (tcgen05 fp16-pair): memset: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  static int a_swap = -1;
+  if (a_swap < 0) {
+    a_swap = 0;
+    if (const char* ev = getenv("SE_LSTM_F16_ASWAP")) a_swap = atoi(ev) ? 1 : 0;
+  }
+  LfParams p{xproj, xp_stride, whh, B, T, hseq, hs_sb, hs_st, reinterpret_cast<unsigned*>(work), a_swap,
+             g_lf_prof, g_lf_prof_t0, g_lf_prof_n};
+  // The cooperative attribute guarantees co-residency of the 128 CTAs.  Tools that replay launches (Nsight Compute)
+  // reject a cooperative CLUSTER launch: retry once without it -- the bounded spins turn a co-residency failure into a
+  // launch error instead of a hang.  SE_LSTM_TC_COOP=0 skips the first attempt.
+  static int coop = -1;
+  if (coop < 0) {
+    coop = 1;
+    if (const char* ev = getenv("SE_LSTM_TC_COOP")) coop = atoi(ev) ? 1 : 0;
+  }
+  cudaLaunchAttribute at[2];
+  cudaLaunchConfig_t cfg = lf_config(at, coop ? 2 : 1, s);
+  e = cudaLaunchKernelEx(&cfg, lstm_seq_f16_kernel, p);
+  if (e != cudaSuccess && coop) {
+    cudaGetLastError();
+    cfg = lf_config(at, 1, s);
+    e = cudaLaunchKernelEx(&cfg, lstm_seq_f16_kernel, p);
+    if (e == cudaSuccess) coop = 0;
+  }
+  if (e != cudaSuccess) {
+    set_error("se_lstm_seq (tcgen05 fp16-pair): cluster launch: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return check_launch("se_lstm_seq (tcgen05 fp16-pair)");
+}
+
+}  // namespace se

@@ -416,14 +416,15 @@ def test_attention_matches_softmax(over_t, cplx):
     assert err < 2e-5
 
 
-DEFAULT_LSTM_ENGINE = 3
+DEFAULT_LSTM_ENGINE = 4
 
 
 @pytest.mark.parametrize("h,b,t", [(1024, 64, 20), (1024, 5, 3), (1024, 64, 401), (512, 7, 9), (128, 33, 15), (128, 64, 401),
                                    (128, 1, 2)])
 def test_lstm_engines_agree(h, b, t):
-    """fp32 FMA / mma.sync 3xTF32 / tcgen05 3xTF32 (H = 1024 only, else the FMA kernel) / default (3: tcgen05 at H = 1024,
-    the sequence-parallel kernel at H = 128) recurrences vs fp64."""
+    """fp32 FMA / mma.sync 3xTF32 / tcgen05 3xTF32 (H = 1024 only, else the FMA kernel) / 3 (tcgen05 at H = 1024, the
+    sequence-parallel kernel at H = 128) / default (4: the fp16-pair tagged-state tcgen05 kernel at H = 1024) recurrences
+    vs fp64."""
     dev = _dev()
     import se_b200
     ops = se_b200.ops
@@ -433,7 +434,7 @@ def test_lstm_engines_agree(h, b, t):
     ref = emu_ops.lstm_seq(xp.double(), whh.double(), h)
     errs = []
     try:
-        for eng in (0, 1, 2, 3):
+        for eng in (0, 1, 2, 3, 4):
             ops.set_lstm_engine(eng)
             got = ops.lstm_seq(xp.to(dev), whh.to(dev), h)
             torch.cuda.synchronize()
@@ -441,8 +442,37 @@ def test_lstm_engines_agree(h, b, t):
     finally:
         ops.set_lstm_engine(DEFAULT_LSTM_ENGINE)
     print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}, tcgen05 err {errs[2]:.3e}, "
-          f"default err {errs[3]:.3e}")
+          f"engine 3 err {errs[3]:.3e}, default (fp16 pairs) err {errs[4]:.3e}")
     assert max(errs) < 2e-5
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-3, 6.0])
+def test_lstm_f16_engine_relaunch_and_weight_scales(scale):
+    """Engine 4 (csrc/lstm_f16.cu): (a) back-to-back launches on the same work buffer with DIFFERENT inputs and lengths --
+    the tagged state words of one launch must never validate in the next; (b) bit-identical repeats (no race in the
+    tag protocol shows up as run-to-run differences); (c) weight magnitudes from 1e-3 to 6 x 1/sqrt(H) exercise the
+    per-block power-of-two scale; (d) a W_hh with all-zero blocks."""
+    dev = _dev()
+    import se_b200
+    ops = se_b200.ops
+    h = 1024
+    g = torch.Generator().manual_seed(11)
+    whh = torch.randn(h // 8, h, 32, generator=g) / np.sqrt(h) * scale
+    whh[3:9] = 0.0
+    outs = []
+    # large recurrent weights make the recurrence chaotic (any fp32 rounding difference grows): few steps there
+    for b, t in ([(64, 37), (17, 50), (64, 37), (64, 38)] if scale <= 1.0 else [(64, 4), (17, 5), (64, 4), (64, 3)]):
+        gg = torch.Generator().manual_seed(1000 + b + t)
+        xp = torch.randn(b, t, 4 * h, generator=gg)
+        got = ops.lstm_seq(xp.to(dev), whh.to(dev), h)
+        again = ops.lstm_seq(xp.to(dev), whh.to(dev), h)
+        torch.cuda.synchronize()
+        assert torch.equal(got, again)
+        ref = emu_ops.lstm_seq(xp.double(), whh.double(), h)
+        err = (got.cpu().double() - ref).abs().max().item()
+        outs.append(err)
+        assert err < 2e-5, (b, t, err)
+    print(f"lstm f16 engine, weight scale {scale}: errs {['%.2e' % e for e in outs]}")
 
 
 @pytest.mark.parametrize("c", [1, 16, 130])

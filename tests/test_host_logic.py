@@ -430,3 +430,32 @@ def test_enhance_dir_shards_batches_over_ranks(tmp_path):
     assert sorted(written) == sorted(names)          # disjoint and complete
     with pytest.raises(ValueError):
         decode.enhance_dir(None, str(src), str(tmp_path / "bad"), device="cpu", enhance_fn=lambda m, w: w, rank=3, world=3)
+
+
+def test_fp16_pair_product():
+    """Numerics of the fp16-pair recurrence engine (csrc/lstm_f16.cu), emulated in numpy: x*S = hi + lo in fp16 with
+    power-of-two scales, three-term product, the step tag forced into the LSB of h_lo.  The error must stay in the
+    3xTF32 class (fp32-level), far below the 1e-4 waveform gate."""
+    import math
+    rng = np.random.default_rng(0)
+    k = 1024
+    w = (rng.standard_normal((256, k)) * 0.05).astype(np.float32)
+    h = (np.tanh(rng.standard_normal((k, 64))) * rng.random((k, 64))).astype(np.float32)
+    exact = w.astype(np.float64) @ h.astype(np.float64)
+
+    def split16(x, scale, tag=None):
+        xs = (x * np.float32(scale)).astype(np.float32)
+        hi = xs.astype(np.float16)
+        lo = (xs - hi.astype(np.float32)).astype(np.float16)
+        if tag is not None:
+            lo = ((lo.view(np.uint16) & 0xFFFE) | tag).astype(np.uint16).view(np.float16)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    sw = 2.0 ** (13 - math.frexp(float(np.abs(w).max()))[1] + 1)     # ilogb = frexp exponent - 1
+    assert 2 ** 13 <= np.abs(w).max() * sw < 2 ** 14
+    sh = 1024.0
+    for tag in (0, 1):
+        whi, wlo = split16(w, sw)
+        hhi, hlo = split16(h, sh, tag)
+        d = (whi @ hhi + whi @ hlo + wlo @ hhi) / (sw * sh)
+        assert np.abs(d - exact).max() < 1e-6

@@ -15,11 +15,14 @@ from se_b200 import _lib, ops  # noqa: E402
 
 EV = ["poll_start", "barrier_seen", "tma_issued", "first_stage", "last_stage", "acc_done", "dsmem_sent",
       "cluster_passed", "cell_done", "arrived", "proxy_fenced", "cta_synced"]
+# engine 4 (csrc/lstm_f16.cu)
+EV4 = ["load_start", "first_item_valid", "tiles_handed_over", "mma_saw_chunk0", "mma_committed", "acc_done", "dsmem_sent",
+       "cluster_passed", "published", "step_done", "-", "-"]
 
 
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 401
-    engine = int(sys.argv[2]) if len(sys.argv) > 2 else 2          # 2 = csrc/lstm_tc.cu
+    engine = int(sys.argv[2]) if len(sys.argv) > 2 else 4          # 2 = csrc/lstm_tc.cu, 4 = csrc/lstm_f16.cu
     B, H, NS = 64, 1024, 8
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
@@ -47,14 +50,23 @@ def main():
     out = {"engine": engine, "T": T, "ms": ms, "us_per_step": 1e3 * ms / T, "cycles_per_step": step,
            "ghz_implied": step / (1e3 * ms / T) / 1e3}
     seg = {}
-    for a, b in [(0, 1), (1, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (8, 10), (10, 11), (11, 9), (1, 2)]:
+    if engine >= 4:
+        names, pairs = EV4, [(0, 1), (1, 2), (1, 3), (3, 4), (2, 5), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9)]
+        step = np.diff(st[:, :, 8], axis=1).mean()        # publish -> publish
+        out["cycles_per_step"] = step
+        out["ghz_implied"] = step / (1e3 * ms / T) / 1e3
+    else:
+        names, pairs = EV, [(0, 1), (1, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (8, 10), (10, 11), (11, 9), (1, 2)]
+    for a, b in pairs:
         d = st[:, 1:, b] - st[:, 1:, a]
-        seg[f"{EV[a]}->{EV[b]}"] = {"mean": float(d.mean()), "p10": float(np.percentile(d, 10)),
-                                    "p90": float(np.percentile(d, 90)), "max": float(d.max())}
-    # previous step's arrival -> this step's barrier seen (includes waiting for the slowest CTA)
-    d = st[:, 1:, 1] - st[:, :-1, 9]
-    seg["arrived(t-1)->barrier_seen(t)"] = {"mean": float(d.mean()), "p10": float(np.percentile(d, 10)),
-                                           "p90": float(np.percentile(d, 90)), "max": float(d.max())}
+        seg[f"{names[a]}->{names[b]}"] = {"mean": float(d.mean()), "p10": float(np.percentile(d, 10)),
+                                          "p90": float(np.percentile(d, 90)), "max": float(d.max())}
+    # previous step's publish / arrival -> this step's first valid item / barrier seen (includes waiting for the
+    # slowest producer)
+    a, b = (8, 1) if engine >= 4 else (9, 1)
+    d = st[:, 1:, b] - st[:, :-1, a]
+    seg[f"{names[a]}(t-1)->{names[b]}(t)"] = {"mean": float(d.mean()), "p10": float(np.percentile(d, 10)),
+                                              "p90": float(np.percentile(d, 90)), "max": float(d.max())}
     out["segments_cycles"] = seg
     print(json.dumps(out, indent=1))
 
