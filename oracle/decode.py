@@ -79,9 +79,11 @@ def enhance_fullsubnet(sd, wav, p=0.5):
     return y.astype(np.float32), taps
 
 
-def enhance_dccrn(sd, wav, p=0.5):
+def enhance_dccrn(sd, wav, p=0.5, crop_first=True):
     """``DCCRN/dccrn_decode.py:30-60`` (torch dialect; zero-pad to a whole number of hops, compress,
-    DCCRN-E forward, decompress (rule (ii)), torch.istft without ``length`` then ``[:wav_len]``)."""
+    DCCRN-E forward, decompress (rule (ii)), torch.istft without ``length`` then ``[:wav_len]``).
+    ``p=1.0, crop_first=False`` is ``DCCRN_SNR/dccrn_decode_snr.py:30-64`` (same loop, exponent 1., and the
+    network of DCCRN_SNR/DCCRN.py whose decoder crops ``[..., :-1]``, :159)."""
     from . import nets as _n
     n_fft, win, hop = dsp.GEOMETRIES["dccrn"]
     x, c = dsp.rms_scale(wav)                                               # :31-32
@@ -93,7 +95,7 @@ def enhance_dccrn(sd, wav, p=0.5):
     mag, ph = np.abs(spec) ** p, np.angle(spec)                             # :44
     feat = np.stack((mag * np.cos(ph), mag * np.sin(ph))).astype(np.float32)     # :46 [2,F,T]
     with torch.no_grad():
-        est = _n.dccrn_forward(sd, torch.from_numpy(feat)[None]).squeeze(0).numpy()   # :48
+        est = _n.dccrn_forward(sd, torch.from_numpy(feat)[None], crop_first=crop_first).squeeze(0).numpy()   # :48
     emag = np.sqrt(est[0] ** 2 + est[1] ** 2) ** (1.0 / p)                  # :49,52
     eph = np.arctan2(est[1], est[0])                                        # :50
     y = dsp.istft((emag * np.cos(eph) + 1j * emag * np.sin(eph)).astype(np.complex64), n_fft, win, hop, None)  # :56

@@ -8,10 +8,11 @@ import shutil
 
 from . import ref_shims
 
-# The CRN (70 MB) and LSTM (87 MB) checkpoints are only fetched with --all: every gpurun push re-sends
-# checkpoints/_ref/ and their parity runs are on record in profiles/gpu_tests_ckpt_crn_lstm_r01.log.
-BIG = [("CRN", "wsj0_si84_300h_crn_noncprs_model.pth"), ("LSTM", "vb_lstm_noncprs_model.pth")]
-WANTED = [("FullSubNet", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
+# Every checkpoint a parity test or bench.py loads.  (The CRN and LSTM files are 70 / 87 MB; bench.py refuses to
+# run without the CRN one.)
+WANTED = [("CRN", "wsj0_si84_300h_crn_noncprs_model.pth"), ("LSTM", "vb_lstm_noncprs_model.pth"),
+          ("DCCRN_SNR", "wsj0_si84_300h_dccrn_snr_model.pth"),
+          ("FullSubNet", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
           ("DCCRN", "wsj0_si84_300h_dccrn_cprs_model.pth"),
           ("Uformer", "wsj0_si84_300h_uformer_noncprs_model.pth"),
           ("GCRN", "vb_gcrn_cprs_model.pth"), ("DPCRN", "vb_dpcrn_noncprs_model.pth"),
@@ -24,8 +25,7 @@ DEST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 
 def main():
     os.makedirs(DEST, exist_ok=True)
-    import sys
-    for mdir, name in WANTED + (BIG if "--all" in sys.argv else []):
+    for mdir, name in WANTED:
         src = ref_shims.checkpoint_path(mdir, name)
         dst = os.path.join(DEST, f"{mdir}__{name}")
         if not os.path.exists(dst):

@@ -39,14 +39,14 @@ FSN_ARGS = dict(sb_num_neighbors=15, fb_num_neighbors=0, num_freqs=257, look_ahe
                 num_groups_in_drop_band=2)     # FullSubNet/fullsubnet_sa_decode.py:11-24
 
 FSN_CASES = [
-    ("fullsubnet_synth", None, 8192, (4, 5)),
-    ("fullsubnet_ckpt", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth", 16000, (4, 5)),
+    ("fullsubnet_synth", None, 8192, (4, 5), None),
+    ("fullsubnet_ckpt", "wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth", 16000, (4, 5), 41),
 ]
 
 
 def make_fullsubnet():
     mod = ref_shims.import_reference("FullSubNet", "fullsubnet_net_sa.model")
-    for name, ckpt, nsamp, clip_ids in FSN_CASES:
+    for name, ckpt, nsamp, clip_ids, long_id in FSN_CASES:
         net = mod.Model(**FSN_ARGS).eval()
         if ckpt is None:
             sd = synth.synthetic_state_dict(templates.fullsubnet_template(), seed=0)
@@ -55,6 +55,16 @@ def make_fullsubnet():
         net.load_state_dict(sd)
         rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp)}
         worst = 0.0
+        if long_id is not None:
+            # BASELINE configs[3] clip length (10 s, T = 626 + 2 look-ahead frames): see make_dccrn
+            wav = synth.noisy_clip(long_id, 160000)
+            _, taps = decode.enhance_fullsubnet(sd, wav.astype(np.float64))
+            with torch.no_grad():
+                mask_ref = net(torch.from_numpy(taps["mag"])[None, None]).squeeze(0).numpy()
+            rec["long_clip_id"] = np.array(long_id)
+            rec["long_ynorm"] = taps["y_norm"]
+            rec["long_ref_vs_oracle"] = np.array(float(np.abs(mask_ref - taps["mask"]).max()))
+            print(f"{name}: 10 s clip, ref_vs_oracle max-abs {float(rec['long_ref_vs_oracle']):.3e}")
         for j, cid in enumerate(clip_ids):
             wav = synth.noisy_clip(cid, nsamp)
             y, taps = decode.enhance_fullsubnet(sd, wav.astype(np.float64))
@@ -74,26 +84,42 @@ def make_fullsubnet():
               f"{float(np.sqrt(np.mean(rec['ynorm0'] ** 2))):.4f}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+# (fixture, reference dir, module, checkpoint, samples, clips, p, crop_first, clip id of the config-length record or None)
 DCCRN_CASES = [
-    ("dccrn_synth", None, 8000, (6, 7)),
-    ("dccrn_ckpt", "wsj0_si84_300h_dccrn_cprs_model.pth", 16000, (6, 7)),
+    ("dccrn_synth", "DCCRN", "DCCRN_cprs", None, 8000, (6, 7), 0.5, True, None),
+    ("dccrn_ckpt", "DCCRN", "DCCRN_cprs", "wsj0_si84_300h_dccrn_cprs_model.pth", 16000, (6, 7), 0.5, True, 40),
+    # DCCRN_SNR/DCCRN.py (decoder keeps [..., :-1]) with the checkpoint dccrn_decode_snr.py:13 loads
+    ("dccrn_snr_ckpt", "DCCRN_SNR", "DCCRN", "wsj0_si84_300h_dccrn_snr_model.pth", 16000, (8, 9), 1.0, False, None),
 ]
 
 
 def make_dccrn():
-    mod = ref_shims.import_reference("DCCRN", "DCCRN_cprs")    # runs with the restated complexnn injected
-    for name, ckpt, nsamp, clip_ids in DCCRN_CASES:
-        net = mod.DCCRN(rnn_units=256, masking_mode='E', use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256]).eval()
+    for name, mdir, module, ckpt, nsamp, clip_ids, p, crop_first, long_id in DCCRN_CASES:
+        mod = ref_shims.import_reference(mdir, module)    # runs with the restated complexnn injected
+        kw = dict(masking_mode='E') if mdir == "DCCRN" else {}
+        net = mod.DCCRN(rnn_units=256, use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256], **kw).eval()
         if ckpt is None:
             sd = synth.synthetic_state_dict(templates.dccrn_template(), seed=0)
         else:
-            sd = torch.load(ref_shims.checkpoint_path("DCCRN", ckpt), map_location="cpu")
+            sd = torch.load(ref_shims.checkpoint_path(mdir, ckpt), map_location="cpu")
         net.load_state_dict(sd)
-        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp)}
+        rec = {"digest": np.array(sd_digest(sd)), "clip_ids": np.array(clip_ids), "nsamp": np.array(nsamp),
+               "p": np.array(p), "crop_first": np.array(crop_first)}
         worst = 0.0
+        if long_id is not None:
+            # BASELINE configs[2] clip length (4 s, T = 501): the oracle is pinned to the reference module at this
+            # length too, and its decode of ONE clip is committed (the GPU test decodes a second one live)
+            wav = synth.noisy_clip(long_id, 64000)
+            _, taps = decode.enhance_dccrn(sd, wav.astype(np.float64), p=p, crop_first=crop_first)
+            with torch.no_grad():
+                est_ref = net(torch.from_numpy(taps["feat"])[None]).squeeze(0).numpy()
+            rec["long_clip_id"] = np.array(long_id)
+            rec["long_ynorm"] = taps["y_norm"]
+            rec["long_ref_vs_oracle"] = np.array(float(np.abs(est_ref - taps["est"]).max()))
+            print(f"{name}: 4 s clip, ref_vs_oracle max-abs {float(rec['long_ref_vs_oracle']):.3e}")
         for j, cid in enumerate(clip_ids):
             wav = synth.noisy_clip(cid, nsamp)
-            y, taps = decode.enhance_dccrn(sd, wav.astype(np.float64))
+            y, taps = decode.enhance_dccrn(sd, wav.astype(np.float64), p=p, crop_first=crop_first)
             with torch.no_grad():
                 est_ref = net(torch.from_numpy(taps["feat"])[None]).squeeze(0).numpy()
             worst = max(worst, float(np.abs(est_ref - taps["est"]).max()))

@@ -1,6 +1,8 @@
 // C-ABI plumbing shared by every entry point: per-thread error string, launch accounting,
 // device check.  No reference counterpart (the reference has no native boundary).
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -26,6 +28,32 @@ int check_launch(const char* what) {
     return SE_ERR_CUDA;
   }
   return SE_OK;
+}
+
+// A launch-replaying tool (Nsight Compute, compute-sanitizer) is attached to this process.  Such tools reject
+// cooperative CLUSTER launches (ncu: "LaunchFailed", and it then tears the application down before any retry), so the
+// persistent recurrence kernels drop the cooperative attribute when this returns true and rely on their occupancy
+// check + bounded spins instead.  CUDA tools inject through CUDA_INJECTION64_PATH; the maps scan covers older ones.
+bool profiler_attached() {
+  static int cached = -1;
+  if (cached >= 0) return cached != 0;
+  cached = 0;
+  if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_PORT_BASE"))
+    cached = 1;
+  if (!cached) {
+    if (FILE* f = fopen("/proc/self/maps", "r")) {
+      char line[1024];
+      while (fgets(line, sizeof(line), f)) {
+        if (strstr(line, "nsight-compute") || strstr(line, "libcuda-injection") || strstr(line, "libsanitizer-collection") ||
+            strstr(line, "libInterceptorInjectionTarget")) {
+          cached = 1;
+          break;
+        }
+      }
+      fclose(f);
+    }
+  }
+  return cached != 0;
 }
 
 }  // namespace se

@@ -11,6 +11,7 @@ namespace se {
 // ---- error plumbing (C-ABI returns int status; message kept per thread) -------------
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> SE_ERR_CUDA
+bool profiler_attached();             // Nsight Compute / compute-sanitizer injected into this process (api.cu)
 
 #define SE_REQUIRE(cond, ...)                    \
   do {                                           \

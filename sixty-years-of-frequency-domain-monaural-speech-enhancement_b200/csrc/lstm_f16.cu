@@ -506,6 +506,7 @@ int lstm_seq_f16_launch(const float* xproj, long long xp_stride, const float* wh
   static int coop = -1;
   if (coop < 0) {
     coop = 1;
+    if (profiler_attached()) coop = 0;
     if (const char* ev = getenv("SE_LSTM_TC_COOP")) coop = atoi(ev) ? 1 : 0;
   }
   cudaLaunchAttribute at[2];

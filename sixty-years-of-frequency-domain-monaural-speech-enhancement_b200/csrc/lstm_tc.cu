@@ -522,6 +522,7 @@ int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh
   static int coop = -1;
   if (coop < 0) {
     coop = 1;
+    if (profiler_attached()) coop = 0;
     if (const char* e = getenv("SE_LSTM_TC_COOP")) coop = atoi(e) ? 1 : 0;
   }
   cudaLaunchAttribute at[2];
@@ -534,6 +535,14 @@ int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh
   cfg.attrs = at;
   cfg.numAttrs = coop ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, lt_kernel(mc), map_hi, map_lo, p);
+  if (e != cudaSuccess && coop) {
+    // tools that replay launches (Nsight Compute) reject a cooperative cluster launch: retry without the attribute;
+    // the bounded spins turn a co-residency failure into a launch error instead of a hang
+    cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, lt_kernel(mc), map_hi, map_lo, p);
+    if (e == cudaSuccess) coop = 0;
+  }
   if (e != cudaSuccess) {
     set_error("se_lstm_seq (tcgen05, multicast %d): cooperative cluster launch: %s", mc, cudaGetErrorString(e));
     return SE_ERR_CUDA;

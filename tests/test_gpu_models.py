@@ -153,16 +153,33 @@ def test_fullsubnet_matches_golden(name, ckpt):
     rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
     y1 = se_b200.decode.enhance_fullsubnet(model, wav[1:2], p=0.5)
     binv = (y[1:2] - y1).abs().max().item()
-    print(f"{name}: mask max-abs {e_net:.3e} (|mask| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
-          f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
+    msg = (f"{name}: mask max-abs {e_net:.3e} (|mask| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
+           f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
+    if "long_ynorm" in g:     # fullsubnet_10s: fullsubnet_sa_decode.py:44-78 at the config-4 clip length (T = 626 + 2)
+        ids = [int(g["long_clip_id"]), int(g["long_clip_id"]) + 1]
+        w10 = np.stack([synth.noisy_clip(i, 160000) for i in ids])
+        t10 = {}
+        y10 = se_b200.decode.enhance_fullsubnet(model, torch.from_numpy(w10).to(dev), p=0.5, taps=t10)
+        yn10 = y10.cpu().numpy() * t10["c"].cpu().numpy()[:, None]
+        _, to = odecode.enhance_fullsubnet(sd, w10[1].astype(np.float64), p=0.5)
+        for r10, ref10 in ((yn10[0], g["long_ynorm"]), (yn10[1], to["y_norm"])):
+            e10 = np.sqrt(np.mean((r10 - ref10) ** 2))
+            rel10 = e10 / np.sqrt(np.mean(ref10 ** 2))
+            msg += f"; fullsubnet_10s RMS err {e10:.3e} rel {rel10:.3e}"
+            assert e10 <= RMS_GATE and rel10 <= 2e-3
+    print(msg)
     assert rms.max() <= RMS_GATE and rel.max() <= 2e-3
     assert binv < 1e-5
 
 
-@pytest.mark.parametrize("name,ckpt", [("dccrn_synth", None), ("dccrn_ckpt", "DCCRN__wsj0_si84_300h_dccrn_cprs_model.pth")])
+@pytest.mark.parametrize("name,ckpt", [("dccrn_synth", None), ("dccrn_ckpt", "DCCRN__wsj0_si84_300h_dccrn_cprs_model.pth"),
+                                       ("dccrn_snr_ckpt", "DCCRN_SNR__wsj0_si84_300h_dccrn_snr_model.pth")])
 def test_dccrn_matches_golden(name, ckpt):
     """Config 3 model (DCCRN-E, complex LSTM): network output vs the reference DCCRN class (run with
-    the restated complexnn) and decoded waveform vs the restated dccrn_decode.py."""
+    the restated complexnn) and decoded waveform vs the restated dccrn_decode.py.  ``dccrn_snr_ckpt`` (SURVEY 8(f)
+    rank 4): the UNMODIFIED DCCRN_SNR/DCCRN.py module (decoder keeps ``[..., :-1]``, :159) with the checkpoint
+    dccrn_decode_snr.py:13 loads, decoded with that script's exponent 1.  ``dccrn_ckpt`` also carries ONE clip at the
+    BASELINE configs[2] length (4 s, T = 501) and a second 4 s clip is decoded by the oracle on the spot."""
     dev = _dev()
     import se_b200
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -173,7 +190,10 @@ def test_dccrn_matches_golden(name, ckpt):
         if not os.path.exists(path):
             pytest.skip("checkpoint copy not present")
         sd = torch.load(path, map_location="cpu")
-    model = se_b200.DCCRN(rnn_units=256, masking_mode='E', use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256])
+    p = float(g["p"]) if "p" in g else 0.5
+    crop_first = bool(g["crop_first"]) if "crop_first" in g else True
+    model = se_b200.DCCRN(rnn_units=256, masking_mode='E', use_clstm=True, kernel_num=[32, 64, 128, 256, 256, 256],
+                          crop_first=crop_first)
     model.load_state_dict(sd)
     model.eval().cuda()
     k = len(g["clip_ids"])
@@ -183,16 +203,29 @@ def test_dccrn_matches_golden(name, ckpt):
     e_net = np.abs(est - ref).max()
     wav = torch.from_numpy(np.stack([g[f"wav{j}"] for j in range(k)])).to(dev)
     taps = {}
-    y = se_b200.decode.enhance_dccrn(model, wav, p=0.5, taps=taps)
+    y = se_b200.decode.enhance_dccrn(model, wav, p=p, taps=taps)
     c = taps["c"].cpu().numpy()
     yn = y.cpu().numpy() * c[:, None]
     refn = np.stack([g[f"ynorm{j}"] for j in range(k)])
     rms = np.sqrt(np.mean((yn - refn) ** 2, axis=1))
     rel = rms / np.sqrt(np.mean(refn ** 2, axis=1))
-    y1 = se_b200.decode.enhance_dccrn(model, wav[1:2], p=0.5)
+    y1 = se_b200.decode.enhance_dccrn(model, wav[1:2], p=p)
     binv = (y[1:2] - y1).abs().max().item()
-    print(f"{name}: net max-abs {e_net:.3e} (|est| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
-          f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
+    msg = (f"{name}: net max-abs {e_net:.3e} (|est| max {np.abs(ref).max():.2f}); wav RMS err {rms.max():.3e} "
+           f"rel {rel.max():.3e}; batch-vs-single {binv:.2e}")
+    if "long_ynorm" in g:                 # dccrn_4s: DCCRN/dccrn_decode.py:30-60 at the config-3 clip length
+        ids = [int(g["long_clip_id"]), int(g["long_clip_id"]) + 1]
+        w4 = np.stack([synth.noisy_clip(i, 64000) for i in ids])
+        t4 = {}
+        y4 = se_b200.decode.enhance_dccrn(model, torch.from_numpy(w4).to(dev), p=p, taps=t4)
+        yn4 = y4.cpu().numpy() * t4["c"].cpu().numpy()[:, None]
+        _, to = odecode.enhance_dccrn(sd, w4[1].astype(np.float64), p=p, crop_first=crop_first)
+        for r4, ref4 in ((yn4[0], g["long_ynorm"]), (yn4[1], to["y_norm"])):
+            e4 = np.sqrt(np.mean((r4 - ref4) ** 2))
+            rel4 = e4 / np.sqrt(np.mean(ref4 ** 2))
+            msg += f"; dccrn_4s RMS err {e4:.3e} rel {rel4:.3e}"
+            assert e4 <= RMS_GATE and rel4 <= 2e-3
+    print(msg)
     assert rms.max() <= RMS_GATE and rel.max() <= 2e-3
     assert binv < 1e-5
 

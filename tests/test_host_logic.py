@@ -121,7 +121,17 @@ def _gloo_worker(rank, world, port, batch, q):
     full = torch.arange(batch * 5, dtype=torch.float32).view(batch, 5)
     s, e = shard.shard_range(batch, rank, world)
     out = shard.gather_waveforms(full[s:e].clone() * 1.0, batch)
-    q.put((rank, bool(torch.equal(out, full))))
+    ok = bool(torch.equal(out, full))
+    if batch % world == 0:
+        # pipelined gather to rank 0: three batches in flight, results in submission order
+        pipe = shard.GatherPipeline(batch, dst=0, depth=2)
+        got = [pipe.submit(full[s:e] * float(k + 1)) for k in range(3)]
+        pipe.drain()
+        if rank == 0:
+            ok = ok and all(torch.equal(torch.cat(g, 0), full * float(k + 1)) for k, g in enumerate(got))
+        else:
+            ok = ok and all(g is None for g in got)
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
@@ -395,6 +405,8 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "checkpoints", "_ref", "CRN__wsj0_si84_300h_crn_noncprs_model.pth")):
+        pytest.skip("bench.py refuses to run without the shipped CRN checkpoint (python -m oracle.fetch_checkpoints)")
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]

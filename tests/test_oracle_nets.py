@@ -21,6 +21,7 @@ CASES = {
                         "FullSubNet__wsj0_si84_300h_fullsubnet_cprs_model_512_256.pth"),
     "dccrn_synth": (templates.dccrn_template, decode.enhance_dccrn, None),
     "dccrn_ckpt": (templates.dccrn_template, decode.enhance_dccrn, "DCCRN__wsj0_si84_300h_dccrn_cprs_model.pth"),
+    "dccrn_snr_ckpt": (templates.dccrn_template, decode.enhance_dccrn, "DCCRN_SNR__wsj0_si84_300h_dccrn_snr_model.pth"),
     "gcrn_synth": (templates.gcrn_template, decode.enhance_gcrn, None),
     "gcrn_ckpt": (templates.gcrn_template, decode.enhance_gcrn, "GCRN__vb_gcrn_cprs_model.pth"),
     "dpcrn_synth": (templates.dpcrn_template, decode.enhance_dpcrn, None),
@@ -53,12 +54,25 @@ def test_oracle_reproduces_golden(name):
         wav = synth.noisy_clip(int(g["clip_ids"][j]), int(g["nsamp"]))
         assert np.array_equal(wav, g[f"wav{j}"]), "synthetic clip generator is not reproducible"
         kw = {"p": float(g["p"])} if "p" in g.files else {}
+        if "crop_first" in g.files:
+            kw["crop_first"] = bool(g["crop_first"])
         y, taps = enh(sd, wav.astype(np.float64), **kw)
         key = "mask" if "mask" in taps else "est"
         # Uformer fixtures come from the unmodified module (different op order than the restatement)
         tol = 5e-4 if name.startswith("uformer") else 2e-5
         assert np.abs(taps[key] - g[f"{key}{j}"]).max() < tol
         assert np.sqrt(np.mean((taps["y_norm"] - g[f"ynorm{j}"]) ** 2)) < 2e-6
+
+
+@pytest.mark.parametrize("name,nsamp", [("dccrn_ckpt", 64000), ("fullsubnet_ckpt", 160000)])
+def test_oracle_reproduces_config_length_record(name, nsamp):
+    """The clip at BASELINE configs[2] / configs[3] length (4 s DCCRN, 10 s FullSubNet) stored by make_golden.py, where
+    the reference module and the oracle agreed to ``long_ref_vs_oracle``."""
+    g, sd, enh = load_case(name)
+    assert float(g["long_ref_vs_oracle"]) < 1e-4
+    wav = synth.noisy_clip(int(g["long_clip_id"]), nsamp)
+    _, taps = enh(sd, wav.astype(np.float64))
+    assert np.sqrt(np.mean((taps["y_norm"] - g["long_ynorm"]) ** 2)) < 2e-6
 
 
 def test_fused_lstm_equals_textbook_recurrence():

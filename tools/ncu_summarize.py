@@ -73,6 +73,19 @@ def full(src, dst, cmd):
         if rec.get("gpu__time_duration.sum", float("nan")) == rec.get("gpu__time_duration.sum"):
             out.append(rec)
     json.dump({"source": cmd, "kernels": out}, open(dst, "w"), indent=1)
+    # profiles/roofline_traffic.json: DRAM bytes per launch of every kernel captured so far, newest capture wins --
+    # the ONE place bench.py reads `roofline.traffic` from (so the number can never come from a stale kernel's capture)
+    import os
+    tpath = os.path.join(os.path.dirname(os.path.abspath(dst)), "roofline_traffic.json")
+    table = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for k in out:
+        if "dram__bytes_read.sum" in k and "dram__bytes_write.sum" in k:
+            tot = (k["dram__bytes_read.sum"] * unit_scale.get(k.get("dram__bytes_read.sum__unit", "byte"), 1.0) +
+                   k["dram__bytes_write.sum"] * unit_scale.get(k.get("dram__bytes_write.sum__unit", "byte"), 1.0))
+            name = re.sub(r"<.*", "", k["kernel"]).strip()
+            table[name] = {"dram_bytes_per_launch": tot, "source": os.path.basename(dst)}
+    json.dump(table, open(tpath, "w"), indent=1, sort_keys=True)
     for k in out:
         print(f"{k['kernel'][:40]:40s} {k.get('gpu__time_duration.sum', 0):8.3f} {k.get('gpu__time_duration.sum__unit', 'ms')}  DRAM r+w "
               f"{k.get('dram__bytes_read.sum', 0) + k.get('dram__bytes_write.sum', 0):8.1f} "
