@@ -62,6 +62,11 @@ unsigned long long se_launch_count(void);
  * ------------------------------------------------------------------------------------- */
 int se_rms_scale(const float* wav, long long wav_stride, int B, int N, int reciprocal, float* c, float* inv_c,
                  se_stream_t stream);
+/* Tail-padded batches of clips of DIFFERENT lengths (the scripts decode any directory one file
+ * at a time, CRN/crn_decode_vb.py:31-33): `lengths` (device int32 [B], or NULL = every clip has N samples) gives the
+ * sample count of each row; the statistics of clip b run over its own lengths[b] samples. */
+int se_rms_scale_len(const float* wav, long long wav_stride, int B, int N, const int* lengths, int reciprocal, float* c,
+                     float* inv_c, se_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a3+a4  Fused reflect-pad + framing + periodic-Hann + one-sided FFT + feature split.
@@ -82,6 +87,12 @@ int se_rms_scale(const float* wav, long long wav_stride, int B, int N, int recip
 int se_stft(const float* wav, long long wav_stride, int B, int N, const float* scale, int n_fft, int win, int hop,
             int T, float* mag, long long msb, long long mst, long long msf, float* re, float* im, long long sb,
             long long st, long long sf, float p_mag, float p_ri, se_stream_t stream);
+/* se_stft on a tail-padded batch: clip b is reflect-padded around ITS last sample lengths[b] - 1 and owns the frames
+ * t < 1 + lengths[b] / hop, bit-identical to the frames of that clip transformed alone; its later frames (up to
+ * T = 1 + N / hop of the padded row) are written as zeros.  lengths[b] >= n_fft.  NULL = se_stft. */
+int se_stft_len(const float* wav, long long wav_stride, int B, int N, const int* lengths, const float* scale, int n_fft,
+                int win, int hop, int T, float* mag, long long msb, long long mst, long long msf, float* re, float* im,
+                long long sb, long long st, long long sf, float p_mag, float p_ri, se_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a7+a8+a9  Fused recombination prologue + irFFT + window + overlap-add + envelope
@@ -109,6 +120,13 @@ int se_istft(int mode, const float* a_re, const float* a_im, long long a_sb, lon
              const float* b_re, const float* b_im, long long b_sb, long long b_st, long long b_sf, float inv_p,
              float p_x, int B, int T, int n_fft, int win, int hop, const float* out_scale, float* out,
              long long out_stride, int L, se_stream_t stream);
+/* se_istft on a tail-padded batch: only the frames t < 1 + lengths[b] / hop of clip b are overlap-added (and enter its
+ * window envelope), samples n >= lengths[b] are written as 0 -- librosa.istft(..., length=len(x)) per file
+ * (CRN/crn_decode_vb.py:50-51).  NULL = se_istft. */
+int se_istft_len(int mode, const float* a_re, const float* a_im, long long a_sb, long long a_st, long long a_sf,
+                 const float* b_re, const float* b_im, long long b_sb, long long b_st, long long b_sf, float inv_p,
+                 float p_x, int B, int T, int n_fft, int win, int hop, const float* out_scale, float* out,
+                 long long out_stride, int L, const int* lengths, se_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a6 building block: causal Conv2d / ConvTranspose2d / Linear as one implicit GEMM.

@@ -48,7 +48,11 @@ PROTOTYPES = {
     "se_device_check": (_I, []),
     "se_launch_count": (C.c_ulonglong, []),
     "se_rms_scale": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P]),
+    "se_rms_scale_len": (_I, [_P, _LL, _I, _I, _P, _I, _P, _P, _P]),
     "se_stft": (_I, [_P, _LL, _I, _I, _P, _I, _I, _I, _I, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _P]),
+    "se_stft_len": (_I, [_P, _LL, _I, _I, _P, _P, _I, _I, _I, _I, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _P]),
+    "se_istft_len": (_I, [_I, _P, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _I, _I, _I, _I, _I, _P, _P, _LL,
+                          _I, _P, _P]),
     "se_istft": (_I, [_I, _P, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _F, _F, _I, _I, _I, _I, _I, _P, _P, _LL,
                       _I, _P]),
     "se_conv_gemm": (_I, [C.POINTER(ConvDesc), _P]),

@@ -19,9 +19,10 @@ constexpr int kDspThreads = 256;
 // a1: RMS scale
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) rms_scale_kernel(const float* __restrict__ wav, long long stride, int N,
-                                                       int reciprocal, float* __restrict__ c,
-                                                       float* __restrict__ inv_c) {
+                                                       const int* __restrict__ lengths, int reciprocal,
+                                                       float* __restrict__ c, float* __restrict__ inv_c) {
   const float* x = wav + (long long)blockIdx.x * stride;
+  if (lengths) N = max(1, min(N, __ldg(lengths + blockIdx.x)));   // tail-padded batch: this clip's own sample count
   double acc = 0.0;
   const bool vec = ((((uintptr_t)x) & 15) == 0);
   if (vec) {
@@ -68,6 +69,7 @@ struct StftParams {
   long long sb, st, sf;
   float p_mag, p_ri;
   const float2* twiddles;   // [32][2R + 5], see WarpFFT<R>::fill_table
+  const int* lengths;       // optional [B]: samples of every clip of a tail-padded batch (N = row length = maximum)
 };
 
 __device__ __forceinline__ float pow_pos(float m, float p) {
@@ -104,9 +106,13 @@ __global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
   const float* x = p.wav + (long long)b * p.wav_stride;
   const int start = t0 * p.hop - NFFT / 2;
   const int tile_len = (nf - 1) * p.hop + NFFT;
+  // per-clip length of a tail-padded batch: the clip ends (and is reflected) at ITS last sample and has 1 + Nb / hop
+  // frames, exactly as when it is decoded alone (crn_decode_vb.py:31-37 loops one file at a time); later frames are 0
+  const int Nb = p.lengths ? max(NFFT, min(p.N, __ldg(p.lengths + b))) : p.N;
+  const int Tb = 1 + Nb / p.hop;
 
   // --- stage the audio span of this frame tile --------------------------------------------
-  const bool interior = (start >= 0) && (start + tile_len <= p.N) && ((((uintptr_t)(x + start)) & 15) == 0) &&
+  const bool interior = (start >= 0) && (start + tile_len <= Nb) && ((((uintptr_t)(x + start)) & 15) == 0) &&
                         ((tile_len & 3) == 0);
   if (interior) {
     // one bulk (TMA-engine) copy, completion on an mbarrier
@@ -124,8 +130,8 @@ __global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
     for (int i = tid; i < tile_len; i += kDspThreads) {
       int j = start + i;
       if (j < 0) j = -j;
-      if (j >= p.N) j = 2 * (p.N - 1) - j;
-      j = max(0, min(j, p.N - 1));
+      if (j >= Nb) j = 2 * (Nb - 1) - j;
+      j = max(0, min(j, Nb - 1));
       tile[i] = __ldg(x + j);
     }
   }
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(kDspThreads) stft_kernel(StftParams p) {
       const int k2 = k / R, k1 = k - k2 * R;
       X = spec[(i * R + k1) * 33 + k2];
     }
+    if (t0 + i >= Tb) X = make_float2(0.0f, 0.0f);     // frame past this clip's end (tail-padded batch)
     const float m = sqrtf(X.x * X.x + X.y * X.y);
     if (p.mag)
       p.mag[(long long)b * p.msb + (long long)(t0 + i) * p.mst + (long long)k * p.msf] = pow_pos(m, p.p_mag);
@@ -215,6 +222,7 @@ struct IstftParams {
   int L;
   int nf_max;
   const float2* twiddles;   // [32][2R + 5], see WarpFFT<R>::fill_table
+  const int* lengths;       // optional [B]: clip b has 1 + lengths[b] / hop frames and min(L, lengths[b]) output samples
 };
 
 template <int R>
@@ -234,7 +242,11 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
   const int s1 = s0 + OB * p.hop;
   const int q = s0 - NFFT;
   const int t_lo = q < 0 ? 0 : q / p.hop + 1;
-  const int t_hi = min(p.T - 1, (s1 - 1) / p.hop);
+  // tail-padded batch: only this clip's own frames overlap-add (and enter the window envelope), output past its end is 0
+  const int Nb = p.lengths ? max(NFFT, __ldg(p.lengths + b)) : 0x7fffffff;
+  const int Tb = p.lengths ? min(p.T, 1 + Nb / p.hop) : p.T;
+  const int Lb = min(p.L, Nb);
+  const int t_hi = min(Tb - 1, (s1 - 1) / p.hop);
   const int nf = t_hi - t_lo + 1;
 
   {
@@ -333,6 +345,10 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
   for (int j = tid; j < span; j += kDspThreads) {
     const int n = n0 + j;
     if (n >= p.L) break;
+    if (n >= Lb) {
+      out[n] = 0.0f;
+      continue;
+    }
     const int s = s0 + j;
     const int first = s - NFFT + 1;
     int ta = first <= 0 ? 0 : (first + p.hop - 1) / p.hop;
@@ -438,11 +454,16 @@ static int dsp_smem_stft(int R, int hop) {
 
 using namespace se;
 
+extern "C" int se_rms_scale_len(const float* wav, long long wav_stride, int B, int N, const int* lengths, int reciprocal,
+                                float* c, float* inv_c, se_stream_t stream) {
+  SE_REQUIRE(wav && c && inv_c && B > 0 && N > 0, "se_rms_scale: bad arguments (B=%d N=%d)", B, N);
+  rms_scale_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wav, wav_stride, N, lengths, reciprocal, c, inv_c);
+  return check_launch("se_rms_scale");
+}
+
 extern "C" int se_rms_scale(const float* wav, long long wav_stride, int B, int N, int reciprocal, float* c,
                             float* inv_c, se_stream_t stream) {
-  SE_REQUIRE(wav && c && inv_c && B > 0 && N > 0, "se_rms_scale: bad arguments (B=%d N=%d)", B, N);
-  rms_scale_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wav, wav_stride, N, reciprocal, c, inv_c);
-  return check_launch("se_rms_scale");
+  return se_rms_scale_len(wav, wav_stride, B, N, nullptr, reciprocal, c, inv_c, stream);
 }
 
 static int geom_ok(const char* who, int n_fft, int win, int hop) {
@@ -461,12 +482,21 @@ extern "C" int se_stft(const float* wav, long long wav_stride, int B, int N, con
                        int hop, int T, float* mag, long long msb, long long mst, long long msf, float* re,
                        float* im, long long sb, long long st, long long sf, float p_mag, float p_ri,
                        se_stream_t stream) {
+  return se_stft_len(wav, wav_stride, B, N, nullptr, scale, n_fft, win, hop, T, mag, msb, mst, msf, re, im, sb, st, sf, p_mag,
+                     p_ri, stream);
+}
+
+extern "C" int se_stft_len(const float* wav, long long wav_stride, int B, int N, const int* lengths, const float* scale,
+                           int n_fft, int win, int hop, int T, float* mag, long long msb, long long mst, long long msf,
+                           float* re, float* im, long long sb, long long st, long long sf, float p_mag, float p_ri,
+                           se_stream_t stream) {
   if (!geom_ok("se_stft", n_fft, win, hop)) return SE_ERR_SHAPE;
   SE_REQUIRE(wav && B > 0 && N >= n_fft, "se_stft: need N >= n_fft (N=%d)", N);
   SE_REQUIRE(T == 1 + N / hop, "se_stft: T=%d but 1+N/hop=%d", T, 1 + N / hop);
   SE_REQUIRE((re == nullptr) == (im == nullptr), "se_stft: re and im must both be given or both NULL");
   SE_REQUIRE(mag || re, "se_stft: no output plane");
-  StftParams p{wav, wav_stride, B, N, scale, win, hop, T, mag, re, im, msb, mst, msf, sb, st, sf, p_mag, p_ri, nullptr};
+  StftParams p{wav, wav_stride, B, N, scale, win, hop, T, mag, re, im, msb, mst, msf, sb, st, sf, p_mag, p_ri, nullptr,
+               lengths};
   p.twiddles = dsp_twiddles(n_fft / 64, (cudaStream_t)stream);
   SE_REQUIRE(p.twiddles != nullptr, "se_stft: twiddle table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   dim3 grid(ceil_div(T, kFramesPerCta), B);
@@ -491,13 +521,22 @@ extern "C" int se_istft(int mode, const float* a_re, const float* a_im, long lon
                         long long a_sf, const float* b_re, const float* b_im, long long b_sb, long long b_st,
                         long long b_sf, float inv_p, float p_x, int B, int T, int n_fft, int win, int hop,
                         const float* out_scale, float* out, long long out_stride, int L, se_stream_t stream) {
+  return se_istft_len(mode, a_re, a_im, a_sb, a_st, a_sf, b_re, b_im, b_sb, b_st, b_sf, inv_p, p_x, B, T, n_fft, win, hop,
+                      out_scale, out, out_stride, L, nullptr, stream);
+}
+
+extern "C" int se_istft_len(int mode, const float* a_re, const float* a_im, long long a_sb, long long a_st,
+                            long long a_sf, const float* b_re, const float* b_im, long long b_sb, long long b_st,
+                            long long b_sf, float inv_p, float p_x, int B, int T, int n_fft, int win, int hop,
+                            const float* out_scale, float* out, long long out_stride, int L, const int* lengths,
+                            se_stream_t stream) {
   if (!geom_ok("se_istft", n_fft, win, hop)) return SE_ERR_SHAPE;
   SE_REQUIRE(mode >= SE_ISTFT_SPEC && mode <= SE_ISTFT_CMASK, "se_istft: bad mode %d", mode);
   SE_REQUIRE(a_re && out && B > 0 && T > 0 && L > 0, "se_istft: bad arguments");
   SE_REQUIRE(mode == SE_ISTFT_MAG_PHASE || a_im, "se_istft: a_im required for mode %d", mode);
   SE_REQUIRE(mode < SE_ISTFT_MAG_PHASE || (b_re && b_im), "se_istft: noisy spectrum (b_re,b_im) required");
   IstftParams p{mode, a_re, a_im, a_sb, a_st, a_sf, b_re, b_im, b_sb, b_st, b_sf, inv_p, p_x, B, T, win, hop,
-                out_scale, out, out_stride, L, 0, nullptr};
+                out_scale, out, out_stride, L, 0, nullptr, lengths};
   p.twiddles = dsp_twiddles(n_fft / 64, (cudaStream_t)stream);
   SE_REQUIRE(p.twiddles != nullptr, "se_istft: twiddle table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   p.nf_max = kHopBlocksPerCta + ceil_div(n_fft, hop) + 1;

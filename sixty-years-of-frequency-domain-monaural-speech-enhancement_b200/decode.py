@@ -20,10 +20,27 @@ from ._lib import ISTFT_CMASK, ISTFT_MAG_PHASE, ISTFT_RI_DECOMP
 GEOM_320 = (320, 320, 160)   # LSTM/config.py:4-6, CRN/config.py:4-6
 
 
+def _lengths_arg(lengths, wav):
+    """Per-clip sample counts of a tail-padded batch -> CUDA int32 [B] (None stays None: every clip fills its row).
+
+    Length-aware batching is offered for the families whose network is CAUSAL along time
+    (LSTM, CRN, GCRN, DPCRN: uni-directional LSTMs over T, convolutions padded on the past side only, eval BatchNorm,
+    per-frame LayerNorm): frame t of the output depends on frames <= t only, so the frames of a clip inside a tail-padded
+    batch equal the frames of that clip decoded alone, and only the DSP ends need the clip's own length."""
+    if lengths is None:
+        return None
+    lengths = torch.as_tensor(lengths, dtype=torch.int32).to(wav.device).contiguous()
+    if lengths.numel() != wav.shape[0]:
+        raise ValueError("one length per clip")
+    return lengths
+
+
 @torch.no_grad()
-def enhance_mag_mapping(model, wav, p=1.0, geom=GEOM_320, taps=None):
+def enhance_mag_mapping(model, wav, p=1.0, geom=GEOM_320, taps=None, lengths=None):
     """Magnitude-mapping models (LSTM, CRN): backend rule (i) of SURVEY.md section 8(a).
-    wav [B,N] float32 CUDA -> enhanced [B,N] float32 CUDA.  CRN/crn_decode.py:38-57."""
+    wav [B,N] float32 CUDA -> enhanced [B,N] float32 CUDA.  CRN/crn_decode.py:38-57.
+    ``lengths`` (optional, [B]): clip b has lengths[b] <= N samples and is zero beyond (tail-padded batch); its output
+    equals its own decode (samples past its end are 0)."""
     if not wav.is_cuda:
         raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
     n_fft, win, hop = geom
@@ -31,29 +48,30 @@ def enhance_mag_mapping(model, wav, p=1.0, geom=GEOM_320, taps=None):
     b, n = wav.shape
     t = 1 + n // hop
     f = n_fft // 2 + 1
-    c, inv_c = ops.rms_scale(wav)
+    lengths = _lengths_arg(lengths, wav)
+    c, inv_c = ops.rms_scale(wav, lengths=lengths)
     mag = torch.empty(b, t, f, device=wav.device, dtype=torch.float32)
     spec = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)   # noisy spectrum (phase)
-    ops.stft(wav, c, n_fft, win, hop, mag=mag, re=spec[..., 0], im=spec[..., 1], p_mag=p)
+    ops.stft(wav, c, n_fft, win, hop, mag=mag, re=spec[..., 0], im=spec[..., 1], p_mag=p, lengths=lengths)
     est = model(mag)
     out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
     ops.istft(ISTFT_MAG_PHASE, est, None, spec[..., 0], spec[..., 1], n_fft, win, hop, out, n, out_scale=inv_c,
-              inv_p=1.0 / p)
+              inv_p=1.0 / p, lengths=lengths)
     if taps is not None:
         taps.update(c=c, mag=mag, spec=spec, est=est)
     return out
 
 
-def enhance_crn(model, wav, p=1.0, taps=None):
-    return enhance_mag_mapping(model, wav, p=p, taps=taps)
+def enhance_crn(model, wav, p=1.0, taps=None, lengths=None):
+    return enhance_mag_mapping(model, wav, p=p, taps=taps, lengths=lengths)
 
 
-def enhance_lstm(model, wav, p=1.0, taps=None):
-    return enhance_mag_mapping(model, wav, p=p, taps=taps)
+def enhance_lstm(model, wav, p=1.0, taps=None, lengths=None):
+    return enhance_mag_mapping(model, wav, p=p, taps=taps, lengths=lengths)
 
 
 @torch.no_grad()
-def enhance_gcrn(model, wav, p=0.5, taps=None):
+def enhance_gcrn(model, wav, p=0.5, taps=None, lengths=None):
     """GCRN/gcrn_decode_vb.py:34-58 (p = 0.5; gcrn_decode.py uses p = 1): compressed real/imag spectrum in,
     real/imag out, |.|^(1/p) with the ESTIMATED phase (backend rule (ii)), iSTFT(length=N), / c.
     wav [B,N] float32 CUDA -> [B,N]."""
@@ -63,19 +81,21 @@ def enhance_gcrn(model, wav, p=0.5, taps=None):
     wav = wav.contiguous().float()
     b, n = wav.shape
     t, f = 1 + n // hop, n_fft // 2 + 1
-    c, inv_c = ops.rms_scale(wav)
+    lengths = _lengths_arg(lengths, wav)
+    c, inv_c = ops.rms_scale(wav, lengths=lengths)
     x = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)        # compressed RI, channels-last
-    ops.stft(wav, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p)
+    ops.stft(wav, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p, lengths=lengths)
     re, im = model.forward_nhwc(x, taps)
     out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
-    ops.istft(ISTFT_RI_DECOMP, re, im, None, None, n_fft, win, hop, out, n, out_scale=inv_c, inv_p=1.0 / p)
+    ops.istft(ISTFT_RI_DECOMP, re, im, None, None, n_fft, win, hop, out, n, out_scale=inv_c, inv_p=1.0 / p,
+              lengths=lengths)
     if taps is not None:
         taps.update(c=c, x=x, est=(re, im))
     return out
 
 
 @torch.no_grad()
-def enhance_dpcrn(model, wav, p=1.0, taps=None):
+def enhance_dpcrn(model, wav, p=1.0, taps=None, lengths=None):
     """DPCRN/dpcrn_decode_vb.py:33-60 (p = 1.0; drcrn_decode.py uses p = 0.5): compressed real/imag spectrum in,
     complex-ratio-masked spectrum out of forward, |.|^(1/p) with its own phase (backend rule (ii)),
     iSTFT(length=N), / c.  wav [B,N] float32 CUDA -> [B,N]."""
@@ -85,13 +105,14 @@ def enhance_dpcrn(model, wav, p=1.0, taps=None):
     wav = wav.contiguous().float()
     b, n = wav.shape
     t, f = 1 + n // hop, n_fft // 2 + 1
-    c, inv_c = ops.rms_scale(wav)
+    lengths = _lengths_arg(lengths, wav)
+    c, inv_c = ops.rms_scale(wav, lengths=lengths)
     x = torch.empty(b, t, f, 2, device=wav.device, dtype=torch.float32)        # compressed RI, channels-last
-    ops.stft(wav, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p)
+    ops.stft(wav, c, n_fft, win, hop, re=x[..., 0], im=x[..., 1], p_ri=p, lengths=lengths)
     est = model.forward_nhwc(x, taps)
     out = torch.empty(b, n, device=wav.device, dtype=torch.float32)
     ops.istft(ISTFT_RI_DECOMP, est[..., 0], est[..., 1], None, None, n_fft, win, hop, out, n, out_scale=inv_c,
-              inv_p=1.0 / p)
+              inv_p=1.0 / p, lengths=lengths)
     if taps is not None:
         taps.update(c=c, x=x, est=est)
     return out
@@ -306,28 +327,31 @@ def enhancer_for(model):
 
 def enhance_host_stream(model, host_batches, enhance_fn=None, depth=2, device=None, **kw):
     """Pipelined host -> host decode: for every pinned host batch [B,N] float32 of ``host_batches`` yields the enhanced
-    batch as a pinned host tensor (valid until ``depth`` more batches have been drawn).  The upload of batch i+1 and
-    the download of batch i-1 run on their own CUDA streams while batch i is in the decode loop, so the PCIe copies the
-    reference pays serially per utterance (CRN/crn_decode.py:46-47,53) disappear behind the compute.  All batches must
-    have the same shape (one ring of ``depth`` device / host buffers)."""
+    batch as a pinned host tensor that stays valid until ``depth`` MORE batches have been drawn from the generator
+    (ring of ``2 * depth`` pinned output buffers: the download of batch i + depth is queued before batch i + 1 is yielded,
+    so a ring of ``depth`` would be overwritten one draw later).  The upload of batch i+1 and the download of batch i-1
+    run on their own CUDA streams while batch i is in the decode loop, so the PCIe copies the reference pays serially
+    per utterance (CRN/crn_decode.py:46-47,53) disappear behind the compute.  All batches must have the same shape."""
     fn = enhance_fn or enhancer_for(model)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     compute = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    dev_in, host_out = [None] * depth, [None] * depth
+    nout = 2 * depth
+    dev_in, host_out = [None] * depth, [None] * nout
     ev_in = [torch.cuda.Event() for _ in range(depth)]
     ev_done = [None] * depth
-    ev_out = [None] * depth
-    pending = []                                    # slots whose download has been queued, oldest first
+    ev_out = [None] * nout
+    pending = []                                    # output slots whose download has been queued, oldest first
     for i, host in enumerate(host_batches):
-        slot = i % depth
-        if ev_out[slot] is not None:                # the consumer gets batch i - depth before its buffers are reused
-            ev_out[slot].synchronize()
-            pending.remove(slot)
-            yield host_out[slot]
+        slot, oslot = i % depth, i % nout
+        if len(pending) == depth:                   # the consumer gets batch i - depth before more work is queued
+            o = pending.pop(0)
+            ev_out[o].synchronize()
+            yield host_out[o]
         if dev_in[slot] is None:
             dev_in[slot] = torch.empty(host.shape, device=dev, dtype=torch.float32)
-            host_out[slot] = torch.empty(host.shape, dtype=torch.float32).pin_memory()
+        if host_out[oslot] is None:
+            host_out[oslot] = torch.empty(host.shape, dtype=torch.float32).pin_memory()
         with torch.cuda.stream(s_in):
             if ev_done[slot] is not None:
                 s_in.wait_event(ev_done[slot])      # the decode loop of batch i - depth has finished reading this buffer
@@ -340,13 +364,13 @@ def enhance_host_stream(model, host_batches, enhance_fn=None, depth=2, device=No
         y.record_stream(s_out)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[slot])
-            host_out[slot].copy_(y, non_blocking=True)
-            ev_out[slot] = torch.cuda.Event()
-            ev_out[slot].record(s_out)
-        pending.append(slot)
-    for slot in pending:
-        ev_out[slot].synchronize()
-        yield host_out[slot]
+            host_out[oslot].copy_(y, non_blocking=True)   # last handed out 2 * depth batches ago: depth draws have passed
+            ev_out[oslot] = torch.cuda.Event()
+            ev_out[oslot].record(s_out)
+        pending.append(oslot)
+    for o in pending:
+        ev_out[o].synchronize()
+        yield host_out[o]
 
 
 def read_wav_any(path):
@@ -372,25 +396,76 @@ def read_wav(path, fs):
 
 
 def write_wav(path, y, fs):
-    """``soundfile.write(path, y, fs)`` with its default subtype for .wav: 16-bit PCM (CRN/crn_decode.py:67)."""
+    """``soundfile.write(path, y, fs)`` with its default subtype for .wav: 16-bit PCM (CRN/crn_decode.py:67).
+    libsndfile converts float -> short as ``lrint(x * 0x7FFF)`` (and short -> float as ``x / 0x8000`` on read)."""
     from scipy.io import wavfile
-    pcm = np.clip(np.round(np.asarray(y, dtype=np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    pcm = np.clip(np.rint(np.asarray(y, dtype=np.float64) * 32767.0), -32768, 32767).astype(np.int16)
     wavfile.write(path, fs, pcm)
 
 
+def _wav_header(path):
+    """(sample rate, samples) of a mono wav file without reading its audio (memory-mapped)."""
+    from scipy.io import wavfile
+    sr, x = wavfile.read(path, mmap=True)
+    if x.ndim != 1:
+        raise ValueError(f"{x.ndim}-D audio; the decode scripts handle mono files only")
+    return int(sr), int(x.shape[0])
+
+
+def plan_batches(infos, batch, ragged, pad_tolerance=0.25, min_len=512):
+    """Deterministic batch list for ``enhance_dir``.  infos: [(name, sample rate, samples)].  ``ragged`` (the decode loop
+    takes per-clip ``lengths``): files of one sample rate are sorted by length and cut into batches of at most ``batch``
+    files whose longest member is at most ``1 + pad_tolerance`` times the shortest (bounded padding waste); otherwise
+    only files of identical (rate, length) share a batch.  Returns [(sr, [names], [lengths])]."""
+    out = []
+    if not ragged:
+        groups = {}
+        for name, sr, n in infos:
+            groups.setdefault((sr, n), []).append(name)
+        for (sr, n), names in sorted(groups.items()):
+            for i in range(0, len(names), batch):
+                out.append((sr, names[i:i + batch], [n] * len(names[i:i + batch])))
+        return out
+    by_sr = {}
+    for name, sr, n in infos:
+        by_sr.setdefault(sr, []).append((n, name))
+    for sr, items in sorted(by_sr.items()):
+        items.sort()
+        cur = []
+        for n, name in items:
+            if cur and (len(cur) >= batch or n > (1.0 + pad_tolerance) * cur[0][0] or cur[0][0] < min_len):
+                out.append((sr, [x[1] for x in cur], [x[0] for x in cur]))
+                cur = []
+            cur.append((n, name))
+        if cur:
+            out.append((sr, [x[1] for x in cur], [x[0] for x in cur]))
+    return out
+
+
 def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, batch=64, device="cuda", enhance_fn=None,
-                resample_to=None, rank=None, world=None, **kw):
+                resample_to=None, rank=None, world=None, pad_tolerance=0.25, report=None, **kw):
     """wav directory in -> wav directory out: the ``enhance(args)`` surface of the decode scripts (``args.mix_file_path``,
     ``args.esti_clean_file_path`` / ``args.esti_file_path``, ``args.fs``; e.g. CRN/crn_decode_vb.py:17-64).  The
-    reference loops one file at a time; here files of equal length are batched (no model in the reference has a padding
-    mask, so clips of different lengths never share a batch) and a batch stays on the device from the noisy waveform to
-    the enhanced one.  ``resample_to=16000`` adds the front step of the ``*_decode_vb.py`` scripts
-    (``librosa.resample(x, orig_fs, 16000, fix=True, scale=False)``, LSTM/lstm_decode_vb.py:33-34) on the device:
-    files are then grouped by (sample rate, length).  ``rank`` / ``world`` (default: the initialised
-    ``torch.distributed`` group, else one rank) shard the work over processes, one per GPU: every rank builds the same
-    list of batches and decodes batches ``rank, rank + world, ...``; utterances are independent and every rank writes
-    its own files, so no collective is involved.  Returns the number of files THIS rank wrote.
-    ``kw`` goes to the decode loop (``p=0.5`` for the compressed checkpoints)."""
+    reference loops one file at a time, any length (crn_decode_vb.py:31-33); here files are batched and a batch stays on
+    the device from the noisy waveform to the enhanced one:
+
+    * decode loops that take per-clip ``lengths`` (the time-causal families LSTM, CRN, GCRN, DPCRN) get LENGTH-BUCKETED
+      batches: files sorted by length, tail-padded to the longest of their batch (at most ``pad_tolerance`` longer than
+      the shortest), every clip decoded exactly as if alone (``plan_batches``);
+    * the other families (utterance-level statistics or attention over time, look-ahead) batch files of identical length;
+    * ``resample_to=16000`` adds the front step of the ``*_decode_vb.py`` scripts (``librosa.resample(x, orig_fs, 16000,
+      fix=True, scale=False)``, LSTM/lstm_decode_vb.py:33-34) on the device; those files are grouped by (rate, length).
+
+    Only wav headers are read up front; audio is loaded per batch, for this rank's batches only, one batch ahead on a
+    reader thread.  Entries that are not readable mono wav files are skipped and reported, never fatal (a script
+    looping over os.listdir would die on the first one).  ``rank`` / ``world`` (default: the
+    initialised ``torch.distributed`` group, else one rank) shard the batch list over processes, one per GPU: every rank
+    builds the same list and decodes batches ``rank, rank + world, ...``; utterances are independent and every rank
+    writes its own files, so no collective is involved.  Returns the number of files THIS rank
+    wrote; ``report`` (a dict) receives the details.  ``kw`` goes to the decode loop (``p=0.5`` for the compressed
+    checkpoints)."""
+    import inspect
+    from concurrent.futures import ThreadPoolExecutor
     if world is None:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -400,30 +475,71 @@ def enhance_dir(model, mix_file_path, esti_file_path, fs=16000, batch=64, device
     if not 0 <= rank < world:
         raise ValueError(f"rank {rank} outside world of {world}")
     fn = enhance_fn or enhancer_for(model)
+    ragged = resample_to is None and "lengths" in inspect.signature(fn).parameters
     os.makedirs(esti_file_path, exist_ok=True)
-    groups = {}
+    infos, skipped = [], {}
     for name in sorted(os.listdir(mix_file_path)):
         path = os.path.join(mix_file_path, name)
-        if resample_to is None:
-            x, sr = read_wav(path, fs), fs
-        else:
-            x, sr = read_wav_any(path)
-        groups.setdefault((sr, len(x)), []).append((name, x.astype(np.float32)))
-    count = 0
-    ibatch = -1
-    for (sr, _), group in sorted(groups.items()):
-        for i in range(0, len(group), batch):
-            ibatch += 1
-            if ibatch % world != rank:
+        if not os.path.isfile(path):
+            skipped[name] = "not a file"
+            continue
+        try:
+            sr, n = _wav_header(path)
+        except Exception as e:                       # not a wav file / unsupported encoding / truncated header
+            skipped[name] = f"unreadable: {e}"
+            continue
+        if resample_to is None and sr != fs:
+            skipped[name] = f"sample rate {sr} != {fs} (pass resample_to=)"
+            continue
+        infos.append((name, sr, n))
+    batches = plan_batches(infos, batch, ragged, pad_tolerance)
+    mine = [bt for i, bt in enumerate(batches) if i % world == rank]
+
+    def load(bt):
+        sr, names, lens = bt
+        nmax = max(lens)
+        buf = np.zeros((len(names), nmax), dtype=np.float32)
+        ok = []
+        for i, (name, n) in enumerate(zip(names, lens)):
+            try:
+                x, _ = read_wav_any(os.path.join(mix_file_path, name))
+                if len(x) != n:
+                    raise ValueError(f"{len(x)} samples, header says {n}")
+                buf[i, :n] = x
+                ok.append(i)
+            except Exception as e:                   # a file that turns out to be corrupt does not poison its batch
+                skipped[name] = f"unreadable: {e}"
+        return buf, ok
+
+    count, padded, total = 0, 0, 0
+    written = []
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        fut = pool.submit(load, mine[0]) if mine else None
+        for k, (sr, names, lens) in enumerate(mine):
+            buf, ok = fut.result()
+            fut = pool.submit(load, mine[k + 1]) if k + 1 < len(mine) else None
+            if not ok:
                 continue
-            chunk = group[i:i + batch]
-            wav = torch.from_numpy(np.stack([x for _, x in chunk])).to(device)
+            if len(ok) != len(names):
+                buf = buf[ok]
+                names, lens = [names[i] for i in ok], [lens[i] for i in ok]
+            wav = torch.from_numpy(buf).to(device)
             if resample_to is not None:
                 wav = ops.resample(wav, sr, resample_to)
-            out = fn(model, wav, **kw).cpu().numpy()
-            for (name, _), y in zip(chunk, out):
-                write_wav(os.path.join(esti_file_path, name), y, fs)
+            if ragged and len(set(lens)) > 1:
+                out = fn(model, wav, lengths=torch.tensor(lens, dtype=torch.int32), **kw)
+            else:
+                out = fn(model, wav, **kw)
+            out = out.cpu().numpy()
+            for name, n, y in zip(names, lens, out):
+                write_wav(os.path.join(esti_file_path, name), y if resample_to is not None else y[:n], fs)
+                written.append(name)
                 count += 1
+            padded += len(names) * max(lens) - sum(lens)
+            total += len(names) * max(lens)
+    if report is not None:
+        report.update(written=written, skipped=skipped, batches=len(mine), batches_total=len(batches), ragged=ragged,
+                      padded_fraction=(padded / total if total else 0.0))
     return count
 
 

@@ -73,17 +73,26 @@ def launch_count() -> int:
     return int(_lib.load().se_launch_count())
 
 
-def rms_scale(wav, reciprocal=False):
-    """wav [B,N] -> (c [B], inv_c [B]).  a1."""
+def _check_lengths(lengths, b, device):
+    if lengths is None:
+        return
+    if not (lengths.is_cuda and lengths.dtype == torch.int32 and lengths.is_contiguous() and lengths.numel() == b):
+        raise _lib.SeB200Error("lengths must be a contiguous CUDA int32 tensor with one entry per clip")
+
+
+def rms_scale(wav, reciprocal=False, lengths=None):
+    """wav [B,N] -> (c [B], inv_c [B]).  a1.  ``lengths`` (int32 [B], CUDA): per-clip sample counts of a tail-padded
+    batch (see se_rms_scale_len)."""
     _need_cuda(wav)
     device_check()
     assert wav.dim() == 2 and wav.stride(1) == 1
     b, n = wav.shape
+    _check_lengths(lengths, b, wav.device)
     c = torch.empty(b, device=wav.device, dtype=torch.float32)
     ic = torch.empty_like(c)
     with _Timed("rms_scale"):
-        check(_lib.load().se_rms_scale(_ptr(wav), wav.stride(0), b, n, int(reciprocal), _ptr(c), _ptr(ic),
-                                       _stream()), "se_rms_scale")
+        check(_lib.load().se_rms_scale_len(_ptr(wav), wav.stride(0), b, n, _ptr(lengths), int(reciprocal), _ptr(c),
+                                           _ptr(ic), _stream()), "se_rms_scale")
     return c, ic
 
 
@@ -94,12 +103,13 @@ def _plane_strides(t, layout):
     return t.stride(0), t.stride(2), t.stride(1)
 
 
-def stft(wav, scale, n_fft, win, hop, mag=None, re=None, im=None, layout="btf", p_mag=1.0, p_ri=1.0):
+def stft(wav, scale, n_fft, win, hop, mag=None, re=None, im=None, layout="btf", p_mag=1.0, p_ri=1.0, lengths=None):
     """Fused STFT.  mag / re / im are pre-allocated planes ([B,T,F] for 'btf', [B,F,T] for 'bft');
-    re and im must share strides, mag has its own."""
+    re and im must share strides, mag has its own.  ``lengths``: see se_stft_len (tail-padded batch)."""
     _need_cuda(wav, scale, mag, re, im)
     device_check()
     b, n = wav.shape
+    _check_lengths(lengths, b, wav.device)
     t = 1 + n // hop
     msb = mst = msf = sb = st = sf = 0
     if mag is not None:
@@ -108,16 +118,17 @@ def stft(wav, scale, n_fft, win, hop, mag=None, re=None, im=None, layout="btf", 
         sb, st, sf = _plane_strides(re, layout)
         assert _plane_strides(im, layout) == (sb, st, sf), "re and im planes must share strides"
     with _Timed("stft"):
-        check(_lib.load().se_stft(_ptr(wav), wav.stride(0), b, n, _ptr(scale), n_fft, win, hop, t, _ptr(mag), msb,
-                                  mst, msf, _ptr(re), _ptr(im), sb, st, sf, float(p_mag), float(p_ri), _stream()),
-              "se_stft")
+        check(_lib.load().se_stft_len(_ptr(wav), wav.stride(0), b, n, _ptr(lengths), _ptr(scale), n_fft, win, hop, t,
+                                      _ptr(mag), msb, mst, msf, _ptr(re), _ptr(im), sb, st, sf, float(p_mag),
+                                      float(p_ri), _stream()), "se_stft")
     return t
 
 
 def istft(mode, a_re, a_im, b_re, b_im, n_fft, win, hop, out, length, out_scale=None, inv_p=1.0, p_x=1.0,
-          layout_a="btf", layout_b="btf"):
+          layout_a="btf", layout_b="btf", lengths=None):
     _need_cuda(a_re, a_im, b_re, b_im, out, out_scale)
     device_check()
+    _check_lengths(lengths, a_re.shape[0], a_re.device)
     asb, ast, asf = _plane_strides(a_re, layout_a)
     if a_im is not None:
         assert _plane_strides(a_im, layout_a) == (asb, ast, asf)
@@ -129,9 +140,9 @@ def istft(mode, a_re, a_im, b_re, b_im, n_fft, win, hop, out, length, out_scale=
     bsz = a_re.shape[0]
     t = a_re.shape[1] if layout_a == "btf" else a_re.shape[2]
     with _Timed("istft"):
-        check(_lib.load().se_istft(mode, _ptr(a_re), _ptr(a_im), asb, ast, asf, _ptr(b_re), _ptr(b_im), bsb, bst,
-                                   bsf, float(inv_p), float(p_x), bsz, t, n_fft, win, hop, _ptr(out_scale),
-                                   _ptr(out), out.stride(0), int(length), _stream()), "se_istft")
+        check(_lib.load().se_istft_len(mode, _ptr(a_re), _ptr(a_im), asb, ast, asf, _ptr(b_re), _ptr(b_im), bsb, bst,
+                                       bsf, float(inv_p), float(p_x), bsz, t, n_fft, win, hop, _ptr(out_scale),
+                                       _ptr(out), out.stride(0), int(length), _ptr(lengths), _stream()), "se_istft")
     return out
 
 

@@ -217,3 +217,43 @@ def test_resample_full_size_batch_properties():
         ref = R.librosa_resample(x[b].astype(np.float64), 48000, 16000)
         assert np.abs(y[b].cpu().numpy() - ref).max() < 1e-5
 
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_ragged_batch_equals_per_clip_dsp(geom):
+    """Tail-padded batch with per-clip lengths (se_rms_scale_len / se_stft_len / se_istft_len): the frames, the scale and the
+    reconstructed samples of every clip are BIT-identical to that clip processed alone at its own length; frames and
+    samples past a clip's end are zero.  Lengths include non-multiples of the hop and the shortest legal clip."""
+    dev, ops = _dev(), _ops()
+    from se_b200._lib import ISTFT_SPEC
+    n_fft, win, hop = geom
+    lens = [n_fft, 3 * hop + n_fft + 1, 9000, 12345, 16000, 16000 - 1]
+    nmax = max(lens)
+    b = len(lens)
+    wav = np.zeros((b, nmax), dtype=np.float32)
+    for i, n in enumerate(lens):
+        wav[i, :n] = synth.noisy_clip(50 + i, n)
+    w = torch.from_numpy(wav).to(dev)
+    lt = torch.tensor(lens, dtype=torch.int32, device=dev)
+    tmax, f = 1 + nmax // hop, n_fft // 2 + 1
+    c, ic = ops.rms_scale(w, lengths=lt)
+    spec = torch.full((b, tmax, f, 2), 7.0, device=dev)
+    mag = torch.full((b, tmax, f), 7.0, device=dev)
+    ops.stft(w, c, n_fft, win, hop, mag=mag, re=spec[..., 0], im=spec[..., 1], lengths=lt)
+    out = torch.full((b, nmax), 7.0, device=dev)
+    ops.istft(ISTFT_SPEC, spec[..., 0], spec[..., 1], None, None, n_fft, win, hop, out, nmax, out_scale=ic, lengths=lt)
+    torch.cuda.synchronize()
+    for i, n in enumerate(lens):
+        wi = w[i:i + 1, :n].contiguous()
+        ti = 1 + n // hop
+        c1, ic1 = ops.rms_scale(wi)
+        s1 = torch.empty(1, ti, f, 2, device=dev)
+        m1 = torch.empty(1, ti, f, device=dev)
+        ops.stft(wi, c1, n_fft, win, hop, mag=m1, re=s1[..., 0], im=s1[..., 1])
+        o1 = torch.empty(1, n, device=dev)
+        ops.istft(ISTFT_SPEC, s1[..., 0], s1[..., 1], None, None, n_fft, win, hop, o1, n, out_scale=ic1)
+        assert torch.equal(c[i:i + 1], c1) and torch.equal(ic[i:i + 1], ic1)
+        assert torch.equal(spec[i, :ti], s1[0]) and torch.equal(mag[i, :ti], m1[0])
+        assert float(spec[i, ti:].abs().sum()) == 0.0 and float(mag[i, ti:].abs().sum()) == 0.0
+        assert torch.equal(out[i, :n], o1[0]) and float(out[i, n:].abs().sum()) == 0.0
+        assert (o1[0] - wi[0]).abs().max().item() < 2e-6          # and it is the identity

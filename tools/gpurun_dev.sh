@@ -1,12 +1,17 @@
 #!/bin/bash
-# Development helper: gpurun with a temporary .gpurunignore (build objects, optionally more) so that kernel-iteration
-# calls push as little as possible -- the push is charged box time.  The ignore file only exists while the call runs,
-# so the driver's round-end snapshot is never affected.
-# usage: tools/gpurun_dev.sh [--timeout S] -- '<command>'      (extra ignore patterns: GPURUN_DEV_IGNORE="a b c")
+# Development helper: gpurun WITHOUT the 385 MB of shipped checkpoints (the push is charged box time).  The checkpoints are
+# moved to a stash outside the repo for the duration of the call and ALWAYS moved back (trap), so the driver's
+# round-end snapshot carries checkpoints/_ref/.  KEEP="CRN__ DCCRN__" keeps the files with those prefixes in place.
+# usage: [KEEP="prefix ..."] tools/gpurun_dev.sh [--timeout S] -- '<command>'
 cd "$(dirname "$0")/.."
-trap 'rm -f .gpurunignore' EXIT
-{
-  printf 'sixty-years-of-frequency-domain-monaural-speech-enhancement_b200/build/\n'
-  for pat in $GPURUN_DEV_IGNORE; do printf '%s\n' "$pat"; done
-} > .gpurunignore
+STASH=/tmp/ckpt_stash
+mkdir -p "$STASH"
+restore() { mv "$STASH"/*.pth checkpoints/_ref/ 2>/dev/null; true; }
+trap restore EXIT
+for f in checkpoints/_ref/*.pth; do
+  [ -e "$f" ] || continue
+  keep=0
+  for k in $KEEP; do case "$(basename "$f")" in "$k"*) keep=1;; esac; done
+  [ $keep = 1 ] || mv "$f" "$STASH"/
+done
 /usr/local/graft/bin/gpurun "$@"
