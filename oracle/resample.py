@@ -7,7 +7,7 @@ Reference call sites: ``LSTM/lstm_decode_vb.py:33-34``, ``DCCRN/dccrn_decode_vb.
     feat_wav, orig_fs = sf.read(path)
     feat_wav = librosa.resample(feat_wav, orig_fs, 16000, fix=True, scale=False)
 
-**Parity unpinned.**  ``librosa`` (positional ``resample(y, orig_sr, target_sr, fix=, scale=)`` => librosa <= 0.7) and
+**Parity unpinned by the reference; pinned here against an independent implementation.**  ``librosa`` (positional ``resample(y, orig_sr, target_sr, fix=, scale=)`` => librosa <= 0.7) and
 its back end ``resampy`` (``res_type='kaiser_best'`` is librosa's default) are third-party dependencies that are neither
 vendored in ``/root/reference`` nor installed here, with no version pin and no test or golden vector in the reference.
 What follows restates their PUBLISHED algorithm (resampy 0.2.x, J. O. Smith's band-limited interpolation):
@@ -21,7 +21,11 @@ What follows restates their PUBLISHED algorithm (resampy 0.2.x, J. O. Smith's ba
 * ``resampy_resample`` -- resampy/core.py: output length ``int(n * ratio)``, table scaled by ``ratio`` when decimating;
 * ``librosa_resample`` -- librosa/core/audio.py: identity when the rates agree, ``fix_length`` to ``ceil(n * ratio)``.
 
-``tests/test_oracle_dsp.py`` checks properties the algorithm must have (unit DC gain, pass-band sinusoids land on
+``tests/test_oracle_dsp.py::test_resample_oracle_pinned_to_torchaudio_kaiser_best`` pins this restatement against
+``torchaudio.functional.resample`` configured as torchaudio documents for 'kaiser_best' (a separate implementation of the
+same filter): 1e-6 agreement where resampy's integer table stride is exact, and at 48 k -> 16 k -- where resampy truncates the
+stride 170.67 -> 170 -- agreement of the un-truncated variant, i.e. the truncation is the only (faithfully restated)
+difference.  The same file also checks properties the algorithm must have (unit DC gain, pass-band sinusoids land on
 the analytic 16 kHz sinusoid, stop-band tones are removed, agreement with ``scipy.signal.resample_poly`` at the
 level two different anti-aliasing filters can agree) -- plausibility pins, not parity pins.
 """

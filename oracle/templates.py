@@ -4,6 +4,13 @@ on a box that has neither the reference tree nor its checkpoints.  Shapes as lis
 TEST / BENCH INFRASTRUCTURE."""
 from __future__ import annotations
 
+import os as _os
+
+# key -> shape tables recorded from the reference modules; ONE copy, kept with the product package (which needs them to build
+# its parameter trees and cannot import oracle/)
+_KEYS_DIR = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                          "sixty-years-of-frequency-domain-monaural-speech-enhancement_b200")
+
 
 def _bn(prefix, c):
     return {f"{prefix}.weight": (c,), f"{prefix}.bias": (c,), f"{prefix}.running_mean": (c,),
@@ -154,10 +161,10 @@ def dpcrn_template():
 
 def uformer_template():
     """The 668 state-dict entries of the shipped Uformer checkpoints (names, shapes, order), as listed by
-    torch.load on Uformer/BEST_MODEL/*.pth and stored in oracle/uformer_keys.json."""
+    torch.load on Uformer/BEST_MODEL/*.pth and stored in <package>/uformer_keys.json."""
     import json
     import os
-    keys = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "uformer_keys.json")))
+    keys = json.load(open(os.path.join(_KEYS_DIR, "uformer_keys.json")))
     return {k: tuple(shape) for k, shape, _ in keys}
 
 
@@ -229,19 +236,19 @@ def ctsnet_step2_template(X=6, R=3, cumulative=False):
 
 def taylorsenet_template(cumulative=False):
     """TaylorSENet/TaylorSENet.py:8-64 in the configuration of taylorsenet_decode_vb.py:11-13 (811 entries, key order as
-    ``TaylorSENet(...).state_dict()`` lists it; recorded from the reference module in oracle/taylor*_keys.json)."""
+    ``TaylorSENet(...).state_dict()`` lists it; recorded from the reference module in <package>/taylor*_keys.json)."""
     import json
     import os
     name = "taylor_new_keys.json" if cumulative else "taylor_keys.json"
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), name)) as f:
+    with open(os.path.join(_KEYS_DIR, name)) as f:
         return {k: tuple(v) for k, v in json.load(f).items()}
 
 
 def g2net_template(cumulative=True):
     """G2Net_new/gaf_net_320.py:10-71 (cumulative LayerNorm) / G2Net_VB (InstanceNorm) in the configuration of
-    com_decode.py:23 (825 entries; recorded from the reference module in oracle/g2net_*_keys.json)."""
+    com_decode.py:23 (825 entries; recorded from the reference module in <package>/g2net_*_keys.json)."""
     import json
     import os
     name = "g2net_new_keys.json" if cumulative else "g2net_vb_keys.json"
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), name)) as f:
+    with open(os.path.join(_KEYS_DIR, name)) as f:
         return {k: tuple(v) for k, v in json.load(f).items()}
