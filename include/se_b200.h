@@ -474,6 +474,47 @@ int se_cts_glue1(const float* x_ri, const float* est_mag, long long n, float* s2
 int se_cts_glue2(const float* out_r, const float* out_i, const float* s2_in, long long n, float* est,
                  se_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Plan-level entry points: the whole CRN path behind four calls, for hosts that are not
+ * Python.  csrc/plan_crn.cu restates crn.py + packing.py + decode.enhance_mag_mapping in C++ over the op-level entry
+ * points above.
+ *   se_crn_weights: HOST pointers to the fp32 tensors of the reference state-dict in torch's own layouts
+ *       (CRN/CRN.py:35-109; the keys `crn_net().state_dict()` lists): en.en_module.i.1.{weight [Co,Ci,2,3], bias},
+ *       en.en_module.i.2.{weight, bias, running_mean, running_var}, lstm.{weight_ih,weight_hh,bias_ih,bias_hh}_l{0,1},
+ *       de.de_module.i.0.{weight [Ci,Co,2,3], bias}, de.de_module.i.{2, 3 for i = 3}.{weight, bias, running_mean,
+ *       running_var}.
+ *   se_plan_create_crn: packs the weights (eval BatchNorm folded, K-major conv matrices + TF32 pairs, output-parity
+ *       classes of the transposed convs, LSTM gate rows in slice order) and allocates ONE set of device buffers for
+ *       batches of up to B_max clips of up to N_max samples; nothing is allocated afterwards.
+ *   se_query_workspace: bytes of device memory the plan holds.
+ *   se_forward_crn: crn_net.forward (CRN/CRN.py:23-33), mag / est [B, T, 161] device fp32.
+ *   se_enhance_crn: CRN/crn_decode.py:38-57 for B device waveforms of N samples (row strides in floats): RMS scale,
+ *       STFT 320/320/160 with |X|^p, forward, est^(1/p) with the noisy phase, iSTFT(length = N), 1/c.  lengths:
+ *       NULL or device int32 [B] per-clip sample counts of a tail-padded batch (se_stft_len).
+ *   se_plan_set_graph(plan, 1): se_enhance_crn captures its launch sequence once per (B, N, ragged, p) in a CUDA graph
+ *       and replays it (the batch is staged through plan-owned buffers because kernel arguments are baked in).
+ * ------------------------------------------------------------------------------------- */
+typedef struct se_plan se_plan_t;
+typedef struct se_crn_weights {
+  const float* en_w[5];
+  const float* en_b[5];
+  const float* en_bn[5][4];   /* weight, bias, running_mean, running_var */
+  const float* lstm_w_ih[2];
+  const float* lstm_w_hh[2];
+  const float* lstm_b_ih[2];
+  const float* lstm_b_hh[2];
+  const float* de_w[5];
+  const float* de_b[5];
+  const float* de_bn[5][4];
+} se_crn_weights;
+int se_plan_create_crn(const se_crn_weights* w, int B_max, int N_max, se_plan_t** plan);
+long long se_query_workspace(const se_plan_t* plan);
+int se_plan_set_graph(se_plan_t* plan, int enabled);
+int se_forward_crn(se_plan_t* plan, const float* mag, float* est, int B, int T, se_stream_t stream);
+int se_enhance_crn(se_plan_t* plan, const float* wav, long long wav_stride, float* out, long long out_stride, int B, int N,
+                   const int* lengths, float p, se_stream_t stream);
+int se_plan_destroy(se_plan_t* plan);
+
 #ifdef __cplusplus
 }
 #endif

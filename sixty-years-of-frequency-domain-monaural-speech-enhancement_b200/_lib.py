@@ -17,6 +17,16 @@ ACT = {"none": 0, "elu": 1, "softplus": 2, "relu": 3, "sigmoid": 4, "tanh": 5, "
 ISTFT_SPEC, ISTFT_RI_DECOMP, ISTFT_MAG_PHASE, ISTFT_CMASK = 0, 1, 2, 3
 
 
+class CrnWeights(C.Structure):
+    """se_crn_weights (include/se_b200.h): host pointers to the reference state-dict tensors."""
+    _fields_ = [
+        ("en_w", C.c_void_p * 5), ("en_b", C.c_void_p * 5), ("en_bn", (C.c_void_p * 4) * 5),
+        ("lstm_w_ih", C.c_void_p * 2), ("lstm_w_hh", C.c_void_p * 2), ("lstm_b_ih", C.c_void_p * 2),
+        ("lstm_b_hh", C.c_void_p * 2),
+        ("de_w", C.c_void_p * 5), ("de_b", C.c_void_p * 5), ("de_bn", (C.c_void_p * 4) * 5),
+    ]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [
         ("src0", C.c_void_p), ("src1", C.c_void_p), ("C0", C.c_int), ("C1", C.c_int),
@@ -98,6 +108,12 @@ PROTOTYPES = {
     "se_taylor_zero": (_I, [_P, _P, _LL, _I, _I, _P, _P, _P, _P]),
     "se_cts_glue1": (_I, [_P, _P, _LL, _P, _P]),
     "se_cts_glue2": (_I, [_P, _P, _P, _LL, _P, _P]),
+    "se_plan_create_crn": (_I, [C.POINTER(CrnWeights), _I, _I, C.POINTER(C.c_void_p)]),
+    "se_query_workspace": (C.c_longlong, [_P]),
+    "se_plan_set_graph": (_I, [_P, _I]),
+    "se_forward_crn": (_I, [_P, _P, _P, _I, _I, _P]),
+    "se_enhance_crn": (_I, [_P, _P, _LL, _P, _LL, _I, _I, _P, _F, _P]),
+    "se_plan_destroy": (_I, [_P]),
 }
 NORM_PRE = {"none": 0, "glu": 1, "prelu": 2, "glu_prelu": 3}
 NORM_POST = {"none": 0, "prelu": 1, "fir": 2}

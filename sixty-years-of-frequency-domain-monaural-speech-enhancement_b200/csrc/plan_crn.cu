@@ -1,0 +1,469 @@
+// Plan-level C ABI for the CRN decode path (se_plan_create_<model> / se_forward_<model> /
+// se_enhance_<model> / se_query_workspace): everything crn.py + packing.py + decode.enhance_mag_mapping do in Python,
+// as a C++ host layer over the op-level entry points of this library, so that a C host (or any FFI) can decode
+// without a Python interpreter:
+//
+//   se_plan_create_crn   reference state-dict tensors (HOST fp32 pointers, torch layouts of CRN/CRN.py:35-109) -> packed
+//                        device weights (eval BatchNorm folded, K-major conv matrices + TF32 hi/lo pairs, transposed-conv
+//                        output-parity classes, LSTM gate rows in slice order with the NCHW <-> NHWC flatten permutation
+//                        absorbed) + ONE device arena for all activations of a (B_max, N_max) batch
+//   se_forward_crn       crn_net.forward (CRN/CRN.py:23-33): [B,T,161] magnitude -> [B,T,161] estimate
+//   se_enhance_crn       the decode loop of CRN/crn_decode.py:38-57 on device waveforms (optionally ragged: per-clip lengths)
+//   se_plan_set_graph    capture se_enhance_crn once per (B, N) in a CUDA graph and replay it (one cudaGraphLaunch per batch)
+//
+// No allocation after creation; re-entrant for distinct plans.  Packing runs on the host CPU once (17.6 M weights).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kEncCh[6] = {1, 16, 32, 64, 128, 256};   // CRN.py:40-62
+constexpr int kEncF[6] = {161, 80, 39, 19, 9, 4};
+constexpr int kDecCi[5] = {512, 256, 128, 64, 32};     // CRN.py:77-99
+constexpr int kDecCo[5] = {128, 64, 32, 16, 1};
+constexpr int kH = 1024, kBins = 161, kNfft = 320, kWin = 320, kHop = 160;
+constexpr float kBnEps = 1e-5f;
+
+inline float rna_tf32(float v) {
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  b = (b + 0x1000u) & ~0x1FFFu;
+  float r;
+  memcpy(&r, &b, 4);
+  return r;
+}
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;
+};
+
+struct ConvW {
+  DevBuf kn, hi, lo, bias, fill;   // kn [K][Co]; hi/lo [Co][K]
+  int K = 0, Co = 0;
+};
+
+struct GraphKey {
+  int B, N, ragged;
+  float p;
+  bool operator<(const GraphKey& o) const { return std::tie(B, N, ragged, p) < std::tie(o.B, o.N, o.ragged, o.p); }
+};
+
+}  // namespace
+
+struct se_plan {
+  int Bmax = 0, Nmax = 0, Tmax = 0;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  // weights
+  DevBuf en0_w, en0_b;
+  ConvW enc[5];                 // 1..4 used
+  DevBuf wih_hi[2], wih_lo[2], lbias[2], whh[2];
+  ConvW dec_even[4], dec_odd[4];
+  DevBuf de4_w;
+  float de4_b = 0.f;
+  // arena
+  float *a1, *a2, *a2h, *a2l, *a3h, *a3l, *a4h, *a4l, *a5h, *a5l, *xp, *hs0, *hs0h, *hs0l, *hs1, *hs1h, *hs1l;
+  float *d0h, *d0l, *d1h, *d1l, *d2h, *d2l, *d3, *est, *mag, *spec, *c, *inv_c, *lwork, *wav_in, *wav_out;
+  unsigned* sync;
+  int* lens;
+  // graphs
+  int use_graph = 0;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  cudaStream_t cap_stream = nullptr;
+};
+
+namespace {
+
+using se::set_error;
+
+bool dev_alloc(se_plan* P, DevBuf& b, size_t nfloats) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, nfloats * sizeof(float)) != cudaSuccess) return false;
+  P->allocs.push_back(p);
+  P->bytes += nfloats * sizeof(float);
+  b.p = static_cast<float*>(p);
+  b.n = nfloats;
+  return true;
+}
+bool upload(se_plan* P, DevBuf& b, const std::vector<float>& h) {
+  if (!dev_alloc(P, b, h.size())) return false;
+  return cudaMemcpy(b.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+bool upload_split(se_plan* P, DevBuf& hi, DevBuf& lo, const std::vector<float>& h) {
+  std::vector<float> a(h.size()), b(h.size());
+  for (size_t i = 0; i < h.size(); ++i) {
+    a[i] = rna_tf32(h[i]);
+    b[i] = rna_tf32(h[i] - a[i]);
+  }
+  return upload(P, hi, a) && upload(P, lo, b);
+}
+// eval BatchNorm as y = x * s + o   (packing.bn_fold)
+void bn_fold(const float* const bn[4], int c, std::vector<float>& s, std::vector<float>& o) {
+  s.resize(c);
+  o.resize(c);
+  for (int i = 0; i < c; ++i) {
+    s[i] = bn[0][i] / sqrtf(bn[3][i] + kBnEps);
+    o[i] = bn[1][i] - bn[2][i] * s[i];
+  }
+}
+// K-major matrix [K][Co] -> ConvW (kn + TF32 pair of its transpose)
+bool make_convw(se_plan* P, ConvW& w, const std::vector<float>& kn, int K, int Co, const std::vector<float>& bias) {
+  w.K = K;
+  w.Co = Co;
+  std::vector<float> t((size_t)K * Co);
+  for (int k = 0; k < K; ++k)
+    for (int c = 0; c < Co; ++c) t[(size_t)c * K + k] = kn[(size_t)k * Co + c];
+  return upload(P, w.kn, kn) && upload_split(P, w.hi, w.lo, t) && upload(P, w.bias, bias);
+}
+
+// torch gate-major rows [i|f|g|o] x H -> slice order: row s*32 + g*8 + j  <-  g*H + unit(s*8+j)   (packing.slice_rows)
+std::vector<int> slice_rows(const std::vector<int>* unit_perm) {
+  std::vector<int> rows(4 * kH);
+  for (int s = 0; s < kH / 8; ++s)
+    for (int g = 0; g < 4; ++g)
+      for (int j = 0; j < 8; ++j) {
+        const int u = s * 8 + j;
+        rows[s * 32 + g * 8 + j] = g * kH + (unit_perm ? (*unit_perm)[u] : u);
+      }
+  return rows;
+}
+
+bool pack_lstm(se_plan* P, int l, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+               const std::vector<int>* in_perm, const std::vector<int>* unit_perm) {
+  const std::vector<int> rows = slice_rows(unit_perm);
+  std::vector<float> wi((size_t)4 * kH * kH), wh((size_t)4 * kH * kH), bias(4 * kH);
+  for (int r = 0; r < 4 * kH; ++r) {
+    const float* si = w_ih + (size_t)rows[r] * kH;
+    const float* sh = w_hh + (size_t)rows[r] * kH;
+    float* di = wi.data() + (size_t)r * kH;
+    for (int q = 0; q < kH; ++q) di[q] = si[in_perm ? (*in_perm)[q] : q];
+    // whh[s][k][c] = W_hh[rows[s*32 + c]][unit(k)]
+    const int s = r / 32, c = r % 32;
+    for (int k = 0; k < kH; ++k) wh[((size_t)s * kH + k) * 32 + c] = sh[unit_perm ? (*unit_perm)[k] : k];
+    bias[r] = b_ih[rows[r]] + b_hh[rows[r]];
+  }
+  return upload_split(P, P->wih_hi[l], P->wih_lo[l], wi) && upload(P, P->lbias[l], bias) && upload(P, P->whh[l], wh);
+}
+
+int launch_conv_tc(const float* s0h, const float* s0l, const float* s1h, const float* s1l, int C0, int C1, int B, int T, int Fin,
+                   int Fout, const int (*taps)[2], int ntaps, int sf, const ConvW& w, float* out, float* oh, float* ol, int dstF,
+                   int f0, int fstep, cudaStream_t s) {
+  se_conv_tc_desc d;
+  memset(&d, 0, sizeof(d));
+  d.src0_hi = s0h;
+  d.src0_lo = s0l;
+  d.src1_hi = s1h;
+  d.src1_lo = s1l;
+  d.C0 = C0;
+  d.C1 = C1;
+  d.B = B;
+  d.T = T;
+  d.Fin = Fin;
+  d.Fout = Fout;
+  d.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) {
+    d.dt[i] = taps[i][0];
+    d.df[i] = taps[i][1];
+  }
+  d.sf = sf;
+  d.w_hi = w.hi.p;
+  d.w_lo = w.lo.p;
+  d.bias = w.bias.p;
+  d.Cout = w.Co;
+  d.act = SE_ACT_ELU;
+  d.out = out;
+  d.out_hi = oh;
+  d.out_lo = ol;
+  d.dstF = dstF;
+  d.dst_f0 = f0;
+  d.dst_fstep = fstep;
+  return se_conv_tf32x3(&d, s);
+}
+
+const int kConv23[6][2] = {{-1, 0}, {-1, 1}, {-1, 2}, {0, 0}, {0, 1}, {0, 2}};   // causal k(2,3): in[t-1+kt, 2f+kf]
+const int kDecEven[4][2] = {{0, 0}, {0, -1}, {-1, 0}, {-1, -1}};                 // (kt,kf) = (0,0),(0,2),(1,0),(1,2)
+const int kDecOdd[2][2] = {{0, 0}, {-1, 0}};                                     // (kt,kf) = (0,1),(1,1)
+
+#define SE_TRY(call)           \
+  do {                         \
+    const int rc_ = (call);    \
+    if (rc_ != SE_OK) return rc_; \
+  } while (0)
+
+int forward(se_plan* P, const float* mag, float* est, int B, int T, cudaStream_t s) {
+  const long long rows = (long long)B * T;
+  // encoder (CRN.py:35-71)
+  SE_TRY(se_conv_in1(mag, B, T, kBins, P->en0_w.p, P->en0_b.p, 16, SE_ACT_ELU, P->a1, kEncF[1], s));
+  {
+    se_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.src0 = P->a1;
+    d.C0 = 16;
+    d.B = B;
+    d.T = T;
+    d.Fin = kEncF[1];
+    d.Fout = kEncF[2];
+    d.ntaps = 6;
+    for (int i = 0; i < 6; ++i) {
+      d.dt[i] = kConv23[i][0];
+      d.df[i] = kConv23[i][1];
+    }
+    d.sf = 2;
+    d.W = P->enc[1].kn.p;
+    d.ldw = 32;
+    d.bias = P->enc[1].bias.p;
+    d.Cout = 32;
+    d.act = SE_ACT_ELU;
+    d.dst = P->a2;
+    d.dstF = kEncF[2];
+    d.dst_fstep = 1;
+    d.fill_f = -1;
+    SE_TRY(se_conv_gemm(&d, s));
+  }
+  SE_TRY(se_split_tf32(P->a2, P->a2h, P->a2l, rows * kEncF[2] * 32, s));
+  const float* ih[3] = {P->a2h, P->a3h, P->a4h};
+  const float* il[3] = {P->a2l, P->a3l, P->a4l};
+  float* oh[3] = {P->a3h, P->a4h, P->a5h};
+  float* ol[3] = {P->a3l, P->a4l, P->a5l};
+  for (int i = 2; i < 5; ++i)
+    SE_TRY(launch_conv_tc(ih[i - 2], il[i - 2], nullptr, nullptr, kEncCh[i], 0, B, T, kEncF[i], kEncF[i + 1], kConv23, 6, 2,
+                          P->enc[i], nullptr, oh[i - 2], ol[i - 2], kEncF[i + 1], 0, 1, s));
+  // LSTM x2 (CRN.py:20,27-31): projection GEMM over all T + persistent recurrence, 64 sequences per launch
+  const float* inh = P->a5h;
+  const float* inl = P->a5l;
+  float* hs[2] = {P->hs0, P->hs1};
+  float* hsh[2] = {P->hs0h, P->hs1h};
+  float* hsl[2] = {P->hs0l, P->hs1l};
+  for (int l = 0; l < 2; ++l) {
+    SE_TRY(se_gemm_tf32x3(inh, inl, kH, P->wih_hi[l].p, P->wih_lo[l].p, kH, (int)rows, 4 * kH, kH, P->lbias[l].p, SE_ACT_NONE,
+                          P->xp, 4 * kH, s));
+    for (int b0 = 0; b0 < B; b0 += 64) {
+      const int nb = B - b0 < 64 ? B - b0 : 64;
+      SE_TRY(se_lstm_seq(P->xp + (size_t)b0 * T * 4 * kH, 4 * kH, P->whh[l].p, nb, T, kH, hs[l] + (size_t)b0 * T * kH,
+                         (long long)T * kH, kH, P->lwork, P->sync, s));
+    }
+    SE_TRY(se_split_tf32(hs[l], hsh[l], hsl[l], rows * kH, s));
+    inh = hsh[l];
+    inl = hsl[l];
+  }
+  // decoder (CRN.py:73-109): cat(x, skip) by pointer, even / odd output columns of every ConvTranspose2d
+  const float* xh = P->hs1h;
+  const float* xl = P->hs1l;
+  const float* skh[4] = {P->a5h, P->a4h, P->a3h, P->a2h};
+  const float* skl[4] = {P->a5l, P->a4l, P->a3l, P->a2l};
+  float* dh[4] = {P->d0h, P->d1h, P->d2h, nullptr};
+  float* dl[4] = {P->d0l, P->d1l, P->d2l, nullptr};
+  int fin = 4;
+  for (int i = 0; i < 4; ++i) {
+    const int shift = i == 3 ? 1 : 0;            // de4: left pad on F (CRN.py:92-97)
+    const int fo = 2 * fin + 1 + shift;
+    const int c = kDecCi[i] / 2;
+    float* of32 = i == 3 ? P->d3 : nullptr;
+    SE_TRY(launch_conv_tc(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin + 1, kDecEven, 4, 1, P->dec_even[i], of32, dh[i], dl[i], fo,
+                          shift, 2, s));
+    SE_TRY(launch_conv_tc(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin, kDecOdd, 2, 1, P->dec_odd[i], of32, dh[i], dl[i], fo,
+                          shift + 1, 2, s));
+    if (shift) SE_TRY(se_fill_column(P->d3, rows, fo, kDecCo[i], 0, P->dec_even[i].fill.p, SE_ACT_ELU, 0.f, s));
+    xh = dh[i];
+    xl = dl[i];
+    fin = fo;
+  }
+  return se_deconv_out1(P->d3, P->a1, 16, 16, B, T, 80, P->de4_w.p, P->de4_b, SE_ACT_SOFTPLUS, est, s);
+}
+
+int enhance_eager(se_plan* P, const float* wav, long long wav_stride, float* out, long long out_stride, int B, int N,
+                  const int* lengths, float p, cudaStream_t s) {
+  const int T = 1 + N / kHop;
+  const long long tf = (long long)T * kBins;
+  SE_TRY(se_rms_scale_len(wav, wav_stride, B, N, lengths, 0, P->c, P->inv_c, s));
+  SE_TRY(se_stft_len(wav, wav_stride, B, N, lengths, P->c, kNfft, kWin, kHop, T, P->mag, tf, kBins, 1, P->spec, P->spec + 1,
+                     2 * tf, 2 * kBins, 2, p, 1.0f, s));
+  SE_TRY(forward(P, P->mag, P->est, B, T, s));
+  return se_istft_len(SE_ISTFT_MAG_PHASE, P->est, nullptr, tf, kBins, 1, P->spec, P->spec + 1, 2 * tf, 2 * kBins, 2, 1.0f / p,
+                      1.0f, B, T, kNfft, kWin, kHop, P->inv_c, out, out_stride, N, lengths, s);
+}
+
+}  // namespace
+
+extern "C" int se_plan_create_crn(const se_crn_weights* w, int B_max, int N_max, se_plan_t** plan) {
+  SE_REQUIRE(w && plan && B_max > 0 && N_max >= kNfft, "se_plan_create_crn: bad arguments (B_max=%d N_max=%d)", B_max, N_max);
+  SE_TRY(se_device_check());
+  se_plan* P = new se_plan();
+  P->Bmax = B_max;
+  P->Nmax = N_max;
+  P->Tmax = 1 + N_max / kHop;
+  bool ok = true;
+  std::vector<float> s, o;
+  // ---- encoder: Conv2d [Co,Ci,2,3] + BN -> K-major [(kt*3+kf)*Ci + ci][Co]   (packing.pack_conv)
+  for (int i = 0; i < 5 && ok; ++i) {
+    const int ci = kEncCh[i], co = kEncCh[i + 1], K = 6 * ci;
+    const float* const bn[4] = {w->en_bn[i][0], w->en_bn[i][1], w->en_bn[i][2], w->en_bn[i][3]};
+    bn_fold(bn, co, s, o);
+    std::vector<float> kn((size_t)K * co), bias(co);
+    for (int c = 0; c < co; ++c) {
+      for (int q = 0; q < ci; ++q)
+        for (int kt = 0; kt < 2; ++kt)
+          for (int kf = 0; kf < 3; ++kf)
+            kn[((size_t)(kt * 3 + kf) * ci + q) * co + c] = w->en_w[i][(((size_t)c * ci + q) * 2 + kt) * 3 + kf] * s[c];
+      bias[c] = w->en_b[i][c] * s[c] + o[c];
+    }
+    if (i == 0)
+      ok = upload(P, P->en0_w, kn) && upload(P, P->en0_b, bias);
+    else
+      ok = make_convw(P, P->enc[i], kn, K, co, bias);
+  }
+  // ---- LSTM: NHWC flatten index q = f*256 + c  <->  reference feature index c*4 + f   (crn.py _pack)
+  std::vector<int> nhwc(kH);
+  for (int q = 0; q < kH; ++q) nhwc[q] = (q % 256) * 4 + q / 256;
+  ok = ok && pack_lstm(P, 0, w->lstm_w_ih[0], w->lstm_w_hh[0], w->lstm_b_ih[0], w->lstm_b_hh[0], &nhwc, nullptr);
+  ok = ok && pack_lstm(P, 1, w->lstm_w_ih[1], w->lstm_w_hh[1], w->lstm_b_ih[1], w->lstm_b_hh[1], nullptr, &nhwc);
+  // ---- decoder: ConvTranspose2d [Ci,Co,2,3] stride (1,2) + BN -> even / odd output-column classes
+  for (int i = 0; i < 5 && ok; ++i) {
+    const int ci = kDecCi[i], co = kDecCo[i];
+    const float* const bn[4] = {w->de_bn[i][0], w->de_bn[i][1], w->de_bn[i][2], w->de_bn[i][3]};
+    bn_fold(bn, co, s, o);
+    auto W = [&](int q, int c, int kt, int kf) { return w->de_w[i][(((size_t)q * co + c) * 2 + kt) * 3 + kf] * s[c]; };
+    if (i < 4) {
+      const int ev[4][2] = {{0, 0}, {0, 2}, {1, 0}, {1, 2}}, od[2][2] = {{0, 1}, {1, 1}};
+      std::vector<float> e((size_t)4 * ci * co), d((size_t)2 * ci * co), bias(co);
+      for (int q = 0; q < ci; ++q)
+        for (int c = 0; c < co; ++c) {
+          for (int k = 0; k < 4; ++k) e[((size_t)k * ci + q) * co + c] = W(q, c, ev[k][0], ev[k][1]);
+          for (int k = 0; k < 2; ++k) d[((size_t)k * ci + q) * co + c] = W(q, c, od[k][0], od[k][1]);
+        }
+      for (int c = 0; c < co; ++c) bias[c] = w->de_b[i][c] * s[c] + o[c];
+      ok = make_convw(P, P->dec_even[i], e, 4 * ci, co, bias) && make_convw(P, P->dec_odd[i], d, 2 * ci, co, bias) &&
+           upload(P, P->dec_even[i].fill, o);
+    } else {
+      std::vector<float> d6((size_t)6 * ci);
+      for (int kt = 0; kt < 2; ++kt)
+        for (int kf = 0; kf < 3; ++kf)
+          for (int q = 0; q < ci; ++q) d6[(size_t)(kt * 3 + kf) * ci + q] = W(q, 0, kt, kf);
+      P->de4_b = w->de_b[i][0] * s[0] + o[0];
+      ok = upload(P, P->de4_w, d6);
+    }
+  }
+  // ---- arena
+  const size_t R = (size_t)B_max * P->Tmax;
+  struct Slot {
+    float** p;
+    size_t n;
+  };
+  const size_t lw = (size_t)se_lstm_seq_work_bytes(64, kH) / 4;
+  Slot slots[] = {{&P->a1, R * 80 * 16},  {&P->a2, R * 39 * 32},  {&P->a2h, R * 39 * 32}, {&P->a2l, R * 39 * 32},
+                  {&P->a3h, R * 19 * 64}, {&P->a3l, R * 19 * 64}, {&P->a4h, R * 9 * 128}, {&P->a4l, R * 9 * 128},
+                  {&P->a5h, R * 1024},    {&P->a5l, R * 1024},    {&P->xp, R * 4096},     {&P->hs0, R * 1024},
+                  {&P->hs0h, R * 1024},   {&P->hs0l, R * 1024},   {&P->hs1, R * 1024},    {&P->hs1h, R * 1024},
+                  {&P->hs1l, R * 1024},   {&P->d0h, R * 9 * 128}, {&P->d0l, R * 9 * 128}, {&P->d1h, R * 19 * 64},
+                  {&P->d1l, R * 19 * 64}, {&P->d2h, R * 39 * 32}, {&P->d2l, R * 39 * 32}, {&P->d3, R * 80 * 16},
+                  {&P->est, R * kBins},   {&P->mag, R * kBins},   {&P->spec, R * kBins * 2}, {&P->c, (size_t)B_max},
+                  {&P->inv_c, (size_t)B_max}, {&P->lwork, lw},    {&P->wav_in, (size_t)B_max * N_max},
+                  {&P->wav_out, (size_t)B_max * N_max}};
+  for (const Slot& sl : slots) {
+    DevBuf b;
+    ok = ok && dev_alloc(P, b, (sl.n + 3) & ~(size_t)3);
+    *sl.p = b.p;
+  }
+  DevBuf sy, le;
+  ok = ok && dev_alloc(P, sy, 16) && dev_alloc(P, le, (size_t)B_max);
+  P->sync = reinterpret_cast<unsigned*>(sy.p);
+  P->lens = reinterpret_cast<int*>(le.p);
+  if (ok) ok = cudaMemset(P->sync, 0, 16 * sizeof(unsigned)) == cudaSuccess;
+  if (!ok) {
+    set_error("se_plan_create_crn: device allocation / upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    se_plan_destroy(P);
+    return SE_ERR_CUDA;
+  }
+  *plan = P;
+  return SE_OK;
+}
+
+extern "C" long long se_query_workspace(const se_plan_t* plan) { return plan ? (long long)plan->bytes : 0; }
+
+extern "C" int se_plan_set_graph(se_plan_t* plan, int enabled) {
+  SE_REQUIRE(plan, "se_plan_set_graph: null plan");
+  plan->use_graph = enabled ? 1 : 0;
+  return SE_OK;
+}
+
+extern "C" int se_forward_crn(se_plan_t* plan, const float* mag, float* est, int B, int T, se_stream_t stream) {
+  SE_REQUIRE(plan && mag && est, "se_forward_crn: null argument");
+  SE_REQUIRE(B > 0 && B <= plan->Bmax && T > 0 && T <= plan->Tmax, "se_forward_crn: B=%d T=%d exceed the plan (%d, %d)", B, T,
+             plan->Bmax, plan->Tmax);
+  return forward(plan, mag, est, B, T, (cudaStream_t)stream);
+}
+
+extern "C" int se_enhance_crn(se_plan_t* plan, const float* wav, long long wav_stride, float* out, long long out_stride, int B,
+                              int N, const int* lengths, float p, se_stream_t stream) {
+  SE_REQUIRE(plan && wav && out, "se_enhance_crn: null argument");
+  SE_REQUIRE(B > 0 && B <= plan->Bmax && N >= kNfft && N <= plan->Nmax, "se_enhance_crn: B=%d N=%d exceed the plan (%d, %d)", B,
+             N, plan->Bmax, plan->Nmax);
+  SE_REQUIRE(p > 0.f && wav_stride >= N && out_stride >= N, "se_enhance_crn: bad exponent / strides");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!plan->use_graph) return enhance_eager(plan, wav, wav_stride, out, out_stride, B, N, lengths, p, s);
+  // graph replay: kernel arguments are baked into the graph, so the batch goes through the plan's own in / out buffers
+  // (two device-to-device copies, ~10 us for 64 x 4 s) and every (B, N, ragged, p) is captured once
+  cudaError_t e = cudaMemcpy2DAsync(plan->wav_in, (size_t)N * 4, wav, (size_t)wav_stride * 4, (size_t)N * 4, B,
+                                    cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess && lengths) e = cudaMemcpyAsync(plan->lens, lengths, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) {
+    set_error("se_enhance_crn: staging copy: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  const GraphKey key{B, N, lengths ? 1 : 0, p};
+  auto it = plan->graphs.find(key);
+  if (it == plan->graphs.end()) {
+    // warm-up outside capture (lazy one-time work: attribute setting, twiddle upload), then capture on a private stream
+    SE_TRY(enhance_eager(plan, plan->wav_in, N, plan->wav_out, N, B, N, lengths ? plan->lens : nullptr, p, s));
+    if (!plan->cap_stream && cudaStreamCreateWithFlags(&plan->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("se_enhance_crn: cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
+      return SE_ERR_CUDA;
+    }
+    cudaStreamSynchronize(s);
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    if (cudaStreamBeginCapture(plan->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      set_error("se_enhance_crn: cudaStreamBeginCapture: %s", cudaGetErrorString(cudaGetLastError()));
+      return SE_ERR_CUDA;
+    }
+    const int rc = enhance_eager(plan, plan->wav_in, N, plan->wav_out, N, B, N, lengths ? plan->lens : nullptr, p, plan->cap_stream);
+    e = cudaStreamEndCapture(plan->cap_stream, &g);
+    if (rc != SE_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&ge, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      set_error("se_enhance_crn: graph capture / instantiate: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return SE_ERR_CUDA;
+    }
+    it = plan->graphs.emplace(key, ge).first;
+  }
+  e = cudaGraphLaunch(it->second, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(out, (size_t)out_stride * 4, plan->wav_out, (size_t)N * 4, (size_t)N * 4, B, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) {
+    set_error("se_enhance_crn: graph launch: %s", cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
+extern "C" int se_plan_destroy(se_plan_t* plan) {
+  if (!plan) return SE_OK;
+  for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
+  if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
+  for (void* p : plan->allocs) cudaFree(p);
+  delete plan;
+  return SE_OK;
+}

@@ -325,6 +325,58 @@ def enhancer_for(model):
     raise TypeError(f"no decode loop registered for {type(model).__name__}")
 
 
+class GraphedEnhance:
+    """A decode loop captured once per input shape in a CUDA graph and replayed: one ``cudaGraphLaunch`` instead of the
+    350 .. 1 900 kernel launches (26 .. 76 us of Python + ctypes each) a batch of the TCM-family / FullSubNet models
+    costs -- for those the GPU otherwise waits for the host (tools/host_bound_check.py).  The reference has no
+    counterpart: it re-dispatches every ATen op per utterance (CRN/crn_decode.py:37-57).
+
+        dec = GraphedEnhance(model)                 # or GraphedEnhance((step1, step2)) for CTSNet; kw -> decode loop
+        y = dec(wav)                                # [B,N] float32 CUDA; y is valid until the next call with this shape
+
+    Shapes are static inside a graph: every distinct (B, N, ragged?) gets its own capture (a warm-up call, then the
+    capture, both on a side stream); ``lengths`` (per-clip sample counts, time-causal families) are copied into a
+    static tensor, so ragged batches of one padded shape share a graph."""
+
+    def __init__(self, model, enhance_fn=None, **kw):
+        self.model, self.fn, self.kw = model, enhance_fn or enhancer_for(model), kw
+        self._graphs = {}
+
+    def _capture(self, wav, lengths):
+        static_in = wav.clone()
+        static_len = None if lengths is None else lengths.clone()
+        kw = dict(self.kw)
+        if static_len is not None:
+            kw["lengths"] = static_len
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.fn(self.model, static_in, **kw)          # packs weights, fills lazy tables, sizes the allocator pools
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self.fn(self.model, static_in, **kw)
+        return graph, static_in, static_len, static_out
+
+    @torch.no_grad()
+    def __call__(self, wav, lengths=None):
+        if not wav.is_cuda:
+            raise RuntimeError("se_b200.decode needs CUDA tensors (no CPU fallback)")
+        wav = wav.contiguous().float()
+        if lengths is not None:
+            lengths = _lengths_arg(lengths, wav)
+        key = (tuple(wav.shape), wav.device, lengths is not None)
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(wav, lengths)
+        graph, static_in, static_len, static_out = self._graphs[key]
+        static_in.copy_(wav)
+        if static_len is not None:
+            static_len.copy_(lengths)
+        graph.replay()
+        return static_out
+
+
 def enhance_host_stream(model, host_batches, enhance_fn=None, depth=2, device=None, **kw):
     """Pipelined host -> host decode: for every pinned host batch [B,N] float32 of ``host_batches`` yields the enhanced
     batch as a pinned host tensor that stays valid until ``depth`` MORE batches have been drawn from the generator

@@ -557,6 +557,121 @@ def test_enhance_dir_length_bucketed_crn(tmp_path):
         assert np.abs(y - np.clip(np.rint(y_ref.astype(np.float64) * 32767.0), -32768, 32767)).max() <= 1.01
 
 
+@pytest.mark.parametrize("family", ["crn", "gcrn"])
+def test_graphed_enhance_equals_eager(family):
+    """decode.GraphedEnhance: the whole decode loop as one CUDA graph per shape (incl. the cluster recurrence launch) is
+    bit-identical to the eager loop, for new inputs, for a second shape, and for ragged batches sharing one graph."""
+    dev = _dev()
+    import se_b200
+    cls, tmpl, enh_name, _, kw, gain = RAGGED_FAMILIES[family]
+    sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=gain)
+    obj = se_b200
+    for part in cls.split("."):
+        obj = getattr(obj, part)
+    model = obj()
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    enh = getattr(se_b200.decode, enh_name)
+    dec = se_b200.decode.GraphedEnhance(model, **kw)
+    for b, n in ((3, 8000), (3, 8000), (2, 6400)):
+        wav = torch.from_numpy(synth.noisy_batch(b, n, first_index=90 + n // 100)).to(dev)
+        want = enh(model, wav, **kw)
+        got = dec(wav).clone()
+        assert torch.equal(got, want), (family, b, n)
+    assert len(dec._graphs) == 2
+    wav = torch.from_numpy(synth.noisy_batch(3, 8000, first_index=70)).to(dev)
+    for lens in ([8000, 7000, 6500], [6400, 8000, 7999]):
+        w = wav.clone()
+        for i, ln in enumerate(lens):
+            w[i, ln:] = 0
+        assert torch.equal(dec(w, lengths=lens).clone(), enh(model, w, lengths=lens, **kw))
+    assert len(dec._graphs) == 3
+
+
+def _crn_weight_blob(sd):
+    """Reference state-dict tensors in the order of se_crn_weights (tests/c_host/crn_plan_host.c)."""
+    keys = [f"en.en_module.{i}.1.weight" for i in range(5)] + [f"en.en_module.{i}.1.bias" for i in range(5)]
+    keys += [f"en.en_module.{i}.2.{n}" for i in range(5) for n in ("weight", "bias", "running_mean", "running_var")]
+    for part in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+        keys += [f"lstm.{part}_l{l}" for l in range(2)]
+    keys += [f"de.de_module.{i}.0.weight" for i in range(5)] + [f"de.de_module.{i}.0.bias" for i in range(5)]
+    keys += [f"de.de_module.{i}.{3 if i == 3 else 2}.{n}" for i in range(5)
+             for n in ("weight", "bias", "running_mean", "running_var")]
+    return np.concatenate([sd[k].detach().float().numpy().ravel() for k in keys])
+
+
+def test_plan_abi_python_front_end_equals_model_path():
+    """Plan-level C ABI (se_plan_create_crn / se_forward_crn / se_enhance_crn / se_query_workspace, csrc/plan_crn.cu)
+    through se_b200.plan (ctypes only): forward and decode equal the crn.py / decode.py path (same kernels, same packing
+    restated in C++ on the host) to fp32 rounding, eager and as a CUDA graph, equal-length and ragged."""
+    dev = _dev()
+    import se_b200
+    sd = synth.synthetic_state_dict(templates.crn_template(), seed=0)
+    model = se_b200.crn_net()
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    wav = torch.from_numpy(synth.noisy_batch(5, 8000, first_index=33)).to(dev)
+    want = se_b200.decode.enhance_crn(model, wav)
+    mag = torch.rand(3, 50, 161, device=dev) * 3       # >= 128 rows: crn.py then takes the tensor-core projection too
+
+    def close(a, b):
+        d = (a - b).abs().max().item()
+        return d <= 2e-6 * max(1.0, b.abs().max().item()), d
+
+    for graph in (False, True):
+        plan = se_b200.plan.CrnPlan(sd, b_max=8, n_max=8000, graph=graph)
+        assert plan.workspace_bytes > 70e6
+        ok, d = close(plan.forward(mag), model(mag))
+        print(f"plan (graph={graph}) forward vs crn.py: max abs diff {d:.2e}")
+        assert ok, d
+        first = plan.enhance(wav).clone()
+        assert close(first, want)[0]
+        assert torch.equal(plan.enhance(wav), first)        # replay == first run
+        lens = torch.tensor([8000, 7000, 6500, 6400, 7999], dtype=torch.int32, device=dev)
+        w = wav.clone()
+        for i, ln in enumerate(lens.tolist()):
+            w[i, ln:] = 0
+        assert close(plan.enhance(w, lengths=lens), se_b200.decode.enhance_crn(model, w, lengths=lens))[0]
+        with pytest.raises(Exception):
+            plan.enhance(torch.zeros(9, 8000, device=dev))        # exceeds B_max: an error code, not a crash
+        plan.close()
+
+
+def test_plan_abi_c_host_decodes_without_python_model_code(tmp_path):
+    """tests/c_host/crn_plan_host.c: a C program that links libse_b200.so + cudart, feeds it the reference state-dict as
+    raw tensors and a batch of waveforms, and writes the enhanced batch -- compared with the oracle decode
+    (CRN/crn_decode.py:38-57).  No Python model file is involved in producing the output."""
+    _dev()
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "sixty-years-of-frequency-domain-monaural-speech-enhancement_b200")
+    cc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if cc is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("no C compiler / CUDA headers on this box")
+    exe = str(tmp_path / "crn_plan_host")
+    subprocess.run([cc, "-O1", "-std=c99", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(root, "tests", "c_host", "crn_plan_host.c"), "-o", exe, "-L", pkg, "-lse_b200",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + pkg, "-Wl,-rpath," + os.path.join(cuda, "lib64")],
+                   check=True, capture_output=True)
+    sd = synth.synthetic_state_dict(templates.crn_template(), seed=0)
+    b, n = 3, 8000
+    wav = synth.noisy_batch(b, n, first_index=44)
+    _crn_weight_blob(sd).astype(np.float32).tofile(str(tmp_path / "w.bin"))
+    wav.astype(np.float32).tofile(str(tmp_path / "x.bin"))
+    for graph in (0, 1):
+        r = subprocess.run([exe, str(tmp_path / "w.bin"), str(tmp_path / "x.bin"), str(tmp_path / "y.bin"), str(b), str(n),
+                            str(graph)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.returncode, r.stderr[-500:])
+        y = np.fromfile(str(tmp_path / "y.bin"), dtype=np.float32).reshape(b, n)
+        for i in range(b):
+            _, to = odecode.enhance_crn(sd, wav[i].astype(np.float64))
+            rms = np.sqrt(np.mean((y[i] * to["c"] - to["y_norm"]) ** 2))
+            assert rms <= RMS_GATE, (graph, i, rms)
+        print(f"C host (graph={graph}): {r.stdout.strip()}")
+
+
 def test_enhance_host_stream_matches_direct_calls():
     """Pipelined pinned-host -> pinned-host decode (copy streams, ring of 2 buffers): every batch comes back in order and
     equals the direct device call, including when more batches than ring slots are in flight."""

@@ -40,9 +40,23 @@ def main():
         t1 = time.perf_counter()
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        print(json.dumps({"model": name, "enqueue_ms": 1e3 * (t1 - t0), "total_ms": 1e3 * (t2 - t0),
-                          "launches": se_b200.ops.launch_count() - n0,
-                          "host_us_per_launch": 1e6 * (t1 - t0) / max(1, se_b200.ops.launch_count() - n0)}), flush=True)
+        rec = {"model": name, "enqueue_ms": 1e3 * (t1 - t0), "total_ms": 1e3 * (t2 - t0),
+               "launches": se_b200.ops.launch_count() - n0,
+               "host_us_per_launch": 1e6 * (t1 - t0) / max(1, se_b200.ops.launch_count() - n0)}
+        # the same batch through decode.GraphedEnhance: one graph launch
+        y_eager = genh(model, wav, **kw)
+        dec = se_b200.decode.GraphedEnhance(model, genh, **kw)
+        dec(wav)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        yg = dec(wav)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        rec.update(graph_enqueue_ms=1e3 * (t1 - t0), graph_total_ms=1e3 * (t2 - t0),
+                   graph_enqueue_share=(t1 - t0) / (t2 - t0), graph_equals_eager=bool(torch.equal(yg, y_eager)))
+        print(json.dumps(rec), flush=True)
+        del dec
 
 
 if __name__ == "__main__":
