@@ -108,6 +108,23 @@ class crn_net(nn.Module):
         x = x.contiguous().float()
         b, t, f = x.shape
         assert f == self.N_BINS, f"CRN checkpoints are hard-wired to 161 bins, got {f}"
+        enc = self._encoder(x, taps)
+        h = enc[-1]
+        # LSTM: two layers, input projection hoisted over all T
+        seq, pair = (h.f32.view(b * t, 1024) if h.f32 is not None else None,
+                     (h.pair[0].view(b * t, 1024), h.pair[1].view(b * t, 1024)) if h.pair is not None else None)
+        for l in range(2):
+            hs = lstm_engine.lstm_layer(seq, P[f"lstm{l}"], b, t, pair)
+            seq, pair = hs.view(b * t, 1024), None
+        if taps is not None:
+            taps["lstm_nhwc"] = hs
+        return self._decoder(hs, enc, taps)
+
+    def _encoder(self, x, taps=None):
+        """CRN/CRN.py:35-71 on a [B,T,161] plane -> the five channels-last encoder activations (the last one, [B,T,4,256],
+        is the LSTM input [B,T,1024])."""
+        P = self._packed
+        b, t, _ = x.shape
         dev = x.device
         tc = lambda c0, c1, co, fo, sf: conv_engine.tc_eligible(c0, c1, co, fo, sf)   # noqa: E731
         enc = []
@@ -128,16 +145,15 @@ class crn_net(nn.Module):
         if taps is not None:
             for i, e in enumerate(enc):
                 taps[f"en{i + 1}"] = e.f32 if e.f32 is not None else e.pair[0] + e.pair[1]
-        # LSTM: two layers, input projection hoisted over all T
-        seq, pair = (h.f32.view(b * t, 1024) if h.f32 is not None else None,
-                     (h.pair[0].view(b * t, 1024), h.pair[1].view(b * t, 1024)) if h.pair is not None else None)
-        for l in range(2):
-            hs = lstm_engine.lstm_layer(seq, P[f"lstm{l}"], b, t, pair)
-            seq, pair = hs.view(b * t, 1024), None
-        if taps is not None:
-            taps["lstm_nhwc"] = hs
+        return enc
+
+    def _decoder(self, hs, enc, taps=None):
+        """CRN/CRN.py:73-109: hs [B,T,1024] (NHWC-flattened LSTM output) + encoder skips -> [B,T,161]."""
+        P = self._packed
+        b, t = hs.shape[0], hs.shape[1]
+        dev = hs.device
+        tc = lambda c0, c1, co, fo, sf: conv_engine.tc_eligible(c0, c1, co, fo, sf)   # noqa: E731
         h = Act(hs.view(b, t, 4, 256))
-        # decoder
         fin = 4
         for i in range(4):
             we, wo, bias, fill = P[f"de{i}"]
@@ -162,3 +178,24 @@ class crn_net(nn.Module):
         enc0 = enc[0].f32
         y = ops.deconv_out1(h, enc0, P["de4_w"], P["de4_b"], "softplus")
         return y
+
+    # -- streaming ---------------------------------------------------------------
+    STREAM_CONTEXT = (5, 5)      # frames of past the encoder / decoder conv stacks look at (one per k(2,.) layer)
+
+    def stream_cells(self):
+        """The two LSTM layers packed for the one-step cell GEMM (se_lstm_cell_tf32x3_ex) with the same NHWC
+        permutations as the offline packing: layer 0 reads the NHWC-flattened encoder output, layer 1 emits NHWC."""
+        self._ensure_packed()
+        if "cells" not in self._packed:
+            sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+            dev = next(self.parameters()).device
+            q = torch.arange(1024, device=dev)
+            nhwc = (q % 256) * 4 + q // 256
+            rows = (torch.arange(4, device=dev).view(4, 1) * 1024 + nhwc.view(1, -1)).reshape(-1)
+            c0 = packing.pack_lstm_cell(sd["lstm.weight_ih_l0"][:, nhwc].contiguous(), sd["lstm.weight_hh_l0"],
+                                        sd["lstm.bias_ih_l0"], sd["lstm.bias_hh_l0"])
+            c1 = packing.pack_lstm_cell(sd["lstm.weight_ih_l1"][rows].contiguous(),
+                                        sd["lstm.weight_hh_l1"][rows][:, nhwc].contiguous(),
+                                        sd["lstm.bias_ih_l1"][rows], sd["lstm.bias_hh_l1"][rows])
+            self._packed["cells"] = [c0, c1]
+        return self._packed["cells"]

@@ -58,6 +58,22 @@ class lstm_net(nn.Module):
         self._packed = None
         return super()._apply(fn, *a, **k)
 
+    def stream_cells(self):
+        """The three LSTM layers packed for the one-step cell GEMM (streaming.MagStream); the eval BatchNorm1d in front of
+        the first layer (LSTM.py:16,25) is folded into its input weights exactly as in the offline packing."""
+        self._ensure_packed()
+        if "cells" not in self._packed:
+            sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+            s, o = packing.bn_fold(sd["bn.weight"], sd["bn.bias"], sd["bn.running_mean"], sd["bn.running_var"])
+            w0 = sd["lstm1.weight_ih_l0"]
+            cells = [packing.pack_lstm_cell((w0 * s[None, :]).contiguous(), sd["lstm1.weight_hh_l0"],
+                                            sd["lstm1.bias_ih_l0"] + w0 @ o, sd["lstm1.bias_hh_l0"])]
+            for l in range(2):
+                cells.append(packing.pack_lstm_cell(sd[f"lstm2.weight_ih_l{l}"], sd[f"lstm2.weight_hh_l{l}"],
+                                                    sd[f"lstm2.bias_ih_l{l}"], sd[f"lstm2.bias_hh_l{l}"]))
+            self._packed["cells"] = cells
+        return self._packed["cells"]
+
     @torch.no_grad()
     def forward(self, x, taps=None):
         if not x.is_cuda:

@@ -588,6 +588,39 @@ def test_graphed_enhance_equals_eager(family):
     assert len(dec._graphs) == 3
 
 
+@pytest.mark.parametrize("family", ["crn", "lstm"])
+def test_streaming_equals_offline(family):
+    """SURVEY.md 8(f) rank 4 (streaming, stateful LSTM): streaming.MagStream fed with chunks of arbitrary sizes -- smaller
+    than a hop, a few frames, hundreds of frames -- returns, concatenated, the offline decode of the whole clips
+    (CRN/crn_decode.py:38-57 / LSTM/lstm_decode_vb.py:35-52) for 3 parallel streams; and the offline decode equals the
+    oracle."""
+    dev = _dev()
+    import se_b200
+    cls, tmpl, enh_name, oenh, kw, gain = RAGGED_FAMILIES[family]
+    sd = synth.synthetic_state_dict(tmpl(), seed=0, gain=gain)
+    model = getattr(se_b200, cls)()
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    n = 16000 + 37
+    wav = torch.from_numpy(synth.noisy_batch(3, n, first_index=120)).to(dev)
+    taps = {}
+    want = getattr(se_b200.decode, enh_name)(model, wav, taps=taps, **kw)
+    c, inv_c = se_b200.ops.rms_scale(wav)
+    st = se_b200.streaming.MagStream(model, c, inv_c)
+    cuts = [0, 100, 150, 700, 701, 2300, 2301, 2460, 9000, 9010, 15990, n]
+    parts = [st.push(wav[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    parts.append(st.flush())
+    got = torch.cat(parts, 1)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert sum(p.shape[1] > 0 for p in parts[:-1]) >= 6          # output really arrives incrementally
+    d = (got - want).abs().max().item()
+    rel = d / want.abs().max().item()
+    _, to = oenh(sd, wav[1].cpu().numpy().astype(np.float64), **kw)
+    e = np.sqrt(np.mean((got[1].cpu().numpy() * float(c[1]) - to["y_norm"]) ** 2))
+    print(f"streaming {family}: {len(parts)} pieces, max |stream - offline| {d:.2e} (rel {rel:.2e}); vs oracle RMS {e:.3e}")
+    assert rel <= 2e-5 and e <= RMS_GATE
+
+
 def _crn_weight_blob(sd):
     """Reference state-dict tensors in the order of se_crn_weights (tests/c_host/crn_plan_host.c)."""
     keys = [f"en.en_module.{i}.1.weight" for i in range(5)] + [f"en.en_module.{i}.1.bias" for i in range(5)]
