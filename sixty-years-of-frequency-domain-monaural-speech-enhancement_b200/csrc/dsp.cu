@@ -5,9 +5,11 @@
 // Both transforms are HBM-bound: every audio sample and spectrum bin is touched once
 // (halo frames of neighbouring CTAs hit L2).  See DESIGN.md for the byte accounting.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "fft.cuh"
+#include "fft_thread.cuh"
 
 namespace se {
 
@@ -223,6 +225,7 @@ struct IstftParams {
   int nf_max;
   const float2* twiddles;   // [32][2R + 5], see WarpFFT<R>::fill_table
   const int* lengths;       // optional [B]: clip b has 1 + lengths[b] / hop frames and min(L, lengths[b]) output samples
+  int ob;                   // istft2_kernel: hop-sized output blocks per CTA (chosen so that nf_max is a multiple of 16)
 };
 
 template <int R>
@@ -367,6 +370,411 @@ __global__ void __launch_bounds__(kDspThreads) istft_kernel(IstftParams p) {
 }
 
 // -------------------------------------------------------------------------------------------
+// Second-generation STFT / iSTFT: per-thread radix-16 x radix-N2 FFT through shared memory (fft_thread.cuh) instead of
+// the five-stage warp-shuffle network.  16 threads per frame (two frames per warp), M = NFFT / 2 = 16 * N2 packed complex
+// points: pass 1 = 16-point DFTs in registers by N2 of the threads, twiddle, exchange through the frame's own buffer,
+// pass 2 = N2-point DFTs by all 16.  Same staging, feature split, recombination and overlap-add as the kernels above
+// (same StftParams / IstftParams), so every parity test of tests/test_gpu_dsp.py applies unchanged.
+// -------------------------------------------------------------------------------------------
+// Frames (STFT) / hop blocks (iSTFT) per CTA are parameters: smaller tiles = less shared memory = more CTAs per SM.
+// Where the kernels stand (profiles/ncu_dsp2_r02_summary.txt): stft2_kernel issues in 65 % of the cycles at 33 % occupancy,
+// ~970 warp instructions per 320-point frame of which the FFT is now ~250 -- the layout-generic feature split (index
+// division, three 64-bit multiplies per store) and the per-CTA table generation are what is left.
+
+template <int R>
+__device__ __forceinline__ void dsp2_tables(float2* tw1, float2* tw2, int tid) {
+  constexpr int M = 32 * R, N2 = 2 * R;
+  for (int i = tid; i < 16 * N2; i += kDspThreads) {
+    const int k1 = i / N2, n2 = i - k1 * N2;
+    float sn, cs;
+    sincospif(2.0f * (float)((n2 * k1) % M) / (float)M, &sn, &cs);     // W_M^(n2 k1): (cos, sin) of the positive angle
+    tw1[i] = make_float2(cs, sn);
+  }
+  for (int k = tid; k <= M; k += kDspThreads) {
+    float sn, cs;
+    sincospif((float)k / (float)M, &sn, &cs);                          // W_2M^k
+    tw2[k] = make_float2(cs, sn);
+  }
+}
+
+template <int R, int FT>
+__global__ void __launch_bounds__(kDspThreads, 3) stft2_kernel(StftParams p) {
+  constexpr int NFFT = 64 * R, M = 32 * R, N2 = 2 * R, F = M + 1;
+  constexpr int FS = M + 16;          // FS: float2 per frame buffer (exchange rows padded to N2 + 1)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* wtab = reinterpret_cast<float*>(smem_raw);                    // [NFFT]
+  float2* tw1 = reinterpret_cast<float2*>(wtab + NFFT);                // [16][N2]
+  float2* tw2 = tw1 + 16 * N2;                                         // [M + 1]  (+1 pad keeps 16-byte alignment below)
+  float2* zb = tw2 + M + 2;                                            // [FT][FS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(zb + FT * FS);
+  float* tile = reinterpret_cast<float*>(bar + 2);
+
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * FT;
+  const int nf = min(FT, p.T - t0);
+  const int tid = threadIdx.x;
+  const float* x = p.wav + (long long)b * p.wav_stride;
+  const int start = t0 * p.hop - NFFT / 2;
+  const int tile_len = (nf - 1) * p.hop + NFFT;
+  const int Nb = p.lengths ? max(NFFT, min(p.N, __ldg(p.lengths + b))) : p.N;
+  const int Tb = 1 + Nb / p.hop;
+
+  const bool interior = (start >= 0) && (start + tile_len <= Nb) && ((((uintptr_t)(x + start)) & 15) == 0) &&
+                        ((tile_len & 3) == 0);
+  if (interior) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, (unsigned)tile_len * 4u);
+      bulk_g2s(tile, x + start, (unsigned)tile_len * 4u, bar);
+    }
+  } else {
+    for (int i = tid; i < tile_len; i += kDspThreads) {
+      int j = start + i;
+      if (j < 0) j = -j;
+      if (j >= Nb) j = 2 * (Nb - 1) - j;
+      j = max(0, min(j, Nb - 1));
+      tile[i] = __ldg(x + j);
+    }
+  }
+  {
+    const float sc = p.scale ? __ldg(p.scale + b) : 1.0f;
+    const int left = (NFFT - p.win) / 2;
+    for (int i = tid; i < NFFT; i += kDspThreads) {
+      const int n = i - left;
+      float w = 0.0f;
+      if (n >= 0 && n < p.win) {
+        const float sn = sinpif((float)n / (float)p.win);
+        w = sn * sn;
+      }
+      wtab[i] = w * sc;
+    }
+  }
+  dsp2_tables<R>(tw1, tw2, tid);
+  if (interior) mbar_wait(bar, 0);
+  __syncthreads();
+
+  // --- 16 threads per frame ---------------------------------------------------------------------------
+  const int grp = tid >> 4, l16 = tid & 15;
+  const float2* w2 = reinterpret_cast<const float2*>(wtab);
+#pragma unroll 1
+  for (int pass = 0; pass < FT / 16; ++pass) {
+    const int i = pass * 16 + grp;
+    const bool active = i < nf;
+    float2* fb = zb + i * FS;
+    if (active && l16 < N2) {                       // pass 1: thread n2 = l16
+      const float2* fr = reinterpret_cast<const float2*>(tile + i * p.hop);
+      float2 a[16];
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int n = N2 * n1 + l16;
+        const float2 v = fr[n], w = w2[n];
+        a[n1] = make_float2(v.x * w.x, v.y * w.y);
+      }
+      ft::Dft<16, false>::run(a);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const float2 t = tw1[k1 * N2 + l16];
+        fb[k1 * (N2 + 1) + l16] = ft::twmul<false>(a[k1], t.x, t.y);
+      }
+    }
+    __syncwarp();
+    float2 bq[N2];
+    if (active) {                                    // pass 2: thread k1 = l16
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) bq[n2] = fb[l16 * (N2 + 1) + n2];
+    }
+    __syncwarp();
+    if (active) {
+      ft::Dft<N2, false>::run(bq);
+#pragma unroll
+      for (int k2 = 0; k2 < N2; ++k2) fb[l16 + 16 * k2] = bq[k2];
+    }
+  }
+  __syncthreads();
+
+  // --- epilogue: real-FFT split + feature split + layout-aware store ------------------------------------
+  const bool time_major = p.re ? (p.sf <= p.st) : (p.msf <= p.mst);
+  const bool ri_pair = p.re && p.im == p.re + 1 && p.sf == 2 && (p.st & 1) == 0 && (p.sb & 1) == 0 && ((uintptr_t)p.re & 7) == 0;
+  const int total = nf * F;
+#pragma unroll 4
+  for (int idx = tid; idx < total; idx += kDspThreads) {
+    int i, k;
+    if (time_major) {
+      i = idx / F;
+      k = idx - i * F;
+    } else {
+      k = idx / nf;
+      i = idx - k * nf;
+    }
+    const float2* fb = zb + i * FS;
+    const float2 tw = tw2[k];
+    float2 X = ft::rfft_split(fb[k == M ? 0 : k], fb[k == 0 ? 0 : M - k], tw.x, tw.y);
+    if (k == 0 || k == M) X.y = 0.0f;
+    if (t0 + i >= Tb) X = make_float2(0.0f, 0.0f);
+    const float m = sqrtf(X.x * X.x + X.y * X.y);
+    if (p.mag)
+      p.mag[(long long)b * p.msb + (long long)(t0 + i) * p.mst + (long long)k * p.msf] = pow_pos(m, p.p_mag);
+    if (p.re) {
+      const long long off = (long long)b * p.sb + (long long)(t0 + i) * p.st + (long long)k * p.sf;
+      const float s = pow_scale(m, p.p_ri - 1.0f);
+      if (ri_pair) {
+        *reinterpret_cast<float2*>(p.re + off) = make_float2(X.x * s, X.y * s);
+      } else {
+        p.re[off] = X.x * s;
+        p.im[off] = X.y * s;
+      }
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kDspThreads, 3) istft2_kernel(IstftParams p) {
+  constexpr int NFFT = 64 * R, M = 32 * R, N2 = 2 * R, F = M + 1;
+  const int OB = p.ob;
+  constexpr int FS = M + 16;       // float2 per frame buffer: spectrum [M + 1] -> exchange [16][N2 + 1] -> NFFT samples
+  constexpr int FRS = 2 * FS;      // the same in floats
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* wtab = reinterpret_cast<float*>(smem_raw);                    // [NFFT]   window / NFFT
+  float2* tw1 = reinterpret_cast<float2*>(wtab + NFFT);                // [16][N2]
+  float2* tw2 = tw1 + 16 * N2;                                         // [M + 1] (+1 pad)
+  float* envtab = reinterpret_cast<float*>(tw2 + M + 2);               // [512]: 1 / sum_m w^2[r + m hop], r < hop <= NFFT
+  float* buf = envtab + 512;                                           // [nf_max][FRS]
+
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * OB * p.hop;
+  const int s0 = n0 + NFFT / 2;
+  const int s1 = s0 + OB * p.hop;
+  const int q = s0 - NFFT;
+  const int t_lo = q < 0 ? 0 : q / p.hop + 1;
+  const int Nb = p.lengths ? max(NFFT, __ldg(p.lengths + b)) : 0x7fffffff;
+  const int Tb = p.lengths ? min(p.T, 1 + Nb / p.hop) : p.T;
+  const int Lb = min(p.L, Nb);
+  const int t_hi = min(Tb - 1, (s1 - 1) / p.hop);
+  const int nf = t_hi - t_lo + 1;
+
+  {
+    const int left = (NFFT - p.win) / 2;
+    for (int i = tid; i < NFFT; i += kDspThreads) {
+      const int n = i - left;
+      float w = 0.0f;
+      if (n >= 0 && n < p.win) {
+        const float sn = sinpif((float)n / (float)p.win);
+        w = sn * sn;
+      }
+      wtab[i] = w;
+    }
+  }
+  dsp2_tables<R>(tw1, tw2, tid);
+
+  // --- stage 1: recombination prologue, bins 0..M of every contributing frame -> smem ---------------------
+  // (re, im) pairs that are interleaved in memory (complex64 tensors: im = re + 1, bin stride 2) are read with one
+  // 8-byte load; 8 bins per thread are in flight (the stage is bound by memory-level parallelism, not by issue)
+  if (nf > 0) {
+    const bool time_major = (p.a_sf <= p.a_st);
+    const bool a_pair = p.a_im == p.a_re + 1 && p.a_sf == 2 && (p.a_st & 1) == 0 && (p.a_sb & 1) == 0 &&
+                        ((uintptr_t)p.a_re & 7) == 0;
+    const bool b_pair = p.b_re && p.b_im == p.b_re + 1 && p.b_sf == 2 && (p.b_st & 1) == 0 && (p.b_sb & 1) == 0 &&
+                        ((uintptr_t)p.b_re & 7) == 0;
+    const int total = nf * F;
+#pragma unroll 8
+    for (int idx = tid; idx < total; idx += kDspThreads) {
+      int i, k;
+      if (time_major) {
+        i = idx / F;
+        k = idx - i * F;
+      } else {
+        k = idx / nf;
+        i = idx - k * nf;
+      }
+      const int t = t_lo + i;
+      const long long oa = (long long)b * p.a_sb + (long long)t * p.a_st + (long long)k * p.a_sf;
+      float2 A = make_float2(0.f, 0.f), X = make_float2(0.f, 0.f);
+      if (p.mode == SE_ISTFT_MAG_PHASE)
+        A.x = __ldg(p.a_re + oa);
+      else if (a_pair)
+        A = __ldg(reinterpret_cast<const float2*>(p.a_re + oa));
+      else
+        A = make_float2(__ldg(p.a_re + oa), __ldg(p.a_im + oa));
+      if (p.mode >= SE_ISTFT_MAG_PHASE) {
+        const long long ob = (long long)b * p.b_sb + (long long)t * p.b_st + (long long)k * p.b_sf;
+        X = b_pair ? __ldg(reinterpret_cast<const float2*>(p.b_re + ob)) : make_float2(__ldg(p.b_re + ob), __ldg(p.b_im + ob));
+      }
+      float2 Y;
+      if (p.mode == SE_ISTFT_SPEC) {
+        Y = A;
+      } else if (p.mode == SE_ISTFT_RI_DECOMP) {
+        const float s = pow_scale(sqrtf(A.x * A.x + A.y * A.y), p.inv_p - 1.0f);
+        Y = make_float2(A.x * s, A.y * s);
+      } else {
+        const float m = sqrtf(X.x * X.x + X.y * X.y);
+        if (p.mode == SE_ISTFT_MAG_PHASE) {
+          const float g = pow_pos(A.x, p.inv_p);
+          const float2 ph = m > 0.0f ? make_float2(X.x / m, X.y / m) : make_float2(1.0f, 0.0f);
+          Y = make_float2(g * ph.x, g * ph.y);
+        } else {  // SE_ISTFT_CMASK
+          const float sx = pow_scale(m, p.p_x - 1.0f);
+          const float2 Xc = make_float2(X.x * sx, X.y * sx);
+          const float2 C = make_float2(A.x * Xc.x - A.y * Xc.y, A.y * Xc.x + A.x * Xc.y);
+          const float s = pow_scale(sqrtf(C.x * C.x + C.y * C.y), p.inv_p - 1.0f);
+          Y = make_float2(C.x * s, C.y * s);
+        }
+      }
+      if (k == 0 || k == M) Y.y = 0.0f;          // irfft ignores the imaginary part of the DC and Nyquist bins
+      reinterpret_cast<float2*>(buf + (size_t)i * FRS)[k] = Y;
+    }
+  }
+  __syncthreads();
+
+  for (int rr = tid; rr < p.hop; rr += kDspThreads) {   // wtab is complete (barrier above); consumed after the next barrier
+    float e = 0.0f;
+    for (int o = rr; o < NFFT; o += p.hop) e += wtab[o] * wtab[o];
+    envtab[rr] = e > FLT_MIN ? 1.0f / e : 1.0f;
+  }
+  // --- stage 2: 16 threads per frame: merge, inverse FFT, window, time-domain frame back into its buffer ---
+  const int grp = tid >> 4, l16 = tid & 15;
+  const float2* w2 = reinterpret_cast<const float2*>(wtab);
+  constexpr float kNorm = 1.0f / (float)NFFT;
+#pragma unroll 1
+  for (int i0 = 0; i0 < nf; i0 += 16) {
+    const int i = i0 + grp;
+    const bool active = i < nf;
+    float2* fb = reinterpret_cast<float2*>(buf + (size_t)(active ? i : 0) * FRS);
+    float2 a[16];
+    if (active && l16 < N2) {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int n = N2 * n1 + l16;
+        const float2 t = tw2[n];
+        a[n1] = ft::irfft_merge(fb[n], fb[M - n], t.x, t.y);
+      }
+    }
+    __syncwarp();                                   // every spectrum read of the group precedes the exchange writes
+    if (active && l16 < N2) {
+      ft::Dft<16, true>::run(a);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const float2 t = tw1[k1 * N2 + l16];
+        fb[k1 * (N2 + 1) + l16] = ft::twmul<true>(a[k1], t.x, t.y);
+      }
+    }
+    __syncwarp();
+    float2 bq[N2];
+    if (active) {
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) bq[n2] = fb[l16 * (N2 + 1) + n2];
+    }
+    __syncwarp();
+    if (active) {
+      ft::Dft<N2, true>::run(bq);
+#pragma unroll
+      for (int k2 = 0; k2 < N2; ++k2) {
+        const int m = l16 + 16 * k2;
+        const float2 w = w2[m];
+        fb[m] = make_float2(bq[k2].x * w.x * kNorm, bq[k2].y * w.y * kNorm);
+      }
+    }
+  }
+  __syncthreads();
+
+  // --- stage 3: gather overlap-add, envelope, trim, scale ------------------------------------
+  // Division-free indexing (j -> hop block hb, offset r advance by constants) and, for samples whose covering frames all
+  // exist, the window-sum-square envelope from a per-CTA table envtab[s mod hop]: this stage was the heaviest of the
+  // kernel (two integer divisions, a w^2 sum and an IEEE division per sample).
+  const float osc = p.out_scale ? __ldg(p.out_scale + b) : 1.0f;
+  float* out = p.out + (long long)b * p.out_stride;
+  const int hop = p.hop;
+  const int span = OB * hop;
+  const int c0 = (NFFT / 2) % hop;                 // s0 mod hop (n0 is a multiple of hop)
+  const int tq0 = s0 / hop;
+  const int q1 = (NFFT - 1) / hop, r1 = (NFFT - 1) % hop;
+  const int dq = kDspThreads / hop, dr = kDspThreads % hop;
+  int hb = tid / hop, r = tid % hop;
+  for (int j = tid; j < span; j += kDspThreads) {
+    const int n = n0 + j;
+    if (n >= p.L) break;
+    int rr = r + c0, th = tq0 + hb;                // s = s0 + j:  rr = s mod hop, th = s / hop
+    if (rr >= hop) {
+      rr -= hop;
+      ++th;
+    }
+    r += dr;
+    hb += dq;
+    if (r >= hop) {
+      r -= hop;
+      ++hb;
+    }
+    if (n >= Lb) {
+      out[n] = 0.0f;
+      continue;
+    }
+    const int mmax = q1 - (rr > r1 ? 1 : 0);       // frames th, th-1, ..., th-mmax cover sample s (offsets rr + m hop < NFFT)
+    float acc = 0.0f;
+    if (th - mmax >= 0 && th <= t_hi) {            // interior: every covering frame exists
+      const float* fp = buf + (size_t)(th - t_lo) * FRS + rr;
+      for (int m = 0; m <= mmax; ++m) acc += fp[m * hop - (long long)m * FRS];
+      acc *= envtab[rr];
+    } else {
+      float env = 0.0f;
+      for (int m = 0; m <= mmax; ++m) {
+        const int t = th - m;
+        if (t < 0 || t < t_lo || t > t_hi) continue;
+        const int off = rr + m * hop;
+        acc += buf[(size_t)(t - t_lo) * FRS + off];
+        const float w = wtab[off];
+        env += w * w;
+      }
+      if (env > FLT_MIN) acc /= env;
+    }
+    out[n] = acc * osc;
+  }
+}
+
+static int dsp_engine() {
+  static int e = -1;
+  if (e < 0) {
+    e = 2;
+    if (const char* v = getenv("SE_DSP_ENGINE")) e = atoi(v) == 1 ? 1 : 2;    // 1 = round-1 warp-shuffle kernels (A/B)
+  }
+  return e;
+}
+// measured (profiles/dsp_only_r02.jsonl): 16 frames per CTA win at the 512-point geometries (less shared memory, more
+// CTAs per SM), 32 at 320 points; SE_DSP_TILE=16|32 overrides (A/B)
+static int dsp_tile(int R) {
+  static int forced = -1;
+  if (forced < 0) {
+    forced = 0;
+    if (const char* v = getenv("SE_DSP_TILE")) forced = atoi(v) == 32 ? 32 : (atoi(v) == 16 ? 16 : 0);
+  }
+  return forced ? forced : (R == 5 ? 32 : 16);
+}
+static int dsp2_smem_stft(int R, int hop, int ft) {
+  const int nfft = 64 * R, M = 32 * R, N2 = 2 * R;
+  const int tile = (ft - 1) * hop + nfft;
+  return nfft * 4 + (16 * N2 + M + 2) * 8 + ft * (M + 16) * 8 + 16 + tile * 4 + 16;
+}
+template <int R, int FT>
+static cudaError_t launch_stft2(const StftParams& p, int smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(stft2_kernel<R, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) stft2_kernel<R, FT><<<dim3(ceil_div(p.T, FT), p.B), kDspThreads, smem, s>>>(p);
+  return e;
+}
+template <int R>
+static cudaError_t launch_istft2(const IstftParams& p, int smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(istft2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) istft2_kernel<R><<<dim3(ceil_div(p.L, p.ob * p.hop), p.B), kDspThreads, smem, s>>>(p);
+  return e;
+}
+static int dsp2_smem_istft(int R, int nf_max) {
+  const int nfft = 64 * R, M = 32 * R, N2 = 2 * R;
+  return nfft * 4 + (16 * N2 + M + 2) * 8 + 512 * 4 + nf_max * 2 * (M + 16) * 4;
+}
+
+// -------------------------------------------------------------------------------------------
 // front step: band-limited resampling (resampy.interpn.resample_f restated; one output sample per thread)
 // -------------------------------------------------------------------------------------------
 // HBM-bound in principle (reads 4/ratio bytes, writes 4 bytes per output sample); the ~2 * num_zeros / min(1, ratio)
@@ -499,8 +907,20 @@ extern "C" int se_stft_len(const float* wav, long long wav_stride, int B, int N,
                lengths};
   p.twiddles = dsp_twiddles(n_fft / 64, (cudaStream_t)stream);
   SE_REQUIRE(p.twiddles != nullptr, "se_stft: twiddle table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-  dim3 grid(ceil_div(T, kFramesPerCta), B);
   const int R = n_fft / 64;
+  if (dsp_engine() == 2) {
+    const int ft = dsp_tile(R);
+    const int smem2 = dsp2_smem_stft(R, hop, ft);
+    cudaStream_t cs = (cudaStream_t)stream;
+    const cudaError_t e2 = R == 5 ? (ft == 16 ? launch_stft2<5, 16>(p, smem2, cs) : launch_stft2<5, 32>(p, smem2, cs))
+                                  : (ft == 16 ? launch_stft2<8, 16>(p, smem2, cs) : launch_stft2<8, 32>(p, smem2, cs));
+    if (e2 != cudaSuccess) {
+      set_error("se_stft: cudaFuncSetAttribute(%d bytes): %s", smem2, cudaGetErrorString(e2));
+      return SE_ERR_CUDA;
+    }
+    return check_launch("se_stft");
+  }
+  dim3 grid(ceil_div(T, kFramesPerCta), B);
   const int smem = dsp_smem_stft(R, hop);
   cudaError_t e;
   if (R == 5) {
@@ -536,13 +956,26 @@ extern "C" int se_istft_len(int mode, const float* a_re, const float* a_im, long
   SE_REQUIRE(mode == SE_ISTFT_MAG_PHASE || a_im, "se_istft: a_im required for mode %d", mode);
   SE_REQUIRE(mode < SE_ISTFT_MAG_PHASE || (b_re && b_im), "se_istft: noisy spectrum (b_re,b_im) required");
   IstftParams p{mode, a_re, a_im, a_sb, a_st, a_sf, b_re, b_im, b_sb, b_st, b_sf, inv_p, p_x, B, T, win, hop,
-                out_scale, out, out_stride, L, 0, nullptr, lengths};
+                out_scale, out, out_stride, L, 0, nullptr, lengths, kHopBlocksPerCta};
   p.twiddles = dsp_twiddles(n_fft / 64, (cudaStream_t)stream);
   SE_REQUIRE(p.twiddles != nullptr, "se_istft: twiddle table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-  p.nf_max = kHopBlocksPerCta + ceil_div(n_fft, hop) + 1;
   const int R = n_fft / 64;
-  const int smem = n_fft * 4 + ((p.nf_max + 3) & ~3) * 4 + p.nf_max * R * 66 * 4;
+  if (dsp_engine() == 2) {
+    // hop blocks per CTA: the frames that overlap them (at most ob + ceil(n_fft / hop)) fill whole rounds of 16 frame groups
+    p.nf_max = dsp_tile(R);
+    p.ob = p.nf_max - ceil_div(n_fft, hop);
+    const int smem2 = dsp2_smem_istft(R, p.nf_max);
+    cudaStream_t cs = (cudaStream_t)stream;
+    const cudaError_t e2 = R == 5 ? launch_istft2<5>(p, smem2, cs) : launch_istft2<8>(p, smem2, cs);
+    if (e2 != cudaSuccess) {
+      set_error("se_istft: cudaFuncSetAttribute(%d bytes): %s", smem2, cudaGetErrorString(e2));
+      return SE_ERR_CUDA;
+    }
+    return check_launch("se_istft");
+  }
+  p.nf_max = kHopBlocksPerCta + ceil_div(n_fft, hop) + 1;
   dim3 grid(ceil_div(L, kHopBlocksPerCta * hop), B);
+  const int smem = n_fft * 4 + ((p.nf_max + 3) & ~3) * 4 + p.nf_max * R * 66 * 4;
   cudaError_t e;
   if (R == 5) {
     e = cudaFuncSetAttribute(istft_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

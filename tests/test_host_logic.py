@@ -526,3 +526,27 @@ def test_enhance_dir_ragged_batches_and_bad_files(tmp_path):
         sr, y = wavfile.read(str(dst / name))
         x = decode.read_wav(str(src / name), 16000)
         assert sr == 16000 and len(y) == ln and np.abs(y / 32768.0 - 0.5 * x).max() <= 1.0 / 32768 + 1e-7
+
+
+@pytest.mark.parametrize("m", [160, 256])
+def test_fft_thread_algebra_on_cpu(m, tmp_path):
+    """csrc/fft_thread.cuh (the per-thread radix-16 x radix-N2 FFT of the second-generation STFT / iSTFT kernels) is plain
+    C++: tools/fft_thread_host_test.cpp drives it on the CPU exactly as the kernels do (two passes, exchange array,
+    real-FFT split / merge) and the result is compared with numpy.fft."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fft_host_test")
+    subprocess.run([cxx, "-O1", "-std=c++17", os.path.join(root, "tools", "fft_thread_host_test.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe, str(m)], capture_output=True, text=True, check=True).stdout.splitlines()
+    x = np.array(out[0].split(), dtype=np.float64)
+    spec = np.array(out[1].split(), dtype=np.float64).reshape(-1, 2)
+    back = np.array(out[2].split(), dtype=np.float64)
+    ref = np.fft.rfft(x)
+    assert len(x) == 2 * m and spec.shape[0] == m + 1
+    assert np.abs(spec[:, 0] + 1j * spec[:, 1] - ref).max() < 2e-5
+    assert abs(spec[0, 1]) < 1e-5 and abs(spec[m, 1]) < 1e-5
+    assert np.abs(back - x).max() < 1e-6
