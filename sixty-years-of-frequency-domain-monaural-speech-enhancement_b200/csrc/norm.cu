@@ -344,6 +344,75 @@ __global__ void __launch_bounds__(NT) chan_norm_kernel(const NormParams p) {
 }
 
 
+// pass 2 with the ShareSepConv FIR (CTSNet TCM branches, Step1_network.py:127-157): y[t] = sum_k w[k] z[t - (K-1) + k] on the
+// NORMALISED signal z.  The scalar kernel above re-normalises every tap of every output from global memory (K up to 63:
+// 225 us per call on a 13 MB slab, 17 % of CTSNet).  Here a CTA owns FIR_TT output rows of one clip: the normalised rows
+// [t0 - (K-1), t0 + FIR_TT) are computed ONCE into shared memory (4 channels per thread, 16-byte loads), then every thread
+// accumulates FIR_TT * C / 256 outputs of one channel from shared memory.
+constexpr int FIR_TT = 32;
+__global__ void __launch_bounds__(NT) chan_norm_fir_kernel(const NormParams p) {
+  extern __shared__ __align__(16) float fir_smem[];
+  const int C = p.C, K = p.fir_k, C4 = C >> 2;
+  float* z = fir_smem;                         // [FIR_TT + K - 1][C]
+  float* wsm = z + (size_t)(FIR_TT + K - 1) * C;   // [fir_groups][K]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const long long t0 = (long long)blockIdx.x * FIR_TT;
+  const int nz = FIR_TT + K - 1;
+  for (int i = tid; i < p.fir_groups * K; i += NT) wsm[i] = __ldg(p.fir_w + i);
+  for (int i = tid; i < nz * C4; i += NT) {
+    const int j = i / C4, c = 4 * (i - j * C4);
+    const long long r = t0 - (K - 1) + j;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0 && r < p.rows) {
+      float v[4];
+      pre_value4(p.x + ((long long)b * p.rows + r) * p.Cin, c, p.Cin, C, p.pre, p.pre_slope, v);
+      float m[4], rs[4];
+      if (p.stat_mode == SE_NORM_STAT_INSTANCE) {
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mean + (long long)b * C + c));
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.rstd + (long long)b * C + c));
+        m[0] = m4.x, m[1] = m4.y, m[2] = m4.z, m[3] = m4.w;
+        rs[0] = r4.x, rs[1] = r4.y, rs[2] = r4.z, rs[3] = r4.w;
+      } else {                                 // cumulative statistics, one row per frame (rows_per_t == 1)
+        const long long si = ((long long)b * p.rows + r) * p.stat_groups + c / (C / p.stat_groups);
+        const float mm = __ldg(p.mean + si), rr = __ldg(p.rstd + si);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m[e] = mm, rs[e] = rr;
+      }
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+      o.x = (v[0] - m[0]) * rs[0] * g4.x + b4.x;
+      o.y = (v[1] - m[1]) * rs[1] * g4.y + b4.y;
+      o.z = (v[2] - m[2]) * rs[2] * g4.z + b4.z;
+      o.w = (v[3] - m[3]) * rs[3] * g4.w + b4.w;
+    }
+    *reinterpret_cast<float4*>(z + (size_t)j * C + c) = o;
+  }
+  __syncthreads();
+  // thread = (channel c, row lane): rows lane, lane + L, ... of the tile (L = NT / C row lanes)
+  const int L = NT / C, c = tid % C, lane = tid / C;
+  const float* w = wsm + (c / (C / p.fir_groups)) * K;
+  constexpr int MAXO = 16;                     // FIR_TT / L outputs per thread (C >= 64: L <= 4 -> <= 8 ... C = 128: 16)
+  float acc[MAXO];
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) acc[o] = 0.f;
+  const int no = FIR_TT / L;                   // <= MAXO (host checks)
+  for (int k = 0; k < K; ++k) {
+    const float wk = w[k];
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o)
+      if (o < no) acc[o] = fmaf(wk, z[(size_t)(lane * no + o + k) * C + c], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) {
+    if (o >= no) break;
+    const long long r = t0 + lane * no + o;
+    if (r >= p.rows) break;
+    const long long i = ((long long)b * p.rows + r) * C + c;
+    if (p.out) p.out[i] = acc[o];
+    if (p.out_hi) split_tf32_dev(acc[o], p.out_hi[i], p.out_lo[i]);
+  }
+}
+
 // pass 2 without FIR, 4 channels per thread (C, Cin, C / stat_groups multiples of 4)
 __global__ void __launch_bounds__(NT) chan_norm_vec_kernel(const NormParams p) {
   const int C4 = p.C >> 2;
@@ -574,7 +643,19 @@ extern "C" int se_chan_norm(const float* x, int B, long long rows, int Cin, int 
                    (stat_mode == SE_NORM_STAT_INSTANCE || ((C / stat_groups) & 3) == 0) && al16(x) && al16(pre_slope) &&
                    al16(mean) && al16(rstd) && al16(gamma) && al16(beta) && al16(post_slope) && al16(out) && al16(out_hi) &&
                    al16(out_lo);
-  if (vec)
+  // tiled FIR kernel: channels divide the block, FIR_TT / (NT / C) outputs per thread fit its accumulators
+  const bool fir_tiled = post == SE_NORM_POST_FIR && (C & 3) == 0 && (Cin & 3) == 0 && NT % C == 0 && FIR_TT % (NT / C) == 0 &&
+                         FIR_TT / (NT / C) <= 16 && (stat_mode == SE_NORM_STAT_INSTANCE || ((C / stat_groups) & 3) == 0) &&
+                         al16(x) && al16(pre_slope) && al16(mean) && al16(rstd) && al16(gamma) && al16(beta);
+  const size_t fir_smem_bytes = ((size_t)(FIR_TT + fir_k - 1) * C + (size_t)fir_groups * fir_k) * sizeof(float);
+  if (fir_tiled && fir_smem_bytes <= 200 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(chan_norm_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes);
+    if (e != cudaSuccess) {
+      set_error("se_chan_norm: %zu bytes of shared memory: %s", fir_smem_bytes, cudaGetErrorString(e));
+      return SE_ERR_CUDA;
+    }
+    chan_norm_fir_kernel<<<dim3((unsigned)((rows + FIR_TT - 1) / FIR_TT), (unsigned)B), NT, fir_smem_bytes, (cudaStream_t)stream>>>(p);
+  } else if (vec)
     chan_norm_vec_kernel<<<grid_for((long long)B * rows * (C / 4)), NT, 0, (cudaStream_t)stream>>>(p);
   else
     chan_norm_kernel<<<grid_for((long long)B * rows * C), NT, 0, (cudaStream_t)stream>>>(p);
