@@ -349,6 +349,10 @@ struct ConvRowsParams {
   int ndt;
   int dtv[kRowsMaxDt];          // distinct time offsets of the taps
   int tap_dti[SE_MAX_TAPS];     // tap -> index into dtv
+  // blockIdx.y = chunk of fc output columns: only the input columns [fo*sf + dfmin, fo*sf + dfmax] of the chunk are staged,
+  // so a CTA needs tens of KB instead of a whole frame per time offset and several CTAs share an SM (one stages while
+  // another computes; with whole frames -- 164 KB at Fin = 80, C = 256 -- the two phases of the only resident CTA were serial)
+  int fc, dfmin, dfmax, nin_max;
 };
 
 template <int NCO>
@@ -357,8 +361,11 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvRowsParams R) 
   const ConvParams& P = R.c;
   const se_conv_desc& d = P.d;
   const int Ct = P.Ctot;
-  float* rows = smem_rows;                                   // [ndt][Fin][Ct]
-  float* wsm = rows + (size_t)R.ndt * d.Fin * Ct;            // [K][NCO]
+  const int f_lo = blockIdx.y * R.fc, f_hi = min(d.Fout, f_lo + R.fc);          // output columns of this CTA
+  const int in_lo = max(0, f_lo * d.sf + R.dfmin), in_hi = min(d.Fin - 1, (f_hi - 1) * d.sf + R.dfmax);
+  const int nin = max(0, in_hi - in_lo + 1);                  // staged input columns [in_lo, in_hi]
+  float* rows = smem_rows;                                   // [ndt][nin_max][Ct]
+  float* wsm = rows + (size_t)R.ndt * R.nin_max * Ct;        // [K][NCO]
   const int bt = blockIdx.x;                                 // b * T + t
   const int t = bt % d.T;
   for (int i = threadIdx.x; i < P.K * NCO; i += blockDim.x) {
@@ -369,9 +376,9 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvRowsParams R) 
   for (int di = 0; di < R.ndt; ++di) {
     const int ti = t + R.dtv[di];
     const bool ok = ti >= 0 && ti < d.T;
-    const long long pos0 = (long long)(bt - t + ti) * d.Fin;
-    float4* dst = reinterpret_cast<float4*>(rows + (size_t)di * d.Fin * Ct);
-    for (int i = threadIdx.x; i < d.Fin * c4; i += blockDim.x) {
+    const long long pos0 = (long long)(bt - t + ti) * d.Fin + in_lo;
+    float4* dst = reinterpret_cast<float4*>(rows + (size_t)di * R.nin_max * Ct);
+    for (int i = threadIdx.x; i < nin * c4; i += blockDim.x) {
       const int f = i / c4, q = i - f * c4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok)
@@ -382,21 +389,22 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvRowsParams R) 
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int fo0 = warp * 4; fo0 < d.Fout; fo0 += nwarp * 4) {
+  for (int fo0 = f_lo + warp * 4; fo0 < f_hi; fo0 += nwarp * 4) {
     float acc[4][NCO];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int co = 0; co < NCO; ++co) acc[r][co] = 0.f;
     for (int tap = 0; tap < d.ntaps; ++tap) {
-      const float* xr = rows + (size_t)R.tap_dti[tap] * d.Fin * Ct;
+      const float* xr = rows + (size_t)R.tap_dti[tap] * R.nin_max * Ct;
       const float* wt = wsm + (size_t)tap * Ct * NCO;
       int fi[4];
       bool fok[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         fi[r] = (fo0 + r) * d.sf + d.df[tap];
-        fok[r] = fo0 + r < d.Fout && fi[r] >= 0 && fi[r] < d.Fin;
+        fok[r] = fo0 + r < f_hi && fi[r] >= 0 && fi[r] < d.Fin;
+        fi[r] -= in_lo;
       }
       for (int c = lane * 4; c < Ct; c += 128) {
         float wv[4 * NCO];
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvRowsParams R) 
         if (lane == r * NCO + co) mine = v;
       }
     const int r = lane / NCO, co = lane - r * NCO;
-    if (lane < 4 * NCO && fo0 + r < d.Fout && co < d.Cout) {
+    if (lane < 4 * NCO && fo0 + r < f_hi && co < d.Cout) {
       const float v = apply_act(mine + (d.bias ? __ldg(d.bias + co) : 0.f), d.act, d.act_param);
       d.dst[(((long long)bt * d.dstF) + d.dst_f0 + (long long)(fo0 + r) * d.dst_fstep) * d.Cout + co] = v;
     }
@@ -454,7 +462,17 @@ static int launch_conv_rows(const ConvParams& P, cudaStream_t s, int* rc) {
     }
     R.tap_dti[tap] = di;
   }
-  const size_t smem = ((size_t)R.ndt * d.Fin * P.Ctot + (size_t)P.K * NCO) * sizeof(float);
+  R.dfmin = R.dfmax = d.df[0];
+  for (int tap = 1; tap < d.ntaps; ++tap) {
+    R.dfmin = d.df[tap] < R.dfmin ? d.df[tap] : R.dfmin;
+    R.dfmax = d.df[tap] > R.dfmax ? d.df[tap] : R.dfmax;
+  }
+  // output columns per CTA: a multiple of 32 (8 warps x 4 columns) whose staged input fits ~64 KB, i.e. 3 CTAs per SM
+  R.fc = ((d.Fout + 31) / 32) * 32;
+  auto nin_of = [&](int fc) { return (fc - 1) * d.sf + (R.dfmax - R.dfmin) + 1; };
+  while (R.fc > 32 && (size_t)R.ndt * nin_of(R.fc) * P.Ctot * sizeof(float) > 64 * 1024) R.fc -= 32;
+  R.nin_max = nin_of(R.fc) < d.Fin ? nin_of(R.fc) : d.Fin;
+  const size_t smem = ((size_t)R.ndt * R.nin_max * P.Ctot + (size_t)P.K * NCO) * sizeof(float);
   if (smem > 200 * 1024) return 0;
   cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -462,7 +480,7 @@ static int launch_conv_rows(const ConvParams& P, cudaStream_t s, int* rc) {
     *rc = SE_ERR_CUDA;
     return 1;
   }
-  conv_rows_kernel<NCO><<<d.B * d.T, 256, smem, s>>>(R);
+  conv_rows_kernel<NCO><<<dim3((unsigned)(d.B * d.T), (unsigned)((d.Fout + R.fc - 1) / R.fc)), 256, smem, s>>>(R);
   *rc = SE_OK;
   return 1;
 }
