@@ -542,11 +542,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_mma_kernel(const Lst
 // 0: fp32 FMA kernel, 1: mma.sync 3xTF32 kernel, 2: tcgen05 cluster kernel (lstm_tc.cu) where it applies (H = 1024, one
 // group, clusters fit the device), the FMA kernel elsewhere; 3: as 2, plus the sequence-parallel kernel
 // (lstm_seq_small_kernel) for H = 128; 4 (default): as 3 with the fp16-pair / tagged-state tcgen05 kernel (lstm_f16.cu) at
-// H = 1024.
+// H = 1024; 5: as 4 with two independent half-batch chains per CTA (lstm_seq_f16_kernel<true>).
 // -1 = not chosen yet: SE_LSTM_ENGINE in the environment (A/B runs), else the default.
 static int g_lstm_engine = -1;
 constexpr int kDefaultLstmEngine = 4;
-constexpr int kMaxLstmEngine = 4;
+constexpr int kMaxLstmEngine = 5;
 static int lstm_engine() {
   if (g_lstm_engine < 0) {
     g_lstm_engine = kDefaultLstmEngine;
@@ -565,7 +565,7 @@ int lstm_seq_tc_launch(const float* xproj, long long xp_stride, const float* whh
 int lstm_f16_supported();
 void lstm_f16_set_profile(long long* dev_buf, int first_step, int nsteps);
 int lstm_seq_f16_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
-                        long long hs_sb, long long hs_st, float* work, cudaStream_t s);
+                        long long hs_sb, long long hs_st, float* work, int pingpong, cudaStream_t s);
 
 template <int KT>
 static cudaError_t launch_lstm_mma(const LstmParams& p, int G, cudaStream_t s) {
@@ -631,7 +631,7 @@ extern "C" int se_lstm_seq_multi(const float* xproj, long long xproj_stride, lon
     return SE_OK;
   }
   if (engine >= 4 && H == LT_H_PUBLIC && ngroups == 1 && lstm_f16_supported())
-    return lstm_seq_f16_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, s);
+    return lstm_seq_f16_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, engine >= 5 ? 1 : 0, s);
   if (engine >= 2 && H == LT_H_PUBLIC && ngroups == 1 && lstm_tc_supported())
     return lstm_seq_tc_launch(xproj, xproj_stride, whh, B, T, hseq, hseq_sb, hseq_st, work, sync, s);
   if (engine == 1 && (H == 1024 || H == 512 || H == 128)) {
@@ -661,8 +661,8 @@ extern "C" int se_debug_lstm_tc_profile(long long* dev_buf, int first_step, int 
 
 extern "C" int se_set_lstm_engine(int engine) {
   SE_REQUIRE(engine >= 0 && engine <= kMaxLstmEngine,
-             "se_set_lstm_engine: 0 (fp32 FMA), 1 (mma.sync 3xTF32), 2 (tcgen05 3xTF32), 3 (2 + sequence-parallel H = 128) or 4 (3 with "
-             "the fp16-pair tcgen05 kernel)");
+             "se_set_lstm_engine: 0 (fp32 FMA), 1 (mma.sync 3xTF32), 2 (tcgen05 3xTF32), 3 (2 + sequence-parallel H = 128), 4 (3 with "
+             "the fp16-pair tcgen05 kernel) or 5 (4 with two half-batch chains per CTA)");
   g_lstm_engine = engine;
   return SE_OK;
 }

@@ -184,6 +184,13 @@ __device__ __forceinline__ bool lf_tags_ok(const uint4& a, const uint4& b, unsig
 
 }  // namespace
 
+// PP = false: one chain per CTA (all eight epilogue warps work on all 64 batch rows).
+// PP = true ("ping-pong"): two independent chains per CTA, one per batch half -- warps 0-3 own rows 0..31, warps 4-7 rows
+// 32..63, each group loads, hands tiles to the MMA thread, reduces (signalled by cluster-scope mbarriers instead of
+// barrier.cluster, which would couple the groups), runs its gates and publishes on its own; the MMA thread serves
+// whichever group has a chunk ready.  While one half waits for the state exchange or the DSMEM reduction the other
+// half's loads / MMAs run: the per-step latency chain is the same length but two of them overlap.
+template <bool PP>
 __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -191,9 +198,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
   unsigned char* htile = base + LF_WLO_BYTES;                  // 4 chunks x [128 rows x 128 B]: rows 0..63 h_hi, 64..127 h_lo
   float* red = reinterpret_cast<float*>(htile + LF_HT_BYTES);  // [2 parities][4 src][64 b][32]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + LF_RED_BYTES);
-  uint64_t* full = bars;                // [LF_NCH]: chunk tiles written (the chunk's 2 loader warps arrive)
-  uint64_t* accfull = bars + LF_NCH;    // accumulators complete (tcgen05.commit)
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(accfull + 1);
+  uint64_t* full = bars;                // [LF_NCH] (PP: [2 groups][LF_NCH]): chunk tiles written by their loader warps
+  uint64_t* accfull = bars + 2 * LF_NCH;   // [2]: accumulators complete (tcgen05.commit)
+  uint64_t* redbar = accfull + 2;       // PP: [2 groups][2 parities]: the four sources' partial sums have landed
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(redbar + 4);
   unsigned* smax = tmem_slot + 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -204,8 +212,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
   const unsigned long long t0 = lf_timer_ns();
 
   if (tid == 0) {
-    for (int c = 0; c < LF_NCH; ++c) mbar_init(&full[c], LF_LOADERS / 32 / LF_NCH);
-    mbar_init(accfull, 1);
+    for (int c = 0; c < 2 * LF_NCH; ++c) mbar_init(&full[c], PP ? 1 : LF_LOADERS / 32 / LF_NCH);
+    mbar_init(&accfull[0], 1);
+    mbar_init(&accfull[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&redbar[i], 4);
     *smax = 0u;
     fence_barrier_init();
   }
@@ -269,6 +279,190 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
   lf_cluster_arrive();          // every CTA of the cluster is running before anyone touches remote smem
   lf_cluster_wait();
 
+  if constexpr (PP) {
+    if (warp == LF_MMA_WARP) {
+      // ===================== MMA issuer: serves the two groups as their chunks arrive =====================
+      constexpr unsigned idesc_wide = lf_idesc(128, LF_NB);        // [h_hi | h_lo] of 32 rows
+      constexpr unsigned idesc_n32 = lf_idesc(128, LF_NB / 2);
+      if (elect_one()) {
+        int tg[2] = {1, 1}, cg[2] = {0, 0};
+        unsigned idle = 0;
+        while (tg[0] < p.T || tg[1] < p.T) {
+          bool did = false;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (tg[g] >= p.T) continue;
+            const int c = cg[g];
+            if (!lf_mbar_try(&full[g * LF_NCH + c], (unsigned)((tg[g] - 1) & 1))) continue;
+            did = true;
+            tc_fence_after();
+            const uint64_t d_b = make_smem_desc(htile + c * LF_TILE_BYTES + g * 64 * 128);   // rows 64g..: 32 hi, 32 lo
+            const uint64_t d_alo = make_smem_desc(wlo + c * LF_TILE_BYTES);
+            const unsigned dg = tmem_d + (unsigned)(64 * g);
+#pragma unroll
+            for (int k = 0; k < LF_CK / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+              lf_umma_ts(dg, tmem_a + (unsigned)(c * 32 + k * 8), d_b + adv, idesc_wide, (c > 0 || k > 0) ? 1u : 0u);
+              lf_umma_ss(dg + 32, d_alo + adv, d_b + adv, idesc_n32, 1u);
+            }
+            if (++cg[g] == LF_NCH) {
+              umma_commit(&accfull[g]);
+              cg[g] = 0;
+              ++tg[g];
+            }
+          }
+          if (!did && ((++idle) & 0x3FFu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
+        }
+      }
+      __syncwarp();
+    } else {
+      // ===================== two loader / epilogue groups of four warps =====================
+      const int g = warp >> 2, wg = warp & 3, tg = tid & 127;      // group, warp in group (= TMEM lane quarter), thread in group
+      float cstate[2] = {0.f, 0.f};
+      const unsigned red_remote = lf_map_rank(smem_u32(red), (unsigned)wg);
+      const unsigned redbar_remote = lf_map_rank(smem_u32(redbar), (unsigned)wg);
+      for (int t = 0; t < p.T; ++t) {
+        float xg[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int pr = tg + 128 * i, b = 32 * g + (pr >> 3), j = pr & 7;
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            xg[i][gg] = 0.f;
+            if (b < p.B) xg[i][gg] = __ldg(p.xproj + ((size_t)b * p.T + t) * (size_t)p.xp_stride + slice * 32 + gg * 8 + j);
+          }
+        }
+        const int rpar = t & 1;
+        if (t > 0) {
+          // ---- h_{t-1}, rows of this group: warp wg loads chunk wg = 8 producers x 32 rows x 32 bytes as 16 fully
+          // coalesced 512-byte warp loads (item e = 32 j + lane: producer e >> 6, row (e & 63) >> 1, half e & 1)
+          const unsigned etag = (unsigned)(((t - 1) >> 1) & 1);
+          const unsigned* src = p.hw + ((size_t)(((t - 1) & 1) * LF_CTAS + (int)q * 32 + wg * 8) * LF_NB + 32 * g) * 8 + lane * 4;
+          if (tid == 0) LF_STAMP(0);
+          uint4 v[16];
+          unsigned pending = 0xFFFFu;
+          {   // canary: the first item only, so that early arrivals do not flood L2
+            unsigned it = 0;
+            for (;;) {
+              v[0] = lf_ld_state(src);
+              const unsigned a = v[0].x & v[0].y & v[0].z & v[0].w, o = v[0].x | v[0].y | v[0].z | v[0].w;
+              if (etag ? (a & 1u) != 0u : (o & 1u) == 0u) break;
+              if (((++it) & 0x3Fu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
+            }
+            pending &= ~1u;
+          }
+          if (tid == 0) LF_STAMP(1);
+          unsigned it = 0;
+          while (pending) {
+#pragma unroll
+            for (int j = 1; j < 16; ++j)
+              if (pending & (1u << j)) v[j] = lf_ld_state(src + (size_t)(j >> 1) * (LF_NB * 8) + (j & 1) * 128);
+#pragma unroll
+            for (int j = 1; j < 16; ++j)
+              if (pending & (1u << j)) {
+                const unsigned a = v[j].x & v[j].y & v[j].z & v[j].w, o = v[j].x | v[j].y | v[j].z | v[j].w;
+                if (etag ? (a & 1u) != 0u : (o & 1u) == 0u) pending &= ~(1u << j);
+              }
+            if (pending && ((++it) & 0x3Fu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int e = (j & 1) * 32 + lane;                   // index inside the producer's 1 KB: row e >> 1, half e & 1
+            const int row = e >> 1, hf = e & 1, c16 = j >> 1;
+            uint2 hv, lv;     // word = (hi << 16) | lo
+            hv.x = __byte_perm(v[j].x, v[j].y, 0x7632);
+            hv.y = __byte_perm(v[j].z, v[j].w, 0x7632);
+            lv.x = __byte_perm(v[j].x, v[j].y, 0x5410);
+            lv.y = __byte_perm(v[j].z, v[j].w, 0x5410);
+            unsigned char* trow = htile + wg * LF_TILE_BYTES + (64 * g + row) * 128 + ((c16 ^ (row & 7)) << 4) + hf * 8;
+            *reinterpret_cast<uint2*>(trow) = hv;
+            *reinterpret_cast<uint2*>(trow + 32 * 128) = lv;
+          }
+          lf_fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) lf_mbar_arrive(&full[g * LF_NCH + wg]);
+          if (tid == 0) LF_STAMP(2);
+
+          lf_mbar_wait(&accfull[g], (unsigned)((t - 1) & 1), t0);
+          if (tid == 0) LF_STAMP(5);
+          tc_fence_after();
+          float d0[32], d1[32];
+          tmem_ld_32x32(tmem_d + ((unsigned)(wg * 32) << 16) + (unsigned)(64 * g), d0);
+          tmem_ld_32x32(tmem_d + ((unsigned)(wg * 32) << 16) + (unsigned)(64 * g + 32), d1);
+          tc_fence_before();
+          // every warp of the group has drained its accumulator lanes before any of them can hand the next step's first
+          // chunk to the MMA thread (whose first MMA overwrites the accumulators); nothing else orders the four warps
+          asm volatile("bar.sync %0, 128;\n" ::"r"(1 + g) : "memory");
+          const unsigned rbase = red_remote + ((unsigned)(rpar * LF_RED_FLOATS) + q * 2048u) * 4u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int b = g * 32 + i;
+            const unsigned off = ((unsigned)b * 32u + (unsigned)((((lane >> 3) ^ (b & 3)) << 3) | (lane & 7))) * 4u;
+            lf_st_cluster(rbase + off, (d0[i] + d1[i]) * descale);
+          }
+          tc_fence_before();
+          asm volatile("fence.acq_rel.cluster;\n" ::: "memory");      // my DSMEM stores before the arrival below
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(redbar_remote + (unsigned)(g * 2 + rpar) * 8u)
+                         : "memory");
+          if (tid == 0) LF_STAMP(6);
+          {   // the four sources of this group's rows have arrived
+            unsigned spins = 0;
+            const unsigned par = (unsigned)(((t - 1) >> 1) & 1);
+            for (;;) {
+              unsigned ok;
+              asm volatile(
+                  "{\n.reg .pred p;\n"
+                  "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+                  "selp.u32 %0, 1, 0, p;\n}\n"
+                  : "=r"(ok)
+                  : "r"(smem_u32(&redbar[g * 2 + rpar])), "r"(par)
+                  : "memory");
+              if (ok) break;
+              if (((++spins) & 0xFFu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
+            }
+          }
+          if (tid == 0) LF_STAMP(7);
+        }
+        const float* redp = red + rpar * LF_RED_FLOATS;
+        const unsigned tag = (unsigned)((t >> 1) & 1);
+        float hv2[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int pr = tg + 128 * i, b = 32 * g + (pr >> 3), j = pr & 7;
+          float g4[4] = {xg[i][0], xg[i][1], xg[i][2], xg[i][3]};
+          if (t > 0) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) g4[gg] += redp[s * 2048 + b * 32 + (((gg ^ (b & 3)) << 3) | j)];
+          }
+          const float ig = fast_sigmoid(g4[0]);
+          const float fg = fast_sigmoid(g4[1]);
+          const float gt = fast_tanh(g4[2]);
+          const float og = fast_sigmoid(g4[3]);
+          const float c = fg * cstate[i] + ig * gt;
+          float h = og * fast_tanh(c);
+          cstate[i] = c;
+          if (b >= p.B) h = 0.f;
+          if (t + 1 < p.T) {
+            unsigned hh, hl;
+            lf_split(h * LF_SH, hh, hl);
+            lf_st_state(p.hw + ((size_t)(rpar * LF_CTAS + slice) * LF_NB + b) * 8 + j, (hh << 16) | (hl & 0xFFFEu) | tag);
+          }
+          hv2[i] = h;
+        }
+        if (tid == 0) LF_STAMP(8);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int pr = tg + 128 * i, b = 32 * g + (pr >> 3), j = pr & 7;
+          if (b < p.B) p.hseq[(size_t)b * p.hs_sb + (size_t)t * p.hs_st + slice * 8 + j] = hv2[i];
+        }
+        if (tid == 0) LF_STAMP(9);
+      }
+    }
+  } else {
   if (warp == LF_MMA_WARP) {
     // ===================== MMA issuer =====================
     constexpr unsigned idesc_wide = lf_idesc(128, 2 * LF_NB);
@@ -427,6 +621,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
       if (tid == 0) LF_STAMP(9);
     }
   }
+  }
   tc_fence_before();
   lf_cluster_arrive();          // no CTA leaves while peers may still write its smem
   lf_cluster_wait();
@@ -456,15 +651,17 @@ int lstm_f16_supported() {
   static int cached = -1;
   if (cached >= 0) return cached;
   cached = 0;
-  if (cudaFuncSetAttribute((const void*)lstm_seq_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES) !=
-      cudaSuccess) {
+  if (cudaFuncSetAttribute((const void*)lstm_seq_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute((const void*)lstm_seq_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES) !=
+          cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   cudaLaunchAttribute at[2];
   cudaLaunchConfig_t cfg = lf_config(at, 1, nullptr);
   int nclusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_seq_f16_kernel, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_seq_f16_kernel<true>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -482,7 +679,7 @@ void lstm_f16_set_profile(long long* dev_buf, int first_step, int nsteps) {
 
 // work: LF_WORK_WORDS 32-bit words (512 KB) of published state
 int lstm_seq_f16_launch(const float* xproj, long long xp_stride, const float* whh, int B, int T, float* hseq,
-                        long long hs_sb, long long hs_st, float* work, cudaStream_t s) {
+                        long long hs_sb, long long hs_st, float* work, int pingpong, cudaStream_t s) {
   if (!lstm_f16_supported()) {
     set_error("se_lstm_seq (tcgen05 fp16-pair): clusters of this kernel do not fit the device");
     return SE_ERR_CUDA;
@@ -511,11 +708,14 @@ int lstm_seq_f16_launch(const float* xproj, long long xp_stride, const float* wh
   }
   cudaLaunchAttribute at[2];
   cudaLaunchConfig_t cfg = lf_config(at, coop ? 2 : 1, s);
-  e = cudaLaunchKernelEx(&cfg, lstm_seq_f16_kernel, p);
+  auto launch = [&]() {
+    return pingpong ? cudaLaunchKernelEx(&cfg, lstm_seq_f16_kernel<true>, p) : cudaLaunchKernelEx(&cfg, lstm_seq_f16_kernel<false>, p);
+  };
+  e = launch();
   if (e != cudaSuccess && coop) {
     cudaGetLastError();
     cfg = lf_config(at, 1, s);
-    e = cudaLaunchKernelEx(&cfg, lstm_seq_f16_kernel, p);
+    e = launch();
     if (e == cudaSuccess) coop = 0;
   }
   if (e != cudaSuccess) {

@@ -628,7 +628,8 @@ def uf_mask(cmask, mdec, mag, phase):
 
 def set_lstm_engine(engine: int):
     """0 = fp32 FMA recurrence kernel, 1 = mma.sync 3xTF32 kernel, 2 = tcgen05 3xTF32 cluster kernel (H = 1024), 3 = 2 plus
-    the sequence-parallel kernel at H = 128, 4 (default) = 3 with the fp16-pair / tagged-state tcgen05 kernel at H = 1024."""
+    the sequence-parallel kernel at H = 128, 4 (default) = 3 with the fp16-pair / tagged-state tcgen05 kernel at H = 1024,
+    5 = 4 with two independent half-batch chains per CTA."""
     check(_lib.load().se_set_lstm_engine(int(engine)), "se_set_lstm_engine")
 
 

@@ -434,7 +434,7 @@ def test_lstm_engines_agree(h, b, t):
     ref = emu_ops.lstm_seq(xp.double(), whh.double(), h)
     errs = []
     try:
-        for eng in (0, 1, 2, 3, 4):
+        for eng in (0, 1, 2, 3, 4, 5):
             ops.set_lstm_engine(eng)
             got = ops.lstm_seq(xp.to(dev), whh.to(dev), h)
             torch.cuda.synchronize()
@@ -442,12 +442,13 @@ def test_lstm_engines_agree(h, b, t):
     finally:
         ops.set_lstm_engine(DEFAULT_LSTM_ENGINE)
     print(f"lstm engines H={h} B={b} T={t}: fma err {errs[0]:.3e}, mma err {errs[1]:.3e}, tcgen05 err {errs[2]:.3e}, "
-          f"engine 3 err {errs[3]:.3e}, default (fp16 pairs) err {errs[4]:.3e}")
+          f"engine 3 err {errs[3]:.3e}, fp16 pairs err {errs[4]:.3e}, fp16 pairs / two chains err {errs[5]:.3e}")
     assert max(errs) < 2e-5
 
 
+@pytest.mark.parametrize("engine", [4, 5])
 @pytest.mark.parametrize("scale", [1.0, 1e-3, 6.0])
-def test_lstm_f16_engine_relaunch_and_weight_scales(scale):
+def test_lstm_f16_engine_relaunch_and_weight_scales(scale, engine):
     """Engine 4 (csrc/lstm_f16.cu): (a) back-to-back launches on the same work buffer with DIFFERENT inputs and lengths --
     the tagged state words of one launch must never validate in the next; (b) bit-identical repeats (no race in the
     tag protocol shows up as run-to-run differences); (c) weight magnitudes from 1e-3 to 6 x 1/sqrt(H) exercise the
@@ -460,6 +461,7 @@ def test_lstm_f16_engine_relaunch_and_weight_scales(scale):
     whh = torch.randn(h // 8, h, 32, generator=g) / np.sqrt(h) * scale
     whh[3:9] = 0.0
     outs = []
+    ops.set_lstm_engine(engine)
     # large recurrent weights make the recurrence chaotic (any fp32 rounding difference grows): few steps there
     for b, t in ([(64, 37), (17, 50), (64, 37), (64, 38)] if scale <= 1.0 else [(64, 4), (17, 5), (64, 4), (64, 3)]):
         gg = torch.Generator().manual_seed(1000 + b + t)
@@ -472,7 +474,8 @@ def test_lstm_f16_engine_relaunch_and_weight_scales(scale):
         err = (got.cpu().double() - ref).abs().max().item()
         outs.append(err)
         assert err < 2e-5, (b, t, err)
-    print(f"lstm f16 engine, weight scale {scale}: errs {['%.2e' % e for e in outs]}")
+    ops.set_lstm_engine(DEFAULT_LSTM_ENGINE)
+    print(f"lstm f16 engine {engine}, weight scale {scale}: errs {['%.2e' % e for e in outs]}")
 
 
 @pytest.mark.parametrize("c", [1, 16, 130])
