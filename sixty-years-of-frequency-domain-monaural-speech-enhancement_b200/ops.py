@@ -425,7 +425,8 @@ def resample(x, sr_orig, sr_new, out=None):
     if tkey not in _RESAMPLE_TIME:           # resample_f's time register: 0, += 1/ratio (sequential float64 adds)
         import numpy as np
         treg = np.concatenate([[0.0], np.cumsum(np.full(n_valid - 1, 1.0 / ratio, dtype=np.float64))])
-        _RESAMPLE_TIME.clear()               # one (ratio, length) at a time: corpora are processed group by group
+        while len(_RESAMPLE_TIME) >= 4:      # small cache: corpora are processed group by group; evicted tables stay
+            _RESAMPLE_TIME.pop(next(iter(_RESAMPLE_TIME)))   # referenced by the caching allocator's stream ordering
         _RESAMPLE_TIME[tkey] = torch.from_numpy(treg).to(x.device)
     treg = _RESAMPLE_TIME[tkey]
     if out is None:
