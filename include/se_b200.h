@@ -309,6 +309,41 @@ int se_fsn_fb_input(const float* x, long long sb, long long st, long long sf, in
 int se_fsn_sb_assemble(const float* mag_tm, const float* fb, int B, int Tp, int F, int num_neighbors,
                        const float* inv, float* out_hi, float* out_lo, se_stream_t stream);
 int se_fsn_sb_fc(const float* h, int M, int H, const float* W, const float* bias, float* out, se_stream_t stream);
+/* se_fsn_sb_assemble for the fp16-pair cell GEMM (se_lstm_cell_f16x3): rows scaled by 2^scale_log2. */
+int se_fsn_sb_assemble_f16(const float* mag_tm, const float* fb, int B, int Tp, int F, int num_neighbors,
+                           const float* inv, int scale_log2, unsigned short* out_hi, unsigned short* out_lo,
+                           se_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The same fp32-class products on fp16 operand PAIRS (tcgen05 kind::f16: twice the MMA rate of kind::tf32 and half
+ * the operand bytes).  An operand x travels as two IEEE fp16 arrays with  x * 2^s = hi + lo  (s = its scale_log2):
+ * 22 significand bits wherever |x * 2^s| >= 2^-3, an absolute floor of 2^-25-s below, saturation (not inf) beyond
+ * +-65504 * 2^-s.  Weights are split once at load time with a per-tensor s that puts max|w| in [2^13, 2^14);
+ * activations use a fixed s (4 by default: |x| < 4094, floor 2e-9).  Same three-term product as se_gemm_tf32x3
+ * (A_lo*B_lo dropped); the epilogue multiplies the fp32 sums by 2^-(s_A + s_B).
+ *     se_split_f16:   x [rows, K] (row stride ldx floats) -> hi / lo [rows, Kpad] fp16, columns K.. zero, Kpad %% 8 == 0
+ *     se_gemm_f16x3:  C = alpha * act(A B^T + bias, act_param) + res, A [M,K] and B [N,K] fp16 pairs (lda / ldb in
+ *                     elements, %% 8), K %% 8 == 0 (k-blocks of 64, zero-filled past K); scale_log2_ab = s_A + s_B;
+ *                     optional outputs: fp32 C, the TF32 pair (c_hi / c_lo) and / or the fp16 pair (c16_hi / c16_lo,
+ *                     scaled by 2^c16_scale_log2) of C for the layer that follows; all with row stride ldc.
+ *                     Replaces the same reference ops as se_gemm_tf32x3 (nn.Linear, hoisted nn.LSTM input projections:
+ *                     CRN/CRN.py:20, LSTM/LSTM.py:17-22).
+ *     se_lstm_cell_f16x3: se_lstm_cell_tf32x3_ex on fp16 pairs: gates = [x | h] [W_ih | W_hh]^T with W laid out as
+ *                     [4H][Kx rounded up to 64 | H] (tile row order as for the TF32 cell), x and h scaled by 2^scale_log2_a,
+ *                     W by 2^scale_log2_w; h_hi_out / h_lo_out leave as fp16 pairs scaled by 2^scale_log2_a.
+ *                     (FullSubNet sub-band LSTM steps, FullSubNet/fullsubnet_net_sa/model.py:106-112.)
+ * ------------------------------------------------------------------------------------- */
+int se_split_f16(const float* x, long long rows, int K, long long ldx, int Kpad, int scale_log2, unsigned short* hi,
+                 unsigned short* lo, se_stream_t stream);
+int se_gemm_f16x3(const unsigned short* a_hi, const unsigned short* a_lo, long long lda, const unsigned short* b_hi,
+                  const unsigned short* b_lo, long long ldb, int M, int N, int K, int scale_log2_ab, const float* bias,
+                  int act, float act_param, float alpha, const float* res, float* C, float* c_hi, float* c_lo,
+                  unsigned short* c16_hi, unsigned short* c16_lo, int c16_scale_log2, long long ldc, se_stream_t stream);
+int se_lstm_cell_f16x3(const unsigned short* x_hi, const unsigned short* x_lo, long long ldx, int Kx,
+                       const unsigned short* h_hi, const unsigned short* h_lo, long long ldh, int H,
+                       const unsigned short* w_hi, const unsigned short* w_lo, long long ldw, int scale_log2_a,
+                       int scale_log2_w, const float* bias, int M, float* c_state, unsigned short* h_hi_out,
+                       unsigned short* h_lo_out, float* h_out, long long ld_hout, int first_step, se_stream_t stream);
 
 /* Tensor-core twin of se_conv_gemm (tcgen05 3xTF32, 4-D TMA im2col-free A tiles; csrc/conv_tc.cu)
  * for layers with C0, C1 multiples of 32 and Fout <= 128.  Activations and weights are TF32 hi/lo

@@ -84,6 +84,10 @@ PROTOTYPES = {
     "se_fsn_fb_input": (_I, [_P, _LL, _LL, _LL, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_assemble": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "se_fsn_sb_fc": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "se_fsn_sb_assemble_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "se_split_f16": (_I, [_P, _LL, _I, _LL, _I, _I, _P, _P, _P]),
+    "se_gemm_f16x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _I, _F, _F, _P, _P, _P, _P, _P, _P, _I, _LL, _P]),
+    "se_lstm_cell_f16x3": (_I, [_P, _P, _LL, _I, _P, _P, _LL, _I, _P, _P, _LL, _I, _I, _P, _I, _P, _P, _P, _P, _LL, _I, _P]),
     "se_conv_tf32x3": (_I, [C.POINTER(ConvTcDesc), _P]),
     "se_uf_prep": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "se_uf_fusion": (_I, [_P, _P, _LL, _I, _P, _P, _P]),

@@ -88,10 +88,12 @@ __global__ void __launch_bounds__(256) fsn_fb_input_kernel(const float* __restri
 
 // out[t][b*F+f][j] = inv[b] * (j < 2n+1 ? mag_tm[b,t,reflect(f+j-n)] : fb[b,t,f]),  split hi/lo.
 // One warp per (t, b, f-group of 4): each thread produces a float4 of one row.
+template <bool F16>
 __global__ void __launch_bounds__(256) fsn_sb_assemble_kernel(const float* __restrict__ mag_tm,
                                                              const float* __restrict__ fb, int B, int Tp, int F,
                                                              int nn, const float* __restrict__ inv,
-                                                             float* __restrict__ out_hi, float* __restrict__ out_lo) {
+                                                             float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                                             float scale16) {
   const int W = 2 * nn + 2;  // 32 features per row
   const long long rows = (long long)Tp * B * F;
   const long long total = rows * (W / 4);
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(256) fsn_sb_assemble_kernel(const float* __res
     const float* m = mag_tm + ((long long)b * Tp + t) * F;
     const float s = __ldg(inv + b);
     float hi[4], lo[4];
+    unsigned short h16[4], l16[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = q * 4 + e;
@@ -118,10 +121,18 @@ __global__ void __launch_bounds__(256) fsn_sb_assemble_kernel(const float* __res
       } else {
         v = __ldg(fb + ((long long)b * Tp + t) * F + f);
       }
-      split_tf32_dev(v * s, hi[e], lo[e]);
+      if constexpr (F16) split_f16_dev(v * s, scale16, h16[e], l16[e]);
+      else split_tf32_dev(v * s, hi[e], lo[e]);
     }
-    *reinterpret_cast<float4*>(out_hi + row * W + q * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(out_lo + row * W + q * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    if constexpr (F16) {
+      unsigned short* o_hi = reinterpret_cast<unsigned short*>(out_hi);
+      unsigned short* o_lo = reinterpret_cast<unsigned short*>(out_lo);
+      *reinterpret_cast<uint2*>(o_hi + row * W + q * 4) = make_uint2(h16[0] | ((unsigned)h16[1] << 16), h16[2] | ((unsigned)h16[3] << 16));
+      *reinterpret_cast<uint2*>(o_lo + row * W + q * 4) = make_uint2(l16[0] | ((unsigned)l16[1] << 16), l16[2] | ((unsigned)l16[3] << 16));
+    } else {
+      *reinterpret_cast<float4*>(out_hi + row * W + q * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(out_lo + row * W + q * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
@@ -180,9 +191,22 @@ extern "C" int se_fsn_sb_assemble(const float* mag_tm, const float* fb, int B, i
   SE_REQUIRE((2 * num_neighbors + 2) % 4 == 0 && num_neighbors < F, "se_fsn_sb_assemble: neighbours=%d", num_neighbors);
   const long long total = (long long)Tp * B * F * ((2 * num_neighbors + 2) / 4);
   const int blocks = (int)min((long long)148 * 32, ceil_div_ll(total, 256));
-  fsn_sb_assemble_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mag_tm, fb, B, Tp, F, num_neighbors, inv, out_hi,
-                                                                   out_lo);
+  fsn_sb_assemble_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(mag_tm, fb, B, Tp, F, num_neighbors, inv, out_hi,
+                                                                          out_lo, 1.0f);
   return check_launch("se_fsn_sb_assemble");
+}
+
+extern "C" int se_fsn_sb_assemble_f16(const float* mag_tm, const float* fb, int B, int Tp, int F, int num_neighbors,
+                                      const float* inv, int scale_log2, unsigned short* out_hi, unsigned short* out_lo,
+                                      se_stream_t stream) {
+  SE_REQUIRE(mag_tm && fb && inv && out_hi && out_lo, "se_fsn_sb_assemble_f16: null pointer");
+  SE_REQUIRE((2 * num_neighbors + 2) % 8 == 0 && num_neighbors < F, "se_fsn_sb_assemble_f16: neighbours=%d", num_neighbors);
+  const long long total = (long long)Tp * B * F * ((2 * num_neighbors + 2) / 4);
+  const int blocks = (int)min((long long)148 * 32, ceil_div_ll(total, 256));
+  fsn_sb_assemble_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      mag_tm, fb, B, Tp, F, num_neighbors, inv, reinterpret_cast<float*>(out_hi), reinterpret_cast<float*>(out_lo),
+      ldexpf(1.0f, scale_log2));
+  return check_launch("se_fsn_sb_assemble_f16");
 }
 
 extern "C" int se_fsn_sb_fc(const float* h, int M, int H, const float* W, const float* bias, float* out,

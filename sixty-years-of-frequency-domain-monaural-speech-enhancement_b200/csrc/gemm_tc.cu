@@ -27,6 +27,7 @@
 namespace se {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
+constexpr int TC_BK16 = 64;                                // fp16-pair operands: the same 128-byte tile rows hold 64 elements
 constexpr int TC_STAGES = 3;
 constexpr int TC_CHUNK_KB = 4;                              // k-blocks (of 32) per TMEM accumulation chunk
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;           // 16 KB (same for A and B tiles)
@@ -61,6 +62,12 @@ struct TcParams {
   int H;
   long long ld_hout;   // row stride of h_hi / h_lo / h_out (>= H; c_state is always [M, H] contiguous)
   int first_step;      // 1: h_{-1} = c_{-1} = 0 -- no recurrent k-blocks, c_state is not read
+  // fp16-pair operands (F16 kernels): A and B arrive scaled by powers of two, out_scale = 1 / (scale_A * scale_B) puts
+  // the sums back (exact); 1.0f on the TF32 path.  c16_hi / c16_lo: optional fp16-pair copy of the output for the next
+  // f16 GEMM, scaled by c16_scale; in the F16 LSTM cell h_hi / h_lo point at fp16 data scaled by c16_scale.
+  float out_scale;
+  unsigned short *c16_hi, *c16_lo;
+  float c16_scale;
 };
 
 // Final epilogue of one thread: NC consecutive columns [n0, n0 + NC) of output row `row`, fp32 sums in registers.
@@ -84,8 +91,11 @@ __device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
       const float4 bb = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float o[4] = {tc_act<ACT>(sum[j] + bb.x, p.act_param) * p.alpha, tc_act<ACT>(sum[j + 1] + bb.y, p.act_param) * p.alpha,
-                    tc_act<ACT>(sum[j + 2] + bb.z, p.act_param) * p.alpha, tc_act<ACT>(sum[j + 3] + bb.w, p.act_param) * p.alpha};
+      const float os = p.out_scale;   // 1.0f on the TF32 path: fmaf(s, 1, b) == s + b
+      float o[4] = {tc_act<ACT>(fmaf(sum[j], os, bb.x), p.act_param) * p.alpha,
+                    tc_act<ACT>(fmaf(sum[j + 1], os, bb.y), p.act_param) * p.alpha,
+                    tc_act<ACT>(fmaf(sum[j + 2], os, bb.z), p.act_param) * p.alpha,
+                    tc_act<ACT>(fmaf(sum[j + 3], os, bb.w), p.act_param) * p.alpha};
       if (res) {
         const float4 rr = __ldg(reinterpret_cast<const float4*>(res + n0 + j));
         o[0] += rr.x;
@@ -101,6 +111,13 @@ __device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float
         *reinterpret_cast<float4*>(p.c_hi + roff + n0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(p.c_lo + roff + n0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
+      if (p.c16_hi) {
+        unsigned short hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_f16_dev(o[e], p.c16_scale, hi[e], lo[e]);
+        *reinterpret_cast<uint2*>(p.c16_hi + roff + n0 + j) = make_uint2(hi[0] | ((unsigned)hi[1] << 16), hi[2] | ((unsigned)hi[3] << 16));
+        *reinterpret_cast<uint2*>(p.c16_lo + roff + n0 + j) = make_uint2(lo[0] | ((unsigned)lo[1] << 16), lo[2] | ((unsigned)lo[3] << 16));
+      }
     }
     return;
   }
@@ -109,15 +126,16 @@ __device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float
   for (int j = 0; j < NC; ++j) {
     const int n = n0 + j;
     if (n < p.N) {
-      float o = tc_act<ACT>(sum[j] + (bias ? __ldg(bias + n) : 0.f), p.act_param) * p.alpha;
+      float o = tc_act<ACT>(fmaf(sum[j], p.out_scale, bias ? __ldg(bias + n) : 0.f), p.act_param) * p.alpha;
       if (res) o += __ldg(res + n);
       if (p.C) p.C[roff + n] = o;
       if (p.c_hi) split_tf32_dev(o, p.c_hi[roff + n], p.c_lo[roff + n]);
+      if (p.c16_hi) split_f16_dev(o, p.c16_scale, p.c16_hi[roff + n], p.c16_lo[roff + n]);
     }
   }
 }
 
-template <int EPI, int NC>
+template <int EPI, int NC, bool F16 = false>
 __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float (&sum)[NC], int row, int n0) {
   if constexpr (EPI == EPI_BIAS_ACT) {
     switch (p.act) {   // uniform across the grid: one predictable branch per tile instead of one per element
@@ -149,19 +167,29 @@ __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float
         const float vbi[4] = {bi.x, bi.y, bi.z, bi.w}, vbf[4] = {bf.x, bf.y, bf.z, bf.w}, vbg[4] = {bg.x, bg.y, bg.z, bg.w},
                     vbo[4] = {bo.x, bo.y, bo.z, bo.w};
         float cn[4], hn[4], hh[4], hl[4];
+        unsigned short h16[4], l16[4];
+        const float os = p.out_scale;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float ig = fast_sigmoid(sum[q * 64 + u + e] + vbi[e]);
-          const float fg = fast_sigmoid(sum[q * 64 + 16 + u + e] + vbf[e]);
-          const float gg = fast_tanh(sum[q * 64 + 32 + u + e] + vbg[e]);
-          const float og = fast_sigmoid(sum[q * 64 + 48 + u + e] + vbo[e]);
+          const float ig = fast_sigmoid(fmaf(sum[q * 64 + u + e], os, vbi[e]));
+          const float fg = fast_sigmoid(fmaf(sum[q * 64 + 16 + u + e], os, vbf[e]));
+          const float gg = fast_tanh(fmaf(sum[q * 64 + 32 + u + e], os, vbg[e]));
+          const float og = fast_sigmoid(fmaf(sum[q * 64 + 48 + u + e], os, vbo[e]));
           cn[e] = fg * co[e] + ig * gg;
           hn[e] = og * fast_tanh(cn[e]);
-          split_tf32_dev(hn[e], hh[e], hl[e]);
+          if constexpr (F16) split_f16_dev(hn[e], p.c16_scale, h16[e], l16[e]);
+          else split_tf32_dev(hn[e], hh[e], hl[e]);
         }
         *reinterpret_cast<float4*>(p.c_state + off + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        *reinterpret_cast<float4*>(p.h_hi + hoff + u) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-        *reinterpret_cast<float4*>(p.h_lo + hoff + u) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+        if constexpr (F16) {
+          unsigned short* o_hi = reinterpret_cast<unsigned short*>(p.h_hi);
+          unsigned short* o_lo = reinterpret_cast<unsigned short*>(p.h_lo);
+          *reinterpret_cast<uint2*>(o_hi + hoff + u) = make_uint2(h16[0] | ((unsigned)h16[1] << 16), h16[2] | ((unsigned)h16[3] << 16));
+          *reinterpret_cast<uint2*>(o_lo + hoff + u) = make_uint2(l16[0] | ((unsigned)l16[1] << 16), l16[2] | ((unsigned)l16[3] << 16));
+        } else {
+          *reinterpret_cast<float4*>(p.h_hi + hoff + u) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<float4*>(p.h_lo + hoff + u) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+        }
         if (p.h_out) *reinterpret_cast<float4*>(p.h_out + hoff + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
       }
     }
@@ -175,7 +203,7 @@ __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float
 // operand traffic (~8 TB/s aggregate: profiles/), which this cuts from 64 KB to 48 KB (1 x 2) or 32 KB (2 x 2) per
 // k-block and CTA.  A stage may be refilled only when every CTA that receives this CTA's multicast has consumed it:
 // `empty` counts CM + CN - 1 arrivals, each MMA thread commits to its row and column peers.
-template <int EPI, int CM, int CN>
+template <int EPI, int CM, int CN, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
                    const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
@@ -193,6 +221,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int CSIZE = CM * CN;
+  constexpr int BK = F16 ? TC_BK16 : TC_BK;                       // elements per k-block (128 bytes either way)
   const unsigned rank = CSIZE > 1 ? cluster_ctarank() : 0u;
   const int rm = (int)rank / CN, rn = (int)rank % CN;             // position of this CTA in the cluster
   const int cl = (int)blockIdx.x / CSIZE, ncl = (int)gridDim.x / CSIZE;
@@ -253,7 +282,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
           unsigned char* st = tiles + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
           const bool src0 = kb < p.kb0;
-          const int ak = (src0 ? kb : kb - p.kb0) * TC_BK;
+          const int ak = (src0 ? kb : kb - p.kb0) * BK;
           if constexpr (CN == 1) {
             tma_load_2d(src0 ? &map_a0hi : &map_a1hi, &full[stage], st + 0 * TC_TILE_BYTES, ak, mb * TC_BM);
             tma_load_2d(src0 ? &map_a0lo : &map_a1lo, &full[stage], st + 1 * TC_TILE_BYTES, ak, mb * TC_BM);
@@ -263,12 +292,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
             tma_load_2d_mc(src0 ? &map_a0lo : &map_a1lo, &full[stage], st + 1 * TC_TILE_BYTES, ak, mb * TC_BM, row_mask);
           }
           if constexpr (CM == 1) {
-            tma_load_2d(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
-            tma_load_2d(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN);
+            tma_load_2d(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * BK, nb * TC_BN);
+            tma_load_2d(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * BK, nb * TC_BN);
           } else if (rm == 0) {   // my column's B_hi, into every CTA of the column (the rm = 1 CTA sends B_lo)
-            tma_load_2d_mc(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN, col_mask);
+            tma_load_2d_mc(&map_bhi, &full[stage], st + 2 * TC_TILE_BYTES, kb * BK, nb * TC_BN, col_mask);
           } else {
-            tma_load_2d_mc(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * TC_BK, nb * TC_BN, col_mask);
+            tma_load_2d_mc(&map_blo, &full[stage], st + 3 * TC_TILE_BYTES, kb * BK, nb * TC_BN, col_mask);
           }
           if (++stage == TC_STAGES) {
             stage = 0;
@@ -280,7 +309,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (elect_one()) {
-      constexpr unsigned idesc = make_idesc_tf32(TC_BM, TC_BN);
+      constexpr unsigned idesc = F16 ? make_idesc_f16(TC_BM, TC_BN) : make_idesc_tf32(TC_BM, TC_BN);
       int stage = 0;
       unsigned phase = 0;
       int acc = 0;
@@ -301,11 +330,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
           const uint64_t d_bhi = make_smem_desc(st + 2 * TC_TILE_BYTES);
           const uint64_t d_blo = make_smem_desc(st + 3 * TC_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 slice, in 16-byte units
-            umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
-            umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
-            umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 32 bytes per MMA K slice (8 tf32 / 16 fp16), in 16-byte units
+            if constexpr (F16) {
+              umma_f16(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+              umma_f16(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_f16(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+              umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            }
           }
           // smem slot reusable once these MMAs have read it: tell every CTA that multicasts into this one
           if constexpr (CSIZE > 1) umma_commit_mc(&empty[stage], (unsigned short)(row_mask | col_mask));
@@ -359,7 +394,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
         }
       }
       if (!row_ok) continue;
-      tc_epilogue_store<EPI, TC_EPI_COLS>(p, sum, row, nb * TC_BN + half * TC_EPI_COLS);
+      tc_epilogue_store<EPI, TC_EPI_COLS, F16>(p, sum, row, nb * TC_BN + half * TC_EPI_COLS);
     }
   }
   tc_fence_before();
@@ -393,7 +428,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
 constexpr int T2_BN = 256;
 constexpr int T2_EPI_COLS = T2_BN / 2;                     // 128 columns per epilogue warp
 constexpr int T2_TMEM_COLS = 512;                          // 2 accumulators x 256 columns: all of tensor memory
-template <int EPI>
+template <int EPI, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
                         const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
@@ -411,6 +446,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_ctarank();            // 0 = leader
+  constexpr int BK = F16 ? TC_BK16 : TC_BK;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int mblocks = ceil_div(p.M, 2 * TC_BM), nblocks = ceil_div(p.N, T2_BN);
   const int ntiles = mblocks * nblocks;
@@ -464,14 +500,14 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
           const unsigned lbar = smem_u32(&full[stage]) & T2_PEER_BIT_MASK;
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * TC_STAGE_BYTES);   // both CTAs' bytes land on this barrier
           if (kb < p.kb0) {
-            tma_load_2d_pair(&map_a0hi, lbar, st + 0 * TC_TILE_BYTES, kb * TC_BK, arow);
-            tma_load_2d_pair(&map_a0lo, lbar, st + 1 * TC_TILE_BYTES, kb * TC_BK, arow);
+            tma_load_2d_pair(&map_a0hi, lbar, st + 0 * TC_TILE_BYTES, kb * BK, arow);
+            tma_load_2d_pair(&map_a0lo, lbar, st + 1 * TC_TILE_BYTES, kb * BK, arow);
           } else {
-            tma_load_2d_pair(&map_a1hi, lbar, st + 0 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, arow);
-            tma_load_2d_pair(&map_a1lo, lbar, st + 1 * TC_TILE_BYTES, (kb - p.kb0) * TC_BK, arow);
+            tma_load_2d_pair(&map_a1hi, lbar, st + 0 * TC_TILE_BYTES, (kb - p.kb0) * BK, arow);
+            tma_load_2d_pair(&map_a1lo, lbar, st + 1 * TC_TILE_BYTES, (kb - p.kb0) * BK, arow);
           }
-          tma_load_2d_pair(&map_bhi, lbar, st + 2 * TC_TILE_BYTES, kb * TC_BK, brow);
-          tma_load_2d_pair(&map_blo, lbar, st + 3 * TC_TILE_BYTES, kb * TC_BK, brow);
+          tma_load_2d_pair(&map_bhi, lbar, st + 2 * TC_TILE_BYTES, kb * BK, brow);
+          tma_load_2d_pair(&map_blo, lbar, st + 3 * TC_TILE_BYTES, kb * BK, brow);
           if (++stage == TC_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -482,7 +518,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
     if (rank == 0 && elect_one()) {
-      constexpr unsigned idesc = make_idesc_tf32(2 * TC_BM, T2_BN);
+      constexpr unsigned idesc = F16 ? make_idesc_f16(2 * TC_BM, T2_BN) : make_idesc_tf32(2 * TC_BM, T2_BN);
       int stage = 0;
       unsigned phase = 0;
       int acc = 0;
@@ -503,11 +539,17 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
           const uint64_t d_bhi = make_smem_desc(st + 2 * TC_TILE_BYTES);
           const uint64_t d_blo = make_smem_desc(st + 3 * TC_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-            umma_tf32_pair(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
-            umma_tf32_pair(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
-            umma_tf32_pair(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            if constexpr (F16) {
+              umma_f16_pair(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+              umma_f16_pair(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_f16_pair(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            } else {
+              umma_tf32_pair(d_tmem, d_alo + adv, d_bhi + adv, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+              umma_tf32_pair(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_tf32_pair(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            }
           }
           umma_commit_pair(&empty[stage]);
           if (++stage == TC_STAGES) {
@@ -559,7 +601,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
         }
       }
       if (row >= p.M) continue;
-      tc_epilogue_store<EPI, T2_EPI_COLS>(p, sum, row, nb * T2_BN + half * T2_EPI_COLS);
+      tc_epilogue_store<EPI, T2_EPI_COLS, F16>(p, sum, row, nb * T2_BN + half * T2_EPI_COLS);
     }
   }
   tc_fence_before();
@@ -607,6 +649,33 @@ __global__ void __launch_bounds__(256) pad_split_tf32_kernel(const float* __rest
   }
 }
 
+// rows of K floats (row stride ldx) -> rows of Kpad >= K fp16 pairs (zero tail): x * scale = hi + lo
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, long long rows, int K, long long ldx,
+                                                       int Kpad, float scale, unsigned short* __restrict__ hi,
+                                                       unsigned short* __restrict__ lo) {
+  const int kq = Kpad >> 2;                                   // 4 elements per thread
+  const long long total = rows * kq;
+  const bool vec = (ldx & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / kq;
+    const int c = (int)(i - r * kq) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec && c + 4 <= K) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c));
+      v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < K) v[e] = __ldg(x + r * ldx + c + e);
+    }
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_f16_dev(v[e], scale, h[e], l[e]);
+    *reinterpret_cast<uint2*>(hi + r * Kpad + c) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
+    *reinterpret_cast<uint2*>(lo + r * Kpad + c) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+  }
+}
+
 // ---- host: tensor maps through the driver entry point (no link-time libcuda dependency) ----------
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -620,17 +689,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, long long ld) {
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int K, long long ld, bool f16 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return SE_ERR_CUDA;
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? TC_BK16 : TC_BK), (cuuint32_t)TC_BM};   // 128 bytes x 128 rows either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -676,6 +745,7 @@ static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 constexpr int kDefaultGemmEngine = 5;
 constexpr int kMaxGemmEngine = 5;
 constexpr int kAutoPairMinKBlocks = 12;
+constexpr int kAutoPairMinKBlocksF16 = 6;     // the same K = 384 in 64-element k-blocks
 static int g_gemm_engine = -1;
 static int gemm_engine() {
   if (g_gemm_engine < 0) {
@@ -690,11 +760,11 @@ static int gemm_engine() {
 
 int se::gemm_engine_is_pair() { return gemm_engine() == 1; }     // conv_tc.cu follows the same switch
 
-template <int EPI>
+template <int EPI, bool F16 = false>
 static int launch_pair_kernel(const CUtensorMap& a0hi, const CUtensorMap& a0lo, const CUtensorMap& a1hi,
                               const CUtensorMap& a1lo, const CUtensorMap& bhi, const CUtensorMap& blo, const TcParams& p,
                               int grid, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) {
     set_error("tcgen05 pair gemm: smem attribute: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
@@ -711,7 +781,7 @@ static int launch_pair_kernel(const CUtensorMap& a0hi, const CUtensorMap& a0lo, 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<EPI>, a0hi, a0lo, a1hi, a1lo, bhi, blo, p);
+  e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<EPI, F16>, a0hi, a0lo, a1hi, a1lo, bhi, blo, p);
   if (e != cudaSuccess) {
     set_error("tcgen05 pair gemm: cluster launch: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
@@ -721,20 +791,23 @@ static int launch_pair_kernel(const CUtensorMap& a0hi, const CUtensorMap& a0lo, 
 
 static int launch_tc_pair(int epi, const CUtensorMap& a0hi, const CUtensorMap& a0lo, const CUtensorMap& a1hi,
                           const CUtensorMap& a1lo, const CUtensorMap& bhi, const CUtensorMap& blo, TcParams p, int sms,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool f16 = false) {
   const int mblocks = ceil_div(p.M, 2 * TC_BM), nblocks = ceil_div(p.N, T2_BN);
   p.panel_m = min(8, mblocks);                    // 8 x 256 rows: the same A panel as 16 x 128
   const int grid = 2 * min(sms / 2, mblocks * nblocks);
+  if (f16)
+    return epi == EPI_BIAS_ACT ? launch_pair_kernel<EPI_BIAS_ACT, true>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream)
+                               : launch_pair_kernel<EPI_LSTM_CELL, true>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
   return epi == EPI_BIAS_ACT ? launch_pair_kernel<EPI_BIAS_ACT>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream)
                              : launch_pair_kernel<EPI_LSTM_CELL>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
 }
 
 // gemm_tf32x3_kernel<EPI, CM, CN>: persistent grid of as many CM x CN clusters as are co-resident on the device (a
 // cluster that had to wait for a second wave would double the run time).
-template <int EPI, int CM, int CN>
+template <int EPI, int CM, int CN, bool F16 = false>
 static int launch_tc_cluster(const CUtensorMap* const* m, TcParams p, int sms, cudaStream_t stream) {
   constexpr int CSIZE = CM * CN;
-  auto kernel = gemm_tf32x3_kernel<EPI, CM, CN>;
+  auto kernel = gemm_tf32x3_kernel<EPI, CM, CN, F16>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) {
     set_error("tcgen05 gemm: smem attribute: %s", cudaGetErrorString(e));
@@ -777,28 +850,39 @@ static int launch_tc_cluster(const CUtensorMap* const* m, TcParams p, int sms, c
   return SE_OK;
 }
 
-static int launch_tc(int epi, const float* a0_hi, const float* a0_lo, long long lda0, int K0, const float* a1_hi,
-                     const float* a1_lo, long long lda1, int K1, const float* b_hi, const float* b_lo, long long ldb,
-                     TcParams p, cudaStream_t stream) {
+// f16: operands are fp16 pairs; K0 / K1 need not be multiples of the 64-element k-block (the TMA box is zero-filled past
+// the end of a row), but B is laid out with source 0 padded to whole k-blocks: B = [K0 rounded up to 64 | K1].
+static int launch_tc(int epi, const void* a0_hi, const void* a0_lo, long long lda0, int K0, const void* a1_hi,
+                     const void* a1_lo, long long lda1, int K1, const void* b_hi, const void* b_lo, long long ldb,
+                     TcParams p, cudaStream_t stream, bool f16 = false) {
   CUtensorMap m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo;
   int rc;
-  if ((rc = make_map(&m_a0hi, a0_hi, p.M, K0, lda0))) return rc;
-  if ((rc = make_map(&m_a0lo, a0_lo, p.M, K0, lda0))) return rc;
+  const int bk = f16 ? TC_BK16 : TC_BK;
+  if ((rc = make_map(&m_a0hi, a0_hi, p.M, K0, lda0, f16))) return rc;
+  if ((rc = make_map(&m_a0lo, a0_lo, p.M, K0, lda0, f16))) return rc;
   if (K1 > 0) {
-    if ((rc = make_map(&m_a1hi, a1_hi, p.M, K1, lda1))) return rc;
-    if ((rc = make_map(&m_a1lo, a1_lo, p.M, K1, lda1))) return rc;
+    if ((rc = make_map(&m_a1hi, a1_hi, p.M, K1, lda1, f16))) return rc;
+    if ((rc = make_map(&m_a1lo, a1_lo, p.M, K1, lda1, f16))) return rc;
   } else {
     m_a1hi = m_a0hi;
     m_a1lo = m_a0lo;
   }
-  if ((rc = make_map(&m_bhi, b_hi, p.N, K0 + K1, ldb))) return rc;
-  if ((rc = make_map(&m_blo, b_lo, p.N, K0 + K1, ldb))) return rc;
+  p.kb0 = ceil_div(K0, bk);
+  p.kb1 = ceil_div(K1, bk);
+  const int kb_total = K1 > 0 ? p.kb0 * bk + K1 : K0;      // columns of B that hold data
+  if ((rc = make_map(&m_bhi, b_hi, p.N, kb_total, ldb, f16))) return rc;
+  if ((rc = make_map(&m_blo, b_lo, p.N, kb_total, ldb, f16))) return rc;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  p.kb0 = K0 / TC_BK;
-  p.kb1 = K1 / TC_BK;
   const int engine = gemm_engine();
+  if (f16) {
+    if ((engine == 1 || (engine == 5 && p.kb0 + p.kb1 >= kAutoPairMinKBlocksF16)) && p.M >= 2 * TC_BM && p.N >= T2_BN)
+      return launch_tc_pair(epi, m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p, sms, stream, true);
+    const CUtensorMap* maps16[6] = {&m_a0hi, &m_a0lo, &m_a1hi, &m_a1lo, &m_bhi, &m_blo};
+    return epi == EPI_BIAS_ACT ? launch_tc_cluster<EPI_BIAS_ACT, 1, 1, true>(maps16, p, sms, stream)
+                               : launch_tc_cluster<EPI_LSTM_CELL, 1, 1, true>(maps16, p, sms, stream);
+  }
   if ((engine == 1 || (engine == 5 && p.kb0 + p.kb1 >= kAutoPairMinKBlocks)) && p.M >= 2 * TC_BM && p.N >= T2_BN)
     return launch_tc_pair(epi, m_a0hi, m_a0lo, m_a1hi, m_a1lo, m_bhi, m_blo, p, sms, stream);
   const CUtensorMap* maps[6] = {&m_a0hi, &m_a0lo, &m_a1hi, &m_a1lo, &m_bhi, &m_blo};
@@ -843,6 +927,7 @@ extern "C" int se_gemm_tf32x3_ex(const float* a_hi, const float* a_lo, long long
   p.c_hi = c_hi;
   p.c_lo = c_lo;
   p.ldc = ldc;
+  p.out_scale = 1.0f;
   int rc = launch_tc(EPI_BIAS_ACT, a_hi, a_lo, lda, K, nullptr, nullptr, 0, 0, b_hi, b_lo, ldb, p, (cudaStream_t)stream);
   if (rc) return rc;
   return check_launch("se_gemm_tf32x3");
@@ -881,6 +966,7 @@ extern "C" int se_lstm_cell_tf32x3_ex(const float* x_hi, const float* x_lo, long
   p.H = H;
   p.ld_hout = ld_hout;
   p.first_step = first_step ? 1 : 0;
+  p.out_scale = 1.0f;
   int rc = launch_tc(EPI_LSTM_CELL, x_hi, x_lo, ldx, Kx, h_hi, h_lo, ldh, first_step ? 0 : H, w_hi, w_lo, ldw, p,
                      (cudaStream_t)stream);
   if (rc) return rc;
@@ -893,4 +979,87 @@ extern "C" int se_lstm_cell_tf32x3(const float* x_hi, const float* x_lo, long lo
                                    float* h_lo_out, float* h_out, se_stream_t stream) {
   return se_lstm_cell_tf32x3_ex(x_hi, x_lo, ldx, Kx, h_hi, h_lo, ldh, H, w_hi, w_lo, ldw, bias, M, c_state, h_hi_out,
                                 h_lo_out, h_out, H, 0, stream);
+}
+
+// ---- fp16-pair operands (kind::f16): half the MMAs and half the operand bytes of 3xTF32 for the same 22-bit products --
+extern "C" int se_split_f16(const float* x, long long rows, int K, long long ldx, int Kpad, int scale_log2,
+                            unsigned short* hi, unsigned short* lo, se_stream_t stream) {
+  SE_REQUIRE(x && hi && lo && rows > 0 && K > 0 && ldx >= K && Kpad >= K && (Kpad & 7) == 0,
+             "se_split_f16: rows=%lld K=%d ldx=%lld Kpad=%d (Kpad %% 8)", rows, K, ldx, Kpad);
+  SE_REQUIRE(aligned16(hi) && aligned16(lo) && scale_log2 >= -14 && scale_log2 <= 15, "se_split_f16: alignment / scale_log2=%d",
+             scale_log2);
+  const int blocks = (int)min((long long)148 * 8, ceil_div_ll(rows * (Kpad / 4), 256));
+  split_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, K, ldx, Kpad, ldexpf(1.0f, scale_log2), hi, lo);
+  return check_launch("se_split_f16");
+}
+
+extern "C" int se_gemm_f16x3(const unsigned short* a_hi, const unsigned short* a_lo, long long lda,
+                             const unsigned short* b_hi, const unsigned short* b_lo, long long ldb, int M, int N, int K,
+                             int scale_log2_ab, const float* bias, int act, float act_param, float alpha,
+                             const float* res, float* C, float* c_hi, float* c_lo, unsigned short* c16_hi,
+                             unsigned short* c16_lo, int c16_scale_log2, long long ldc, se_stream_t stream) {
+  SE_REQUIRE(a_hi && a_lo && b_hi && b_lo && (C || c_hi || c16_hi), "se_gemm_f16x3: null pointer");
+  SE_REQUIRE((c_hi == nullptr) == (c_lo == nullptr) && (c16_hi == nullptr) == (c16_lo == nullptr),
+             "se_gemm_f16x3: hi / lo outputs go together");
+  SE_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, "se_gemm_f16x3: K=%d must be a multiple of 8", K);
+  SE_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0, "se_gemm_f16x3: operand leading dims must be %% 8");
+  SE_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && (((uintptr_t)C) & 3) == 0,
+             "se_gemm_f16x3: pointers must be 16-byte aligned");
+  SE_REQUIRE((ldc & 3) != 0 || ((!C || aligned16(C)) && (!c_hi || (aligned16(c_hi) && aligned16(c_lo))) &&
+                                (!c16_hi || (aligned16(c16_hi) && aligned16(c16_lo))) && (!res || aligned16(res))),
+             "se_gemm_f16x3: outputs must be 16-byte aligned when ldc %% 4 == 0");
+  TcParams p{};
+  p.M = M;
+  p.N = N;
+  p.bias = bias;
+  p.act = act;
+  p.act_param = act_param;
+  p.alpha = alpha;
+  p.res = res;
+  p.C = C;
+  p.c_hi = c_hi;
+  p.c_lo = c_lo;
+  p.c16_hi = c16_hi;
+  p.c16_lo = c16_lo;
+  p.c16_scale = ldexpf(1.0f, c16_scale_log2);
+  p.ldc = ldc;
+  p.out_scale = ldexpf(1.0f, -scale_log2_ab);
+  int rc = launch_tc(EPI_BIAS_ACT, a_hi, a_lo, lda, K, nullptr, nullptr, 0, 0, b_hi, b_lo, ldb, p, (cudaStream_t)stream, true);
+  if (rc) return rc;
+  return check_launch("se_gemm_f16x3");
+}
+
+extern "C" int se_lstm_cell_f16x3(const unsigned short* x_hi, const unsigned short* x_lo, long long ldx, int Kx,
+                                  const unsigned short* h_hi, const unsigned short* h_lo, long long ldh, int H,
+                                  const unsigned short* w_hi, const unsigned short* w_lo, long long ldw,
+                                  int scale_log2_a, int scale_log2_w, const float* bias, int M, float* c_state,
+                                  unsigned short* h_hi_out, unsigned short* h_lo_out, float* h_out, long long ld_hout,
+                                  int first_step, se_stream_t stream) {
+  SE_REQUIRE(x_hi && x_lo && w_hi && w_lo && bias && c_state && h_hi_out && h_lo_out, "se_lstm_cell_f16x3: null pointer");
+  SE_REQUIRE(first_step || (h_hi && h_lo), "se_lstm_cell_f16x3: state pointers are required after the first step");
+  SE_REQUIRE(M > 0 && Kx > 0 && Kx % 8 == 0 && H > 0 && H % 32 == 0, "se_lstm_cell_f16x3: Kx=%d (%%8) H=%d (%%32)", Kx, H);
+  SE_REQUIRE((ldx & 7) == 0 && (ldh & 7) == 0 && (ldw & 7) == 0 && (ld_hout & 7) == 0 && ld_hout >= H,
+             "se_lstm_cell_f16x3: leading dims must be %% 8 (ld_hout=%lld)", ld_hout);
+  SE_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(h_hi) && aligned16(h_lo) && aligned16(w_hi) &&
+                 aligned16(w_lo) && aligned16(c_state) && aligned16(h_hi_out) && aligned16(h_lo_out) &&
+                 (!h_out || aligned16(h_out)) && aligned16(bias),
+             "se_lstm_cell_f16x3: pointers must be 16-byte aligned");
+  SE_REQUIRE(first_step || (h_hi != h_hi_out && h_lo != h_lo_out), "se_lstm_cell_f16x3: state must be double buffered");
+  TcParams p{};
+  p.M = M;
+  p.N = 4 * H;
+  p.bias = bias;
+  p.c_state = c_state;
+  p.h_hi = reinterpret_cast<float*>(h_hi_out);     // fp16 data in the F16 kernels
+  p.h_lo = reinterpret_cast<float*>(h_lo_out);
+  p.h_out = h_out;
+  p.H = H;
+  p.ld_hout = ld_hout;
+  p.first_step = first_step ? 1 : 0;
+  p.out_scale = ldexpf(1.0f, -(scale_log2_a + scale_log2_w));
+  p.c16_scale = ldexpf(1.0f, scale_log2_a);        // h leaves with the scale the next step's A operand expects
+  int rc = launch_tc(EPI_LSTM_CELL, x_hi, x_lo, ldx, Kx, h_hi, h_lo, ldh, first_step ? 0 : H, w_hi, w_lo, ldw, p,
+                     (cudaStream_t)stream, true);
+  if (rc) return rc;
+  return check_launch("se_lstm_cell_f16x3");
 }

@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA / mbarrier PTX wrappers shared by the tensor-core kernels (sm_100a).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -69,6 +70,18 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with fp16 operands (kind::f16: K = 16 per instruction, twice the rate of kind::tf32)
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc,
+                                         unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
@@ -120,6 +133,17 @@ __device__ __forceinline__ void umma_tf32_pair(unsigned tmem_d, uint64_t adesc, 
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc,
+                                              unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -206,7 +230,25 @@ constexpr unsigned make_idesc_tf32(int m, int n) {
          | (0u << 15) | (0u << 16)      // A, B K-major
          | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
+constexpr unsigned make_idesc_f16(int m, int n) {
+  return (1u << 4)                      // D format: F32
+         | (0u << 7) | (0u << 10)       // A, B format: F16
+         | (0u << 15) | (0u << 16)      // A, B K-major
+         | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
 
+// fp16 operand pair: x * scale = hi + lo  (scale a power of two).  22 significand bits like a TF32 pair wherever
+// |x * scale| >= 2^-3 (lo stays a normal fp16), an absolute floor of 2^-25 / scale below that; |x * scale| beyond the
+// fp16 range saturates instead of turning into inf (hi = +-65504, lo = the saturated rest).
+__device__ __forceinline__ void split_f16_dev(float x, float scale, unsigned short& hi, unsigned short& lo) {
+  const float xs = x * scale;
+  unsigned short h, l;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;\n" : "=h"(h) : "f"(xs));
+  const float r = xs - __half2float(__ushort_as_half(h));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;\n" : "=h"(l) : "f"(r));
+  hi = h;
+  lo = l;
+}
 
 __device__ __forceinline__ void split_tf32_dev(float x, float& hi, float& lo) {
   unsigned hb, lb;

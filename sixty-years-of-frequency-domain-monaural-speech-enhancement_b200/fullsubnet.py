@@ -68,6 +68,8 @@ class Model(nn.Module):
             pre = "sb_model.sequence_model"
             P[f"sb{l}"] = packing.pack_lstm_cell(sd[f"{pre}.weight_ih_l{l}"], sd[f"{pre}.weight_hh_l{l}"],
                                                  sd[f"{pre}.bias_ih_l{l}"], sd[f"{pre}.bias_hh_l{l}"])
+            P[f"sb{l}_f16"] = packing.pack_lstm_cell_f16(sd[f"{pre}.weight_ih_l{l}"], sd[f"{pre}.weight_hh_l{l}"],
+                                                         sd[f"{pre}.bias_ih_l{l}"], sd[f"{pre}.bias_hh_l{l}"])
         w = sd["fb_model.fc_output_layer.weight"].contiguous()
         P["fb_fc_hi"], P["fb_fc_lo"] = packing.split_tf32(w)
         P["fb_fc_kn"] = packing.pad_cols(w.t().contiguous())
@@ -128,10 +130,27 @@ class Model(nn.Module):
         nn_ = self.sb_num_neighbors
         inv_sb = ops.fsn_clip_inv_mean(mag_tm, (tp * f, f, 1), b, tp, f, denom=float(f * self.sb_in * tp),
                                        wgt=P["unfold_count"], extra=fb_out)
-        sbx_hi, sbx_lo = ops.fsn_sb_assemble(mag_tm, fb_out, nn_, inv_sb)      # [Tp, B*F, 32]
         m, hd = b * f, self.sb_hidden
-        L0, L1 = P["sb0"], P["sb1"]
         z = lambda: torch.zeros(m, hd, device=dev, dtype=torch.float32)   # noqa: E731
+        if lstm_engine.USE_F16_PAIRS:
+            # fp16 operand pairs: x, h and W travel as scaled fp16 (hi, lo); half the MMAs and bytes of the TF32 pairs
+            sbx_hi, sbx_lo = ops.fsn_sb_assemble_f16(mag_tm, fb_out, nn_, inv_sb)      # [Tp, B*F, 32] fp16
+            L0, L1 = P["sb0_f16"], P["sb1_f16"]
+            z16 = lambda: torch.zeros(m, hd, device=dev, dtype=torch.float16)   # noqa: E731
+            h0 = [(z16(), z16()), (z16(), z16())]
+            h1 = [(z16(), z16()), (z16(), z16())]
+            c0, c1 = z(), z()
+            h1_out = torch.empty(m, hd, device=dev, dtype=torch.float32)
+            mask = torch.empty(tp, m, 2, device=dev, dtype=torch.float32)
+            for s in range(tp):
+                src0, dst0 = h0[s & 1], h0[(s + 1) & 1]
+                src1, dst1 = h1[s & 1], h1[(s + 1) & 1]
+                ops.lstm_cell_f16x3((sbx_hi[s], sbx_lo[s]), src0, L0, c0, dst0[0], dst0[1])
+                ops.lstm_cell_f16x3(dst0, src1, L1, c1, dst1[0], dst1[1], h1_out)
+                ops.fsn_sb_fc(h1_out, P["sb_fc_w"], P["sb_fc_b"], mask[s])
+            return mask.view(tp, b, f, 2).permute(1, 3, 2, 0)[:, :, :, self.look_ahead:]
+        sbx_hi, sbx_lo = ops.fsn_sb_assemble(mag_tm, fb_out, nn_, inv_sb)      # [Tp, B*F, 32]
+        L0, L1 = P["sb0"], P["sb1"]
         h0 = [(z(), z()), (z(), z())]      # layer-0 state (hi, lo), double buffered by step parity
         h1 = [(z(), z()), (z(), z())]
         c0, c1 = z(), z()

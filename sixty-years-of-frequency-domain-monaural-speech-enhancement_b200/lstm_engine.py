@@ -8,7 +8,12 @@ from __future__ import annotations
 
 from . import ops
 
+import os
+
 USE_TENSOR_CORES = True   # flipped by tests / bench A-B runs only
+# fp16 operand pairs (tcgen05 kind::f16) instead of TF32 pairs where a model has the f16 packing: the same 22-bit
+# products at twice the MMA rate.  SE_F16_PAIRS=0 restores the 3xTF32 path everywhere (A/B runs).
+USE_F16_PAIRS = os.environ.get("SE_F16_PAIRS", "1") != "0"
 
 
 def input_projection(seq2d, layer, pair=None):

@@ -310,6 +310,108 @@ def lstm_cell_tf32x3_ex(x_pair, h_pair, w_hi, w_lo, bias, c_state, h_hi_out, h_l
                                                  1 if h_hi is None else 0, _stream()), "se_lstm_cell_tf32x3_ex")
 
 
+# ---- fp16-pair tensor-core path (kind::f16; see include/se_b200.h "fp16 operand PAIRS") ----------------------------
+F16_ACT_SCALE_LOG2 = 4
+
+
+def _need_cuda_any(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SeB200Error("se_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def split_f16(x2d, kpad=None, scale_log2=F16_ACT_SCALE_LOG2):
+    """x2d [rows, K] fp32 (row stride free, unit column stride) -> (hi, lo) fp16 [rows, kpad] with
+    x * 2^scale_log2 = hi + lo (columns K.. zero)."""
+    _need_cuda(x2d)
+    device_check()
+    rows, k = x2d.shape
+    assert x2d.stride(1) == 1
+    kpad = kpad or (k + 7) // 8 * 8
+    hi = torch.empty(rows, kpad, device=x2d.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    with _Timed("split_f16"):
+        check(_lib.load().se_split_f16(_ptr(x2d), rows, k, x2d.stride(0), kpad, scale_log2, _ptr(hi), _ptr(lo),
+                                       _stream()), "se_split_f16")
+    return hi, lo
+
+
+def gemm_f16x3(a_pair, b_pair, b_scale_log2, bias, n_out, act="none", out=None, a_scale_log2=F16_ACT_SCALE_LOG2,
+               act_param=0.0, alpha=1.0, res=None, want_out=True, pair_out=False, pair16_out=False,
+               c16_scale_log2=F16_ACT_SCALE_LOG2):
+    """(a_hi+a_lo) [M,K] @ (b_hi+b_lo) [N,Kb]^T (+bias, act) -> [M, n_out] on tcgen05 with fp16 operand pairs.
+    Returns out, or (out, (hi, lo) TF32 pair, (hi, lo) fp16 pair) members as requested."""
+    a_hi, a_lo = a_pair
+    b_hi, b_lo = b_pair
+    _need_cuda_any(a_hi, a_lo, b_hi, b_lo)
+    _need_cuda(bias, res, out)
+    device_check()
+    assert a_hi.dtype == torch.float16 and b_hi.dtype == torch.float16
+    m, k = a_hi.shape
+    n = b_hi.shape[0]
+    assert n == n_out and b_hi.shape[1] >= k and a_hi.stride(1) == 1 and b_hi.stride(1) == 1
+    assert a_lo.stride() == a_hi.stride() and b_lo.stride() == b_hi.stride()
+    dev = a_hi.device
+    if out is None and want_out:
+        out = torch.empty(m, n_out, device=dev, dtype=torch.float32)
+    ldc = out.stride(0) if out is not None else n_out
+    c_hi = c_lo = c16_hi = c16_lo = None
+    if pair_out:
+        c_hi = torch.empty(m, ldc, device=dev, dtype=torch.float32)
+        c_lo = torch.empty_like(c_hi)
+    if pair16_out:
+        c16_hi = torch.empty(m, ldc, device=dev, dtype=torch.float16)
+        c16_lo = torch.empty_like(c16_hi)
+    with _Timed(f"gemm_f16x3[K={k},N={n}]"):
+        check(_lib.load().se_gemm_f16x3(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(b_hi), _ptr(b_lo), b_hi.stride(0),
+                                        m, n, k, a_scale_log2 + b_scale_log2, _ptr(bias), ACT[act], float(act_param),
+                                        float(alpha), _ptr(res), _ptr(out), _ptr(c_hi), _ptr(c_lo), _ptr(c16_hi),
+                                        _ptr(c16_lo), c16_scale_log2, ldc, _stream()), "se_gemm_f16x3")
+    if not (pair_out or pair16_out):
+        return out
+    return out, ((c_hi, c_lo) if pair_out else None), ((c16_hi, c16_lo) if pair16_out else None)
+
+
+def lstm_cell_f16x3(x_pair, h_pair, cell, c_state, h_hi_out, h_lo_out, h_out=None, a_scale_log2=F16_ACT_SCALE_LOG2):
+    """One fused LSTM step for M independent sequences on fp16 operand pairs (se_lstm_cell_f16x3).  ``cell`` is
+    packing.pack_lstm_cell_f16's dict; x_pair [M, Kx] and h_pair [M, H] are fp16 pairs scaled by 2^a_scale_log2
+    (h_pair=None: zero initial state); the new h leaves in h_hi_out / h_lo_out with the same scale."""
+    x_hi, x_lo = x_pair
+    h_hi, h_lo = h_pair if h_pair is not None else (None, None)
+    _need_cuda_any(x_hi, x_lo, h_hi, h_lo, cell["w_hi"], cell["w_lo"], h_hi_out, h_lo_out)
+    _need_cuda(cell["bias"], c_state, h_out)
+    device_check()
+    m, kx = x_hi.shape
+    hdim = cell["hidden"]
+    w_hi, w_lo = cell["w_hi"], cell["w_lo"]
+    assert x_hi.dtype == torch.float16 and h_hi_out.dtype == torch.float16 and w_hi.dtype == torch.float16
+    assert kx <= cell["kx_pad"] and w_hi.shape == (4 * hdim, cell["kx_pad"] + hdim)
+    assert x_hi.stride(1) == 1 and x_lo.stride() == x_hi.stride()
+    assert c_state.is_contiguous() and c_state.shape == (m, hdim)
+    ldo = h_hi_out.stride(0)
+    assert h_hi_out.stride(1) == 1 and h_lo_out.stride() == h_hi_out.stride()
+    assert h_out is None or h_out.stride() == h_hi_out.stride()
+    assert h_hi is None or (h_hi.stride(1) == 1 and h_lo.stride() == h_hi.stride())
+    with _Timed("lstm_cell_f16x3"):
+        check(_lib.load().se_lstm_cell_f16x3(_ptr(x_hi), _ptr(x_lo), x_hi.stride(0), kx, _ptr(h_hi), _ptr(h_lo),
+                                             h_hi.stride(0) if h_hi is not None else hdim, hdim, _ptr(w_hi), _ptr(w_lo),
+                                             w_hi.stride(0), a_scale_log2, cell["w_scale_log2"], _ptr(cell["bias"]), m,
+                                             _ptr(c_state), _ptr(h_hi_out), _ptr(h_lo_out), _ptr(h_out), ldo,
+                                             1 if h_hi is None else 0, _stream()), "se_lstm_cell_f16x3")
+
+
+def fsn_sb_assemble_f16(mag_tm, fb, nn, inv, scale_log2=F16_ACT_SCALE_LOG2):
+    _need_cuda(mag_tm, fb, inv)
+    B, Tp, F = mag_tm.shape
+    w = 2 * nn + 2
+    hi = torch.empty(Tp, B * F, w, device=mag_tm.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    with _Timed("fsn_sb_assemble"):
+        check(_lib.load().se_fsn_sb_assemble_f16(_ptr(mag_tm), _ptr(fb), B, Tp, F, nn, _ptr(inv), scale_log2, _ptr(hi),
+                                                 _ptr(lo), _stream()), "se_fsn_sb_assemble_f16")
+    return hi, lo
+
+
 def cmul(x, m):
     """x, m [..., 2] interleaved complex -> x * m."""
     _need_cuda(x, m)

@@ -138,3 +138,35 @@ def pack_lstm_cell(w_ih, w_hh, b_ih, b_hh, kx_pad=None):
     w[:, kx_pad:] = w_hh[rows]
     hi, lo = split_tf32(w)
     return {"w_hi": hi, "w_lo": lo, "bias": (b_ih + b_hh)[rows].contiguous(), "hidden": hidden, "kx": kx_pad}
+
+
+F16_ACT_SCALE_LOG2 = 4     # activations of the fp16-pair GEMMs travel as x * 2^4 = hi + lo (|x| < 4094, floor 2e-9)
+
+
+def split_f16(x, scale_log2=None):
+    """x -> (hi, lo, s): IEEE fp16 tensors with x * 2^s = hi + lo, the operand format of the fp16-pair tensor-core GEMM
+    (csrc/gemm_tc.cu, kind::f16).  s defaults to the power of two that puts max|x| in [2^13, 2^14) (weights)."""
+    x = x.float()
+    if scale_log2 is None:
+        amax = float(x.abs().max())
+        scale_log2 = 0 if amax == 0.0 else 13 - int(torch.floor(torch.log2(torch.tensor(amax, dtype=torch.float64))))
+        scale_log2 = max(-14, min(15, scale_log2))
+    xs = x * float(2.0 ** scale_log2)
+    hi = xs.clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = (xs - hi.float()).clamp(-65504.0, 65504.0).to(torch.float16)
+    return hi.contiguous(), lo.contiguous(), scale_log2
+
+
+def pack_lstm_cell_f16(w_ih, w_hh, b_ih, b_hh):
+    """pack_lstm_cell for se_lstm_cell_f16x3: [W_ih zero-padded to a multiple of 64 | W_hh], rows in tile order, fp16 pair
+    with one per-tensor scale.  Returns dict(w_hi, w_lo, w_scale_log2, bias, hidden, kx)."""
+    hidden = w_hh.shape[1]
+    kx = w_ih.shape[1]
+    kx_pad = (kx + 63) // 64 * 64
+    rows = tile_rows(hidden).to(w_ih.device)
+    w = w_ih.new_zeros(4 * hidden, kx_pad + hidden)
+    w[:, :kx] = w_ih[rows]
+    w[:, kx_pad:] = w_hh[rows]
+    hi, lo, s = split_f16(w)
+    return {"w_hi": hi, "w_lo": lo, "w_scale_log2": s, "bias": (b_ih + b_hh)[rows].contiguous(), "hidden": hidden,
+            "kx": kx, "kx_pad": kx_pad}

@@ -804,3 +804,87 @@ def test_conv_tf32x3_gated_epilogue(case):
     err_pair = ((got_hi + got_lo).cpu().double() - ref).abs().max().item()
     print(f"gated conv {case}: max err {err:.3e} (hi+lo {err_pair:.3e})")
     assert err < 2e-5 and err_pair < 2e-5
+
+
+@pytest.mark.parametrize("m,k,n,act", [(256, 64, 256, "none"), (300, 1024, 256, "none"), (1000, 192, 4096, "softplus"),
+                                       (2309, 2048, 512 + 164, "none"), (25664, 1024, 4096, "none"),
+                                       (130, 40, 24, "relu")])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_gemm_f16x3_fp32_accuracy(m, k, n, act, engine):
+    """fp16-pair GEMM (tcgen05 kind::f16, three products of scaled hi/lo halves): fp32-class error vs fp64, at least as
+    good as the 3xTF32 engine on the same data; also the fp16-pair / TF32-pair copies of the output it can emit."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g) * 3.0
+    a[0, 0] = 900.0                        # far-out activations stay inside the fp16 range at scale 2^4
+    a[1, : min(k, 8)] = 1e-5               # and tiny ones keep an absolute floor of 2^-29
+    w = torch.randn(n, k, generator=g) / np.sqrt(k)
+    bias = torch.randn(n, generator=g)
+    w_hi, w_lo, ws = packing.split_f16(w)
+    assert ((w_hi.double() + w_lo.double()) * 2.0 ** -ws - w.double()).abs().max().item() < 2e-7 * w.abs().max().item()
+    a_pair = ops.split_f16(a.to(dev))
+    back = (a_pair[0].double() + a_pair[1].double()).cpu()[:, :k] / 16.0
+    assert bool(((back - a.double()).abs() <= 2.0 ** -21 * a.double().abs() + 2.0 ** -28).all())   # 22 bits or the floor
+    rows = torch.unique(torch.cat([torch.arange(0, min(m, 300)), torch.arange(max(0, m - 300), m),
+                                   torch.randint(0, m, (256,), generator=g)]))
+    ref = emu_ops._act(a[rows].double() @ w.double().t() + bias.double(), act)
+    try:
+        ops.set_gemm_engine(engine)
+        got, p32, p16 = ops.gemm_f16x3(a_pair, (w_hi.to(dev), w_lo.to(dev)), ws, bias.to(dev), n, act, pair_out=True,
+                                       pair16_out=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
+    err = (got.cpu()[rows].double() - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    e32 = ((p32[0] + p32[1]).cpu()[rows].double() - got.cpu()[rows].double()).abs().max().item()
+    e16 = ((p16[0].double() + p16[1].double()).cpu()[rows] / 16.0 - got.cpu()[rows].double()).abs().max().item()
+    print(f"gemm_f16x3 engine {engine} {m}x{k}x{n}: max err vs fp64 {err:.3e} (|ref| max {scale:.1f}), "
+          f"TF32-pair copy {e32:.2e}, fp16-pair copy {e16:.2e}")
+    assert err < 1e-5 * scale and e32 < 1e-6 * scale and e16 < 1e-6 * scale
+
+
+@pytest.mark.parametrize("m,kx,h,steps", [(300, 32, 384, 4), (8224, 32, 384, 3), (1031, 64, 128, 3)])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_lstm_cell_f16x3_matches_recurrence(m, kx, h, steps, engine):
+    """Fused LSTM cell on fp16 operand pairs vs the float64 recurrence (and hence vs the TF32 cell's 1e-5 gate)."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    ops = se_b200.ops
+    g = torch.Generator().manual_seed(m + h)
+    w_ih = torch.randn(4 * h, kx, generator=g) / np.sqrt(kx)
+    w_hh = torch.randn(4 * h, h, generator=g) / np.sqrt(h)
+    b_ih = torch.randn(4 * h, generator=g) * 0.1
+    b_hh = torch.randn(4 * h, generator=g) * 0.1
+    xs = torch.randn(steps, m, kx, generator=g) * 2.0
+    P = packing.pack_lstm_cell_f16(w_ih, w_hh, b_ih, b_hh)
+    P = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in P.items()}
+    c = torch.zeros(m, h, device=dev)
+    z16 = lambda: torch.zeros(m, h, device=dev, dtype=torch.float16)   # noqa: E731
+    hbuf = [(z16(), z16()), (z16(), z16())]
+    hout = torch.empty(m, h, device=dev)
+    hr = torch.zeros(m, h, dtype=torch.float64)
+    cr = torch.zeros(m, h, dtype=torch.float64)
+    try:
+        ops.set_gemm_engine(engine)
+        for t in range(steps):
+            x_pair = ops.split_f16(xs[t].to(dev))
+            src, dst = hbuf[t & 1], hbuf[(t + 1) & 1]
+            ops.lstm_cell_f16x3(x_pair, None if t == 0 else src, P, c, dst[0], dst[1], hout)
+            gates = xs[t].double() @ w_ih.double().t() + hr @ w_hh.double().t() + (b_ih + b_hh).double()
+            i, f, gg, o = gates.chunk(4, dim=1)
+            cr = torch.sigmoid(f) * cr + torch.sigmoid(i) * torch.tanh(gg)
+            hr = torch.sigmoid(o) * torch.tanh(cr)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
+    e_h = (hout.cpu().double() - hr).abs().max().item()
+    e_c = (c.cpu().double() - cr).abs().max().item()
+    e_split = ((dst[0].double() + dst[1].double()).cpu() / 16.0 - hr).abs().max().item()
+    print(f"lstm_cell_f16 engine {engine} M={m} Kx={kx} H={h} steps={steps}: h err {e_h:.3e} c err {e_c:.3e} "
+          f"hi+lo err {e_split:.3e}")
+    assert e_h < 1e-5 and e_c < 1e-5 and e_split < 1e-5
