@@ -373,6 +373,35 @@ typedef struct se_conv_tc_desc {
 } se_conv_tc_desc;
 int se_conv_tf32x3(const se_conv_tc_desc* desc, se_stream_t stream);
 
+/* se_conv_tf32x3 on fp16 operand pairs (see "fp16 operand PAIRS" above; csrc/conv_f16.cu): activations [B,T,F,C] and
+ * weights are (hi, lo) fp16 pairs scaled by 2^scale_log2_a / 2^scale_log2_w.  A k-block is a 64-channel slice: C0 / C1
+ * only need to be multiples of 8 (the TMA unit zero-fills the rest of a slice), the packed weights are
+ * [Cout][ntaps * (pad64(C0) + pad64(C1))] with zero columns in the padding.  Outputs: fp32 `out`, the TF32 pair and / or
+ * the fp16 pair (scaled by 2^out16_scale_log2) for the layer that follows.  Replaces the same reference layers as
+ * se_conv_tf32x3 / se_conv_gemm (nn.Conv2d / nn.ConvTranspose2d of CRN/CRN.py:35-109, DCCRN/DCCRN_cprs.py:60-132, ...). */
+typedef struct se_conv_f16_desc {
+  const unsigned short *src0_hi, *src0_lo, *src1_hi, *src1_lo;
+  int C0, C1;
+  int B, T, Fin, Fout;
+  int ntaps;
+  int dt[SE_MAX_TAPS];
+  int df[SE_MAX_TAPS];
+  int sf;
+  const unsigned short *w_hi, *w_lo;
+  int scale_log2_a, scale_log2_w;
+  const float* bias;
+  int Cout;
+  int act;
+  float act_param;
+  float *out, *out_hi, *out_lo;
+  unsigned short *out16_hi, *out16_lo;
+  int out16_scale_log2;
+  int dstF, dst_f0, dst_fstep;
+  int glu;
+  const float *glu_scale, *glu_shift;
+} se_conv_f16_desc;
+int se_conv_f16x3(const se_conv_f16_desc* d, se_stream_t stream);
+
 /* GCRN gated-conv tail and skip re-activation (csrc/pointwise.cu):
  *   se_glu_affine_act: x [rows, 2C] = [conv1 | conv2] -> act((conv1 * sigmoid(conv2)) * scale[c] + shift[c])
  *                      (GluConv2d + eval BatchNorm2d + ELU, GCRN/GCRN_noncprs.py:55-57,138); scale/shift may be NULL.

@@ -50,6 +50,21 @@ class ConvTcDesc(C.Structure):
     ]
 
 
+class ConvF16Desc(C.Structure):
+    """se_conv_f16_desc (include/se_b200.h)."""
+    _fields_ = [
+        ("src0_hi", C.c_void_p), ("src0_lo", C.c_void_p), ("src1_hi", C.c_void_p), ("src1_lo", C.c_void_p),
+        ("C0", C.c_int), ("C1", C.c_int), ("B", C.c_int), ("T", C.c_int), ("Fin", C.c_int), ("Fout", C.c_int),
+        ("ntaps", C.c_int), ("dt", C.c_int * SE_MAX_TAPS), ("df", C.c_int * SE_MAX_TAPS), ("sf", C.c_int),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("scale_log2_a", C.c_int), ("scale_log2_w", C.c_int),
+        ("bias", C.c_void_p), ("Cout", C.c_int), ("act", C.c_int), ("act_param", C.c_float),
+        ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("out16_hi", C.c_void_p), ("out16_lo", C.c_void_p), ("out16_scale_log2", C.c_int),
+        ("dstF", C.c_int), ("dst_f0", C.c_int), ("dst_fstep", C.c_int),
+        ("glu", C.c_int), ("glu_scale", C.c_void_p), ("glu_shift", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list EVERY symbol include/se_b200.h declares
 _LL, _I, _F, _P = C.c_longlong, C.c_int, C.c_float, C.c_void_p
 PROTOTYPES = {
@@ -89,6 +104,7 @@ PROTOTYPES = {
     "se_gemm_f16x3": (_I, [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _I, _F, _F, _P, _P, _P, _P, _P, _P, _I, _LL, _P]),
     "se_lstm_cell_f16x3": (_I, [_P, _P, _LL, _I, _P, _P, _LL, _I, _P, _P, _LL, _I, _I, _P, _I, _P, _P, _P, _P, _LL, _I, _P]),
     "se_conv_tf32x3": (_I, [C.POINTER(ConvTcDesc), _P]),
+    "se_conv_f16x3": (_I, [C.POINTER(ConvF16Desc), _P]),
     "se_uf_prep": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "se_uf_fusion": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
     "se_uf_fusion_ex": (_I, [_P, _P, _LL, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libse_b200.so")
-SOURCES = ["api.cu", "dsp.cu", "gemm.cu", "gemm_tc.cu", "lstm.cu", "fullsubnet.cu", "dccrn.cu", "conv_tc.cu", "uformer.cu", "pointwise.cu", "lstm_tc.cu", "lstm_f16.cu", "norm.cu", "plan_crn.cu"]
+SOURCES = ["api.cu", "dsp.cu", "gemm.cu", "gemm_tc.cu", "lstm.cu", "fullsubnet.cu", "dccrn.cu", "conv_tc.cu", "conv_f16.cu", "uformer.cu", "pointwise.cu", "lstm_tc.cu", "lstm_f16.cu", "norm.cu", "plan_crn.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",

@@ -2,9 +2,12 @@
 ConvTranspose2d parity class goes either to the tensor-core implicit GEMM (csrc/conv_tc.cu, 3xTF32,
 needs channel counts that are multiples of 32) or to the fp32 FMA implicit GEMM (csrc/gemm.cu).
 
-Activations travel between layers as :class:`Act`: the fp32 tensor and/or its TF32 (hi, lo) split.
-A tensor-core layer writes the split of its output in its epilogue, so consecutive tensor-core
-layers need no separate split pass.
+Activations travel between layers as :class:`Act`: the fp32 tensor and/or its (hi, lo) operand pair.
+A tensor-core layer writes the pair of its output in its epilogue, so consecutive tensor-core
+layers need no separate split pass.  The pair is either a TF32 pair (two fp32 tensors, 3xTF32 kernels)
+or an fp16 pair (two fp16 tensors scaled by 2^ops.F16_ACT_SCALE_LOG2, kind::f16 kernels: twice the MMA
+rate, half the bytes); a model opts into the latter per activation (``new_act(..., f16=True)``) and
+``conv`` follows the dtype of what it is given.
 """
 from __future__ import annotations
 
@@ -24,10 +27,27 @@ class Act:
     def shape(self):
         return (self.f32 if self.f32 is not None else self.pair[0]).shape
 
-    def get_pair(self):
+    def get_pair(self, f16=False):
         if self.pair is None:
-            self.pair = ops.split_tf32(self.f32)
+            if f16:
+                x = self.f32
+                hi, lo = ops.split_f16(x.view(-1, x.shape[-1]))
+                self.pair = (hi.view(x.shape), lo.view(x.shape))
+            else:
+                self.pair = ops.split_tf32(self.f32)
         return self.pair
+
+    @property
+    def is_f16(self):
+        return self.pair is not None and self.pair[0].dtype == torch.float16
+
+    def value(self):
+        """fp32 value of this activation (taps / tests)."""
+        if self.f32 is not None:
+            return self.f32
+        if self.is_f16:
+            return (self.pair[0].float() + self.pair[1].float()) * (2.0 ** -ops.F16_ACT_SCALE_LOG2)
+        return self.pair[0] + self.pair[1]
 
     def get_f32(self):
         if self.f32 is None:
@@ -38,16 +58,25 @@ class Act:
 class ConvWeights:
     """One conv (or one output-column parity of a transposed conv): K-major fp32 for the FMA kernel
     and [Cout, K] TF32 pair for the tensor-core kernel."""
-    __slots__ = ("kn", "hi", "lo", "cout")
+    __slots__ = ("kn", "hi", "lo", "cout", "_f16")
 
     def __init__(self, w_kn, cout):
         self.kn = packing.pad_cols(w_kn)
         self.hi, self.lo = packing.split_tf32(w_kn[:, :cout].t().contiguous())
         self.cout = cout
+        self._f16 = {}
+
+    def f16(self, ntaps, c0, c1):
+        """(hi, lo, scale_log2) fp16 pair in the se_conv_f16x3 layout, packed on first use."""
+        key = (ntaps, c0, c1)
+        if key not in self._f16:
+            self._f16[key] = packing.pack_conv_f16(self.kn[:, :self.cout].t().contiguous(), ntaps, c0, c1)
+        return self._f16[key]
 
 
-def tc_eligible(c0, c1, cout, fout, sf):
-    return (lstm_engine.USE_TENSOR_CORES and c0 % 32 == 0 and c1 % 32 == 0 and cout % 4 == 0 and cout >= 4
+def tc_eligible(c0, c1, cout, fout, sf, f16=False):
+    cm = 8 if f16 else 32            # fp16 k-blocks are zero-filled past the last channel
+    return (lstm_engine.USE_TENSOR_CORES and c0 % cm == 0 and c1 % cm == 0 and cout % 4 == 0 and cout >= 4
             and fout <= 128 and (fout - 1) * sf + 1 <= 256)
 
 
@@ -58,6 +87,18 @@ def conv(src: Act, skip, B, T, Fin, Fout, taps, sf, w: ConvWeights, bias, act, d
     ``dst`` with w.cout / 2 channels); tensor-core layers only."""
     c0 = src.shape[-1]
     c1 = skip.shape[-1] if skip is not None else 0
+    f16 = src.is_f16 or (dst.is_f16 and src.pair is None)
+    if f16 and tc_eligible(c0, c1, w.cout, Fout, sf, True):
+        w_hi, w_lo, ws = w.f16(len(taps), c0, c1)
+        ops.conv_f16x3(src.get_pair(True), skip.get_pair(True) if skip is not None else None, B, T, Fin, Fout, taps, sf,
+                       w_hi, w_lo, ws, bias, w.cout, act, dstF, dst_f0, dst_fstep, act_param=act_param, out=dst.f32,
+                       out_pair16=dst.pair, glu=glu)
+        if fill_f >= 0:
+            if dst.f32 is not None:
+                ops.fill_column(dst.f32, fill, fill_f, act, act_param)
+            if dst.pair is not None:
+                raise NotImplementedError("fill column on a split-only output")
+        return
     if glu is not None and not tc_eligible(c0, c1, w.cout, Fout, sf):
         raise RuntimeError("the fused gate needs a tensor-core eligible layer")
     if tc_eligible(c0, c1, w.cout, Fout, sf):
@@ -79,6 +120,7 @@ def conv(src: Act, skip, B, T, Fin, Fout, taps, sf, w: ConvWeights, bias, act, d
             raise RuntimeError("split output requested from the FMA path: allocate dst without a pair and split")
 
 
-def new_act(b, t, f, c, device, want_f32, want_pair):
+def new_act(b, t, f, c, device, want_f32, want_pair, f16=False):
     mk = lambda: torch.empty(b, t, f, c, device=device, dtype=torch.float32)   # noqa: E731
-    return Act(mk() if want_f32 else None, (mk(), mk()) if want_pair else None)
+    mk16 = lambda: torch.empty(b, t, f, c, device=device, dtype=torch.float16)   # noqa: E731
+    return Act(mk() if want_f32 else None, ((mk16(), mk16()) if f16 else (mk(), mk())) if want_pair else None)

@@ -108,7 +108,7 @@ class crn_net(nn.Module):
         x = x.contiguous().float()
         b, t, f = x.shape
         assert f == self.N_BINS, f"CRN checkpoints are hard-wired to 161 bins, got {f}"
-        enc = self._encoder(x, taps)
+        enc = self._encoder(x, taps)      # tensor-core layers on fp16 operand pairs unless SE_F16_PAIRS=0
         h = enc[-1]
         # LSTM: two layers, input projection hoisted over all T
         seq, pair = (h.f32.view(b * t, 1024) if h.f32 is not None else None,
@@ -120,13 +120,14 @@ class crn_net(nn.Module):
             taps["lstm_nhwc"] = hs
         return self._decoder(hs, enc, taps)
 
-    def _encoder(self, x, taps=None):
+    def _encoder(self, x, taps=None, f16=None):
         """CRN/CRN.py:35-71 on a [B,T,161] plane -> the five channels-last encoder activations (the last one, [B,T,4,256],
-        is the LSTM input [B,T,1024])."""
+        is the LSTM input [B,T,1024]).  f16: operand pairs of the tensor-core layers (None = lstm_engine.USE_F16_PAIRS)."""
         P = self._packed
         b, t, _ = x.shape
         dev = x.device
-        tc = lambda c0, c1, co, fo, sf: conv_engine.tc_eligible(c0, c1, co, fo, sf)   # noqa: E731
+        f16 = lstm_engine.USE_F16_PAIRS if f16 is None else f16
+        tc = lambda c0, c1, co, fo, sf: conv_engine.tc_eligible(c0, c1, co, fo, sf, f16)   # noqa: E731
         enc = []
         w, bias = P["en0"]
         h = Act(ops.conv_in1(x, w, bias, 16, "elu", _ENC_F[1]))
@@ -137,22 +138,23 @@ class crn_net(nn.Module):
             is_tc = tc(ci, 0, co, _ENC_F[i + 1], 2)
             # every consumer of en2..en5 (next encoder layer / LSTM projection / decoder skip) is a
             # tensor-core layer when tensor cores are on: emit the TF32 split only
-            out = conv_engine.new_act(b, t, _ENC_F[i + 1], co, dev, want_f32=not is_tc, want_pair=is_tc)
+            out = conv_engine.new_act(b, t, _ENC_F[i + 1], co, dev, want_f32=not is_tc, want_pair=is_tc, f16=f16)
             conv_engine.conv(h, None, b, t, _ENC_F[i], _ENC_F[i + 1], packing.CONV23_TAPS, 2, w, bias, "elu", out,
                              _ENC_F[i + 1])
             h = out
             enc.append(h)
         if taps is not None:
             for i, e in enumerate(enc):
-                taps[f"en{i + 1}"] = e.f32 if e.f32 is not None else e.pair[0] + e.pair[1]
+                taps[f"en{i + 1}"] = e.value()
         return enc
 
-    def _decoder(self, hs, enc, taps=None):
+    def _decoder(self, hs, enc, taps=None, f16=None):
         """CRN/CRN.py:73-109: hs [B,T,1024] (NHWC-flattened LSTM output) + encoder skips -> [B,T,161]."""
         P = self._packed
         b, t = hs.shape[0], hs.shape[1]
         dev = hs.device
-        tc = lambda c0, c1, co, fo, sf: conv_engine.tc_eligible(c0, c1, co, fo, sf)   # noqa: E731
+        f16 = lstm_engine.USE_F16_PAIRS if f16 is None else f16
+        tc = lambda c0, c1, co, fo, sf: conv_engine.tc_eligible(c0, c1, co, fo, sf, f16)   # noqa: E731
         h = Act(hs.view(b, t, 4, 256))
         fin = 4
         for i in range(4):
@@ -164,7 +166,8 @@ class crn_net(nn.Module):
             c0, c1 = h.shape[-1], skip.shape[-1]
             is_tc = tc(c0, c1, co, fin + 1, 1)
             last = i == 3                                   # de4 feeds the fp32 direct kernel
-            out = conv_engine.new_act(b, t, fo, co, dev, want_f32=(not is_tc) or last, want_pair=is_tc and not last)
+            out = conv_engine.new_act(b, t, fo, co, dev, want_f32=(not is_tc) or last, want_pair=is_tc and not last,
+                                      f16=f16)
             conv_engine.conv(h, skip, b, t, fin, fin + 1, packing.DECONV_EVEN_TAPS, 1, we, bias, "elu", out, fo,
                              dst_f0=shift, dst_fstep=2)
             conv_engine.conv(h, skip, b, t, fin, fin, packing.DECONV_ODD_TAPS, 1, wo, bias, "elu", out, fo,
@@ -173,7 +176,7 @@ class crn_net(nn.Module):
             h = out
             fin = fo
             if taps is not None:
-                taps[f"de{i + 1}"] = h.f32 if h.f32 is not None else h.pair[0] + h.pair[1]
+                taps[f"de{i + 1}"] = h.value()
         h = h.f32
         enc0 = enc[0].f32
         y = ops.deconv_out1(h, enc0, P["de4_w"], P["de4_b"], "softplus")

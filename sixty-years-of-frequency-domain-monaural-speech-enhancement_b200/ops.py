@@ -8,7 +8,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ACT, ConvDesc, ConvTcDesc, check
+from ._lib import ACT, ConvDesc, ConvF16Desc, ConvTcDesc, check
 
 
 def _stream():
@@ -570,6 +570,45 @@ def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, a
     d.glu_shift = glu[1].data_ptr() if glu is not None and glu[1] is not None else 0
     with _Timed(f"conv_tf32x3[K={len(taps) * (c0 + c1)},N={Cout}]"):
         check(_lib.load().se_conv_tf32x3(C.byref(d), _stream()), "se_conv_tf32x3")
+
+
+def conv_f16x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, w_scale_log2, bias, Cout, act, dstF, dst_f0=0,
+               dst_fstep=1, act_param=0.0, out=None, out_pair=None, out_pair16=None, glu=None,
+               a_scale_log2=F16_ACT_SCALE_LOG2, out16_scale_log2=F16_ACT_SCALE_LOG2):
+    """conv_tf32x3 on fp16 operand pairs (se_conv_f16x3).  src0 / src1: (hi, lo) fp16 tuples of channels-last
+    [B,T,Fin,C] scaled by 2^a_scale_log2; w_hi / w_lo fp16 [Cout, ntaps*(pad64(C0)+pad64(C1))] scaled by 2^w_scale_log2
+    (packing.pack_conv_f16).  Outputs as requested: fp32, TF32 pair, fp16 pair (scaled by 2^out16_scale_log2)."""
+    device_check()
+    d = ConvF16Desc()
+    assert src0[0].dtype == torch.float16 and w_hi.dtype == torch.float16
+    d.src0_hi, d.src0_lo = src0[0].data_ptr(), src0[1].data_ptr()
+    c0 = src0[0].shape[-1]
+    c1 = src1[0].shape[-1] if src1 is not None else 0
+    d.src1_hi = src1[0].data_ptr() if src1 is not None else 0
+    d.src1_lo = src1[1].data_ptr() if src1 is not None else 0
+    d.C0, d.C1, d.B, d.T, d.Fin, d.Fout = c0, c1, B, T, Fin, Fout
+    d.ntaps = len(taps)
+    for i, (dt, df) in enumerate(taps):
+        d.dt[i], d.df[i] = dt, df
+    d.sf = sf
+    kpad = len(taps) * ((c0 + 63) // 64 * 64 + (c1 + 63) // 64 * 64)
+    assert w_hi.shape == (Cout, kpad) and w_hi.is_contiguous() and w_lo.is_contiguous(), (w_hi.shape, Cout, kpad)
+    d.w_hi, d.w_lo = w_hi.data_ptr(), w_lo.data_ptr()
+    d.scale_log2_a, d.scale_log2_w = a_scale_log2, w_scale_log2
+    d.bias = bias.data_ptr() if bias is not None else 0
+    d.Cout, d.act, d.act_param = Cout, ACT[act], float(act_param)
+    d.out = out.data_ptr() if out is not None else 0
+    d.out_hi = out_pair[0].data_ptr() if out_pair is not None else 0
+    d.out_lo = out_pair[1].data_ptr() if out_pair is not None else 0
+    d.out16_hi = out_pair16[0].data_ptr() if out_pair16 is not None else 0
+    d.out16_lo = out_pair16[1].data_ptr() if out_pair16 is not None else 0
+    d.out16_scale_log2 = out16_scale_log2
+    d.dstF, d.dst_f0, d.dst_fstep = dstF, dst_f0, dst_fstep
+    d.glu = 0 if glu is None else 1
+    d.glu_scale = glu[0].data_ptr() if glu is not None and glu[0] is not None else 0
+    d.glu_shift = glu[1].data_ptr() if glu is not None and glu[1] is not None else 0
+    with _Timed(f"conv_f16x3[K={len(taps) * (c0 + c1)},N={Cout}]"):
+        check(_lib.load().se_conv_f16x3(C.byref(d), _stream()), "se_conv_f16x3")
 
 
 def fill_column(dst, fill, fill_f, act, act_param=0.0):

@@ -112,8 +112,9 @@ def pack_lstm_layer(w_ih, w_hh, b_ih, b_hh, in_perm=None, unit_perm=None, in_sca
     kpad = -(-kin // 32) * 32          # the tensor-core GEMM wants K % 32 == 0: zero columns (LSTM.py:17 has K = 161)
     wi_tc = wi if kpad == kin else torch.cat([wi, wi.new_zeros(wi.shape[0], kpad - kin)], dim=1).contiguous()
     hi, lo = split_tf32(wi_tc)
+    h16, l16, s16 = pack_linear_f16(wi)
     return {"wih_kn": pad_cols(wi.t().contiguous()), "wih_hi": hi, "wih_lo": lo, "bias": bias.contiguous(),
-            "whh": whp, "hidden": hidden, "kin": kin}
+            "whh": whp, "hidden": hidden, "kin": kin, "wih16": (h16, l16), "wih16_scale": s16}
 
 
 def tile_rows(hidden):
@@ -170,3 +171,26 @@ def pack_lstm_cell_f16(w_ih, w_hh, b_ih, b_hh):
     hi, lo, s = split_f16(w)
     return {"w_hi": hi, "w_lo": lo, "w_scale_log2": s, "bias": (b_ih + b_hh)[rows].contiguous(), "hidden": hidden,
             "kx": kx, "kx_pad": kx_pad}
+
+
+def pack_conv_f16(w_nk, ntaps, c0, c1):
+    """[Cout, ntaps*(c0+c1)] fp32 conv weights (K order: tap, then [source 0 | source 1] channels) -> the fp16-pair
+    layout of se_conv_f16x3: every (tap, source) block zero-padded to a multiple of 64 channels.  Returns (hi, lo, s)."""
+    cout, k = w_nk.shape
+    assert k == ntaps * (c0 + c1)
+    p0, p1 = (c0 + 63) // 64 * 64, (c1 + 63) // 64 * 64
+    w = w_nk.new_zeros(cout, ntaps, p0 + p1)
+    src = w_nk.view(cout, ntaps, c0 + c1)
+    w[:, :, :c0] = src[:, :, :c0]
+    if c1:
+        w[:, :, p0:p0 + c1] = src[:, :, c0:]
+    return split_f16(w.view(cout, ntaps * (p0 + p1)))
+
+
+def pack_linear_f16(w_nk):
+    """nn.Linear / LSTM input weights [N, K] -> fp16 pair with K zero-padded to a multiple of 8.  Returns (hi, lo, s)."""
+    n, k = w_nk.shape
+    kp = (k + 7) // 8 * 8
+    if kp != k:
+        w_nk = torch.cat([w_nk, w_nk.new_zeros(n, kp - k)], dim=1)
+    return split_f16(w_nk.contiguous())

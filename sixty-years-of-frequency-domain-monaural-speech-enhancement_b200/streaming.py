@@ -103,7 +103,7 @@ class MagStream:
         model = self.model
         k = self.mag_hist.shape[1]
         mag = torch.cat([self.mag_hist, mag_new], 1).contiguous()           # local frames [0, k + tc)
-        enc = model._encoder(mag)
+        enc = model._encoder(mag, f16=False)      # the streaming path stays on TF32 pairs (its cells are packed that way)
         e5 = enc[-1]
         if e5.pair is None:
             e5.pair = ops.split_tf32(e5.f32)
@@ -114,7 +114,7 @@ class MagStream:
         hs = torch.zeros(b, k + tc, 1024, device=dev)
         hs[:, k - kl:k] = self.lstm_hist
         hs[:, k:] = hs_new
-        est = model._decoder(hs, enc)[:, k:]
+        est = model._decoder(hs, enc, f16=False)[:, k:]
         keep = self.ctx_enc + self.ctx_dec
         self.mag_hist = mag[:, max(0, k + tc - keep):].contiguous()
         self.lstm_hist = hs[:, max(0, k + tc - self.ctx_dec):].contiguous()

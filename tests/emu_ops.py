@@ -237,9 +237,104 @@ def fsn_sb_fc(h, W, bias, out):
     return out
 
 
+# ---- fp16-pair mirrors (se_split_f16 / se_gemm_f16x3 / se_lstm_cell_f16x3 / se_conv_f16x3) ---------------------
+F16_ACT_SCALE_LOG2 = 4
+
+
+def _from16(pair, scale_log2):
+    return (pair[0].float() + pair[1].float()) * (2.0 ** -scale_log2)
+
+
+def split_f16(x2d, kpad=None, scale_log2=F16_ACT_SCALE_LOG2):
+    from se_b200 import packing
+    rows, k = x2d.shape
+    kpad = kpad or (k + 7) // 8 * 8
+    xp = x2d if kpad == k else torch.cat([x2d, x2d.new_zeros(rows, kpad - k)], dim=1)
+    hi, lo, _ = packing.split_f16(xp, scale_log2)
+    return hi, lo
+
+
+def gemm_f16x3(a_pair, b_pair, b_scale_log2, bias, n_out, act="none", out=None, a_scale_log2=F16_ACT_SCALE_LOG2,
+               act_param=0.0, alpha=1.0, res=None, want_out=True, pair_out=False, pair16_out=False,
+               c16_scale_log2=F16_ACT_SCALE_LOG2):
+    from se_b200 import packing
+    a = _from16(a_pair, a_scale_log2)
+    w = _from16(b_pair, b_scale_log2)[:, :a.shape[1]]
+    y = a @ w.t()
+    if bias is not None:
+        y = y + bias
+    y = _act(y, act, act_param) * alpha
+    if res is not None:
+        y = y + res
+    if out is not None:
+        out.copy_(y)
+        y = out
+    if not (pair_out or pair16_out):
+        return y
+    return (y, packing.split_tf32(y.contiguous()) if pair_out else None,
+            packing.split_f16(y, c16_scale_log2)[:2] if pair16_out else None)
+
+
+def lstm_cell_f16x3(x_pair, h_pair, cell, c_state, h_hi_out, h_lo_out, h_out=None, a_scale_log2=F16_ACT_SCALE_LOG2):
+    from se_b200 import packing
+    m, hd = c_state.shape
+    x = _from16(x_pair, a_scale_log2)
+    w = _from16((cell["w_hi"], cell["w_lo"]), cell["w_scale_log2"])
+    g = x @ w[:, :x.shape[1]].t() + cell["bias"]
+    if h_pair is not None:
+        g = g + _from16(h_pair, a_scale_log2) @ w[:, cell["kx_pad"]:].t()
+    else:
+        c_state.zero_()
+    g = g.view(m, hd // 16, 4, 16)
+    i, f, gg, o = g[:, :, 0], g[:, :, 1], g[:, :, 2], g[:, :, 3]
+    c = torch.sigmoid(f) * c_state.view(m, hd // 16, 16) + torch.sigmoid(i) * torch.tanh(gg)
+    h = (torch.sigmoid(o) * torch.tanh(c)).reshape(m, hd)
+    c_state.copy_(c.reshape(m, hd))
+    hi, lo, _ = packing.split_f16(h, a_scale_log2)
+    h_hi_out.copy_(hi)
+    h_lo_out.copy_(lo)
+    if h_out is not None:
+        h_out.copy_(h)
+
+
+def fsn_sb_assemble_f16(mag_tm, fb, nn, inv, scale_log2=F16_ACT_SCALE_LOG2):
+    from se_b200 import packing
+    hi, lo = fsn_sb_assemble(mag_tm, fb, nn, inv)
+    h16, l16, _ = packing.split_f16(hi + lo, scale_log2)
+    return h16, l16
+
+
+def conv_f16x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, w_scale_log2, bias, Cout, act, dstF, dst_f0=0,
+               dst_fstep=1, act_param=0.0, out=None, out_pair=None, out_pair16=None, glu=None,
+               a_scale_log2=F16_ACT_SCALE_LOG2, out16_scale_log2=F16_ACT_SCALE_LOG2):
+    from se_b200 import packing
+    assert glu is None
+    x0 = _from16(src0, a_scale_log2)
+    x1 = _from16(src1, a_scale_log2) if src1 is not None else None
+    c0 = x0.shape[-1]
+    c1 = x1.shape[-1] if x1 is not None else 0
+    p0, p1 = (c0 + 63) // 64 * 64, (c1 + 63) // 64 * 64
+    wp = _from16((w_hi, w_lo), w_scale_log2).view(Cout, len(taps), p0 + p1)
+    assert float(wp[:, :, c0:p0].abs().max() if p0 > c0 else 0.0) == 0.0      # the padding columns must be zero
+    w = torch.cat([wp[:, :, :c0], wp[:, :, p0:p0 + c1]], dim=2).reshape(Cout, len(taps) * (c0 + c1)).t().contiguous()
+    tmp = out if out is not None else torch.zeros(B, T, dstF, Cout, dtype=x0.dtype)
+    if out is None and out_pair16 is not None:
+        tmp.copy_(_from16(out_pair16, out16_scale_log2))
+    conv_gemm(x0, x1, B, T, Fin, Fout, taps, sf, w, bias, Cout, act, tmp, dstF, dst_f0, dst_fstep, -1, None, act_param)
+    if out_pair16 is not None:
+        hi, lo, _ = packing.split_f16(tmp, out16_scale_log2)
+        out_pair16[0].copy_(hi)
+        out_pair16[1].copy_(lo)
+    if out_pair is not None:
+        hi, lo = packing.split_tf32(tmp)
+        out_pair[0].copy_(hi)
+        out_pair[1].copy_(lo)
+
+
 def install(ops_module, monkeypatch):
     for name in ("conv_gemm", "linear", "conv_in1", "deconv_out1", "lstm_seq", "split_tf32", "pad_split_tf32", "gemm_tf32x3",
-                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask", "conv_tf32x3", "fill_column", "lstm_seq_multi"):
+                 "lstm_cell_tf32x3", "fsn_clip_inv_mean", "fsn_fb_input", "fsn_sb_assemble", "fsn_sb_fc", "dccrn_mask", "conv_tf32x3", "fill_column", "lstm_seq_multi",
+                 "split_f16", "gemm_f16x3", "lstm_cell_f16x3", "fsn_sb_assemble_f16", "conv_f16x3"):
         monkeypatch.setattr(ops_module, name, globals()[name])
 
 

@@ -888,3 +888,63 @@ def test_lstm_cell_f16x3_matches_recurrence(m, kx, h, steps, engine):
     print(f"lstm_cell_f16 engine {engine} M={m} Kx={kx} H={h} steps={steps}: h err {e_h:.3e} c err {e_c:.3e} "
           f"hi+lo err {e_split:.3e}")
     assert e_h < 1e-5 and e_c < 1e-5 and e_split < 1e-5
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("case", TC_CONV_CASES + [(3, 5, 9, 128, 0, 256, "crn_conv"), (1, 1, 8, 256, 0, 192, "dccrn_conv"),
+                                                  (2, 23, 80, 16, 0, 32, "crn_conv"),       # 16 of a 64-channel k-block
+                                                  (2, 9, 39, 96, 40, 16, "crn_deconv")])    # ragged slices, two sources
+def test_conv_f16x3_matches_semantics(case, engine):
+    """The tensor-core conv on fp16 operand pairs (64-channel k-blocks, zero-filled / zero-padded ragged slices) vs the
+    declared conv semantics in fp64; fp32, TF32-pair and fp16-pair outputs."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import packing
+    from se_b200.dccrn import DEC_EVEN, DEC_ODD, ENC_TAPS
+    ops = se_b200.ops
+    b, t, fin, c0, c1, co, kind = case
+    g = torch.Generator().manual_seed(abs(hash(case)) % 1000)
+    x0 = torch.randn(b, t, fin, c0, generator=g) * 2.0
+    x1 = torch.randn(b, t, fin, c1, generator=g) if c1 else None
+    ct = c0 + c1
+    bias = torch.randn(co, generator=g)
+    if kind == "crn_conv":
+        fout = (fin - 3) // 2 + 1
+        runs = [(packing.CONV23_TAPS, 2, fout, 0, 1)]
+        dstF = fout
+    elif kind == "crn_deconv":
+        dstF = 2 * fin + 1
+        runs = [(packing.DECONV_EVEN_TAPS, 1, fin + 1, 0, 2), (packing.DECONV_ODD_TAPS, 1, fin, 1, 2)]
+    elif kind == "dccrn_conv":
+        runs = [(ENC_TAPS, 2, fin // 2, 0, 1)]
+        dstF = fin // 2
+    else:
+        dstF = 2 * fin
+        runs = [(DEC_EVEN, 1, fin, 0, 2), (DEC_ODD, 1, fin, 1, 2)]
+    ref = torch.zeros(b, t, dstF, co, dtype=torch.float64)
+    got = torch.zeros(b, t, dstF, co, device=dev)
+    got_hi, got_lo = torch.zeros_like(got), torch.zeros_like(got)
+    g16_hi, g16_lo = torch.zeros_like(got, dtype=torch.float16), torch.zeros_like(got, dtype=torch.float16)
+
+    def pair16(x):
+        hi, lo = ops.split_f16(x.to(dev).view(-1, x.shape[-1]))
+        return hi.view(x.shape), lo.view(x.shape)
+    s0 = pair16(x0)
+    s1 = pair16(x1) if x1 is not None else None
+    try:
+        ops.set_gemm_engine(engine)
+        for taps, sf, fout, f0, fstep in runs:
+            w = torch.randn(len(taps) * ct, co, generator=g) / np.sqrt(len(taps) * ct)
+            emu_ops.conv_gemm(x0.double(), None if x1 is None else x1.double(), b, t, fin, fout, taps, sf, w.double(),
+                              bias.double(), co, "prelu", ref, dstF, f0, fstep, -1, None, 0.2)
+            w_hi, w_lo, ws = packing.pack_conv_f16(w.t().contiguous(), len(taps), c0, c1)
+            ops.conv_f16x3(s0, s1, b, t, fin, fout, taps, sf, w_hi.to(dev), w_lo.to(dev), ws, bias.to(dev), co, "prelu",
+                           dstF, f0, fstep, act_param=0.2, out=got, out_pair=(got_hi, got_lo), out_pair16=(g16_hi, g16_lo))
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
+    err = (got.cpu().double() - ref).abs().max().item()
+    err_pair = ((got_hi + got_lo).cpu().double() - ref).abs().max().item()
+    err_16 = ((g16_hi.double() + g16_lo.double()).cpu() / 16.0 - ref).abs().max().item()
+    print(f"conv_f16x3 engine {engine} {case}: max err {err:.3e} (TF32 pair {err_pair:.3e}, fp16 pair {err_16:.3e})")
+    assert err < 2e-5 and err_pair < 2e-5 and err_16 < 2e-5
