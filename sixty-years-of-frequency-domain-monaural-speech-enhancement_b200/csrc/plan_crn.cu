@@ -20,6 +20,8 @@
 #include <tuple>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -47,8 +49,35 @@ struct DevBuf {
 
 struct ConvW {
   DevBuf kn, hi, lo, bias, fill;   // kn [K][Co]; hi/lo [Co][K]
+  DevBuf hi16, lo16;               // fp16 pair [Co][ntaps * (pad64(c0) + pad64(c1))], scaled by 2^ws16 (packing.pack_conv_f16)
+  int ws16 = 0;
   int K = 0, Co = 0;
 };
+
+constexpr int kActScaleLog2 = 4;   // ops.F16_ACT_SCALE_LOG2: activations travel as x * 2^4 = hi + lo
+
+// packing.split_f16 on the host: per-tensor power-of-two scale that puts max|x| in [2^13, 2^14), RNE halves
+int f16_scale_log2(const std::vector<float>& x) {
+  float amax = 0.f;
+  for (float v : x) amax = fmaxf(amax, fabsf(v));
+  if (amax == 0.f) return 0;
+  int s = 13 - (int)floor(log2((double)amax));
+  return s < -14 ? -14 : (s > 15 ? 15 : s);
+}
+void split_f16_host(const std::vector<float>& x, int s, std::vector<unsigned short>& hi, std::vector<unsigned short>& lo) {
+  hi.resize(x.size());
+  lo.resize(x.size());
+  const float sc = ldexpf(1.0f, s);
+  for (size_t i = 0; i < x.size(); ++i) {
+    const float xs = x[i] * sc;
+    const float c = fminf(fmaxf(xs, -65504.f), 65504.f);
+    const __half h = __float2half_rn(c);
+    const float r = fminf(fmaxf(xs - __half2float(h), -65504.f), 65504.f);
+    const __half l = __float2half_rn(r);
+    memcpy(&hi[i], &h, 2);
+    memcpy(&lo[i], &l, 2);
+  }
+}
 
 struct GraphKey {
   int B, N, ragged;
@@ -66,6 +95,11 @@ struct se_plan {
   DevBuf en0_w, en0_b;
   ConvW enc[5];                 // 1..4 used
   DevBuf wih_hi[2], wih_lo[2], lbias[2], whh[2];
+  DevBuf wih16_hi[2], wih16_lo[2];          // fp16 pair of the projection weights (packing.pack_linear_f16)
+  int wih16_s[2] = {0, 0};
+  int f16 = 1;                              // fp16 operand pairs (default) or TF32 pairs (SE_F16_PAIRS=0), as crn.py
+  unsigned short *a1h16, *a1l16, *a2h16, *a2l16, *a3h16, *a3l16, *a4h16, *a4l16, *a5h16, *a5l16, *hs0h16, *hs0l16, *hs1h16,
+      *hs1l16, *d0h16, *d0l16, *d1h16, *d1l16, *d2h16, *d2l16;
   ConvW dec_even[4], dec_odd[4];
   DevBuf de4_w;
   float de4_b = 0.f;
@@ -105,6 +139,10 @@ bool upload_split(se_plan* P, DevBuf& hi, DevBuf& lo, const std::vector<float>& 
   }
   return upload(P, hi, a) && upload(P, lo, b);
 }
+bool upload16(se_plan* P, DevBuf& b, const std::vector<unsigned short>& h) {
+  if (!dev_alloc(P, b, (h.size() + 1) / 2)) return false;
+  return cudaMemcpy(b.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+}
 // eval BatchNorm as y = x * s + o   (packing.bn_fold)
 void bn_fold(const float* const bn[4], int c, std::vector<float>& s, std::vector<float>& o) {
   s.resize(c);
@@ -115,13 +153,29 @@ void bn_fold(const float* const bn[4], int c, std::vector<float>& s, std::vector
   }
 }
 // K-major matrix [K][Co] -> ConvW (kn + TF32 pair of its transpose)
-bool make_convw(se_plan* P, ConvW& w, const std::vector<float>& kn, int K, int Co, const std::vector<float>& bias) {
+// ntaps / c0 / c1: the K order is (tap, [source 0 | source 1] channels); the fp16 layout pads every (tap, source) block to
+// a multiple of 64 channels (packing.pack_conv_f16)
+bool make_convw(se_plan* P, ConvW& w, const std::vector<float>& kn, int K, int Co, const std::vector<float>& bias, int ntaps,
+                int c0, int c1) {
   w.K = K;
   w.Co = Co;
   std::vector<float> t((size_t)K * Co);
   for (int k = 0; k < K; ++k)
     for (int c = 0; c < Co; ++c) t[(size_t)c * K + k] = kn[(size_t)k * Co + c];
-  return upload(P, w.kn, kn) && upload_split(P, w.hi, w.lo, t) && upload(P, w.bias, bias);
+  const int p0 = (c0 + 63) / 64 * 64, p1 = (c1 + 63) / 64 * 64, Kp = ntaps * (p0 + p1);
+  std::vector<float> tp((size_t)Co * Kp, 0.f);
+  for (int c = 0; c < Co; ++c)
+    for (int tap = 0; tap < ntaps; ++tap) {
+      const float* src = t.data() + (size_t)c * K + (size_t)tap * (c0 + c1);
+      float* dst = tp.data() + (size_t)c * Kp + (size_t)tap * (p0 + p1);
+      for (int q = 0; q < c0; ++q) dst[q] = src[q];
+      for (int q = 0; q < c1; ++q) dst[p0 + q] = src[c0 + q];
+    }
+  w.ws16 = f16_scale_log2(tp);
+  std::vector<unsigned short> h16, l16;
+  split_f16_host(tp, w.ws16, h16, l16);
+  return upload(P, w.kn, kn) && upload_split(P, w.hi, w.lo, t) && upload(P, w.bias, bias) && upload16(P, w.hi16, h16) &&
+         upload16(P, w.lo16, l16);
 }
 
 // torch gate-major rows [i|f|g|o] x H -> slice order: row s*32 + g*8 + j  <-  g*H + unit(s*8+j)   (packing.slice_rows)
@@ -150,7 +204,49 @@ bool pack_lstm(se_plan* P, int l, const float* w_ih, const float* w_hh, const fl
     for (int k = 0; k < kH; ++k) wh[((size_t)s * kH + k) * 32 + c] = sh[unit_perm ? (*unit_perm)[k] : k];
     bias[r] = b_ih[rows[r]] + b_hh[rows[r]];
   }
-  return upload_split(P, P->wih_hi[l], P->wih_lo[l], wi) && upload(P, P->lbias[l], bias) && upload(P, P->whh[l], wh);
+  P->wih16_s[l] = f16_scale_log2(wi);
+  std::vector<unsigned short> h16, l16;
+  split_f16_host(wi, P->wih16_s[l], h16, l16);
+  return upload_split(P, P->wih_hi[l], P->wih_lo[l], wi) && upload(P, P->lbias[l], bias) && upload(P, P->whh[l], wh) &&
+         upload16(P, P->wih16_hi[l], h16) && upload16(P, P->wih16_lo[l], l16);
+}
+
+int launch_conv_f16(const unsigned short* s0h, const unsigned short* s0l, const unsigned short* s1h, const unsigned short* s1l,
+                    int C0, int C1, int B, int T, int Fin, int Fout, const int (*taps)[2], int ntaps, int sf, const ConvW& w,
+                    float* out, unsigned short* oh, unsigned short* ol, int dstF, int f0, int fstep, cudaStream_t s) {
+  se_conv_f16_desc d;
+  memset(&d, 0, sizeof(d));
+  d.src0_hi = s0h;
+  d.src0_lo = s0l;
+  d.src1_hi = s1h;
+  d.src1_lo = s1l;
+  d.C0 = C0;
+  d.C1 = C1;
+  d.B = B;
+  d.T = T;
+  d.Fin = Fin;
+  d.Fout = Fout;
+  d.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) {
+    d.dt[i] = taps[i][0];
+    d.df[i] = taps[i][1];
+  }
+  d.sf = sf;
+  d.w_hi = reinterpret_cast<const unsigned short*>(w.hi16.p);
+  d.w_lo = reinterpret_cast<const unsigned short*>(w.lo16.p);
+  d.scale_log2_a = kActScaleLog2;
+  d.scale_log2_w = w.ws16;
+  d.bias = w.bias.p;
+  d.Cout = w.Co;
+  d.act = SE_ACT_ELU;
+  d.out = out;
+  d.out16_hi = oh;
+  d.out16_lo = ol;
+  d.out16_scale_log2 = kActScaleLog2;
+  d.dstF = dstF;
+  d.dst_f0 = f0;
+  d.dst_fstep = fstep;
+  return se_conv_f16x3(&d, s);
 }
 
 int launch_conv_tc(const float* s0h, const float* s0l, const float* s1h, const float* s1l, int C0, int C1, int B, int T, int Fin,
@@ -198,7 +294,63 @@ const int kDecOdd[2][2] = {{0, 0}, {-1, 0}};                                    
     if (rc_ != SE_OK) return rc_; \
   } while (0)
 
+// crn.py with lstm_engine.USE_F16_PAIRS: every tensor-core layer (en2-en5, both projections, de1-de4) on fp16 operand pairs
+int forward_f16(se_plan* P, const float* mag, float* est, int B, int T, cudaStream_t s) {
+  const long long rows = (long long)B * T;
+  SE_TRY(se_conv_in1(mag, B, T, kBins, P->en0_w.p, P->en0_b.p, 16, SE_ACT_ELU, P->a1, kEncF[1], s));
+  SE_TRY(se_split_f16(P->a1, rows * kEncF[1], 16, 16, 16, kActScaleLog2, P->a1h16, P->a1l16, s));
+  const unsigned short* ih[4] = {P->a1h16, P->a2h16, P->a3h16, P->a4h16};
+  const unsigned short* il[4] = {P->a1l16, P->a2l16, P->a3l16, P->a4l16};
+  unsigned short* oh[4] = {P->a2h16, P->a3h16, P->a4h16, P->a5h16};
+  unsigned short* ol[4] = {P->a2l16, P->a3l16, P->a4l16, P->a5l16};
+  for (int i = 1; i < 5; ++i)
+    SE_TRY(launch_conv_f16(ih[i - 1], il[i - 1], nullptr, nullptr, kEncCh[i], 0, B, T, kEncF[i], kEncF[i + 1], kConv23, 6, 2,
+                           P->enc[i], nullptr, oh[i - 1], ol[i - 1], kEncF[i + 1], 0, 1, s));
+  const unsigned short* inh = P->a5h16;
+  const unsigned short* inl = P->a5l16;
+  float* hs[2] = {P->hs0, P->hs1};
+  unsigned short* hsh[2] = {P->hs0h16, P->hs1h16};
+  unsigned short* hsl[2] = {P->hs0l16, P->hs1l16};
+  for (int l = 0; l < 2; ++l) {
+    SE_TRY(se_gemm_f16x3(inh, inl, kH, reinterpret_cast<const unsigned short*>(P->wih16_hi[l].p),
+                         reinterpret_cast<const unsigned short*>(P->wih16_lo[l].p), kH, (int)rows, 4 * kH, kH,
+                         kActScaleLog2 + P->wih16_s[l], P->lbias[l].p, SE_ACT_NONE, 0.f, 1.f, nullptr, P->xp, nullptr, nullptr,
+                         nullptr, nullptr, kActScaleLog2, 4 * kH, s));
+    for (int b0 = 0; b0 < B; b0 += 64) {
+      const int nb = B - b0 < 64 ? B - b0 : 64;
+      SE_TRY(se_lstm_seq(P->xp + (size_t)b0 * T * 4 * kH, 4 * kH, P->whh[l].p, nb, T, kH, hs[l] + (size_t)b0 * T * kH,
+                         (long long)T * kH, kH, P->lwork, P->sync, s));
+    }
+    SE_TRY(se_split_f16(hs[l], rows, kH, kH, kH, kActScaleLog2, hsh[l], hsl[l], s));
+    inh = hsh[l];
+    inl = hsl[l];
+  }
+  const unsigned short* xh = P->hs1h16;
+  const unsigned short* xl = P->hs1l16;
+  const unsigned short* skh[4] = {P->a5h16, P->a4h16, P->a3h16, P->a2h16};
+  const unsigned short* skl[4] = {P->a5l16, P->a4l16, P->a3l16, P->a2l16};
+  unsigned short* dh[4] = {P->d0h16, P->d1h16, P->d2h16, nullptr};
+  unsigned short* dl[4] = {P->d0l16, P->d1l16, P->d2l16, nullptr};
+  int fin = 4;
+  for (int i = 0; i < 4; ++i) {
+    const int shift = i == 3 ? 1 : 0;            // de4: left pad on F (CRN.py:92-97)
+    const int fo = 2 * fin + 1 + shift;
+    const int c = kDecCi[i] / 2;
+    float* of32 = i == 3 ? P->d3 : nullptr;
+    SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin + 1, kDecEven, 4, 1, P->dec_even[i], of32, dh[i], dl[i],
+                           fo, shift, 2, s));
+    SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin, kDecOdd, 2, 1, P->dec_odd[i], of32, dh[i], dl[i], fo,
+                           shift + 1, 2, s));
+    if (shift) SE_TRY(se_fill_column(P->d3, rows, fo, kDecCo[i], 0, P->dec_even[i].fill.p, SE_ACT_ELU, 0.f, s));
+    xh = dh[i];
+    xl = dl[i];
+    fin = fo;
+  }
+  return se_deconv_out1(P->d3, P->a1, 16, 16, B, T, 80, P->de4_w.p, P->de4_b, SE_ACT_SOFTPLUS, est, s);
+}
+
 int forward(se_plan* P, const float* mag, float* est, int B, int T, cudaStream_t s) {
+  if (P->f16) return forward_f16(P, mag, est, B, T, s);
   const long long rows = (long long)B * T;
   // encoder (CRN.py:35-71)
   SE_TRY(se_conv_in1(mag, B, T, kBins, P->en0_w.p, P->en0_b.p, 16, SE_ACT_ELU, P->a1, kEncF[1], s));
@@ -297,6 +449,10 @@ extern "C" int se_plan_create_crn(const se_crn_weights* w, int B_max, int N_max,
   SE_REQUIRE(w && plan && B_max > 0 && N_max >= kNfft, "se_plan_create_crn: bad arguments (B_max=%d N_max=%d)", B_max, N_max);
   SE_TRY(se_device_check());
   se_plan* P = new se_plan();
+  {
+    const char* e = getenv("SE_F16_PAIRS");      // the switch crn.py / lstm_engine.py read
+    P->f16 = !(e && e[0] == '0' && e[1] == 0);
+  }
   P->Bmax = B_max;
   P->Nmax = N_max;
   P->Tmax = 1 + N_max / kHop;
@@ -318,7 +474,7 @@ extern "C" int se_plan_create_crn(const se_crn_weights* w, int B_max, int N_max,
     if (i == 0)
       ok = upload(P, P->en0_w, kn) && upload(P, P->en0_b, bias);
     else
-      ok = make_convw(P, P->enc[i], kn, K, co, bias);
+      ok = make_convw(P, P->enc[i], kn, K, co, bias, 6, ci, 0);
   }
   // ---- LSTM: NHWC flatten index q = f*256 + c  <->  reference feature index c*4 + f   (crn.py _pack)
   std::vector<int> nhwc(kH);
@@ -340,7 +496,8 @@ extern "C" int se_plan_create_crn(const se_crn_weights* w, int B_max, int N_max,
           for (int k = 0; k < 2; ++k) d[((size_t)k * ci + q) * co + c] = W(q, c, od[k][0], od[k][1]);
         }
       for (int c = 0; c < co; ++c) bias[c] = w->de_b[i][c] * s[c] + o[c];
-      ok = make_convw(P, P->dec_even[i], e, 4 * ci, co, bias) && make_convw(P, P->dec_odd[i], d, 2 * ci, co, bias) &&
+      ok = make_convw(P, P->dec_even[i], e, 4 * ci, co, bias, 4, ci / 2, ci / 2) &&
+           make_convw(P, P->dec_odd[i], d, 2 * ci, co, bias, 2, ci / 2, ci / 2) &&
            upload(P, P->dec_even[i].fill, o);
     } else {
       std::vector<float> d6((size_t)6 * ci);
@@ -371,6 +528,20 @@ extern "C" int se_plan_create_crn(const se_crn_weights* w, int B_max, int N_max,
     DevBuf b;
     ok = ok && dev_alloc(P, b, (sl.n + 3) & ~(size_t)3);
     *sl.p = b.p;
+  }
+  struct Slot16 {
+    unsigned short** p;
+    size_t n;
+  };
+  Slot16 slots16[] = {{&P->a1h16, R * 80 * 16}, {&P->a1l16, R * 80 * 16}, {&P->a2h16, R * 39 * 32}, {&P->a2l16, R * 39 * 32},
+                      {&P->a3h16, R * 19 * 64}, {&P->a3l16, R * 19 * 64}, {&P->a4h16, R * 9 * 128}, {&P->a4l16, R * 9 * 128},
+                      {&P->a5h16, R * 1024},    {&P->a5l16, R * 1024},    {&P->hs0h16, R * 1024},   {&P->hs0l16, R * 1024},
+                      {&P->hs1h16, R * 1024},   {&P->hs1l16, R * 1024},   {&P->d0h16, R * 9 * 128}, {&P->d0l16, R * 9 * 128},
+                      {&P->d1h16, R * 19 * 64}, {&P->d1l16, R * 19 * 64}, {&P->d2h16, R * 39 * 32}, {&P->d2l16, R * 39 * 32}};
+  for (const Slot16& sl : slots16) {
+    DevBuf b;
+    ok = ok && dev_alloc(P, b, ((sl.n + 7) & ~(size_t)7) / 2);
+    *sl.p = reinterpret_cast<unsigned short*>(b.p);
   }
   DevBuf sy, le;
   ok = ok && dev_alloc(P, sy, 16) && dev_alloc(P, le, (size_t)B_max);

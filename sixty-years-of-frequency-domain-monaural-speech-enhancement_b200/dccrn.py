@@ -150,6 +150,7 @@ class DCCRN(nn.Module):
             biases.append(bsel)
         w0 = torch.cat(blocks, dim=1).t().contiguous()           # [2048, 1024]  (N, K) K-major
         P["l0_hi"], P["l0_lo"] = packing.split_tf32(w0)
+        P["l0_16"] = packing.pack_linear_f16(w0)
         P["l0_kn"] = packing.pad_cols(w0.t().contiguous())
         P["l0_b"] = torch.cat(biases).contiguous()
 
@@ -169,6 +170,7 @@ class DCCRN(nn.Module):
         w1 = torch.cat([from_parts(wr1, real_in), from_parts(wi1, real_in), from_parts(wr1, imag_in),
                         from_parts(wi1, imag_in)], dim=0).contiguous()           # [2048, 512]
         P["l1_hi"], P["l1_lo"] = packing.split_tf32(w1)
+        P["l1_16"] = packing.pack_linear_f16(w1)
         P["l1_kn"] = packing.pad_cols(w1.t().contiguous())
         P["l1_b"] = torch.cat([br1, bi1, br1, bi1]).contiguous()
         P["whh1"] = torch.stack([whh_pack(whr1), whh_pack(whi1), whh_pack(whr1), whh_pack(whi1)]).contiguous()
@@ -184,6 +186,7 @@ class DCCRN(nn.Module):
         bp[is_real] = bp_r[ref_feat[is_real]]
         bp[~is_real] = bp_i[ref_feat[~is_real]]
         P["proj_hi"], P["proj_lo"] = packing.split_tf32(wp.contiguous())           # [1024, 512] (N, K)
+        P["proj_16"] = packing.pack_linear_f16(wp.contiguous())
         P["proj_kn"] = packing.pad_cols(wp.t().contiguous())
         P["proj_b"] = bp.contiguous()
         # ---- decoder ----
@@ -241,17 +244,19 @@ class DCCRN(nn.Module):
         dev = x.device
         kn = self.kernel_num
         use_tc = self._use_tc()
+        from . import lstm_engine
+        f16 = use_tc and lstm_engine.USE_F16_PAIRS      # tensor-core layers on fp16 operand pairs (SE_F16_PAIRS=0: TF32 pairs)
         # encoder: drop the DC bin (DCCRN_cprs.py:166) by pointing at bin 1 with row stride 257
         enc = []
         h = Act(x[:, :, 1:, :].contiguous())                       # [B,T,256,2] (small: 2 channels)
         fin = 256
-        f32_of = lambda a: a.f32 if a.f32 is not None else a.pair[0] + a.pair[1]   # noqa: E731 (debug taps only)
+        f32_of = lambda a: a.value()   # noqa: E731 (debug taps only)
         for i in range(6):
             w, bias, slope = P[f"enc{i}"]
             ci, co = kn[i], kn[i + 1]
             fo = fin // 2
-            is_tc = conv_engine.tc_eligible(ci, 0, co, fo, 2)
-            out = conv_engine.new_act(b, t, fo, co, dev, want_f32=not is_tc, want_pair=is_tc)
+            is_tc = conv_engine.tc_eligible(ci, 0, co, fo, 2, f16)
+            out = conv_engine.new_act(b, t, fo, co, dev, want_f32=not is_tc, want_pair=is_tc, f16=f16)
             conv_engine.conv(h, None, b, t, fin, fo, ENC_TAPS, 2, w, bias, "prelu", out, fo, act_param=slope)
             h, fin = out, fo
             enc.append(h)
@@ -264,13 +269,15 @@ class DCCRN(nn.Module):
         pair = (h.pair[0].view(m, -1), h.pair[1].view(m, -1)) if h.pair is not None else None
         hs = torch.empty(b, t, 4 * hid, device=dev, dtype=torch.float32)
         for l in range(2):
-            xp = self._proj(seq, pair, P[f"l{l}_hi"], P[f"l{l}_lo"], P[f"l{l}_kn"], P[f"l{l}_b"], 16 * hid, use_tc)
+            xp = self._proj(seq, pair, P[f"l{l}_hi"], P[f"l{l}_lo"], P[f"l{l}_kn"], P[f"l{l}_b"], 16 * hid, use_tc,
+                            P[f"l{l}_16"] if f16 else None)
             xp = xp.view(b, t, 16 * hid)
             ops.lstm_seq_multi(xp, P[f"whh{l}"], hid, 4, hs)       # the four real LSTM passes, one launch
             seq, pair = hs.view(m, 4 * hid), None
             if l == 0:
                 hs = torch.empty(b, t, 4 * hid, device=dev, dtype=torch.float32)
-        dec_in = self._proj(seq, None, P["proj_hi"], P["proj_lo"], P["proj_kn"], P["proj_b"], fin * kn[-1], use_tc)
+        dec_in = self._proj(seq, None, P["proj_hi"], P["proj_lo"], P["proj_kn"], P["proj_b"], fin * kn[-1], use_tc,
+                            P["proj_16"] if f16 else None)
         h = Act(dec_in.view(b, t, fin, kn[-1]))
         if taps is not None:
             taps["rnn_out"] = h.f32
@@ -283,11 +290,11 @@ class DCCRN(nn.Module):
             fo = 2 * fin
             act = "prelu" if i < 5 else "none"
             c0, c1 = h.shape[-1], skip.shape[-1]
-            is_tc = conv_engine.tc_eligible(c0, c1, co, fin, 1)
+            is_tc = conv_engine.tc_eligible(c0, c1, co, fin, 1, f16)
             # the consumer of dec4 (Cout=2 last layer) and of dec5 (mask kernel) run on fp32
-            nxt_tc = i < 4 and conv_engine.tc_eligible(co, kn[4 - i], kn[4 - i], fo, 1)
+            nxt_tc = i < 4 and conv_engine.tc_eligible(co, kn[4 - i], kn[4 - i], fo, 1, f16)
             out = conv_engine.new_act(b, t, fo, co, dev, want_f32=(not is_tc) or (not nxt_tc),
-                                      want_pair=is_tc and nxt_tc)
+                                      want_pair=is_tc and nxt_tc, f16=f16)
             ev = [(dt + dt_shift, df) for dt, df in DEC_EVEN]
             od = [(dt + dt_shift, df) for dt, df in DEC_ODD]
             conv_engine.conv(h, skip, b, t, fin, fin, ev, 1, we, bias, act, out, fo, dst_f0=0, dst_fstep=2,
@@ -308,8 +315,11 @@ class DCCRN(nn.Module):
         return lstm_engine.USE_TENSOR_CORES
 
     @staticmethod
-    def _proj(seq, pair, w_hi, w_lo, w_kn, bias, n, use_tc):
+    def _proj(seq, pair, w_hi, w_lo, w_kn, bias, n, use_tc, w16=None):
         k = (seq if seq is not None else pair[0]).shape[1]
+        if w16 is not None and k % 8 == 0 and (pair is not None or seq.shape[0] >= 128) and \
+                (pair is None or pair[0].dtype == torch.float16):
+            return ops.gemm_f16x3(pair if pair is not None else ops.split_f16(seq), w16[:2], w16[2], bias, n)
         if use_tc and k % 32 == 0 and (pair is not None or seq.shape[0] >= 128):
             a_hi, a_lo = pair if pair is not None else ops.split_tf32(seq)
             return ops.gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias, n)

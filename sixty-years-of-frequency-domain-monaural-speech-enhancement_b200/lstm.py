@@ -45,6 +45,7 @@ class lstm_net(nn.Module):
                                                      sd[f"lstm2.bias_ih_l{l}"], sd[f"lstm2.bias_hh_l{l}"])
         P["fc_w"] = packing.pad_cols(sd["fc.0.weight"].t().contiguous())
         P["fc_hi"], P["fc_lo"] = packing.split_tf32(sd["fc.0.weight"].contiguous())   # [161, 1024] K-major
+        P["fc16"] = packing.pack_linear_f16(sd["fc.0.weight"].contiguous())
         P["fc_b"] = sd["fc.0.bias"].contiguous()
         self._packed = P
 
@@ -92,7 +93,9 @@ class lstm_net(nn.Module):
             seq = hs.view(b * t, 1024)
             if taps is not None:
                 taps[f"h{l}"] = hs
-        if lstm_engine.USE_TENSOR_CORES and seq.shape[0] >= 128:
+        if lstm_engine.USE_TENSOR_CORES and lstm_engine.USE_F16_PAIRS and seq.shape[0] >= 128:
+            y = ops.gemm_f16x3(ops.split_f16(seq), P["fc16"][:2], P["fc16"][2], P["fc_b"], 161, act="softplus")
+        elif lstm_engine.USE_TENSOR_CORES and seq.shape[0] >= 128:
             a_hi, a_lo = ops.split_tf32(seq)
             y = ops.gemm_tf32x3(a_hi, a_lo, P["fc_hi"], P["fc_lo"], P["fc_b"], 161, act="softplus")
         else:
