@@ -22,10 +22,10 @@ def input_projection(seq2d, layer, pair=None):
     """seq2d [M, K] fp32 (or None when ``pair`` = its TF32 (hi, lo) split is already available)."""
     m, k = (seq2d if seq2d is not None else pair[0]).shape
     n = 4 * layer["hidden"]
-    if USE_TENSOR_CORES and USE_F16_PAIRS and "wih16" in layer and (m >= 128 or pair is not None) and \
+    if USE_TENSOR_CORES and USE_F16_PAIRS and "wih16_hi" in layer and (m >= 128 or pair is not None) and \
             (pair is None or pair[0].dtype == torch.float16):
         a = pair if pair is not None else ops.split_f16(seq2d)       # K rounded up to 8, zero tail
-        return ops.gemm_f16x3(a, layer["wih16"], layer["wih16_scale"], layer["bias"], n)
+        return ops.gemm_f16x3(a, (layer["wih16_hi"], layer["wih16_lo"]), layer["wih16_scale"], layer["bias"], n)
     kw = layer["wih_hi"].shape[1]                # K of the packed tensor-core weights: the input width rounded up to 32
     if USE_TENSOR_CORES and (m >= 128 or pair is not None) and (kw == k or (pair is None and layer.get("kin") == k)):
         if pair is not None:

@@ -114,7 +114,7 @@ def pack_lstm_layer(w_ih, w_hh, b_ih, b_hh, in_perm=None, unit_perm=None, in_sca
     hi, lo = split_tf32(wi_tc)
     h16, l16, s16 = pack_linear_f16(wi)
     return {"wih_kn": pad_cols(wi.t().contiguous()), "wih_hi": hi, "wih_lo": lo, "bias": bias.contiguous(),
-            "whh": whp, "hidden": hidden, "kin": kin, "wih16": (h16, l16), "wih16_scale": s16}
+            "whh": whp, "hidden": hidden, "kin": kin, "wih16_hi": h16, "wih16_lo": l16, "wih16_scale": s16}
 
 
 def tile_rows(hidden):
