@@ -399,6 +399,12 @@ typedef struct se_conv_f16_desc {
   int dstF, dst_f0, dst_fstep;
   int glu;
   const float *glu_scale, *glu_shift;
+  /* ncls == 2: both output-column parity classes of a stride-2 ConvTranspose2d in ONE launch (the activation tiles are
+   * read once instead of twice).  The Cout GEMM columns are two classes of Cout / 2 channels: columns [0, Cout/2) are
+   * written at output column dst_f0 + fo * dst_fstep, columns [Cout/2, Cout) at dst_f0 + 1 + fo * dst_fstep for
+   * fo < fout1; the tap list is the union of the two classes' taps (zero weights where a class does not use a tap),
+   * bias has Cout / 2 entries, the outputs have Cout / 2 channels.  0 / 1: one class (the fields above as they are). */
+  int ncls, fout1;
 } se_conv_f16_desc;
 int se_conv_f16x3(const se_conv_f16_desc* d, se_stream_t stream);
 

@@ -62,6 +62,7 @@ class ConvF16Desc(C.Structure):
         ("out16_hi", C.c_void_p), ("out16_lo", C.c_void_p), ("out16_scale_log2", C.c_int),
         ("dstF", C.c_int), ("dst_f0", C.c_int), ("dst_fstep", C.c_int),
         ("glu", C.c_int), ("glu_scale", C.c_void_p), ("glu_shift", C.c_void_p),
+        ("ncls", C.c_int), ("fout1", C.c_int),
     ]
 
 

@@ -120,6 +120,44 @@ def conv(src: Act, skip, B, T, Fin, Fout, taps, sf, w: ConvWeights, bias, act, d
             raise RuntimeError("split output requested from the FMA path: allocate dst without a pair and split")
 
 
+def merge_parity(w_even: ConvWeights, taps_even, w_odd: ConvWeights, taps_odd):
+    """The two output-column parity classes of a stride-2 transposed conv as ONE weight matrix for
+    ``conv_parity2``: K order = the even class's taps (the odd class's taps must be among them), columns
+    [even class | odd class], zero rows where the odd class does not use a tap."""
+    co = w_even.cout
+    assert w_odd.cout == co and all(tp in taps_even for tp in taps_odd)
+    ct = w_even.kn.shape[0] // len(taps_even)
+    assert w_odd.kn.shape[0] == ct * len(taps_odd)
+    m = w_even.kn.new_zeros(len(taps_even) * ct, 2 * co)
+    m[:, :co] = w_even.kn[:, :co]
+    for j, tp in enumerate(taps_odd):
+        i = taps_even.index(tp)
+        m[i * ct:(i + 1) * ct, co:] = w_odd.kn[j * ct:(j + 1) * ct, :co]
+    return ConvWeights(m, 2 * co)
+
+
+def parity2_eligible(src: Act, skip, w_merged: ConvWeights, fout_even, sf=1):
+    """One-launch parity pair: fp16-pair tensor-core layers whose class width fits the epilogue's column groups."""
+    c0 = src.shape[-1]
+    c1 = skip.shape[-1] if skip is not None else 0
+    co2 = w_merged.cout
+    bn = 128 if co2 > 64 else (64 if co2 > 32 else (32 if co2 > 16 else 16))
+    return (src.is_f16 or src.pair is None) and tc_eligible(c0, c1, co2, fout_even, sf, True) and \
+        co2 % 8 == 0 and (co2 // 2) % (bn // 2) == 0
+
+
+def conv_parity2(src: Act, skip, B, T, Fin, fout_even, fout_odd, taps_even, w_merged: ConvWeights, bias, act, dst: Act,
+                 dstF, dst_f0=0, act_param=0.0):
+    """Both parity classes of a stride-2 transposed conv in one se_conv_f16x3 launch (ncls = 2): even class at output
+    columns dst_f0 + 2 m (m < fout_even), odd class at dst_f0 + 1 + 2 m (m < fout_odd)."""
+    c0 = src.shape[-1]
+    c1 = skip.shape[-1] if skip is not None else 0
+    w_hi, w_lo, ws = w_merged.f16(len(taps_even), c0, c1)
+    ops.conv_f16x3(src.get_pair(True), skip.get_pair(True) if skip is not None else None, B, T, Fin, fout_even, taps_even,
+                   1, w_hi, w_lo, ws, bias, w_merged.cout, act, dstF, dst_f0, 2, act_param=act_param, out=dst.f32,
+                   out_pair16=dst.pair, fout1=fout_odd)
+
+
 def new_act(b, t, f, c, device, want_f32, want_pair, f16=False):
     mk = lambda: torch.empty(b, t, f, c, device=device, dtype=torch.float32)   # noqa: E731
     mk16 = lambda: torch.empty(b, t, f, c, device=device, dtype=torch.float16)   # noqa: E731

@@ -77,7 +77,9 @@ class crn_net(nn.Module):
             if i < 4:
                 we, wo, bias, fill = packing.pack_deconv_parity(w, b, bn)
                 co = _DEC_CH[i][1]
-                P[f"de{i}"] = (ConvWeights(we, co), ConvWeights(wo, co), bias, fill)
+                cwe, cwo = ConvWeights(we, co), ConvWeights(wo, co)
+                P[f"de{i}"] = (cwe, cwo, bias, fill)
+                P[f"de{i}_m"] = conv_engine.merge_parity(cwe, packing.DECONV_EVEN_TAPS, cwo, packing.DECONV_ODD_TAPS)
             else:
                 s, o = packing.bn_fold(*bn)
                 wf = w * s[None, :, None, None]
@@ -168,11 +170,19 @@ class crn_net(nn.Module):
             last = i == 3                                   # de4 feeds the fp32 direct kernel
             out = conv_engine.new_act(b, t, fo, co, dev, want_f32=(not is_tc) or last, want_pair=is_tc and not last,
                                       f16=f16)
-            conv_engine.conv(h, skip, b, t, fin, fin + 1, packing.DECONV_EVEN_TAPS, 1, we, bias, "elu", out, fo,
-                             dst_f0=shift, dst_fstep=2)
-            conv_engine.conv(h, skip, b, t, fin, fin, packing.DECONV_ODD_TAPS, 1, wo, bias, "elu", out, fo,
-                             dst_f0=shift + 1, dst_fstep=2, fill_f=(0 if shift else -1),
-                             fill=(fill if shift else None))
+            wm = P[f"de{i}_m"]
+            if f16 and conv_engine.parity2_eligible(h, skip, wm, fin + 1):
+                # both output-column parity classes in one launch: the activation tiles are read once
+                conv_engine.conv_parity2(h, skip, b, t, fin, fin + 1, fin, packing.DECONV_EVEN_TAPS, wm, bias, "elu", out,
+                                         fo, dst_f0=shift)
+                if shift:
+                    ops.fill_column(out.f32, fill, 0, "elu", 0.0)
+            else:
+                conv_engine.conv(h, skip, b, t, fin, fin + 1, packing.DECONV_EVEN_TAPS, 1, we, bias, "elu", out, fo,
+                                 dst_f0=shift, dst_fstep=2)
+                conv_engine.conv(h, skip, b, t, fin, fin, packing.DECONV_ODD_TAPS, 1, wo, bias, "elu", out, fo,
+                                 dst_f0=shift + 1, dst_fstep=2, fill_f=(0 if shift else -1),
+                                 fill=(fill if shift else None))
             h = out
             fin = fo
             if taps is not None:

@@ -16,5 +16,6 @@ extern "C" int se_conv_f16x3(const se_conv_f16_desc* d, se_stream_t stream) {
   a.out16_scale = ldexpf(1.0f, d->out16_scale_log2);
   a.dstF = d->dstF, a.dst_f0 = d->dst_f0, a.dst_fstep = d->dst_fstep;
   a.glu = d->glu, a.glu_scale = d->glu_scale, a.glu_shift = d->glu_shift;
+  a.ncls = d->ncls, a.fout1 = d->fout1;
   return conv_tc_run<true>(&a, "se_conv_f16x3", (cudaStream_t)stream);
 }

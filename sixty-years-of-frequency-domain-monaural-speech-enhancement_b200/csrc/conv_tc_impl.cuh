@@ -47,6 +47,11 @@ struct ConvTcParams {
   int act;
   float act_param;
   float *out, *out_hi, *out_lo;  // any may be NULL
+  // Two output-column parity classes of a transposed conv in ONE launch (cls_cols > 0): GEMM columns [0, cls_cols) are the
+  // class written at output column dst_f0 + fo * dst_fstep, columns [cls_cols, 2 cls_cols) the class at dst_f0 + 1 +
+  // fo * dst_fstep for fo < fout1; both have cls_cols channels and share the bias.  The tap list is the union (the second
+  // class has zero weights on the taps it does not use), so the activation tiles are read once instead of twice.
+  int cls_cols, fout1;
   float out_scale;               // fp32 sums -> values: 1 / (scale_A * scale_W) with fp16 pairs, 1 otherwise
   unsigned short *out16_hi, *out16_lo;   // fp16-pair copy of the output (scaled by out16_scale) or NULL
   float out16_scale;
@@ -117,11 +122,11 @@ __device__ __forceinline__ void tmem_ld_cols<8>(unsigned taddr, float (&v)[8]) {
 // channels go four at a time; like the GEMM epilogue (gemm_tc.cu) this code runs on the warps that drain the TMEM chunk
 // sums, so it is kept short: activation as a template parameter, float4 bias loads.
 template <int NC, int ACT>
-__device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float (&sum)[NC], long long orow, int n0) {
+__device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float (&sum)[NC], long long orow, int n0, int cout) {
   const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 #pragma unroll
   for (int j = 0; j < NC; j += 4) {
-    if (n0 + j >= p.Cout) break;
+    if (n0 + j >= cout) break;
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias_vec) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
     else if (p.bias) bb = make_float4(__ldg(p.bias + n0 + j), __ldg(p.bias + n0 + j + 1), __ldg(p.bias + n0 + j + 2),
@@ -414,9 +419,16 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
       const int fo = r - tl * p.Fout;
       const int t = t0 + tl;
       if (tl >= p.Tbox || t >= p.T || b >= p.B) continue;
-      const long long opos = ((long long)b * p.T + t) * p.dstF + p.dst_f0 + (long long)fo * p.dst_fstep;
-      const long long orow = opos * (long long)p.Cout;
-      const int n0 = nb * BN + half * EPI_COLS;
+      int n0 = nb * BN + half * EPI_COLS;
+      int cout = p.Cout, cls = 0;
+      if (p.cls_cols) {                   // EPI_COLS divides cls_cols (host check): a thread's columns are of one class
+        cls = n0 >= p.cls_cols ? 1 : 0;
+        n0 -= cls * p.cls_cols;
+        cout = p.cls_cols;
+        if (cls && fo >= p.fout1) continue;
+      }
+      const long long opos = ((long long)b * p.T + t) * p.dstF + p.dst_f0 + cls + (long long)fo * p.dst_fstep;
+      const long long orow = opos * (long long)cout;
       if (p.glu) {
         const long long grow = opos * (long long)(p.Cout >> 1);
         if (p.act == SE_ACT_ELU) conv_tc_store_glu<EPI_COLS, SE_ACT_ELU>(p, sum, grow, n0);
@@ -424,13 +436,13 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
         continue;
       }
       switch (p.act) {   // uniform: one branch per tile, the activation itself is a template parameter
-        case SE_ACT_PRELU: conv_tc_store<EPI_COLS, SE_ACT_PRELU>(p, sum, orow, n0); break;
-        case SE_ACT_ELU: conv_tc_store<EPI_COLS, SE_ACT_ELU>(p, sum, orow, n0); break;
-        case SE_ACT_SOFTPLUS: conv_tc_store<EPI_COLS, SE_ACT_SOFTPLUS>(p, sum, orow, n0); break;
-        case SE_ACT_RELU: conv_tc_store<EPI_COLS, SE_ACT_RELU>(p, sum, orow, n0); break;
-        case SE_ACT_SIGMOID: conv_tc_store<EPI_COLS, SE_ACT_SIGMOID>(p, sum, orow, n0); break;
-        case SE_ACT_TANH: conv_tc_store<EPI_COLS, SE_ACT_TANH>(p, sum, orow, n0); break;
-        default: conv_tc_store<EPI_COLS, SE_ACT_NONE>(p, sum, orow, n0); break;
+        case SE_ACT_PRELU: conv_tc_store<EPI_COLS, SE_ACT_PRELU>(p, sum, orow, n0, cout); break;
+        case SE_ACT_ELU: conv_tc_store<EPI_COLS, SE_ACT_ELU>(p, sum, orow, n0, cout); break;
+        case SE_ACT_SOFTPLUS: conv_tc_store<EPI_COLS, SE_ACT_SOFTPLUS>(p, sum, orow, n0, cout); break;
+        case SE_ACT_RELU: conv_tc_store<EPI_COLS, SE_ACT_RELU>(p, sum, orow, n0, cout); break;
+        case SE_ACT_SIGMOID: conv_tc_store<EPI_COLS, SE_ACT_SIGMOID>(p, sum, orow, n0, cout); break;
+        case SE_ACT_TANH: conv_tc_store<EPI_COLS, SE_ACT_TANH>(p, sum, orow, n0, cout); break;
+        default: conv_tc_store<EPI_COLS, SE_ACT_NONE>(p, sum, orow, n0, cout); break;
       }
     }
   }
@@ -540,6 +552,7 @@ struct ConvTcArgs {
   float out_scale, out16_scale;
   int dstF, dst_f0, dst_fstep, glu;
   const float *glu_scale, *glu_shift;
+  int ncls, fout1;                 // ncls = 2: two parity classes of Cout / 2 channels (see ConvTcParams::cls_cols)
 };
 
 template <bool F16>
@@ -596,6 +609,15 @@ static int conv_tc_run(const ConvTcArgs* d, const char* what, cudaStream_t s) {
   // engine 1 (se_set_gemm_engine): CTA pairs where at least two activation tiles exist and the tile is >= 64 wide
   const bool pair = gemm_engine_is_pair() && d->Cout > 32 && (long long)d->B * ceil_div(d->T, p.Tbox) >= 2;
   const int BN = (pair && d->Cout > 128) ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : (d->Cout > 16 ? 32 : 16)));
+  if (d->ncls == 2) {
+    SE_REQUIRE(!d->glu && d->Cout % 8 == 0 && (d->Cout / 2) % (BN / 2) == 0 && d->fout1 >= 0 && d->fout1 <= d->Fout,
+               "%s (two parity classes): Cout=%d must be 2 x a multiple of %d, fout1=%d <= Fout=%d", what, d->Cout, BN / 2,
+               d->fout1, d->Fout);
+    p.cls_cols = d->Cout / 2;
+    p.fout1 = d->fout1;
+  } else {
+    SE_REQUIRE(d->ncls == 0 || d->ncls == 1, "%s: ncls=%d", what, d->ncls);
+  }
   CUtensorMap m[6];
   int rc;
   if ((rc = make_act_map(&m[0], d->src0_hi, d->B, d->T, d->Fin, d->C0, d->Fout, d->sf, p.Tbox, F16))) return rc;

@@ -426,10 +426,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_co
 //   * both CTAs: 8 epilogue warps drain their own TMEM (32 lanes x 128 columns each), promote chunk sums to fp32
 //     registers as above, and arrive REMOTELY on the leader's `tempty` barrier (count 16).
 constexpr int T2_BN = 256;
-constexpr int T2_EPI_COLS = T2_BN / 2;                     // 128 columns per epilogue warp
+constexpr int T2_EPI_COLS = T2_BN / 2;                     // 128 columns per epilogue warp (EW = 8)
+// EW = 16 epilogue warps (four per TMEM lane quarter, 64 columns each): an experiment for the fused LSTM cell on fp16 pairs,
+// where the MMA stream of a tile (12 k-blocks at twice the TF32 rate) is about as long as the cell epilogue of eight warps
+// (8192 cell updates, ten MUFU each, two warps per scheduler).  Measured on B200: slower (FullSubNet 118.7 vs 101.2 ms per
+// batch; 576 threads leave 96 registers per thread and the cell epilogue spills) -- not the default, SE_CELL_EPI_WARPS=16.
 constexpr int T2_TMEM_COLS = 512;                          // 2 accumulators x 256 columns: all of tensor memory
-template <int EPI, bool F16 = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int EPI, bool F16 = false, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
                         const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
                         const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
@@ -459,7 +463,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 2 * TC_EPI_WARPS);  // one arrive per epilogue warp of either CTA
+      mbar_init(&tempty[a], 2 * EW);  // one arrive per epilogue warp of either CTA
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_a0hi);
@@ -568,8 +572,9 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
     }
   } else {
     // ===================== epilogue (both CTAs): own TMEM rows -> registers -> global =====================
+    constexpr int ECOLS = T2_BN / (EW / 4);   // columns per epilogue warp: 128 (EW = 8) or 64 (EW = 16)
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;    // which 128 columns of the 256-column accumulator
+    const int half = (warp - 2) >> 2;    // which ECOLS columns of the 256-column accumulator
     int acc = 0;
     unsigned acc_phase = 0;
     const int nchunks = (kblocks + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
@@ -577,17 +582,17 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
       int mb, nb;
       tile_coords(tile, mb, nb);
       const int row = mb * 2 * TC_BM + (int)rank * TC_BM + quarter * 32 + lane;
-      float sum[T2_EPI_COLS];
+      float sum[ECOLS];
 #pragma unroll
-      for (int j = 0; j < T2_EPI_COLS; ++j) sum[j] = 0.f;
+      for (int j = 0; j < ECOLS; ++j) sum[j] = 0.f;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait_parity(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll
-        for (int piece = 0; piece < T2_EPI_COLS / 32; ++piece) {
+        for (int piece = 0; piece < ECOLS / 32; ++piece) {
           float v[32];
           const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) +
-                                 (unsigned)(acc * T2_BN + half * T2_EPI_COLS + piece * 32);
+                                 (unsigned)(acc * T2_BN + half * ECOLS + piece * 32);
           tmem_ld_32x32(taddr, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[piece * 32 + j] += v[j];
@@ -601,7 +606,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __gr
         }
       }
       if (row >= p.M) continue;
-      tc_epilogue_store<EPI, T2_EPI_COLS, F16>(p, sum, row, nb * T2_BN + half * T2_EPI_COLS);
+      tc_epilogue_store<EPI, ECOLS, F16>(p, sum, row, nb * T2_BN + half * ECOLS);
     }
   }
   tc_fence_before();
@@ -760,18 +765,18 @@ static int gemm_engine() {
 
 int se::gemm_engine_is_pair() { return gemm_engine() == 1; }     // conv_tc.cu follows the same switch
 
-template <int EPI, bool F16 = false>
+template <int EPI, bool F16 = false, int EW = 8>
 static int launch_pair_kernel(const CUtensorMap& a0hi, const CUtensorMap& a0lo, const CUtensorMap& a1hi,
                               const CUtensorMap& a1lo, const CUtensorMap& bhi, const CUtensorMap& blo, const TcParams& p,
                               int grid, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<EPI, F16, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) {
     set_error("tcgen05 pair gemm: smem attribute: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(64 + 32 * EW);
   cfg.dynamicSmemBytes = TC_SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -781,7 +786,7 @@ static int launch_pair_kernel(const CUtensorMap& a0hi, const CUtensorMap& a0lo, 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<EPI, F16>, a0hi, a0lo, a1hi, a1lo, bhi, blo, p);
+  e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<EPI, F16, EW>, a0hi, a0lo, a1hi, a1lo, bhi, blo, p);
   if (e != cudaSuccess) {
     set_error("tcgen05 pair gemm: cluster launch: %s", cudaGetErrorString(e));
     return SE_ERR_CUDA;
@@ -795,9 +800,15 @@ static int launch_tc_pair(int epi, const CUtensorMap& a0hi, const CUtensorMap& a
   const int mblocks = ceil_div(p.M, 2 * TC_BM), nblocks = ceil_div(p.N, T2_BN);
   p.panel_m = min(8, mblocks);                    // 8 x 256 rows: the same A panel as 16 x 128
   const int grid = 2 * min(sms / 2, mblocks * nblocks);
-  if (f16)
-    return epi == EPI_BIAS_ACT ? launch_pair_kernel<EPI_BIAS_ACT, true>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream)
-                               : launch_pair_kernel<EPI_LSTM_CELL, true>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
+  if (f16) {
+    static const bool wide = []() {            // SE_CELL_EPI_WARPS=16: measured SLOWER (FullSubNet 118.7 vs 101.2 ms per batch:
+      const char* e = getenv("SE_CELL_EPI_WARPS");   // 96 registers per thread with spills) -- kept for A/B runs only
+      return e && atoi(e) == 16;
+    }();
+    if (epi == EPI_BIAS_ACT) return launch_pair_kernel<EPI_BIAS_ACT, true>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
+    return wide ? launch_pair_kernel<EPI_LSTM_CELL, true, 16>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream)
+                : launch_pair_kernel<EPI_LSTM_CELL, true>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
+  }
   return epi == EPI_BIAS_ACT ? launch_pair_kernel<EPI_BIAS_ACT>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream)
                              : launch_pair_kernel<EPI_LSTM_CELL>(a0hi, a0lo, a1hi, a1lo, bhi, blo, p, grid, stream);
 }

@@ -101,6 +101,7 @@ struct se_plan {
   unsigned short *a1h16, *a1l16, *a2h16, *a2l16, *a3h16, *a3l16, *a4h16, *a4l16, *a5h16, *a5l16, *hs0h16, *hs0l16, *hs1h16,
       *hs1l16, *d0h16, *d0l16, *d1h16, *d1l16, *d2h16, *d2l16;
   ConvW dec_even[4], dec_odd[4];
+  ConvW dec_m[4];               // both parity classes as one weight matrix (conv_engine.merge_parity)
   DevBuf de4_w;
   float de4_b = 0.f;
   // arena
@@ -213,7 +214,8 @@ bool pack_lstm(se_plan* P, int l, const float* w_ih, const float* w_hh, const fl
 
 int launch_conv_f16(const unsigned short* s0h, const unsigned short* s0l, const unsigned short* s1h, const unsigned short* s1l,
                     int C0, int C1, int B, int T, int Fin, int Fout, const int (*taps)[2], int ntaps, int sf, const ConvW& w,
-                    float* out, unsigned short* oh, unsigned short* ol, int dstF, int f0, int fstep, cudaStream_t s) {
+                    float* out, unsigned short* oh, unsigned short* ol, int dstF, int f0, int fstep, cudaStream_t s,
+                    int ncls = 0, int fout1 = 0) {
   se_conv_f16_desc d;
   memset(&d, 0, sizeof(d));
   d.src0_hi = s0h;
@@ -246,6 +248,8 @@ int launch_conv_f16(const unsigned short* s0h, const unsigned short* s0l, const 
   d.dstF = dstF;
   d.dst_f0 = f0;
   d.dst_fstep = fstep;
+  d.ncls = ncls;
+  d.fout1 = fout1;
   return se_conv_f16x3(&d, s);
 }
 
@@ -337,10 +341,9 @@ int forward_f16(se_plan* P, const float* mag, float* est, int B, int T, cudaStre
     const int fo = 2 * fin + 1 + shift;
     const int c = kDecCi[i] / 2;
     float* of32 = i == 3 ? P->d3 : nullptr;
-    SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin + 1, kDecEven, 4, 1, P->dec_even[i], of32, dh[i], dl[i],
-                           fo, shift, 2, s));
-    SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin, kDecOdd, 2, 1, P->dec_odd[i], of32, dh[i], dl[i], fo,
-                           shift + 1, 2, s));
+    // both output-column parity classes in one launch (crn.py: conv_engine.conv_parity2)
+    SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin + 1, kDecEven, 4, 1, P->dec_m[i], of32, dh[i], dl[i], fo,
+                           shift, 2, s, 2, fin));
     if (shift) SE_TRY(se_fill_column(P->d3, rows, fo, kDecCo[i], 0, P->dec_even[i].fill.p, SE_ACT_ELU, 0.f, s));
     xh = dh[i];
     xl = dl[i];
@@ -496,7 +499,16 @@ extern "C" int se_plan_create_crn(const se_crn_weights* w, int B_max, int N_max,
           for (int k = 0; k < 2; ++k) d[((size_t)k * ci + q) * co + c] = W(q, c, od[k][0], od[k][1]);
         }
       for (int c = 0; c < co; ++c) bias[c] = w->de_b[i][c] * s[c] + o[c];
-      ok = make_convw(P, P->dec_even[i], e, 4 * ci, co, bias, 4, ci / 2, ci / 2) &&
+      // merged classes: K order of the even class, columns [even | odd]; odd tap 0 / 1 = even tap 0 / 2
+      std::vector<float> mg((size_t)4 * ci * 2 * co, 0.f);
+      for (int k = 0; k < 4; ++k)
+        for (int q = 0; q < ci; ++q)
+          for (int c = 0; c < co; ++c) {
+            mg[((size_t)k * ci + q) * 2 * co + c] = e[((size_t)k * ci + q) * co + c];
+            if (k == 0 || k == 2) mg[((size_t)k * ci + q) * 2 * co + co + c] = d[((size_t)(k / 2) * ci + q) * co + c];
+          }
+      ok = make_convw(P, P->dec_m[i], mg, 4 * ci, 2 * co, bias, 4, ci / 2, ci / 2) &&
+           make_convw(P, P->dec_even[i], e, 4 * ci, co, bias, 4, ci / 2, ci / 2) &&
            make_convw(P, P->dec_odd[i], d, 2 * ci, co, bias, 2, ci / 2, ci / 2) &&
            upload(P, P->dec_even[i].fill, o);
     } else {

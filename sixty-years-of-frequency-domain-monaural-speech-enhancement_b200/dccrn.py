@@ -213,6 +213,7 @@ class DCCRN(nn.Module):
                         out += [a0, a1]
                 return ConvWeights(torch.cat(out, dim=0) * s[None, :], 2 * co2)
             P[f"dec{i}"] = (parity((0, 2, 4)), parity((1, 3)), bias, slope)
+            P[f"dec{i}_m"] = conv_engine.merge_parity(P[f"dec{i}"][0], DEC_EVEN, P[f"dec{i}"][1], DEC_ODD)
         self._packed = P
 
     def _ensure_packed(self):
@@ -297,10 +298,15 @@ class DCCRN(nn.Module):
                                       want_pair=is_tc and nxt_tc, f16=f16)
             ev = [(dt + dt_shift, df) for dt, df in DEC_EVEN]
             od = [(dt + dt_shift, df) for dt, df in DEC_ODD]
-            conv_engine.conv(h, skip, b, t, fin, fin, ev, 1, we, bias, act, out, fo, dst_f0=0, dst_fstep=2,
-                             act_param=slope)
-            conv_engine.conv(h, skip, b, t, fin, fin, od, 1, wo, bias, act, out, fo, dst_f0=1, dst_fstep=2,
-                             act_param=slope)
+            wm = P[f"dec{i}_m"]
+            if f16 and is_tc and conv_engine.parity2_eligible(h, skip, wm, fin):
+                # both output-column parity classes in one launch (the odd class's taps are among the even class's)
+                conv_engine.conv_parity2(h, skip, b, t, fin, fin, fin, ev, wm, bias, act, out, fo, act_param=slope)
+            else:
+                conv_engine.conv(h, skip, b, t, fin, fin, ev, 1, we, bias, act, out, fo, dst_f0=0, dst_fstep=2,
+                                 act_param=slope)
+                conv_engine.conv(h, skip, b, t, fin, fin, od, 1, wo, bias, act, out, fo, dst_f0=1, dst_fstep=2,
+                                 act_param=slope)
             h, fin = out, fo
             if taps is not None:
                 taps[f"dec{i}"] = f32_of(h)

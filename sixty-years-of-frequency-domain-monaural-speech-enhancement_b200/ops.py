@@ -574,10 +574,12 @@ def conv_tf32x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, bias, Cout, a
 
 def conv_f16x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, w_scale_log2, bias, Cout, act, dstF, dst_f0=0,
                dst_fstep=1, act_param=0.0, out=None, out_pair=None, out_pair16=None, glu=None,
-               a_scale_log2=F16_ACT_SCALE_LOG2, out16_scale_log2=F16_ACT_SCALE_LOG2):
+               a_scale_log2=F16_ACT_SCALE_LOG2, out16_scale_log2=F16_ACT_SCALE_LOG2, fout1=None):
     """conv_tf32x3 on fp16 operand pairs (se_conv_f16x3).  src0 / src1: (hi, lo) fp16 tuples of channels-last
     [B,T,Fin,C] scaled by 2^a_scale_log2; w_hi / w_lo fp16 [Cout, ntaps*(pad64(C0)+pad64(C1))] scaled by 2^w_scale_log2
-    (packing.pack_conv_f16).  Outputs as requested: fp32, TF32 pair, fp16 pair (scaled by 2^out16_scale_log2)."""
+    (packing.pack_conv_f16).  Outputs as requested: fp32, TF32 pair, fp16 pair (scaled by 2^out16_scale_log2).
+    fout1 is not None: two output-column parity classes in one launch (se_conv_f16_desc.ncls = 2): Cout counts the
+    GEMM columns of both classes, the outputs have Cout / 2 channels."""
     device_check()
     d = ConvF16Desc()
     assert src0[0].dtype == torch.float16 and w_hi.dtype == torch.float16
@@ -607,6 +609,7 @@ def conv_f16x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, w_scale_log2, 
     d.glu = 0 if glu is None else 1
     d.glu_scale = glu[0].data_ptr() if glu is not None and glu[0] is not None else 0
     d.glu_shift = glu[1].data_ptr() if glu is not None and glu[1] is not None else 0
+    d.ncls, d.fout1 = (2, fout1) if fout1 is not None else (0, 0)
     with _Timed(f"conv_f16x3[K={len(taps) * (c0 + c1)},N={Cout}]"):
         check(_lib.load().se_conv_f16x3(C.byref(d), _stream()), "se_conv_f16x3")
 

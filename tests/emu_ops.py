@@ -306,9 +306,17 @@ def fsn_sb_assemble_f16(mag_tm, fb, nn, inv, scale_log2=F16_ACT_SCALE_LOG2):
 
 def conv_f16x3(src0, src1, B, T, Fin, Fout, taps, sf, w_hi, w_lo, w_scale_log2, bias, Cout, act, dstF, dst_f0=0,
                dst_fstep=1, act_param=0.0, out=None, out_pair=None, out_pair16=None, glu=None,
-               a_scale_log2=F16_ACT_SCALE_LOG2, out16_scale_log2=F16_ACT_SCALE_LOG2):
+               a_scale_log2=F16_ACT_SCALE_LOG2, out16_scale_log2=F16_ACT_SCALE_LOG2, fout1=None):
     from se_b200 import packing
     assert glu is None
+    if fout1 is not None:        # two parity classes in one launch: columns [class 0 | class 1], class 1 one column further
+        co = Cout // 2
+        for cls, fo in ((0, Fout), (1, fout1)):
+            if fo > 0:
+                conv_f16x3(src0, src1, B, T, Fin, fo, taps, sf, w_hi[cls * co:(cls + 1) * co].contiguous(),
+                           w_lo[cls * co:(cls + 1) * co].contiguous(), w_scale_log2, bias, co, act, dstF, dst_f0 + cls,
+                           dst_fstep, act_param, out, out_pair, out_pair16, None, a_scale_log2, out16_scale_log2)
+        return
     x0 = _from16(src0, a_scale_log2)
     x1 = _from16(src1, a_scale_log2) if src1 is not None else None
     c0 = x0.shape[-1]

@@ -948,3 +948,45 @@ def test_conv_f16x3_matches_semantics(case, engine):
     err_16 = ((g16_hi.double() + g16_lo.double()).cpu() / 16.0 - ref).abs().max().item()
     print(f"conv_f16x3 engine {engine} {case}: max err {err:.3e} (TF32 pair {err_pair:.3e}, fp16 pair {err_16:.3e})")
     assert err < 2e-5 and err_pair < 2e-5 and err_16 < 2e-5
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("case", [(2, 33, 4, 256, 256, 128, "crn"), (1, 17, 19, 64, 64, 32, "crn"), (2, 9, 39, 32, 32, 16, "crn"),
+                                  (2, 13, 4, 256, 256, 256, "dccrn"), (1, 7, 64, 64, 64, 32, "dccrn")])
+def test_conv_f16x3_two_parity_classes_in_one_launch(case, engine):
+    """se_conv_f16x3 with ncls = 2 (both output-column parity classes of a stride-2 transposed conv in one launch, the odd
+    class's taps a subset of the even class's) vs the declared semantics of the two classes in fp64."""
+    dev = _dev()
+    import se_b200
+    from se_b200 import conv_engine, packing
+    from se_b200.conv_engine import Act, ConvWeights
+    from se_b200.dccrn import DEC_EVEN, DEC_ODD
+    ops = se_b200.ops
+    b, t, fin, c0, c1, co, kind = case
+    g = torch.Generator().manual_seed(abs(hash(case)) % 1000)
+    x0 = torch.randn(b, t, fin, c0, generator=g)
+    x1 = torch.randn(b, t, fin, c1, generator=g)
+    bias = torch.randn(co, generator=g)
+    ev, od = (packing.DECONV_EVEN_TAPS, packing.DECONV_ODD_TAPS) if kind == "crn" else (DEC_EVEN, DEC_ODD)
+    fe, fo_, dstF = (fin + 1, fin, 2 * fin + 1) if kind == "crn" else (fin, fin, 2 * fin)
+    ct = c0 + c1
+    we = torch.randn(len(ev) * ct, co, generator=g) / np.sqrt(len(ev) * ct)
+    wo = torch.randn(len(od) * ct, co, generator=g) / np.sqrt(len(od) * ct)
+    ref = torch.zeros(b, t, dstF, co, dtype=torch.float64)
+    emu_ops.conv_gemm(x0.double(), x1.double(), b, t, fin, fe, ev, 1, we.double(), bias.double(), co, "elu", ref, dstF, 0, 2)
+    emu_ops.conv_gemm(x0.double(), x1.double(), b, t, fin, fo_, od, 1, wo.double(), bias.double(), co, "elu", ref, dstF, 1, 2)
+    wm = conv_engine.merge_parity(ConvWeights(we.to(dev), co), ev, ConvWeights(wo.to(dev), co), od)
+    src, skip = Act(x0.to(dev)), Act(x1.to(dev))
+    out = conv_engine.new_act(b, t, dstF, co, dev, want_f32=True, want_pair=True, f16=True)
+    out.f32.zero_()
+    assert conv_engine.parity2_eligible(src, skip, wm, fe)
+    try:
+        ops.set_gemm_engine(engine)
+        conv_engine.conv_parity2(src, skip, b, t, fin, fe, fo_, ev, wm, bias.to(dev), "elu", out, dstF)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_engine(DEFAULT_GEMM_ENGINE)
+    err = (out.f32.cpu().double() - ref).abs().max().item()
+    err16 = ((out.pair[0].double() + out.pair[1].double()).cpu() / 16.0 - ref).abs().max().item()
+    print(f"conv_f16x3 ncls=2 engine {engine} {case}: max err {err:.3e} (fp16 pair {err16:.3e})")
+    assert err < 2e-5 and err16 < 2e-5
