@@ -137,13 +137,16 @@ def merge_parity(w_even: ConvWeights, taps_even, w_odd: ConvWeights, taps_odd):
 
 
 def parity2_eligible(src: Act, skip, w_merged: ConvWeights, fout_even, sf=1):
-    """One-launch parity pair: fp16-pair tensor-core layers whose class width fits the epilogue's column groups."""
+    """One-launch parity pair: fp16-pair tensor-core layers whose class width fits the epilogue's column groups and is at
+    most 64 channels -- wider layers are tensor-bound and the zero taps of the odd class cost more than the second read of
+    the activation saves (measured on B200, CRN de1 with 128 channels: 0.38 ms merged vs 0.35 ms as two launches; de2-de4
+    with 64 / 32 / 16 channels: 0.66 vs 0.77 ms)."""
     c0 = src.shape[-1]
     c1 = skip.shape[-1] if skip is not None else 0
     co2 = w_merged.cout
     bn = 128 if co2 > 64 else (64 if co2 > 32 else (32 if co2 > 16 else 16))
     return (src.is_f16 or src.pair is None) and tc_eligible(c0, c1, co2, fout_even, sf, True) and \
-        co2 % 8 == 0 and (co2 // 2) % (bn // 2) == 0
+        co2 % 8 == 0 and (co2 // 2) % (bn // 2) == 0 and co2 // 2 <= 64
 
 
 def conv_parity2(src: Act, skip, B, T, Fin, fout_even, fout_odd, taps_even, w_merged: ConvWeights, bias, act, dst: Act,

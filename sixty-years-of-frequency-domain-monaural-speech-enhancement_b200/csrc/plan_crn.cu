@@ -341,9 +341,15 @@ int forward_f16(se_plan* P, const float* mag, float* est, int B, int T, cudaStre
     const int fo = 2 * fin + 1 + shift;
     const int c = kDecCi[i] / 2;
     float* of32 = i == 3 ? P->d3 : nullptr;
-    // both output-column parity classes in one launch (crn.py: conv_engine.conv_parity2)
-    SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin + 1, kDecEven, 4, 1, P->dec_m[i], of32, dh[i], dl[i], fo,
-                           shift, 2, s, 2, fin));
+    if (kDecCo[i] <= 64) {   // both output-column parity classes in one launch (conv_engine.parity2_eligible / conv_parity2)
+      SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin + 1, kDecEven, 4, 1, P->dec_m[i], of32, dh[i], dl[i],
+                             fo, shift, 2, s, 2, fin));
+    } else {                 // tensor-bound layer: the zero taps of the merged odd class would cost more than the re-read
+      SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin + 1, kDecEven, 4, 1, P->dec_even[i], of32, dh[i],
+                             dl[i], fo, shift, 2, s));
+      SE_TRY(launch_conv_f16(xh, xl, skh[i], skl[i], c, c, B, T, fin, fin, kDecOdd, 2, 1, P->dec_odd[i], of32, dh[i], dl[i], fo,
+                             shift + 1, 2, s));
+    }
     if (shift) SE_TRY(se_fill_column(P->d3, rows, fo, kDecCo[i], 0, P->dec_even[i].fill.p, SE_ACT_ELU, 0.f, s));
     xh = dh[i];
     xl = dl[i];

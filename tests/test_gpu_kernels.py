@@ -979,7 +979,7 @@ def test_conv_f16x3_two_parity_classes_in_one_launch(case, engine):
     src, skip = Act(x0.to(dev)), Act(x1.to(dev))
     out = conv_engine.new_act(b, t, dstF, co, dev, want_f32=True, want_pair=True, f16=True)
     out.f32.zero_()
-    assert conv_engine.parity2_eligible(src, skip, wm, fe)
+    assert conv_engine.parity2_eligible(src, skip, wm, fe) == (co <= 64)     # the models merge narrow layers only
     try:
         ops.set_gemm_engine(engine)
         conv_engine.conv_parity2(src, skip, b, t, fin, fe, fo_, ev, wm, bias.to(dev), "elu", out, dstF)
