@@ -110,8 +110,13 @@ def test_conv_in1_and_deconv_out1():
     ref2 = emu_ops.deconv_out1(s0.double(), s1.double(), w2.double(), 0.3, "softplus")
     got2 = ops.deconv_out1(s0.to(dev), s1.to(dev), w2.to(dev), 0.3, "softplus")
     e2 = (got2.cpu().double() - ref2).abs().max().item()
-    print(f"conv_in1 {e1:.3e} deconv_out1 {e2:.3e}")
-    assert e1 < 1e-5 and e2 < 1e-5
+    s2 = torch.randn(2, 7, 39, 64, generator=g)                 # one source, 64 channels, T not a multiple of the row tile
+    w3 = torch.randn(6, 64, generator=g) * 0.2
+    ref3 = emu_ops.deconv_out1(s2.double(), None, w3.double(), -0.1, "none")
+    got3 = ops.deconv_out1(s2.to(dev), None, w3.to(dev), -0.1, "none")
+    e3 = (got3.cpu().double() - ref3).abs().max().item()
+    print(f"conv_in1 {e1:.3e} deconv_out1 {e2:.3e} {e3:.3e}")
+    assert e1 < 1e-5 and e2 < 1e-5 and e3 < 1e-5
 
 
 @pytest.mark.parametrize("b,t,h", [(1, 6, 1024), (5, 9, 1024), (64, 12, 1024), (70, 5, 1024), (3, 7, 256)])
