@@ -51,6 +51,17 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
 }
 
+// ELU for the tensor-core epilogues: expm1f (about 30 instructions with two branches) was the largest single item of the
+// conv epilogue, and the epilogue -- eight warps, two per scheduler, dependent ALU chains -- is what bounds the small-
+// channel conv layers (profiles/ncu_conv_f16_r02p_*: 70 instructions per output element, issue slots 33 % busy, tensor
+// pipe 17-49 %).  ex2.approx - 1 has an ABSOLUTE error of ~1e-7 (fp32 rounding of a value near 1); next to zero, where
+// that would be a large relative error, the second-order series is exact to 1.6e-10.
+__device__ __forceinline__ float fast_elu(float x) {
+  const float e = __expf(x) - 1.0f;
+  const float s = fmaf(0.5f * x, x, x);
+  return x > 0.0f ? x : (x > -9.765625e-4f ? s : e);
+}
+
 // ---- packed fp32x2 FMA (Blackwell FFMA2) -----------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(SE_NO_FFMA2)

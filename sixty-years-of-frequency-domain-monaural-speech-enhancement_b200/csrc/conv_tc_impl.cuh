@@ -124,13 +124,27 @@ __device__ __forceinline__ void tmem_ld_cols<8>(unsigned taddr, float (&v)[8]) {
 template <int NC, int ACT>
 __device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float (&sum)[NC], long long orow, int n0, int cout) {
   const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  // the bias loads of 32 columns in one batch (one exposed latency instead of eight: two epilogue warps per scheduler
+  // cannot hide a load per four columns -- the FFMAs behind these loads were the top stall sites of the kernel)
+  constexpr int G = NC < 32 ? NC : 32;
 #pragma unroll
-  for (int j = 0; j < NC; j += 4) {
-    if (n0 + j >= cout) break;
+  for (int g0 = 0; g0 < NC; g0 += G) {
+  float4 bias4[G / 4];
+#pragma unroll
+  for (int j = 0; j < G; j += 4) {
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias_vec) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-    else if (p.bias) bb = make_float4(__ldg(p.bias + n0 + j), __ldg(p.bias + n0 + j + 1), __ldg(p.bias + n0 + j + 2),
-                                      __ldg(p.bias + n0 + j + 3));
+    if (n0 + g0 + j < cout) {
+      if (bias_vec) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g0 + j));
+      else if (p.bias) bb = make_float4(__ldg(p.bias + n0 + g0 + j), __ldg(p.bias + n0 + g0 + j + 1),
+                                        __ldg(p.bias + n0 + g0 + j + 2), __ldg(p.bias + n0 + g0 + j + 3));
+    }
+    bias4[j / 4] = bb;
+  }
+#pragma unroll
+  for (int jj = 0; jj < G; jj += 4) {
+    const int j = g0 + jj;
+    if (n0 + j >= cout) break;
+    const float4 bb = bias4[jj / 4];
     const float os = p.out_scale;   // 1.0f on the TF32 path: fmaf(s, 1, b) == s + b
     const float o[4] = {tc_act<ACT>(fmaf(sum[j], os, bb.x), p.act_param), tc_act<ACT>(fmaf(sum[j + 1], os, bb.y), p.act_param),
                         tc_act<ACT>(fmaf(sum[j + 2], os, bb.z), p.act_param), tc_act<ACT>(fmaf(sum[j + 3], os, bb.w), p.act_param)};
@@ -149,6 +163,7 @@ __device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float
       *reinterpret_cast<uint2*>(p.out16_hi + orow + n0 + j) = make_uint2(hi[0] | ((unsigned)hi[1] << 16), hi[2] | ((unsigned)hi[3] << 16));
       *reinterpret_cast<uint2*>(p.out16_lo + orow + n0 + j) = make_uint2(lo[0] | ((unsigned)lo[1] << 16), lo[2] | ((unsigned)lo[3] << 16));
     }
+  }
   }
 }
 

@@ -263,7 +263,7 @@ __device__ __forceinline__ void split_tf32_dev(float x, float& hi, float& lo) {
 template <int ACT>
 __device__ __forceinline__ float tc_act(float x, float param) {
   if constexpr (ACT == SE_ACT_PRELU) return x >= 0.0f ? x : param * x;
-  else if constexpr (ACT == SE_ACT_ELU) return elu_f(x);
+  else if constexpr (ACT == SE_ACT_ELU) return fast_elu(x);
   else if constexpr (ACT == SE_ACT_SOFTPLUS) return softplus_f(x);
   else if constexpr (ACT == SE_ACT_RELU) return fmaxf(x, 0.0f);
   else if constexpr (ACT == SE_ACT_SIGMOID) return sigmoid_f(x);
