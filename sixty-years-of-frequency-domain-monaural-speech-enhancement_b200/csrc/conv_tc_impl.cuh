@@ -185,7 +185,7 @@ __device__ __forceinline__ void conv_tc_store_glu(const ConvTcParams& p, const f
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float a = fmaf(sum[j + 2 * e], p.out_scale, bb[2 * e]), g = fmaf(sum[j + 2 * e + 1], p.out_scale, bb[2 * e + 1]);
-        float v = a * sigmoid_f(g);
+        float v = a * fast_sigmoid(g);     // ex2.approx + fast divide (|error| ~ 2e-7), as in the fused LSTM cell epilogue
         v = v * (p.glu_scale ? __ldg(p.glu_scale + co + e) : 1.f) + (p.glu_shift ? __ldg(p.glu_shift + co + e) : 0.f);
         o[e] = tc_act<ACT>(v, p.act_param);
       }

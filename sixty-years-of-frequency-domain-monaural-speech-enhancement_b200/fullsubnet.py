@@ -70,7 +70,16 @@ class Model(nn.Module):
                                                  sd[f"{pre}.bias_ih_l{l}"], sd[f"{pre}.bias_hh_l{l}"])
             P[f"sb{l}_f16"] = packing.pack_lstm_cell_f16(sd[f"{pre}.weight_ih_l{l}"], sd[f"{pre}.weight_hh_l{l}"],
                                                          sd[f"{pre}.bias_ih_l{l}"], sd[f"{pre}.bias_hh_l{l}"])
+        if self.fb_hidden == 512:
+            # H = 512 as the first block of a block-diagonal H = 1024 recurrence: the tcgen05 cluster kernel (lstm_f16.cu)
+            # exists for H = 1024 only, and its 5.4 us per step beat the 8.9 us of the fp32 slice kernel at H = 512 even with
+            # half of the units idle (their xproj columns and weights are zero: gates 0.5 / 0, c = h = 0)
+            for l in range(2):
+                bd = torch.zeros(128, 1024, 32, device=dev)
+                bd[:64, :512] = P[f"fb{l}"]["whh"]
+                P[f"fb{l}_bd"] = bd.contiguous()
         w = sd["fb_model.fc_output_layer.weight"].contiguous()
+        P["fb_fc16"] = packing.pack_linear_f16(w)
         P["fb_fc_hi"], P["fb_fc_lo"] = packing.split_tf32(w)
         P["fb_fc_kn"] = packing.pad_cols(w.t().contiguous())
         P["fb_fc_b"] = sd["fb_model.fc_output_layer.bias"].contiguous()
@@ -114,10 +123,21 @@ class Model(nn.Module):
         inv_fb = ops.fsn_clip_inv_mean(x, strides, b, t, f, denom=float(f * tp))
         mag_tm, xn = ops.fsn_fb_input(x, strides, b, t, tp, f, inv_fb)
         seq = xn.view(b * tp, f)
+        f16 = lstm_engine.USE_TENSOR_CORES and lstm_engine.USE_F16_PAIRS and b * tp >= 128
         for l in range(2):
-            hs = lstm_engine.lstm_layer(seq, P[f"fb{l}"], b, tp)
-            seq = hs.view(b * tp, self.fb_hidden)
-        if lstm_engine.USE_TENSOR_CORES and seq.shape[0] >= 128:
+            if f16 and f"fb{l}_bd" in P and b <= 64:
+                lay = P[f"fb{l}"]
+                xp = torch.zeros(b * tp, 4096, device=dev, dtype=torch.float32)          # columns of the idle units stay 0
+                ops.gemm_f16x3(ops.split_f16(seq), (lay["wih16_hi"], lay["wih16_lo"]), lay["wih16_scale"], lay["bias"], 2048,
+                               out=xp[:, :2048])
+                hs = ops.lstm_seq(xp.view(b, tp, 4096), P[f"fb{l}_bd"], 1024)
+                seq = hs.view(b * tp, 1024)[:, :512]                                       # strided view, no copy
+            else:
+                hs = lstm_engine.lstm_layer(seq, P[f"fb{l}"], b, tp)
+                seq = hs.view(b * tp, self.fb_hidden)
+        if f16:
+            fb_out = ops.gemm_f16x3(ops.split_f16(seq), P["fb_fc16"][:2], P["fb_fc16"][2], P["fb_fc_b"], f, act="relu")
+        elif lstm_engine.USE_TENSOR_CORES and seq.shape[0] >= 128:
             a_hi, a_lo = ops.split_tf32(seq)
             fb_out = ops.gemm_tf32x3(a_hi, a_lo, P["fb_fc_hi"], P["fb_fc_lo"], P["fb_fc_b"], f, act="relu")
         else:

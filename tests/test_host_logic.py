@@ -101,6 +101,17 @@ def test_fullsubnet_host_logic_matches_oracle(monkeypatch):
         yr = nets.fullsubnet_forward(sd, x)
     assert y.shape == yr.shape == (2, 2, 257, 7)
     assert (y - yr).abs().max() < 2e-4 * max(1.0, yr.abs().max().item())
+    # >= 128 rows: the fp16-pair plan -- full-band H = 512 layers as the first block of a block-diagonal H = 1024 recurrence
+    # (idle units: zero xproj columns and weights), fp16-pair projections / output layer / sub-band cells
+    seen = []
+    orig = se_b200.ops.lstm_seq
+    monkeypatch.setattr(se_b200.ops, "lstm_seq", lambda xp, whh, hidden, out=None: (seen.append(hidden), orig(xp, whh, hidden, out))[1])
+    x = torch.rand(2, 1, 257, 70, generator=torch.Generator().manual_seed(2)) * 3
+    y = m._forward_impl(x)
+    with torch.no_grad():
+        yr = nets.fullsubnet_forward(sd, x)
+    assert seen == [1024, 1024]
+    assert (y - yr).abs().max() < 2e-4 * max(1.0, yr.abs().max().item())
 
 
 def test_shard_range_partitions():
