@@ -4,6 +4,7 @@
 //   se_istft      (a7..a9)  recombination prologue + irFFT + window + OLA + envelope + 1/c
 // Both transforms are HBM-bound: every audio sample and spectrum bin is touched once
 // (halo frames of neighbouring CTAs hit L2).  See DESIGN.md for the byte accounting.
+#include <mutex>
 #include <float.h>
 #include <stdlib.h>
 
@@ -830,6 +831,9 @@ __device__ float2 g_twiddles8[32 * WarpFFT<8>::kTwPerLane];
 static const float2* dsp_twiddles(int R, cudaStream_t s) {
   constexpr int kMaxDev = 64;
   static bool ready[kMaxDev][2] = {};
+  static std::mutex mu;                       // first calls from several host threads / streams of one device
+  std::lock_guard<std::mutex> guard(mu);
+  (void)s;
   int dev = 0;
   cudaGetDevice(&dev);
   const int which = R == 5 ? 0 : 1;
@@ -845,8 +849,10 @@ static const float2* dsp_twiddles(int R, cudaStream_t s) {
       WarpFFT<8>::fill_table(host);
       bytes = sizeof(float2) * 32 * WarpFFT<8>::kTwPerLane;
     }
-    // pageable source: the copy is staged before the call returns; ordered before the launch that follows on `s`
-    if (cudaMemcpyAsync(sym, host, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return nullptr;
+    // SYNCHRONOUS copy: complete when it returns, so a launch on ANY stream that follows sees the table (an async copy on
+    // the caller's stream let a first STFT on another stream read zeros).  Not legal inside a stream capture: the first
+    // call per device must be made outside one (decode.GraphedEnhance / se_enhance_crn warm up before they capture).
+    if (cudaMemcpy(sym, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
     if (dev >= 0 && dev < kMaxDev) ready[dev][which] = true;
   }
   return reinterpret_cast<const float2*>(sym);
