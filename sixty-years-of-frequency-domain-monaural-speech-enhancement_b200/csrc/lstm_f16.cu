@@ -704,8 +704,9 @@ int lstm_f16_supported() {
 // 600 .. 1500 cycles, 5.91 at 1900.  The gain is small because the wait is not the polling scheme: all eight items of a
 // producer validate ~3.3 K cycles after the consumer's own publish whatever the delay -- that is the skew of the slowest
 // of the 32 producers plus the store -> L2 -> load visibility latency across the two dies, i.e. every step is a chip-wide
-// all-to-all and its latency, not the protocol around it, is the floor of this kernel.
-constexpr int kDefaultPollDelay = 1000;
+// all-to-all and its latency, not the protocol around it, is the floor of this kernel.  WITHOUT the stamps the timed poll
+// is slower than the canary (bench step: 2.229 vs 2.135 ms per launch at a delay of 1000): the canary stays the default.
+constexpr int kDefaultPollDelay = 0;
 
 static long long* g_lf_prof = nullptr;
 static int g_lf_prof_t0 = 0, g_lf_prof_n = 0;
