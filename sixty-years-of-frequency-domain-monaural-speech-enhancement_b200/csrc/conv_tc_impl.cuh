@@ -31,7 +31,10 @@ struct CtCfg {
   static constexpr int B_BYTES = B_ROWS * CT_BK * 4;
   static constexpr int B_SLOT = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = 2 * CT_A_BYTES + 2 * B_SLOT;
-  static constexpr int STAGES = STAGE_BYTES >= 64 * 1024 ? 3 : 4;     // 227 KB smem limit
+  // Measured and dropped: TWO CTAs per SM for the narrow tiles (BN <= 64: 16 epilogue warps, two stages each) -- no gain
+  // at BN = 16 / 32 (0.204 / 0.193 vs 0.201 / 0.192 ms), slower at BN = 64 (96 registers per thread: 0.180 vs 0.162 ms).
+  static constexpr int CTAS_PER_SM = 1;
+  static constexpr int STAGES = CTAS_PER_SM == 2 ? 2 : (STAGE_BYTES >= 64 * 1024 ? 3 : 4);     // 227 KB smem limit
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
 };
 constexpr int CT_THREADS = 320;
@@ -209,7 +212,7 @@ __device__ __forceinline__ void conv_tc_store_glu(const ConvTcParams& p, const f
 }
 
 template <int BN, int PAIR, bool F16>
-__global__ void __launch_bounds__(CT_THREADS, 1)
+__global__ void __launch_bounds__(CT_THREADS, CtCfg<BN, PAIR>::CTAS_PER_SM)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a0hi, const __grid_constant__ CUtensorMap map_a0lo,
                    const __grid_constant__ CUtensorMap map_a1hi, const __grid_constant__ CUtensorMap map_a1lo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
@@ -546,7 +549,7 @@ static int launch_conv_tc(const CUtensorMap* m, const ConvTcParams& p, int sms, 
     }
   } else {
     const int tiles = mtiles * ceil_div(p.Cout, BN);
-    conv_tf32x3_kernel<BN, PAIR, F16><<<min(sms, tiles), CT_THREADS, SMEM, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
+    conv_tf32x3_kernel<BN, PAIR, F16><<<min(sms * CtCfg<BN, PAIR>::CTAS_PER_SM, tiles), CT_THREADS, SMEM, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], p);
   }
   return SE_OK;
 }

@@ -73,8 +73,6 @@ struct LfParams {
   long long hs_sb, hs_st;
   unsigned* hw;      // [2 parities][128 groups of 8 units][64 batch rows][8]: (hi << 16) | lo, tag in bit 0
   int a_swap;        // debug: swap the two fp16 of a TMEM column of the A operand
-  int poll_delay;    // > 0: timed full poll (cycles after this thread's own publish before the first load of h_{t-1});
-                     // 0: canary poll (spin on the first item, then fetch the other seven)
   long long* prof;   // optional phase timestamps, see LF_NEV
   int prof_t0, prof_n;
 };
@@ -501,7 +499,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
     // loader items: ONE producer per thread (group lg of the K slice = 16-byte piece lg & 7 of chunk lg >> 3), batch rows
     // lb0 + 8 i -- a producer publishes its 2 KB within ~100 cycles, so once the first item validates the rest does too
     const int lg = tid >> 3, lb0 = tid & 7, lchunk = lg >> 3, lc16 = lg & 7;
-    long long tpub = clock64();
     for (int t = 0; t < p.T; ++t) {
       float xg[2][4];
 #pragma unroll
@@ -520,27 +517,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
         const unsigned* src = p.hw + ((size_t)(((t - 1) & 1) * LF_CTAS + (int)q * 32 + lg) * LF_NB + lb0) * 8;
         if (tid == 0) LF_STAMP(0);
         uint4 v[8][2];
-        unsigned pending = 0xFFu;       // items not yet validated (timed poll)
-        if (p.poll_delay > 0) {
-          // timed full poll: wait out the visibility latency, then load all eight items at once and re-load only the
-          // ones whose tags do not match yet
-          while (clock64() - tpub < (long long)p.poll_delay) {
-          }
-          unsigned it = 0;
-          while (pending) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (pending & (1u << i)) {
-                v[i][0] = lf_ld_state(src + i * 64);
-                v[i][1] = lf_ld_state(src + i * 64 + 4);
-              }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((pending & (1u << i)) && lf_tags_ok(v[i][0], v[i][1], etag)) pending &= ~(1u << i);
-            if (pending && ((++it) & 0x3Fu) == 0 && lf_timer_ns() - t0 > LF_SPIN_NS) __trap();
-          }
-          if (tid == 0) LF_STAMP(1);
-        } else {
         {   // canary: spin on the first item only, so that early arrivals do not flood L2 with 64 KB re-reads
           unsigned it = 0;
           for (;;) {
@@ -556,10 +532,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
           v[i][0] = lf_ld_state(src + i * 64);
           v[i][1] = lf_ld_state(src + i * 64 + 4);
         }
-        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (i > 0 && pending) {       // canary scheme: items 1..7 are checked (and re-read) here
+          if (i > 0) {
             unsigned it = 0;
             while (!lf_tags_ok(v[i][0], v[i][1], etag)) {
               v[i][0] = lf_ld_state(src + i * 64);
@@ -636,7 +611,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_seq_f16_kernel(const LfPar
         }
         hv2[i] = h;
       }
-      tpub = clock64();
       if (tid == 0) LF_STAMP(8);
       // the sequence output is not on the step's critical path: store it after the state
 #pragma unroll
@@ -695,19 +669,6 @@ int lstm_f16_supported() {
   return cached;
 }
 
-// Cycles a loader thread waits after its OWN publish of h_t before its first (full, eight-item) poll of h_t from the
-// producer it reads: every CTA publishes at about the same time (the step is a data-dependent lockstep), a store needs
-// > 1 K cycles to become visible to an L2 load from another SM, and a poll issued earlier only comes back invalid.
-// With the canary scheme (0) a thread learned that its producer was ready from ONE item and only then fetched the other
-// seven: a second, serial L2 round trip in the chain of every step.  SE_LSTM_POLL_DELAY overrides (A/B; 0 = canary).
-// Measured (profiles/lstm_f16_phases_poll_r02.json, stamps on): 5.87 us per step with the canary, 5.70-5.77 with delays of
-// 600 .. 1500 cycles, 5.91 at 1900.  The gain is small because the wait is not the polling scheme: all eight items of a
-// producer validate ~3.3 K cycles after the consumer's own publish whatever the delay -- that is the skew of the slowest
-// of the 32 producers plus the store -> L2 -> load visibility latency across the two dies, i.e. every step is a chip-wide
-// all-to-all and its latency, not the protocol around it, is the floor of this kernel.  WITHOUT the stamps the timed poll
-// is slower than the canary (bench step: 2.229 vs 2.135 ms per launch at a delay of 1000): the canary stays the default.
-constexpr int kDefaultPollDelay = 0;
-
 static long long* g_lf_prof = nullptr;
 static int g_lf_prof_t0 = 0, g_lf_prof_n = 0;
 void lstm_f16_set_profile(long long* dev_buf, int first_step, int nsteps) {
@@ -734,13 +695,8 @@ int lstm_seq_f16_launch(const float* xproj, long long xp_stride, const float* wh
     a_swap = 0;
     if (const char* ev = getenv("SE_LSTM_F16_ASWAP")) a_swap = atoi(ev) ? 1 : 0;
   }
-  static int poll_delay = -1;
-  if (poll_delay < 0) {
-    poll_delay = kDefaultPollDelay;
-    if (const char* ev = getenv("SE_LSTM_POLL_DELAY")) poll_delay = atoi(ev) < 0 ? 0 : atoi(ev);
-  }
   LfParams p{xproj, xp_stride, whh, B, T, hseq, hs_sb, hs_st, reinterpret_cast<unsigned*>(work), a_swap,
-             poll_delay, g_lf_prof, g_lf_prof_t0, g_lf_prof_n};
+             g_lf_prof, g_lf_prof_t0, g_lf_prof_n};
   // The cooperative attribute guarantees co-residency of the 128 CTAs.  Tools that replay launches (Nsight Compute)
   // reject a cooperative CLUSTER launch: retry once without it -- the bounded spins turn a co-residency failure into a
   // launch error instead of a hang.  SE_LSTM_TC_COOP=0 skips the first attempt.
