@@ -11,6 +11,8 @@ rate, half the bytes); a model opts into the latter per activation (``new_act(..
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import lstm_engine, ops, packing
@@ -66,12 +68,25 @@ class ConvWeights:
         self.cout = cout
         self._f16 = {}
 
-    def f16(self, ntaps, c0, c1):
-        """(hi, lo, scale_log2) fp16 pair in the se_conv_f16x3 layout, packed on first use."""
-        key = (ntaps, c0, c1)
+    def f16(self, ntaps, c0, c1, c0p=None, c1p=None):
+        """(hi, lo, scale_log2) fp16 pair in the se_conv_f16x3 layout, packed on first use.  c0p / c1p: channel counts the
+        ACTIVATIONS are zero-padded to (multiples of 8) when the layer's own are not -- zero weight rows for the padding."""
+        c0p, c1p = c0p or c0, c1p or c1
+        key = (ntaps, c0, c1, c0p, c1p)
         if key not in self._f16:
-            self._f16[key] = packing.pack_conv_f16(self.kn[:, :self.cout].t().contiguous(), ntaps, c0, c1)
+            w = self.kn[:, :self.cout]
+            if (c0p, c1p) != (c0, c1):
+                src = w.view(ntaps, c0 + c1, self.cout)
+                wp = w.new_zeros(ntaps, c0p + c1p, self.cout)
+                wp[:, :c0] = src[:, :c0]
+                if c1:
+                    wp[:, c0p:c0p + c1] = src[:, c0:]
+                w = wp.view(ntaps * (c0p + c1p), self.cout)
+            self._f16[key] = packing.pack_conv_f16(w.t().contiguous(), ntaps, c0p, c1p)
         return self._f16[key]
+
+
+SMALL_CIN_ON_F16 = os.environ.get("SE_F16_SMALL_CIN", "1") != "0"      # A/B switch for the rule in conv() below
 
 
 def tc_eligible(c0, c1, cout, fout, sf, f16=False):
@@ -101,6 +116,28 @@ def conv(src: Act, skip, B, T, Fin, Fout, taps, sf, w: ConvWeights, bias, act, d
         return
     if glu is not None and not tc_eligible(c0, c1, w.cout, Fout, sf):
         raise RuntimeError("the fused gate needs a tensor-core eligible layer")
+    # Layers the TF32 tensor path cannot take (channel counts that are not multiples of 32: the 2-channel RI inputs of the
+    # U2-Net / DCCRN / Uformer encoders, 8 / 16-channel levels) ran on the fp32 FMA implicit GEMM, which is store-bound at
+    # wide outputs (TaylorSENet en1, K = 20, N = 128: 2.7 ms per launch).  On fp16 pairs a k-block is zero-filled past the
+    # last channel, so they run on the tensor cores after a split of the fp32 activation (channels padded to 8).
+    c0p, c1p = (c0 + 7) // 8 * 8, (c1 + 7) // 8 * 8
+    if (SMALL_CIN_ON_F16 and lstm_engine.USE_F16_PAIRS and glu is None and not tc_eligible(c0, c1, w.cout, Fout, sf)
+            and src.f32 is not None and (skip is None or skip.f32 is not None) and w.cout >= 16
+            and tc_eligible(c0p, c1p, w.cout, Fout, sf, True) and not dst.is_f16):
+        def pair16(a, c, cp):
+            x = a.f32
+            hi, lo = ops.split_f16(x.reshape(-1, c), kpad=cp)
+            return hi.view(*x.shape[:-1], cp), lo.view(*x.shape[:-1], cp)
+        w_hi, w_lo, ws = w.f16(len(taps), c0, c1, c0p, c1p)
+        ops.conv_f16x3(pair16(src, c0, c0p), pair16(skip, c1, c1p) if skip is not None else None, B, T, Fin, Fout, taps, sf,
+                       w_hi, w_lo, ws, bias, w.cout, act, dstF, dst_f0, dst_fstep, act_param=act_param, out=dst.f32,
+                       out_pair=dst.pair)
+        if fill_f >= 0:
+            if dst.f32 is not None:
+                ops.fill_column(dst.f32, fill, fill_f, act, act_param)
+            if dst.pair is not None:
+                raise NotImplementedError("fill column on a split-only output")
+        return
     if tc_eligible(c0, c1, w.cout, Fout, sf):
         ops.conv_tf32x3(src.get_pair(), skip.get_pair() if skip is not None else None, B, T, Fin, Fout, taps, sf,
                         w.hi, w.lo, bias, w.cout, act, dstF, dst_f0, dst_fstep, act_param=act_param, out=dst.f32,

@@ -80,7 +80,9 @@ def main():
             times.append(e0.elapsed_time(e1))
         ms = min(times)
         share = {k: round(v[1] / sum(x[1] for x in per_op.values()), 3)
-                 for k, v in sorted(per_op.items(), key=lambda kv: -kv[1][1])[:8]}
+                 for k, v in sorted(per_op.items(), key=lambda kv: -kv[1][1])[:(64 if "--all-ops" in sys.argv else 8)]}
+        if "--all-ops" in sys.argv:      # launches per op as well
+            share = {k: [v, per_op[k][0]] for k, v in share.items()}
         rec = {"model": name, "batch": bsz, "clip_s": secs, "frames_per_clip": frames, "ms_per_batch": ms,
                "frames_per_s": bsz * frames / (ms * 1e-3), "rtf": ms * 1e-3 / (bsz * secs), "op_time_share": share,
                "weights": "seeded synthetic"}
