@@ -119,10 +119,13 @@ def conv(src: Act, skip, B, T, Fin, Fout, taps, sf, w: ConvWeights, bias, act, d
     # Layers the TF32 tensor path cannot take (channel counts that are not multiples of 32: the 2-channel RI inputs of the
     # U2-Net / DCCRN / Uformer encoders, 8 / 16-channel levels) ran on the fp32 FMA implicit GEMM, which is store-bound at
     # wide outputs (TaylorSENet en1, K = 20, N = 128: 2.7 ms per launch).  On fp16 pairs a k-block is zero-filled past the
-    # last channel, so they run on the tensor cores after a split of the fp32 activation (channels padded to 8).
+    # last channel, so they run on the tensor cores after a split of the fp32 activation (channels padded to 8) -- where the
+    # output is WIDE (>= 64 channels): TaylorSENet +4 %, CTSNet +7 %, G2Net +1 %.  Narrow outputs stay on the FMA kernel: with
+    # 16 / 32 output channels the ten 16-byte-row TMA boxes per tile cost more than the FMA kernel's stores (measured: DCCRN
+    # enc0 0.93 ms, Uformer's first level 2.4 ms on the tensor path vs < 0.65 ms on the FMA path; DCCRN / Uformer / DPCRN -3 %).
     c0p, c1p = (c0 + 7) // 8 * 8, (c1 + 7) // 8 * 8
     if (SMALL_CIN_ON_F16 and lstm_engine.USE_F16_PAIRS and glu is None and not tc_eligible(c0, c1, w.cout, Fout, sf)
-            and src.f32 is not None and (skip is None or skip.f32 is not None) and w.cout >= 16
+            and src.f32 is not None and (skip is None or skip.f32 is not None) and w.cout >= 64
             and tc_eligible(c0p, c1p, w.cout, Fout, sf, True) and not dst.is_f16):
         def pair16(a, c, cp):
             x = a.f32
