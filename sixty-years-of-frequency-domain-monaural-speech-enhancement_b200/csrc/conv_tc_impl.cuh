@@ -130,6 +130,11 @@ __device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float
   // the bias loads of 32 columns in one batch (one exposed latency instead of eight: two epilogue warps per scheduler
   // cannot hide a load per four columns -- the FFMAs behind these loads were the top stall sites of the kernel)
   constexpr int G = NC < 32 ? NC : 32;
+  // rows of cout floats: 32-byte aligned pieces when cout % 8 == 0 and the bases are (every epilogue span starts at a
+  // multiple of 8 columns)
+  const bool v8 = (cout & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.out_hi) |
+                                       reinterpret_cast<uintptr_t>(p.out_lo)) & 31) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(p.out16_hi) | reinterpret_cast<uintptr_t>(p.out16_lo)) & 15) == 0;
 #pragma unroll
   for (int g0 = 0; g0 < NC; g0 += G) {
   float4 bias4[G / 4];
@@ -142,6 +147,35 @@ __device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float
                                         __ldg(p.bias + n0 + g0 + j + 2), __ldg(p.bias + n0 + g0 + j + 3));
     }
     bias4[j / 4] = bb;
+  }
+  if (v8) {   // eight columns per step: 32-byte fp32 stores (whole sectors), 16-byte fp16 stores
+#pragma unroll
+    for (int jj = 0; jj < G; jj += 8) {
+      const int j = g0 + jj;
+      if (n0 + j >= cout) break;
+      const float4 b0 = bias4[jj / 4], b1 = bias4[jj / 4 + 1];
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float os = p.out_scale;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = tc_act<ACT>(fmaf(sum[j + e], os, bb[e]), p.act_param);
+      if (p.out) st_global_v8(p.out + orow + n0 + j, o);
+      if (p.out_hi) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+        st_global_v8(p.out_hi + orow + n0 + j, hi);
+        st_global_v8(p.out_lo + orow + n0 + j, lo);
+      }
+      if (p.out16_hi) {
+        unsigned short hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_f16_dev(o[e], p.out16_scale, hi[e], lo[e]);
+        st_global_h8(p.out16_hi + orow + n0 + j, hi);
+        st_global_h8(p.out16_lo + orow + n0 + j, lo);
+      }
+    }
+    continue;
   }
 #pragma unroll
   for (int jj = 0; jj < G; jj += 4) {

@@ -88,6 +88,44 @@ __device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float
   const float* res = p.res ? p.res + roff : nullptr;
   if (vec && n0 + NC <= p.N && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
     // whole span in range, 16-byte aligned rows: float4 traffic only, no per-element checks
+    const bool v8 = (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(p.c_hi) |
+                                         reinterpret_cast<uintptr_t>(p.c_lo) | reinterpret_cast<uintptr_t>(bias)) & 31) == 0;
+    if (v8) {   // 32-byte rows: eight columns per step, whole-sector stores (st_global_v8)
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (bias) {
+          b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j));
+          b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j + 4));
+        }
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float os = p.out_scale;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = tc_act<ACT>(fmaf(sum[j + e], os, bb[e]), p.act_param) * p.alpha;
+        if (res) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + n0 + j));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(res + n0 + j + 4));
+          o[0] += r0.x, o[1] += r0.y, o[2] += r0.z, o[3] += r0.w, o[4] += r1.x, o[5] += r1.y, o[6] += r1.z, o[7] += r1.w;
+        }
+        if (p.C) st_global_v8(p.C + roff + n0 + j, o);
+        if (p.c_hi) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+          st_global_v8(p.c_hi + roff + n0 + j, hi);
+          st_global_v8(p.c_lo + roff + n0 + j, lo);
+        }
+        if (p.c16_hi) {
+          unsigned short hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_f16_dev(o[e], p.c16_scale, hi[e], lo[e]);
+          st_global_h8(p.c16_hi + roff + n0 + j, hi);
+          st_global_h8(p.c16_lo + roff + n0 + j, lo);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
       const float4 bb = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);

@@ -250,6 +250,18 @@ __device__ __forceinline__ void split_f16_dev(float x, float scale, unsigned sho
   lo = l;
 }
 
+// 256-bit global store (sm_100: STG.256): a thread of the tensor-core epilogues owns ONE output row, so a store instruction
+// of a warp touches 32 different rows -- with 16-byte pieces every 32-byte sector is written half, with 32-byte pieces whole.
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_global_h8(unsigned short* p, const unsigned short (&h)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16),
+                                            h[4] | ((unsigned)h[5] << 16), h[6] | ((unsigned)h[7] << 16));
+}
+
 __device__ __forceinline__ void split_tf32_dev(float x, float& hi, float& lo) {
   unsigned hb, lb;
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hb) : "f"(x));
