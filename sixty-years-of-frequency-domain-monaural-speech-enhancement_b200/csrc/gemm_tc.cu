@@ -195,6 +195,46 @@ __device__ __forceinline__ void tc_epilogue_store(const TcParams& p, const float
       const long long off = (long long)row * p.H + unit0;
       const long long hoff = (long long)row * p.ld_hout + unit0;
       const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nq);   // 16-byte aligned (checked on the host)
+      const bool v8 = (p.ld_hout & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.c_state) | reinterpret_cast<uintptr_t>(p.h_out) |
+                                                 (F16 ? 0 : (reinterpret_cast<uintptr_t>(p.h_hi) | reinterpret_cast<uintptr_t>(p.h_lo)))) & 31) == 0;
+      if (v8) {   // eight units per step: 32-byte state loads / stores (whole sectors), 16-byte fp16 pairs
+#pragma unroll
+        for (int u = 0; u < 16; u += 8) {
+          float co[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (!p.first_step) ld_global_v8(p.c_state + off + u, co);
+          float vb[4][8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b0 = __ldg(bias4 + 4 * g + (u >> 2)), b1 = __ldg(bias4 + 4 * g + (u >> 2) + 1);
+            vb[g][0] = b0.x, vb[g][1] = b0.y, vb[g][2] = b0.z, vb[g][3] = b0.w;
+            vb[g][4] = b1.x, vb[g][5] = b1.y, vb[g][6] = b1.z, vb[g][7] = b1.w;
+          }
+          float cn[8], hn[8], hh[8], hl[8];
+          unsigned short h16[8], l16[8];
+          const float os = p.out_scale;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float ig = fast_sigmoid(fmaf(sum[q * 64 + u + e], os, vb[0][e]));
+            const float fg = fast_sigmoid(fmaf(sum[q * 64 + 16 + u + e], os, vb[1][e]));
+            const float gg = fast_tanh(fmaf(sum[q * 64 + 32 + u + e], os, vb[2][e]));
+            const float og = fast_sigmoid(fmaf(sum[q * 64 + 48 + u + e], os, vb[3][e]));
+            cn[e] = fg * co[e] + ig * gg;
+            hn[e] = og * fast_tanh(cn[e]);
+            if constexpr (F16) split_f16_dev(hn[e], p.c16_scale, h16[e], l16[e]);
+            else split_tf32_dev(hn[e], hh[e], hl[e]);
+          }
+          st_global_v8(p.c_state + off + u, cn);
+          if constexpr (F16) {
+            st_global_h8(reinterpret_cast<unsigned short*>(p.h_hi) + hoff + u, h16);
+            st_global_h8(reinterpret_cast<unsigned short*>(p.h_lo) + hoff + u, l16);
+          } else {
+            st_global_v8(p.h_hi + hoff + u, hh);
+            st_global_v8(p.h_lo + hoff + u, hl);
+          }
+          if (p.h_out) st_global_v8(p.h_out + hoff + u, hn);
+        }
+        continue;
+      }
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
         const float4 cold = p.first_step ? make_float4(0.f, 0.f, 0.f, 0.f)
