@@ -208,6 +208,44 @@ __device__ __forceinline__ void conv_tc_store(const ConvTcParams& p, const float
 // `orow` is the row offset in the OUTPUT tensor (Cout / 2 channels).
 template <int NC, int ACT>
 __device__ __forceinline__ void conv_tc_store_glu(const ConvTcParams& p, const float (&sum)[NC], long long orow, int n0) {
+  if constexpr (NC >= 16) {
+    // 16 columns = 8 output channels per step: 32-byte stores (whole sectors) where the rows allow it
+    const bool v8 = (p.Cout & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.out_hi) |
+                                            reinterpret_cast<uintptr_t>(p.out_lo)) & 31) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(p.out16_hi) | reinterpret_cast<uintptr_t>(p.out16_lo)) & 15) == 0;
+    if (v8) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 16) {
+        if (n0 + j >= p.Cout) break;
+        const int co = (n0 + j) >> 1;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float ba = p.bias ? __ldg(p.bias + n0 + j + 2 * e) : 0.f, bg = p.bias ? __ldg(p.bias + n0 + j + 2 * e + 1) : 0.f;
+          const float a = fmaf(sum[j + 2 * e], p.out_scale, ba), g = fmaf(sum[j + 2 * e + 1], p.out_scale, bg);
+          float v = a * fast_sigmoid(g);
+          v = v * (p.glu_scale ? __ldg(p.glu_scale + co + e) : 1.f) + (p.glu_shift ? __ldg(p.glu_shift + co + e) : 0.f);
+          o[e] = tc_act<ACT>(v, p.act_param);
+        }
+        if (p.out) st_global_v8(p.out + orow + co, o);
+        if (p.out_hi) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_tf32_dev(o[e], hi[e], lo[e]);
+          st_global_v8(p.out_hi + orow + co, hi);
+          st_global_v8(p.out_lo + orow + co, lo);
+        }
+        if (p.out16_hi) {
+          unsigned short hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_f16_dev(o[e], p.out16_scale, hi[e], lo[e]);
+          st_global_h8(p.out16_hi + orow + co, hi);
+          st_global_h8(p.out16_lo + orow + co, lo);
+        }
+      }
+      return;
+    }
+  }
   if constexpr (NC >= 8) {
 #pragma unroll
     for (int j = 0; j < NC; j += 8) {

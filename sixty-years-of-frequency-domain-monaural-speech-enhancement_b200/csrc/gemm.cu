@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(256) deconv_out1_rows_kernel(const float* __re
   const int b = blockIdx.x / tiles_t;
   const int t = (blockIdx.x - b * tiles_t) * R + r;
   const bool live = r < R && t < T;
+  const bool wide = (C0 & 7) == 0 && (C1 & 7) == 0 && ((reinterpret_cast<uintptr_t>(src0) | reinterpret_cast<uintptr_t>(src1)) & 31) == 0;
   __syncthreads();
   float a[3] = {0.f, 0.f, 0.f};
   if (live) {
@@ -357,26 +358,43 @@ __global__ void __launch_bounds__(256) deconv_out1_rows_kernel(const float* __re
       if (t - kt < 0) continue;
       const long long pos = ((long long)b * T + (t - kt)) * Fin + f;
       const float4* w4 = reinterpret_cast<const float4*>(wsm + kt * 3 * CT);
-      const float4* p0 = reinterpret_cast<const float4*>(src0 + pos * C0);
-#pragma unroll 4
-      for (int c = 0; c < C0 / 4; ++c) {
-        const float4 v = __ldg(p0 + c);
+      // a thread reads its own contiguous channel vector: 32-byte loads (whole sectors) where the vectors are 32-byte multiples
+      auto dot8 = [&](const float* src, int cbase) {
+        float v[8];
+        asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(src));
 #pragma unroll
         for (int kf = 0; kf < 3; ++kf) {
-          const float4 w = w4[kf * (CT / 4) + c];
+          const float4 w0 = w4[kf * (CT / 4) + cbase], w1 = w4[kf * (CT / 4) + cbase + 1];
+          a[kf] = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, a[kf]))));
+          a[kf] = fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, a[kf]))));
+        }
+      };
+      auto dot4 = [&](const float* src, int cbase) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+#pragma unroll
+        for (int kf = 0; kf < 3; ++kf) {
+          const float4 w = w4[kf * (CT / 4) + cbase];
           a[kf] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, a[kf]))));
         }
+      };
+      const float* p0 = src0 + pos * C0;
+      if (wide) {
+#pragma unroll 2
+        for (int c = 0; c < C0 / 8; ++c) dot8(p0 + 8 * c, 2 * c);
+      } else {
+#pragma unroll 4
+        for (int c = 0; c < C0 / 4; ++c) dot4(p0 + 4 * c, c);
       }
       if (C1 > 0) {
-        const float4* p1 = reinterpret_cast<const float4*>(src1 + pos * C1);
+        const float* p1 = src1 + pos * C1;
+        if (wide) {
+#pragma unroll 2
+          for (int c = 0; c < C1 / 8; ++c) dot8(p1 + 8 * c, C0 / 4 + 2 * c);
+        } else {
 #pragma unroll 4
-        for (int c = 0; c < C1 / 4; ++c) {
-          const float4 v = __ldg(p1 + c);
-#pragma unroll
-          for (int kf = 0; kf < 3; ++kf) {
-            const float4 w = w4[kf * (CT / 4) + C0 / 4 + c];
-            a[kf] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, a[kf]))));
-          }
+          for (int c = 0; c < C1 / 4; ++c) dot4(p1 + 4 * c, C0 / 4 + c);
         }
       }
     }

@@ -89,7 +89,8 @@ __device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float
   if (vec && n0 + NC <= p.N && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
     // whole span in range, 16-byte aligned rows: float4 traffic only, no per-element checks
     const bool v8 = (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(p.c_hi) |
-                                         reinterpret_cast<uintptr_t>(p.c_lo) | reinterpret_cast<uintptr_t>(bias)) & 31) == 0;
+                                         reinterpret_cast<uintptr_t>(p.c_lo) | reinterpret_cast<uintptr_t>(bias) |
+                                         reinterpret_cast<uintptr_t>(p.res)) & 31) == 0;
     if (v8) {   // 32-byte rows: eight columns per step, whole-sector stores (st_global_v8)
 #pragma unroll
       for (int j = 0; j < NC; j += 8) {
@@ -104,9 +105,10 @@ __device__ __forceinline__ void tc_store_bias_act(const TcParams& p, const float
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = tc_act<ACT>(fmaf(sum[j + e], os, bb[e]), p.act_param) * p.alpha;
         if (res) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + n0 + j));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(res + n0 + j + 4));
-          o[0] += r0.x, o[1] += r0.y, o[2] += r0.z, o[3] += r0.w, o[4] += r1.x, o[5] += r1.y, o[6] += r1.z, o[7] += r1.w;
+          float r[8];
+          ldg_v8(res + n0 + j, r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += r[e];
         }
         if (p.C) st_global_v8(p.C + roff + n0 + j, o);
         if (p.c_hi) {

@@ -263,6 +263,11 @@ __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
                : "l"(p)
                : "memory");
 }
+__device__ __forceinline__ void ldg_v8(const float* p, float (&v)[8]) {      // read-only data (residuals, activations)
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void st_global_h8(unsigned short* p, const unsigned short (&h)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16),
                                             h[4] | ((unsigned)h[5] << 16), h[6] | ((unsigned)h[7] << 16));
