@@ -362,6 +362,11 @@ class Runner:
         torch.cuda.empty_cache()
 
 
+def se_f16_pairs():
+    import se_b200
+    return bool(se_b200.lstm_engine.USE_F16_PAIRS and se_b200.lstm_engine.USE_TENSOR_CORES)
+
+
 def step_roofline(cfg, frames_step, ms_step, peaks, peak_src):
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     tf = cfg["flops_frame"] * frames_step / (ms_step * 1e-3) / 1e12
@@ -620,7 +625,12 @@ def main():
                        "parallelism": (f"dp{world} (utterance shards; gather of the enhanced clips to rank 0 on a side "
                                        "stream behind the next step)") if world > 1 else "single GPU",
                        "l2": f"inputs rotate over {nsets} batches ({nsets * per_rank * n_samples * 4 / 1e6:.0f} MB > 126 MB L2); "
-                             "per-step activations stream through L2"},
+                             "per-step activations stream through L2",
+                       "arithmetic": ("fp32 results; dense contractions as three tensor-core products of fp16 hi/lo operand "
+                                      "pairs (tcgen05 kind::f16, fp32 accumulation in tensor memory): the 22-bit products of "
+                                      "3xTF32, within the 1e-4 RMS gate (a single half / TF32 pass is not)")
+                                     if se_f16_pairs() else
+                                     "fp32 results; dense contractions as 3xTF32 on tcgen05 (SE_F16_PAIRS=0)"},
             "rtf": (ms_step * 1e-3) / (per_rank * world * cfg["seconds"]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s",
