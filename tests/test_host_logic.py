@@ -561,3 +561,56 @@ def test_fft_thread_algebra_on_cpu(m, tmp_path):
     assert np.abs(spec[:, 0] + 1j * spec[:, 1] - ref).max() < 2e-5
     assert abs(spec[0, 1]) < 1e-5 and abs(spec[m, 1]) < 1e-5
     assert np.abs(back - x).max() < 1e-6
+
+
+def test_split_f16_pair_precision_range_and_saturation():
+    """packing.split_f16 (the host twin of split_f16_dev / split_f16_kernel): x * 2^s = hi + lo to 22 significand bits
+    wherever |x * 2^s| >= 2^-3, an absolute floor of 2^-25 / 2^s below, saturation (not inf) beyond the fp16 range, and
+    the per-tensor scale that puts max|w| in [2^13, 2^14)."""
+    from se_b200 import packing
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.randn(4096, generator=g) * 3, torch.tensor([900.0, -1e-5, 3e-7, 0.0, 4093.0])])
+    hi, lo, s = packing.split_f16(x, 4)
+    assert s == 4 and hi.dtype == torch.float16 and lo.dtype == torch.float16
+    back = (hi.double() + lo.double()) / 16.0
+    err = (back - x.double()).abs()
+    assert bool((err <= 2.0 ** -21 * x.double().abs() + 2.0 ** -29).all())
+    hs, ls, _ = packing.split_f16(torch.tensor([1e6, -1e6]), 4)              # beyond +-4094: saturates, stays finite
+    assert torch.isfinite(hs.float()).all() and torch.isfinite(ls.float()).all() and float(hs[0]) == 65504.0
+    w = torch.randn(64, 96, generator=g) * 0.07
+    wh, wl, ws = packing.split_f16(w)
+    m = float(w.abs().max()) * 2.0 ** ws
+    assert 2.0 ** 13 <= m < 2.0 ** 14
+    assert ((wh.double() + wl.double()) * 2.0 ** -ws - w.double()).abs().max() < 2.0 ** -21 * float(w.abs().max())
+    z = packing.split_f16(torch.zeros(8, 8))
+    assert z[2] == 0 and float(z[0].abs().max()) == 0.0
+
+
+def test_pack_conv_f16_pads_every_tap_and_source_block_to_64_channels():
+    """The se_conv_f16x3 weight layout: K order (tap, [source 0 | source 1]); every block zero-padded to a multiple of 64
+    channels; ConvWeights.f16 with activation channels padded to 8 (2-channel inputs) puts zero rows on the padding."""
+    from se_b200 import packing
+    from se_b200.conv_engine import ConvWeights, merge_parity
+    g = torch.Generator().manual_seed(1)
+    ntaps, c0, c1, co = 3, 96, 40, 16
+    w = torch.randn(co, ntaps * (c0 + c1), generator=g)
+    hi, lo, s = packing.pack_conv_f16(w, ntaps, c0, c1)
+    p0, p1 = 128, 64
+    assert hi.shape == (co, ntaps * (p0 + p1))
+    full = ((hi.double() + lo.double()) * 2.0 ** -s).view(co, ntaps, p0 + p1)
+    src = w.double().view(co, ntaps, c0 + c1)
+    assert (full[:, :, :c0] - src[:, :, :c0]).abs().max() < 1e-6 and (full[:, :, p0:p0 + c1] - src[:, :, c0:]).abs().max() < 1e-6
+    assert float(full[:, :, c0:p0].abs().max()) == 0.0 and float(full[:, :, p0 + c1:].abs().max()) == 0.0
+    # 2 input channels carried in an 8-channel activation
+    kn = torch.randn(10 * 2, 128, generator=g)
+    cw = ConvWeights(kn, 128)
+    h2, l2, s2 = cw.f16(10, 2, 0, 8, 0)
+    f2 = ((h2.double() + l2.double()) * 2.0 ** -s2).view(128, 10, 64)
+    assert (f2[:, :, :2] - kn.double().t().reshape(128, 10, 2)).abs().max() < 1e-6 and float(f2[:, :, 2:].abs().max()) == 0.0
+    # both parity classes as one matrix: odd taps are a subset of the even taps, zero rows elsewhere
+    ev, od = [(0, 0), (0, -1), (-1, 0), (-1, -1)], [(0, 0), (-1, 0)]
+    we, wo = ConvWeights(torch.randn(4 * 8, 4, generator=g), 4), ConvWeights(torch.randn(2 * 8, 4, generator=g), 4)
+    m = merge_parity(we, ev, wo, od)
+    assert m.cout == 8 and torch.equal(m.kn[:, :4], we.kn[:, :4])
+    assert torch.equal(m.kn[0:8, 4:8], wo.kn[0:8, :4]) and torch.equal(m.kn[16:24, 4:8], wo.kn[8:16, :4])
+    assert float(m.kn[8:16, 4:8].abs().max()) == 0.0 and float(m.kn[24:32, 4:8].abs().max()) == 0.0
